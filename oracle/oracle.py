@@ -1,0 +1,253 @@
+"""ctypes binding of the CPU oracle (oracle/plstvo_oracle.c).
+
+TEST INFRASTRUCTURE: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs import this module.  The product package (stvo_pl_b200) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+
+from stvo_pl_b200 import types as T
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = [os.path.join(_HERE, "plstvo_oracle.c"), os.path.join(_HERE, "plstvo_oracle.h"),
+        os.path.join(_HERE, "..", "include", "plstvo.h")]
+
+
+def _build(out: str, march: str) -> None:
+    """Same flags as oracle/Makefile (= the reference's CMakeLists.txt:18 flags)."""
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = ["gcc", "-O3", f"-march={march}", f"-mtune={'native' if march == 'native' else 'generic'}",
+           "-std=gnu11", "-fPIC", "-ffp-contract=off", "-shared", "-o", out, _SRC[0], "-lm", "-lpthread"]
+    subprocess.run(cmd, check=True, capture_output=True)
+
+
+def _stale(lib: str) -> bool:
+    return (not os.path.exists(lib)) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in _SRC)
+
+
+def lib_path(native: bool = False) -> str:
+    """Portable build (x86-64-v3: AVX2 + POPCNT) travels with the repo; the native build used for the CPU
+    baseline is compiled on the machine that times it (-march=native, the reference's own flag)."""
+    if not native:
+        lib = os.path.join(_HERE, "libplstvo_oracle.so")
+        if _stale(lib):
+            _build(lib, "x86-64-v3")
+        return lib
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = next((l for l in f if l.startswith("flags")), "")
+    except OSError:
+        flags = ""
+    tag = hashlib.sha1(flags.encode()).hexdigest()[:10]
+    lib = os.path.join(_HERE, "_native", tag, "libplstvo_oracle.so")
+    if _stale(lib):
+        _build(lib, "native")
+    return lib
+
+
+class Oracle:
+    def __init__(self, native: bool = False):
+        self.lib = L = C.CDLL(lib_path(native))
+        u8p, i32p, dp = T.c_uint8_p, T.c_int32_p, T.c_double_p
+        L.orc_distance.restype = C.c_int
+        L.orc_distance.argtypes = [u8p, u8p]
+        L.orc_match_nnr.restype = C.c_int
+        L.orc_match_nnr.argtypes = [u8p, C.c_int, u8p, C.c_int, C.c_float, i32p]
+        L.orc_match.restype = C.c_int
+        L.orc_match.argtypes = [u8p, C.c_int, u8p, C.c_int, C.c_float, C.c_int, C.c_int, i32p]
+        L.orc_knn2.restype = None
+        L.orc_knn2.argtypes = [u8p, C.c_int, u8p, C.c_int, i32p, i32p]
+        for name, n_in, n_out in [("orc_inverse_se3", 16, 16), ("orc_expmap_se3", 6, 16),
+                                  ("orc_logmap_se3", 16, 6), ("orc_adjoint_se3", 16, 36),
+                                  ("orc_inv6", 36, 36), ("orc_eig6_sym", 36, 6)]:
+            getattr(L, name).restype = None
+            getattr(L, name).argtypes = [dp, dp]
+        L.orc_unccomp_se3.restype = None
+        L.orc_unccomp_se3.argtypes = [dp, dp, dp, dp]
+        L.orc_is_finite.restype = C.c_int
+        L.orc_is_finite.argtypes = [dp, C.c_int]
+        L.orc_vector_mean_stdv_mad.restype = None
+        L.orc_vector_mean_stdv_mad.argtypes = [dp, C.c_int, dp, dp]
+        L.orc_vector_stdv_mad.restype = C.c_double
+        L.orc_vector_stdv_mad.argtypes = [dp, C.c_int]
+        L.orc_robust_weight_cauchy.restype = C.c_double
+        L.orc_robust_weight_cauchy.argtypes = [C.c_double]
+        L.orc_line_segment_overlap.restype = C.c_double
+        L.orc_line_segment_overlap.argtypes = [dp, dp, dp, dp]
+        L.orc_projection.restype = None
+        L.orc_projection.argtypes = [C.POINTER(T.PlCamera), dp, dp]
+        L.orc_back_projection.restype = None
+        L.orc_back_projection.argtypes = [C.POINTER(T.PlCamera), C.c_double, C.c_double, C.c_double, dp]
+        L.orc_qr6_solve.restype = C.c_int
+        L.orc_qr6_solve.argtypes = [dp, dp, dp, dp]
+        L.orc_optimize_functions.restype = None
+        L.orc_optimize_functions.argtypes = [C.POINTER(T.PlCamera), C.POINTER(T.PlConfig),
+                                             C.POINTER(T.PlMatchedBatch), C.c_int, dp, C.c_int, dp, dp, dp]
+        L.orc_optimize_pose.restype = C.c_int
+        L.orc_optimize_pose.argtypes = [C.POINTER(T.PlCamera), C.POINTER(T.PlConfig),
+                                        C.POINTER(T.PlMatchedBatch), C.c_void_p, C.c_void_p, u8p, u8p]
+        L.orc_f2f_tracking.restype = C.c_int
+        L.orc_f2f_tracking.argtypes = [C.POINTER(T.PlConfig), C.POINTER(T.PlFrameBatch),
+                                       C.POINTER(T.PlFrameBatch), i32p, i32p, i32p]
+        L.orc_track_batch.restype = C.c_int
+        L.orc_track_batch.argtypes = [C.POINTER(T.PlCamera), C.POINTER(T.PlConfig), C.POINTER(T.PlFrameBatch),
+                                      C.POINTER(T.PlFrameBatch), C.c_void_p, C.c_void_p, i32p, i32p, u8p, u8p,
+                                      C.c_int, C.c_int, dp]
+
+    # ---- helpers ----
+    @staticmethod
+    def _d(a):
+        return np.ascontiguousarray(a, dtype=np.float64)
+
+    @staticmethod
+    def _dp(a):
+        return a.ctypes.data_as(T.c_double_p)
+
+    def _unary(self, name, x, n_out):
+        x = self._d(x).ravel()
+        out = np.zeros(n_out)
+        getattr(self.lib, name)(self._dp(x), self._dp(out))
+        return out
+
+    # ---- matching ----
+    def distance(self, a, b) -> int:
+        a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
+        return self.lib.orc_distance(a.ctypes.data_as(T.c_uint8_p), b.ctypes.data_as(T.c_uint8_p))
+
+    def knn2(self, d1, d2):
+        d1, d2 = np.ascontiguousarray(d1, np.uint8), np.ascontiguousarray(d2, np.uint8)
+        idx = np.full((len(d1), 2), -1, np.int32)
+        dist = np.full((len(d1), 2), -1, np.int32)
+        self.lib.orc_knn2(d1.ctypes.data_as(T.c_uint8_p), len(d1), d2.ctypes.data_as(T.c_uint8_p), len(d2),
+                          idx.ctypes.data_as(T.c_int32_p), dist.ctypes.data_as(T.c_int32_p))
+        return idx, dist
+
+    def match_nnr(self, d1, d2, nnr):
+        d1, d2 = np.ascontiguousarray(d1, np.uint8), np.ascontiguousarray(d2, np.uint8)
+        m12 = np.full(len(d1), -1, np.int32)
+        n = self.lib.orc_match_nnr(d1.ctypes.data_as(T.c_uint8_p), len(d1), d2.ctypes.data_as(T.c_uint8_p),
+                                   len(d2), C.c_float(nnr), m12.ctypes.data_as(T.c_int32_p))
+        return n, m12
+
+    def match(self, d1, d2, nnr, best_lr=True, threads=False):
+        d1, d2 = np.ascontiguousarray(d1, np.uint8), np.ascontiguousarray(d2, np.uint8)
+        m12 = np.full(len(d1), -1, np.int32)
+        n = self.lib.orc_match(d1.ctypes.data_as(T.c_uint8_p), len(d1), d2.ctypes.data_as(T.c_uint8_p), len(d2),
+                               C.c_float(nnr), int(best_lr), int(threads), m12.ctypes.data_as(T.c_int32_p))
+        return n, m12
+
+    # ---- SE(3) / statistics ----
+    def inverse_se3(self, Tm):
+        return self._unary("orc_inverse_se3", Tm, 16).reshape(4, 4)
+
+    def expmap_se3(self, x):
+        return self._unary("orc_expmap_se3", x, 16).reshape(4, 4)
+
+    def logmap_se3(self, Tm):
+        return self._unary("orc_logmap_se3", Tm, 6)
+
+    def adjoint_se3(self, Tm):
+        return self._unary("orc_adjoint_se3", Tm, 36).reshape(6, 6)
+
+    def inv6(self, A):
+        return self._unary("orc_inv6", A, 36).reshape(6, 6)
+
+    def eig6_sym(self, A):
+        return self._unary("orc_eig6_sym", A, 6)
+
+    def unccomp_se3(self, T1, c1, cinc):
+        T1, c1, cinc = self._d(T1).ravel(), self._d(c1).ravel(), self._d(cinc).ravel()
+        out = np.zeros(36)
+        self.lib.orc_unccomp_se3(self._dp(T1), self._dp(c1), self._dp(cinc), self._dp(out))
+        return out.reshape(6, 6)
+
+    def qr6_solve(self, H, g):
+        H, g = self._d(H).ravel(), self._d(g).ravel()
+        x, lad = np.zeros(6), np.zeros(1)
+        rank = self.lib.orc_qr6_solve(self._dp(H), self._dp(g), self._dp(x), self._dp(lad))
+        return x, float(lad[0]), rank
+
+    def is_finite(self, x) -> bool:
+        x = self._d(x).ravel()
+        return bool(self.lib.orc_is_finite(self._dp(x), len(x)))
+
+    def vector_mean_stdv_mad(self, res):
+        res = self._d(res).ravel()
+        m, s = np.zeros(1), np.zeros(1)
+        self.lib.orc_vector_mean_stdv_mad(self._dp(res), len(res), self._dp(m), self._dp(s))
+        return float(m[0]), float(s[0])
+
+    def vector_stdv_mad(self, res) -> float:
+        res = self._d(res).ravel()
+        return float(self.lib.orc_vector_stdv_mad(self._dp(res), len(res)))
+
+    def robust_weight_cauchy(self, r) -> float:
+        return float(self.lib.orc_robust_weight_cauchy(float(r)))
+
+    def line_segment_overlap(self, spl_obs, epl_obs, spl_proj, epl_proj) -> float:
+        a, b, c, d = (self._d(v).ravel() for v in (spl_obs, epl_obs, spl_proj, epl_proj))
+        return float(self.lib.orc_line_segment_overlap(self._dp(a), self._dp(b), self._dp(c), self._dp(d)))
+
+    def projection(self, cam, P):
+        P = self._d(P).ravel()
+        uv = np.zeros(2)
+        self.lib.orc_projection(C.byref(cam), self._dp(P), self._dp(uv))
+        return uv
+
+    def back_projection(self, cam, u, v, disp):
+        P = np.zeros(3)
+        self.lib.orc_back_projection(C.byref(cam), float(u), float(v), float(disp), self._dp(P))
+        return P
+
+    # ---- solver ----
+    def optimize_functions(self, cam, cfg, matched: T.MatchedBatch, p, DT, robust=False):
+        DT = self._d(DT).ravel()
+        H, g, e = np.zeros(36), np.zeros(6), np.zeros(1)
+        mc = matched.as_c()
+        self.lib.orc_optimize_functions(C.byref(cam), C.byref(cfg), C.byref(mc), int(p), self._dp(DT), int(robust),
+                                        self._dp(H), self._dp(g), self._dp(e))
+        return H.reshape(6, 6), g, float(e[0])
+
+    def optimize_pose(self, cam, cfg, matched: T.MatchedBatch, priors=None):
+        B = matched.B
+        res = np.zeros(B, dtype=T.POSE_RESULT_DTYPE)
+        inl_pt = np.zeros(int(matched.pt_off[-1]), np.uint8)
+        inl_ls = np.zeros(int(matched.ls_off[-1]), np.uint8)
+        mc = matched.as_c()
+        rc = self.lib.orc_optimize_pose(C.byref(cam), C.byref(cfg), C.byref(mc),
+                                        priors.ctypes.data if priors is not None else None, res.ctypes.data,
+                                        inl_pt.ctypes.data_as(T.c_uint8_p), inl_ls.ctypes.data_as(T.c_uint8_p))
+        return rc, res, inl_pt, inl_ls
+
+    def f2f_tracking(self, cfg, prev: T.FrameBatch, curr: T.FrameBatch):
+        m12_pt = np.full(prev.n_pt, -1, np.int32)
+        m12_ls = np.full(prev.n_ls, -1, np.int32)
+        n = np.zeros((prev.B, 2), np.int32)
+        pc, cc = prev.as_c(), curr.as_c()
+        rc = self.lib.orc_f2f_tracking(C.byref(cfg), C.byref(pc), C.byref(cc), m12_pt.ctypes.data_as(T.c_int32_p),
+                                       m12_ls.ctypes.data_as(T.c_int32_p), n.ctypes.data_as(T.c_int32_p))
+        return rc, m12_pt, m12_ls, n
+
+    def track_batch(self, cam, cfg, prev: T.FrameBatch, curr: T.FrameBatch, priors=None, threads=1,
+                    faithful=False):
+        B = prev.B
+        res = np.zeros(B, dtype=T.POSE_RESULT_DTYPE)
+        m12_pt = np.full(prev.n_pt, -1, np.int32)
+        m12_ls = np.full(prev.n_ls, -1, np.int32)
+        inl_pt = np.zeros(prev.n_pt, np.uint8)
+        inl_ls = np.zeros(prev.n_ls, np.uint8)
+        stage = np.zeros(2)
+        pc, cc = prev.as_c(), curr.as_c()
+        rc = self.lib.orc_track_batch(C.byref(cam), C.byref(cfg), C.byref(pc), C.byref(cc),
+                                      priors.ctypes.data if priors is not None else None, res.ctypes.data,
+                                      m12_pt.ctypes.data_as(T.c_int32_p), m12_ls.ctypes.data_as(T.c_int32_p),
+                                      inl_pt.ctypes.data_as(T.c_uint8_p), inl_ls.ctypes.data_as(T.c_uint8_p),
+                                      int(threads), int(faithful), self._dp(stage))
+        return dict(rc=rc, results=res, m12_pt=m12_pt, m12_ls=m12_ls, inlier_pt=inl_pt, inlier_ls=inl_ls,
+                    stage_ms=stage)

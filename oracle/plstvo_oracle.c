@@ -1,0 +1,1210 @@
+/*
+ * plstvo_oracle.c — CPU ORACLE (test infrastructure, see plstvo_oracle.h for the rules and
+ * the parity-pinning statement).  Plain C restatement of the reference's frame-to-frame path;
+ * every function cites the reference lines it follows (paths relative to rubengooj/stvo-pl).
+ */
+#define _GNU_SOURCE
+#include "plstvo_oracle.h"
+
+#include <float.h>
+#include <limits.h>
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+/* ------------------------------------------------------------------------------------------------
+ * small dense helpers (row-major)
+ * ---------------------------------------------------------------------------------------------- */
+static void mat4_identity(double T[16]) {
+    memset(T, 0, 16 * sizeof(double));
+    T[0] = T[5] = T[10] = T[15] = 1.0;
+}
+static void mat4_mul(const double A[16], const double B[16], double C[16]) {
+    double R[16];
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) {
+            double s = 0.0;
+            for (int k = 0; k < 4; k++) s += A[i * 4 + k] * B[k * 4 + j];
+            R[i * 4 + j] = s;
+        }
+    memcpy(C, R, sizeof(R));
+}
+static int mat4_is_identity(const double T[16]) { /* `DT != Matrix4d::Identity()` — exact compare */
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++)
+            if (T[i * 4 + j] != (i == j ? 1.0 : 0.0)) return 0;
+    return 1;
+}
+static void mat3_mul(const double A[9], const double B[9], double C[9]) {
+    double R[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            double s = 0.0;
+            for (int k = 0; k < 3; k++) s += A[i * 3 + k] * B[k * 3 + j];
+            R[i * 3 + j] = s;
+        }
+    memcpy(C, R, sizeof(R));
+}
+/* src/auxiliar.cpp:29-44 */
+static void skew3(const double v[3], double S[9]) {
+    S[0] = 0;      S[1] = -v[2];  S[2] = v[1];
+    S[3] = v[2];   S[4] = 0;      S[5] = -v[0];
+    S[6] = -v[1];  S[7] = v[0];   S[8] = 0;
+}
+/* Eigen computes a fixed-size 3x3 inverse by cofactors */
+static void mat3_inverse(const double A[9], double Ainv[9]) {
+    double c00 = A[4] * A[8] - A[5] * A[7];
+    double c01 = A[5] * A[6] - A[3] * A[8];
+    double c02 = A[3] * A[7] - A[4] * A[6];
+    double det = A[0] * c00 + A[1] * c01 + A[2] * c02;
+    double id = 1.0 / det;
+    Ainv[0] = c00 * id;
+    Ainv[1] = (A[2] * A[7] - A[1] * A[8]) * id;
+    Ainv[2] = (A[1] * A[5] - A[2] * A[4]) * id;
+    Ainv[3] = c01 * id;
+    Ainv[4] = (A[0] * A[8] - A[2] * A[6]) * id;
+    Ainv[5] = (A[2] * A[3] - A[0] * A[5]) * id;
+    Ainv[6] = c02 * id;
+    Ainv[7] = (A[1] * A[6] - A[0] * A[7]) * id;
+    Ainv[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * SE(3) helpers — src/auxiliar.cpp
+ * ---------------------------------------------------------------------------------------------- */
+void orc_inverse_se3(const double T[16], double Tinv[16]) { /* :113-122 */
+    double R[9], t[3];
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) R[i * 3 + j] = T[i * 4 + j];
+        t[i] = T[i * 4 + 3];
+    }
+    double out[16];
+    mat4_identity(out);
+    for (int i = 0; i < 3; i++) {
+        double s = 0.0;
+        for (int j = 0; j < 3; j++) {
+            out[i * 4 + j] = R[j * 3 + i];
+            s += R[j * 3 + i] * t[j];
+        }
+        out[i * 4 + 3] = -s;
+    }
+    memcpy(Tinv, out, sizeof(out));
+}
+
+void orc_expmap_se3(const double x[6], double T[16]) { /* :124-141, x = [t; w] */
+    double w[3] = {x[3], x[4], x[5]};
+    double t[3] = {x[0], x[1], x[2]};
+    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    double theta = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    if (!(theta < 0.000001)) {
+        double s[9], ss[9], wn[3] = {w[0] / theta, w[1] / theta, w[2] / theta};
+        skew3(wn, s); /* skew(w)/theta: every entry is +-w_i/theta */
+        mat3_mul(s, s, ss);
+        double sn = sin(theta), cs = cos(theta);
+        double V[9];
+        for (int i = 0; i < 9; i++) {
+            double I = (i % 4 == 0) ? 1.0 : 0.0;
+            R[i] = I + s[i] * sn + ss[i] * (1.0 - cs);
+            V[i] = I + s[i] * (1.0 - cs) / theta + ss[i] * (theta - sn) / theta;
+        }
+        double tv[3];
+        for (int i = 0; i < 3; i++) tv[i] = V[i * 3] * t[0] + V[i * 3 + 1] * t[1] + V[i * 3 + 2] * t[2];
+        memcpy(t, tv, sizeof(tv));
+    }
+    mat4_identity(T);
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) T[i * 4 + j] = R[i * 3 + j];
+        T[i * 4 + 3] = t[i];
+    }
+}
+
+void orc_logmap_se3(const double T[16], double x[6]) { /* :143-173 */
+    double R[9], Vt[3], w[3] = {0, 0, 0};
+    double V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) R[i * 3 + j] = T[i * 4 + j];
+        Vt[i] = T[i * 4 + 3];
+    }
+    double cosine = (R[0] + R[4] + R[8] - 1.0) / 2.0;
+    if (cosine > 1.0) cosine = 1.0;
+    else if (cosine < -1.0) cosine = -1.0;
+    double sine = sqrt(1.0 - cosine * cosine);
+    if (sine > 1.0) sine = 1.0;
+    else if (sine < -1.0) sine = -1.0;
+    double theta = acos(cosine);
+    if (theta > 0.000001) {
+        double w_hat[9];
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++)
+                w_hat[i * 3 + j] = theta * (R[i * 3 + j] - R[j * 3 + i]) / (2.0 * sine);
+        w[0] = w_hat[2 * 3 + 1]; /* skewcoords: M(2,1), M(0,2), M(1,0)  (:58-62) */
+        w[1] = w_hat[0 * 3 + 2];
+        w[2] = w_hat[1 * 3 + 0];
+        double s[9], ss[9], wn[3] = {w[0] / theta, w[1] / theta, w[2] / theta};
+        skew3(wn, s);
+        mat3_mul(s, s, ss);
+        for (int i = 0; i < 9; i++) {
+            double I = (i % 4 == 0) ? 1.0 : 0.0;
+            V[i] = I + s[i] * (1.0 - cosine) / theta + ss[i] * (theta - sine) / theta;
+        }
+    }
+    double Vi[9];
+    mat3_inverse(V, Vi);
+    for (int i = 0; i < 3; i++) x[i] = Vi[i * 3] * Vt[0] + Vi[i * 3 + 1] * Vt[1] + Vi[i * 3 + 2] * Vt[2];
+    x[3] = w[0];
+    x[4] = w[1];
+    x[5] = w[2];
+}
+
+void orc_adjoint_se3(const double T[16], double Ad[36]) { /* :175-182 */
+    double R[9], t[3], S[9], SR[9];
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) R[i * 3 + j] = T[i * 4 + j];
+        t[i] = T[i * 4 + 3];
+    }
+    skew3(t, S);
+    mat3_mul(S, R, SR);
+    memset(Ad, 0, 36 * sizeof(double));
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            Ad[i * 6 + j] = R[i * 3 + j];
+            Ad[i * 6 + 3 + j] = SR[i * 3 + j];
+            Ad[(i + 3) * 6 + 3 + j] = R[i * 3 + j];
+        }
+}
+
+void orc_unccomp_se3(const double T1[16], const double c1[36], const double cinc[36], double out[36]) { /* :192-197 */
+    double Ad[36], tmp[36];
+    orc_adjoint_se3(T1, Ad);
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) {
+            double s = 0.0;
+            for (int k = 0; k < 6; k++) s += Ad[i * 6 + k] * cinc[k * 6 + j];
+            tmp[i * 6 + j] = s;
+        }
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) {
+            double s = 0.0;
+            for (int k = 0; k < 6; k++) s += tmp[i * 6 + k] * Ad[j * 6 + k];
+            out[i * 6 + j] = c1[i * 6 + j] + s;
+        }
+}
+
+int orc_is_finite(const double* x, int n) { /* :353-355: ((x-x) == (x-x)).all() */
+    for (int i = 0; i < n; i++) {
+        double d = x[i] - x[i];
+        if (!(d == d)) return 0;
+    }
+    return 1;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * robust statistics — src/auxiliar.cpp
+ * ---------------------------------------------------------------------------------------------- */
+static int cmp_double(const void* a, const void* b) {
+    double x = *(const double*)a, y = *(const double*)b;
+    return (x > y) - (x < y);
+}
+
+void orc_vector_mean_stdv_mad(const double* res, int n, double* mean, double* stdv) { /* :387-430 */
+    *mean = 0.0;
+    *stdv = 0.0;
+    if (n == 0) return;
+    double* r = (double*)malloc((size_t)n * sizeof(double));
+    memcpy(r, res, (size_t)n * sizeof(double));
+    qsort(r, (size_t)n, sizeof(double), cmp_double);
+    double median = r[n / 2];
+    for (int i = 0; i < n; i++) r[i] = (double)fabsf((float)(r[i] - median)); /* fabsf: float rounding (:400) */
+    qsort(r, (size_t)n, sizeof(double), cmp_double);
+    *stdv = 1.4826 * r[n / 2];
+    int k = 0;
+    double m = 0.0;
+    for (int i = 0; i < n; i++)
+        if (res[i] < 2.0 * (*stdv)) {
+            m += res[i];
+            k++;
+        }
+    if (k >= (int)(0.2 * (double)n))
+        m /= (double)k; /* k == 0 can only pass when int(0.2 n) == 0: 0/0 = NaN like the reference */
+    else {
+        k = 0;
+        m = 0.0;
+        for (int i = 0; i < n; i++) {
+            m += res[i];
+            k++;
+        }
+        m /= (double)k;
+    }
+    *mean = m;
+    free(r);
+}
+
+double orc_vector_stdv_mad(const double* res, int n) { /* :444-460 */
+    if (n == 0) return 0.0;
+    double* r = (double*)malloc((size_t)n * sizeof(double));
+    memcpy(r, res, (size_t)n * sizeof(double));
+    qsort(r, (size_t)n, sizeof(double), cmp_double);
+    double median = r[n / 2];
+    for (int i = 0; i < n; i++) r[i] = (double)fabsf((float)(r[i] - median));
+    qsort(r, (size_t)n, sizeof(double), cmp_double);
+    double mad = r[n / 2];
+    free(r);
+    return 1.4826 * mad;
+}
+
+double orc_robust_weight_cauchy(double r) { return 1.0 / (1.0 + r * r); } /* :556-559 */
+
+/* ------------------------------------------------------------------------------------------------
+ * camera — src/pinholeStereoCamera.cpp
+ * ---------------------------------------------------------------------------------------------- */
+void orc_projection(const PlCamera* cam, const double P[3], double uv[2]) { /* :231-237 */
+    uv[0] = cam->cx + cam->fx * P[0] / P[2];
+    uv[1] = cam->cy + cam->fy * P[1] / P[2];
+}
+void orc_back_projection(const PlCamera* cam, double u, double v, double disp, double P[3]) { /* :221-229 */
+    double bd = cam->b / disp;
+    P[0] = bd * (u - cam->cx);
+    P[1] = bd * (v - cam->cy);
+    P[2] = bd * cam->fx;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * StereoFrame::lineSegmentOverlap — src/stereoFrame.cpp:510-616
+ * ---------------------------------------------------------------------------------------------- */
+static double overlap_from_lambdas(double lambda_s, double lambda_e) { /* :531-541 et al. */
+    double lambda_min = (lambda_e < lambda_s) ? lambda_e : lambda_s; /* std::min(a,b) = (b<a)?b:a */
+    double lambda_max = (lambda_s < lambda_e) ? lambda_e : lambda_s; /* std::max(a,b) = (a<b)?b:a */
+    double overlap;
+    if (lambda_min < 0.0 && lambda_max > 1.0) overlap = 1.0;
+    else if (lambda_max < 0.0 || lambda_min > 1.0) overlap = 0.0;
+    else if (lambda_min < 0.0) overlap = lambda_max;
+    else if (lambda_max > 1.0) overlap = 1.0 - lambda_min;
+    else overlap = lambda_max - lambda_min;
+    return overlap;
+}
+
+double orc_line_segment_overlap(const double spl_obs[2], const double epl_obs[2],
+                                const double spl_proj[2], const double epl_proj[2]) {
+    double lx = epl_obs[0] - spl_obs[0], ly = epl_obs[1] - spl_obs[1];
+    if (fabs(spl_obs[0] - epl_obs[0]) < 1.0) { /* vertical (:515-544) */
+        double lambda_s = (spl_proj[1] - spl_obs[1]) / ly;
+        double lambda_e = (epl_proj[1] - spl_obs[1]) / ly;
+        return overlap_from_lambdas(lambda_s, lambda_e);
+    } else if (fabs(spl_obs[1] - epl_obs[1]) < 1.0) { /* horizontal (:545-574) */
+        double lambda_s = (spl_proj[0] - spl_obs[0]) / lx;
+        double lambda_e = (epl_proj[0] - spl_obs[0]) / lx;
+        return overlap_from_lambdas(lambda_s, lambda_e);
+    } else { /* generic (:575-612) */
+        double a = spl_obs[1] - epl_obs[1];
+        double b = epl_obs[0] - spl_obs[0];
+        double c = spl_obs[0] * epl_obs[1] - epl_obs[0] * spl_obs[1];
+        double lxy = 1.0 / (a * a + b * b);
+        double sx = (b * (b * spl_proj[0] - a * spl_proj[1]) - a * c) * lxy;
+        double ex = (b * (b * epl_proj[0] - a * epl_proj[1]) - a * c) * lxy;
+        double lambda_s = (sx - spl_obs[0]) / lx;
+        double lambda_e = (ex - spl_obs[0]) / lx;
+        return overlap_from_lambdas(lambda_s, lambda_e);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Eigen pieces restated (agree with Eigen to rounding)
+ * ---------------------------------------------------------------------------------------------- */
+/* ColPivHouseholderQR<Matrix6d>(H).solve(g) and logAbsDeterminant()
+ * (src/stereoFrameHandler.cpp:417-418, :453-455).  Column-pivoted Householder QR, rank decided with
+ * Eigen's default threshold (eps * 6 relative to the largest pivot).  Returns the rank. */
+int orc_qr6_solve(const double H[36], const double g[6], double x[6], double* log_abs_det) {
+    double A[36], c[6];
+    int perm[6];
+    memcpy(A, H, sizeof(A));
+    memcpy(c, g, sizeof(c));
+    for (int j = 0; j < 6; j++) perm[j] = j;
+    double maxpivot = 0.0;
+    for (int k = 0; k < 6; k++) {
+        /* pivot: remaining column with the largest norm below row k */
+        int best = k;
+        double bestn = -1.0;
+        for (int j = k; j < 6; j++) {
+            double s = 0.0;
+            for (int i = k; i < 6; i++) s += A[i * 6 + j] * A[i * 6 + j];
+            if (s > bestn) { bestn = s; best = j; }
+        }
+        if (best != k) {
+            for (int i = 0; i < 6; i++) { double t = A[i * 6 + k]; A[i * 6 + k] = A[i * 6 + best]; A[i * 6 + best] = t; }
+            int t = perm[k]; perm[k] = perm[best]; perm[best] = t;
+        }
+        /* Householder vector for column k, rows k..5 (Eigen makeHouseholderInPlace convention) */
+        double tail = 0.0;
+        for (int i = k + 1; i < 6; i++) tail += A[i * 6 + k] * A[i * 6 + k];
+        double c0 = A[k * 6 + k], beta, tau;
+        double v[6] = {0, 0, 0, 0, 0, 0};
+        if (tail <= DBL_MIN) {
+            tau = 0.0;
+            beta = c0;
+        } else {
+            beta = sqrt(c0 * c0 + tail);
+            if (c0 >= 0.0) beta = -beta;
+            for (int i = k + 1; i < 6; i++) v[i] = A[i * 6 + k] / (c0 - beta);
+            tau = (beta - c0) / beta;
+        }
+        v[k] = 1.0;
+        /* apply (I - tau v v^T) to the trailing columns and to the right-hand side */
+        for (int j = k + 1; j < 6; j++) {
+            double s = 0.0;
+            for (int i = k; i < 6; i++) s += v[i] * A[i * 6 + j];
+            s *= tau;
+            for (int i = k; i < 6; i++) A[i * 6 + j] -= s * v[i];
+        }
+        {
+            double s = 0.0;
+            for (int i = k; i < 6; i++) s += v[i] * c[i];
+            s *= tau;
+            for (int i = k; i < 6; i++) c[i] -= s * v[i];
+        }
+        A[k * 6 + k] = beta;
+        for (int i = k + 1; i < 6; i++) A[i * 6 + k] = 0.0;
+        if (fabs(beta) > maxpivot) maxpivot = fabs(beta);
+    }
+    int rank = 0;
+    double thr = maxpivot * (DBL_EPSILON * 6.0);
+    double lad = 0.0;
+    for (int k = 0; k < 6; k++) {
+        if (fabs(A[k * 6 + k]) > thr) rank++;
+        lad += log(fabs(A[k * 6 + k]));
+    }
+    if (log_abs_det) *log_abs_det = lad;
+    double y[6] = {0, 0, 0, 0, 0, 0};
+    for (int k = rank - 1; k >= 0; k--) {
+        double s = c[k];
+        for (int j = k + 1; j < rank; j++) s -= A[k * 6 + j] * y[j];
+        y[k] = s / A[k * 6 + k];
+    }
+    for (int k = 0; k < 6; k++) x[perm[k]] = y[k];
+    return rank;
+}
+
+/* Matrix6d::inverse() — Eigen uses PartialPivLU for dynamic/large fixed sizes
+ * (src/stereoFrameHandler.cpp:429, :470) */
+void orc_inv6(const double Ain[36], double Ainv[36]) {
+    double A[36], B[36];
+    memcpy(A, Ain, sizeof(A));
+    memset(B, 0, sizeof(B));
+    for (int i = 0; i < 6; i++) B[i * 6 + i] = 1.0;
+    for (int k = 0; k < 6; k++) {
+        int piv = k;
+        double big = fabs(A[k * 6 + k]);
+        for (int i = k + 1; i < 6; i++)
+            if (fabs(A[i * 6 + k]) > big) { big = fabs(A[i * 6 + k]); piv = i; }
+        if (piv != k)
+            for (int j = 0; j < 6; j++) {
+                double t = A[k * 6 + j]; A[k * 6 + j] = A[piv * 6 + j]; A[piv * 6 + j] = t;
+                t = B[k * 6 + j]; B[k * 6 + j] = B[piv * 6 + j]; B[piv * 6 + j] = t;
+            }
+        double d = A[k * 6 + k];
+        for (int i = k + 1; i < 6; i++) {
+            double f = A[i * 6 + k] / d;
+            A[i * 6 + k] = 0.0;
+            for (int j = k + 1; j < 6; j++) A[i * 6 + j] -= f * A[k * 6 + j];
+            for (int j = 0; j < 6; j++) B[i * 6 + j] -= f * B[k * 6 + j];
+        }
+    }
+    for (int j = 0; j < 6; j++)
+        for (int i = 5; i >= 0; i--) {
+            double s = B[i * 6 + j];
+            for (int k = i + 1; k < 6; k++) s -= A[i * 6 + k] * Ainv[k * 6 + j];
+            Ainv[i * 6 + j] = s / A[i * 6 + i];
+        }
+}
+
+/* SelfAdjointEigenSolver<Matrix6d>::eigenvalues(): reads the LOWER triangle, ascending
+ * (src/stereoFrameHandler.cpp:294-295, :379-380).  Cyclic Jacobi. */
+void orc_eig6_sym(const double Ain[36], double w[6]) {
+    double A[36];
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j <= i; j++) A[i * 6 + j] = A[j * 6 + i] = Ain[i * 6 + j];
+    for (int sweep = 0; sweep < 60; sweep++) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < 6; i++) {
+            diag += A[i * 6 + i] * A[i * 6 + i];
+            for (int j = 0; j < i; j++) off += 2.0 * A[i * 6 + j] * A[i * 6 + j];
+        }
+        if (!(off > 1e-40 * diag) || off == 0.0) break;
+        for (int p = 0; p < 5; p++)
+            for (int q = p + 1; q < 6; q++) {
+                double apq = A[p * 6 + q];
+                if (apq == 0.0) continue;
+                double app = A[p * 6 + p], aqq = A[q * 6 + q];
+                double tau = (aqq - app) / (2.0 * apq);
+                double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                double cs = 1.0 / sqrt(1.0 + t * t), sn = t * cs;
+                for (int k = 0; k < 6; k++) { /* columns p,q */
+                    double akp = A[k * 6 + p], akq = A[k * 6 + q];
+                    A[k * 6 + p] = cs * akp - sn * akq;
+                    A[k * 6 + q] = sn * akp + cs * akq;
+                }
+                for (int k = 0; k < 6; k++) { /* rows p,q */
+                    double apk = A[p * 6 + k], aqk = A[q * 6 + k];
+                    A[p * 6 + k] = cs * apk - sn * aqk;
+                    A[q * 6 + k] = sn * apk + cs * aqk;
+                }
+            }
+    }
+    for (int i = 0; i < 6; i++) w[i] = A[i * 6 + i];
+    qsort(w, 6, sizeof(double), cmp_double);
+    /* NaN input: qsort leaves an arbitrary order; the gate below only asks w[0] < 0 || w[5] > 1,
+     * both false for NaN, exactly like Eigen's NaN eigenvalues. */
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * matching — src/matching.cpp
+ * ---------------------------------------------------------------------------------------------- */
+int orc_distance(const uint8_t* a, const uint8_t* b) { /* :93-109, SWAR popcount over 8 x int32 */
+    int dist = 0;
+    for (int i = 0; i < 8; i++) {
+        uint32_t pa, pb;
+        memcpy(&pa, a + 4 * i, 4);
+        memcpy(&pb, b + 4 * i, 4);
+        uint32_t v = pa ^ pb;
+        v = v - ((v >> 1) & 0x55555555u);
+        v = (v & 0x33333333u) + ((v >> 2) & 0x33333333u);
+        dist += (int)((((v + (v >> 4)) & 0xF0F0F0Fu) * 0x1010101u) >> 24);
+    }
+    return dist;
+}
+
+/* Hamming norm the way OpenCV's normHamming does it (hardware popcount), used inside knnMatch */
+static inline int hamming256(const uint8_t* a, const uint8_t* b) {
+    uint64_t x[4], y[4];
+    memcpy(x, a, 32);
+    memcpy(y, b, 32);
+    return __builtin_popcountll(x[0] ^ y[0]) + __builtin_popcountll(x[1] ^ y[1]) +
+           __builtin_popcountll(x[2] ^ y[2]) + __builtin_popcountll(x[3] ^ y[3]);
+}
+
+/* cv::BFMatcher(NORM_HAMMING,false)::knnMatch(d1, d2, ., 2) -> cv::batchDistance with K = 2
+ * (third-party: OpenCV features2d/core, not under /root/reference; call site src/matching.cpp:47-48).
+ * Published algorithm: for each query row the integer distances to all train rows are scanned in
+ * ascending train index and inserted into a K-long list kept sorted by strict `<` comparisons, so
+ * the list ends up ordered by (distance, trainIdx) ascending. */
+void orc_knn2(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int32_t* idx, int32_t* dist) {
+    for (int i = 0; i < n1; i++) {
+        int bd[2] = {INT_MAX, INT_MAX}, bi[2] = {-1, -1};
+        const uint8_t* q = d1 + (size_t)i * 32;
+        for (int j = 0; j < n2; j++) {
+            int d = hamming256(q, d2 + (size_t)j * 32);
+            if (d < bd[1]) {
+                int k = 0; /* insertion position */
+                if (!(bd[0] > d)) k = 1;
+                if (k == 0) { bd[1] = bd[0]; bi[1] = bi[0]; }
+                bd[k] = d;
+                bi[k] = j;
+            }
+        }
+        idx[2 * i] = bi[0];
+        idx[2 * i + 1] = bi[1];
+        dist[2 * i] = bi[0] >= 0 ? bd[0] : -1;
+        dist[2 * i + 1] = bi[1] >= 0 ? bd[1] : -1;
+    }
+}
+
+int orc_match_nnr(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr, int32_t* m12) { /* :41-61 */
+    int matches = 0;
+    for (int i = 0; i < n1; i++) m12[i] = -1; /* matches_12.resize(desc1.rows, -1) (:44) */
+    if (n1 <= 0) return 0;
+    if (n2 < 2) return 0; /* reference: matches_[idx][1] out of range (UB); defined here as "no match" */
+    int32_t* idx = (int32_t*)malloc((size_t)n1 * 2 * sizeof(int32_t));
+    int32_t* dist = (int32_t*)malloc((size_t)n1 * 2 * sizeof(int32_t));
+    orc_knn2(d1, n1, d2, n2, idx, dist);
+    for (int i = 0; i < n1; i++) {
+        float dd0 = (float)dist[2 * i], dd1 = (float)dist[2 * i + 1]; /* DMatch::distance is float */
+        if (dd0 < dd1 * nnr) { /* float multiply, :54 */
+            m12[i] = idx[2 * i];
+            matches++;
+        }
+    }
+    free(idx);
+    free(dist);
+    return matches;
+}
+
+typedef struct {
+    const uint8_t *d1, *d2;
+    int n1, n2;
+    float nnr;
+    int32_t* out;
+    int ret;
+} NnrJob;
+static void* nnr_thread(void* p) {
+    NnrJob* j = (NnrJob*)p;
+    j->ret = orc_match_nnr(j->d1, j->n1, j->d2, j->n2, j->nnr, j->out);
+    return NULL;
+}
+
+int orc_match(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr, int best_lr,
+              int threads, int32_t* m12) { /* :63-91 */
+    if (!best_lr) return orc_match_nnr(d1, n1, d2, n2, nnr, m12);
+    int32_t* m21 = (int32_t*)malloc((size_t)(n2 > 0 ? n2 : 1) * sizeof(int32_t));
+    int matches;
+    if (threads) { /* lrInParallel: two std::async tasks (:68-74) */
+        NnrJob a = {d1, d2, n1, n2, nnr, m12, 0}, b = {d2, d1, n2, n1, nnr, m21, 0};
+        pthread_t tb;
+        pthread_create(&tb, NULL, nnr_thread, &b);
+        nnr_thread(&a);
+        pthread_join(tb, NULL);
+        matches = a.ret;
+    } else {
+        matches = orc_match_nnr(d1, n1, d2, n2, nnr, m12);
+        orc_match_nnr(d2, n2, d1, n1, nnr, m21);
+    }
+    for (int i1 = 0; i1 < n1; i1++) { /* :80-86 */
+        int i2 = m12[i1];
+        if (i2 >= 0 && m21[i2] != i1) {
+            m12[i1] = -1;
+            matches--;
+        }
+    }
+    free(m21);
+    return matches;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * the handler state (StereoFrameHandler: matched_pt / matched_ls lists, include/stereoFrameHandler.h)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { /* PointFeature fields the path reads (include/stereoFeatures.h:30-58) */
+    double P[3], pl_obs[2], sigma2;
+    int inlier;
+} OrcPoint;
+typedef struct { /* LineFeature fields the path reads (include/stereoFeatures.h:60-121) */
+    double sP[3], eP[3], le_obs[3], spl[2], epl[2], sigma2;
+    int inlier;
+} OrcLine;
+typedef struct {
+    const PlCamera* cam;
+    const PlConfig* cfg;
+    OrcPoint* pt;
+    int n_pt; /* matched_pt */
+    OrcLine* ls;
+    int n_ls; /* matched_ls */
+    int n_inliers, n_inliers_pt, n_inliers_ls;
+    int evals; /* instrumentation: optimizeFunctions calls in the current GN run */
+} OrcHandler;
+
+static void transform_point(const double DT[16], const double P[3], double out[3]) {
+    /* DT.block(0,0,3,3) * P + DT.col(3).head(3)   (src/stereoFrameHandler.cpp:567) */
+    for (int i = 0; i < 3; i++)
+        out[i] = (DT[i * 4 + 0] * P[0] + DT[i * 4 + 1] * P[1] + DT[i * 4 + 2] * P[2]) + DT[i * 4 + 3];
+}
+
+static double dmax(double a, double b) { return (a < b) ? b : a; } /* std::max */
+
+/* the 6-vector of src/stereoFrameHandler.cpp:582-587 / :636-641 with (dx,dy) or (lx,ly) */
+static void jac_aux(double fgz2, double gx, double gy, double gz, double dx, double dy, double J[6]) {
+    J[0] = +fgz2 * dx * gz;
+    J[1] = +fgz2 * dy * gz;
+    J[2] = -fgz2 * (gx * dx + gy * dy);
+    J[3] = -fgz2 * (gx * gy * dx + gy * gy * dy + gz * gz * dy);
+    J[4] = +fgz2 * (gx * gx * dx + gz * gz * dx + gx * gy * dy);
+    J[5] = +fgz2 * (gx * gz * dy - gy * gz * dx);
+}
+
+static void accumulate(double H[36], double g[6], double* e, const double J[6], double r, double w) {
+    /* H += J*J^T*w; g += J*r*w; e += r*r*w   (:601-603) — Eigen evaluates (J*J^T)*w, (J*r)*w */
+    for (int i = 0; i < 6; i++) {
+        for (int j = 0; j < 6; j++) H[i * 6 + j] += (J[i] * J[j]) * w;
+        g[i] += (J[i] * r) * w;
+    }
+    *e += r * r * w;
+}
+
+static double point_residual_norm(const OrcHandler* h, const double DT[16], const OrcPoint* pt,
+                                  double P_[3], double err[2]) {
+    double uv[2];
+    transform_point(DT, pt->P, P_);
+    orc_projection(h->cam, P_, uv);
+    err[0] = uv[0] - pt->pl_obs[0];
+    err[1] = uv[1] - pt->pl_obs[1];
+    return sqrt(err[0] * err[0] + err[1] * err[1]);
+}
+
+static double line_residual_norm(const OrcHandler* h, const double DT[16], const OrcLine* ls,
+                                 double sP_[3], double eP_[3], double sproj[2], double eproj[2],
+                                 double err[2]) {
+    transform_point(DT, ls->sP, sP_);
+    orc_projection(h->cam, sP_, sproj);
+    transform_point(DT, ls->eP, eP_);
+    orc_projection(h->cam, eP_, eproj);
+    err[0] = ls->le_obs[0] * sproj[0] + ls->le_obs[1] * sproj[1] + ls->le_obs[2];
+    err[1] = ls->le_obs[0] * eproj[0] + ls->le_obs[1] * eproj[1] + ls->le_obs[2];
+    return sqrt(err[0] * err[0] + err[1] * err[1]);
+}
+
+/* optimizeFunctions (src/stereoFrameHandler.cpp:549-694) and optimizeFunctionsRobust (:696-962) */
+static void optimize_functions(OrcHandler* h, const double DT[16], int robust, double H[36],
+                               double g[6], double* e_out) {
+    const double homog_th = h->cfg->homog_th, fx = h->cam->fx;
+    double H_p[36], H_l[36], g_p[6], g_l[6], e_p = 0.0, e_l = 0.0;
+    memset(H_p, 0, sizeof(H_p));
+    memset(H_l, 0, sizeof(H_l));
+    memset(g_p, 0, sizeof(g_p));
+    memset(g_l, 0, sizeof(g_l));
+    h->evals++;
+
+    double s_p = 1.0, s_l = 1.0;
+    if (robust) { /* pre-weight pass + MAD scales (:707-781) */
+        double* res_p = (double*)malloc((size_t)(h->n_pt + 1) * sizeof(double));
+        double* res_l = (double*)malloc((size_t)(h->n_ls + 1) * sizeof(double));
+        int np = 0, nl = 0;
+        for (int i = 0; i < h->n_pt; i++)
+            if (h->pt[i].inlier) {
+                double P_[3], err[2];
+                res_p[np++] = point_residual_norm(h, DT, &h->pt[i], P_, err);
+            }
+        for (int i = 0; i < h->n_ls; i++)
+            if (h->ls[i].inlier) {
+                double a[3], b[3], c[2], d[2], err[2];
+                res_l[nl++] = line_residual_norm(h, DT, &h->ls[i], a, b, c, d, err);
+            }
+        const double th_min = 0.0001, th_max = sqrt(7.815);
+        s_p = orc_vector_stdv_mad(res_p, np);
+        s_l = orc_vector_stdv_mad(res_l, nl);
+        if (s_p < th_min) s_p = th_min;
+        if (s_p > th_max) s_p = th_max;
+        if (s_l < th_min) s_l = th_min;
+        if (s_l > th_max) s_l = th_max;
+        free(res_p);
+        free(res_l);
+    }
+
+    int N_p = 0;
+    for (int i = 0; i < h->n_pt; i++) { /* point block (:563-606 / :785-870) */
+        const OrcPoint* pt = &h->pt[i];
+        if (!pt->inlier) continue;
+        double P_[3], err[2], J[6];
+        double err_norm = point_residual_norm(h, DT, pt, P_, err);
+        double gx = P_[0], gy = P_[1], gz = P_[2];
+        double gz2 = gz * gz;
+        double fgz2 = fx / dmax(homog_th, gz2);
+        jac_aux(fgz2, gx, gy, gz, err[0], err[1], J);
+        double den = dmax(homog_th, err_norm);
+        for (int k = 0; k < 6; k++) J[k] = J[k] / den;
+        double s2 = pt->sigma2, r, w;
+        if (!robust) {
+            r = err_norm * sqrt(s2);
+            w = orc_robust_weight_cauchy(r);
+        } else {
+            r = err_norm;
+            w = orc_robust_weight_cauchy(r / s_p);
+        }
+        accumulate(H_p, g_p, &e_p, J, r, w);
+        N_p++;
+    }
+
+    int N_l = 0;
+    for (int i = 0; i < h->n_ls; i++) { /* line block (:610-684 / :874-952) */
+        const OrcLine* ls = &h->ls[i];
+        if (!ls->inlier) continue;
+        double sP_[3], eP_[3], sproj[2], eproj[2], err[2], Js[6], Je[6], J[6];
+        double err_norm = line_residual_norm(h, DT, ls, sP_, eP_, sproj, eproj, err);
+        double lx = ls->le_obs[0], ly = ls->le_obs[1];
+        double ds = err[0], de = err[1];
+        double fgz2 = fx / dmax(homog_th, sP_[2] * sP_[2]);
+        jac_aux(fgz2, sP_[0], sP_[1], sP_[2], lx, ly, Js);
+        fgz2 = fx / dmax(homog_th, eP_[2] * eP_[2]);
+        jac_aux(fgz2, eP_[0], eP_[1], eP_[2], lx, ly, Je);
+        double den = dmax(homog_th, err_norm);
+        for (int k = 0; k < 6; k++) J[k] = (Js[k] * ds + Je[k] * de) / den;
+        double s2 = ls->sigma2, r, w;
+        if (!robust) {
+            r = err_norm * sqrt(s2);
+            w = orc_robust_weight_cauchy(r);
+        } else {
+            r = err_norm;
+            w = orc_robust_weight_cauchy(r / s_l);
+        }
+        /* overlap with the PREVIOUS frame's endpoints spl/epl (:668, :930) */
+        double overlap = orc_line_segment_overlap(ls->spl, ls->epl, sproj, eproj);
+        w *= overlap;
+        accumulate(H_l, g_l, &e_l, J, r, w);
+        N_l++;
+    }
+
+    for (int i = 0; i < 36; i++) H[i] = H_p[i] + H_l[i]; /* :687-692 */
+    for (int i = 0; i < 6; i++) g[i] = g_p[i] + g_l[i];
+    double e = e_p + e_l;
+    e /= (double)(N_l + N_p);
+    *e_out = e;
+}
+
+static double norm3(const double* v) { return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+
+/* DT << DT * inverse_se3( expmap_se3(DT_inc) )   (:419, :460) */
+static void apply_increment(double DT[16], const double inc[6]) {
+    double E[16], Ei[16];
+    orc_expmap_se3(inc, E);
+    orc_inverse_se3(E, Ei);
+    mat4_mul(DT, Ei, DT);
+}
+
+/* gaussNewtonOptimization (src/stereoFrameHandler.cpp:394-431) */
+static void gauss_newton(OrcHandler* h, double DT[16], double DT_cov[36], double* err_, int max_iters) {
+    double H[36], g[6], inc[6];
+    double err = 0.0, err_prev = 999999999.9;
+    memset(H, 0, sizeof(H));
+    h->evals = 0;
+    for (int iters = 0; iters < max_iters; iters++) {
+        optimize_functions(h, DT, 0, H, g, &err);
+        if (err > err_prev) {
+            if (iters > 0) break;
+            *err_ = -1.0;
+            return;
+        }
+        if ((err < h->cfg->min_error) || fabs(err - err_prev) < h->cfg->min_error_change) break;
+        orc_qr6_solve(H, g, inc, NULL);
+        apply_increment(DT, inc);
+        if (norm3(inc) < h->cfg->min_error_change && norm3(inc + 3) < h->cfg->min_error_change) break;
+        err_prev = err;
+    }
+    orc_inv6(H, DT_cov);
+    *err_ = err;
+}
+
+/* gaussNewtonOptimizationRobust (src/stereoFrameHandler.cpp:433-480) */
+static void gauss_newton_robust(OrcHandler* h, double DT[16], double DT_cov[36], double* err_, int max_iters) {
+    double DT0[16], H[36], g[6], inc[6];
+    double err = 0.0, err_prev = 999999999.9;
+    int solution_is_good = 1;
+    memcpy(DT0, DT, sizeof(DT0));
+    memset(H, 0, sizeof(H));
+    h->evals = 0;
+    for (int iters = 0; iters < max_iters; iters++) {
+        optimize_functions(h, DT, 1, H, g, &err);
+        if ((fabs(err - err_prev) < h->cfg->min_error_change) || (err < h->cfg->min_error)) break;
+        double lad;
+        orc_qr6_solve(H, g, inc, &lad);
+        if (lad < 0.0) { /* solver.info() is always Success for ColPivHouseholderQR */
+            solution_is_good = 0;
+            break;
+        }
+        apply_increment(DT, inc);
+        if (sqrt(inc[0] * inc[0] + inc[1] * inc[1] + inc[2] * inc[2] + inc[3] * inc[3] + inc[4] * inc[4] +
+                 inc[5] * inc[5]) < h->cfg->min_error_change)
+            break;
+        err_prev = err;
+    }
+    if (solution_is_good) {
+        orc_inv6(H, DT_cov);
+        *err_ = err;
+    } else {
+        memcpy(DT, DT0, sizeof(DT0));
+        *err_ = -1.0;
+        memset(DT_cov, 0, 36 * sizeof(double));
+        for (int i = 0; i < 6; i++) DT_cov[i * 6 + i] = 1.0;
+    }
+}
+
+/* isGoodSolution (src/stereoFrameHandler.cpp:292-305) */
+static int is_good_solution(const double DT[16], const double DT_cov[36], double err) {
+    double w[6];
+    orc_eig6_sym(DT_cov, w);
+    if (w[0] < 0.0 || w[5] > 1.0 || err < 0.0 || err > 1.0 || !orc_is_finite(DT, 16)) return 0;
+    return 1;
+}
+
+/* removeOutliers (src/stereoFrameHandler.cpp:988-1067) */
+static int remove_outliers(OrcHandler* h, const double DT[16]) {
+    if (h->cfg->has_points) {
+        double* res = (double*)malloc((size_t)(h->n_pt + 1) * sizeof(double));
+        for (int i = 0; i < h->n_pt; i++) {
+            double P_[3], err[2];
+            res[i] = point_residual_norm(h, DT, &h->pt[i], P_, err) * sqrt(h->pt[i].sigma2);
+        }
+        double mean, stdv;
+        orc_vector_mean_stdv_mad(res, h->n_pt, &mean, &stdv);
+        double th = h->cfg->inlier_k * stdv;
+        for (int i = 0; i < h->n_pt; i++)
+            if (h->pt[i].inlier && fabs(res[i] - mean) > th) {
+                h->pt[i].inlier = 0;
+                h->n_inliers--;
+                h->n_inliers_pt--;
+            }
+        free(res);
+    }
+    if (h->cfg->has_lines) {
+        double* res = (double*)malloc((size_t)(h->n_ls + 1) * sizeof(double));
+        for (int i = 0; i < h->n_ls; i++) {
+            double a[3], b[3], c[2], d[2], err[2];
+            res[i] = line_residual_norm(h, DT, &h->ls[i], a, b, c, d, err) * sqrt(h->ls[i].sigma2);
+        }
+        double mean, stdv;
+        orc_vector_mean_stdv_mad(res, h->n_ls, &mean, &stdv);
+        double th = h->cfg->inlier_k * stdv;
+        for (int i = 0; i < h->n_ls; i++)
+            if (fabs(res[i] - mean) > th && h->ls[i].inlier) {
+                h->ls[i].inlier = 0;
+                h->n_inliers--;
+                h->n_inliers_ls--;
+            }
+        free(res);
+    }
+    if (h->n_inliers != h->n_inliers_pt + h->n_inliers_ls) return PLSTVO_E_SIZE; /* :1065-1066 throws */
+    return 0;
+}
+
+/* optimizePose (src/stereoFrameHandler.cpp:307-392) */
+static int optimize_pose(OrcHandler* h, const PlPrior* prior, PlPoseResult* out) {
+    const PlConfig* cfg = h->cfg;
+    double DT[16], DT_[16], DT_cov[36];
+    double err = -1.0;
+    int rc = 0;
+    memset(DT_cov, 0, sizeof(DT_cov)); /* uninitialised in the reference; only read after a GN call set it,
+                                          or together with err == -1 which fails the gate regardless */
+    out->status = PLSTVO_ST_REFINED;
+    out->iters_stage1 = out->iters_stage2 = 0;
+
+    if (cfg->use_motion_model && prior) { /* :317-324 */
+        memcpy(DT, prior->DT, sizeof(DT));
+        if (!is_good_solution(DT, prior->DT_cov, prior->err_norm)) mat4_identity(DT);
+    } else
+        mat4_identity(DT);
+
+    const int mode = cfg->solver_mode; /* hard-wired 0 in the reference (:329) */
+    if (h->n_inliers >= cfg->min_features) {
+        memcpy(DT_, DT, sizeof(DT));
+        if (mode == 0) gauss_newton(h, DT_, DT_cov, &err, cfg->max_iters);
+        else gauss_newton_robust(h, DT_, DT_cov, &err, cfg->max_iters);
+        out->iters_stage1 = h->evals;
+        if (is_good_solution(DT_, DT_cov, err)) {
+            rc = remove_outliers(h, DT_);
+            if (h->n_inliers >= cfg->min_features) {
+                if (mode == 0) gauss_newton(h, DT, DT_cov, &err, cfg->max_iters_ref);
+                else gauss_newton_robust(h, DT, DT_cov, &err, cfg->max_iters_ref);
+                out->iters_stage2 = h->evals;
+            } else {
+                mat4_identity(DT);
+                out->status = PLSTVO_ST_FEW_AFTER;
+            }
+        } else {
+            gauss_newton_robust(h, DT, DT_cov, &err, cfg->max_iters_ref);
+            out->iters_stage2 = h->evals;
+            out->status = PLSTVO_ST_ROBUST_FALLBACK;
+        }
+    } else {
+        mat4_identity(DT);
+        out->status = PLSTVO_ST_FEW_BEFORE;
+    }
+    memcpy(out->DT_opt, DT, sizeof(DT));
+
+    double Tfw_prev[16], Tfw_cov_prev[36];
+    if (prior) {
+        memcpy(Tfw_prev, prior->Tfw, sizeof(Tfw_prev));
+        memcpy(Tfw_cov_prev, prior->Tfw_cov, sizeof(Tfw_cov_prev));
+    } else { /* initialize(): Tfw = I, Tfw_cov = I (src/stereoFrameHandler.cpp:43-44) */
+        mat4_identity(Tfw_prev);
+        memset(Tfw_cov_prev, 0, sizeof(Tfw_cov_prev));
+        for (int i = 0; i < 6; i++) Tfw_cov_prev[i * 6 + i] = 1.0;
+    }
+
+    if (is_good_solution(DT, DT_cov, err) && !mat4_is_identity(DT)) { /* :372-381 */
+        double Ti[16], x[6], T2[16];
+        orc_inverse_se3(DT, Ti);
+        orc_logmap_se3(Ti, x);
+        orc_expmap_se3(x, out->DT);
+        memcpy(out->DT_cov, DT_cov, sizeof(DT_cov));
+        out->err_norm = err;
+        mat4_mul(Tfw_prev, out->DT, T2);
+        orc_logmap_se3(T2, x);
+        orc_expmap_se3(x, out->Tfw);
+        orc_unccomp_se3(Tfw_prev, Tfw_cov_prev, DT_cov, out->Tfw_cov);
+        orc_eig6_sym(DT_cov, out->DT_cov_eig);
+        out->good = 1;
+    } else { /* :382-391 */
+        mat4_identity(out->DT);
+        memset(out->DT_cov, 0, sizeof(out->DT_cov));
+        out->err_norm = -1.0;
+        memcpy(out->Tfw, Tfw_prev, sizeof(Tfw_prev));
+        memcpy(out->Tfw_cov, Tfw_cov_prev, sizeof(Tfw_cov_prev));
+        memset(out->DT_cov_eig, 0, sizeof(out->DT_cov_eig));
+        out->good = 0;
+    }
+    out->n_matched_pt = h->n_pt;
+    out->n_matched_ls = h->n_ls;
+    out->n_inliers_pt = h->n_inliers_pt;
+    out->n_inliers_ls = h->n_inliers_ls;
+    out->n_inliers = h->n_inliers;
+    out->reserved = 0;
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * public entry points
+ * ---------------------------------------------------------------------------------------------- */
+static void handler_from_matched(OrcHandler* h, const PlCamera* cam, const PlConfig* cfg,
+                                 const PlMatchedBatch* m, int p) {
+    int p0 = m->pt_off[p], p1 = m->pt_off[p + 1], l0 = m->ls_off[p], l1 = m->ls_off[p + 1];
+    h->cam = cam;
+    h->cfg = cfg;
+    h->n_pt = p1 - p0;
+    h->n_ls = l1 - l0;
+    h->pt = (OrcPoint*)calloc((size_t)h->n_pt + 1, sizeof(OrcPoint));
+    h->ls = (OrcLine*)calloc((size_t)h->n_ls + 1, sizeof(OrcLine));
+    for (int i = 0; i < h->n_pt; i++) {
+        OrcPoint* q = &h->pt[i];
+        memcpy(q->P, m->pt_P + 3 * (size_t)(p0 + i), 24);
+        memcpy(q->pl_obs, m->pt_pl_obs + 2 * (size_t)(p0 + i), 16);
+        q->sigma2 = m->pt_sigma2[p0 + i];
+        q->inlier = m->pt_inlier ? (m->pt_inlier[p0 + i] != 0) : 1;
+    }
+    for (int i = 0; i < h->n_ls; i++) {
+        OrcLine* q = &h->ls[i];
+        memcpy(q->sP, m->ls_sP + 3 * (size_t)(l0 + i), 24);
+        memcpy(q->eP, m->ls_eP + 3 * (size_t)(l0 + i), 24);
+        memcpy(q->le_obs, m->ls_le_obs + 3 * (size_t)(l0 + i), 24);
+        memcpy(q->spl, m->ls_spl + 2 * (size_t)(l0 + i), 16);
+        memcpy(q->epl, m->ls_epl + 2 * (size_t)(l0 + i), 16);
+        q->sigma2 = m->ls_sigma2[l0 + i];
+        q->inlier = m->ls_inlier ? (m->ls_inlier[l0 + i] != 0) : 1;
+    }
+    /* f2fTracking: n_inliers_* = list sizes (src/stereoFrameHandler.cpp:126-128) */
+    h->n_inliers_pt = h->n_pt;
+    h->n_inliers_ls = h->n_ls;
+    h->n_inliers = h->n_pt + h->n_ls;
+    h->evals = 0;
+}
+
+void orc_optimize_functions(const PlCamera* cam, const PlConfig* cfg, const PlMatchedBatch* m, int p,
+                            const double DT[16], int robust, double H[36], double g[6], double* e) {
+    OrcHandler h;
+    handler_from_matched(&h, cam, cfg, m, p);
+    optimize_functions(&h, DT, robust, H, g, e);
+    free(h.pt);
+    free(h.ls);
+}
+
+int orc_optimize_pose(const PlCamera* cam, const PlConfig* cfg, const PlMatchedBatch* matched,
+                      const PlPrior* priors, PlPoseResult* results, uint8_t* inlier_pt,
+                      uint8_t* inlier_ls) {
+    int rc = 0;
+    for (int p = 0; p < matched->B; p++) {
+        OrcHandler h;
+        handler_from_matched(&h, cam, cfg, matched, p);
+        int r = optimize_pose(&h, priors ? &priors[p] : NULL, &results[p]);
+        if (r < 0) rc = r;
+        if (inlier_pt)
+            for (int i = 0; i < h.n_pt; i++) inlier_pt[matched->pt_off[p] + i] = (uint8_t)h.pt[i].inlier;
+        if (inlier_ls)
+            for (int i = 0; i < h.n_ls; i++) inlier_ls[matched->ls_off[p] + i] = (uint8_t)h.ls[i].inlier;
+        free(h.pt);
+        free(h.ls);
+    }
+    return rc;
+}
+
+typedef struct {
+    const PlConfig* cfg;
+    const PlFrameBatch *prev, *curr;
+    int p, lines, threads;
+    int32_t* m12;
+    int ret;
+} F2fJob;
+
+static void* f2f_job(void* arg) { /* matchF2FPoints :131-153 / matchF2FLines :155-180 (matching part) */
+    F2fJob* j = (F2fJob*)arg;
+    const PlFrameBatch *a = j->prev, *b = j->curr;
+    const int32_t *oa = j->lines ? a->ls_off : a->pt_off, *ob = j->lines ? b->ls_off : b->pt_off;
+    int n1 = oa[j->p + 1] - oa[j->p], n2 = ob[j->p + 1] - ob[j->p];
+    int enabled = j->lines ? j->cfg->has_lines : j->cfg->has_points;
+    for (int i = 0; i < n1; i++) j->m12[i] = -1;
+    j->ret = 0;
+    if (!enabled || n1 == 0 || n2 == 0) return NULL; /* :137-138, :160-161 */
+    const uint8_t* d1 = (j->lines ? a->ldesc : a->pdesc) + (size_t)oa[j->p] * 32;
+    const uint8_t* d2 = (j->lines ? b->ldesc : b->pdesc) + (size_t)ob[j->p] * 32;
+    float nnr = (float)(j->lines ? j->cfg->min_ratio_12_l : j->cfg->min_ratio_12_p); /* double -> float at the call */
+    j->ret = orc_match(d1, n1, d2, n2, nnr, j->cfg->best_lr_matches, j->threads, j->m12);
+    return NULL;
+}
+
+static void f2f_pair(const PlConfig* cfg, const PlFrameBatch* prev, const PlFrameBatch* curr, int p,
+                     int faithful, int32_t* m12_pt, int32_t* m12_ls, int* n_pt, int* n_ls) {
+    F2fJob jp = {cfg, prev, curr, p, 0, faithful, m12_pt, 0};
+    F2fJob jl = {cfg, prev, curr, p, 1, faithful, m12_ls, 0};
+    if (faithful && cfg->has_points && cfg->has_lines) { /* plInParallel (:113-119) */
+        pthread_t t;
+        pthread_create(&t, NULL, f2f_job, &jl);
+        f2f_job(&jp);
+        pthread_join(t, NULL);
+    } else {
+        f2f_job(&jp);
+        f2f_job(&jl);
+    }
+    *n_pt = jp.ret;
+    *n_ls = jl.ret;
+}
+
+int orc_f2f_tracking(const PlConfig* cfg, const PlFrameBatch* prev, const PlFrameBatch* curr,
+                     int32_t* m12_pt, int32_t* m12_ls, int32_t* n_matched) {
+    if (prev->B != curr->B) return PLSTVO_E_SIZE;
+    for (int p = 0; p < prev->B; p++) {
+        int np, nl;
+        f2f_pair(cfg, prev, curr, p, 0, m12_pt + prev->pt_off[p], m12_ls + prev->ls_off[p], &np, &nl);
+        if (n_matched) {
+            n_matched[2 * p] = np;
+            n_matched[2 * p + 1] = nl;
+        }
+    }
+    return 0;
+}
+
+static double now_ms(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+/* one (prev, curr) pair: f2fTracking glue (src/stereoFrameHandler.cpp:144-152, :167-179) + optimizePose */
+static int track_pair(const PlCamera* cam, const PlConfig* cfg, const PlFrameBatch* prev,
+                      const PlFrameBatch* curr, const PlPrior* prior, int p, int faithful,
+                      PlPoseResult* res, int32_t* m12_pt, int32_t* m12_ls, uint8_t* inl_pt,
+                      uint8_t* inl_ls, double* stage_ms) {
+    int n1p = prev->pt_off[p + 1] - prev->pt_off[p], n1l = prev->ls_off[p + 1] - prev->ls_off[p];
+    int32_t* mp = m12_pt ? m12_pt : (int32_t*)malloc((size_t)(n1p + 1) * sizeof(int32_t));
+    int32_t* ml = m12_ls ? m12_ls : (int32_t*)malloc((size_t)(n1l + 1) * sizeof(int32_t));
+    int np, nl;
+    double t0 = now_ms();
+    f2f_pair(cfg, prev, curr, p, faithful, mp, ml, &np, &nl);
+    double t1 = now_ms();
+
+    OrcHandler h;
+    h.cam = cam;
+    h.cfg = cfg;
+    h.pt = (OrcPoint*)calloc((size_t)np + 1, sizeof(OrcPoint));
+    h.ls = (OrcLine*)calloc((size_t)nl + 1, sizeof(OrcLine));
+    int* ipt = (int*)malloc((size_t)(np + 1) * sizeof(int));
+    int* ils = (int*)malloc((size_t)(nl + 1) * sizeof(int));
+    h.n_pt = h.n_ls = 0;
+    size_t a0 = (size_t)prev->pt_off[p], b0 = (size_t)curr->pt_off[p];
+    for (int i1 = 0; i1 < n1p; i1++) { /* :144-152 */
+        int i2 = mp[i1];
+        if (i2 < 0) continue;
+        OrcPoint* q = &h.pt[h.n_pt];
+        memcpy(q->P, prev->pt_P + 3 * (a0 + i1), 24);
+        memcpy(q->pl_obs, curr->pt_pl + 2 * (b0 + i2), 16); /* pl_obs = curr pl (:148) */
+        q->sigma2 = prev->pt_sigma2[a0 + i1];               /* PointFeature::safeCopy keeps sigma2 */
+        q->inlier = 1;
+        ipt[h.n_pt++] = i1;
+    }
+    a0 = (size_t)prev->ls_off[p];
+    b0 = (size_t)curr->ls_off[p];
+    for (int i1 = 0; i1 < n1l; i1++) { /* :167-179 */
+        int i2 = ml[i1];
+        if (i2 < 0) continue;
+        OrcLine* q = &h.ls[h.n_ls];
+        memcpy(q->sP, prev->ls_sP + 3 * (a0 + i1), 24);
+        memcpy(q->eP, prev->ls_eP + 3 * (a0 + i1), 24);
+        memcpy(q->le_obs, curr->ls_le + 3 * (b0 + i2), 24); /* le_obs = curr le (:175) */
+        memcpy(q->spl, prev->ls_spl + 2 * (a0 + i1), 16);
+        memcpy(q->epl, prev->ls_epl + 2 * (a0 + i1), 16);
+        /* LineFeature::safeCopy -> ctor re-applies the level rule on the passed sigma2
+         * (src/stereoFeatures.cpp:117-135): for level times sigma2 *= lsdScale; sigma2 = 1/(sigma2*sigma2) */
+        double s2 = prev->ls_sigma2[a0 + i1];
+        int level = prev->ls_level ? prev->ls_level[a0 + i1] : 0;
+        for (int k = 0; k < level; k++) s2 *= cfg->lsd_scale;
+        q->sigma2 = 1.0 / (s2 * s2);
+        q->inlier = 1;
+        ils[h.n_ls++] = i1;
+    }
+    h.n_inliers_pt = h.n_pt;
+    h.n_inliers_ls = h.n_ls;
+    h.n_inliers = h.n_pt + h.n_ls;
+    h.evals = 0;
+    int rc = optimize_pose(&h, prior, res);
+    double t2 = now_ms();
+    if (stage_ms) {
+        stage_ms[0] = t1 - t0;
+        stage_ms[1] = t2 - t1;
+    }
+    if (inl_pt) {
+        memset(inl_pt, 0, (size_t)n1p);
+        for (int k = 0; k < h.n_pt; k++) inl_pt[ipt[k]] = (uint8_t)h.pt[k].inlier;
+    }
+    if (inl_ls) {
+        memset(inl_ls, 0, (size_t)n1l);
+        for (int k = 0; k < h.n_ls; k++) inl_ls[ils[k]] = (uint8_t)h.ls[k].inlier;
+    }
+    free(h.pt);
+    free(h.ls);
+    free(ipt);
+    free(ils);
+    if (!m12_pt) free(mp);
+    if (!m12_ls) free(ml);
+    return rc;
+}
+
+typedef struct {
+    const PlCamera* cam;
+    const PlConfig* cfg;
+    const PlFrameBatch *prev, *curr;
+    const PlPrior* priors;
+    PlPoseResult* results;
+    int32_t *m12_pt, *m12_ls;
+    uint8_t *inl_pt, *inl_ls;
+    int faithful;
+    int* next;
+    pthread_mutex_t* mu;
+    double stage_ms[2];
+    int rc;
+} BatchWorker;
+
+static void* batch_worker(void* arg) {
+    BatchWorker* w = (BatchWorker*)arg;
+    for (;;) {
+        pthread_mutex_lock(w->mu);
+        int p = (*w->next)++;
+        pthread_mutex_unlock(w->mu);
+        if (p >= w->prev->B) break;
+        double st[2];
+        int r = track_pair(w->cam, w->cfg, w->prev, w->curr, w->priors ? &w->priors[p] : NULL, p,
+                           w->faithful, &w->results[p],
+                           w->m12_pt ? w->m12_pt + w->prev->pt_off[p] : NULL,
+                           w->m12_ls ? w->m12_ls + w->prev->ls_off[p] : NULL,
+                           w->inl_pt ? w->inl_pt + w->prev->pt_off[p] : NULL,
+                           w->inl_ls ? w->inl_ls + w->prev->ls_off[p] : NULL, st);
+        if (r < 0) w->rc = r;
+        w->stage_ms[0] += st[0];
+        w->stage_ms[1] += st[1];
+    }
+    return NULL;
+}
+
+int orc_track_batch(const PlCamera* cam, const PlConfig* cfg, const PlFrameBatch* prev,
+                    const PlFrameBatch* curr, const PlPrior* priors, PlPoseResult* results,
+                    int32_t* m12_pt, int32_t* m12_ls, uint8_t* inlier_pt, uint8_t* inlier_ls,
+                    int threads, int faithful, double* stage_ms) {
+    if (prev->B != curr->B) return PLSTVO_E_SIZE;
+    if (threads < 1 || faithful) threads = 1;
+    if (threads > 1024) threads = 1024;
+    int next = 0, rc = 0;
+    pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+    BatchWorker* w = (BatchWorker*)calloc((size_t)threads, sizeof(BatchWorker));
+    pthread_t* th = (pthread_t*)calloc((size_t)threads, sizeof(pthread_t));
+    for (int t = 0; t < threads; t++) {
+        BatchWorker b = {cam, cfg, prev, curr, priors, results, m12_pt, m12_ls, inlier_pt, inlier_ls,
+                         faithful, &next, &mu, {0, 0}, 0};
+        w[t] = b;
+    }
+    for (int t = 1; t < threads; t++) pthread_create(&th[t], NULL, batch_worker, &w[t]);
+    batch_worker(&w[0]);
+    for (int t = 1; t < threads; t++) pthread_join(th[t], NULL);
+    if (stage_ms) stage_ms[0] = stage_ms[1] = 0.0;
+    for (int t = 0; t < threads; t++) {
+        if (w[t].rc < 0) rc = w[t].rc;
+        if (stage_ms) {
+            stage_ms[0] += w[t].stage_ms[0];
+            stage_ms[1] += w[t].stage_ms[1];
+        }
+    }
+    free(w);
+    free(th);
+    return rc;
+}

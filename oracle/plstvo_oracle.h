@@ -1,0 +1,86 @@
+/*
+ * plstvo_oracle.h — CPU ORACLE for the PL-StVO frame-to-frame hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+ * The product library (stvo_pl_b200/csrc) never includes, links or calls this code.
+ *
+ * It is a dependency-free restatement (plain C, double precision, scalar loops in the
+ * reference's own order) of rubengooj/stvo-pl @ baecb5f; each function cites the lines it follows.
+ *
+ * PARITY PINNING
+ *   matching half : pinned against OpenCV's cv::BFMatcher (the third-party library the
+ *                   reference calls at src/matching.cpp:47-48; opencv-python 4.13.0 in this
+ *                   image) through committed golden vectors, tests/golden/match_*.npz.
+ *   pose half     : PARITY UNPINNED — the reference ships no tests, fixtures or golden vectors and
+ *                   cannot be compiled here (no Eigen / OpenCV C++ / Boost / yaml-cpp).  The oracle
+ *                   is cross-checked only against source-derived known answers and an independent
+ *                   numpy/scipy restatement (tests/ref_numpy.py).
+ */
+#ifndef PLSTVO_ORACLE_H_
+#define PLSTVO_ORACLE_H_
+
+#include "../include/plstvo.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* src/matching.cpp:93-109 */
+int orc_distance(const uint8_t* a, const uint8_t* b);
+/* src/matching.cpp:41-61 (+ OpenCV BFMatcher::knnMatch semantics) */
+int orc_match_nnr(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr, int32_t* m12);
+/* src/matching.cpp:63-91; threads != 0 runs both directions on two threads (lrInParallel) */
+int orc_match(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr, int best_lr,
+              int threads, int32_t* m12);
+/* raw 2-NN lists, for the comparison with cv2.BFMatcher: idx[2*i+k], dist[2*i+k]; -1 when absent */
+void orc_knn2(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int32_t* idx, int32_t* dist);
+
+/* src/auxiliar.cpp */
+void   orc_inverse_se3(const double T[16], double Tinv[16]);            /* :113-122 */
+void   orc_expmap_se3(const double x[6], double T[16]);                 /* :124-141 */
+void   orc_logmap_se3(const double T[16], double x[6]);                 /* :143-173 */
+void   orc_adjoint_se3(const double T[16], double Ad[36]);              /* :175-182 */
+void   orc_unccomp_se3(const double T1[16], const double c1[36], const double cinc[36], double out[36]); /* :192-197 */
+int    orc_is_finite(const double* x, int n);                           /* :353-355 */
+void   orc_vector_mean_stdv_mad(const double* res, int n, double* mean, double* stdv); /* :387-430 */
+double orc_vector_stdv_mad(const double* res, int n);                   /* :444-460 */
+double orc_robust_weight_cauchy(double r);                              /* :556-559 */
+/* src/stereoFrame.cpp:510-616 */
+double orc_line_segment_overlap(const double spl_obs[2], const double epl_obs[2],
+                                const double spl_proj[2], const double epl_proj[2]);
+/* src/pinholeStereoCamera.cpp:221-237 */
+void   orc_projection(const PlCamera* cam, const double P[3], double uv[2]);
+void   orc_back_projection(const PlCamera* cam, double u, double v, double disp, double P[3]);
+
+/* Eigen pieces restated numerically (agree to rounding, not bitwise) */
+int    orc_qr6_solve(const double H[36], const double g[6], double x[6], double* log_abs_det); /* ColPivHouseholderQR::solve */
+void   orc_inv6(const double A[36], double Ainv[36]);                   /* Matrix6d::inverse (PartialPivLU) */
+void   orc_eig6_sym(const double A[36], double w[6]);                   /* SelfAdjointEigenSolver::eigenvalues, lower triangle, ascending */
+
+/* src/stereoFrameHandler.cpp:549-694 / :696-962 on explicit lists (problem p of the batch);
+ * H row-major 6x6 */
+void   orc_optimize_functions(const PlCamera* cam, const PlConfig* cfg, const PlMatchedBatch* m, int p,
+                              const double DT[16], int robust, double H[36], double g[6], double* e);
+
+/* src/stereoFrameHandler.cpp:307-392 on explicit matched lists */
+int orc_optimize_pose(const PlCamera* cam, const PlConfig* cfg, const PlMatchedBatch* matched,
+                      const PlPrior* priors, PlPoseResult* results, uint8_t* inlier_pt,
+                      uint8_t* inlier_ls);
+/* src/stereoFrameHandler.cpp:106-180 */
+int orc_f2f_tracking(const PlConfig* cfg, const PlFrameBatch* prev, const PlFrameBatch* curr,
+                     int32_t* m12_pt, int32_t* m12_ls, int32_t* n_matched);
+/* insertStereoPair's f2fTracking + optimizePose for B pairs (same contract as plstvo_track_batch).
+ * threads: number of worker threads, one pair per thread at a time (all-cores throughput);
+ * faithful != 0: reference-faithful threading inside a pair instead (points || lines, 1->2 || 2->1:
+ * src/stereoFrameHandler.cpp:113-119, src/matching.cpp:68-74), pairs processed one at a time.
+ * stage_ms (optional, [2]): wall time spent in matching and in optimizePose, summed over pairs. */
+int orc_track_batch(const PlCamera* cam, const PlConfig* cfg, const PlFrameBatch* prev,
+                    const PlFrameBatch* curr, const PlPrior* priors, PlPoseResult* results,
+                    int32_t* m12_pt, int32_t* m12_ls, uint8_t* inlier_pt, uint8_t* inlier_ls,
+                    int threads, int faithful, double* stage_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
