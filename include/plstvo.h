@@ -218,11 +218,12 @@ void  plstvo_host_free(void* p);
 /* ---- instrumentation -------------------------------------------------------------------------- */
 /* kernels launched by this library since the context was created (bench.py's gpu_launches) */
 int64_t plstvo_launch_count(const PlContext* ctx);
-/* average device time of the dominant kernel classes over the launches recorded since the last
- * reset, measured with CUDA events on the launching stream when profiling is enabled */
-void    plstvo_profile_enable(PlContext* ctx, int on);
-int     plstvo_profile_read(PlContext* ctx, double* ms_match, int64_t* n_match,
-                            double* ms_solve, int64_t* n_solve);
+/* device time of the two kernels of one pass over the resident batch, each launched alone `iters` times
+ * on the context's stream and bracketed by CUDA events on that stream: *ms_match / *ms_solve = average
+ * duration of one K1 (hamming_knn2 over all tiles of the batch) / one K2 (track_solve, one CTA per pair)
+ * launch.  n_tiles / n_pairs (optional) = CTAs per launch. */
+int     plstvo_batch_kernel_times(PlContext* ctx, PlDeviceBatch* db, int iters, double* ms_match,
+                                  double* ms_solve, int32_t* n_tiles, int32_t* n_pairs);
 /* GN evaluation (optimizeFunctions, src/stereoFrameHandler.cpp:549-694) of the resident matched
  * lists at given poses, streamed from HBM: the roofline kernel of config C5.
  * DT: [B][16]; H: [B][36]; g: [B][6]; e: [B]. */

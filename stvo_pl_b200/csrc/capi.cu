@@ -1,0 +1,902 @@
+// capi.cu — host side of the C-ABI (include/plstvo.h): context, device buffers, work planning,
+// chunked H2D / compute / D2H pipelining.  No CPU compute path exists in this library: without a CUDA
+// device plstvo_create() fails with PLSTVO_E_NO_DEVICE and every other entry point needs a context.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace plstvo;
+
+namespace {
+
+struct DevBuf {
+    void*  p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Work plan + device storage of one batch of frame pairs (also the body of PlDeviceBatch)
+struct Workspace {
+    int B = 0;
+    PlCamera cam{};
+    PlConfig cfg{};
+    bool has_priors = false;
+    bool have_level = false;   // prev->ls_level supplied (null = level 0 everywhere)
+    // host copies of the offsets
+    std::vector<int32_t> p_off1, p_off2, l_off1, l_off2;
+    // plan
+    std::vector<MatchProblem> problems;   // [2B]: points, lines
+    std::vector<MatchTile> tiles;
+    std::vector<int32_t> tile_start;      // [B+1] first tile of each pair
+    int max_tsplit = 32, cap_pt = 0, cap_ls = 0, sort_cap = 1, max_n2 = 0;
+    bool feat_in_smem = true;
+    // device storage
+    DevBuf d_poff1, d_poff2, d_loff1, d_loff2;
+    DevBuf d_pdesc1, d_pdesc2, d_ldesc1, d_ldesc2;
+    DevBuf d_ptP, d_pts2, d_ptpl;                                      // prev P, prev sigma2, curr pl
+    DevBuf d_lssP, d_lseP, d_lsspl, d_lsepl, d_lss2, d_lslev, d_lsle;  // prev ...; curr le
+    DevBuf d_priors, d_results, d_m12p, d_m12l, d_inlp, d_inll;
+    DevBuf d_rowpart, d_colpart, d_problems, d_tiles, d_feat;
+    size_t feat_stride = 0;
+    void release() {
+        DevBuf* all[] = {&d_poff1, &d_poff2, &d_loff1, &d_loff2, &d_pdesc1, &d_pdesc2, &d_ldesc1, &d_ldesc2,
+                         &d_ptP, &d_pts2, &d_ptpl, &d_lssP, &d_lseP, &d_lsspl, &d_lsepl, &d_lss2, &d_lslev,
+                         &d_lsle, &d_priors, &d_results, &d_m12p, &d_m12l, &d_inlp, &d_inll, &d_rowpart,
+                         &d_colpart, &d_problems, &d_tiles, &d_feat};
+        for (DevBuf* b : all) b->release();
+    }
+};
+
+}  // namespace
+
+struct PlContext {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    cudaStream_t s_main = nullptr, s_alt = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    std::vector<cudaEvent_t> events;
+    size_t next_event = 0;
+    std::string err;
+    int64_t launches = 0;
+    Workspace ws;          // reused by the host-buffer entry points
+    DevBuf scratch;        // misc (popc bench, L2 flush)
+    DevBuf gn_in[8], gn_out[4];
+};
+
+struct PlDeviceBatch {
+    Workspace ws;
+};
+
+namespace {
+
+#define CK(ctx, call)                                                                            \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            char buf__[512];                                                                     \
+            snprintf(buf__, sizeof(buf__), "%s:%d: %s -> %s", __FILE__, __LINE__, #call,         \
+                     cudaGetErrorString(e__));                                                   \
+            (ctx)->err = buf__;                                                                  \
+            return PLSTVO_E_CUDA;                                                                \
+        }                                                                                        \
+    } while (0)
+
+int fail(PlContext* ctx, int code, const char* msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+cudaEvent_t next_event(PlContext* ctx) {
+    if (ctx->next_event == ctx->events.size()) {
+        cudaEvent_t e;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        ctx->events.push_back(e);
+    }
+    return ctx->events[ctx->next_event++];
+}
+
+int pow2_ceil_host(int n) {
+    int m = 1;
+    while (m < n) m <<= 1;
+    return m;
+}
+
+// ---- planning -------------------------------------------------------------------------------------
+// target_ctas: how many K1 tiles we would like at least, so that small batches still fill the chip
+void plan_problem(MatchProblem& pr, int n1, int n2, bool enabled, float nnr, int best_lr, int tsplit_hint) {
+    pr.n1 = n1;
+    pr.n2 = n2;
+    pr.nnr = nnr;
+    pr.best_lr = best_lr;
+    pr.enabled = (enabled && n1 > 0 && n2 > 0) ? 1 : 0;   // src/stereoFrameHandler.cpp:137-138, :160-161
+    if (!pr.enabled) {
+        pr.nqb = pr.ntb = 0;
+        pr.tsplit = 32;
+        return;
+    }
+    pr.nqb = (n1 + K1_THREADS - 1) / K1_THREADS;
+    int ts = ((n2 + 31) / 32) * 32;
+    if (tsplit_hint > 0 && tsplit_hint < ts) ts = tsplit_hint;
+    pr.tsplit = ts;
+    pr.ntb = (n2 + ts - 1) / ts;
+}
+
+int validate_frames(PlContext* ctx, const PlFrameBatch* prev, const PlFrameBatch* curr, bool need_features) {
+    if (!prev || !curr) return fail(ctx, PLSTVO_E_INVALID, "null frame batch");
+    if (prev->B != curr->B) return fail(ctx, PLSTVO_E_SIZE, "prev and curr hold a different number of frames");
+    if (prev->B < 0) return fail(ctx, PLSTVO_E_INVALID, "negative batch size");
+    if (prev->B == 0) return 0;
+    if (!prev->pt_off || !prev->ls_off || !curr->pt_off || !curr->ls_off)
+        return fail(ctx, PLSTVO_E_INVALID, "null offsets");
+    if (prev->pt_off[0] || prev->ls_off[0] || curr->pt_off[0] || curr->ls_off[0])
+        return fail(ctx, PLSTVO_E_INVALID, "offsets must start at 0");
+    for (int p = 0; p < prev->B; ++p) {
+        const int n[4] = {prev->pt_off[p + 1] - prev->pt_off[p], curr->pt_off[p + 1] - curr->pt_off[p],
+                          prev->ls_off[p + 1] - prev->ls_off[p], curr->ls_off[p + 1] - curr->ls_off[p]};
+        for (int k = 0; k < 4; ++k) {
+            if (n[k] < 0) return fail(ctx, PLSTVO_E_INVALID, "offsets are not non-decreasing");
+            if (n[k] > PLSTVO_MAX_FEATURES) return fail(ctx, PLSTVO_E_TOO_LARGE, "more than 65535 features in a frame");
+        }
+    }
+    const int np1 = prev->pt_off[prev->B], np2 = curr->pt_off[curr->B];
+    const int nl1 = prev->ls_off[prev->B], nl2 = curr->ls_off[curr->B];
+    if ((np1 && !prev->pdesc) || (np2 && !curr->pdesc) || (nl1 && !prev->ldesc) || (nl2 && !curr->ldesc))
+        return fail(ctx, PLSTVO_E_INVALID, "null descriptor matrix");
+    if (need_features) {
+        if (np1 && (!prev->pt_P || !prev->pt_sigma2)) return fail(ctx, PLSTVO_E_INVALID, "prev point arrays missing");
+        if (np2 && !curr->pt_pl) return fail(ctx, PLSTVO_E_INVALID, "curr pt_pl missing");
+        if (nl1 && (!prev->ls_sP || !prev->ls_eP || !prev->ls_spl || !prev->ls_epl || !prev->ls_sigma2))
+            return fail(ctx, PLSTVO_E_INVALID, "prev line arrays missing");
+        if (nl2 && !curr->ls_le) return fail(ctx, PLSTVO_E_INVALID, "curr ls_le missing");
+    }
+    return 0;
+}
+
+// Builds the plan of a batch of pairs and sizes every device buffer.  `with_features` = track mode.
+int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfig* cfg, const PlFrameBatch* prev,
+               const PlFrameBatch* curr, bool with_features, bool has_priors) {
+    const int B = prev->B;
+    ws.B = B;
+    if (cam) ws.cam = *cam;
+    ws.cfg = *cfg;
+    ws.has_priors = has_priors;
+    ws.p_off1.assign(prev->pt_off, prev->pt_off + B + 1);
+    ws.p_off2.assign(curr->pt_off, curr->pt_off + B + 1);
+    ws.l_off1.assign(prev->ls_off, prev->ls_off + B + 1);
+    ws.l_off2.assign(curr->ls_off, curr->ls_off + B + 1);
+    const size_t np1 = ws.p_off1[B], np2 = ws.p_off2[B], nl1 = ws.l_off1[B], nl2 = ws.l_off2[B];
+
+    // --- tile split: enough CTAs for a small batch, whole train sets per tile for a big one ---
+    long base_tiles = 0;
+    for (int p = 0; p < B; ++p) {
+        base_tiles += (ws.p_off1[p + 1] - ws.p_off1[p] + K1_THREADS - 1) / K1_THREADS;
+        base_tiles += (ws.l_off1[p + 1] - ws.l_off1[p] + K1_THREADS - 1) / K1_THREADS;
+    }
+    const long want = 3L * ctx->sm_count;   // about one full wave of resident K1 CTAs
+    int split = 1;
+    if (base_tiles > 0 && base_tiles < want) split = (int)((want + base_tiles - 1) / base_tiles);
+
+    ws.problems.assign((size_t)2 * B, MatchProblem{});
+    ws.tiles.clear();
+    ws.tile_start.assign((size_t)B + 1, 0);
+    ws.max_tsplit = 32;
+    ws.cap_pt = ws.cap_ls = 0;
+    ws.max_n2 = 0;
+    size_t row_elems = 0, col_elems = 0;
+    const float nnr_p = (float)cfg->min_ratio_12_p, nnr_l = (float)cfg->min_ratio_12_l;   // double -> float at the call
+    for (int p = 0; p < B; ++p) {
+        ws.tile_start[p] = (int32_t)ws.tiles.size();
+        for (int type = 0; type < 2; ++type) {
+            MatchProblem& pr = ws.problems[(size_t)2 * p + type];
+            const int n1 = type ? ws.l_off1[p + 1] - ws.l_off1[p] : ws.p_off1[p + 1] - ws.p_off1[p];
+            const int n2 = type ? ws.l_off2[p + 1] - ws.l_off2[p] : ws.p_off2[p + 1] - ws.p_off2[p];
+            int hint = 0;
+            if (split > 1) {
+                hint = ((n2 + split - 1) / split + 31) / 32 * 32;
+                if (hint < 256) hint = 256;
+            }
+            plan_problem(pr, n1, n2, type ? cfg->has_lines != 0 : cfg->has_points != 0, type ? nnr_l : nnr_p,
+                         cfg->best_lr_matches != 0, hint);
+            // offsets into the partial buffers are stored as element indices first, fixed up after allocation
+            pr.rowpart = reinterpret_cast<uint2*>(row_elems);
+            pr.colpart = reinterpret_cast<uint2*>(col_elems);
+            row_elems += (size_t)pr.ntb * n1;
+            col_elems += (size_t)pr.nqb * n2;
+            for (int qb = 0; qb < pr.nqb; ++qb)
+                for (int tb = 0; tb < pr.ntb; ++tb) ws.tiles.push_back(MatchTile{2 * p + type, qb, tb});
+            if (pr.enabled) ws.max_tsplit = std::max(ws.max_tsplit, pr.tsplit);
+            ws.max_n2 = std::max(ws.max_n2, n2);
+            if (type == 0) ws.cap_pt = std::max(ws.cap_pt, n1);
+            else ws.cap_ls = std::max(ws.cap_ls, n1);
+        }
+    }
+    ws.tile_start[B] = (int32_t)ws.tiles.size();
+    ws.cap_pt = std::max(ws.cap_pt, 1);
+    ws.cap_ls = std::max(ws.cap_ls, 1);
+    ws.sort_cap = pow2_ceil_host(std::max(std::max(ws.cap_pt, ws.cap_ls), (ws.max_n2 + 1) / 2));
+    ws.feat_in_smem = k2_smem_bytes(ws.cap_pt, ws.cap_ls, ws.sort_cap, true) <= ctx->smem_optin;
+    if (!ws.feat_in_smem && k2_smem_bytes(ws.cap_pt, ws.cap_ls, ws.sort_cap, false) > ctx->smem_optin)
+        return fail(ctx, PLSTVO_E_TOO_LARGE, "frame too large for the per-pair solver's shared memory");
+    if (k1_smem_bytes(ws.max_tsplit) > ctx->smem_optin)
+        return fail(ctx, PLSTVO_E_TOO_LARGE, "train set too large for one K1 tile");
+
+    // --- device storage ---
+    CK(ctx, ws.d_pdesc1.ensure(np1 * 32));
+    CK(ctx, ws.d_pdesc2.ensure(np2 * 32));
+    CK(ctx, ws.d_ldesc1.ensure(nl1 * 32));
+    CK(ctx, ws.d_ldesc2.ensure(nl2 * 32));
+    CK(ctx, ws.d_m12p.ensure(np1 * 4));
+    CK(ctx, ws.d_m12l.ensure(nl1 * 4));
+    CK(ctx, ws.d_rowpart.ensure(row_elems * sizeof(uint2)));
+    CK(ctx, ws.d_colpart.ensure(col_elems * sizeof(uint2)));
+    CK(ctx, ws.d_problems.ensure(ws.problems.size() * sizeof(MatchProblem)));
+    CK(ctx, ws.d_tiles.ensure(ws.tiles.size() * sizeof(MatchTile)));
+    if (with_features) {
+        CK(ctx, ws.d_poff1.ensure((B + 1) * 4));
+        CK(ctx, ws.d_poff2.ensure((B + 1) * 4));
+        CK(ctx, ws.d_loff1.ensure((B + 1) * 4));
+        CK(ctx, ws.d_loff2.ensure((B + 1) * 4));
+        CK(ctx, ws.d_ptP.ensure(np1 * 24));
+        CK(ctx, ws.d_pts2.ensure(np1 * 8));
+        CK(ctx, ws.d_ptpl.ensure(np2 * 16));
+        CK(ctx, ws.d_lssP.ensure(nl1 * 24));
+        CK(ctx, ws.d_lseP.ensure(nl1 * 24));
+        CK(ctx, ws.d_lsspl.ensure(nl1 * 16));
+        CK(ctx, ws.d_lsepl.ensure(nl1 * 16));
+        CK(ctx, ws.d_lss2.ensure(nl1 * 8));
+        CK(ctx, ws.d_lslev.ensure(nl1 * 4));
+        CK(ctx, ws.d_lsle.ensure(nl2 * 24));
+        CK(ctx, ws.d_priors.ensure((size_t)B * sizeof(PlPrior)));
+        CK(ctx, ws.d_results.ensure((size_t)B * sizeof(PlPoseResult)));
+        CK(ctx, ws.d_inlp.ensure(np1));
+        CK(ctx, ws.d_inll.ensure(nl1));
+        if (!ws.feat_in_smem) {
+            ws.feat_stride = (size_t)6 * ws.cap_pt + (size_t)14 * ws.cap_ls;
+            CK(ctx, ws.d_feat.ensure((size_t)B * ws.feat_stride * sizeof(double)));
+        }
+    }
+    // --- fix up pointers, upload the plan ---
+    for (int p = 0; p < B; ++p)
+        for (int type = 0; type < 2; ++type) {
+            MatchProblem& pr = ws.problems[(size_t)2 * p + type];
+            pr.rowpart = ws.d_rowpart.as<uint2>() + reinterpret_cast<size_t>(pr.rowpart);
+            pr.colpart = ws.d_colpart.as<uint2>() + reinterpret_cast<size_t>(pr.colpart);
+            if (type == 0) {
+                pr.d1 = ws.d_pdesc1.as<uint8_t>() + (size_t)ws.p_off1[p] * 32;
+                pr.d2 = ws.d_pdesc2.as<uint8_t>() + (size_t)ws.p_off2[p] * 32;
+                pr.m12 = ws.d_m12p.as<int32_t>() + ws.p_off1[p];
+            } else {
+                pr.d1 = ws.d_ldesc1.as<uint8_t>() + (size_t)ws.l_off1[p] * 32;
+                pr.d2 = ws.d_ldesc2.as<uint8_t>() + (size_t)ws.l_off2[p] * 32;
+                pr.m12 = ws.d_m12l.as<int32_t>() + ws.l_off1[p];
+            }
+        }
+    cudaStream_t s = ctx->s_h2d;
+    if (!ws.problems.empty())
+        CK(ctx, cudaMemcpyAsync(ws.d_problems.p, ws.problems.data(), ws.problems.size() * sizeof(MatchProblem),
+                                cudaMemcpyHostToDevice, s));
+    if (!ws.tiles.empty())
+        CK(ctx, cudaMemcpyAsync(ws.d_tiles.p, ws.tiles.data(), ws.tiles.size() * sizeof(MatchTile),
+                                cudaMemcpyHostToDevice, s));
+    if (with_features) {
+        CK(ctx, cudaMemcpyAsync(ws.d_poff1.p, ws.p_off1.data(), (B + 1) * 4, cudaMemcpyHostToDevice, s));
+        CK(ctx, cudaMemcpyAsync(ws.d_poff2.p, ws.p_off2.data(), (B + 1) * 4, cudaMemcpyHostToDevice, s));
+        CK(ctx, cudaMemcpyAsync(ws.d_loff1.p, ws.l_off1.data(), (B + 1) * 4, cudaMemcpyHostToDevice, s));
+        CK(ctx, cudaMemcpyAsync(ws.d_loff2.p, ws.l_off2.data(), (B + 1) * 4, cudaMemcpyHostToDevice, s));
+    }
+    return 0;
+}
+
+#define H2D(ctx, dst, src, elem_bytes, first, count, stream)                                                 \
+    do {                                                                                                     \
+        if ((count) > 0 && (src) != nullptr)                                                                 \
+            CK(ctx, cudaMemcpyAsync((dst).as<uint8_t>() + (size_t)(first) * (elem_bytes),                    \
+                                    reinterpret_cast<const uint8_t*>(src) + (size_t)(first) * (elem_bytes),  \
+                                    (size_t)(count) * (elem_bytes), cudaMemcpyHostToDevice, stream));        \
+    } while (0)
+
+// descriptors (+ features when with_features) of pairs [p0, p1) host -> device
+int ws_upload_range(PlContext* ctx, Workspace& ws, const PlFrameBatch* prev, const PlFrameBatch* curr,
+                    const PlPrior* priors, int p0, int p1, bool with_features, cudaStream_t s) {
+    const int a = ws.p_off1[p0], an = ws.p_off1[p1] - a, b = ws.p_off2[p0], bn = ws.p_off2[p1] - b;
+    const int c = ws.l_off1[p0], cn = ws.l_off1[p1] - c, d = ws.l_off2[p0], dn = ws.l_off2[p1] - d;
+    H2D(ctx, ws.d_pdesc1, prev->pdesc, 32, a, an, s);
+    H2D(ctx, ws.d_pdesc2, curr->pdesc, 32, b, bn, s);
+    H2D(ctx, ws.d_ldesc1, prev->ldesc, 32, c, cn, s);
+    H2D(ctx, ws.d_ldesc2, curr->ldesc, 32, d, dn, s);
+    if (with_features) {
+        H2D(ctx, ws.d_ptP, prev->pt_P, 24, a, an, s);
+        H2D(ctx, ws.d_pts2, prev->pt_sigma2, 8, a, an, s);
+        H2D(ctx, ws.d_ptpl, curr->pt_pl, 16, b, bn, s);
+        H2D(ctx, ws.d_lssP, prev->ls_sP, 24, c, cn, s);
+        H2D(ctx, ws.d_lseP, prev->ls_eP, 24, c, cn, s);
+        H2D(ctx, ws.d_lsspl, prev->ls_spl, 16, c, cn, s);
+        H2D(ctx, ws.d_lsepl, prev->ls_epl, 16, c, cn, s);
+        H2D(ctx, ws.d_lss2, prev->ls_sigma2, 8, c, cn, s);
+        H2D(ctx, ws.d_lslev, prev->ls_level, 4, c, cn, s);
+        H2D(ctx, ws.d_lsle, curr->ls_le, 24, d, dn, s);
+        if (priors) H2D(ctx, ws.d_priors, priors, sizeof(PlPrior), p0, p1 - p0, s);
+    }
+    return 0;
+}
+
+int ws_launch_match(PlContext* ctx, Workspace& ws, int p0, int p1, cudaStream_t s) {
+    const int t0 = ws.tile_start[p0], t1 = ws.tile_start[p1];
+    if (t1 > t0) {
+        CK(ctx, launch_hamming_knn2(ws.d_problems.as<MatchProblem>(), ws.d_tiles.as<MatchTile>() + t0, t1 - t0,
+                                    ws.max_tsplit, s));
+        ctx->launches++;
+    }
+    return 0;
+}
+
+int ws_launch_solve(PlContext* ctx, Workspace& ws, int p0, int p1, bool have_level, cudaStream_t s) {
+    if (p1 <= p0) return 0;
+    SolveParams prm{};
+    prm.cam = ws.cam;
+    prm.cfg = ws.cfg;
+    prm.mode = 0;
+    prm.first_pair = p0;
+    prm.prev = FrameDev{ws.d_poff1.as<int32_t>(), ws.d_loff1.as<int32_t>(), nullptr, nullptr,
+                        ws.d_ptP.as<double>(), nullptr, ws.d_pts2.as<double>(), ws.d_lssP.as<double>(),
+                        ws.d_lseP.as<double>(), nullptr, ws.d_lsspl.as<double>(), ws.d_lsepl.as<double>(),
+                        ws.d_lss2.as<double>(), have_level ? ws.d_lslev.as<int32_t>() : nullptr};
+    prm.curr = FrameDev{ws.d_poff2.as<int32_t>(), ws.d_loff2.as<int32_t>(), nullptr, nullptr, nullptr,
+                        ws.d_ptpl.as<double>(), nullptr, nullptr, nullptr, ws.d_lsle.as<double>(), nullptr,
+                        nullptr, nullptr, nullptr};
+    prm.problems = ws.d_problems.as<MatchProblem>();
+    prm.priors = ws.has_priors ? ws.d_priors.as<PlPrior>() : nullptr;
+    prm.results = ws.d_results.as<PlPoseResult>();
+    prm.inlier_pt = ws.d_inlp.as<uint8_t>();
+    prm.inlier_ls = ws.d_inll.as<uint8_t>();
+    prm.feat_scratch = ws.feat_in_smem ? nullptr : ws.d_feat.as<double>() + (size_t)p0 * ws.feat_stride;
+    prm.feat_scratch_stride = ws.feat_stride;
+    prm.cap_pt = ws.cap_pt;
+    prm.cap_ls = ws.cap_ls;
+    prm.sort_cap = ws.sort_cap;
+    prm.feat_in_smem = ws.feat_in_smem ? 1 : 0;
+    CK(ctx, launch_track_solve(prm, p1 - p0, s));
+    ctx->launches++;
+    return 0;
+}
+
+#define D2H(ctx, dst, src, elem_bytes, first, count, stream)                                                 \
+    do {                                                                                                     \
+        if ((count) > 0 && (dst) != nullptr)                                                                 \
+            CK(ctx, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(dst) + (size_t)(first) * (elem_bytes),        \
+                                    (src).as<uint8_t>() + (size_t)(first) * (elem_bytes),                    \
+                                    (size_t)(count) * (elem_bytes), cudaMemcpyDeviceToHost, stream));        \
+    } while (0)
+
+int ws_download_range(PlContext* ctx, Workspace& ws, int p0, int p1, PlPoseResult* results, int32_t* m12_pt,
+                      int32_t* m12_ls, uint8_t* inl_pt, uint8_t* inl_ls, cudaStream_t s) {
+    const int a = ws.p_off1[p0], an = ws.p_off1[p1] - a, c = ws.l_off1[p0], cn = ws.l_off1[p1] - c;
+    D2H(ctx, results, ws.d_results, sizeof(PlPoseResult), p0, p1 - p0, s);
+    D2H(ctx, m12_pt, ws.d_m12p, 4, a, an, s);
+    D2H(ctx, m12_ls, ws.d_m12l, 4, c, cn, s);
+    D2H(ctx, inl_pt, ws.d_inlp, 1, a, an, s);
+    D2H(ctx, inl_ls, ws.d_inll, 1, c, cn, s);
+    return 0;
+}
+
+int pick_chunk(const Workspace& ws, int sm_count) {
+    // pairs per pipeline chunk: enough K2 CTAs to cover about half the chip, at least 8 chunks per big batch
+    int chunk = std::max(1, sm_count / 2);
+    if (ws.B < chunk) chunk = std::max(1, ws.B);
+    return chunk;
+}
+
+// resident pass: K1 / K2 over the whole batch, chunked over two streams so that the (latency-bound) per-pair
+// solver of chunk i overlaps the (throughput-bound) distance tiles of chunk i+1
+int ws_run(PlContext* ctx, Workspace& ws, bool have_level) {
+    if (ws.B == 0) return 0;
+    const int chunk = std::max(pick_chunk(ws, ctx->sm_count), ctx->sm_count);
+    cudaEvent_t start = next_event(ctx);
+    CK(ctx, cudaEventRecord(start, ctx->s_main));
+    CK(ctx, cudaStreamWaitEvent(ctx->s_alt, start, 0));
+    int k = 0;
+    for (int p0 = 0; p0 < ws.B; p0 += chunk, ++k) {
+        const int p1 = std::min(ws.B, p0 + chunk);
+        cudaStream_t s = (k & 1) ? ctx->s_alt : ctx->s_main;
+        int rc = ws_launch_match(ctx, ws, p0, p1, s);
+        if (rc) return rc;
+        rc = ws_launch_solve(ctx, ws, p0, p1, have_level, s);
+        if (rc) return rc;
+    }
+    cudaEvent_t done = next_event(ctx);
+    CK(ctx, cudaEventRecord(done, ctx->s_alt));
+    CK(ctx, cudaStreamWaitEvent(ctx->s_main, done, 0));
+    return 0;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int plstvo_version(void) { return PLSTVO_VERSION; }
+
+int plstvo_create(int device, PlContext** out) {
+    if (!out) return PLSTVO_E_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return PLSTVO_E_NO_DEVICE;
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) return PLSTVO_E_NO_DEVICE;
+    }
+    if (device >= n) return PLSTVO_E_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PLSTVO_E_NO_DEVICE;
+    if (prop.major != 10) return PLSTVO_E_NO_DEVICE;   // the kernels are built for sm_100a only
+    if (cudaSetDevice(device) != cudaSuccess) return PLSTVO_E_NO_DEVICE;
+    PlContext* ctx = new PlContext();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    cudaStreamCreateWithFlags(&ctx->s_main, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->s_alt, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking);
+    *out = ctx;
+    return 0;
+}
+
+void plstvo_destroy(PlContext* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    ctx->ws.release();
+    ctx->scratch.release();
+    for (auto& b : ctx->gn_in) b.release();
+    for (auto& b : ctx->gn_out) b.release();
+    for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->s_main);
+    cudaStreamDestroy(ctx->s_alt);
+    cudaStreamDestroy(ctx->s_h2d);
+    cudaStreamDestroy(ctx->s_d2h);
+    delete ctx;
+}
+
+const char* plstvo_last_error(const PlContext* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+void plstvo_default_config(PlConfig* c) {   // src/config.cpp:36-113
+    c->has_points = 1; c->has_lines = 1; c->best_lr_matches = 1; c->use_motion_model = 0;
+    c->min_features = 10; c->max_iters = 5; c->max_iters_ref = 10; c->solver_mode = 0;
+    c->min_ratio_12_p = 0.9; c->min_ratio_12_l = 0.9; c->homog_th = 1e-7; c->min_error = 1e-7;
+    c->min_error_change = 1e-7; c->inlier_k = 4.0; c->lsd_scale = 1.2;
+}
+
+void plstvo_kitti_config(PlConfig* c) {   // config/config/config_kitti.yaml:19,27,45
+    plstvo_default_config(c);
+    c->min_ratio_12_p = 0.75;
+    c->min_ratio_12_l = 0.75;
+    c->inlier_k = 1.2;
+}
+
+int plstvo_synchronize(PlContext* ctx) {
+    if (!ctx) return PLSTVO_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->s_h2d));
+    CK(ctx, cudaStreamSynchronize(ctx->s_main));
+    CK(ctx, cudaStreamSynchronize(ctx->s_alt));
+    CK(ctx, cudaStreamSynchronize(ctx->s_d2h));
+    ctx->next_event = 0;
+    return 0;
+}
+
+void* plstvo_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+void plstvo_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int64_t plstvo_launch_count(const PlContext* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- matching.h surface -------------------------------------------------------------------------------
+int plstvo_match_batch(PlContext* ctx, int B, const uint8_t* d1, const int32_t* off1, const uint8_t* d2,
+                       const int32_t* off2, float nnr, int best_lr_matches, int32_t* m12, int32_t* counts) {
+    if (!ctx) return PLSTVO_E_INVALID;
+    if (B < 0 || (B > 0 && (!off1 || !off2 || !m12))) return fail(ctx, PLSTVO_E_INVALID, "bad arguments");
+    if (B == 0) return 0;
+    CK(ctx, cudaSetDevice(ctx->device));
+    // express the problems as a points-only frame batch
+    std::vector<int32_t> zeros((size_t)B + 1, 0);
+    PlFrameBatch a{}, b{};
+    a.B = b.B = B;
+    a.pt_off = off1; b.pt_off = off2;
+    a.ls_off = b.ls_off = zeros.data();
+    a.pdesc = d1; b.pdesc = d2;
+    int rc = validate_frames(ctx, &a, &b, false);
+    if (rc) return rc;
+    PlConfig cfg;
+    plstvo_default_config(&cfg);
+    cfg.has_lines = 0;
+    cfg.best_lr_matches = best_lr_matches;
+    Workspace& ws = ctx->ws;
+    rc = ws_prepare(ctx, ws, nullptr, &cfg, &a, &b, false, false);
+    if (rc) return rc;
+    for (auto& pr : ws.problems) pr.nnr = nnr;   // the caller's float, not the config's double
+    CK(ctx, cudaMemcpyAsync(ws.d_problems.p, ws.problems.data(), ws.problems.size() * sizeof(MatchProblem),
+                            cudaMemcpyHostToDevice, ctx->s_h2d));
+    rc = ws_upload_range(ctx, ws, &a, &b, nullptr, 0, B, false, ctx->s_h2d);
+    if (rc) return rc;
+    cudaEvent_t up = next_event(ctx);
+    CK(ctx, cudaEventRecord(up, ctx->s_h2d));
+    CK(ctx, cudaStreamWaitEvent(ctx->s_main, up, 0));
+    rc = ws_launch_match(ctx, ws, 0, B, ctx->s_main);
+    if (rc) return rc;
+    // finalize only the point problems (even indices): compact view
+    CK(ctx, ctx->scratch.ensure((size_t)B * (sizeof(MatchProblem) + 4)));
+    std::vector<MatchProblem> pts((size_t)B);
+    for (int p = 0; p < B; ++p) pts[p] = ws.problems[(size_t)2 * p];
+    MatchProblem* d_pts = ctx->scratch.as<MatchProblem>();
+    int32_t* d_counts = reinterpret_cast<int32_t*>(d_pts + B);
+    CK(ctx, cudaMemcpyAsync(d_pts, pts.data(), (size_t)B * sizeof(MatchProblem), cudaMemcpyHostToDevice, ctx->s_main));
+    CK(ctx, launch_match_finalize(d_pts, B, ws.max_n2, d_counts, ctx->s_main));
+    ctx->launches++;
+    CK(ctx, cudaMemcpyAsync(m12, ws.d_m12p.p, (size_t)off1[B] * 4, cudaMemcpyDeviceToHost, ctx->s_main));
+    std::vector<int32_t> cnt((size_t)B);
+    CK(ctx, cudaMemcpyAsync(cnt.data(), d_counts, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->s_main));
+    CK(ctx, cudaStreamSynchronize(ctx->s_main));
+    ctx->next_event = 0;
+    long total = 0;
+    for (int p = 0; p < B; ++p) {
+        if (counts) counts[p] = cnt[p];
+        total += cnt[p];
+    }
+    return (int)total;
+}
+
+int plstvo_match(PlContext* ctx, const uint8_t* d1, int n1, const uint8_t* d2, int n2, int stride_bytes,
+                 float nnr, int best_lr_matches, int32_t* m12) {
+    if (!ctx) return PLSTVO_E_INVALID;
+    if (stride_bytes != PLSTVO_DESC_BYTES) return fail(ctx, PLSTVO_E_INVALID, "descriptor rows must be 32 contiguous bytes");
+    if (n1 < 0 || n2 < 0) return fail(ctx, PLSTVO_E_INVALID, "negative row count");
+    if (n1 == 0) return 0;
+    if (!m12) return fail(ctx, PLSTVO_E_INVALID, "null output");
+    const int32_t o1[2] = {0, n1}, o2[2] = {0, n2};
+    return plstvo_match_batch(ctx, 1, d1, o1, d2, o2, nnr, best_lr_matches, m12, nullptr);
+}
+
+int plstvo_match_nnr(PlContext* ctx, const uint8_t* d1, int n1, const uint8_t* d2, int n2, int stride_bytes,
+                     float nnr, int32_t* m12) {
+    return plstvo_match(ctx, d1, n1, d2, n2, stride_bytes, nnr, 0, m12);
+}
+
+// ---- stereoFrameHandler.h surface ------------------------------------------------------------------------
+int plstvo_f2f_tracking(PlContext* ctx, const PlConfig* cfg, const PlFrameBatch* prev, const PlFrameBatch* curr,
+                        int32_t* m12_pt, int32_t* m12_ls, int32_t* n_matched) {
+    if (!ctx || !cfg) return PLSTVO_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc = validate_frames(ctx, prev, curr, false);
+    if (rc) return rc;
+    const int B = prev->B;
+    if (B == 0) return 0;
+    Workspace& ws = ctx->ws;
+    rc = ws_prepare(ctx, ws, nullptr, cfg, prev, curr, false, false);
+    if (rc) return rc;
+    rc = ws_upload_range(ctx, ws, prev, curr, nullptr, 0, B, false, ctx->s_h2d);
+    if (rc) return rc;
+    cudaEvent_t up = next_event(ctx);
+    CK(ctx, cudaEventRecord(up, ctx->s_h2d));
+    CK(ctx, cudaStreamWaitEvent(ctx->s_main, up, 0));
+    rc = ws_launch_match(ctx, ws, 0, B, ctx->s_main);
+    if (rc) return rc;
+    CK(ctx, ctx->scratch.ensure((size_t)2 * B * 4));
+    CK(ctx, launch_match_finalize(ws.d_problems.as<MatchProblem>(), 2 * B, ws.max_n2, ctx->scratch.as<int32_t>(),
+                                  ctx->s_main));
+    ctx->launches++;
+    if (m12_pt && prev->pt_off[B])
+        CK(ctx, cudaMemcpyAsync(m12_pt, ws.d_m12p.p, (size_t)prev->pt_off[B] * 4, cudaMemcpyDeviceToHost, ctx->s_main));
+    if (m12_ls && prev->ls_off[B])
+        CK(ctx, cudaMemcpyAsync(m12_ls, ws.d_m12l.p, (size_t)prev->ls_off[B] * 4, cudaMemcpyDeviceToHost, ctx->s_main));
+    if (n_matched)
+        CK(ctx, cudaMemcpyAsync(n_matched, ctx->scratch.p, (size_t)2 * B * 4, cudaMemcpyDeviceToHost, ctx->s_main));
+    CK(ctx, cudaStreamSynchronize(ctx->s_main));
+    ctx->next_event = 0;
+    return 0;
+}
+
+int plstvo_optimize_pose(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlMatchedBatch* m,
+                         const PlPrior* priors, PlPoseResult* results, uint8_t* inlier_pt, uint8_t* inlier_ls) {
+    if (!ctx || !cam || !cfg || !m || !results) return PLSTVO_E_INVALID;
+    const int B = m->B;
+    if (B < 0) return fail(ctx, PLSTVO_E_INVALID, "negative batch size");
+    if (B == 0) return 0;
+    if (!m->pt_off || !m->ls_off) return fail(ctx, PLSTVO_E_INVALID, "null offsets");
+    CK(ctx, cudaSetDevice(ctx->device));
+    int cap_pt = 1, cap_ls = 1;
+    for (int p = 0; p < B; ++p) {
+        const int n = m->pt_off[p + 1] - m->pt_off[p], l = m->ls_off[p + 1] - m->ls_off[p];
+        if (n < 0 || l < 0) return fail(ctx, PLSTVO_E_INVALID, "offsets are not non-decreasing");
+        if (n > PLSTVO_MAX_FEATURES || l > PLSTVO_MAX_FEATURES) return fail(ctx, PLSTVO_E_TOO_LARGE, "list too long");
+        cap_pt = std::max(cap_pt, n);
+        cap_ls = std::max(cap_ls, l);
+    }
+    const size_t n = m->pt_off[B], l = m->ls_off[B];
+    if (n && (!m->pt_P || !m->pt_pl_obs || !m->pt_sigma2)) return fail(ctx, PLSTVO_E_INVALID, "point arrays missing");
+    if (l && (!m->ls_sP || !m->ls_eP || !m->ls_le_obs || !m->ls_spl || !m->ls_epl || !m->ls_sigma2))
+        return fail(ctx, PLSTVO_E_INVALID, "line arrays missing");
+    const int sort_cap = pow2_ceil_host(std::max(cap_pt, cap_ls));
+    bool in_smem = k2_smem_bytes(cap_pt, cap_ls, sort_cap, true) <= ctx->smem_optin;
+    if (!in_smem && k2_smem_bytes(cap_pt, cap_ls, sort_cap, false) > ctx->smem_optin)
+        return fail(ctx, PLSTVO_E_TOO_LARGE, "lists too long for the per-pair solver's shared memory");
+
+    Workspace& ws = ctx->ws;
+    cudaStream_t s = ctx->s_main;
+    struct Up { DevBuf* buf; const void* src; size_t bytes; };
+    Up ups[] = {{&ws.d_poff1, m->pt_off, (size_t)(B + 1) * 4}, {&ws.d_loff1, m->ls_off, (size_t)(B + 1) * 4},
+                {&ws.d_ptP, m->pt_P, n * 24}, {&ws.d_ptpl, m->pt_pl_obs, n * 16}, {&ws.d_pts2, m->pt_sigma2, n * 8},
+                {&ws.d_inlp, m->pt_inlier, n}, {&ws.d_lssP, m->ls_sP, l * 24}, {&ws.d_lseP, m->ls_eP, l * 24},
+                {&ws.d_lsle, m->ls_le_obs, l * 24}, {&ws.d_lsspl, m->ls_spl, l * 16}, {&ws.d_lsepl, m->ls_epl, l * 16},
+                {&ws.d_lss2, m->ls_sigma2, l * 8}, {&ws.d_inll, m->ls_inlier, l}};
+    for (auto& u : ups) {
+        CK(ctx, u.buf->ensure(std::max<size_t>(u.bytes, 16)));
+        if (u.src && u.bytes) CK(ctx, cudaMemcpyAsync(u.buf->p, u.src, u.bytes, cudaMemcpyHostToDevice, s));
+    }
+    CK(ctx, ws.d_results.ensure((size_t)B * sizeof(PlPoseResult)));
+    CK(ctx, ws.d_priors.ensure((size_t)B * sizeof(PlPrior)));
+    if (priors) CK(ctx, cudaMemcpyAsync(ws.d_priors.p, priors, (size_t)B * sizeof(PlPrior), cudaMemcpyHostToDevice, s));
+    // output flags live in separate buffers (the input flags are read while the outputs are written)
+    CK(ctx, ctx->gn_out[0].ensure(std::max<size_t>(n, 16)));
+    CK(ctx, ctx->gn_out[1].ensure(std::max<size_t>(l, 16)));
+    size_t stride = 0;
+    if (!in_smem) {
+        stride = (size_t)6 * cap_pt + (size_t)14 * cap_ls;
+        CK(ctx, ws.d_feat.ensure((size_t)B * stride * sizeof(double)));
+    }
+    SolveParams prm{};
+    prm.cam = *cam;
+    prm.cfg = *cfg;
+    prm.mode = 1;
+    prm.first_pair = 0;
+    prm.matched = MatchedDev{ws.d_poff1.as<int32_t>(), ws.d_loff1.as<int32_t>(), ws.d_ptP.as<double>(),
+                             ws.d_ptpl.as<double>(), ws.d_pts2.as<double>(),
+                             m->pt_inlier ? ws.d_inlp.as<uint8_t>() : nullptr, ws.d_lssP.as<double>(),
+                             ws.d_lseP.as<double>(), ws.d_lsle.as<double>(), ws.d_lsspl.as<double>(),
+                             ws.d_lsepl.as<double>(), ws.d_lss2.as<double>(),
+                             m->ls_inlier ? ws.d_inll.as<uint8_t>() : nullptr};
+    prm.priors = priors ? ws.d_priors.as<PlPrior>() : nullptr;
+    prm.results = ws.d_results.as<PlPoseResult>();
+    prm.inlier_pt = ctx->gn_out[0].as<uint8_t>();
+    prm.inlier_ls = ctx->gn_out[1].as<uint8_t>();
+    prm.feat_scratch = in_smem ? nullptr : ws.d_feat.as<double>();
+    prm.feat_scratch_stride = stride;
+    prm.cap_pt = cap_pt;
+    prm.cap_ls = cap_ls;
+    prm.sort_cap = sort_cap;
+    prm.feat_in_smem = in_smem ? 1 : 0;
+    CK(ctx, launch_track_solve(prm, B, s));
+    ctx->launches++;
+    CK(ctx, cudaMemcpyAsync(results, ws.d_results.p, (size_t)B * sizeof(PlPoseResult), cudaMemcpyDeviceToHost, s));
+    if (inlier_pt && n) CK(ctx, cudaMemcpyAsync(inlier_pt, ctx->gn_out[0].p, n, cudaMemcpyDeviceToHost, s));
+    if (inlier_ls && l) CK(ctx, cudaMemcpyAsync(inlier_ls, ctx->gn_out[1].p, l, cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaStreamSynchronize(s));
+    return 0;
+}
+
+int plstvo_track_batch(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlFrameBatch* prev,
+                       const PlFrameBatch* curr, const PlPrior* priors, PlPoseResult* results, int32_t* m12_pt,
+                       int32_t* m12_ls, uint8_t* inlier_pt, uint8_t* inlier_ls) {
+    if (!ctx || !cam || !cfg) return PLSTVO_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc = validate_frames(ctx, prev, curr, true);
+    if (rc) return rc;
+    const int B = prev->B;
+    if (B == 0) return 0;
+    Workspace& ws = ctx->ws;
+    rc = ws_prepare(ctx, ws, cam, cfg, prev, curr, true, priors != nullptr);
+    if (rc) return rc;
+    const bool have_level = prev->ls_level != nullptr;
+    const int chunk = pick_chunk(ws, ctx->sm_count);
+    int k = 0;
+    for (int p0 = 0; p0 < B; p0 += chunk, ++k) {
+        const int p1 = std::min(B, p0 + chunk);
+        rc = ws_upload_range(ctx, ws, prev, curr, priors, p0, p1, true, ctx->s_h2d);
+        if (rc) return rc;
+        cudaEvent_t up = next_event(ctx);
+        CK(ctx, cudaEventRecord(up, ctx->s_h2d));
+        cudaStream_t s = (k & 1) ? ctx->s_alt : ctx->s_main;
+        CK(ctx, cudaStreamWaitEvent(s, up, 0));
+        rc = ws_launch_match(ctx, ws, p0, p1, s);
+        if (rc) return rc;
+        rc = ws_launch_solve(ctx, ws, p0, p1, have_level, s);
+        if (rc) return rc;
+        cudaEvent_t done = next_event(ctx);
+        CK(ctx, cudaEventRecord(done, s));
+        CK(ctx, cudaStreamWaitEvent(ctx->s_d2h, done, 0));
+        rc = ws_download_range(ctx, ws, p0, p1, results, m12_pt, m12_ls, inlier_pt, inlier_ls, ctx->s_d2h);
+        if (rc) return rc;
+    }
+    CK(ctx, cudaStreamSynchronize(ctx->s_d2h));
+    CK(ctx, cudaStreamSynchronize(ctx->s_main));
+    CK(ctx, cudaStreamSynchronize(ctx->s_alt));
+    ctx->next_event = 0;
+    return 0;
+}
+
+// ---- throughput mode ----------------------------------------------------------------------------------
+int plstvo_batch_upload(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlFrameBatch* prev,
+                        const PlFrameBatch* curr, const PlPrior* priors, PlDeviceBatch** out) {
+    if (!ctx || !cam || !cfg || !out) return PLSTVO_E_INVALID;
+    *out = nullptr;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc = validate_frames(ctx, prev, curr, true);
+    if (rc) return rc;
+    PlDeviceBatch* db = new PlDeviceBatch();
+    rc = ws_prepare(ctx, db->ws, cam, cfg, prev, curr, true, priors != nullptr);
+    if (rc == 0 && prev->B > 0) rc = ws_upload_range(ctx, db->ws, prev, curr, priors, 0, prev->B, true, ctx->s_h2d);
+    if (rc == 0) {
+        cudaError_t e = cudaStreamSynchronize(ctx->s_h2d);
+        if (e != cudaSuccess) {
+            ctx->err = cudaGetErrorString(e);
+            rc = PLSTVO_E_CUDA;
+        }
+    }
+    if (rc) {
+        db->ws.release();
+        delete db;
+        return rc;
+    }
+    db->ws.have_level = prev->ls_level != nullptr;
+    *out = db;
+    return 0;
+}
+
+int plstvo_batch_run(PlContext* ctx, PlDeviceBatch* db) {
+    if (!ctx || !db) return PLSTVO_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    ctx->next_event = 0;
+    return ws_run(ctx, db->ws, db->ws.have_level);
+}
+
+int plstvo_batch_run_timed(PlContext* ctx, PlDeviceBatch* db, int iters, int flush_l2, float* ms_total) {
+    if (!ctx || !db || iters <= 0 || !ms_total) return PLSTVO_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t flush_bytes = 256u << 20;
+    if (flush_l2) CK(ctx, ctx->scratch.ensure(flush_bytes));
+    cudaEvent_t e0, e1;
+    CK(ctx, cudaEventCreate(&e0));
+    CK(ctx, cudaEventCreate(&e1));
+    double total = 0.0;
+    CK(ctx, cudaStreamSynchronize(ctx->s_main));
+    if (!flush_l2) {
+        CK(ctx, cudaEventRecord(e0, ctx->s_main));
+        for (int i = 0; i < iters; ++i) {
+            ctx->next_event = 0;
+            int rc = ws_run(ctx, db->ws, db->ws.have_level);
+            if (rc) return rc;
+        }
+        CK(ctx, cudaEventRecord(e1, ctx->s_main));
+        CK(ctx, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        total = ms;
+    } else {
+        for (int i = 0; i < iters; ++i) {
+            CK(ctx, cudaMemsetAsync(ctx->scratch.p, i & 0xFF, flush_bytes, ctx->s_main));
+            CK(ctx, cudaEventRecord(e0, ctx->s_main));
+            ctx->next_event = 0;
+            int rc = ws_run(ctx, db->ws, db->ws.have_level);
+            if (rc) return rc;
+            CK(ctx, cudaEventRecord(e1, ctx->s_main));
+            CK(ctx, cudaEventSynchronize(e1));
+            float ms = 0.f;
+            CK(ctx, cudaEventElapsedTime(&ms, e0, e1));
+            total += ms;
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    ctx->next_event = 0;
+    *ms_total = (float)total;
+    return 0;
+}
+
+int plstvo_batch_kernel_times(PlContext* ctx, PlDeviceBatch* db, int iters, double* ms_match, double* ms_solve,
+                              int32_t* n_tiles, int32_t* n_pairs) {
+    if (!ctx || !db || iters <= 0) return PLSTVO_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    Workspace& ws = db->ws;
+    cudaEvent_t e0, e1, e2;
+    CK(ctx, cudaEventCreate(&e0));
+    CK(ctx, cudaEventCreate(&e1));
+    CK(ctx, cudaEventCreate(&e2));
+    double tm = 0.0, tsv = 0.0;
+    const bool lev = ws.have_level;
+    for (int i = 0; i < iters; ++i) {
+        CK(ctx, cudaEventRecord(e0, ctx->s_main));
+        int rc = ws_launch_match(ctx, ws, 0, ws.B, ctx->s_main);
+        if (rc) return rc;
+        CK(ctx, cudaEventRecord(e1, ctx->s_main));
+        rc = ws_launch_solve(ctx, ws, 0, ws.B, lev, ctx->s_main);
+        if (rc) return rc;
+        CK(ctx, cudaEventRecord(e2, ctx->s_main));
+        CK(ctx, cudaEventSynchronize(e2));
+        float a = 0.f, b = 0.f;
+        CK(ctx, cudaEventElapsedTime(&a, e0, e1));
+        CK(ctx, cudaEventElapsedTime(&b, e1, e2));
+        tm += a;
+        tsv += b;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    if (ms_match) *ms_match = tm / iters;
+    if (ms_solve) *ms_solve = tsv / iters;
+    if (n_tiles) *n_tiles = (int32_t)ws.tiles.size();
+    if (n_pairs) *n_pairs = ws.B;
+    return 0;
+}
+
+int plstvo_batch_download(PlContext* ctx, PlDeviceBatch* db, PlPoseResult* results, int32_t* m12_pt,
+                          int32_t* m12_ls, uint8_t* inlier_pt, uint8_t* inlier_ls) {
+    if (!ctx || !db) return PLSTVO_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (db->ws.B == 0) return 0;
+    int rc = ws_download_range(ctx, db->ws, 0, db->ws.B, results, m12_pt, m12_ls, inlier_pt, inlier_ls, ctx->s_main);
+    if (rc) return rc;
+    CK(ctx, cudaStreamSynchronize(ctx->s_main));
+    return 0;
+}
+
+void plstvo_batch_free(PlContext* ctx, PlDeviceBatch* db) {
+    if (!db) return;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaDeviceSynchronize();
+    }
+    db->ws.release();
+    delete db;
+}
+
+int plstvo_popc_rate(PlContext* ctx, double* popc_per_s) {
+    if (!ctx || !popc_per_s) return PLSTVO_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * 8, iters = 20000;
+    CK(ctx, ctx->scratch.ensure((size_t)blocks * 256 * 4));
+    cudaEvent_t e0, e1;
+    CK(ctx, cudaEventCreate(&e0));
+    CK(ctx, cudaEventCreate(&e1));
+    CK(ctx, launch_popc_bench(ctx->scratch.as<uint32_t>(), 2000, blocks, ctx->s_main));   // warm-up
+    CK(ctx, cudaEventRecord(e0, ctx->s_main));
+    CK(ctx, launch_popc_bench(ctx->scratch.as<uint32_t>(), iters, blocks, ctx->s_main));
+    CK(ctx, cudaEventRecord(e1, ctx->s_main));
+    CK(ctx, cudaEventSynchronize(e1));
+    ctx->launches += 2;
+    float ms = 0.f;
+    CK(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *popc_per_s = (double)blocks * 256.0 * iters * 8.0 / (ms * 1e-3);
+    return 0;
+}
+
+int plstvo_gn_eval_stream(PlContext* ctx, const PlCamera*, const PlConfig*, const PlMatchedBatch*, const double*,
+                          int, double*, double*, double*, float*) {
+    return fail(ctx, PLSTVO_E_INVALID, "plstvo_gn_eval_stream: not built yet");
+}
+
+}  // extern "C"

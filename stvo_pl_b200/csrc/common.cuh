@@ -1,0 +1,154 @@
+// common.cuh — internal declarations shared by the sm_100a kernels and the C-ABI host code.
+// Nothing here is part of the public boundary (include/plstvo.h is).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/plstvo.h"
+
+namespace plstvo {
+
+constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;  // "no neighbour": larger than any (dist << 16 | idx) key
+
+// ---- K1 (hamming_knn2) work description -----------------------------------------------------------
+// One matching problem = StVO::match(desc1, desc2) for one feature type of one frame pair
+// (src/matching.cpp:63-91).  The N1 x N2 distance matrix is cut into nqb x ntb tiles; every tile emits
+// a row partial (top-2 over its trains for each of its queries) and a column partial (top-2 over its
+// queries for each of its trains): both directions of the mutual check from ONE pass over the distances.
+struct MatchProblem {
+    const uint8_t* d1;     // [n1][32]
+    const uint8_t* d2;     // [n2][32]
+    int32_t n1, n2;
+    int32_t nqb, ntb;      // tiles along queries / trains
+    int32_t tsplit;        // trains per tile (multiple of 32)
+    int32_t enabled;       // 0: Config::hasPoints()/hasLines() false or an empty side -> all -1, no tiles
+    uint2*  rowpart;       // [ntb][n1]  (k1,k2) packed keys (dist << 16 | train index)
+    uint2*  colpart;       // [nqb][n2]  (k1,k2) packed keys (dist << 16 | query index)
+    int32_t* m12;          // [n1] result (problem-local train index or -1)
+    float   nnr;
+    int32_t best_lr;
+};
+
+struct MatchTile {
+    int32_t problem;
+    int32_t qb;
+    int32_t tb;
+};
+
+constexpr int K1_THREADS = 256;   // = queries per tile: one query descriptor per thread, in registers
+constexpr int K1_CHUNK   = 512;   // train rows per TMA stage (16 KB)
+
+// ---- K2 (track_solve) ------------------------------------------------------------------------------
+constexpr int K2_THREADS = 512;
+constexpr int K2_WARPS   = K2_THREADS / 32;
+constexpr int ACC_N      = 28;    // 21 (upper triangle of J J^T w) + 6 (J r w) + 1 (r^2 w)
+
+// device copies of the PlFrameBatch arrays (all frames of a batch concatenated)
+struct FrameDev {
+    const int32_t* pt_off;
+    const int32_t* ls_off;
+    const uint8_t* pdesc;
+    const uint8_t* ldesc;
+    const double*  pt_P;
+    const double*  pt_pl;
+    const double*  pt_sigma2;
+    const double*  ls_sP;
+    const double*  ls_eP;
+    const double*  ls_le;
+    const double*  ls_spl;
+    const double*  ls_epl;
+    const double*  ls_sigma2;
+    const int32_t* ls_level;
+};
+
+// device copy of PlMatchedBatch (explicit matched lists)
+struct MatchedDev {
+    const int32_t* pt_off;
+    const int32_t* ls_off;
+    const double*  pt_P;
+    const double*  pt_pl_obs;
+    const double*  pt_sigma2;
+    const uint8_t* pt_inlier;
+    const double*  ls_sP;
+    const double*  ls_eP;
+    const double*  ls_le_obs;
+    const double*  ls_spl;
+    const double*  ls_epl;
+    const double*  ls_sigma2;
+    const uint8_t* ls_inlier;
+};
+
+struct SolveParams {
+    PlCamera cam;
+    PlConfig cfg;
+    int32_t  mode;            // 0: track (match partials -> mutual -> gather -> optimizePose); 1: explicit lists
+    int32_t  first_pair;      // pair index of blockIdx.x == 0
+    FrameDev prev, curr;      // mode 0
+    MatchedDev matched;       // mode 1
+    const MatchProblem* problems;   // mode 0: [2 * pair + {0: points, 1: lines}]
+    const PlPrior* priors;    // may be null
+    PlPoseResult*  results;
+    uint8_t* inlier_pt;       // mode 0: per prev feature; mode 1: per list entry
+    uint8_t* inlier_ls;
+    // feature storage: shared memory when it fits, else this global scratch (per CTA slice)
+    double*  feat_scratch;
+    size_t   feat_scratch_stride;  // doubles per CTA
+    int32_t  cap_pt, cap_ls;  // capacity of the SoA arrays (max matched features per pair in this launch)
+    int32_t  sort_cap;        // power of two >= max(cap_pt, cap_ls)
+    int32_t  feat_in_smem;
+};
+
+size_t k2_smem_bytes(int cap_pt, int cap_ls, int sort_cap, bool feat_in_smem);
+
+// kernel launchers (defined in match.cu / solve.cu)
+cudaError_t launch_hamming_knn2(const MatchProblem* problems, const MatchTile* tiles, int n_tiles,
+                                int max_tsplit, cudaStream_t stream);
+cudaError_t launch_match_finalize(const MatchProblem* problems, int n_problems, int max_n2, int32_t* counts,
+                                  cudaStream_t stream);
+cudaError_t launch_track_solve(const SolveParams& prm, int n_pairs, cudaStream_t stream);
+cudaError_t launch_popc_bench(uint32_t* out, int iters, int blocks, cudaStream_t stream);
+size_t k1_smem_bytes(int max_tsplit);
+
+// GN evaluation streamed from HBM (roofline kernel of config C5)
+cudaError_t launch_gn_eval_stream(const PlCamera& cam, const PlConfig& cfg, const MatchedDev& m, int B,
+                                  const double* DT, double* partial, int blocks_per_problem,
+                                  double* H, double* g, double* e, cudaStream_t stream);
+
+// ---- PTX helpers: mbarrier + 1-D bulk async copy (TMA engine, UBLKCP in SASS) ------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy completing on an mbarrier; addresses and size must be multiples of 16 B
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+}  // namespace plstvo

@@ -1,0 +1,180 @@
+// match.cu — K1: brute-force 256-bit Hamming 2-NN over descriptor tiles (sm_100a).
+//
+// Replaces the arithmetic of StVO::matchNNR / StVO::match (src/matching.cpp:41-91), i.e. OpenCV's
+// cv::BFMatcher(NORM_HAMMING)::knnMatch(desc1, desc2, ., 2) called once per direction.  One pass over the
+// N1 x N2 distance matrix produces BOTH directions:
+//   row    top-2 (query  -> nearest trains)  kept in registers, one query descriptor per thread;
+//   column top-2 (train  -> nearest queries) by two warp REDUX.MIN per (warp, train) on packed keys,
+//   merged across warps with shared-memory atomicMin.
+// Keys are (distance << 16 | index): unsigned min == OpenCV's ordering by (distance, trainIdx) ascending,
+// lowest index wins ties for the first and the second neighbour (SURVEY 8(c) probe; golden vectors in
+// tests/golden/match_*.npz).  Train descriptor rows are staged into shared memory by the TMA engine
+// (cp.async.bulk + mbarrier, double buffered); every thread then reads the same row (broadcast LDS.128).
+//
+// Integer work only: XOR + POPC + IADD.  No tensor cores: there is no dense contraction here.
+#include "common.cuh"
+#include "match_finalize.cuh"
+
+namespace plstvo {
+
+size_t k1_smem_bytes(int max_tsplit) {
+    return 2 * (size_t)K1_CHUNK * 32 + (size_t)max_tsplit * sizeof(uint2) + 64;
+}
+
+__device__ __forceinline__ uint32_t hamming256(const uint4& qa, const uint4& qb, const uint4& a, const uint4& b) {
+    return __popc(qa.x ^ a.x) + __popc(qa.y ^ a.y) + __popc(qa.z ^ a.z) + __popc(qa.w ^ a.w) +
+           __popc(qb.x ^ b.x) + __popc(qb.y ^ b.y) + __popc(qb.z ^ b.z) + __popc(qb.w ^ b.w);
+}
+
+__global__ void __launch_bounds__(K1_THREADS, 3)
+hamming_knn2_kernel(const MatchProblem* __restrict__ problems, const MatchTile* __restrict__ tiles) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint4* stage0 = reinterpret_cast<uint4*>(smem);
+    uint4* stage1 = reinterpret_cast<uint4*>(smem + (size_t)K1_CHUNK * 32);
+    uint2* col = reinterpret_cast<uint2*>(smem + 2 * (size_t)K1_CHUNK * 32);
+
+    const MatchTile tile = tiles[blockIdx.x];
+    const MatchProblem pr = problems[tile.problem];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int q = tile.qb * K1_THREADS + tid;
+    const bool qvalid = q < pr.n1;
+    const int t0 = tile.tb * pr.tsplit;
+    const int nt = min(pr.tsplit, pr.n2 - t0);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * (size_t)K1_CHUNK * 32 + (size_t)pr.tsplit * sizeof(uint2));
+
+    uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
+    if (qvalid) {
+        const uint4* p = reinterpret_cast<const uint4*>(pr.d1 + (size_t)q * 32);
+        qa = __ldg(p);
+        qb = __ldg(p + 1);
+    }
+    for (int i = tid; i < nt; i += K1_THREADS) col[i] = make_uint2(KEY_NONE, KEY_NONE);
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int nchunks = (nt + K1_CHUNK - 1) / K1_CHUNK;
+    const uint8_t* src = pr.d2 + (size_t)t0 * 32;
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)min(K1_CHUNK, nt) * 32u;
+        mbar_arrive_expect_tx(&bars[0], bytes);
+        bulk_g2s(stage0, src, bytes, &bars[0]);
+    }
+
+    const uint32_t qkey = qvalid ? (uint32_t)q : KEY_NONE;  // invalid lanes: OR-ing this saturates the key
+    uint32_t k1 = KEY_NONE, k2 = KEY_NONE;
+
+    for (int c = 0; c < nchunks; ++c) {
+        if (tid == 0 && c + 1 < nchunks) {  // prefetch the next stage (its buffer was released by the
+            const int rows = min(K1_CHUNK, nt - (c + 1) * K1_CHUNK);  // __syncthreads of iteration c-1)
+            uint64_t* bar = &bars[(c + 1) & 1];
+            mbar_arrive_expect_tx(bar, (uint32_t)rows * 32u);
+            bulk_g2s(((c + 1) & 1) ? stage1 : stage0, src + (size_t)(c + 1) * K1_CHUNK * 32, (uint32_t)rows * 32u, bar);
+        }
+        mbar_wait(&bars[c & 1], (uint32_t)((c >> 1) & 1));
+        const uint4* s = (c & 1) ? stage1 : stage0;
+        const int cn = min(K1_CHUNK, nt - c * K1_CHUNK);
+        const uint32_t tbase = (uint32_t)(t0 + c * K1_CHUNK);
+
+        for (int g = 0; g < cn; g += 32) {
+            const int gn = min(32, cn - g);
+            uint32_t c1 = KEY_NONE, c2 = KEY_NONE;
+#pragma unroll 4
+            for (int j = 0; j < gn; ++j) {
+                const uint4 a = s[(g + j) * 2], b = s[(g + j) * 2 + 1];
+                const uint32_t dsh = hamming256(qa, qb, a, b) << 16;
+                // row direction: this thread's query against train (tbase + g + j)
+                const uint32_t key = dsh | (tbase + (uint32_t)(g + j));
+                k2 = min(k2, max(k1, key));
+                k1 = min(k1, key);
+                // column direction: this train against the warp's 32 queries
+                const uint32_t kc = dsh | qkey;
+                const uint32_t m1 = __reduce_min_sync(0xFFFFFFFFu, kc);
+                const uint32_t m2 = __reduce_min_sync(0xFFFFFFFFu, kc == m1 ? KEY_NONE : kc);
+                if (lane == j) {
+                    c1 = m1;
+                    c2 = m2;
+                }
+            }
+            // lane j now owns the warp's top-2 for train (g + j): merge into the CTA's column state.
+            // atomicMin chain keeps the two smallest of all keys ever offered (keys are unique):
+            // whatever loses the contest for slot .x is offered to slot .y.
+            if (lane < gn && c1 != KEY_NONE) {
+                uint2* cs = &col[c * K1_CHUNK + g + lane];
+                const uint32_t old = atomicMin(&cs->x, c1);
+                atomicMin(&cs->y, max(old, c1));
+                if (c2 != KEY_NONE) atomicMin(&cs->y, c2);
+            }
+        }
+        __syncthreads();
+    }
+
+    if (qvalid) pr.rowpart[(size_t)tile.tb * pr.n1 + q] = make_uint2(k1, k2);
+    uint2* cp = pr.colpart + (size_t)tile.qb * pr.n2 + t0;
+    for (int i = tid; i < nt; i += K1_THREADS) cp[i] = col[i];
+}
+
+cudaError_t launch_hamming_knn2(const MatchProblem* problems, const MatchTile* tiles, int n_tiles,
+                                int max_tsplit, cudaStream_t stream) {
+    if (n_tiles <= 0) return cudaSuccess;
+    const size_t smem = k1_smem_bytes(max_tsplit);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(hamming_knn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    hamming_knn2_kernel<<<n_tiles, K1_THREADS, smem, stream>>>(problems, tiles);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) match_finalize_kernel(const MatchProblem* __restrict__ problems,
+                                                             int32_t* __restrict__ counts) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ int s_count;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    const MatchProblem pr = problems[blockIdx.x];
+    int c = match_finalize_block(pr, reinterpret_cast<int32_t*>(smem));
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_count, c);
+    __syncthreads();
+    if (threadIdx.x == 0 && counts) counts[blockIdx.x] = s_count;
+}
+
+cudaError_t launch_match_finalize(const MatchProblem* problems, int n_problems, int max_n2, int32_t* counts,
+                                  cudaStream_t stream) {
+    if (n_problems <= 0) return cudaSuccess;
+    const size_t smem = (size_t)(max_n2 > 0 ? max_n2 : 1) * sizeof(int32_t);
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(match_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    match_finalize_kernel<<<n_problems, 256, smem, stream>>>(problems, counts);
+    return cudaGetLastError();
+}
+
+// ---- POPC issue-rate micro-benchmark (the integer roofline the matcher is held against) -------------
+__global__ void __launch_bounds__(256) popc_bench_kernel(uint32_t* out, int iters) {
+    uint32_t x0 = threadIdx.x * 2654435761u + blockIdx.x, x1 = x0 ^ 0x9E3779B9u, x2 = x0 + 0x7F4A7C15u,
+             x3 = x1 * 3u, x4 = x0 ^ 0x12345u, x5 = x1 + 77u, x6 = x2 ^ 0xABCDEFu, x7 = x3 + 1234567u;
+    uint32_t acc = 0;
+    for (int i = 0; i < iters; ++i) {
+        // 8 independent POPCs per iteration, inputs perturbed so nothing folds
+        acc += __popc(x0) + __popc(x1) + __popc(x2) + __popc(x3) + __popc(x4) + __popc(x5) + __popc(x6) + __popc(x7);
+        x0 ^= acc; x1 += x0; x2 ^= x1; x3 += x2; x4 ^= x3; x5 += x4; x6 ^= x5; x7 += x6;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+cudaError_t launch_popc_bench(uint32_t* out, int iters, int blocks, cudaStream_t stream) {
+    popc_bench_kernel<<<blocks, 256, 0, stream>>>(out, iters);
+    return cudaGetLastError();
+}
+
+}  // namespace plstvo

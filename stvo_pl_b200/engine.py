@@ -1,0 +1,258 @@
+"""ctypes binding of the CUDA library (stvo_pl_b200/lib/libplstvo_b200.so) through its C-ABI
+(include/plstvo.h).  There is no CPU fallback: a missing extension or a missing sm_100 device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from . import types as T
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libplstvo_b200.so")
+
+ERRORS = {-1: "PLSTVO_E_INVALID", -2: "PLSTVO_E_TOO_LARGE", -3: "PLSTVO_E_CUDA", -4: "PLSTVO_E_NO_DEVICE",
+          -5: "PLSTVO_E_SIZE"}
+
+
+class PlstvoError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+def load_library(path: str = LIB_PATH) -> C.CDLL:
+    if not os.path.exists(path):
+        raise RuntimeError(f"CUDA extension missing: {path}. Build it with `python -m stvo_pl_b200.build` "
+                           "(there is no CPU fallback).")
+    L = C.CDLL(path)
+    vp, i32p, u8p, dp = C.c_void_p, T.c_int32_p, T.c_uint8_p, T.c_double_p
+    cam, cfg = C.POINTER(T.PlCamera), C.POINTER(T.PlConfig)
+    fb, mb = C.POINTER(T.PlFrameBatch), C.POINTER(T.PlMatchedBatch)
+    sig = {
+        "plstvo_version": (C.c_int, []),
+        "plstvo_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "plstvo_destroy": (None, [vp]),
+        "plstvo_last_error": (C.c_char_p, [vp]),
+        "plstvo_default_config": (None, [cfg]),
+        "plstvo_kitti_config": (None, [cfg]),
+        "plstvo_match_nnr": (C.c_int, [vp, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_float, i32p]),
+        "plstvo_match": (C.c_int, [vp, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_float, C.c_int, i32p]),
+        "plstvo_match_batch": (C.c_int, [vp, C.c_int, u8p, i32p, u8p, i32p, C.c_float, C.c_int, i32p, i32p]),
+        "plstvo_f2f_tracking": (C.c_int, [vp, cfg, fb, fb, i32p, i32p, i32p]),
+        "plstvo_optimize_pose": (C.c_int, [vp, cam, cfg, mb, vp, vp, u8p, u8p]),
+        "plstvo_track_batch": (C.c_int, [vp, cam, cfg, fb, fb, vp, vp, i32p, i32p, u8p, u8p]),
+        "plstvo_batch_upload": (C.c_int, [vp, cam, cfg, fb, fb, vp, C.POINTER(vp)]),
+        "plstvo_batch_run": (C.c_int, [vp, vp]),
+        "plstvo_batch_run_timed": (C.c_int, [vp, vp, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+        "plstvo_batch_download": (C.c_int, [vp, vp, vp, i32p, i32p, u8p, u8p]),
+        "plstvo_batch_free": (None, [vp, vp]),
+        "plstvo_synchronize": (C.c_int, [vp]),
+        "plstvo_host_alloc": (vp, [C.c_size_t]),
+        "plstvo_host_free": (None, [vp]),
+        "plstvo_launch_count": (C.c_int64, [vp]),
+        "plstvo_batch_kernel_times": (C.c_int, [vp, vp, C.c_int, dp, dp, i32p, i32p]),
+        "plstvo_gn_eval_stream": (C.c_int, [vp, cam, cfg, mb, dp, C.c_int, dp, dp, dp, C.POINTER(C.c_float)]),
+        "plstvo_popc_rate": (C.c_int, [vp, dp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)   # AttributeError if the library does not export a declared symbol
+        fn.restype, fn.argtypes = res, args
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "plstvo_version", "plstvo_create", "plstvo_destroy", "plstvo_last_error", "plstvo_default_config",
+    "plstvo_kitti_config", "plstvo_match_nnr", "plstvo_match", "plstvo_match_batch", "plstvo_f2f_tracking",
+    "plstvo_optimize_pose", "plstvo_track_batch", "plstvo_batch_upload", "plstvo_batch_run",
+    "plstvo_batch_run_timed", "plstvo_batch_download", "plstvo_batch_free", "plstvo_synchronize",
+    "plstvo_host_alloc", "plstvo_host_free", "plstvo_launch_count", "plstvo_batch_kernel_times",
+    "plstvo_gn_eval_stream", "plstvo_popc_rate"]
+
+
+def _p(a: Optional[np.ndarray], typ):
+    return C.cast(None, typ) if a is None else a.ctypes.data_as(typ)
+
+
+class PinnedPool:
+    """Pinned host arrays (cudaMallocHost) so that H2D/D2H run at full PCIe rate without staging."""
+
+    def __init__(self, lib):
+        self.lib = lib
+        self._ptrs = []
+
+    def empty(self, shape, dtype) -> np.ndarray:
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        ptr = self.lib.plstvo_host_alloc(max(n, 1))
+        if not ptr:
+            raise MemoryError("cudaMallocHost failed")
+        self._ptrs.append(ptr)
+        buf = (C.c_uint8 * max(n, 1)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def copy(self, a: Optional[np.ndarray]) -> Optional[np.ndarray]:
+        if a is None:
+            return None
+        out = self.empty(a.shape, a.dtype)
+        out[...] = a
+        return out
+
+    def pin_frames(self, f: T.FrameBatch) -> T.FrameBatch:
+        return T.FrameBatch(**{k: self.copy(getattr(f, k)) for k in (
+            "pt_off", "ls_off", "pdesc", "ldesc", "pt_P", "pt_pl", "pt_sigma2", "ls_sP", "ls_eP", "ls_le",
+            "ls_spl", "ls_epl", "ls_sigma2", "ls_level")})
+
+    def close(self):
+        for p in self._ptrs:
+            self.lib.plstvo_host_free(p)
+        self._ptrs = []
+
+
+class DeviceBatch:
+    """Inputs resident in HBM (PlDeviceBatch)."""
+
+    def __init__(self, eng: "Engine", handle, prev: T.FrameBatch):
+        self.eng, self.handle = eng, handle
+        self.B, self.n_pt, self.n_ls = prev.B, prev.n_pt, prev.n_ls
+
+    def run(self):
+        self.eng._ck(self.eng.lib.plstvo_batch_run(self.eng.ctx, self.handle))
+
+    def run_timed(self, iters: int, flush_l2: bool = False) -> float:
+        ms = C.c_float(0)
+        self.eng._ck(self.eng.lib.plstvo_batch_run_timed(self.eng.ctx, self.handle, iters, int(flush_l2), C.byref(ms)))
+        return float(ms.value)
+
+    def kernel_times(self, iters: int = 3):
+        a, b = np.zeros(1), np.zeros(1)
+        nt, npairs = np.zeros(1, np.int32), np.zeros(1, np.int32)
+        self.eng._ck(self.eng.lib.plstvo_batch_kernel_times(
+            self.eng.ctx, self.handle, iters, a.ctypes.data_as(T.c_double_p), b.ctypes.data_as(T.c_double_p),
+            nt.ctypes.data_as(T.c_int32_p), npairs.ctypes.data_as(T.c_int32_p)))
+        return dict(ms_match=float(a[0]), ms_solve=float(b[0]), n_tiles=int(nt[0]), n_pairs=int(npairs[0]))
+
+    def download(self):
+        res = np.zeros(self.B, dtype=T.POSE_RESULT_DTYPE)
+        m12_pt, m12_ls = np.full(self.n_pt, -1, np.int32), np.full(self.n_ls, -1, np.int32)
+        inl_pt, inl_ls = np.zeros(self.n_pt, np.uint8), np.zeros(self.n_ls, np.uint8)
+        self.eng._ck(self.eng.lib.plstvo_batch_download(
+            self.eng.ctx, self.handle, res.ctypes.data, _p(m12_pt, T.c_int32_p), _p(m12_ls, T.c_int32_p),
+            _p(inl_pt, T.c_uint8_p), _p(inl_ls, T.c_uint8_p)))
+        return dict(results=res, m12_pt=m12_pt, m12_ls=m12_ls, inlier_pt=inl_pt, inlier_ls=inl_ls)
+
+    def free(self):
+        if self.handle:
+            self.eng.lib.plstvo_batch_free(self.eng.ctx, self.handle)
+            self.handle = None
+
+
+class Engine:
+    """One PlContext (one GPU)."""
+
+    def __init__(self, device: int = -1):
+        self.lib = load_library()
+        ctx = C.c_void_p()
+        rc = self.lib.plstvo_create(device, C.byref(ctx))
+        if rc != 0:
+            raise PlstvoError(rc, "plstvo_create failed: no sm_100 CUDA device visible (no CPU fallback exists)")
+        self.ctx = ctx
+        self.pinned = PinnedPool(self.lib)
+
+    def close(self):
+        if self.ctx:
+            self.pinned.close()
+            self.lib.plstvo_destroy(self.ctx)
+            self.ctx = None
+
+    def _ck(self, rc: int) -> int:
+        if rc < 0:
+            raise PlstvoError(rc, (self.lib.plstvo_last_error(self.ctx) or b"").decode())
+        return rc
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.plstvo_launch_count(self.ctx))
+
+    # ---- matching.h surface ----
+    def match_nnr(self, d1, d2, nnr):
+        d1, d2 = np.ascontiguousarray(d1, np.uint8).reshape(-1, 32), np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
+        m12 = np.full(len(d1), -1, np.int32)
+        n = self._ck(self.lib.plstvo_match_nnr(self.ctx, _p(d1, T.c_uint8_p), len(d1), _p(d2, T.c_uint8_p), len(d2),
+                                               32, C.c_float(nnr), _p(m12, T.c_int32_p)))
+        return n, m12
+
+    def match(self, d1, d2, nnr, best_lr=True):
+        d1, d2 = np.ascontiguousarray(d1, np.uint8).reshape(-1, 32), np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
+        m12 = np.full(len(d1), -1, np.int32)
+        n = self._ck(self.lib.plstvo_match(self.ctx, _p(d1, T.c_uint8_p), len(d1), _p(d2, T.c_uint8_p), len(d2), 32,
+                                           C.c_float(nnr), int(best_lr), _p(m12, T.c_int32_p)))
+        return n, m12
+
+    def match_batch(self, d1, off1, d2, off2, nnr, best_lr=True):
+        d1, d2 = np.ascontiguousarray(d1, np.uint8).reshape(-1, 32), np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
+        off1, off2 = np.ascontiguousarray(off1, np.int32), np.ascontiguousarray(off2, np.int32)
+        B = len(off1) - 1
+        m12 = np.full(len(d1), -1, np.int32)
+        counts = np.zeros(B, np.int32)
+        n = self._ck(self.lib.plstvo_match_batch(self.ctx, B, _p(d1, T.c_uint8_p), _p(off1, T.c_int32_p),
+                                                 _p(d2, T.c_uint8_p), _p(off2, T.c_int32_p), C.c_float(nnr),
+                                                 int(best_lr), _p(m12, T.c_int32_p), _p(counts, T.c_int32_p)))
+        return n, m12, counts
+
+    # ---- stereoFrameHandler.h surface ----
+    def f2f_tracking(self, cfg, prev: T.FrameBatch, curr: T.FrameBatch):
+        m12_pt, m12_ls = np.full(prev.n_pt, -1, np.int32), np.full(prev.n_ls, -1, np.int32)
+        n = np.zeros((prev.B, 2), np.int32)
+        pc, cc = prev.as_c(), curr.as_c()
+        self._ck(self.lib.plstvo_f2f_tracking(self.ctx, C.byref(cfg), C.byref(pc), C.byref(cc),
+                                              _p(m12_pt, T.c_int32_p), _p(m12_ls, T.c_int32_p), _p(n, T.c_int32_p)))
+        return m12_pt, m12_ls, n
+
+    def optimize_pose(self, cam, cfg, matched: T.MatchedBatch, priors=None):
+        res = np.zeros(matched.B, dtype=T.POSE_RESULT_DTYPE)
+        inl_pt = np.zeros(int(matched.pt_off[-1]), np.uint8)
+        inl_ls = np.zeros(int(matched.ls_off[-1]), np.uint8)
+        mc = matched.as_c()
+        self._ck(self.lib.plstvo_optimize_pose(self.ctx, C.byref(cam), C.byref(cfg), C.byref(mc),
+                                               priors.ctypes.data if priors is not None else None, res.ctypes.data,
+                                               _p(inl_pt, T.c_uint8_p), _p(inl_ls, T.c_uint8_p)))
+        return res, inl_pt, inl_ls
+
+    def track_batch(self, cam, cfg, prev: T.FrameBatch, curr: T.FrameBatch, priors=None, out=None):
+        """insertStereoPair's f2fTracking + optimizePose for B pairs, host buffers in / out."""
+        if out is None:
+            out = dict(results=np.zeros(prev.B, dtype=T.POSE_RESULT_DTYPE),
+                       m12_pt=np.full(prev.n_pt, -1, np.int32), m12_ls=np.full(prev.n_ls, -1, np.int32),
+                       inlier_pt=np.zeros(prev.n_pt, np.uint8), inlier_ls=np.zeros(prev.n_ls, np.uint8))
+        pc, cc = prev.as_c(), curr.as_c()
+        self._ck(self.lib.plstvo_track_batch(
+            self.ctx, C.byref(cam), C.byref(cfg), C.byref(pc), C.byref(cc),
+            priors.ctypes.data if priors is not None else None, out["results"].ctypes.data,
+            _p(out["m12_pt"], T.c_int32_p), _p(out["m12_ls"], T.c_int32_p), _p(out["inlier_pt"], T.c_uint8_p),
+            _p(out["inlier_ls"], T.c_uint8_p)))
+        return out
+
+    def pinned_outputs(self, prev: T.FrameBatch):
+        e = self.pinned.empty
+        return dict(results=e((prev.B,), T.POSE_RESULT_DTYPE), m12_pt=e((prev.n_pt,), np.int32),
+                    m12_ls=e((prev.n_ls,), np.int32), inlier_pt=e((prev.n_pt,), np.uint8),
+                    inlier_ls=e((prev.n_ls,), np.uint8))
+
+    def upload(self, cam, cfg, prev: T.FrameBatch, curr: T.FrameBatch, priors=None) -> DeviceBatch:
+        h = C.c_void_p()
+        pc, cc = prev.as_c(), curr.as_c()
+        self._ck(self.lib.plstvo_batch_upload(self.ctx, C.byref(cam), C.byref(cfg), C.byref(pc), C.byref(cc),
+                                              priors.ctypes.data if priors is not None else None, C.byref(h)))
+        return DeviceBatch(self, h, prev)
+
+    def synchronize(self):
+        self._ck(self.lib.plstvo_synchronize(self.ctx))
+
+    def popc_rate(self) -> float:
+        r = np.zeros(1)
+        self._ck(self.lib.plstvo_popc_rate(self.ctx, r.ctypes.data_as(T.c_double_p)))
+        return float(r[0])

@@ -1,0 +1,197 @@
+"""Parity of the fused CUDA path (K1 -> K2: match, gather, optimizePose) with the oracle, through the C-ABI.
+Bars: match indices and inlier flags bit-exact; pose within 1e-5 rad / 1e-4 m (north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+import ref_numpy as R
+from conftest import GOLDEN
+from stvo_pl_b200 import synth, types as T
+
+pytestmark = pytest.mark.gpu
+TOL_ANG, TOL_TR = 1e-5, 1e-4      # north_star tolerance
+TIGHT_ANG, TIGHT_TR = 1e-9, 1e-8  # what an all-fp64 implementation actually achieves on the GN path
+
+
+def compare(gpu, ref, prev, tight=True, flags_exact=True):
+    np.testing.assert_array_equal(gpu["m12_pt"], ref["m12_pt"])
+    np.testing.assert_array_equal(gpu["m12_ls"], ref["m12_ls"])
+    worst = (0.0, 0.0)
+    for p in range(prev.B):
+        g, r = gpu["results"][p], ref["results"][p]
+        assert g["status"] == r["status"] and g["good"] == r["good"], (p, g["status"], r["status"])
+        assert g["n_matched_pt"] == r["n_matched_pt"] and g["n_matched_ls"] == r["n_matched_ls"]
+        ang, tr = R.pose_error(g["DT"], r["DT"])
+        worst = (max(worst[0], ang), max(worst[1], tr))
+        assert ang < (TIGHT_ANG if tight else TOL_ANG) and tr < (TIGHT_TR if tight else TOL_TR), (p, ang, tr)
+        if tight:
+            assert g["iters_stage1"] == r["iters_stage1"] and g["iters_stage2"] == r["iters_stage2"]
+            assert g["n_inliers_pt"] == r["n_inliers_pt"] and g["n_inliers_ls"] == r["n_inliers_ls"]
+            assert abs(g["err_norm"] - r["err_norm"]) < 1e-9
+            np.testing.assert_allclose(g["DT_cov"], r["DT_cov"], rtol=1e-6, atol=1e-15)
+            np.testing.assert_allclose(g["DT_cov_eig"], r["DT_cov_eig"], rtol=1e-6, atol=1e-16)
+            np.testing.assert_allclose(g["Tfw"], r["Tfw"], atol=1e-8)
+            np.testing.assert_allclose(g["Tfw_cov"], r["Tfw_cov"], rtol=1e-6, atol=1e-12)
+    if flags_exact:
+        np.testing.assert_array_equal(gpu["inlier_pt"], ref["inlier_pt"])
+        np.testing.assert_array_equal(gpu["inlier_ls"], ref["inlier_ls"])
+    return worst
+
+
+@pytest.mark.parametrize("shape,cfgf,B,kw", [
+    ("kitti", T.kitti_config, 3, dict(n_pt=400, n_ls=100)),
+    ("kitti", T.kitti_config, 2, dict()),                       # C2 full size: 2000 + 500
+    ("kitti", T.kitti_config, 2, dict(overlap=1.0)),            # bench workload: every feature re-observed
+    ("euroc", T.euroc_config, 3, dict()),                       # 1000 + 300, 4 pyramid levels (sigma2 != 1)
+    ("kitti_points", T.kitti_config, 2, dict()),                # C1: points only
+    ("kitti", T.kitti_config, 2, dict(n_pt=700, n_ls=300, tie_stress=True)),
+])
+def test_track_vs_oracle(engine, oracle, shape, cfgf, B, kw):
+    cfg = cfgf()
+    prev, curr, Tgt, cam = synth.make_batch(shape, B, **kw)
+    ref = oracle.track_batch(cam, cfg, prev, curr, threads=4)
+    gpu = engine.track_batch(cam, cfg, prev, curr)
+    compare(gpu, ref, prev)
+    for p in range(B):
+        if gpu["results"][p]["good"]:
+            ang, tr = R.pose_error(gpu["results"]["DT_opt"][p], Tgt[p])
+            assert ang < 3e-3 and tr < 3e-2
+
+
+def test_points_only_config_flags(engine, oracle):
+    cfg = T.kitti_config()
+    cfg.has_lines = 0
+    prev, curr, _, cam = synth.make_batch("kitti", 2, n_pt=500, n_ls=100)
+    compare(engine.track_batch(cam, cfg, prev, curr), oracle.track_batch(cam, cfg, prev, curr), prev)
+    cfg.has_lines, cfg.has_points = 1, 0
+    compare(engine.track_batch(cam, cfg, prev, curr), oracle.track_batch(cam, cfg, prev, curr), prev)
+    cfg.has_points, cfg.best_lr_matches = 1, 0
+    compare(engine.track_batch(cam, cfg, prev, curr), oracle.track_batch(cam, cfg, prev, curr), prev)
+
+
+def test_robust_mode(engine, oracle):
+    """C3 'robust weights on': the `mode == 1` evaluator (MAD-scaled Cauchy weights).  The MAD-scaled IRLS is a
+    discontinuous iteration (see tests/test_oracle_pose.py), so the bar is north_star's tolerance."""
+    cfg = T.euroc_config()
+    cfg.solver_mode = 1
+    prev, curr, _, cam = synth.make_batch("euroc", 4)
+    compare(engine.track_batch(cam, cfg, prev, curr), oracle.track_batch(cam, cfg, prev, curr, threads=4), prev,
+            tight=False, flags_exact=False)
+
+
+def test_explicit_list_api(engine, oracle):
+    cfg = T.kitti_config()
+    prev, curr, _, cam = synth.make_batch("kitti", 3, n_pt=600, n_ls=150)
+    o = oracle.track_batch(cam, cfg, prev, curr)
+    matched = T.matched_from_frames(prev, curr, o["m12_pt"], o["m12_ls"], cfg.lsd_scale)
+    rc, ref, rp, rl = oracle.optimize_pose(cam, cfg, matched)
+    res, ip, il = engine.optimize_pose(cam, cfg, matched)
+    for p in range(3):
+        ang, tr = R.pose_error(res["DT"][p], ref["DT"][p])
+        assert ang < TIGHT_ANG and tr < TIGHT_TR
+        assert res["status"][p] == ref["status"][p]
+    np.testing.assert_array_equal(ip, rp)
+    np.testing.assert_array_equal(il, rl)
+
+
+def test_failure_encodings(engine, oracle):
+    cfg = T.kitti_config()
+    for kw in (dict(n_pt=6, n_ls=2, overlap=1.0), dict(n_pt=0, n_ls=0), dict(n_pt=30, n_ls=0, overlap=0.2)):
+        prev, curr, _, cam = synth.make_batch("kitti", 2, **kw)
+        ref = oracle.track_batch(cam, cfg, prev, curr)
+        gpu = engine.track_batch(cam, cfg, prev, curr)
+        compare(gpu, ref, prev)
+        for p in range(2):
+            if not gpu["results"][p]["good"]:
+                np.testing.assert_array_equal(gpu["results"][p]["DT"], np.eye(4))
+                np.testing.assert_array_equal(gpu["results"][p]["DT_cov"], np.zeros((6, 6)))
+                assert gpu["results"][p]["err_norm"] == -1.0
+
+
+def test_robust_fallback_branch(engine, oracle):
+    cfg = T.kitti_config()
+    cam = T.kitti_camera()
+    rng = np.random.default_rng(2)
+    n = 40
+    P = np.stack([rng.normal(0, 1e-4, n), rng.normal(0, 1e-4, n), 400 + rng.normal(0, 1e-3, n)], 1)
+    obs = np.stack([cam.cx + rng.normal(0, 0.3, n), cam.cy + rng.normal(0, 0.3, n)], 1)
+    m = T.MatchedBatch(pt_off=[0, n], ls_off=[0, 0], pt_P=P, pt_pl_obs=obs, pt_sigma2=np.ones(n),
+                       ls_sP=np.zeros((0, 3)), ls_eP=np.zeros((0, 3)), ls_le_obs=np.zeros((0, 3)),
+                       ls_spl=np.zeros((0, 2)), ls_epl=np.zeros((0, 2)), ls_sigma2=np.zeros(0))
+    rc, ref, _, _ = oracle.optimize_pose(cam, cfg, m)
+    res, _, _ = engine.optimize_pose(cam, cfg, m)
+    assert res[0]["status"] == ref[0]["status"] == T.ST_ROBUST_FALLBACK
+    assert res[0]["good"] == ref[0]["good"]
+
+
+def test_priors_motion_model_and_chaining(engine, oracle):
+    cfg = T.kitti_config()
+    cfg.use_motion_model = 1
+    prev, curr, Tgt, cam = synth.make_batch("kitti", 2, n_pt=500, n_ls=120)
+    pri = T.identity_priors(2)
+    for p in range(2):
+        pri["Tfw"][p] = R.expmap_se3([1.0, 2.0, 3.0, 0.1, -0.2, 0.05 * p])
+        pri["Tfw_cov"][p] = np.eye(6) * 0.01
+        pri["DT"][p] = Tgt[p]
+        pri["DT_cov"][p] = np.eye(6) * 1e-6
+        pri["err_norm"][p] = 0.2
+    compare(engine.track_batch(cam, cfg, prev, curr, priors=pri),
+            oracle.track_batch(cam, cfg, prev, curr, priors=pri), prev)
+
+
+def test_line_level_sigma_rule(engine, oracle):
+    cfg = T.kitti_config()
+    prev, curr, _, cam = synth.make_batch("kitti", 2, n_pt=300, n_ls=100, overlap=1.0)
+    prev.ls_level[:] = np.arange(prev.n_ls) % 3
+    prev.ls_sigma2[:] = 1.0 / (1.2 ** prev.ls_level) ** 2
+    compare(engine.track_batch(cam, cfg, prev, curr), oracle.track_batch(cam, cfg, prev, curr), prev)
+
+
+def test_resident_batch_equals_host_call_and_is_deterministic(engine):
+    cfg = T.kitti_config()
+    prev, curr, _, cam = synth.make_batch("kitti", 6, n_pt=600, n_ls=150)
+    a = engine.track_batch(cam, cfg, prev, curr)
+    db = engine.upload(cam, cfg, prev, curr)
+    db.run()
+    b = db.download()
+    db.run()
+    c = db.download()
+    db.free()
+    for k in ("m12_pt", "m12_ls", "inlier_pt", "inlier_ls"):
+        np.testing.assert_array_equal(a[k], b[k])
+        np.testing.assert_array_equal(b[k], c[k])
+    assert a["results"].tobytes() == b["results"].tobytes() == c["results"].tobytes()   # bit-identical reruns
+
+
+def test_pose_golden_vectors(engine):
+    for shape, cfgf in (("kitti", T.kitti_config), ("euroc", T.euroc_config)):
+        g = np.load(os.path.join(GOLDEN, f"pose_{shape}.npz"))
+        prev, curr, _, cam = synth.make_batch(shape, int(g["B"]), n_pt=int(g["n_pt"]), n_ls=int(g["n_ls"]))
+        gpu = engine.track_batch(cam, cfgf(), prev, curr)
+        np.testing.assert_array_equal(gpu["m12_pt"], g["m12_pt"])
+        np.testing.assert_array_equal(gpu["m12_ls"], g["m12_ls"])
+        np.testing.assert_array_equal(gpu["inlier_pt"], g["oracle_inlier_pt"])
+        np.testing.assert_array_equal(gpu["inlier_ls"], g["oracle_inlier_ls"])
+        for p in range(prev.B):
+            for key in ("oracle_DT", "numpy_DT"):
+                ang, tr = R.pose_error(gpu["results"]["DT"][p], g[key][p])
+                assert ang < TIGHT_ANG and tr < TIGHT_TR
+
+
+def test_large_frames_use_global_feature_storage(engine, oracle):
+    """C5 shape (8000 + 2000) does not fit the shared-memory feature store: the streamed variant must agree."""
+    cfg = T.kitti_config()
+    prev, curr, _, cam = synth.make_batch("hd", 1)
+    compare(engine.track_batch(cam, cfg, prev, curr), oracle.track_batch(cam, cfg, prev, curr), prev)
+
+
+def test_batch_of_64_pairs_sharded_invariance(engine, oracle):
+    """A batch processed in one call equals the same pairs processed as two half batches (what two ranks do)."""
+    cfg = T.kitti_config()
+    prev, curr, _, cam = synth.make_batch("kitti", 8, n_pt=500, n_ls=120)
+    full = engine.track_batch(cam, cfg, prev, curr)
+    lo = engine.track_batch(cam, cfg, prev.select(range(0, 4)), curr.select(range(0, 4)))
+    hi = engine.track_batch(cam, cfg, prev.select(range(4, 8)), curr.select(range(4, 8)))
+    assert full["results"].tobytes() == lo["results"].tobytes() + hi["results"].tobytes()
+    np.testing.assert_array_equal(full["m12_pt"], np.concatenate([lo["m12_pt"], hi["m12_pt"]]))
