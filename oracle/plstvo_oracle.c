@@ -430,7 +430,7 @@ void orc_eig6_sym(const double Ain[36], double w[6]) {
             diag += A[i * 6 + i] * A[i * 6 + i];
             for (int j = 0; j < i; j++) off += 2.0 * A[i * 6 + j] * A[i * 6 + j];
         }
-        if (!(off > 1e-40 * diag) || off == 0.0) break;
+        if (!(off > 1e-30 * diag) || off == 0.0) break;   /* off-diagonal mass at rounding level: eigenvalues settled to ~1e-15 */
         for (int p = 0; p < 5; p++)
             for (int q = p + 1; q < 6; q++) {
                 double apq = A[p * 6 + q];

@@ -3,6 +3,7 @@
 // device plstvo_create() fails with PLSTVO_E_NO_DEVICE and every other entry point needs a context.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -56,12 +57,13 @@ struct Workspace {
     DevBuf d_lssP, d_lseP, d_lsspl, d_lsepl, d_lss2, d_lslev, d_lsle;  // prev ...; curr le
     DevBuf d_priors, d_results, d_m12p, d_m12l, d_inlp, d_inll;
     DevBuf d_rowpart, d_colpart, d_problems, d_tiles, d_feat;
+    DevBuf d_phase;   // debug phase timers (PLSTVO_PHASE_DEBUG)
     size_t feat_stride = 0;
     void release() {
         DevBuf* all[] = {&d_poff1, &d_poff2, &d_loff1, &d_loff2, &d_pdesc1, &d_pdesc2, &d_ldesc1, &d_ldesc2,
                          &d_ptP, &d_pts2, &d_ptpl, &d_lssP, &d_lseP, &d_lsspl, &d_lsepl, &d_lss2, &d_lslev,
                          &d_lsle, &d_priors, &d_results, &d_m12p, &d_m12l, &d_inlp, &d_inll, &d_rowpart,
-                         &d_colpart, &d_problems, &d_tiles, &d_feat};
+                         &d_colpart, &d_problems, &d_tiles, &d_feat, &d_phase};
         for (DevBuf* b : all) b->release();
     }
 };
@@ -374,6 +376,7 @@ int ws_launch_solve(PlContext* ctx, Workspace& ws, int p0, int p1, bool have_lev
     prm.cap_ls = ws.cap_ls;
     prm.sort_cap = ws.sort_cap;
     prm.feat_in_smem = ws.feat_in_smem ? 1 : 0;
+    prm.phase_cycles = ws.d_phase.as<long long>();
     CK(ctx, launch_track_solve(prm, p1 - p0, s));
     ctx->launches++;
     return 0;
@@ -844,6 +847,21 @@ int plstvo_batch_kernel_times(PlContext* ctx, PlDeviceBatch* db, int iters, doub
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaEventDestroy(e2);
+    if (getenv("PLSTVO_PHASE_DEBUG") && ws.B > 0) {   // per-phase device cycles of K2, averaged over the pairs
+        CK(ctx, ws.d_phase.ensure((size_t)ws.B * 8 * sizeof(long long)));
+        int rc2 = ws_launch_solve(ctx, ws, 0, ws.B, lev, ctx->s_main);
+        if (rc2) return rc2;
+        std::vector<long long> h((size_t)ws.B * 8);
+        CK(ctx, cudaMemcpyAsync(h.data(), ws.d_phase.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->s_main));
+        CK(ctx, cudaStreamSynchronize(ctx->s_main));
+        static const char* names[8] = {"match_finalize", "gather", "gn_eval", "gn_serial", "gates_eig", "outliers", "final", "-"};
+        for (int k = 0; k < 7; ++k) {
+            double sum = 0;
+            for (int p = 0; p < ws.B; ++p) sum += (double)h[(size_t)p * 8 + k];
+            fprintf(stderr, "[plstvo phase] %-15s %10.0f cycles/pair\n", names[k], sum / ws.B);
+        }
+        ws.d_phase.release();
+    }
     if (ms_match) *ms_match = tm / iters;
     if (ms_solve) *ms_solve = tsv / iters;
     if (n_tiles) *n_tiles = (int32_t)ws.tiles.size();
@@ -894,9 +912,64 @@ int plstvo_popc_rate(PlContext* ctx, double* popc_per_s) {
     return 0;
 }
 
-int plstvo_gn_eval_stream(PlContext* ctx, const PlCamera*, const PlConfig*, const PlMatchedBatch*, const double*,
-                          int, double*, double*, double*, float*) {
-    return fail(ctx, PLSTVO_E_INVALID, "plstvo_gn_eval_stream: not built yet");
+int plstvo_gn_eval_stream(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlMatchedBatch* m,
+                          const double* DT, int iters, double* H, double* g, double* e, float* ms_total) {
+    if (!ctx || !cam || !cfg || !m || !DT || iters <= 0) return PLSTVO_E_INVALID;
+    const int B = m->B;
+    if (B <= 0) return 0;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t n = m->pt_off[B], l = m->ls_off[B];
+    cudaStream_t s = ctx->s_main;
+    struct Up { const void* src; size_t bytes; };
+    const Up ups[8 + 5] = {{m->pt_off, (size_t)(B + 1) * 4}, {m->ls_off, (size_t)(B + 1) * 4}, {m->pt_P, n * 24},
+                           {m->pt_pl_obs, n * 16}, {m->pt_sigma2, n * 8}, {m->ls_sP, l * 24}, {m->ls_eP, l * 24},
+                           {m->ls_le_obs, l * 24}, {m->ls_spl, l * 16}, {m->ls_epl, l * 16}, {m->ls_sigma2, l * 8},
+                           {m->pt_inlier, n}, {m->ls_inlier, l}};
+    static DevBuf bufs[13];   // resident inputs of the roofline run (process lifetime)
+    for (int i = 0; i < 13; ++i) {
+        CK(ctx, bufs[i].ensure(std::max<size_t>(ups[i].bytes, 16)));
+        if (ups[i].src && ups[i].bytes)
+            CK(ctx, cudaMemcpyAsync(bufs[i].p, ups[i].src, ups[i].bytes, cudaMemcpyHostToDevice, s));
+    }
+    MatchedDev md{bufs[0].as<int32_t>(), bufs[1].as<int32_t>(), bufs[2].as<double>(), bufs[3].as<double>(),
+                  bufs[4].as<double>(), m->pt_inlier ? bufs[11].as<uint8_t>() : nullptr, bufs[5].as<double>(),
+                  bufs[6].as<double>(), bufs[7].as<double>(), bufs[8].as<double>(), bufs[9].as<double>(),
+                  bufs[10].as<double>(), m->ls_inlier ? bufs[12].as<uint8_t>() : nullptr};
+    // blocks per problem: enough CTAs for >= 4 waves of the chip, at least ~512 features per CTA
+    size_t max_feat = 1;
+    for (int p = 0; p < B; ++p)
+        max_feat = std::max<size_t>(max_feat, (size_t)(m->pt_off[p + 1] - m->pt_off[p]) + (m->ls_off[p + 1] - m->ls_off[p]));
+    int bpp = (int)std::max<size_t>(1, std::min<size_t>(max_feat / 512, 64));
+    while ((long)B * bpp < 8L * ctx->sm_count && bpp < 64) ++bpp;
+    CK(ctx, ctx->gn_in[0].ensure((size_t)B * 16 * 8));
+    CK(ctx, ctx->gn_in[1].ensure((size_t)B * bpp * (ACC_N + 1) * 8));
+    CK(ctx, ctx->gn_out[2].ensure((size_t)B * 36 * 8));
+    CK(ctx, ctx->gn_out[3].ensure((size_t)B * 7 * 8));
+    CK(ctx, cudaMemcpyAsync(ctx->gn_in[0].p, DT, (size_t)B * 16 * 8, cudaMemcpyHostToDevice, s));
+    double* dH = ctx->gn_out[2].as<double>();
+    double* dg = ctx->gn_out[3].as<double>();
+    double* de = dg + (size_t)B * 6;
+    cudaEvent_t e0, e1;
+    CK(ctx, cudaEventCreate(&e0));
+    CK(ctx, cudaEventCreate(&e1));
+    CK(ctx, launch_gn_eval_stream(*cam, *cfg, md, B, ctx->gn_in[0].as<double>(), ctx->gn_in[1].as<double>(), bpp, dH, dg,
+                                  de, s));   // warm-up
+    CK(ctx, cudaEventRecord(e0, s));
+    for (int i = 0; i < iters; ++i)
+        CK(ctx, launch_gn_eval_stream(*cam, *cfg, md, B, ctx->gn_in[0].as<double>(), ctx->gn_in[1].as<double>(), bpp, dH,
+                                      dg, de, s));
+    CK(ctx, cudaEventRecord(e1, s));
+    ctx->launches += 2 * (iters + 1);
+    if (H) CK(ctx, cudaMemcpyAsync(H, dH, (size_t)B * 36 * 8, cudaMemcpyDeviceToHost, s));
+    if (g) CK(ctx, cudaMemcpyAsync(g, dg, (size_t)B * 6 * 8, cudaMemcpyDeviceToHost, s));
+    if (e) CK(ctx, cudaMemcpyAsync(e, de, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaStreamSynchronize(s));
+    float ms = 0.f;
+    CK(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_total) *ms_total = ms;
+    return 0;
 }
 
 }  // extern "C"

@@ -97,6 +97,7 @@ struct SolveParams {
     int32_t  cap_pt, cap_ls;  // capacity of the SoA arrays (max matched features per pair in this launch)
     int32_t  sort_cap;        // power of two >= max(cap_pt, cap_ls)
     int32_t  feat_in_smem;
+    long long* phase_cycles;  // optional [pairs][8] debug timers (PLSTVO_PHASE_DEBUG), else null
 };
 
 size_t k2_smem_bytes(int cap_pt, int cap_ls, int sort_cap, bool feat_in_smem);

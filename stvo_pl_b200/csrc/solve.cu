@@ -39,6 +39,7 @@ struct State {
     int    n_inl_p, n_inl_l;
     int    evals;
     int    scan[K2_WARPS];
+    long long tc[8];         // debug phase timers: 0 match-finalize 1 gather 2 GN-eval 3 GN-serial 4 gates/eig 5 outliers 6 final
     PlPoseResult out;
 };
 
@@ -284,7 +285,7 @@ __device__ void eig6_sym(const double* Ain, double* w) {
             diag += A[i * 6 + i] * A[i * 6 + i];
             for (int j = 0; j < i; j++) off += 2.0 * A[i * 6 + j] * A[i * 6 + j];
         }
-        if (!(off > 1e-40 * diag) || off == 0.0) break;
+        if (!(off > 1e-30 * diag) || off == 0.0) break;   /* off-diagonal mass at rounding level: eigenvalues settled to ~1e-15 */
         for (int p = 0; p < 5; p++)
             for (int q = p + 1; q < 6; q++) {
                 const double apq = A[p * 6 + q];
@@ -624,7 +625,9 @@ __device__ void gauss_newton(const Feat& f, State& st, double* sortbuf, const Ca
         st.evals = 0;
     }
     for (int it = 0; it < max_iters; it++) {
+        const long long t_a = clock64();
         evaluate(f, st, sortbuf, st.DT, cam, cfg.homog_th, robust);
+        const long long t_b = clock64();
         if (tid == 0) {
             double g[6], inc[6], lad;
             int ctrl = 0;   // 0 continue, 1 stop
@@ -662,6 +665,8 @@ __device__ void gauss_newton(const Feat& f, State& st, double* sortbuf, const Ca
                 }
             }
             st.ctrl = ctrl;
+            st.tc[2] += t_b - t_a;
+            st.tc[3] += clock64() - t_b;
         }
         __syncthreads();
         const int ctrl = st.ctrl;
@@ -669,6 +674,7 @@ __device__ void gauss_newton(const Feat& f, State& st, double* sortbuf, const Ca
         if (ctrl) break;
     }
     if (tid == 0) {
+        const long long t_c = clock64();
         if (fail_first) {
             st.err = -1.0;   // :408-409: DT_cov left untouched
         } else if (good) {
@@ -679,6 +685,7 @@ __device__ void gauss_newton(const Feat& f, State& st, double* sortbuf, const Ca
             st.err = -1.0;
             for (int i = 0; i < 36; i++) st.cov[i] = (i % 7 == 0) ? 1.0 : 0.0;
         }
+        st.tc[3] += clock64() - t_c;
     }
     __syncthreads();
 }
@@ -787,6 +794,9 @@ __global__ void __launch_bounds__(K2_THREADS, 1) track_solve_kernel(const SolveP
     const PlConfig& cfg = prm.cfg;
     const Cam cam = {prm.cam.fx, prm.cam.fy, prm.cam.cx, prm.cam.cy};
 
+    if (tid == 0)
+        for (int i = 0; i < 8; i++) st.tc[i] = 0;
+    long long t_ph = clock64();
     int n1p = 0, n1l = 0;        // prev-frame feature counts (mode 0) / list lengths (mode 1)
     size_t out_p0 = 0, out_l0 = 0;   // where this pair's inlier flags start
 
@@ -797,6 +807,8 @@ __global__ void __launch_bounds__(K2_THREADS, 1) track_solve_kernel(const SolveP
         __syncthreads();
         match_finalize_block(pl, reinterpret_cast<int32_t*>(sortbuf));
         __syncthreads();
+        if (tid == 0) { st.tc[0] += clock64() - t_ph; }
+        t_ph = clock64();
 
         // ---- B. f2fTracking glue: ordered compaction of the matched features into SoA ----
         const FrameDev& P = prm.prev;
@@ -896,6 +908,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) track_solve_kernel(const SolveP
         }
     }
     __syncthreads();
+    if (tid == 0) { st.tc[1] += clock64() - t_ph; }
 
     // ---- C. optimizePose (:307-392) ----
     const PlPrior* prior = prm.priors ? &prm.priors[pair] : nullptr;
@@ -919,13 +932,17 @@ __global__ void __launch_bounds__(K2_THREADS, 1) track_solve_kernel(const SolveP
         gauss_newton(f, st, sortbuf, cam, cfg, cfg.max_iters, robust_mode);     // stage 1 on DT_ = DT (:335-338)
         if (tid == 0) {
             st.out.iters_stage1 = st.evals;
+            const long long t_g = clock64();
             st.ctrl = is_good_solution(st.DT, st.cov, st.err, nullptr) ? 1 : 0;   // :341
+            st.tc[4] += clock64() - t_g;
         }
         __syncthreads();
         if (st.ctrl) {
             __syncthreads();
+            const long long t_o = clock64();
             remove_outliers(f, st, sortbuf, st.DT, cam, cfg);                     // at the stage-1 pose (:343)
             if (tid == 0) {
+                st.tc[5] += clock64() - t_o;
                 st.ctrl = (st.n_inl_p + st.n_inl_l >= cfg.min_features) ? 1 : 0;
                 for (int i = 0; i < 16; i++) st.DT[i] = st.DT0[i];                // stage 2 restarts from DT (:347)
             }
@@ -961,6 +978,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) track_solve_kernel(const SolveP
 
     // ---- pose finalisation (:372-391) ----
     if (tid == 0) {
+        const long long t_f = clock64();
         PlPoseResult& o = st.out;
         double Tfw_prev[16], Tfw_cov_prev[36];
         if (prior) {
@@ -1000,6 +1018,9 @@ __global__ void __launch_bounds__(K2_THREADS, 1) track_solve_kernel(const SolveP
         o.n_inliers_ls = st.n_inl_l;
         o.n_inliers = st.n_inl_p + st.n_inl_l;
         o.reserved = 0;
+        st.tc[6] += clock64() - t_f;
+        if (prm.phase_cycles)
+            for (int i = 0; i < 8; i++) prm.phase_cycles[(size_t)pair * 8 + i] = st.tc[i];
     }
     __syncthreads();
     {   // result struct -> HBM, cooperatively (sizeof(PlPoseResult) is a multiple of 8)

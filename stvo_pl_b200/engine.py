@@ -249,6 +249,18 @@ class Engine:
                                               priors.ctypes.data if priors is not None else None, C.byref(h)))
         return DeviceBatch(self, h, prev)
 
+    def gn_eval_stream(self, cam, cfg, matched: T.MatchedBatch, DT, iters: int = 1):
+        """optimizeFunctions for B problems streamed from HBM (C5 roofline kernel); returns H, g, e, ms_total."""
+        B = matched.B
+        DT = np.ascontiguousarray(DT, np.float64).reshape(B, 16)
+        H, g, e = np.zeros((B, 6, 6)), np.zeros((B, 6)), np.zeros(B)
+        ms = C.c_float(0)
+        mc = matched.as_c()
+        self._ck(self.lib.plstvo_gn_eval_stream(self.ctx, C.byref(cam), C.byref(cfg), C.byref(mc), _p(DT, T.c_double_p),
+                                                iters, _p(H, T.c_double_p), _p(g, T.c_double_p), _p(e, T.c_double_p),
+                                                C.byref(ms)))
+        return H, g, e, float(ms.value)
+
     def synchronize(self):
         self._ck(self.lib.plstvo_synchronize(self.ctx))
 

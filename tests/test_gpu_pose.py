@@ -195,3 +195,19 @@ def test_batch_of_64_pairs_sharded_invariance(engine, oracle):
     hi = engine.track_batch(cam, cfg, prev.select(range(4, 8)), curr.select(range(4, 8)))
     assert full["results"].tobytes() == lo["results"].tobytes() + hi["results"].tobytes()
     np.testing.assert_array_equal(full["m12_pt"], np.concatenate([lo["m12_pt"], hi["m12_pt"]]))
+
+
+def test_gn_eval_stream_vs_oracle(engine, oracle):
+    """optimizeFunctions streamed from HBM (the C5 roofline kernel) against the oracle's evaluation."""
+    cfg = T.kitti_config()
+    prev, curr, Tgt, cam = synth.make_batch("kitti", 3, n_pt=900, n_ls=250)
+    o = oracle.track_batch(cam, cfg, prev, curr)
+    matched = T.matched_from_frames(prev, curr, o["m12_pt"], o["m12_ls"], cfg.lsd_scale)
+    DT = np.stack([np.eye(4), Tgt[1], o["results"]["DT_opt"][2]])
+    H, g, e, ms = engine.gn_eval_stream(cam, cfg, matched, DT, iters=2)
+    for p in range(3):
+        Hr, gr, er = oracle.optimize_functions(cam, cfg, matched, p, DT[p])
+        np.testing.assert_allclose(H[p], Hr, rtol=1e-10, atol=1e-6 * np.abs(Hr).max() * 1e-6)
+        np.testing.assert_allclose(g[p], gr, rtol=1e-9, atol=1e-9 * np.abs(gr).max())
+        assert abs(e[p] - er) < 1e-12
+    assert ms > 0
