@@ -229,6 +229,8 @@ def run_ours(args):
     # ---------------- value: inputs resident in HBM ----------------
     db = eng.upload(cam, cfg, prev, curr)
     if args.kernels_only:
+        db.run()                      # first launches pay module load / local-memory setup: keep them out
+        eng.synchronize()
         print(json.dumps(db.kernel_times(iters=2)), flush=True)
         db.free()
         eng.close()
@@ -267,10 +269,12 @@ def run_ours(args):
         "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": kt["ms_match"], "ctas_per_launch": kt["n_tiles"],
         "share_of_step": kt["ms_match"] / (kt["ms_match"] + kt["ms_solve"]),
         "note": "K1 is integer-ALU (POPC) bound, not HBM bound: see `alu`",
-        "alu": {"unit": "Gpopc32/s", "achieved": 8 * pair_dists / (kt["ms_match"] * 1e-3) / 1e9,
-                "peak": popc_rate / 1e9, "frac": 8 * pair_dists / (kt["ms_match"] * 1e-3) / popc_rate,
-                "peak_kind": "measured POPC issue rate (plstvo_popc_rate micro-benchmark, same process)",
-                "pair_distances_per_s": pair_dists / (kt["ms_match"] * 1e-3)},
+        "alu": {"unit": "G pair-distances/s", "achieved": pair_dists / (kt["ms_match"] * 1e-3) / 1e9,
+                "peak": popc_rate / 8 / 1e9, "frac": 8 * pair_dists / (kt["ms_match"] * 1e-3) / popc_rate,
+                "peak_kind": "measured POPC issue rate (plstvo_popc_rate micro-benchmark, same process) / 8 POPC per "
+                             "256-bit distance = the XU-pipe bound of the straightforward XOR+POPC matcher; the kernel "
+                             "folds the 8 XOR words with carry-save adders (6 LOP3) into 5 POPC, so frac > 1 is possible",
+                "popc32_per_s_measured": popc_rate},
         "k2": {"kernel": "track_solve_kernel (K2)", "ms_per_launch": kt["ms_solve"], "ctas_per_launch": kt["n_pairs"]},
         "step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes * args.steps / (ms * 1e-3) / 1e9,
                  "frac": step_bytes * args.steps / (ms * 1e-3) / 1e9 / peak},

@@ -230,6 +230,10 @@ int     plstvo_batch_kernel_times(PlContext* ctx, PlDeviceBatch* db, int iters, 
 int  plstvo_gn_eval_stream(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg,
                            const PlMatchedBatch* matched, const double* DT, int iters,
                            double* H, double* g, double* e, float* ms_total);
+/* test hook for the on-chip 6x6 routines of the solver (ColPivHouseholderQR solve + log|det|, inverse, symmetric
+ * eigenvalues) on n caller-supplied matrices: H [n][36] row-major, g [n][6] -> x [n][6], lad [n], inv [n][36], eig [n][6] */
+int  plstvo_debug_algebra(PlContext* ctx, int n, const double* H, const double* g, double* x, double* lad,
+                          double* inv, double* eig);
 /* POPC issue-rate micro-benchmark: returns 32-bit popcounts per second on this device */
 int  plstvo_popc_rate(PlContext* ctx, double* popc_per_s);
 

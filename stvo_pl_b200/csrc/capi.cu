@@ -135,7 +135,7 @@ void plan_problem(MatchProblem& pr, int n1, int n2, bool enabled, float nnr, int
         pr.tsplit = 32;
         return;
     }
-    pr.nqb = (n1 + K1_THREADS - 1) / K1_THREADS;
+    pr.nqb = (n1 + K1_QTILE - 1) / K1_QTILE;
     int ts = ((n2 + 31) / 32) * 32;
     if (tsplit_hint > 0 && tsplit_hint < ts) ts = tsplit_hint;
     pr.tsplit = ts;
@@ -190,8 +190,8 @@ int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfi
     // --- tile split: enough CTAs for a small batch, whole train sets per tile for a big one ---
     long base_tiles = 0;
     for (int p = 0; p < B; ++p) {
-        base_tiles += (ws.p_off1[p + 1] - ws.p_off1[p] + K1_THREADS - 1) / K1_THREADS;
-        base_tiles += (ws.l_off1[p + 1] - ws.l_off1[p] + K1_THREADS - 1) / K1_THREADS;
+        base_tiles += (ws.p_off1[p + 1] - ws.p_off1[p] + K1_QTILE - 1) / K1_QTILE;
+        base_tiles += (ws.l_off1[p + 1] - ws.l_off1[p] + K1_QTILE - 1) / K1_QTILE;
     }
     const long want = 3L * ctx->sm_count;   // about one full wave of resident K1 CTAs
     int split = 1;
@@ -272,7 +272,7 @@ int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfi
         CK(ctx, ws.d_inlp.ensure(np1));
         CK(ctx, ws.d_inll.ensure(nl1));
         if (!ws.feat_in_smem) {
-            ws.feat_stride = (size_t)6 * ws.cap_pt + (size_t)14 * ws.cap_ls;
+            ws.feat_stride = k2_feat_stride(ws.cap_pt, ws.cap_ls);
             CK(ctx, ws.d_feat.ensure((size_t)B * ws.feat_stride * sizeof(double)));
         }
     }
@@ -667,7 +667,7 @@ int plstvo_optimize_pose(PlContext* ctx, const PlCamera* cam, const PlConfig* cf
     CK(ctx, ctx->gn_out[1].ensure(std::max<size_t>(l, 16)));
     size_t stride = 0;
     if (!in_smem) {
-        stride = (size_t)6 * cap_pt + (size_t)14 * cap_ls;
+        stride = k2_feat_stride(cap_pt, cap_ls);
         CK(ctx, ws.d_feat.ensure((size_t)B * stride * sizeof(double)));
     }
     SolveParams prm{};
@@ -888,6 +888,29 @@ void plstvo_batch_free(PlContext* ctx, PlDeviceBatch* db) {
     }
     db->ws.release();
     delete db;
+}
+
+int plstvo_debug_algebra(PlContext* ctx, int n, const double* H, const double* g, double* x, double* lad, double* inv,
+                         double* eig) {
+    if (!ctx || n < 0 || !H || !g || !x || !lad || !inv || !eig) return PLSTVO_E_INVALID;
+    if (n == 0) return 0;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t in_b = (size_t)n * 42 * 8, out_b = (size_t)n * 49 * 8;
+    CK(ctx, ctx->scratch.ensure(in_b + out_b));
+    double* d = ctx->scratch.as<double>();
+    double *dH = d, *dg = d + (size_t)n * 36, *dx = dg + (size_t)n * 6, *dl = dx + (size_t)n * 6, *di = dl + n,
+           *de = di + (size_t)n * 36;
+    cudaStream_t s = ctx->s_main;
+    CK(ctx, cudaMemcpyAsync(dH, H, (size_t)n * 36 * 8, cudaMemcpyHostToDevice, s));
+    CK(ctx, cudaMemcpyAsync(dg, g, (size_t)n * 6 * 8, cudaMemcpyHostToDevice, s));
+    CK(ctx, launch_algebra_selftest(dH, dg, n, dx, dl, di, de, s));
+    ctx->launches++;
+    CK(ctx, cudaMemcpyAsync(x, dx, (size_t)n * 6 * 8, cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaMemcpyAsync(lad, dl, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaMemcpyAsync(inv, di, (size_t)n * 36 * 8, cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaMemcpyAsync(eig, de, (size_t)n * 6 * 8, cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaStreamSynchronize(s));
+    return 0;
 }
 
 int plstvo_popc_rate(PlContext* ctx, double* popc_per_s) {

@@ -36,8 +36,10 @@ struct MatchTile {
     int32_t tb;
 };
 
-constexpr int K1_THREADS = 256;   // = queries per tile: one query descriptor per thread, in registers
-constexpr int K1_CHUNK   = 512;   // train rows per TMA stage (16 KB)
+constexpr int K1_THREADS = 256;
+constexpr int K1_QPT     = 2;                      // query descriptors per thread, in registers
+constexpr int K1_QTILE   = K1_THREADS * K1_QPT;    // queries per tile
+constexpr int K1_CHUNK   = 512;                    // train rows per TMA stage (16 KB)
 
 // ---- K2 (track_solve) ------------------------------------------------------------------------------
 constexpr int K2_THREADS = 512;
@@ -101,6 +103,7 @@ struct SolveParams {
 };
 
 size_t k2_smem_bytes(int cap_pt, int cap_ls, int sort_cap, bool feat_in_smem);
+size_t k2_feat_stride(int cap_pt, int cap_ls);   // doubles of global feature scratch per pair
 
 // kernel launchers (defined in match.cu / solve.cu)
 cudaError_t launch_hamming_knn2(const MatchProblem* problems, const MatchTile* tiles, int n_tiles,
@@ -108,6 +111,8 @@ cudaError_t launch_hamming_knn2(const MatchProblem* problems, const MatchTile* t
 cudaError_t launch_match_finalize(const MatchProblem* problems, int n_problems, int max_n2, int32_t* counts,
                                   cudaStream_t stream);
 cudaError_t launch_track_solve(const SolveParams& prm, int n_pairs, cudaStream_t stream);
+cudaError_t launch_algebra_selftest(const double* H, const double* g, int n, double* x, double* lad, double* inv,
+                                    double* eig, cudaStream_t stream);
 cudaError_t launch_popc_bench(uint32_t* out, int iters, int blocks, cudaStream_t stream);
 size_t k1_smem_bytes(int max_tsplit);
 

@@ -3,7 +3,7 @@
 // Replaces the arithmetic of StVO::matchNNR / StVO::match (src/matching.cpp:41-91), i.e. OpenCV's
 // cv::BFMatcher(NORM_HAMMING)::knnMatch(desc1, desc2, ., 2) called once per direction.  One pass over the
 // N1 x N2 distance matrix produces BOTH directions:
-//   row    top-2 (query  -> nearest trains)  kept in registers, one query descriptor per thread;
+//   row    top-2 (query  -> nearest trains)  kept in registers, two query descriptors per thread;
 //   column top-2 (train  -> nearest queries) by two warp REDUX.MIN per (warp, train) on packed keys,
 //   merged across warps with shared-memory atomicMin.
 // Keys are (distance << 16 | index): unsigned min == OpenCV's ordering by (distance, trainIdx) ascending,
@@ -11,42 +11,77 @@
 // tests/golden/match_*.npz).  Train descriptor rows are staged into shared memory by the TMA engine
 // (cp.async.bulk + mbarrier, double buffered); every thread then reads the same row (broadcast LDS.128).
 //
-// Integer work only: XOR + POPC + IADD.  No tensor cores: there is no dense contraction here.
+// Integer work only: XOR + carry-save adders (LOP3) + POPC + IMAD.  No tensor cores: there is no dense
+// contraction here.
 #include "common.cuh"
 #include "match_finalize.cuh"
 
 namespace plstvo {
 
+constexpr int K1_WARPS = K1_THREADS / 32;
+
 size_t k1_smem_bytes(int max_tsplit) {
-    return 2 * (size_t)K1_CHUNK * 32 + (size_t)max_tsplit * sizeof(uint2) + 64;
+    return 2 * (size_t)K1_CHUNK * 32 + (size_t)max_tsplit * sizeof(uint2) + (size_t)K1_WARPS * 32 * sizeof(uint2) + 64;
 }
 
-__device__ __forceinline__ uint32_t hamming256(const uint4& qa, const uint4& qb, const uint4& a, const uint4& b) {
-    return __popc(qa.x ^ a.x) + __popc(qa.y ^ a.y) + __popc(qa.z ^ a.z) + __popc(qa.w ^ a.w) +
-           __popc(qb.x ^ b.x) + __popc(qb.y ^ b.y) + __popc(qb.z ^ b.z) + __popc(qb.w ^ b.w);
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// Hamming distance of two 256-bit rows, already shifted into the key's distance field (d << 16).
+// POPC issues at 16 lanes/clk/SM on the XU pipe, LOP3 at 64 on the ALU pipe: three carry-save adders (6 LOP3)
+// fold the eight XOR words into five, so 5 POPC instead of 8 per distance and the two pipes end up balanced.
+//   x0+x1+x2 = s0 + 2 c0,  x3+x4+x5 = s1 + 2 c1,  s0+s1+x6 = s2 + 2 c2   (bitwise, per bit position)
+//   popc(x0..x7) = popc(s2) + popc(x7) + 2 (popc(c0) + popc(c1) + popc(c2))
+__device__ __forceinline__ uint32_t hamming256_shl16(const uint4& qa, const uint4& qb, const uint4& a, const uint4& b) {
+    const uint32_t x0 = qa.x ^ a.x, x1 = qa.y ^ a.y, x2 = qa.z ^ a.z, x3 = qa.w ^ a.w;
+    const uint32_t x4 = qb.x ^ b.x, x5 = qb.y ^ b.y, x6 = qb.z ^ b.z, x7 = qb.w ^ b.w;
+    const uint32_t s0 = xor3(x0, x1, x2), c0 = maj3(x0, x1, x2);
+    const uint32_t s1 = xor3(x3, x4, x5), c1 = maj3(x3, x4, x5);
+    const uint32_t s2 = xor3(s0, s1, x6), c2 = maj3(s0, s1, x6);
+    const uint32_t ones = __popc(s2) + __popc(x7);
+    const uint32_t twos = __popc(c0) + __popc(c1) + __popc(c2);
+    return ones * 65536u + twos * 131072u;   // IMAD: stays off the ALU pipe
 }
 
 __global__ void __launch_bounds__(K1_THREADS, 3)
 hamming_knn2_kernel(const MatchProblem* __restrict__ problems, const MatchTile* __restrict__ tiles) {
     extern __shared__ __align__(128) uint8_t smem[];
+    const MatchTile tile = tiles[blockIdx.x];
+    const MatchProblem pr = problems[tile.problem];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
     uint4* stage0 = reinterpret_cast<uint4*>(smem);
     uint4* stage1 = reinterpret_cast<uint4*>(smem + (size_t)K1_CHUNK * 32);
     uint2* col = reinterpret_cast<uint2*>(smem + 2 * (size_t)K1_CHUNK * 32);
+    uint2* wstage = col + pr.tsplit + (size_t)warp * 32;    // this warp's column results of the current 32 trains
+    uint64_t* bars = reinterpret_cast<uint64_t*>(col + pr.tsplit + (size_t)K1_WARPS * 32);
 
-    const MatchTile tile = tiles[blockIdx.x];
-    const MatchProblem pr = problems[tile.problem];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int q = tile.qb * K1_THREADS + tid;
-    const bool qvalid = q < pr.n1;
     const int t0 = tile.tb * pr.tsplit;
     const int nt = min(pr.tsplit, pr.n2 - t0);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * (size_t)K1_CHUNK * 32 + (size_t)pr.tsplit * sizeof(uint2));
 
-    uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
-    if (qvalid) {
-        const uint4* p = reinterpret_cast<const uint4*>(pr.d1 + (size_t)q * 32);
-        qa = __ldg(p);
-        qb = __ldg(p + 1);
+    // two query rows per thread: q and q + K1_THREADS (consecutive lanes -> consecutive rows: coalesced)
+    uint4 qa[K1_QPT], qb[K1_QPT];
+    uint32_t qkey[K1_QPT];
+#pragma unroll
+    for (int u = 0; u < K1_QPT; ++u) {
+        const int q = tile.qb * K1_QTILE + u * K1_THREADS + tid;
+        qa[u] = make_uint4(0, 0, 0, 0);
+        qb[u] = qa[u];
+        qkey[u] = KEY_NONE;   // invalid rows: OR-ing this saturates the column key
+        if (q < pr.n1) {
+            const uint4* p = reinterpret_cast<const uint4*>(pr.d1 + (size_t)q * 32);
+            qa[u] = __ldg(p);
+            qb[u] = __ldg(p + 1);
+            qkey[u] = (uint32_t)q;
+        }
     }
     for (int i = tid; i < nt; i += K1_THREADS) col[i] = make_uint2(KEY_NONE, KEY_NONE);
     if (tid == 0) {
@@ -64,8 +99,9 @@ hamming_knn2_kernel(const MatchProblem* __restrict__ problems, const MatchTile* 
         bulk_g2s(stage0, src, bytes, &bars[0]);
     }
 
-    const uint32_t qkey = qvalid ? (uint32_t)q : KEY_NONE;  // invalid lanes: OR-ing this saturates the key
-    uint32_t k1 = KEY_NONE, k2 = KEY_NONE;
+    uint32_t k1[K1_QPT], k2[K1_QPT];
+#pragma unroll
+    for (int u = 0; u < K1_QPT; ++u) k1[u] = k2[u] = KEY_NONE;
 
     for (int c = 0; c < nchunks; ++c) {
         if (tid == 0 && c + 1 < nchunks) {  // prefetch the next stage (its buffer was released by the
@@ -81,38 +117,49 @@ hamming_knn2_kernel(const MatchProblem* __restrict__ problems, const MatchTile* 
 
         for (int g = 0; g < cn; g += 32) {
             const int gn = min(32, cn - g);
-            uint32_t c1 = KEY_NONE, c2 = KEY_NONE;
 #pragma unroll 4
             for (int j = 0; j < gn; ++j) {
-                const uint4 a = s[(g + j) * 2], b = s[(g + j) * 2 + 1];
-                const uint32_t dsh = hamming256(qa, qb, a, b) << 16;
-                // row direction: this thread's query against train (tbase + g + j)
-                const uint32_t key = dsh | (tbase + (uint32_t)(g + j));
-                k2 = min(k2, max(k1, key));
-                k1 = min(k1, key);
-                // column direction: this train against the warp's 32 queries
-                const uint32_t kc = dsh | qkey;
-                const uint32_t m1 = __reduce_min_sync(0xFFFFFFFFu, kc);
-                const uint32_t m2 = __reduce_min_sync(0xFFFFFFFFu, kc == m1 ? KEY_NONE : kc);
-                if (lane == j) {
-                    c1 = m1;
-                    c2 = m2;
+                const uint4 a = s[(g + j) * 2], b = s[(g + j) * 2 + 1];   // same row for every lane: broadcast
+                const uint32_t tkey = tbase + (uint32_t)(g + j);
+                uint32_t kc[K1_QPT];
+#pragma unroll
+                for (int u = 0; u < K1_QPT; ++u) {
+                    const uint32_t dsh = hamming256_shl16(qa[u], qb[u], a, b);
+                    // row direction: query u of this thread against train tkey
+                    const uint32_t key = dsh | tkey;
+                    k2[u] = min(k2[u], max(k1[u], key));
+                    k1[u] = min(k1[u], key);
+                    kc[u] = dsh | qkey[u];
+                }
+                // column direction: this train against the warp's 64 queries.  Thread-local pair sort, then two
+                // warp REDUX.MIN: the runner-up is the minimum once every lane has dropped the winner.
+                const uint32_t lo = min(kc[0], kc[1]), hi = max(kc[0], kc[1]);
+                const uint32_t m1 = __reduce_min_sync(0xFFFFFFFFu, lo);
+                const uint32_t m2 = __reduce_min_sync(0xFFFFFFFFu, lo == m1 ? hi : lo);
+                wstage[j] = make_uint2(m1, m2);   // warp-uniform value, every lane stores the same word: one wavefront
+            }
+            __syncwarp();
+            // lane j now merges train (g + j) into the CTA's column state.  The atomicMin chain keeps the two
+            // smallest of all keys ever offered (keys are unique): whatever loses slot .x is offered to slot .y.
+            if (lane < gn) {
+                const uint2 w = wstage[lane];
+                if (w.x != KEY_NONE) {
+                    uint2* cs = &col[c * K1_CHUNK + g + lane];
+                    const uint32_t old = atomicMin(&cs->x, w.x);
+                    atomicMin(&cs->y, max(old, w.x));
+                    if (w.y != KEY_NONE) atomicMin(&cs->y, w.y);
                 }
             }
-            // lane j now owns the warp's top-2 for train (g + j): merge into the CTA's column state.
-            // atomicMin chain keeps the two smallest of all keys ever offered (keys are unique):
-            // whatever loses the contest for slot .x is offered to slot .y.
-            if (lane < gn && c1 != KEY_NONE) {
-                uint2* cs = &col[c * K1_CHUNK + g + lane];
-                const uint32_t old = atomicMin(&cs->x, c1);
-                atomicMin(&cs->y, max(old, c1));
-                if (c2 != KEY_NONE) atomicMin(&cs->y, c2);
-            }
+            __syncwarp();
         }
         __syncthreads();
     }
 
-    if (qvalid) pr.rowpart[(size_t)tile.tb * pr.n1 + q] = make_uint2(k1, k2);
+#pragma unroll
+    for (int u = 0; u < K1_QPT; ++u) {
+        const int q = tile.qb * K1_QTILE + u * K1_THREADS + tid;
+        if (q < pr.n1) pr.rowpart[(size_t)tile.tb * pr.n1 + q] = make_uint2(k1[u], k2[u]);
+    }
     uint2* cp = pr.colpart + (size_t)tile.qb * pr.n2 + t0;
     for (int i = tid; i < nt; i += K1_THREADS) cp[i] = col[i];
 }

@@ -1,16 +1,20 @@
 // solve.cu — K2: one persistent CTA per frame pair does everything after the distance tiles:
 //   A. merge K1's partials, ratio test, mutual filter        (src/matching.cpp:50-61, :76-86)
 //   B. build matched_pt / matched_ls in ascending prev index  (src/stereoFrameHandler.cpp:144-152, :167-179)
-//      as structure-of-arrays in shared memory (coalesced, conflict-free)
+//      as structure-of-arrays in shared memory (coalesced, conflict-free), with the per-feature constants of the
+//      evaluator (sqrt(sigma2), the line-overlap coefficients) computed once
 //   C. optimizePose                                            (src/stereoFrameHandler.cpp:307-392):
-//      Gauss-Newton (:394-431) / robust Gauss-Newton (:433-480) with the per-feature residual, 1x6 Jacobian row
-//      and Cauchy weight evaluated by all threads (:549-694, :696-962), warp-shuffle + shared-memory reduction
-//      into the 21 + 6 + 1 normal-equation sums, 6x6 solve / SE(3) update / stop tests on-chip,
-//      removeOutliers with median / MAD by bitonic sort (:988-1067, src/auxiliar.cpp:387-430),
-//      isGoodSolution (:292-305), pose finalisation (:372-391).
+//      Gauss-Newton (:394-431) / robust Gauss-Newton (:433-480): all threads evaluate the per-feature residual,
+//      1x6 Jacobian row and Cauchy weight (:549-694, :696-962); a transposed warp reduction + one shared-memory
+//      pass give the 21 + 6 + 1 normal-equation sums; warp 0 then solves the 6x6 system with lanes-as-columns
+//      Householder QR, updates the SE(3) pose and evaluates the stop tests, all on-chip;
+//      removeOutliers (:988-1067) with median / MAD (src/auxiliar.cpp:387-430) from a segment-local bitonic sort
+//      and a binary search on the V-shaped deviation sequence; isGoodSolution (:292-305) with a parallel-order
+//      Jacobi eigen-solver; pose finalisation (:372-391).
 // Features are read from HBM exactly once per solve; every GN evaluation runs out of shared memory.
-// All arithmetic is double precision like the reference (B200 has a full-rate FP64 pipe); the summation order
-// differs from the reference's sequential lists (fixed tree order -> run-to-run deterministic).
+// All arithmetic is double precision like the reference (B200 has a full-rate FP64 pipe).  Summation order,
+// reciprocal-multiplies and the 6x6 algorithms differ from the reference at rounding level (1e-16 relative),
+// far inside the 1e-5 rad / 1e-4 m bar; the reduction order is fixed, so results are run-to-run deterministic.
 #include <math.h>
 
 #include "common.cuh"
@@ -18,23 +22,27 @@
 
 namespace plstvo {
 
+#define FULL_MASK 0xFFFFFFFFu
+
 // ---- SoA views of the matched lists --------------------------------------------------------------
 struct Feat {
-    double *Px, *Py, *Pz, *pu, *pv, *ps2;                                               // points
-    double *sX, *sY, *sZ, *eX, *eY, *eZ, *l0, *l1, *l2, *su, *sv, *eu, *ev, *ls2;       // lines
+    double *Px, *Py, *Pz, *pu, *pv, *pss;                                          // points (pss = sqrt(sigma2))
+    double *sX, *sY, *sZ, *eX, *eY, *eZ, *l0, *l1, *l2, *oa, *ob, *oc, *lss;       // lines  (oa,ob,oc: overlap)
     uint8_t *inl_p, *inl_l;
     int np, nl;
 };
+constexpr int PT_ARRAYS = 6, LS_ARRAYS = 13;
 
 struct State {
-    double red[K2_WARPS][ACC_N + 1];
-    double acc[ACC_N + 1];   // reduced sums: H upper triangle (21), g (6), e (1), count (1)
+    double red[K2_WARPS][32];
+    double acc[32];          // reduced sums: H upper triangle (21), g (6), e (1), count (1)
     double DT[16];           // pose being optimised
     double DT0[16];          // initial pose of optimizePose
-    double H[36];
+    double H[36];            // normal matrix of the last evaluation (row-major, symmetric)
     double cov[36];
     double err;
-    double scal[4];          // block-wide scalars (median, stdv, mean, ...)
+    double scal[4];
+    double sum[K2_WARPS][4];
     int    ctrl;             // loop control broadcast
     int    n_inl_p, n_inl_l;
     int    evals;
@@ -50,280 +58,380 @@ size_t k2_smem_bytes(int cap_pt, int cap_ls, int sort_cap, bool feat_in_smem) {
     b += (size_t)sort_cap * sizeof(double);
     b += align_up((size_t)cap_pt, 16) + align_up((size_t)cap_ls, 16);                      // inlier flags
     b += align_up((size_t)cap_pt * 2, 16) + align_up((size_t)cap_ls * 2, 16);              // prev index of entry k
-    if (feat_in_smem) b += ((size_t)6 * cap_pt + (size_t)14 * cap_ls) * sizeof(double);
+    if (feat_in_smem) b += ((size_t)PT_ARRAYS * cap_pt + (size_t)LS_ARRAYS * cap_ls) * sizeof(double);
     return b;
 }
 
-// ---- tiny dense algebra (thread 0) -------------------------------------------------------------------
-__device__ void mat4_identity(double* T) {
+size_t k2_feat_stride(int cap_pt, int cap_ls) { return (size_t)PT_ARRAYS * cap_pt + (size_t)LS_ARRAYS * cap_ls; }
+
+__device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(FULL_MASK, v, src); }
+__device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(FULL_MASK, v, m); }
+__device__ __forceinline__ double sum8(double v) {   // sum over each aligned group of 8 lanes
+    v += shfl_xor(v, 1);
+    v += shfl_xor(v, 2);
+    v += shfl_xor(v, 4);
+    return v;
+}
+__device__ __forceinline__ int tri(int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); }   // i <= j
+__device__ __forceinline__ double sel6(const double* a, int i) {   // a[i] with a register-resident a
+    double r = a[0];
+#pragma unroll
+    for (int k = 1; k < 6; k++) r = (i == k) ? a[k] : r;
+    return r;
+}
+__device__ __forceinline__ double sel9(const double* a, int i) {
+    double r = a[0];
+#pragma unroll
+    for (int k = 1; k < 9; k++) r = (i == k) ? a[k] : r;
+    return r;
+}
+
+// ---- small SE(3) helpers: every lane of the calling warp computes the same thing in registers -------------
+__device__ __forceinline__ void mat4_identity(double* T) {
+#pragma unroll
     for (int i = 0; i < 16; i++) T[i] = (i % 5 == 0) ? 1.0 : 0.0;
 }
-__device__ void mat4_mul(const double* A, const double* B, double* C) {
-    double R[16];
+__device__ __forceinline__ void mat4_mul(const double* A, const double* B, double* C) {   // C must not alias A or B
+#pragma unroll
     for (int i = 0; i < 4; i++)
+#pragma unroll
         for (int j = 0; j < 4; j++) {
             double s = 0.0;
+#pragma unroll
             for (int k = 0; k < 4; k++) s += A[i * 4 + k] * B[k * 4 + j];
-            R[i * 4 + j] = s;
+            C[i * 4 + j] = s;
         }
-    for (int i = 0; i < 16; i++) C[i] = R[i];
 }
-__device__ bool mat4_is_identity(const double* T) {
-    for (int i = 0; i < 16; i++)
-        if (T[i] != ((i % 5 == 0) ? 1.0 : 0.0)) return false;
-    return true;
+__device__ __forceinline__ bool mat4_is_identity(const double* T) {
+    bool id = true;
+#pragma unroll
+    for (int i = 0; i < 16; i++) id = id && (T[i] == ((i % 5 == 0) ? 1.0 : 0.0));
+    return id;
 }
-__device__ void mat3_mul(const double* A, const double* B, double* C) {
+__device__ __forceinline__ void mat3_mul(const double* A, const double* B, double* C) {
+#pragma unroll
     for (int i = 0; i < 3; i++)
+#pragma unroll
         for (int j = 0; j < 3; j++) C[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
 }
-__device__ void skew3(double x, double y, double z, double* S) {  // src/auxiliar.cpp:29-44
+__device__ __forceinline__ void skew3(double x, double y, double z, double* S) {  // src/auxiliar.cpp:29-44
     S[0] = 0;  S[1] = -z; S[2] = y;
     S[3] = z;  S[4] = 0;  S[5] = -x;
     S[6] = -y; S[7] = x;  S[8] = 0;
 }
-__device__ void inverse_se3(const double* T, double* Ti) {  // src/auxiliar.cpp:113-122
-    double R[16];
-    mat4_identity(R);
+__device__ __forceinline__ void inverse_se3(const double* T, double* Ti) {  // src/auxiliar.cpp:113-122
+    mat4_identity(Ti);
+#pragma unroll
     for (int i = 0; i < 3; i++) {
         double s = 0.0;
+#pragma unroll
         for (int j = 0; j < 3; j++) {
-            R[i * 4 + j] = T[j * 4 + i];
+            Ti[i * 4 + j] = T[j * 4 + i];
             s += T[j * 4 + i] * T[j * 4 + 3];
         }
-        R[i * 4 + 3] = -s;
+        Ti[i * 4 + 3] = -s;
     }
-    for (int i = 0; i < 16; i++) Ti[i] = R[i];
 }
-__device__ void expmap_se3(const double* x, double* T) {  // src/auxiliar.cpp:124-141, x = [t; w]
-    double t[3] = {x[0], x[1], x[2]};
+__device__ __forceinline__ void expmap_se3(const double* x, double* T) {  // src/auxiliar.cpp:124-141, x = [t; w]
+    double t0 = x[0], t1 = x[1], t2 = x[2];
     double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     const double theta = sqrt(x[3] * x[3] + x[4] * x[4] + x[5] * x[5]);
     if (!(theta < 0.000001)) {
         double s[9], ss[9], V[9];
-        skew3(x[3] / theta, x[4] / theta, x[5] / theta, s);
+        const double it = 1.0 / theta;
+        skew3(x[3] * it, x[4] * it, x[5] * it, s);
         mat3_mul(s, s, ss);
-        const double sn = sin(theta), cs = cos(theta);
+        double sn, cs;
+        sincos(theta, &sn, &cs);
+        const double a = (1.0 - cs) * it, b = (theta - sn) * it;
+#pragma unroll
         for (int i = 0; i < 9; i++) {
             const double I = (i % 4 == 0) ? 1.0 : 0.0;
             R[i] = I + s[i] * sn + ss[i] * (1.0 - cs);
-            V[i] = I + s[i] * (1.0 - cs) / theta + ss[i] * (theta - sn) / theta;
+            V[i] = I + s[i] * a + ss[i] * b;
         }
-        double tv[3];
-        for (int i = 0; i < 3; i++) tv[i] = V[i * 3] * t[0] + V[i * 3 + 1] * t[1] + V[i * 3 + 2] * t[2];
-        t[0] = tv[0]; t[1] = tv[1]; t[2] = tv[2];
+        const double u0 = V[0] * t0 + V[1] * t1 + V[2] * t2, u1 = V[3] * t0 + V[4] * t1 + V[5] * t2,
+                     u2 = V[6] * t0 + V[7] * t1 + V[8] * t2;
+        t0 = u0; t1 = u1; t2 = u2;
     }
     mat4_identity(T);
-    for (int i = 0; i < 3; i++) {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
         for (int j = 0; j < 3; j++) T[i * 4 + j] = R[i * 3 + j];
-        T[i * 4 + 3] = t[i];
-    }
+    T[3] = t0; T[7] = t1; T[11] = t2;
 }
-__device__ void mat3_inverse(const double* A, double* Ai) {
+__device__ __forceinline__ void mat3_inverse(const double* A, double* Ai) {
     const double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
     const double id = 1.0 / (A[0] * c00 + A[1] * c01 + A[2] * c02);
     Ai[0] = c00 * id; Ai[1] = (A[2] * A[7] - A[1] * A[8]) * id; Ai[2] = (A[1] * A[5] - A[2] * A[4]) * id;
     Ai[3] = c01 * id; Ai[4] = (A[0] * A[8] - A[2] * A[6]) * id; Ai[5] = (A[2] * A[3] - A[0] * A[5]) * id;
     Ai[6] = c02 * id; Ai[7] = (A[1] * A[6] - A[0] * A[7]) * id; Ai[8] = (A[0] * A[4] - A[1] * A[3]) * id;
 }
-__device__ void logmap_se3(const double* T, double* x) {  // src/auxiliar.cpp:143-173
-    double R[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, w[3] = {0, 0, 0};
-    for (int i = 0; i < 3; i++)
-        for (int j = 0; j < 3; j++) R[i * 3 + j] = T[i * 4 + j];
-    double cosine = (R[0] + R[4] + R[8] - 1.0) / 2.0;
+__device__ __forceinline__ void logmap_se3(const double* T, double* x) {  // src/auxiliar.cpp:143-173
+    double V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, w0 = 0, w1 = 0, w2 = 0;
+    double cosine = (T[0] + T[5] + T[10] - 1.0) / 2.0;
     if (cosine > 1.0) cosine = 1.0;
     else if (cosine < -1.0) cosine = -1.0;
     double sine = sqrt(1.0 - cosine * cosine);
     if (sine > 1.0) sine = 1.0;
     const double theta = acos(cosine);
     if (theta > 0.000001) {
-        w[0] = theta * (R[7] - R[5]) / (2.0 * sine);
-        w[1] = theta * (R[2] - R[6]) / (2.0 * sine);
-        w[2] = theta * (R[3] - R[1]) / (2.0 * sine);
+        const double f = theta / (2.0 * sine);
+        w0 = f * (T[9] - T[6]);      // skewcoords(theta (R - R^T) / (2 sine)): M(2,1), M(0,2), M(1,0)
+        w1 = f * (T[2] - T[8]);
+        w2 = f * (T[4] - T[1]);
         double s[9], ss[9];
-        skew3(w[0] / theta, w[1] / theta, w[2] / theta, s);
+        const double it = 1.0 / theta;
+        skew3(w0 * it, w1 * it, w2 * it, s);
         mat3_mul(s, s, ss);
-        for (int i = 0; i < 9; i++) {
-            const double I = (i % 4 == 0) ? 1.0 : 0.0;
-            V[i] = I + s[i] * (1.0 - cosine) / theta + ss[i] * (theta - sine) / theta;
-        }
+        const double a = (1.0 - cosine) * it, b = (theta - sine) * it;
+#pragma unroll
+        for (int i = 0; i < 9; i++) V[i] = ((i % 4 == 0) ? 1.0 : 0.0) + s[i] * a + ss[i] * b;
     }
     double Vi[9];
     mat3_inverse(V, Vi);
-    for (int i = 0; i < 3; i++) x[i] = Vi[i * 3] * T[3] + Vi[i * 3 + 1] * T[7] + Vi[i * 3 + 2] * T[11];
-    x[3] = w[0]; x[4] = w[1]; x[5] = w[2];
-}
-__device__ void unccomp_se3(const double* T1, const double* c1, const double* cinc, double* out) {
-    // src/auxiliar.cpp:175-197: cov1 + Ad(T1) covinc Ad(T1)^T, Ad = [R, skew(t) R; 0, R]
-    double Ad[36], S[9], R[9], SR[9], tmp[36];
-    for (int i = 0; i < 3; i++)
-        for (int j = 0; j < 3; j++) R[i * 3 + j] = T1[i * 4 + j];
-    skew3(T1[3], T1[7], T1[11], S);
-    mat3_mul(S, R, SR);
-    for (int i = 0; i < 36; i++) Ad[i] = 0.0;
-    for (int i = 0; i < 3; i++)
-        for (int j = 0; j < 3; j++) {
-            Ad[i * 6 + j] = R[i * 3 + j];
-            Ad[i * 6 + 3 + j] = SR[i * 3 + j];
-            Ad[(i + 3) * 6 + 3 + j] = R[i * 3 + j];
-        }
-    for (int i = 0; i < 6; i++)
-        for (int j = 0; j < 6; j++) {
-            double s = 0.0;
-            for (int k = 0; k < 6; k++) s += Ad[i * 6 + k] * cinc[k * 6 + j];
-            tmp[i * 6 + j] = s;
-        }
-    for (int i = 0; i < 6; i++)
-        for (int j = 0; j < 6; j++) {
-            double s = 0.0;
-            for (int k = 0; k < 6; k++) s += tmp[i * 6 + k] * Ad[j * 6 + k];
-            out[i * 6 + j] = c1[i * 6 + j] + s;
-        }
+    x[0] = Vi[0] * T[3] + Vi[1] * T[7] + Vi[2] * T[11];
+    x[1] = Vi[3] * T[3] + Vi[4] * T[7] + Vi[5] * T[11];
+    x[2] = Vi[6] * T[3] + Vi[7] * T[7] + Vi[8] * T[11];
+    x[3] = w0; x[4] = w1; x[5] = w2;
 }
 
-// ColPivHouseholderQR<Matrix6d>(H).solve(g) + logAbsDeterminant (src/stereoFrameHandler.cpp:417-418, :453-455)
-__device__ void qr6_solve(const double* H, const double* g, double* x, double* log_abs_det) {
-    double A[36], c[6], v[6];
-    int perm[6];
-    for (int i = 0; i < 36; i++) A[i] = H[i];
-    for (int i = 0; i < 6; i++) { c[i] = g[i]; perm[i] = i; }
+// ---- 6x6 algebra on ONE warp, lane j holding column j -----------------------------------------------------
+// ColPivHouseholderQR<Matrix6d>(H).solve(g) and logAbsDeterminant (src/stereoFrameHandler.cpp:417-418, :453-455).
+// Lanes 0..5 hold the columns of H, lane 6 the right-hand side.  Every lane returns x[6] and log|det|.
+__device__ void warp_qr6_solve(const double* Hs /* shared, row-major symmetric */, const double* gs, double* x,
+                               double& log_abs_det) {
+    const int lane = threadIdx.x & 31;
+    double a[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) a[i] = (lane < 6) ? Hs[i * 6 + lane] : (lane == 6 ? gs[i] : 0.0);
+    int pj = lane;
     double maxpivot = 0.0;
+#pragma unroll
     for (int k = 0; k < 6; k++) {
-        int best = k;
-        double bestn = -1.0;
-        for (int j = k; j < 6; j++) {
-            double s = 0.0;
-            for (int i = k; i < 6; i++) s += A[i * 6 + j] * A[i * 6 + j];
-            if (s > bestn) { bestn = s; best = j; }
+        double nrm = 0.0;
+#pragma unroll
+        for (int i = k; i < 6; i++) nrm += a[i] * a[i];
+        if (lane < k || lane > 5) nrm = -1.0;
+        double bv = nrm;
+        int bl = lane;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {   // first maximum over lanes 0..7 (lowest lane on ties, like Eigen's maxCoeff)
+            const double ov = shfl_xor(bv, o);
+            const int ol = __shfl_xor_sync(FULL_MASK, bl, o);
+            if (ov > bv || (ov == bv && ol < bl)) { bv = ov; bl = ol; }
         }
-        if (best != k) {
-            for (int i = 0; i < 6; i++) { const double t = A[i * 6 + k]; A[i * 6 + k] = A[i * 6 + best]; A[i * 6 + best] = t; }
-            const int t = perm[k]; perm[k] = perm[best]; perm[best] = t;
-        }
+        bl = __shfl_sync(FULL_MASK, bl, 0);
+        const int src = (lane == k) ? bl : ((lane == bl) ? k : lane);   // swap columns k <-> bl
+#pragma unroll
+        for (int i = 0; i < 6; i++) a[i] = shfl(a[i], src);
+        pj = __shfl_sync(FULL_MASK, pj, src);
+        double ck[6], v[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) ck[i] = (i >= k) ? shfl(a[i], k) : 0.0;
         double tail = 0.0;
-        for (int i = k + 1; i < 6; i++) tail += A[i * 6 + k] * A[i * 6 + k];
-        const double c0 = A[k * 6 + k];
+#pragma unroll
+        for (int i = k + 1; i < 6; i++) tail += ck[i] * ck[i];
+        const double c0 = ck[k];
         double beta, tau;
-        for (int i = 0; i < 6; i++) v[i] = 0.0;
         if (tail <= 2.2250738585072014e-308) {
             tau = 0.0;
             beta = c0;
+#pragma unroll
+            for (int i = 0; i < 6; i++) v[i] = 0.0;
         } else {
             beta = sqrt(c0 * c0 + tail);
             if (c0 >= 0.0) beta = -beta;
-            for (int i = k + 1; i < 6; i++) v[i] = A[i * 6 + k] / (c0 - beta);
+            const double den = c0 - beta;
+#pragma unroll
+            for (int i = 0; i < 6; i++) v[i] = (i > k) ? ck[i] / den : 0.0;
             tau = (beta - c0) / beta;
         }
         v[k] = 1.0;
-        for (int j = k + 1; j < 6; j++) {
+        if (lane > k && lane <= 6) {
             double s = 0.0;
-            for (int i = k; i < 6; i++) s += v[i] * A[i * 6 + j];
+#pragma unroll
+            for (int i = k; i < 6; i++) s += v[i] * a[i];
             s *= tau;
-            for (int i = k; i < 6; i++) A[i * 6 + j] -= s * v[i];
+#pragma unroll
+            for (int i = k; i < 6; i++) a[i] -= s * v[i];
         }
-        double s = 0.0;
-        for (int i = k; i < 6; i++) s += v[i] * c[i];
-        s *= tau;
-        for (int i = k; i < 6; i++) c[i] -= s * v[i];
-        A[k * 6 + k] = beta;
-        if (fabs(beta) > maxpivot) maxpivot = fabs(beta);
+        if (lane == k) {
+#pragma unroll
+            for (int i = k; i < 6; i++) a[i] = (i == k) ? beta : 0.0;
+        }
+        maxpivot = fmax(maxpivot, fabs(beta));
     }
-    int rank = 0;
+    double d[6], c[6], y[6];
+    int perm[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        d[k] = shfl(a[k], k);
+        c[k] = shfl(a[k], 6);
+        perm[k] = __shfl_sync(FULL_MASK, pj, k);
+    }
     const double thr = maxpivot * (2.220446049250313e-16 * 6.0);
+    int rank = 0;
     double lad = 0.0;
+#pragma unroll
     for (int k = 0; k < 6; k++) {
-        if (fabs(A[k * 6 + k]) > thr) rank++;
-        lad += log(fabs(A[k * 6 + k]));
+        rank += (fabs(d[k]) > thr) ? 1 : 0;
+        lad += log(fabs(d[k]));
     }
-    *log_abs_det = lad;
-    double y[6] = {0, 0, 0, 0, 0, 0};
-    for (int k = rank - 1; k >= 0; k--) {
-        double s2 = c[k];
-        for (int j = k + 1; j < rank; j++) s2 -= A[k * 6 + j] * y[j];
-        y[k] = s2 / A[k * 6 + k];
+    log_abs_det = lad;
+#pragma unroll
+    for (int k = 5; k >= 0; k--) {
+        double s = c[k];
+#pragma unroll
+        for (int j = k + 1; j < 6; j++) {
+            const double rkj = shfl(a[k], j);
+            if (j < rank) s -= rkj * y[j];
+        }
+        y[k] = (k < rank) ? s / d[k] : 0.0;
     }
-    for (int k = 0; k < 6; k++) x[perm[k]] = y[k];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        double xi = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) xi = (perm[k] == i) ? y[k] : xi;
+        x[i] = xi;
+    }
 }
 
-// Matrix6d::inverse() (partial-pivot LU), src/stereoFrameHandler.cpp:429, :470
-__device__ void inv6(const double* Ain, double* Ainv) {
-    double A[36], B[36];
-    for (int i = 0; i < 36; i++) { A[i] = Ain[i]; B[i] = (i % 7 == 0) ? 1.0 : 0.0; }
+// Matrix6d::inverse() (partial-pivot LU), src/stereoFrameHandler.cpp:429, :470.  Lanes 0..5 hold the columns of A,
+// lanes 6..11 the columns of the identity; row operations are the same in every lane.  Result -> out (shared).
+__device__ void warp_inv6(const double* As /* shared row-major */, double* out /* shared row-major */) {
+    const int lane = threadIdx.x & 31;
+    double a[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) a[i] = (lane < 6) ? As[i * 6 + lane] : ((lane - 6 == i) ? 1.0 : 0.0);
+#pragma unroll
     for (int k = 0; k < 6; k++) {
-        int piv = k;
-        double big = fabs(A[k * 6 + k]);
+        int p = k;
+        double big = fabs(a[k]);
+#pragma unroll
         for (int i = k + 1; i < 6; i++)
-            if (fabs(A[i * 6 + k]) > big) { big = fabs(A[i * 6 + k]); piv = i; }
-        if (piv != k)
-            for (int j = 0; j < 6; j++) {
-                double t = A[k * 6 + j]; A[k * 6 + j] = A[piv * 6 + j]; A[piv * 6 + j] = t;
-                t = B[k * 6 + j]; B[k * 6 + j] = B[piv * 6 + j]; B[piv * 6 + j] = t;
-            }
-        const double d = A[k * 6 + k];
+            if (fabs(a[i]) > big) { big = fabs(a[i]); p = i; }
+        p = __shfl_sync(FULL_MASK, p, k);          // the pivot row is decided by column k
+#pragma unroll
+        for (int i = k + 1; i < 6; i++)
+            if (p == i) { const double t = a[k]; a[k] = a[i]; a[i] = t; }
+        const double piv = shfl(a[k], k);
+#pragma unroll
         for (int i = k + 1; i < 6; i++) {
-            const double f = A[i * 6 + k] / d;
-            for (int j = k + 1; j < 6; j++) A[i * 6 + j] -= f * A[k * 6 + j];
-            for (int j = 0; j < 6; j++) B[i * 6 + j] -= f * B[k * 6 + j];
+            const double f = shfl(a[i], k) / piv;
+            a[i] = (lane == k) ? 0.0 : a[i] - f * a[k];
         }
     }
-    for (int j = 0; j < 6; j++)
-        for (int i = 5; i >= 0; i--) {
-            double s = B[i * 6 + j];
-            for (int k = i + 1; k < 6; k++) s -= A[i * 6 + k] * Ainv[k * 6 + j];
-            Ainv[i * 6 + j] = s / A[i * 6 + i];
-        }
+    double xv[6];
+#pragma unroll
+    for (int i = 5; i >= 0; i--) {
+        double s = a[i];
+#pragma unroll
+        for (int m = i + 1; m < 6; m++) s -= shfl(a[i], m) * xv[m];
+        xv[i] = s / shfl(a[i], i);
+    }
+    __syncwarp();
+    if (lane >= 6 && lane < 12) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) out[i * 6 + (lane - 6)] = xv[i];
+    }
+    __syncwarp();
 }
 
-// SelfAdjointEigenSolver<Matrix6d>::eigenvalues(): lower triangle, ascending (cyclic Jacobi)
-__device__ void eig6_sym(const double* Ain, double* w) {
-    double A[36];
-    for (int i = 0; i < 6; i++)
-        for (int j = 0; j <= i; j++) A[i * 6 + j] = A[j * 6 + i] = Ain[i * 6 + j];
+// SelfAdjointEigenSolver<Matrix6d>::eigenvalues(): lower triangle, ascending.  Parallel-order Jacobi: the 15 plane
+// rotations of a sweep are done as 5 rounds of 3 disjoint rotations (round-robin pairing); lane j holds column j.
+__device__ void warp_eig6_sym(const double* Ms /* shared row-major */, double* w /* all lanes: ascending */) {
+    const int lane = threadIdx.x & 31;
+    const int lj = (lane < 6) ? lane : 0;
+    double a[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) a[i] = (lane < 6) ? ((i >= lj) ? Ms[i * 6 + lj] : Ms[lj * 6 + i]) : 0.0;
     for (int sweep = 0; sweep < 60; sweep++) {
-        double off = 0.0, diag = 0.0;
+        double off = 0.0, dg = 0.0;
+#pragma unroll
         for (int i = 0; i < 6; i++) {
-            diag += A[i * 6 + i] * A[i * 6 + i];
-            for (int j = 0; j < i; j++) off += 2.0 * A[i * 6 + j] * A[i * 6 + j];
+            const double v = a[i] * a[i];
+            if (i == lj) dg += v; else off += v;
         }
-        if (!(off > 1e-30 * diag) || off == 0.0) break;   /* off-diagonal mass at rounding level: eigenvalues settled to ~1e-15 */
-        for (int p = 0; p < 5; p++)
-            for (int q = p + 1; q < 6; q++) {
-                const double apq = A[p * 6 + q];
-                if (apq == 0.0) continue;
-                const double tau = (A[q * 6 + q] - A[p * 6 + p]) / (2.0 * apq);
+        if (lane >= 6) { off = 0.0; dg = 0.0; }
+        off = shfl(sum8(off), 0);
+        dg = shfl(sum8(dg), 0);
+        if (!(off > 1e-22 * dg) || off == 0.0) break;   // quadratic convergence: the eigenvalues are settled to ~1e-16
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+            // round-robin pairing of {0..5}: partner of lane j in round r (nibble 5-j), and the pairs (p < q)
+            int partner, p0, q0, p1, q1, p2, q2;
+            if (r == 0) { p0 = 0; q0 = 5; p1 = 1; q1 = 4; p2 = 2; q2 = 3; }
+            else if (r == 1) { p0 = 0; q0 = 4; p1 = 3; q1 = 5; p2 = 1; q2 = 2; }
+            else if (r == 2) { p0 = 0; q0 = 3; p1 = 2; q1 = 4; p2 = 1; q2 = 5; }
+            else if (r == 3) { p0 = 0; q0 = 2; p1 = 1; q1 = 3; p2 = 4; q2 = 5; }
+            else { p0 = 0; q0 = 1; p1 = 2; q1 = 5; p2 = 3; q2 = 4; }
+            partner = lane;
+            if (lane == p0) partner = q0;
+            if (lane == q0) partner = p0;
+            if (lane == p1) partner = q1;
+            if (lane == q1) partner = p1;
+            if (lane == p2) partner = q2;
+            if (lane == q2) partner = p2;
+            const double own_d = sel6(a, lj), other_d = shfl(own_d, partner);
+            // A[p][q] as seen by lane p and by lane q drift apart at rounding level; both lanes must derive the
+            // SAME angle or the update stops being a rotation: use the symmetrised entry
+            const double apq_own = sel6(a, (lane < 6) ? partner : 0);
+            const double apq = 0.5 * (apq_own + shfl(apq_own, partner));
+            const bool is_p = lane < partner;
+            const double app = is_p ? own_d : other_d, aqq = is_p ? other_d : own_d;
+            double cs = 1.0, sn = 0.0;
+            if (lane < 6 && apq != 0.0) {
+                const double tau = (aqq - app) / (2.0 * apq);
                 const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                const double cs = 1.0 / sqrt(1.0 + t * t), sn = t * cs;
-                for (int k = 0; k < 6; k++) {
-                    const double akp = A[k * 6 + p], akq = A[k * 6 + q];
-                    A[k * 6 + p] = cs * akp - sn * akq;
-                    A[k * 6 + q] = sn * akp + cs * akq;
-                }
-                for (int k = 0; k < 6; k++) {
-                    const double apk = A[p * 6 + k], aqk = A[q * 6 + k];
-                    A[p * 6 + k] = cs * apk - sn * aqk;
-                    A[q * 6 + k] = sn * apk + cs * aqk;
-                }
+                cs = 1.0 / sqrt(1.0 + t * t);
+                sn = t * cs;
             }
+#pragma unroll
+            for (int i = 0; i < 6; i++) {   // columns p, q  (A <- A J)
+                const double o = shfl(a[i], partner);
+                a[i] = is_p ? (cs * a[i] - sn * o) : (sn * o + cs * a[i]);
+            }
+            {   // rows p, q of every column  (A <- J^T A), the three disjoint planes of this round
+                const double c0 = shfl(cs, p0), s0 = shfl(sn, p0), c1 = shfl(cs, p1), s1 = shfl(sn, p1),
+                             c2 = shfl(cs, p2), s2 = shfl(sn, p2);
+                double ap = a[p0], aq = a[q0];
+                a[p0] = c0 * ap - s0 * aq; a[q0] = s0 * ap + c0 * aq;
+                ap = a[p1]; aq = a[q1];
+                a[p1] = c1 * ap - s1 * aq; a[q1] = s1 * ap + c1 * aq;
+                ap = a[p2]; aq = a[q2];
+                a[p2] = c2 * ap - s2 * aq; a[q2] = s2 * ap + c2 * aq;
+            }
+        }
     }
-    for (int i = 0; i < 6; i++) w[i] = A[i * 6 + i];
-    for (int i = 1; i < 6; i++) {  // insertion sort, ascending
-        const double v = w[i];
-        int j = i - 1;
-        while (j >= 0 && w[j] > v) { w[j + 1] = w[j]; j--; }
-        w[j + 1] = v;
-    }
+    const double dj = sel6(a, lj);
+#pragma unroll
+    for (int i = 0; i < 6; i++) w[i] = shfl(dj, i);
+#pragma unroll
+    for (int i = 1; i < 6; i++)   // insertion sort, static network; NaNs are left where they are
+#pragma unroll
+        for (int j = i; j > 0; j--) {
+            const double lo = fmin(w[j - 1], w[j]), hi = fmax(w[j - 1], w[j]);
+            const bool nanv = (w[j - 1] != w[j - 1]) || (w[j] != w[j]);
+            if (!nanv) { w[j - 1] = lo; w[j] = hi; }
+        }
 }
 
-// isGoodSolution (src/stereoFrameHandler.cpp:292-305)
-__device__ bool is_good_solution(const double* DT, const double* cov, double err, double* eig_out) {
+// isGoodSolution (src/stereoFrameHandler.cpp:292-305); one warp, every lane returns the verdict
+__device__ bool warp_is_good_solution(const double* DTs, const double* covs, double err, double* eig_out) {
     double w[6];
-    eig6_sym(cov, w);
-    if (eig_out)
+    warp_eig6_sym(covs, w);
+    if (eig_out) {
+#pragma unroll
         for (int i = 0; i < 6; i++) eig_out[i] = w[i];
+    }
     bool finite = true;
+#pragma unroll
     for (int i = 0; i < 16; i++) {
-        const double d = DT[i] - DT[i];
-        if (!(d == d)) finite = false;
+        const double d = DTs[i] - DTs[i];
+        finite = finite && (d == d);
     }
     return !(w[0] < 0.0 || w[5] > 1.0 || err < 0.0 || err > 1.0 || !finite);
 }
@@ -339,38 +447,49 @@ __device__ __forceinline__ void transform(const double* DT, double x, double y, 
     Z = (DT[8] * x + DT[9] * y + DT[10] * z) + DT[11];
 }
 
+// residual norm of point i; also the quantities the Jacobian needs
 __device__ __forceinline__ double point_residual(const Feat& f, int i, const double* DT, const Cam& c, double& X,
-                                                 double& Y, double& Z, double& dx, double& dy) {
+                                                 double& Y, double& Z, double& iz, double& dx, double& dy) {
     transform(DT, f.Px[i], f.Py[i], f.Pz[i], X, Y, Z);
-    dx = (c.cx + c.fx * X / Z) - f.pu[i];   // PinholeStereoCamera::projection (src/pinholeStereoCamera.cpp:231-237)
-    dy = (c.cy + c.fy * Y / Z) - f.pv[i];
+    iz = 1.0 / Z;
+    dx = (c.cx + (c.fx * X) * iz) - f.pu[i];   // PinholeStereoCamera::projection (src/pinholeStereoCamera.cpp:231-237)
+    dy = (c.cy + (c.fy * Y) * iz) - f.pv[i];
     return sqrt(dx * dx + dy * dy);
 }
 
 struct LineRes {
-    double sX, sY, sZ, eX, eY, eZ, spu, spv, epu, epv, ds, de;
+    double sX, sY, sZ, eX, eY, eZ, isz, iez, spu, spv, epu, epv, ds, de;
 };
 
 __device__ __forceinline__ double line_residual(const Feat& f, int i, const double* DT, const Cam& c, LineRes& r) {
     transform(DT, f.sX[i], f.sY[i], f.sZ[i], r.sX, r.sY, r.sZ);
     transform(DT, f.eX[i], f.eY[i], f.eZ[i], r.eX, r.eY, r.eZ);
-    r.spu = c.cx + c.fx * r.sX / r.sZ;
-    r.spv = c.cy + c.fy * r.sY / r.sZ;
-    r.epu = c.cx + c.fx * r.eX / r.eZ;
-    r.epv = c.cy + c.fy * r.eY / r.eZ;
+    r.isz = 1.0 / r.sZ;
+    r.iez = 1.0 / r.eZ;
+    r.spu = c.cx + (c.fx * r.sX) * r.isz;
+    r.spv = c.cy + (c.fy * r.sY) * r.isz;
+    r.epu = c.cx + (c.fx * r.eX) * r.iez;
+    r.epv = c.cy + (c.fy * r.eY) * r.iez;
     const double l0 = f.l0[i], l1 = f.l1[i], l2 = f.l2[i];
     r.ds = l0 * r.spu + l1 * r.spv + l2;   // :621-622
     r.de = l0 * r.epu + l1 * r.epv + l2;
     return sqrt(r.ds * r.ds + r.de * r.de);
 }
 
-__device__ __forceinline__ void jac_aux(double fgz2, double gx, double gy, double gz, double dx, double dy, double* J) {
-    J[0] = +fgz2 * dx * gz;                                   // :582-587 / :636-641
-    J[1] = +fgz2 * dy * gz;
-    J[2] = -fgz2 * (gx * dx + gy * dy);
-    J[3] = -fgz2 * (gx * gy * dx + gy * gy * dy + gz * gz * dy);
-    J[4] = +fgz2 * (gx * gx * dx + gz * gz * dx + gx * gy * dy);
-    J[5] = +fgz2 * (gx * gz * dy - gy * gz * dx);
+// fx / max(homogTh, Z^2) (:577) with the reciprocal of Z already at hand
+__device__ __forceinline__ double fgz2_of(double fx, double Z, double iz, double th) {
+    const double zz = Z * Z;
+    return (zz > th) ? (fx * iz) * iz : fx / th;
+}
+
+// the 6-vector of :582-587 / :636-641 scaled by `sc` (fgz2 and 1/max(homogTh,|e|) folded in by the caller)
+__device__ __forceinline__ void jac_aux(double sc, double gx, double gy, double gz, double dx, double dy, double* J) {
+    J[0] = +sc * dx * gz;
+    J[1] = +sc * dy * gz;
+    J[2] = -sc * (gx * dx + gy * dy);
+    J[3] = -sc * (gx * gy * dx + gy * gy * dy + gz * gz * dy);
+    J[4] = +sc * (gx * gx * dx + gz * gz * dx + gx * gy * dy);
+    J[5] = +sc * (gx * gz * dy - gy * gz * dx);
 }
 
 __device__ __forceinline__ double overlap_from_lambdas(double ls, double le) {
@@ -382,17 +501,23 @@ __device__ __forceinline__ double overlap_from_lambdas(double ls, double le) {
     return hi - lo;
 }
 
-// StereoFrame::lineSegmentOverlap (src/stereoFrame.cpp:510-616) with the PREVIOUS frame's endpoints
-__device__ __forceinline__ double line_overlap(double su, double sv, double eu, double ev, double pu, double pv,
-                                               double qu, double qv) {
+// StereoFrame::lineSegmentOverlap (src/stereoFrame.cpp:510-616): for a fixed previous-frame segment (spl, epl) the
+// parameter lambda of a projected endpoint (u, v) is affine in (u, v) in all three branches; the coefficients are
+// computed once per matched line when the list is built.
+__device__ __forceinline__ void overlap_coeffs(double su, double sv, double eu, double ev, double& oa, double& ob,
+                                               double& oc) {
     const double lx = eu - su, ly = ev - sv;
-    if (fabs(su - eu) < 1.0) return overlap_from_lambdas((pv - sv) / ly, (qv - sv) / ly);
-    if (fabs(sv - ev) < 1.0) return overlap_from_lambdas((pu - su) / lx, (qu - su) / lx);
-    const double a = sv - ev, b = eu - su, c = su * ev - eu * sv;
-    const double lxy = 1.0 / (a * a + b * b);
-    const double sx = (b * (b * pu - a * pv) - a * c) * lxy;
-    const double ex = (b * (b * qu - a * qv) - a * c) * lxy;
-    return overlap_from_lambdas((sx - su) / lx, (ex - su) / lx);
+    if (fabs(su - eu) < 1.0) {          // vertical (:515-544): lambda = (v - sv) / ly
+        oa = 0.0; ob = 1.0 / ly; oc = -sv / ly;
+    } else if (fabs(sv - ev) < 1.0) {   // horizontal (:545-574): lambda = (u - su) / lx
+        oa = 1.0 / lx; ob = 0.0; oc = -su / lx;
+    } else {                            // generic (:575-612): foot of the perpendicular, then (x - su) / lx
+        const double a = sv - ev, b = eu - su, c = su * ev - eu * sv;
+        const double lxy = 1.0 / (a * a + b * b);
+        oa = (b * b * lxy) / lx;
+        ob = (-(a * b) * lxy) / lx;
+        oc = (-(a * c) * lxy - su) / lx;
+    }
 }
 
 __device__ __forceinline__ void accumulate(double* acc, const double* J, double r, double w) {
@@ -408,55 +533,88 @@ __device__ __forceinline__ void accumulate(double* acc, const double* J, double 
     acc[28] += 1.0;
 }
 
-// block-wide sum of ACC_N + 1 doubles per thread -> st.acc (fixed order: deterministic)
+// Transposed warp reduction: 32 values per lane -> lane L ends with the warp total of element L (31 shuffles
+// instead of 5 per element).  Fixed order: deterministic.
+__device__ __forceinline__ double warp_reduce_32(double* v, int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; i++) {
+            const double mine = up ? v[i + off] : v[i];
+            const double send = up ? v[i] : v[i + off];
+            v[i] = mine + shfl_xor(send, off);
+        }
+    }
+    return v[0];
+}
+
+// block-wide sums of the per-thread accumulators -> st.acc[0..28]
 __device__ void block_reduce_acc(State& st, double* acc) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-    for (int k = 0; k <= ACC_N; k++) {
-        double v = acc[k];
-#pragma unroll
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-        if (lane == 0) st.red[warp][k] = v;
-    }
+    const double mine = warp_reduce_32(acc, lane);
+    st.red[warp][lane] = mine;
     __syncthreads();
-    if (tid <= ACC_N) {
+    if (tid < 32) {
         double s = 0.0;
+#pragma unroll
         for (int w = 0; w < K2_WARPS; w++) s += st.red[w][tid];
         st.acc[tid] = s;
     }
     __syncthreads();
 }
 
-__device__ double block_sum(State& st, double v) {
+// up to 4 block-wide sums at once (fixed order)
+template <int N>
+__device__ void block_sum(State& st, double* v) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+#pragma unroll
+    for (int k = 0; k < N; k++)
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v[k] += shfl_xor(v[k], o);
     __syncthreads();
-    if (lane == 0) st.red[warp][0] = v;
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < N; k++) st.sum[warp][k] = v[k];
     __syncthreads();
-    double s = 0.0;
-    for (int w = 0; w < K2_WARPS; w++) s += st.red[w][0];
-    __syncthreads();
-    return s;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < K2_WARPS; w++) s += st.sum[w][k];
+        v[k] = s;
+    }
 }
 
-// ---- bitonic sort in shared memory: a[0..m), m a power of two -----------------------------------------
+// ---- bitonic sort in shared memory: a[0..m), m a power of two >= 32.  Each warp owns a contiguous segment of
+// max(m / K2_WARPS, 32) elements: compare-exchange strides inside a segment only need __syncwarp. --------------
 __device__ void bitonic_sort(double* a, int m) {
-    const int tid = threadIdx.x, nth = blockDim.x;
-    for (int k = 2; k <= m; k <<= 1)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int seg = max(m / K2_WARPS, 32);
+    const int nseg = m / seg;
+    const int base = warp * seg;
+    __syncthreads();
+    for (int k = 2; k <= m; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < m; i += nth) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const double x = a[i], y = a[ixj];
-                    const bool up = ((i & k) == 0);
-                    if ((x > y) == up) {
-                        a[i] = y;
-                        a[ixj] = x;
+            if (warp < nseg) {
+                for (int e = lane; e < seg; e += 32) {
+                    const int i = base + e, ixj = i ^ j;
+                    if (ixj > i) {
+                        const double x = a[i], y = a[ixj];
+                        const bool up = ((i & k) == 0);
+                        if ((x > y) == up) {
+                            a[i] = y;
+                            a[ixj] = x;
+                        }
                     }
                 }
             }
-            __syncthreads();
+            const int next = (j > 1) ? (j >> 1) : k;   // stride of the following stage (k = first stride of the next k)
+            if (j >= seg || next >= seg) __syncthreads();
+            else __syncwarp();
         }
+    }
+    __syncthreads();
 }
 
 __device__ __forceinline__ int pow2_ceil(int n) {
@@ -465,102 +623,97 @@ __device__ __forceinline__ int pow2_ceil(int n) {
     return m;
 }
 
-// median / MAD of the n finite values placed (unordered, padded with +inf up to m) in `buf`:
-// median = sorted[n/2]; stdv = 1.4826 * sorted(|x - median| rounded to float)[n/2]  (src/auxiliar.cpp:396-403)
-__device__ void median_mad(double* buf, int n, int m, State& st) {
-    const int tid = threadIdx.x, nth = blockDim.x;
-    bitonic_sort(buf, m);
-    const double median = buf[n / 2];
-    __syncthreads();
-    for (int i = tid; i < n; i += nth) buf[i] = (double)fabsf((float)(buf[i] - median));
-    __syncthreads();
-    bitonic_sort(buf, m);
-    if (tid == 0) {
-        st.scal[0] = median;
-        st.scal[1] = 1.4826 * buf[n / 2];
+// median / MAD of the n finite values in `buf` SORTED ascending (+inf padding behind them):
+// median = sorted[n/2]; stdv = 1.4826 * sorted(|x - median| rounded to float)[n/2]  (src/auxiliar.cpp:396-403).
+// The deviations of a sorted array form a V (non-increasing up to the median, non-decreasing after it): their n/2-th
+// smallest is the k-th element of the union of two sorted runs, found by binary search by every thread on its own.
+__device__ void median_mad(const double* buf, int n, double& median, double& stdv) {
+    const int h = n / 2;
+    const double med = buf[h];
+    const int nL = h + 1, nR = n - h - 1, k = h;      // left run: buf[h], buf[h-1], ...; right run: buf[h+1], ...
+    auto dev = [&](int idx) -> double { return (double)fabsf((float)(buf[idx] - med)); };
+    auto Lat = [&](int i) -> double { return (i < 0) ? -INFINITY : (i >= nL ? INFINITY : dev(h - i)); };
+    auto Rat = [&](int i) -> double { return (i < 0) ? -INFINITY : (i >= nR ? INFINITY : dev(h + 1 + i)); };
+    // a = how many of the k+1 smallest deviations come from the left run: smallest a with L[a] >= R[k - a]
+    int lo = max(0, k + 1 - nR), hi = min(k + 1, nL);
+    while (lo < hi) {
+        const int a = (lo + hi) >> 1;
+        if (Lat(a) < Rat(k - a)) lo = a + 1;
+        else hi = a;
     }
-    __syncthreads();
+    const double mad = fmax(Lat(lo - 1), Rat(k - lo));
+    median = med;
+    stdv = 1.4826 * mad;
 }
 
 // ---- optimizeFunctions / optimizeFunctionsRobust -------------------------------------------------------
+// pre-weight pass + MAD scales (src/stereoFrameHandler.cpp:707-781)
 __device__ void robust_scales(const Feat& f, State& st, double* sortbuf, const double* DT, const Cam& cam,
                               double& s_p, double& s_l) {
-    // pre-weight pass + MAD scales (src/stereoFrameHandler.cpp:707-781)
     const int tid = threadIdx.x, nth = blockDim.x;
     const double th_min = 0.0001, th_max = sqrt(7.815);
-    {   // points: residual norms of the inliers, order irrelevant for a median
-        const int m = pow2_ceil(max(f.np, 1));
-        double cnt = 0.0;
+    double sc[2];
+    for (int type = 0; type < 2; type++) {
+        const int nn = type ? f.nl : f.np;
+        const int m = pow2_ceil(max(nn, 32));
+        double cnt[1] = {0.0};
         for (int i = tid; i < m; i += nth) {
             double v = INFINITY;
-            if (i < f.np && f.inl_p[i]) {
-                double X, Y, Z, dx, dy;
-                v = point_residual(f, i, DT, cam, X, Y, Z, dx, dy);
-                cnt += 1.0;
+            if (i < nn && (type ? f.inl_l[i] : f.inl_p[i])) {
+                if (type == 0) {
+                    double X, Y, Z, iz, dx, dy;
+                    v = point_residual(f, i, DT, cam, X, Y, Z, iz, dx, dy);
+                } else {
+                    LineRes r;
+                    v = line_residual(f, i, DT, cam, r);
+                }
+                cnt[0] += 1.0;
             }
             sortbuf[i] = v;
         }
-        const int n = (int)block_sum(st, cnt);   // res_p.size(): the inliers only (:710-720)
+        block_sum<1>(st, cnt);                       // res.size(): the inliers only (:710-739)
+        const int n = (int)cnt[0];
+        double s = 0.0;                              // vector_stdv_mad of an empty vector
         if (n > 0) {
-            median_mad(sortbuf, n, m, st);
-            s_p = st.scal[1];
-        } else
-            s_p = 0.0;
-        __syncthreads();
-    }
-    {
-        const int m = pow2_ceil(max(f.nl, 1));
-        double cnt = 0.0;
-        for (int i = tid; i < m; i += nth) {
-            double v = INFINITY;
-            if (i < f.nl && f.inl_l[i]) {
-                LineRes r;
-                v = line_residual(f, i, DT, cam, r);
-                cnt += 1.0;
-            }
-            sortbuf[i] = v;
+            bitonic_sort(sortbuf, m);
+            double med;
+            median_mad(sortbuf, n, med, s);
         }
-        const int n = (int)block_sum(st, cnt);
-        if (n > 0) {
-            median_mad(sortbuf, n, m, st);
-            s_l = st.scal[1];
-        } else
-            s_l = 0.0;
         __syncthreads();
+        sc[type] = fmin(fmax(s, th_min), th_max);
     }
-    if (s_p < th_min) s_p = th_min;
-    if (s_p > th_max) s_p = th_max;
-    if (s_l < th_min) s_l = th_min;
-    if (s_l > th_max) s_l = th_max;
+    s_p = sc[0];
+    s_l = sc[1];
 }
 
 // leaves the reduced sums in st.acc (H upper triangle, g, e, N)
 __device__ void evaluate(const Feat& f, State& st, double* sortbuf, const double* DT, const Cam& cam,
                          double homog_th, bool robust) {
     const int tid = threadIdx.x, nth = blockDim.x;
-    double s_p = 1.0, s_l = 1.0;
-    if (robust) robust_scales(f, st, sortbuf, DT, cam, s_p, s_l);
-
-    double acc[ACC_N + 1];
+    double is_p = 1.0, is_l = 1.0;
+    if (robust) {
+        double s_p, s_l;
+        robust_scales(f, st, sortbuf, DT, cam, s_p, s_l);
+        is_p = 1.0 / s_p;
+        is_l = 1.0 / s_l;
+    }
+    double acc[32];
 #pragma unroll
-    for (int k = 0; k <= ACC_N; k++) acc[k] = 0.0;
+    for (int k = 0; k < 32; k++) acc[k] = 0.0;
 
     for (int i = tid; i < f.np; i += nth) {   // point block (:563-606 / :785-870)
         if (!f.inl_p[i]) continue;
-        double X, Y, Z, dx, dy, J[6];
-        const double n = point_residual(f, i, DT, cam, X, Y, Z, dx, dy);
-        const double fgz2 = cam.fx / fmax(homog_th, Z * Z);
-        jac_aux(fgz2, X, Y, Z, dx, dy, J);
-        const double den = fmax(homog_th, n);
-#pragma unroll
-        for (int k = 0; k < 6; k++) J[k] = J[k] / den;
+        double X, Y, Z, iz, dx, dy, J[6];
+        const double n = point_residual(f, i, DT, cam, X, Y, Z, iz, dx, dy);
+        const double sc = fgz2_of(cam.fx, Z, iz, homog_th) / fmax(homog_th, n);   // fgz2 / max(homogTh, |e|)
+        jac_aux(sc, X, Y, Z, dx, dy, J);
         double r, w;
         if (!robust) {
-            r = n * sqrt(f.ps2[i]);
-            w = 1.0 / (1.0 + r * r);             // robustWeightCauchy (src/auxiliar.cpp:556-559)
+            r = n * f.pss[i];                   // |e| sqrt(sigma2)  (:591)
+            w = 1.0 / (1.0 + r * r);            // robustWeightCauchy (src/auxiliar.cpp:556-559)
         } else {
             r = n;
-            const double x = r / s_p;
+            const double x = r * is_p;
             w = 1.0 / (1.0 + x * x);
         }
         accumulate(acc, J, r, w);
@@ -571,68 +724,77 @@ __device__ void evaluate(const Feat& f, State& st, double* sortbuf, const double
         double Js[6], Je[6], J[6];
         const double n = line_residual(f, i, DT, cam, lr);
         const double lx = f.l0[i], ly = f.l1[i];
-        jac_aux(cam.fx / fmax(homog_th, lr.sZ * lr.sZ), lr.sX, lr.sY, lr.sZ, lx, ly, Js);
-        jac_aux(cam.fx / fmax(homog_th, lr.eZ * lr.eZ), lr.eX, lr.eY, lr.eZ, lx, ly, Je);
-        const double den = fmax(homog_th, n);
+        const double iden = 1.0 / fmax(homog_th, n);
+        jac_aux(fgz2_of(cam.fx, lr.sZ, lr.isz, homog_th) * lr.ds * iden, lr.sX, lr.sY, lr.sZ, lx, ly, Js);
+        jac_aux(fgz2_of(cam.fx, lr.eZ, lr.iez, homog_th) * lr.de * iden, lr.eX, lr.eY, lr.eZ, lx, ly, Je);
 #pragma unroll
-        for (int k = 0; k < 6; k++) J[k] = (Js[k] * lr.ds + Je[k] * lr.de) / den;
+        for (int k = 0; k < 6; k++) J[k] = Js[k] + Je[k];                          // (Js ds + Je de) / max(homogTh, |e|)
         double r, w;
         if (!robust) {
-            r = n * sqrt(f.ls2[i]);
+            r = n * f.lss[i];
             w = 1.0 / (1.0 + r * r);
         } else {
             r = n;
-            const double x = r / s_l;
+            const double x = r * is_l;
             w = 1.0 / (1.0 + x * x);
         }
-        w *= line_overlap(f.su[i], f.sv[i], f.eu[i], f.ev[i], lr.spu, lr.spv, lr.epu, lr.epv);   // :668, :930
+        const double oa = f.oa[i], ob = f.ob[i], oc = f.oc[i];                     // overlap with the PREVIOUS segment (:668)
+        w *= overlap_from_lambdas(oa * lr.spu + ob * lr.spv + oc, oa * lr.epu + ob * lr.epv + oc);
         accumulate(acc, J, r, w);
     }
     block_reduce_acc(st, acc);
 }
 
-// thread 0: unpack st.acc into H (full symmetric), g, err = e / N
-__device__ void unpack_normal_equations(State& st, double* g, double& err) {
-    int k = 0;
-    for (int i = 0; i < 6; i++)
-        for (int j = i; j < 6; j++) {
-            st.H[i * 6 + j] = st.acc[k];
-            st.H[j * 6 + i] = st.acc[k];
-            k++;
+// warp 0: st.acc -> st.H (full symmetric); returns err = e / N
+__device__ __forceinline__ double unpack_normal_equations(State& st, int lane) {
+    if (lane < 6) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            const int lo = min(i, lane), hi = max(i, lane);
+            st.H[i * 6 + lane] = st.acc[tri(lo, hi)];
         }
-    for (int i = 0; i < 6; i++) g[i] = st.acc[21 + i];
-    err = st.acc[27] / st.acc[28];   // e /= (N_l + N_p)  (:692)
+    }
+    __syncwarp();
+    return st.acc[27] / st.acc[28];   // e /= (N_l + N_p)  (:692)
 }
 
-__device__ void apply_increment(double* DT, const double* inc) {   // DT << DT * inverse_se3(expmap_se3(inc))  (:419)
-    double E[16], Ei[16];
+// warp 0: DT << DT * inverse_se3(expmap_se3(inc))  (:419); every lane computes, lanes 0..15 store
+__device__ __forceinline__ void apply_increment(double* DTs, const double* inc, int lane) {
+    double E[16], Ei[16], D[16], R[16];
     expmap_se3(inc, E);
     inverse_se3(E, Ei);
-    mat4_mul(DT, Ei, DT);
+#pragma unroll
+    for (int i = 0; i < 16; i++) D[i] = DTs[i];
+    mat4_mul(D, Ei, R);
+    __syncwarp();
+    double mine = R[0];
+#pragma unroll
+    for (int i = 1; i < 16; i++) mine = (lane == i) ? R[i] : mine;
+    if (lane < 16) DTs[lane] = mine;
+    __syncwarp();
 }
 
 // gaussNewtonOptimization (:394-431) and gaussNewtonOptimizationRobust (:433-480).
-// Pose in st.DT (in/out), covariance to st.cov, error to st.err.  Block-wide; thread 0 runs the 6x6 part.
+// Pose in st.DT (in/out), covariance to st.cov, error to st.err.  Block-wide; warp 0 runs the 6x6 part.
 __device__ void gauss_newton(const Feat& f, State& st, double* sortbuf, const Cam& cam, const PlConfig& cfg,
                              int max_iters, bool robust) {
-    const int tid = threadIdx.x;
-    double err_prev = 999999999.9, err = 0.0;   // thread 0's copies are the authoritative ones
-    double DTstart[16];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double err_prev = 999999999.9, err = 0.0;   // warp 0's copies are the authoritative ones (uniform across its lanes)
     bool good = true, fail_first = false;
-    if (tid == 0) {
-        for (int i = 0; i < 16; i++) DTstart[i] = st.DT[i];
-        for (int i = 0; i < 36; i++) st.H[i] = 0.0;
-        st.evals = 0;
+    double DTstart = 0.0;                       // lane i < 16 of warp 0 keeps entry i of the initial pose
+    if (warp == 0) {
+        if (lane < 16) DTstart = st.DT[lane];
+        for (int i = lane; i < 36; i += 32) st.H[i] = 0.0;
+        if (lane == 0) st.evals = 0;
     }
     for (int it = 0; it < max_iters; it++) {
         const long long t_a = clock64();
         evaluate(f, st, sortbuf, st.DT, cam, cfg.homog_th, robust);
         const long long t_b = clock64();
-        if (tid == 0) {
-            double g[6], inc[6], lad;
+        if (warp == 0) {
+            double inc[6], lad;
             int ctrl = 0;   // 0 continue, 1 stop
-            st.evals++;
-            unpack_normal_equations(st, g, err);
+            err = unpack_normal_equations(st, lane);
             if (!robust) {
                 if (err > err_prev) {
                     ctrl = 1;
@@ -640,8 +802,8 @@ __device__ void gauss_newton(const Feat& f, State& st, double* sortbuf, const Ca
                 } else if ((err < cfg.min_error) || fabs(err - err_prev) < cfg.min_error_change) {
                     ctrl = 1;
                 } else {
-                    qr6_solve(st.H, g, inc, &lad);
-                    apply_increment(st.DT, inc);
+                    warp_qr6_solve(st.H, &st.acc[21], inc, lad);
+                    apply_increment(st.DT, inc, lane);
                     if (sqrt(inc[0] * inc[0] + inc[1] * inc[1] + inc[2] * inc[2]) < cfg.min_error_change &&
                         sqrt(inc[3] * inc[3] + inc[4] * inc[4] + inc[5] * inc[5]) < cfg.min_error_change)
                         ctrl = 1;
@@ -651,41 +813,45 @@ __device__ void gauss_newton(const Feat& f, State& st, double* sortbuf, const Ca
                 if ((fabs(err - err_prev) < cfg.min_error_change) || (err < cfg.min_error)) {
                     ctrl = 1;
                 } else {
-                    qr6_solve(st.H, g, inc, &lad);
+                    warp_qr6_solve(st.H, &st.acc[21], inc, lad);
                     if (lad < 0.0) {
                         good = false;
                         ctrl = 1;
                     } else {
-                        apply_increment(st.DT, inc);
+                        apply_increment(st.DT, inc, lane);
                         double n2 = 0.0;
+#pragma unroll
                         for (int i = 0; i < 6; i++) n2 += inc[i] * inc[i];
                         if (sqrt(n2) < cfg.min_error_change) ctrl = 1;
                         err_prev = err;
                     }
                 }
             }
-            st.ctrl = ctrl;
-            st.tc[2] += t_b - t_a;
-            st.tc[3] += clock64() - t_b;
+            if (lane == 0) {
+                st.ctrl = ctrl;
+                st.evals++;
+                st.tc[2] += t_b - t_a;
+                st.tc[3] += clock64() - t_b;
+            }
         }
         __syncthreads();
         const int ctrl = st.ctrl;
         __syncthreads();
         if (ctrl) break;
     }
-    if (tid == 0) {
+    if (warp == 0) {
         const long long t_c = clock64();
         if (fail_first) {
-            st.err = -1.0;   // :408-409: DT_cov left untouched
+            if (lane == 0) st.err = -1.0;   // :408-409: DT_cov left untouched
         } else if (good) {
-            inv6(st.H, st.cov);
-            st.err = err;
+            warp_inv6(st.H, st.cov);
+            if (lane == 0) st.err = err;
         } else {   // :473-478
-            for (int i = 0; i < 16; i++) st.DT[i] = DTstart[i];
-            st.err = -1.0;
-            for (int i = 0; i < 36; i++) st.cov[i] = (i % 7 == 0) ? 1.0 : 0.0;
+            if (lane < 16) st.DT[lane] = DTstart;
+            if (lane == 0) st.err = -1.0;
+            for (int i = lane; i < 36; i += 32) st.cov[i] = (i % 7 == 0) ? 1.0 : 0.0;
         }
-        st.tc[3] += clock64() - t_c;
+        if (lane == 0) st.tc[3] += clock64() - t_c;
     }
     __syncthreads();
 }
@@ -698,48 +864,45 @@ __device__ void remove_outliers(const Feat& f, State& st, double* sortbuf, const
         const int n = type ? f.nl : f.np;
         if (type == 0 ? !cfg.has_points : !cfg.has_lines) continue;
         if (n == 0) continue;   // vector_mean_stdv_mad of an empty vector: nothing to flag
-        const int m = pow2_ceil(n);
-        // residuals of ALL matched features (inliers or not)
+        const int m = pow2_ceil(max(n, 32));
+        // residuals of ALL matched features (inliers or not), |e| sqrt(sigma2)
         auto residual = [&](int i) -> double {
             if (type == 0) {
-                double X, Y, Z, dx, dy;
-                return point_residual(f, i, DT, cam, X, Y, Z, dx, dy) * sqrt(f.ps2[i]);
+                double X, Y, Z, iz, dx, dy;
+                return point_residual(f, i, DT, cam, X, Y, Z, iz, dx, dy) * f.pss[i];
             }
             LineRes r;
-            return line_residual(f, i, DT, cam, r) * sqrt(f.ls2[i]);
+            return line_residual(f, i, DT, cam, r) * f.lss[i];
         };
         for (int i = tid; i < m; i += nth) sortbuf[i] = (i < n) ? residual(i) : INFINITY;
-        __syncthreads();
-        median_mad(sortbuf, n, m, st);
-        const double stdv = st.scal[1];
-        __syncthreads();
+        bitonic_sort(sortbuf, m);
+        double median, stdv;
+        median_mad(sortbuf, n, median, stdv);
         // mean of the residuals below 2 stdv if there are enough of them, else plain mean (auxiliar.cpp:406-427)
-        double s_sel = 0.0, c_sel = 0.0, s_all = 0.0;
+        double s[3] = {0.0, 0.0, 0.0};
         for (int i = tid; i < n; i += nth) {
             const double r = residual(i);
-            s_all += r;
+            s[2] += r;
             if (r < 2.0 * stdv) {
-                s_sel += r;
-                c_sel += 1.0;
+                s[0] += r;
+                s[1] += 1.0;
             }
         }
-        s_sel = block_sum(st, s_sel);
-        c_sel = block_sum(st, c_sel);
-        s_all = block_sum(st, s_all);
-        const int k = (int)c_sel;
-        const double mean = (k >= (int)(0.2 * (double)n)) ? s_sel / (double)k : s_all / (double)n;
+        block_sum<3>(st, s);
+        const int k = (int)s[1];
+        const double mean = (k >= (int)(0.2 * (double)n)) ? s[0] / (double)k : s[2] / (double)n;
         const double th = cfg.inlier_k * stdv;
-        double removed = 0.0;
+        double removed[1] = {0.0};
         uint8_t* inl = type ? f.inl_l : f.inl_p;
         for (int i = tid; i < n; i += nth)
             if (inl[i] && fabs(residual(i) - mean) > th) {
                 inl[i] = 0;
-                removed += 1.0;
+                removed[0] += 1.0;
             }
-        removed = block_sum(st, removed);
+        block_sum<1>(st, removed);
         if (tid == 0) {
-            if (type == 0) st.n_inl_p -= (int)removed;
-            else st.n_inl_l -= (int)removed;
+            if (type == 0) st.n_inl_p -= (int)removed[0];
+            else st.n_inl_l -= (int)removed[0];
         }
         __syncthreads();
     }
@@ -750,7 +913,7 @@ __device__ int block_exclusive_scan(State& st, int v, int* total) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int inc = v;
     for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        const int t = __shfl_up_sync(FULL_MASK, inc, o);
         if (lane >= o) inc += t;
     }
     __syncthreads();
@@ -768,7 +931,7 @@ __device__ int block_exclusive_scan(State& st, int v, int* total) {
 
 __global__ void __launch_bounds__(K2_THREADS, 1) track_solve_kernel(const SolveParams prm) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int tid = threadIdx.x, nth = blockDim.x;
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const int pair = prm.first_pair + blockIdx.x;
 
     // ---- carve shared memory ----
@@ -785,11 +948,11 @@ __global__ void __launch_bounds__(K2_THREADS, 1) track_solve_kernel(const SolveP
                                   : prm.feat_scratch + (size_t)blockIdx.x * prm.feat_scratch_stride;
     {
         const int cp = prm.cap_pt, cl = prm.cap_ls;
-        f.Px = fb; f.Py = fb + cp; f.Pz = fb + 2 * cp; f.pu = fb + 3 * cp; f.pv = fb + 4 * cp; f.ps2 = fb + 5 * cp;
-        double* lb = fb + 6 * (size_t)cp;
+        f.Px = fb; f.Py = fb + cp; f.Pz = fb + 2 * cp; f.pu = fb + 3 * cp; f.pv = fb + 4 * cp; f.pss = fb + 5 * cp;
+        double* lb = fb + PT_ARRAYS * (size_t)cp;
         f.sX = lb; f.sY = lb + cl; f.sZ = lb + 2 * cl; f.eX = lb + 3 * cl; f.eY = lb + 4 * cl; f.eZ = lb + 5 * cl;
-        f.l0 = lb + 6 * cl; f.l1 = lb + 7 * cl; f.l2 = lb + 8 * cl; f.su = lb + 9 * cl; f.sv = lb + 10 * cl;
-        f.eu = lb + 11 * cl; f.ev = lb + 12 * cl; f.ls2 = lb + 13 * cl;
+        f.l0 = lb + 6 * cl; f.l1 = lb + 7 * cl; f.l2 = lb + 8 * cl; f.oa = lb + 9 * cl; f.ob = lb + 10 * cl;
+        f.oc = lb + 11 * cl; f.lss = lb + 12 * cl;
     }
     const PlConfig& cfg = prm.cfg;
     const Cam cam = {prm.cam.fx, prm.cam.fy, prm.cam.cx, prm.cam.cy};
@@ -829,7 +992,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) track_solve_kernel(const SolveP
                 f.Px[k] = p3[0]; f.Py[k] = p3[1]; f.Pz[k] = p3[2];
                 const double* o2 = C.pt_pl + 2 * (size_t)(b0 + i2);    // pl_obs = curr pl (:148)
                 f.pu[k] = o2[0]; f.pv[k] = o2[1];
-                f.ps2[k] = P.pt_sigma2[a0 + i];                        // PointFeature::safeCopy keeps sigma2
+                f.pss[k] = sqrt(P.pt_sigma2[a0 + i]);                  // PointFeature::safeCopy keeps sigma2
                 f.inl_p[k] = 1;
                 midx_p[k] = (uint16_t)i;
                 k++;
@@ -853,13 +1016,14 @@ __global__ void __launch_bounds__(K2_THREADS, 1) track_solve_kernel(const SolveP
                 f.eX[k] = P.ls_eP[3 * a]; f.eY[k] = P.ls_eP[3 * a + 1]; f.eZ[k] = P.ls_eP[3 * a + 2];
                 const double* le = C.ls_le + 3 * (size_t)(d0 + i2);    // le_obs = curr le (:175)
                 f.l0[k] = le[0]; f.l1[k] = le[1]; f.l2[k] = le[2];
-                f.su[k] = P.ls_spl[2 * a]; f.sv[k] = P.ls_spl[2 * a + 1];
-                f.eu[k] = P.ls_epl[2 * a]; f.ev[k] = P.ls_epl[2 * a + 1];
-                // LineFeature::safeCopy -> ctor re-applies the level rule (src/stereoFeatures.cpp:117-135)
+                overlap_coeffs(P.ls_spl[2 * a], P.ls_spl[2 * a + 1], P.ls_epl[2 * a], P.ls_epl[2 * a + 1], f.oa[k],
+                               f.ob[k], f.oc[k]);
+                // LineFeature::safeCopy -> ctor re-applies the level rule (src/stereoFeatures.cpp:117-135):
+                // sigma2' = 1 / (sigma2 * lsdScale^level)^2
                 double s2 = P.ls_sigma2[a];
                 const int level = P.ls_level ? P.ls_level[a] : 0;
                 for (int l = 0; l < level; l++) s2 *= cfg.lsd_scale;
-                f.ls2[k] = 1.0 / (s2 * s2);
+                f.lss[k] = sqrt(1.0 / (s2 * s2));
                 f.inl_l[k] = 1;
                 midx_l[k] = (uint16_t)i;
                 k++;
@@ -878,30 +1042,24 @@ __global__ void __launch_bounds__(K2_THREADS, 1) track_solve_kernel(const SolveP
         n1l = f.nl = M.ls_off[pair + 1] - c0;
         out_p0 = (size_t)a0;
         out_l0 = (size_t)c0;
-        int cp = 0, cl = 0;
         for (int i = tid; i < f.np; i += nth) {
             const size_t a = (size_t)(a0 + i);
             f.Px[i] = M.pt_P[3 * a]; f.Py[i] = M.pt_P[3 * a + 1]; f.Pz[i] = M.pt_P[3 * a + 2];
             f.pu[i] = M.pt_pl_obs[2 * a]; f.pv[i] = M.pt_pl_obs[2 * a + 1];
-            f.ps2[i] = M.pt_sigma2[a];
-            const uint8_t in = M.pt_inlier ? (M.pt_inlier[a] != 0) : 1;
-            f.inl_p[i] = in;
-            cp += in;
+            f.pss[i] = sqrt(M.pt_sigma2[a]);
+            f.inl_p[i] = M.pt_inlier ? (M.pt_inlier[a] != 0) : 1;
         }
         for (int i = tid; i < f.nl; i += nth) {
             const size_t a = (size_t)(c0 + i);
             f.sX[i] = M.ls_sP[3 * a]; f.sY[i] = M.ls_sP[3 * a + 1]; f.sZ[i] = M.ls_sP[3 * a + 2];
             f.eX[i] = M.ls_eP[3 * a]; f.eY[i] = M.ls_eP[3 * a + 1]; f.eZ[i] = M.ls_eP[3 * a + 2];
             f.l0[i] = M.ls_le_obs[3 * a]; f.l1[i] = M.ls_le_obs[3 * a + 1]; f.l2[i] = M.ls_le_obs[3 * a + 2];
-            f.su[i] = M.ls_spl[2 * a]; f.sv[i] = M.ls_spl[2 * a + 1];
-            f.eu[i] = M.ls_epl[2 * a]; f.ev[i] = M.ls_epl[2 * a + 1];
-            f.ls2[i] = M.ls_sigma2[a];
-            const uint8_t in = M.ls_inlier ? (M.ls_inlier[a] != 0) : 1;
-            f.inl_l[i] = in;
-            cl += in;
+            overlap_coeffs(M.ls_spl[2 * a], M.ls_spl[2 * a + 1], M.ls_epl[2 * a], M.ls_epl[2 * a + 1], f.oa[i], f.ob[i],
+                           f.oc[i]);
+            f.lss[i] = sqrt(M.ls_sigma2[a]);
+            f.inl_l[i] = M.ls_inlier ? (M.ls_inlier[a] != 0) : 1;
         }
         // the reference sets n_inliers from the list sizes; explicit flags only matter to the evaluator
-        (void)cp; (void)cl;
         if (tid == 0) {
             st.n_inl_p = f.np;
             st.n_inl_l = f.nl;
@@ -912,39 +1070,51 @@ __global__ void __launch_bounds__(K2_THREADS, 1) track_solve_kernel(const SolveP
 
     // ---- C. optimizePose (:307-392) ----
     const PlPrior* prior = prm.priors ? &prm.priors[pair] : nullptr;
-    if (tid == 0) {
-        st.out.status = PLSTVO_ST_REFINED;
-        st.out.iters_stage1 = st.out.iters_stage2 = 0;
-        for (int i = 0; i < 36; i++) st.cov[i] = 0.0;
-        st.err = -1.0;
-        mat4_identity(st.DT0);
-        if (cfg.use_motion_model && prior) {   // :317-324
-            for (int i = 0; i < 16; i++) st.DT0[i] = prior->DT[i];
-            if (!is_good_solution(st.DT0, prior->DT_cov, prior->err_norm, nullptr)) mat4_identity(st.DT0);
+    if (warp == 0) {
+        if (lane == 0) {
+            st.out.status = PLSTVO_ST_REFINED;
+            st.out.iters_stage1 = st.out.iters_stage2 = 0;
+            st.err = -1.0;
         }
-        for (int i = 0; i < 16; i++) st.DT[i] = st.DT0[i];
-        st.ctrl = (st.n_inl_p + st.n_inl_l >= cfg.min_features) ? 1 : 0;
+        for (int i = lane; i < 36; i += 32) st.cov[i] = 0.0;
+        bool use_prior = false;
+        if (cfg.use_motion_model && prior) {   // :317-324
+            if (lane < 16) st.DT0[lane] = prior->DT[lane];
+            for (int i = lane; i < 36; i += 32) st.H[i] = prior->DT_cov[i];   // staging for the gate
+            __syncwarp();
+            use_prior = warp_is_good_solution(st.DT0, st.H, prior->err_norm, nullptr);
+            __syncwarp();
+        }
+        if (lane < 16) {
+            const double v = use_prior ? st.DT0[lane] : ((lane % 5 == 0) ? 1.0 : 0.0);
+            st.DT0[lane] = v;
+            st.DT[lane] = v;
+        }
+        if (lane == 0) st.ctrl = (st.n_inl_p + st.n_inl_l >= cfg.min_features) ? 1 : 0;
     }
     __syncthreads();
     const bool robust_mode = (cfg.solver_mode != 0);
     if (st.ctrl) {   // block-uniform
         __syncthreads();
         gauss_newton(f, st, sortbuf, cam, cfg, cfg.max_iters, robust_mode);     // stage 1 on DT_ = DT (:335-338)
-        if (tid == 0) {
-            st.out.iters_stage1 = st.evals;
+        if (warp == 0) {
             const long long t_g = clock64();
-            st.ctrl = is_good_solution(st.DT, st.cov, st.err, nullptr) ? 1 : 0;   // :341
-            st.tc[4] += clock64() - t_g;
+            const bool ok = warp_is_good_solution(st.DT, st.cov, st.err, nullptr);   // :341
+            if (lane == 0) {
+                st.out.iters_stage1 = st.evals;
+                st.ctrl = ok ? 1 : 0;
+                st.tc[4] += clock64() - t_g;
+            }
         }
         __syncthreads();
         if (st.ctrl) {
             __syncthreads();
             const long long t_o = clock64();
             remove_outliers(f, st, sortbuf, st.DT, cam, cfg);                     // at the stage-1 pose (:343)
+            if (tid < 16) st.DT[tid] = st.DT0[tid];                               // stage 2 restarts from DT (:347)
             if (tid == 0) {
                 st.tc[5] += clock64() - t_o;
                 st.ctrl = (st.n_inl_p + st.n_inl_l >= cfg.min_features) ? 1 : 0;
-                for (int i = 0; i < 16; i++) st.DT[i] = st.DT0[i];                // stage 2 restarts from DT (:347)
             }
             __syncthreads();
             if (st.ctrl) {
@@ -952,15 +1122,12 @@ __global__ void __launch_bounds__(K2_THREADS, 1) track_solve_kernel(const SolveP
                 gauss_newton(f, st, sortbuf, cam, cfg, cfg.max_iters_ref, robust_mode);
                 if (tid == 0) st.out.iters_stage2 = st.evals;
             } else {
-                if (tid == 0) {
-                    mat4_identity(st.DT);                                         // :351-355
-                    st.out.status = PLSTVO_ST_FEW_AFTER;
-                }
+                if (tid < 16) st.DT[tid] = (tid % 5 == 0) ? 1.0 : 0.0;            // :351-355
+                if (tid == 0) st.out.status = PLSTVO_ST_FEW_AFTER;
             }
         } else {
             __syncthreads();
-            if (tid == 0)
-                for (int i = 0; i < 16; i++) st.DT[i] = st.DT0[i];
+            if (tid < 16) st.DT[tid] = st.DT0[tid];
             __syncthreads();
             gauss_newton(f, st, sortbuf, cam, cfg, cfg.max_iters_ref, true);      // fallback (:357-359)
             if (tid == 0) {
@@ -969,58 +1136,93 @@ __global__ void __launch_bounds__(K2_THREADS, 1) track_solve_kernel(const SolveP
             }
         }
     } else {
-        if (tid == 0) {
-            mat4_identity(st.DT);                                                 // :364-368
-            st.out.status = PLSTVO_ST_FEW_BEFORE;
-        }
+        if (tid < 16) st.DT[tid] = (tid % 5 == 0) ? 1.0 : 0.0;                    // :364-368
+        if (tid == 0) st.out.status = PLSTVO_ST_FEW_BEFORE;
     }
     __syncthreads();
 
-    // ---- pose finalisation (:372-391) ----
-    if (tid == 0) {
+    // ---- pose finalisation (:372-391), warp 0 ----
+    if (warp == 0) {
         const long long t_f = clock64();
         PlPoseResult& o = st.out;
-        double Tfw_prev[16], Tfw_cov_prev[36];
-        if (prior) {
-            for (int i = 0; i < 16; i++) Tfw_prev[i] = prior->Tfw[i];
-            for (int i = 0; i < 36; i++) Tfw_cov_prev[i] = prior->Tfw_cov[i];
-        } else {   // initialize(): Tfw = I, Tfw_cov = I (:43-44)
-            mat4_identity(Tfw_prev);
-            for (int i = 0; i < 36; i++) Tfw_cov_prev[i] = (i % 7 == 0) ? 1.0 : 0.0;
-        }
-        for (int i = 0; i < 16; i++) o.DT_opt[i] = st.DT[i];
-        double eig[6];
-        if (is_good_solution(st.DT, st.cov, st.err, eig) && !mat4_is_identity(st.DT)) {
-            double Ti[16], x[6], T2[16];
-            inverse_se3(st.DT, Ti);
+        double* Tfw_prev = st.red[0];        // 16 doubles of scratch
+        double* Tfw_cov_prev = st.red[1];    // 36 doubles (runs into red[2], free here)
+        double* Ad = st.red[4];              // 36 doubles (red[4], red[5])
+        if (lane < 16) Tfw_prev[lane] = prior ? prior->Tfw[lane] : ((lane % 5 == 0) ? 1.0 : 0.0);
+        for (int i = lane; i < 36; i += 32)  // initialize(): Tfw = I, Tfw_cov = I (:43-44)
+            Tfw_cov_prev[i] = prior ? prior->Tfw_cov[i] : ((i % 7 == 0) ? 1.0 : 0.0);
+        if (lane < 16) o.DT_opt[lane] = st.DT[lane];
+        __syncwarp();
+        double eig[6], D[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) D[i] = st.DT[i];
+        const bool ok = warp_is_good_solution(st.DT, st.cov, st.err, eig) && !mat4_is_identity(D);
+        if (ok) {
+            double Ti[16], x[6], E[16], T2[16], T3[16], P[16];
+            inverse_se3(D, Ti);
             logmap_se3(Ti, x);
-            expmap_se3(x, o.DT);                                                  // :374
-            for (int i = 0; i < 36; i++) o.DT_cov[i] = st.cov[i];
-            o.err_norm = st.err;
-            mat4_mul(Tfw_prev, o.DT, T2);
+            expmap_se3(x, E);                                                     // :374
+#pragma unroll
+            for (int i = 0; i < 16; i++) P[i] = Tfw_prev[i];
+            mat4_mul(P, E, T2);
             logmap_se3(T2, x);
-            expmap_se3(x, o.Tfw);                                                 // :377
-            unccomp_se3(Tfw_prev, Tfw_cov_prev, st.cov, o.Tfw_cov);               // :378
-            for (int i = 0; i < 6; i++) o.DT_cov_eig[i] = eig[i];
-            o.good = 1;
+            expmap_se3(x, T3);                                                    // :377
+            double e_mine = E[0], t_mine = T3[0];
+#pragma unroll
+            for (int i = 1; i < 16; i++) {
+                e_mine = (lane == i) ? E[i] : e_mine;
+                t_mine = (lane == i) ? T3[i] : t_mine;
+            }
+            if (lane < 16) { o.DT[lane] = e_mine; o.Tfw[lane] = t_mine; }
+            for (int i = lane; i < 36; i += 32) o.DT_cov[i] = st.cov[i];
+            // unccomp_se3 (src/auxiliar.cpp:175-197): cov1 + Ad(T1) covinc Ad(T1)^T, Ad = [R, skew(t) R; 0, R]
+            {
+                double S[9], R3[9], SR[9];
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int j = 0; j < 3; j++) R3[i * 3 + j] = P[i * 4 + j];
+                skew3(P[3], P[7], P[11], S);
+                mat3_mul(S, R3, SR);
+                for (int e = lane; e < 36; e += 32) {
+                    const int i = e / 6, j = e % 6;
+                    double v = 0.0;
+                    if (i < 3 && j < 3) v = sel9(R3, i * 3 + j);
+                    else if (i < 3 && j >= 3) v = sel9(SR, i * 3 + (j - 3));
+                    else if (i >= 3 && j >= 3) v = sel9(R3, (i - 3) * 3 + (j - 3));
+                    Ad[e] = v;
+                }
+            }
+            __syncwarp();
+            for (int e = lane; e < 36; e += 32) {
+                const int i = e / 6, j = e % 6;
+                double s = 0.0;
+                for (int k = 0; k < 6; k++) {
+                    double tk = 0.0;
+                    for (int l = 0; l < 6; l++) tk += Ad[i * 6 + l] * st.cov[l * 6 + k];
+                    s += tk * Ad[j * 6 + k];
+                }
+                o.Tfw_cov[e] = Tfw_cov_prev[e] + s;                               // :378
+            }
+            if (lane < 6) o.DT_cov_eig[lane] = sel6(eig, lane);                   // :379-380
+            if (lane == 0) { o.err_norm = st.err; o.good = 1; }
         } else {
-            mat4_identity(o.DT);
-            for (int i = 0; i < 36; i++) o.DT_cov[i] = 0.0;
-            o.err_norm = -1.0;
-            for (int i = 0; i < 16; i++) o.Tfw[i] = Tfw_prev[i];
-            for (int i = 0; i < 36; i++) o.Tfw_cov[i] = Tfw_cov_prev[i];
-            for (int i = 0; i < 6; i++) o.DT_cov_eig[i] = 0.0;
-            o.good = 0;
+            if (lane < 16) { o.DT[lane] = (lane % 5 == 0) ? 1.0 : 0.0; o.Tfw[lane] = Tfw_prev[lane]; }
+            for (int i = lane; i < 36; i += 32) { o.DT_cov[i] = 0.0; o.Tfw_cov[i] = Tfw_cov_prev[i]; }
+            if (lane < 6) o.DT_cov_eig[lane] = 0.0;
+            if (lane == 0) { o.err_norm = -1.0; o.good = 0; }
         }
-        o.n_matched_pt = f.np;
-        o.n_matched_ls = f.nl;
-        o.n_inliers_pt = st.n_inl_p;
-        o.n_inliers_ls = st.n_inl_l;
-        o.n_inliers = st.n_inl_p + st.n_inl_l;
-        o.reserved = 0;
-        st.tc[6] += clock64() - t_f;
-        if (prm.phase_cycles)
-            for (int i = 0; i < 8; i++) prm.phase_cycles[(size_t)pair * 8 + i] = st.tc[i];
+        if (lane == 0) {
+            o.n_matched_pt = f.np;
+            o.n_matched_ls = f.nl;
+            o.n_inliers_pt = st.n_inl_p;
+            o.n_inliers_ls = st.n_inl_l;
+            o.n_inliers = st.n_inl_p + st.n_inl_l;
+            o.reserved = 0;
+            st.tc[6] += clock64() - t_f;
+            if (prm.phase_cycles)
+                for (int i = 0; i < 8; i++) prm.phase_cycles[(size_t)pair * 8 + i] = st.tc[i];
+        }
     }
     __syncthreads();
     {   // result struct -> HBM, cooperatively (sizeof(PlPoseResult) is a multiple of 8)
@@ -1047,6 +1249,35 @@ __global__ void __launch_bounds__(K2_THREADS, 1) track_solve_kernel(const SolveP
         if (prm.inlier_ls)
             for (int k = tid; k < f.nl; k += nth) prm.inlier_ls[out_l0 + k] = f.inl_l[k];
     }
+}
+
+// test hook: the warp-level 6x6 routines on caller-supplied matrices (one warp per problem)
+__global__ void algebra_selftest_kernel(const double* __restrict__ H, const double* __restrict__ g, int n,
+                                        double* __restrict__ x, double* __restrict__ lad, double* __restrict__ inv,
+                                        double* __restrict__ eig) {
+    __shared__ double sH[36], sg[6], sInv[36];
+    const int lane = threadIdx.x & 31, p = blockIdx.x;
+    if (p >= n) return;
+    for (int i = lane; i < 36; i += 32) sH[i] = H[(size_t)p * 36 + i];
+    if (lane < 6) sg[lane] = g[(size_t)p * 6 + lane];
+    __syncwarp();
+    double xs[6], l, w[6];
+    warp_qr6_solve(sH, sg, xs, l);
+    warp_inv6(sH, sInv);
+    warp_eig6_sym(sH, w);
+    if (lane < 6) {
+        x[(size_t)p * 6 + lane] = sel6(xs, lane);
+        eig[(size_t)p * 6 + lane] = sel6(w, lane);
+    }
+    if (lane == 0) lad[p] = l;
+    for (int i = lane; i < 36; i += 32) inv[(size_t)p * 36 + i] = sInv[i];
+}
+
+cudaError_t launch_algebra_selftest(const double* H, const double* g, int n, double* x, double* lad, double* inv,
+                                    double* eig, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    algebra_selftest_kernel<<<n, 32, 0, stream>>>(H, g, n, x, lad, inv, eig);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_track_solve(const SolveParams& prm, int n_pairs, cudaStream_t stream) {

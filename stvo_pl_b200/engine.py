@@ -57,6 +57,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "plstvo_batch_kernel_times": (C.c_int, [vp, vp, C.c_int, dp, dp, i32p, i32p]),
         "plstvo_gn_eval_stream": (C.c_int, [vp, cam, cfg, mb, dp, C.c_int, dp, dp, dp, C.POINTER(C.c_float)]),
         "plstvo_popc_rate": (C.c_int, [vp, dp]),
+        "plstvo_debug_algebra": (C.c_int, [vp, C.c_int, dp, dp, dp, dp, dp, dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)   # AttributeError if the library does not export a declared symbol
@@ -70,7 +71,7 @@ EXPORTED_SYMBOLS = [
     "plstvo_optimize_pose", "plstvo_track_batch", "plstvo_batch_upload", "plstvo_batch_run",
     "plstvo_batch_run_timed", "plstvo_batch_download", "plstvo_batch_free", "plstvo_synchronize",
     "plstvo_host_alloc", "plstvo_host_free", "plstvo_launch_count", "plstvo_batch_kernel_times",
-    "plstvo_gn_eval_stream", "plstvo_popc_rate"]
+    "plstvo_gn_eval_stream", "plstvo_popc_rate", "plstvo_debug_algebra"]
 
 
 def _p(a: Optional[np.ndarray], typ):
@@ -260,6 +261,16 @@ class Engine:
                                                 iters, _p(H, T.c_double_p), _p(g, T.c_double_p), _p(e, T.c_double_p),
                                                 C.byref(ms)))
         return H, g, e, float(ms.value)
+
+    def debug_algebra(self, H, g):
+        """On-chip 6x6 routines (test hook): returns x = H^-1 g (col-pivot QR), log|det H|, inv(H), eigvals(H)."""
+        H = np.ascontiguousarray(H, np.float64).reshape(-1, 36)
+        g = np.ascontiguousarray(g, np.float64).reshape(-1, 6)
+        n = len(H)
+        x, lad, inv, eig = np.zeros((n, 6)), np.zeros(n), np.zeros((n, 36)), np.zeros((n, 6))
+        self._ck(self.lib.plstvo_debug_algebra(self.ctx, n, _p(H, T.c_double_p), _p(g, T.c_double_p), _p(x, T.c_double_p),
+                                               _p(lad, T.c_double_p), _p(inv, T.c_double_p), _p(eig, T.c_double_p)))
+        return x, lad, inv.reshape(n, 6, 6), eig
 
     def synchronize(self):
         self._ck(self.lib.plstvo_synchronize(self.ctx))

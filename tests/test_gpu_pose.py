@@ -211,3 +211,29 @@ def test_gn_eval_stream_vs_oracle(engine, oracle):
         np.testing.assert_allclose(g[p], gr, rtol=1e-9, atol=1e-9 * np.abs(gr).max())
         assert abs(e[p] - er) < 1e-12
     assert ms > 0
+
+
+def test_onchip_6x6_algebra(engine, oracle):
+    """The warp-level 6x6 routines of K2 (lanes-as-columns Householder QR, LU inverse, parallel-order Jacobi)
+    against numpy and the oracle's restatements."""
+    rng = np.random.default_rng(42)
+    Hs, gs = [], []
+    for k in range(64):
+        J = rng.normal(0, 1, (40, 6)) * np.array([1, 1, 1, 30, 30, 30]) ** (k % 3)
+        Hs.append(J.T @ J)
+        gs.append(rng.normal(0, 1, 6))
+    Hs.append(np.diag([1.0, 2.0, 3.0, 0.0, 0.0, 0.0]))     # rank deficient: truncated solve, like Eigen
+    gs.append(np.ones(6))
+    Hs.append(np.eye(6))
+    gs.append(np.arange(6.0))
+    H, g = np.stack(Hs), np.stack(gs)
+    x, lad, inv, eig = engine.debug_algebra(H, g)
+    for k in range(64):
+        np.testing.assert_allclose(x[k], np.linalg.solve(H[k], g[k]), rtol=1e-9, atol=1e-12)
+        assert abs(lad[k] - np.linalg.slogdet(H[k])[1]) < 1e-9
+        np.testing.assert_allclose(inv[k], np.linalg.inv(H[k]), rtol=1e-8, atol=1e-14)
+        np.testing.assert_allclose(eig[k], np.linalg.eigvalsh(H[k], UPLO="L"), rtol=1e-9, atol=1e-12 * eig[k].max())
+    xo, lado, rank = oracle.qr6_solve(H[64], g[64])
+    np.testing.assert_allclose(x[64], xo, atol=1e-12)
+    np.testing.assert_allclose(x[65], g[65], atol=1e-14)
+    np.testing.assert_allclose(eig[65], np.ones(6), atol=1e-14)
