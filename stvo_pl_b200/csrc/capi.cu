@@ -854,8 +854,8 @@ int plstvo_batch_kernel_times(PlContext* ctx, PlDeviceBatch* db, int iters, doub
         std::vector<long long> h((size_t)ws.B * 8);
         CK(ctx, cudaMemcpyAsync(h.data(), ws.d_phase.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->s_main));
         CK(ctx, cudaStreamSynchronize(ctx->s_main));
-        static const char* names[8] = {"match_finalize", "gather", "gn_eval", "gn_serial", "gates_eig", "outliers", "final", "-"};
-        for (int k = 0; k < 7; ++k) {
+        static const char* names[8] = {"match_finalize", "gather", "gn_eval", "gn_serial", "gates_eig", "outliers", "final", "sort_mad"};
+        for (int k = 0; k < 8; ++k) {
             double sum = 0;
             for (int p = 0; p < ws.B; ++p) sum += (double)h[(size_t)p * 8 + k];
             fprintf(stderr, "[plstvo phase] %-15s %10.0f cycles/pair\n", names[k], sum / ws.B);

@@ -13,6 +13,8 @@
 //
 // Integer work only: XOR + carry-save adders (LOP3) + POPC + IMAD.  No tensor cores: there is no dense
 // contraction here.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "match_finalize.cuh"
 
@@ -40,18 +42,31 @@ __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
 // fold the eight XOR words into five, so 5 POPC instead of 8 per distance and the two pipes end up balanced.
 //   x0+x1+x2 = s0 + 2 c0,  x3+x4+x5 = s1 + 2 c1,  s0+s1+x6 = s2 + 2 c2   (bitwise, per bit position)
 //   popc(x0..x7) = popc(s2) + popc(x7) + 2 (popc(c0) + popc(c1) + popc(c2))
+template <int NPOPC>
 __device__ __forceinline__ uint32_t hamming256_shl16(const uint4& qa, const uint4& qb, const uint4& a, const uint4& b) {
     const uint32_t x0 = qa.x ^ a.x, x1 = qa.y ^ a.y, x2 = qa.z ^ a.z, x3 = qa.w ^ a.w;
     const uint32_t x4 = qb.x ^ b.x, x5 = qb.y ^ b.y, x6 = qb.z ^ b.z, x7 = qb.w ^ b.w;
     const uint32_t s0 = xor3(x0, x1, x2), c0 = maj3(x0, x1, x2);
     const uint32_t s1 = xor3(x3, x4, x5), c1 = maj3(x3, x4, x5);
+    if (NPOPC == 6) {   // two adders: 6 POPC, 4 LOP3
+        const uint32_t ones = __popc(s0) + __popc(s1) + __popc(x6) + __popc(x7);
+        const uint32_t twos = __popc(c0) + __popc(c1);
+        return ones * 65536u + twos * 131072u;
+    }
     const uint32_t s2 = xor3(s0, s1, x6), c2 = maj3(s0, s1, x6);
+    if (NPOPC == 5) {   // three adders: 5 POPC, 6 LOP3
+        const uint32_t ones = __popc(s2) + __popc(x7);
+        const uint32_t twos = __popc(c0) + __popc(c1) + __popc(c2);
+        return ones * 65536u + twos * 131072u;   // IMAD: stays off the ALU pipe
+    }
+    // four adders: 4 POPC, 8 LOP3  (c0 + c1 + c2 = s3 + 2 c3)
+    const uint32_t s3 = xor3(c0, c1, c2), c3 = maj3(c0, c1, c2);
     const uint32_t ones = __popc(s2) + __popc(x7);
-    const uint32_t twos = __popc(c0) + __popc(c1) + __popc(c2);
-    return ones * 65536u + twos * 131072u;   // IMAD: stays off the ALU pipe
+    return ones * 65536u + __popc(s3) * 131072u + __popc(c3) * 262144u;
 }
 
-__global__ void __launch_bounds__(K1_THREADS, 3)
+template <int NPOPC, int MINB>
+__global__ void __launch_bounds__(K1_THREADS, MINB)
 hamming_knn2_kernel(const MatchProblem* __restrict__ problems, const MatchTile* __restrict__ tiles) {
     extern __shared__ __align__(128) uint8_t smem[];
     const MatchTile tile = tiles[blockIdx.x];
@@ -124,7 +139,7 @@ hamming_knn2_kernel(const MatchProblem* __restrict__ problems, const MatchTile* 
                 uint32_t kc[K1_QPT];
 #pragma unroll
                 for (int u = 0; u < K1_QPT; ++u) {
-                    const uint32_t dsh = hamming256_shl16(qa[u], qb[u], a, b);
+                    const uint32_t dsh = hamming256_shl16<NPOPC>(qa[u], qb[u], a, b);
                     // row direction: query u of this thread against train tkey
                     const uint32_t key = dsh | tkey;
                     k2[u] = min(k2[u], max(k1[u], key));
@@ -164,17 +179,37 @@ hamming_knn2_kernel(const MatchProblem* __restrict__ problems, const MatchTile* 
     for (int i = tid; i < nt; i += K1_THREADS) cp[i] = col[i];
 }
 
+typedef void (*K1Fn)(const MatchProblem*, const MatchTile*);
+
+static K1Fn k1_variant() {
+    // tuning knob (PLSTVO_K1_VARIANT = "<popc><minblocks>"); the default is the measured best
+    static K1Fn fn = [] {
+        const char* v = getenv("PLSTVO_K1_VARIANT");
+        const int code = v ? atoi(v) : 54;
+        switch (code) {
+            case 53: return (K1Fn)hamming_knn2_kernel<5, 3>;
+            case 63: return (K1Fn)hamming_knn2_kernel<6, 3>;
+            case 64: return (K1Fn)hamming_knn2_kernel<6, 4>;
+            case 43: return (K1Fn)hamming_knn2_kernel<4, 3>;
+            case 44: return (K1Fn)hamming_knn2_kernel<4, 4>;
+            default: return (K1Fn)hamming_knn2_kernel<5, 4>;
+        }
+    }();
+    return fn;
+}
+
 cudaError_t launch_hamming_knn2(const MatchProblem* problems, const MatchTile* tiles, int n_tiles,
                                 int max_tsplit, cudaStream_t stream) {
     if (n_tiles <= 0) return cudaSuccess;
     const size_t smem = k1_smem_bytes(max_tsplit);
     static size_t configured = 0;
+    K1Fn fn = k1_variant();
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(hamming_knn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    hamming_knn2_kernel<<<n_tiles, K1_THREADS, smem, stream>>>(problems, tiles);
+    fn<<<n_tiles, K1_THREADS, smem, stream>>>(problems, tiles);
     return cudaGetLastError();
 }
 

@@ -47,7 +47,7 @@ struct State {
     int    n_inl_p, n_inl_l;
     int    evals;
     int    scan[K2_WARPS];
-    long long tc[8];         // debug phase timers: 0 match-finalize 1 gather 2 GN-eval 3 GN-serial 4 gates/eig 5 outliers 6 final
+    long long tc[8];         // debug phase timers: 0 match-finalize 1 gather 2 GN-eval 3 GN-serial 4 gates/eig 5 outliers 6 final 7 sort+MAD (inside 5)
     PlPoseResult out;
 };
 
@@ -200,6 +200,7 @@ __device__ __forceinline__ void logmap_se3(const double* T, double* x) {  // src
 // ---- 6x6 algebra on ONE warp, lane j holding column j -----------------------------------------------------
 // ColPivHouseholderQR<Matrix6d>(H).solve(g) and logAbsDeterminant (src/stereoFrameHandler.cpp:417-418, :453-455).
 // Lanes 0..5 hold the columns of H, lane 6 the right-hand side.  Every lane returns x[6] and log|det|.
+template <bool NEED_LAD>
 __device__ void warp_qr6_solve(const double* Hs /* shared, row-major symmetric */, const double* gs, double* x,
                                double& log_abs_det) {
     const int lane = threadIdx.x & 31;
@@ -243,9 +244,9 @@ __device__ void warp_qr6_solve(const double* Hs /* shared, row-major symmetric *
         } else {
             beta = sqrt(c0 * c0 + tail);
             if (c0 >= 0.0) beta = -beta;
-            const double den = c0 - beta;
+            const double iden = 1.0 / (c0 - beta);
 #pragma unroll
-            for (int i = 0; i < 6; i++) v[i] = (i > k) ? ck[i] / den : 0.0;
+            for (int i = 0; i < 6; i++) v[i] = (i > k) ? ck[i] * iden : 0.0;
             tau = (beta - c0) / beta;
         }
         v[k] = 1.0;
@@ -273,11 +274,12 @@ __device__ void warp_qr6_solve(const double* Hs /* shared, row-major symmetric *
     }
     const double thr = maxpivot * (2.220446049250313e-16 * 6.0);
     int rank = 0;
-    double lad = 0.0;
+    double lad = 0.0, rd[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) {
         rank += (fabs(d[k]) > thr) ? 1 : 0;
-        lad += log(fabs(d[k]));
+        if (NEED_LAD) lad += log(fabs(d[k]));
+        rd[k] = 1.0 / d[k];             // six independent reciprocals: pipelined, off the substitution's chain
     }
     log_abs_det = lad;
 #pragma unroll
@@ -288,7 +290,7 @@ __device__ void warp_qr6_solve(const double* Hs /* shared, row-major symmetric *
             const double rkj = shfl(a[k], j);
             if (j < rank) s -= rkj * y[j];
         }
-        y[k] = (k < rank) ? s / d[k] : 0.0;
+        y[k] = (k < rank) ? s * rd[k] : 0.0;
     }
 #pragma unroll
     for (int i = 0; i < 6; i++) {
@@ -802,7 +804,7 @@ __device__ void gauss_newton(const Feat& f, State& st, double* sortbuf, const Ca
                 } else if ((err < cfg.min_error) || fabs(err - err_prev) < cfg.min_error_change) {
                     ctrl = 1;
                 } else {
-                    warp_qr6_solve(st.H, &st.acc[21], inc, lad);
+                    warp_qr6_solve<false>(st.H, &st.acc[21], inc, lad);
                     apply_increment(st.DT, inc, lane);
                     if (sqrt(inc[0] * inc[0] + inc[1] * inc[1] + inc[2] * inc[2]) < cfg.min_error_change &&
                         sqrt(inc[3] * inc[3] + inc[4] * inc[4] + inc[5] * inc[5]) < cfg.min_error_change)
@@ -813,7 +815,7 @@ __device__ void gauss_newton(const Feat& f, State& st, double* sortbuf, const Ca
                 if ((fabs(err - err_prev) < cfg.min_error_change) || (err < cfg.min_error)) {
                     ctrl = 1;
                 } else {
-                    warp_qr6_solve(st.H, &st.acc[21], inc, lad);
+                    warp_qr6_solve<true>(st.H, &st.acc[21], inc, lad);
                     if (lad < 0.0) {
                         good = false;
                         ctrl = 1;
@@ -875,9 +877,11 @@ __device__ void remove_outliers(const Feat& f, State& st, double* sortbuf, const
             return line_residual(f, i, DT, cam, r) * f.lss[i];
         };
         for (int i = tid; i < m; i += nth) sortbuf[i] = (i < n) ? residual(i) : INFINITY;
+        const long long t_s = clock64();
         bitonic_sort(sortbuf, m);
         double median, stdv;
         median_mad(sortbuf, n, median, stdv);
+        if (tid == 0) st.tc[7] += clock64() - t_s;
         // mean of the residuals below 2 stdv if there are enough of them, else plain mean (auxiliar.cpp:406-427)
         double s[3] = {0.0, 0.0, 0.0};
         for (int i = tid; i < n; i += nth) {
@@ -1262,7 +1266,7 @@ __global__ void algebra_selftest_kernel(const double* __restrict__ H, const doub
     if (lane < 6) sg[lane] = g[(size_t)p * 6 + lane];
     __syncwarp();
     double xs[6], l, w[6];
-    warp_qr6_solve(sH, sg, xs, l);
+    warp_qr6_solve<true>(sH, sg, xs, l);
     warp_inv6(sH, sInv);
     warp_eig6_sym(sH, w);
     if (lane < 6) {

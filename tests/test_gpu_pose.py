@@ -237,3 +237,36 @@ def test_onchip_6x6_algebra(engine, oracle):
     np.testing.assert_allclose(x[64], xo, atol=1e-12)
     np.testing.assert_allclose(x[65], g[65], atol=1e-14)
     np.testing.assert_allclose(eig[65], np.ones(6), atol=1e-14)
+
+
+def test_handler_mirror_sequence(engine, oracle):
+    """app/imagesStVO.cpp:88-124 call sequence through the Python mirror of StereoFrameHandler: a 4-frame sequence,
+    poses chained through Tfw, against the oracle run pair by pair with the same priors."""
+    from stvo_pl_b200.handler import StereoFrameHandler
+    from stvo_pl_b200 import matching
+    cfg = T.kitti_config()
+    cam = T.kitti_camera()
+    frames = []
+    for k in range(3):
+        prev, curr, _, _ = synth.make_batch("kitti", 1, first_pair=50 + k, n_pt=500, n_ls=120)
+        frames.append((prev, curr))
+    h = StereoFrameHandler(cam, cfg, engine)
+    h.initialize(frames[0][0])
+    pri = T.identity_priors(1)
+    for k, (prev, curr) in enumerate(frames):
+        h.prev_frame.features = prev          # synthetic pairs are independent: swap in the pair's prev features
+        h.insertStereoPair(curr, k + 1)
+        h.optimizePose()
+        ref = oracle.track_batch(cam, cfg, prev, curr, priors=pri)
+        r = ref["results"][0]
+        ang, tr = R.pose_error(h.curr_frame.DT, r["DT"])
+        assert ang < TIGHT_ANG and tr < TIGHT_TR
+        np.testing.assert_allclose(h.curr_frame.Tfw, r["Tfw"], atol=1e-8)
+        assert h.n_inliers_pt == r["n_inliers_pt"] and len(h.matched_pt) == r["n_matched_pt"]
+        pri["Tfw"][0], pri["Tfw_cov"][0] = r["Tfw"], r["Tfw_cov"]
+        pri["DT"][0], pri["DT_cov"][0], pri["err_norm"][0] = r["DT"], r["DT_cov"], r["err_norm"]
+        h.updateFrame()
+    n, m = matching.match(frames[0][0].pdesc, frames[0][1].pdesc, 0.75, True, engine)
+    np.testing.assert_array_equal(m, oracle.match(frames[0][0].pdesc, frames[0][1].pdesc, 0.75)[1])
+    with pytest.raises(RuntimeError):
+        matching.matchNNR(np.zeros((3, 16), np.uint8), np.zeros((3, 32), np.uint8), 0.9, engine)
