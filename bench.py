@@ -229,8 +229,7 @@ def run_ours(args):
     # ---------------- value: inputs resident in HBM ----------------
     db = eng.upload(cam, cfg, prev, curr)
     if args.kernels_only:
-        db.run()                      # first launches pay module load / local-memory setup: keep them out
-        eng.synchronize()
+        db.kernel_times(iters=1)      # first launches pay module load / local-memory setup: keep them out
         print(json.dumps(db.kernel_times(iters=2)), flush=True)
         db.free()
         eng.close()

@@ -42,6 +42,8 @@ struct Workspace {
     PlConfig cfg{};
     bool has_priors = false;
     bool have_level = false;   // prev->ls_level supplied (null = level 0 everywhere)
+    bool planned = false, planned_features = false;   // plan cache (ws_prepare)
+    int sm_planned = 0;
     // host copies of the offsets
     std::vector<int32_t> p_off1, p_off2, l_off1, l_off2;
     // plan
@@ -177,6 +179,22 @@ int validate_frames(PlContext* ctx, const PlFrameBatch* prev, const PlFrameBatch
 int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfig* cfg, const PlFrameBatch* prev,
                const PlFrameBatch* curr, bool with_features, bool has_priors) {
     const int B = prev->B;
+    // Same shapes and matching parameters as the previous call on this workspace (a video stream, a benchmark loop):
+    // the plan, the partial buffers and their device copies are still valid — skip the rebuild and its uploads.
+    if (ws.planned && ws.B == B && ws.planned_features == with_features && ws.sm_planned == ctx->sm_count &&
+        ws.cfg.has_points == cfg->has_points && ws.cfg.has_lines == cfg->has_lines &&
+        ws.cfg.best_lr_matches == cfg->best_lr_matches && ws.cfg.min_ratio_12_p == cfg->min_ratio_12_p &&
+        ws.cfg.min_ratio_12_l == cfg->min_ratio_12_l && (int)ws.p_off1.size() == B + 1 &&
+        !memcmp(ws.p_off1.data(), prev->pt_off, (size_t)(B + 1) * 4) &&
+        !memcmp(ws.p_off2.data(), curr->pt_off, (size_t)(B + 1) * 4) &&
+        !memcmp(ws.l_off1.data(), prev->ls_off, (size_t)(B + 1) * 4) &&
+        !memcmp(ws.l_off2.data(), curr->ls_off, (size_t)(B + 1) * 4)) {
+        if (cam) ws.cam = *cam;
+        ws.cfg = *cfg;
+        ws.has_priors = has_priors;
+        return 0;
+    }
+    ws.planned = false;
     ws.B = B;
     if (cam) ws.cam = *cam;
     ws.cfg = *cfg;
@@ -235,7 +253,9 @@ int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfi
     ws.cap_pt = std::max(ws.cap_pt, 1);
     ws.cap_ls = std::max(ws.cap_ls, 1);
     ws.sort_cap = pow2_ceil_host(std::max(std::max(ws.cap_pt, ws.cap_ls), (ws.max_n2 + 1) / 2));
-    ws.feat_in_smem = k2_smem_bytes(ws.cap_pt, ws.cap_ls, ws.sort_cap, true) <= ctx->smem_optin;
+    // matched lists live in shared memory when they fit (C2: 152 KB), else in a global scratch slice (C5)
+    static const bool no_smem = getenv("PLSTVO_K2_FEAT_GLOBAL") != nullptr;
+    ws.feat_in_smem = !no_smem && k2_smem_bytes(ws.cap_pt, ws.cap_ls, ws.sort_cap, true) <= ctx->smem_optin;
     if (!ws.feat_in_smem && k2_smem_bytes(ws.cap_pt, ws.cap_ls, ws.sort_cap, false) > ctx->smem_optin)
         return fail(ctx, PLSTVO_E_TOO_LARGE, "frame too large for the per-pair solver's shared memory");
     if (k1_smem_bytes(ws.max_tsplit) > ctx->smem_optin)
@@ -305,6 +325,9 @@ int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfi
         CK(ctx, cudaMemcpyAsync(ws.d_loff1.p, ws.l_off1.data(), (B + 1) * 4, cudaMemcpyHostToDevice, s));
         CK(ctx, cudaMemcpyAsync(ws.d_loff2.p, ws.l_off2.data(), (B + 1) * 4, cudaMemcpyHostToDevice, s));
     }
+    ws.planned = true;
+    ws.planned_features = with_features;
+    ws.sm_planned = ctx->sm_count;
     return 0;
 }
 
@@ -401,18 +424,42 @@ int ws_download_range(PlContext* ctx, Workspace& ws, int p0, int p1, PlPoseResul
     return 0;
 }
 
-int pick_chunk(const Workspace& ws, int sm_count) {
-    // pairs per pipeline chunk: enough K2 CTAs to cover about half the chip, at least 8 chunks per big batch
-    int chunk = std::max(1, sm_count / 2);
-    if (ws.B < chunk) chunk = std::max(1, ws.B);
-    return chunk;
+// Pipeline chunking of the host-buffer entry point: small first chunks (the GPU starts working after a few MB have
+// crossed PCIe), then chunks of about two thirds of the SM count in pairs (K2 runs one pair per SM; the rest of the
+// chip keeps running the next chunk's distance tiles on the other compute stream).
+std::vector<int> chunk_schedule(int B, int sm_count) {
+    static const int forced = getenv("PLSTVO_E2E_CHUNK") ? atoi(getenv("PLSTVO_E2E_CHUNK")) : 0;
+    std::vector<int> bounds{0};
+    if (forced > 0) {
+        for (int p = forced; p < B; p += forced) bounds.push_back(p);
+        bounds.push_back(B);
+        return bounds;
+    }
+    // ramp 1/6, 1/3, 2/3 of the SM count, then equal chunks of at most one pair per SM
+    int p = 0;
+    for (int c = std::max(8, sm_count / 6); c < sm_count && p + c < B; c *= 2) {
+        p += c;
+        bounds.push_back(p);
+    }
+    const int rest = B - p;
+    if (rest > 0) {
+        const int n = (rest + sm_count - 1) / sm_count;
+        for (int k = 1; k <= n; ++k) bounds.push_back(p + (int)((long)rest * k / n));
+    }
+    return bounds;
+}
+
+int run_chunk(const Workspace& ws, int sm_count) {
+    static const int forced = getenv("PLSTVO_RUN_CHUNK") ? atoi(getenv("PLSTVO_RUN_CHUNK")) : 0;
+    if (forced > 0) return forced;
+    return std::max(1, std::max(std::min(ws.B, sm_count), (ws.B + 1) / 2));   // two launches per pass (measured best)
 }
 
 // resident pass: K1 / K2 over the whole batch, chunked over two streams so that the (latency-bound) per-pair
 // solver of chunk i overlaps the (throughput-bound) distance tiles of chunk i+1
 int ws_run(PlContext* ctx, Workspace& ws, bool have_level) {
     if (ws.B == 0) return 0;
-    const int chunk = std::max(pick_chunk(ws, ctx->sm_count), ctx->sm_count);
+    const int chunk = run_chunk(ws, ctx->sm_count);
     cudaEvent_t start = next_event(ctx);
     CK(ctx, cudaEventRecord(start, ctx->s_main));
     CK(ctx, cudaStreamWaitEvent(ctx->s_alt, start, 0));
@@ -540,6 +587,7 @@ int plstvo_match_batch(PlContext* ctx, int B, const uint8_t* d1, const int32_t* 
     Workspace& ws = ctx->ws;
     rc = ws_prepare(ctx, ws, nullptr, &cfg, &a, &b, false, false);
     if (rc) return rc;
+    ws.planned = false;                          // this entry point patches the plan below: never reuse it
     for (auto& pr : ws.problems) pr.nnr = nnr;   // the caller's float, not the config's double
     CK(ctx, cudaMemcpyAsync(ws.d_problems.p, ws.problems.data(), ws.problems.size() * sizeof(MatchProblem),
                             cudaMemcpyHostToDevice, ctx->s_h2d));
@@ -643,11 +691,12 @@ int plstvo_optimize_pose(PlContext* ctx, const PlCamera* cam, const PlConfig* cf
     if (l && (!m->ls_sP || !m->ls_eP || !m->ls_le_obs || !m->ls_spl || !m->ls_epl || !m->ls_sigma2))
         return fail(ctx, PLSTVO_E_INVALID, "line arrays missing");
     const int sort_cap = pow2_ceil_host(std::max(cap_pt, cap_ls));
-    bool in_smem = k2_smem_bytes(cap_pt, cap_ls, sort_cap, true) <= ctx->smem_optin;
+    bool in_smem = getenv("PLSTVO_K2_FEAT_GLOBAL") == nullptr && k2_smem_bytes(cap_pt, cap_ls, sort_cap, true) <= ctx->smem_optin;
     if (!in_smem && k2_smem_bytes(cap_pt, cap_ls, sort_cap, false) > ctx->smem_optin)
         return fail(ctx, PLSTVO_E_TOO_LARGE, "lists too long for the per-pair solver's shared memory");
 
     Workspace& ws = ctx->ws;
+    ws.planned = false;   // the explicit-list path reuses the workspace's buffers with its own layout
     cudaStream_t s = ctx->s_main;
     struct Up { DevBuf* buf; const void* src; size_t bytes; };
     Up ups[] = {{&ws.d_poff1, m->pt_off, (size_t)(B + 1) * 4}, {&ws.d_loff1, m->ls_off, (size_t)(B + 1) * 4},
@@ -713,10 +762,9 @@ int plstvo_track_batch(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg,
     rc = ws_prepare(ctx, ws, cam, cfg, prev, curr, true, priors != nullptr);
     if (rc) return rc;
     const bool have_level = prev->ls_level != nullptr;
-    const int chunk = pick_chunk(ws, ctx->sm_count);
-    int k = 0;
-    for (int p0 = 0; p0 < B; p0 += chunk, ++k) {
-        const int p1 = std::min(B, p0 + chunk);
+    const std::vector<int> bounds = chunk_schedule(B, ctx->sm_count);
+    for (int k = 0; k + 1 < (int)bounds.size(); ++k) {
+        const int p0 = bounds[k], p1 = bounds[k + 1];
         rc = ws_upload_range(ctx, ws, prev, curr, priors, p0, p1, true, ctx->s_h2d);
         if (rc) return rc;
         cudaEvent_t up = next_event(ctx);

@@ -42,7 +42,8 @@ constexpr int K1_QTILE   = K1_THREADS * K1_QPT;    // queries per tile
 constexpr int K1_CHUNK   = 512;                    // train rows per TMA stage (16 KB)
 
 // ---- K2 (track_solve) ------------------------------------------------------------------------------
-constexpr int K2_THREADS = 512;
+constexpr int K2_THREADS = 512;   // one pair per SM at a time: at a few pairs per SM the per-pair latency is what counts
+                                  // (128-thread CTAs x 4 per SM were measured: 3x the latency, same throughput at B = 512)
 constexpr int K2_WARPS   = K2_THREADS / 32;
 constexpr int ACC_N      = 28;    // 21 (upper triangle of J J^T w) + 6 (J r w) + 1 (r^2 w)
 

@@ -301,6 +301,61 @@ __device__ void warp_qr6_solve(const double* Hs /* shared, row-major symmetric *
     }
 }
 
+// Fast path of the solve: H is symmetric positive definite whenever the problem is well posed, so a lanes-as-columns
+// Cholesky (6 rsqrt on the critical path instead of the QR's pivot searches, square roots and divisions) gives the
+// same x to rounding.  Returns false — and the caller runs the column-pivoted QR, which also handles rank deficiency
+// like Eigen — when a pivot is not safely positive.
+__device__ bool warp_chol6_solve(const double* Hs, const double* gs, double* x) {
+    const int lane = threadIdx.x & 31;
+    const int lj = (lane < 6) ? lane : 0;
+    double a[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) a[i] = (lane < 6) ? Hs[i * 6 + lane] : 0.0;
+    double dmax = (lane < 6) ? sel6(a, lj) : 0.0;
+    dmax = fmax(dmax, shfl_xor(dmax, 1));
+    dmax = fmax(dmax, shfl_xor(dmax, 2));
+    dmax = fmax(dmax, shfl_xor(dmax, 4));
+    dmax = shfl(dmax, 0);
+    const double thr = dmax * 1e-12;
+    bool ok = (dmax > 0.0) && (dmax == dmax) && (dmax < 1e300);
+    double rinv[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const double d = shfl(a[k], k);
+        ok = ok && (d > thr);
+        const double r = rsqrt(fmax(d, 1e-300));
+        rinv[k] = r;
+        double lk[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) lk[i] = (i >= k) ? shfl(a[i], k) * r : 0.0;    // column k of L, everywhere
+        const double ljk = sel6(lk, lj);                                            // L[lane][k]
+        if (lane > k && lane < 6) {
+#pragma unroll
+            for (int i = k + 1; i < 6; i++) a[i] -= lk[i] * ljk;
+        }
+        if (lane == k) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) a[i] = lk[i];
+        }
+    }
+    double y[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {          // L y = g
+        double s = gs[k];
+#pragma unroll
+        for (int j = 0; j < k; j++) s -= shfl(a[k], j) * y[j];
+        y[k] = s * rinv[k];
+    }
+#pragma unroll
+    for (int k = 5; k >= 0; k--) {         // L^T x = y
+        double s = y[k];
+#pragma unroll
+        for (int j = k + 1; j < 6; j++) s -= shfl(a[j], k) * x[j];
+        x[k] = s * rinv[k];
+    }
+    return ok;
+}
+
 // Matrix6d::inverse() (partial-pivot LU), src/stereoFrameHandler.cpp:429, :470.  Lanes 0..5 hold the columns of A,
 // lanes 6..11 the columns of the identity; row operations are the same in every lane.  Result -> out (shared).
 __device__ void warp_inv6(const double* As /* shared row-major */, double* out /* shared row-major */) {
@@ -588,9 +643,10 @@ __device__ void block_sum(State& st, double* v) {
     }
 }
 
-// ---- bitonic sort in shared memory: a[0..m), m a power of two >= 32.  Each warp owns a contiguous segment of
-// max(m / K2_WARPS, 32) elements: compare-exchange strides inside a segment only need __syncwarp. --------------
-__device__ void bitonic_sort(double* a, int m) {
+// ---- bitonic sort of a[0..m) in shared memory, m a power of two >= 32 ------------------------------------------
+// Fast path (128 <= m <= 4 * blockDim): thread t keeps positions 4t..4t+3 in registers; strides 1, 2 are in-thread,
+// strides 4..64 are warp shuffles, only strides >= 128 go through shared memory with a block barrier.
+__device__ void bitonic_sort_smem(double* a, int m) {   // generic path: every stride through shared memory
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int seg = max(m / K2_WARPS, 32);
     const int nseg = m / seg;
@@ -611,10 +667,86 @@ __device__ void bitonic_sort(double* a, int m) {
                     }
                 }
             }
-            const int next = (j > 1) ? (j >> 1) : k;   // stride of the following stage (k = first stride of the next k)
+            const int next = (j > 1) ? (j >> 1) : k;   // stride of the following stage
             if (j >= seg || next >= seg) __syncthreads();
             else __syncwarp();
         }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void cmpx(double& x, double& y, bool up) {   // (x, y) -> ascending if up
+    const double lo = fmin(x, y), hi = fmax(x, y);
+    x = up ? lo : hi;
+    y = up ? hi : lo;
+}
+
+__device__ void bitonic_sort(double* a, int m) {
+    const int tid = threadIdx.x, nth = blockDim.x;
+    if (m < 128 || m > 4 * nth) {
+        bitonic_sort_smem(a, m);
+        return;
+    }
+    const bool active = tid < (m >> 2);      // whole warps: m / 4 is a multiple of 32
+    __syncthreads();
+    double v[4];
+    if (active) {
+        const double2 p0 = *reinterpret_cast<const double2*>(a + 4 * tid);
+        const double2 p1 = *reinterpret_cast<const double2*>(a + 4 * tid + 2);
+        v[0] = p0.x; v[1] = p0.y; v[2] = p1.x; v[3] = p1.y;
+    }
+    for (int k = 2; k <= m; k <<= 1) {
+        int j = k >> 1;
+        if (j >= 128) {                       // strides that cross warps: through shared memory
+            if (active) {
+                *reinterpret_cast<double2*>(a + 4 * tid) = make_double2(v[0], v[1]);
+                *reinterpret_cast<double2*>(a + 4 * tid + 2) = make_double2(v[2], v[3]);
+            }
+            __syncthreads();
+            for (; j >= 128; j >>= 1) {
+                for (int p = tid; p < (m >> 1); p += nth) {
+                    const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1)), ixj = i | j;
+                    const double x = a[i], y = a[ixj];
+                    const bool up = ((i & k) == 0);
+                    if ((x > y) == up) {
+                        a[i] = y;
+                        a[ixj] = x;
+                    }
+                }
+                __syncthreads();
+            }
+            if (active) {
+                const double2 p0 = *reinterpret_cast<const double2*>(a + 4 * tid);
+                const double2 p1 = *reinterpret_cast<const double2*>(a + 4 * tid + 2);
+                v[0] = p0.x; v[1] = p0.y; v[2] = p1.x; v[3] = p1.y;
+            }
+        }
+        if (active) {
+            const int i0 = 4 * tid;
+            for (; j >= 4; j >>= 1) {         // partner in another lane of this warp
+                const int lm = j >> 2;
+                const bool up = ((i0 & k) == 0), lower = ((i0 & j) == 0);   // bits >= 2: the same for all four
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const double y = shfl_xor(v[e], lm);
+                    v[e] = (lower == up) ? fmin(v[e], y) : fmax(v[e], y);
+                }
+            }
+            if (k >= 4) {                     // stride 2: (0,2) (1,3)
+                const bool up = ((i0 & k) == 0);
+                cmpx(v[0], v[2], up);
+                cmpx(v[1], v[3], up);
+            }
+            {                                 // stride 1: (0,1) (2,3)
+                const bool up0 = (((i0) & k) == 0), up2 = (((i0 + 2) & k) == 0);
+                cmpx(v[0], v[1], up0);
+                cmpx(v[2], v[3], up2);
+            }
+        }
+    }
+    if (active) {
+        *reinterpret_cast<double2*>(a + 4 * tid) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2*>(a + 4 * tid + 2) = make_double2(v[2], v[3]);
     }
     __syncthreads();
 }
@@ -804,7 +936,7 @@ __device__ void gauss_newton(const Feat& f, State& st, double* sortbuf, const Ca
                 } else if ((err < cfg.min_error) || fabs(err - err_prev) < cfg.min_error_change) {
                     ctrl = 1;
                 } else {
-                    warp_qr6_solve<false>(st.H, &st.acc[21], inc, lad);
+                    if (!warp_chol6_solve(st.H, &st.acc[21], inc)) warp_qr6_solve<false>(st.H, &st.acc[21], inc, lad);
                     apply_increment(st.DT, inc, lane);
                     if (sqrt(inc[0] * inc[0] + inc[1] * inc[1] + inc[2] * inc[2]) < cfg.min_error_change &&
                         sqrt(inc[3] * inc[3] + inc[4] * inc[4] + inc[5] * inc[5]) < cfg.min_error_change)
