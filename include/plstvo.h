@@ -196,6 +196,17 @@ int plstvo_track_batch(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg,
                        PlPoseResult* results, int32_t* m12_pt, int32_t* m12_ls,
                        uint8_t* inlier_pt, uint8_t* inlier_ls);
 
+/* Streaming form of plstvo_track_batch: enqueues the batch (H2D, kernels, D2H) and returns a ticket >= 0 without
+ * waiting, so that the caller can submit batch k+1 (its H2D then overlaps the kernels of batch k) before it waits for
+ * batch k.  Two batches may be in flight per context; all input AND output buffers of a batch must stay valid and
+ * untouched until plstvo_wait(ticket) returned (use plstvo_host_alloc memory: pageable memory makes the copies
+ * synchronous).  This is how a video pipeline drives the engine: frame k+1's features go up while pair k solves. */
+int plstvo_track_batch_async(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg,
+                             const PlFrameBatch* prev, const PlFrameBatch* curr, const PlPrior* priors,
+                             PlPoseResult* results, int32_t* m12_pt, int32_t* m12_ls,
+                             uint8_t* inlier_pt, uint8_t* inlier_ls);
+int plstvo_wait(PlContext* ctx, int ticket);
+
 /* ---- throughput mode: inputs resident in HBM -------------------------------------------------- */
 int  plstvo_batch_upload(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg,
                          const PlFrameBatch* prev, const PlFrameBatch* curr, const PlPrior* priors,

@@ -82,6 +82,10 @@ struct PlContext {
     std::string err;
     int64_t launches = 0;
     Workspace ws;          // reused by the host-buffer entry points
+    Workspace ws_async[2]; // double-buffered workspaces of plstvo_track_batch_async
+    cudaEvent_t slot_done[2] = {nullptr, nullptr};
+    bool slot_busy[2] = {false, false};
+    int next_slot = 0;
     DevBuf scratch;        // misc (popc bench, L2 flush)
     DevBuf gn_in[8], gn_out[4];
 };
@@ -109,13 +113,17 @@ int fail(PlContext* ctx, int code, const char* msg) {
     return code;
 }
 
+// Cross-stream ordering events.  Each one is recorded and immediately waited on by the enqueuing host code, so a ring
+// can be recycled while earlier work is still in flight (a wait captures the record that preceded it).
 cudaEvent_t next_event(PlContext* ctx) {
-    if (ctx->next_event == ctx->events.size()) {
+    constexpr size_t RING = 512;
+    if (ctx->events.size() < RING) {
         cudaEvent_t e;
         cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
         ctx->events.push_back(e);
+        return e;
     }
-    return ctx->events[ctx->next_event++];
+    return ctx->events[ctx->next_event++ % RING];
 }
 
 int pow2_ceil_host(int n) {
@@ -137,7 +145,7 @@ void plan_problem(MatchProblem& pr, int n1, int n2, bool enabled, float nnr, int
         pr.tsplit = 32;
         return;
     }
-    pr.nqb = (n1 + K1_QTILE - 1) / K1_QTILE;
+    pr.nqb = (n1 + k1_queries_per_tile() - 1) / k1_queries_per_tile();
     int ts = ((n2 + 31) / 32) * 32;
     if (tsplit_hint > 0 && tsplit_hint < ts) ts = tsplit_hint;
     pr.tsplit = ts;
@@ -208,8 +216,8 @@ int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfi
     // --- tile split: enough CTAs for a small batch, whole train sets per tile for a big one ---
     long base_tiles = 0;
     for (int p = 0; p < B; ++p) {
-        base_tiles += (ws.p_off1[p + 1] - ws.p_off1[p] + K1_QTILE - 1) / K1_QTILE;
-        base_tiles += (ws.l_off1[p + 1] - ws.l_off1[p] + K1_QTILE - 1) / K1_QTILE;
+        base_tiles += (ws.p_off1[p + 1] - ws.p_off1[p] + k1_queries_per_tile() - 1) / k1_queries_per_tile();
+        base_tiles += (ws.l_off1[p + 1] - ws.l_off1[p] + k1_queries_per_tile() - 1) / k1_queries_per_tile();
     }
     const long want = 3L * ctx->sm_count;   // about one full wave of resident K1 CTAs
     int split = 1;
@@ -515,6 +523,10 @@ void plstvo_destroy(PlContext* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     ctx->ws.release();
+    ctx->ws_async[0].release();
+    ctx->ws_async[1].release();
+    for (auto& e : ctx->slot_done)
+        if (e) cudaEventDestroy(e);
     ctx->scratch.release();
     for (auto& b : ctx->gn_in) b.release();
     for (auto& b : ctx->gn_out) b.release();
@@ -549,7 +561,6 @@ int plstvo_synchronize(PlContext* ctx) {
     CK(ctx, cudaStreamSynchronize(ctx->s_main));
     CK(ctx, cudaStreamSynchronize(ctx->s_alt));
     CK(ctx, cudaStreamSynchronize(ctx->s_d2h));
-    ctx->next_event = 0;
     return 0;
 }
 
@@ -611,7 +622,6 @@ int plstvo_match_batch(PlContext* ctx, int B, const uint8_t* d1, const int32_t* 
     std::vector<int32_t> cnt((size_t)B);
     CK(ctx, cudaMemcpyAsync(cnt.data(), d_counts, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->s_main));
     CK(ctx, cudaStreamSynchronize(ctx->s_main));
-    ctx->next_event = 0;
     long total = 0;
     for (int p = 0; p < B; ++p) {
         if (counts) counts[p] = cnt[p];
@@ -666,7 +676,6 @@ int plstvo_f2f_tracking(PlContext* ctx, const PlConfig* cfg, const PlFrameBatch*
     if (n_matched)
         CK(ctx, cudaMemcpyAsync(n_matched, ctx->scratch.p, (size_t)2 * B * 4, cudaMemcpyDeviceToHost, ctx->s_main));
     CK(ctx, cudaStreamSynchronize(ctx->s_main));
-    ctx->next_event = 0;
     return 0;
 }
 
@@ -749,17 +758,13 @@ int plstvo_optimize_pose(PlContext* ctx, const PlCamera* cam, const PlConfig* cf
     return 0;
 }
 
-int plstvo_track_batch(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlFrameBatch* prev,
-                       const PlFrameBatch* curr, const PlPrior* priors, PlPoseResult* results, int32_t* m12_pt,
-                       int32_t* m12_ls, uint8_t* inlier_pt, uint8_t* inlier_ls) {
-    if (!ctx || !cam || !cfg) return PLSTVO_E_INVALID;
-    CK(ctx, cudaSetDevice(ctx->device));
-    int rc = validate_frames(ctx, prev, curr, true);
-    if (rc) return rc;
+// enqueue one batch on the context's streams: chunked H2D -> K1 -> K2 -> D2H, nothing is waited for
+static int track_enqueue(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfig* cfg,
+                         const PlFrameBatch* prev, const PlFrameBatch* curr, const PlPrior* priors,
+                         PlPoseResult* results, int32_t* m12_pt, int32_t* m12_ls, uint8_t* inlier_pt,
+                         uint8_t* inlier_ls) {
     const int B = prev->B;
-    if (B == 0) return 0;
-    Workspace& ws = ctx->ws;
-    rc = ws_prepare(ctx, ws, cam, cfg, prev, curr, true, priors != nullptr);
+    int rc = ws_prepare(ctx, ws, cam, cfg, prev, curr, true, priors != nullptr);
     if (rc) return rc;
     const bool have_level = prev->ls_level != nullptr;
     const std::vector<int> bounds = chunk_schedule(B, ctx->sm_count);
@@ -781,10 +786,54 @@ int plstvo_track_batch(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg,
         rc = ws_download_range(ctx, ws, p0, p1, results, m12_pt, m12_ls, inlier_pt, inlier_ls, ctx->s_d2h);
         if (rc) return rc;
     }
-    CK(ctx, cudaStreamSynchronize(ctx->s_d2h));
-    CK(ctx, cudaStreamSynchronize(ctx->s_main));
-    CK(ctx, cudaStreamSynchronize(ctx->s_alt));
-    ctx->next_event = 0;
+    return 0;
+}
+
+int plstvo_track_batch(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlFrameBatch* prev,
+                       const PlFrameBatch* curr, const PlPrior* priors, PlPoseResult* results, int32_t* m12_pt,
+                       int32_t* m12_ls, uint8_t* inlier_pt, uint8_t* inlier_ls) {
+    if (!ctx || !cam || !cfg) return PLSTVO_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc = validate_frames(ctx, prev, curr, true);
+    if (rc) return rc;
+    if (prev->B == 0) return 0;
+    rc = track_enqueue(ctx, ctx->ws, cam, cfg, prev, curr, priors, results, m12_pt, m12_ls, inlier_pt, inlier_ls);
+    if (rc) return rc;
+    CK(ctx, cudaStreamSynchronize(ctx->s_d2h));   // every chunk's D2H waited for its compute, which waited for its H2D
+    return 0;
+}
+
+int plstvo_track_batch_async(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlFrameBatch* prev,
+                             const PlFrameBatch* curr, const PlPrior* priors, PlPoseResult* results, int32_t* m12_pt,
+                             int32_t* m12_ls, uint8_t* inlier_pt, uint8_t* inlier_ls) {
+    if (!ctx || !cam || !cfg) return PLSTVO_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc = validate_frames(ctx, prev, curr, true);
+    if (rc) return rc;
+    const int slot = ctx->next_slot;
+    ctx->next_slot ^= 1;
+    if (ctx->slot_busy[slot]) {   // the caller skipped plstvo_wait on the batch that used this slot: finish it first
+        CK(ctx, cudaEventSynchronize(ctx->slot_done[slot]));
+        ctx->slot_busy[slot] = false;
+    }
+    if (!ctx->slot_done[slot]) CK(ctx, cudaEventCreateWithFlags(&ctx->slot_done[slot], cudaEventDisableTiming));
+    if (prev->B > 0) {
+        rc = track_enqueue(ctx, ctx->ws_async[slot], cam, cfg, prev, curr, priors, results, m12_pt, m12_ls, inlier_pt,
+                           inlier_ls);
+        if (rc) return rc;
+    }
+    CK(ctx, cudaEventRecord(ctx->slot_done[slot], ctx->s_d2h));
+    ctx->slot_busy[slot] = true;
+    return slot;
+}
+
+int plstvo_wait(PlContext* ctx, int ticket) {
+    if (!ctx || ticket < 0 || ticket > 1) return PLSTVO_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->slot_busy[ticket]) {
+        CK(ctx, cudaEventSynchronize(ctx->slot_done[ticket]));
+        ctx->slot_busy[ticket] = false;
+    }
     return 0;
 }
 
@@ -819,7 +868,6 @@ int plstvo_batch_upload(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg
 int plstvo_batch_run(PlContext* ctx, PlDeviceBatch* db) {
     if (!ctx || !db) return PLSTVO_E_INVALID;
     CK(ctx, cudaSetDevice(ctx->device));
-    ctx->next_event = 0;
     return ws_run(ctx, db->ws, db->ws.have_level);
 }
 
@@ -836,8 +884,7 @@ int plstvo_batch_run_timed(PlContext* ctx, PlDeviceBatch* db, int iters, int flu
     if (!flush_l2) {
         CK(ctx, cudaEventRecord(e0, ctx->s_main));
         for (int i = 0; i < iters; ++i) {
-            ctx->next_event = 0;
-            int rc = ws_run(ctx, db->ws, db->ws.have_level);
+                    int rc = ws_run(ctx, db->ws, db->ws.have_level);
             if (rc) return rc;
         }
         CK(ctx, cudaEventRecord(e1, ctx->s_main));
@@ -849,8 +896,7 @@ int plstvo_batch_run_timed(PlContext* ctx, PlDeviceBatch* db, int iters, int flu
         for (int i = 0; i < iters; ++i) {
             CK(ctx, cudaMemsetAsync(ctx->scratch.p, i & 0xFF, flush_bytes, ctx->s_main));
             CK(ctx, cudaEventRecord(e0, ctx->s_main));
-            ctx->next_event = 0;
-            int rc = ws_run(ctx, db->ws, db->ws.have_level);
+                    int rc = ws_run(ctx, db->ws, db->ws.have_level);
             if (rc) return rc;
             CK(ctx, cudaEventRecord(e1, ctx->s_main));
             CK(ctx, cudaEventSynchronize(e1));
@@ -861,7 +907,6 @@ int plstvo_batch_run_timed(PlContext* ctx, PlDeviceBatch* db, int iters, int flu
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    ctx->next_event = 0;
     *ms_total = (float)total;
     return 0;
 }

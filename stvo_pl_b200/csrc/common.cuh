@@ -37,8 +37,7 @@ struct MatchTile {
 };
 
 constexpr int K1_THREADS = 256;
-constexpr int K1_QPT     = 2;                      // query descriptors per thread, in registers
-constexpr int K1_QTILE   = K1_THREADS * K1_QPT;    // queries per tile
+int k1_queries_per_tile();                         // K1_THREADS x (query descriptors per thread: 2 or 4), see match.cu
 constexpr int K1_CHUNK   = 512;                    // train rows per TMA stage (16 KB)
 
 // ---- K2 (track_solve) ------------------------------------------------------------------------------

@@ -65,9 +65,10 @@ __device__ __forceinline__ uint32_t hamming256_shl16(const uint4& qa, const uint
     return ones * 65536u + __popc(s3) * 131072u + __popc(c3) * 262144u;
 }
 
-template <int NPOPC, int MINB>
+template <int NPOPC, int MINB, int QPT>
 __global__ void __launch_bounds__(K1_THREADS, MINB)
 hamming_knn2_kernel(const MatchProblem* __restrict__ problems, const MatchTile* __restrict__ tiles) {
+    constexpr int QTILE = K1_THREADS * QPT;
     extern __shared__ __align__(128) uint8_t smem[];
     const MatchTile tile = tiles[blockIdx.x];
     const MatchProblem pr = problems[tile.problem];
@@ -82,12 +83,12 @@ hamming_knn2_kernel(const MatchProblem* __restrict__ problems, const MatchTile* 
     const int t0 = tile.tb * pr.tsplit;
     const int nt = min(pr.tsplit, pr.n2 - t0);
 
-    // two query rows per thread: q and q + K1_THREADS (consecutive lanes -> consecutive rows: coalesced)
-    uint4 qa[K1_QPT], qb[K1_QPT];
-    uint32_t qkey[K1_QPT];
+    // QPT query rows per thread: q, q + K1_THREADS, ... (consecutive lanes -> consecutive rows: coalesced)
+    uint4 qa[QPT], qb[QPT];
+    uint32_t qkey[QPT];
 #pragma unroll
-    for (int u = 0; u < K1_QPT; ++u) {
-        const int q = tile.qb * K1_QTILE + u * K1_THREADS + tid;
+    for (int u = 0; u < QPT; ++u) {
+        const int q = tile.qb * QTILE + u * K1_THREADS + tid;
         qa[u] = make_uint4(0, 0, 0, 0);
         qb[u] = qa[u];
         qkey[u] = KEY_NONE;   // invalid rows: OR-ing this saturates the column key
@@ -114,9 +115,9 @@ hamming_knn2_kernel(const MatchProblem* __restrict__ problems, const MatchTile* 
         bulk_g2s(stage0, src, bytes, &bars[0]);
     }
 
-    uint32_t k1[K1_QPT], k2[K1_QPT];
+    uint32_t k1[QPT], k2[QPT];
 #pragma unroll
-    for (int u = 0; u < K1_QPT; ++u) k1[u] = k2[u] = KEY_NONE;
+    for (int u = 0; u < QPT; ++u) k1[u] = k2[u] = KEY_NONE;
 
     for (int c = 0; c < nchunks; ++c) {
         if (tid == 0 && c + 1 < nchunks) {  // prefetch the next stage (its buffer was released by the
@@ -136,9 +137,9 @@ hamming_knn2_kernel(const MatchProblem* __restrict__ problems, const MatchTile* 
             for (int j = 0; j < gn; ++j) {
                 const uint4 a = s[(g + j) * 2], b = s[(g + j) * 2 + 1];   // same row for every lane: broadcast
                 const uint32_t tkey = tbase + (uint32_t)(g + j);
-                uint32_t kc[K1_QPT];
+                uint32_t kc[QPT];
 #pragma unroll
-                for (int u = 0; u < K1_QPT; ++u) {
+                for (int u = 0; u < QPT; ++u) {
                     const uint32_t dsh = hamming256_shl16<NPOPC>(qa[u], qb[u], a, b);
                     // row direction: query u of this thread against train tkey
                     const uint32_t key = dsh | tkey;
@@ -146,9 +147,18 @@ hamming_knn2_kernel(const MatchProblem* __restrict__ problems, const MatchTile* 
                     k1[u] = min(k1[u], key);
                     kc[u] = dsh | qkey[u];
                 }
-                // column direction: this train against the warp's 64 queries.  Thread-local pair sort, then two
-                // warp REDUX.MIN: the runner-up is the minimum once every lane has dropped the winner.
-                const uint32_t lo = min(kc[0], kc[1]), hi = max(kc[0], kc[1]);
+                // column direction: this train against the warp's 32 * QPT queries.  Thread-local top-2, then two
+                // warp REDUX.MIN: the runner-up is the minimum once the winner's lane has swapped in its own second.
+                uint32_t lo, hi;
+                if (QPT == 2) {
+                    lo = min(kc[0], kc[1]);
+                    hi = max(kc[0], kc[1]);
+                } else {
+                    const uint32_t a0 = min(kc[0], kc[1]), b0 = max(kc[0], kc[1]);
+                    const uint32_t a1 = min(kc[QPT - 2], kc[QPT - 1]), b1 = max(kc[QPT - 2], kc[QPT - 1]);
+                    lo = min(a0, a1);
+                    hi = min(max(a0, a1), min(b0, b1));
+                }
                 const uint32_t m1 = __reduce_min_sync(0xFFFFFFFFu, lo);
                 const uint32_t m2 = __reduce_min_sync(0xFFFFFFFFu, lo == m1 ? hi : lo);
                 wstage[j] = make_uint2(m1, m2);   // warp-uniform value, every lane stores the same word: one wavefront
@@ -171,8 +181,8 @@ hamming_knn2_kernel(const MatchProblem* __restrict__ problems, const MatchTile* 
     }
 
 #pragma unroll
-    for (int u = 0; u < K1_QPT; ++u) {
-        const int q = tile.qb * K1_QTILE + u * K1_THREADS + tid;
+    for (int u = 0; u < QPT; ++u) {
+        const int q = tile.qb * QTILE + u * K1_THREADS + tid;
         if (q < pr.n1) pr.rowpart[(size_t)tile.tb * pr.n1 + q] = make_uint2(k1[u], k2[u]);
     }
     uint2* cp = pr.colpart + (size_t)tile.qb * pr.n2 + t0;
@@ -181,21 +191,28 @@ hamming_knn2_kernel(const MatchProblem* __restrict__ problems, const MatchTile* 
 
 typedef void (*K1Fn)(const MatchProblem*, const MatchTile*);
 
-static K1Fn k1_variant() {
-    // tuning knob (PLSTVO_K1_VARIANT = "<popc><minblocks>"); the default is the measured best
-    static K1Fn fn = [] {
+// tuning knob PLSTVO_K1_VARIANT = "<queries per thread><popc per distance><min blocks per SM>"; default = measured best
+static int k1_variant_code() {
+    static const int code = [] {
         const char* v = getenv("PLSTVO_K1_VARIANT");
-        const int code = v ? atoi(v) : 54;
-        switch (code) {
-            case 53: return (K1Fn)hamming_knn2_kernel<5, 3>;
-            case 63: return (K1Fn)hamming_knn2_kernel<6, 3>;
-            case 64: return (K1Fn)hamming_knn2_kernel<6, 4>;
-            case 43: return (K1Fn)hamming_knn2_kernel<4, 3>;
-            case 44: return (K1Fn)hamming_knn2_kernel<4, 4>;
-            default: return (K1Fn)hamming_knn2_kernel<5, 4>;
-        }
+        return v ? atoi(v) : 253;
     }();
-    return fn;
+    return code;
+}
+
+int k1_queries_per_tile() { return K1_THREADS * ((k1_variant_code() / 100 == 4) ? 4 : 2); }
+
+static K1Fn k1_variant() {
+    switch (k1_variant_code()) {
+        case 254: return (K1Fn)hamming_knn2_kernel<5, 4, 2>;
+        case 263: return (K1Fn)hamming_knn2_kernel<6, 3, 2>;
+        case 243: return (K1Fn)hamming_knn2_kernel<4, 3, 2>;
+        case 452: return (K1Fn)hamming_knn2_kernel<5, 2, 4>;
+        case 462: return (K1Fn)hamming_knn2_kernel<6, 2, 4>;
+        case 442: return (K1Fn)hamming_knn2_kernel<4, 2, 4>;
+        case 453: return (K1Fn)hamming_knn2_kernel<5, 3, 4>;
+        default: return (K1Fn)hamming_knn2_kernel<5, 3, 2>;
+    }
 }
 
 cudaError_t launch_hamming_knn2(const MatchProblem* problems, const MatchTile* tiles, int n_tiles,

@@ -45,6 +45,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "plstvo_f2f_tracking": (C.c_int, [vp, cfg, fb, fb, i32p, i32p, i32p]),
         "plstvo_optimize_pose": (C.c_int, [vp, cam, cfg, mb, vp, vp, u8p, u8p]),
         "plstvo_track_batch": (C.c_int, [vp, cam, cfg, fb, fb, vp, vp, i32p, i32p, u8p, u8p]),
+        "plstvo_track_batch_async": (C.c_int, [vp, cam, cfg, fb, fb, vp, vp, i32p, i32p, u8p, u8p]),
+        "plstvo_wait": (C.c_int, [vp, C.c_int]),
         "plstvo_batch_upload": (C.c_int, [vp, cam, cfg, fb, fb, vp, C.POINTER(vp)]),
         "plstvo_batch_run": (C.c_int, [vp, vp]),
         "plstvo_batch_run_timed": (C.c_int, [vp, vp, C.c_int, C.c_int, C.POINTER(C.c_float)]),
@@ -68,7 +70,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
 EXPORTED_SYMBOLS = [
     "plstvo_version", "plstvo_create", "plstvo_destroy", "plstvo_last_error", "plstvo_default_config",
     "plstvo_kitti_config", "plstvo_match_nnr", "plstvo_match", "plstvo_match_batch", "plstvo_f2f_tracking",
-    "plstvo_optimize_pose", "plstvo_track_batch", "plstvo_batch_upload", "plstvo_batch_run",
+    "plstvo_optimize_pose", "plstvo_track_batch", "plstvo_track_batch_async", "plstvo_wait", "plstvo_batch_upload", "plstvo_batch_run",
     "plstvo_batch_run_timed", "plstvo_batch_download", "plstvo_batch_free", "plstvo_synchronize",
     "plstvo_host_alloc", "plstvo_host_free", "plstvo_launch_count", "plstvo_batch_kernel_times",
     "plstvo_gn_eval_stream", "plstvo_popc_rate", "plstvo_debug_algebra"]
@@ -236,6 +238,23 @@ class Engine:
             _p(out["m12_pt"], T.c_int32_p), _p(out["m12_ls"], T.c_int32_p), _p(out["inlier_pt"], T.c_uint8_p),
             _p(out["inlier_ls"], T.c_uint8_p)))
         return out
+
+    def track_batch_async(self, cam, cfg, prev: T.FrameBatch, curr: T.FrameBatch, out, priors=None) -> int:
+        """Streaming form: returns a ticket; `prev`, `curr`, `priors` and `out` must stay alive and untouched until
+        wait(ticket).  Use pinned arrays (self.pinned) so that the copies really are asynchronous."""
+        pc, cc = prev.as_c(), curr.as_c()
+        self._keep = getattr(self, "_keep", {})
+        t = self._ck(self.lib.plstvo_track_batch_async(
+            self.ctx, C.byref(cam), C.byref(cfg), C.byref(pc), C.byref(cc),
+            priors.ctypes.data if priors is not None else None, out["results"].ctypes.data,
+            _p(out["m12_pt"], T.c_int32_p), _p(out["m12_ls"], T.c_int32_p), _p(out["inlier_pt"], T.c_uint8_p),
+            _p(out["inlier_ls"], T.c_uint8_p)))
+        self._keep[t] = (prev, curr, priors, out)
+        return t
+
+    def wait(self, ticket: int):
+        self._ck(self.lib.plstvo_wait(self.ctx, ticket))
+        getattr(self, "_keep", {}).pop(ticket, None)
 
     def pinned_outputs(self, prev: T.FrameBatch):
         e = self.pinned.empty

@@ -270,3 +270,23 @@ def test_handler_mirror_sequence(engine, oracle):
     np.testing.assert_array_equal(m, oracle.match(frames[0][0].pdesc, frames[0][1].pdesc, 0.75)[1])
     with pytest.raises(RuntimeError):
         matching.matchNNR(np.zeros((3, 16), np.uint8), np.zeros((3, 32), np.uint8), 0.9, engine)
+
+
+def test_async_streaming_equals_blocking_call(engine):
+    """plstvo_track_batch_async / plstvo_wait with two batches in flight give the blocking call's bytes."""
+    cfg = T.kitti_config()
+    batches = [synth.make_batch("kitti", 5, first_pair=10 * k, n_pt=400 + 50 * k, n_ls=100)[:2] for k in range(4)]
+    cam = T.kitti_camera()
+    ref = [engine.track_batch(cam, cfg, p, c) for p, c in batches]
+    pinned = [(engine.pinned.pin_frames(p), engine.pinned.pin_frames(c), engine.pinned_outputs(p)) for p, c in batches]
+    pending = None
+    for k, (p, c, o) in enumerate(pinned):
+        t = engine.track_batch_async(cam, cfg, p, c, o)
+        if pending is not None:
+            engine.wait(pending)
+        pending = t
+    engine.wait(pending)
+    for k in range(4):
+        for key in ("m12_pt", "m12_ls", "inlier_pt", "inlier_ls"):
+            np.testing.assert_array_equal(pinned[k][2][key], ref[k][key])
+        assert pinned[k][2]["results"].tobytes() == ref[k]["results"].tobytes()
