@@ -206,3 +206,48 @@ def make_batch(shape_name: str, B: int, *, first_pair: int = 0, **kw):
         p, c, T = make_pair(shape, first_pair + i, **kw)
         prevs.append(p); currs.append(c); Ts.append(T)
     return _stack(prevs), _stack(currs), np.stack(Ts) if Ts else np.zeros((0, 4, 4)), camera_for(shape.camera)
+
+
+def make_matched_batch(shape_name: str, B: int, *, first_pair: int = 0, noise_px=0.5, outlier_frac=0.10):
+    """Explicit matched_pt / matched_ls lists for B problems of one configuration, without descriptors (the C5
+    roofline run streams GN evaluations and never matches).  Vectorised: cheap even for 1024 x (8000 + 2000).
+    Returns (MatchedBatch, T_gt[B,4,4], camera)."""
+    from .types import MatchedBatch
+    shape = SHAPES[shape_name]
+    cam = camera_for(shape.camera)
+    rng = np.random.default_rng(BASE_SEED + 1000 * shape.config_id + 500000 + first_pair)
+    W, H, n, m = cam.width, cam.height, shape.n_pt, shape.n_ls
+    Ts = np.stack([expmap_se3(np.concatenate([rng.normal(shape.t_mean, shape.t_std), rng.normal(0.0, shape.w_std, 3)]))
+                   for _ in range(B)])
+    lo, hi = shape.depth
+
+    def lift(u, v, z):
+        return back_projection(cam, u, v, np.maximum(cam.b * cam.fx / z, 1.0))
+
+    def tf(P, b_idx):
+        R, t = Ts[b_idx, :3, :3], Ts[b_idx, :3, 3]
+        return np.einsum("nij,nj->ni", R, P) + t
+
+    # points
+    N = B * n
+    bi = np.repeat(np.arange(B), n)
+    u, v = rng.uniform(0, W, N), rng.uniform(0, H, N)
+    P = lift(u, v, np.exp(rng.uniform(np.log(lo), np.log(hi), N)))
+    obs = projection(cam, tf(P, bi)) + rng.normal(0, noise_px, (N, 2))
+    out = rng.random(N) < outlier_frac
+    obs[out] = np.stack([rng.uniform(0, W, out.sum()), rng.uniform(0, H, out.sum())], 1)
+    # lines
+    M = B * m
+    li = np.repeat(np.arange(B), m)
+    su, sv = rng.uniform(0, W, M), rng.uniform(0, H, M)
+    z = np.exp(rng.uniform(np.log(lo), np.log(hi), M))
+    length, ang = rng.uniform(30, 150, M), rng.uniform(0.2, np.pi - 0.2, M)
+    spl = np.stack([su, sv], 1)
+    epl = spl + np.stack([length * np.cos(ang), length * np.sin(ang)], 1)
+    sP, eP = lift(su, sv, z), lift(epl[:, 0], epl[:, 1], z * rng.uniform(0.85, 1.15, M))
+    s_obs = projection(cam, tf(sP, li)) + rng.normal(0, noise_px, (M, 2))
+    e_obs = projection(cam, tf(eP, li)) + rng.normal(0, noise_px, (M, 2))
+    mb = MatchedBatch(pt_off=np.arange(B + 1) * n, ls_off=np.arange(B + 1) * m, pt_P=P, pt_pl_obs=obs,
+                      pt_sigma2=np.ones(N), ls_sP=sP, ls_eP=eP, ls_le_obs=_line_eq(s_obs, e_obs), ls_spl=spl,
+                      ls_epl=epl, ls_sigma2=np.ones(M))
+    return mb, Ts, cam

@@ -290,3 +290,19 @@ def test_async_streaming_equals_blocking_call(engine):
         for key in ("m12_pt", "m12_ls", "inlier_pt", "inlier_ls"):
             np.testing.assert_array_equal(pinned[k][2][key], ref[k][key])
         assert pinned[k][2]["results"].tobytes() == ref[k]["results"].tobytes()
+
+
+def test_explicit_lists_c5_size(engine, oracle):
+    """C5-size explicit lists (8000 + 2000 per problem): the solver's global-scratch variant against the oracle."""
+    cfg = T.kitti_config()
+    mb, Ts, cam = synth.make_matched_batch("hd", 3)
+    rc, ref, rp, rl = oracle.optimize_pose(cam, cfg, mb)
+    res, ip, il = engine.optimize_pose(cam, cfg, mb)
+    for p in range(3):
+        assert res["status"][p] == ref["status"][p] and res["good"][p] == ref["good"][p] == 1
+        ang, tr = R.pose_error(res["DT"][p], ref["DT"][p])
+        assert ang < TIGHT_ANG and tr < TIGHT_TR
+        ang, tr = R.pose_error(res["DT_opt"][p], Ts[p])
+        assert ang < 1e-3 and tr < 1e-2
+    np.testing.assert_array_equal(ip, rp)
+    np.testing.assert_array_equal(il, rl)

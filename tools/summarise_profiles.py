@@ -78,7 +78,7 @@ def main():
         lines.append("")
         with open(os.path.join(PROF, f"{tag}_launches.csv"), "w") as f:
             f.write(open(ll).read())
-    for kname in ("k1", "k2"):
+    for kname in ("k1", "k2", "gn"):
         rep = os.path.join(OUT, f"prof_{kname}_{tag}.ncu-rep")
         if not os.path.exists(rep):
             continue
@@ -98,7 +98,7 @@ def main():
                        "dram_bytes_write": num("dram__bytes_write.sum"), "capture": f"profiles/{tag}_ncu_summary.md",
                        "launch": m.get("launch__grid_size", "")},
                       open(os.path.join(PROF, "k1_traffic.json"), "w"), indent=1)
-    for name in (f"bench_{tag}.json", f"bench_ref_{tag}.json"):
+    for name in (f"bench_{tag}.json", f"bench_ref_{tag}.json", f"bench_c5_{tag}.json"):
         p = os.path.join(OUT, name)
         if os.path.exists(p):
             txt = open(p).read().strip()
