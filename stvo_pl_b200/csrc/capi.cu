@@ -1051,12 +1051,19 @@ int plstvo_gn_eval_stream(PlContext* ctx, const PlCamera* cam, const PlConfig* c
                   bufs[4].as<double>(), m->pt_inlier ? bufs[11].as<uint8_t>() : nullptr, bufs[5].as<double>(),
                   bufs[6].as<double>(), bufs[7].as<double>(), bufs[8].as<double>(), bufs[9].as<double>(),
                   bufs[10].as<double>(), m->ls_inlier ? bufs[12].as<uint8_t>() : nullptr};
-    // blocks per problem: enough CTAs for >= 4 waves of the chip, at least ~512 features per CTA
-    size_t max_feat = 1;
+    // fp32-packed records (32 B per point, 64 B per line), packed once on the device
+    static DevBuf rec_pt, rec_ls;
+    CK(ctx, rec_pt.ensure(std::max<size_t>(n * 32, 32)));
+    CK(ctx, rec_ls.ensure(std::max<size_t>(l * 64, 64)));
+    CK(ctx, launch_pack_records(md, (int)n, (int)l, rec_pt.as<float4>(), rec_ls.as<float4>(), s));
+    ctx->launches++;
+    // blocks per problem: every CTA gets at least ~4 tiles of 256 records, and the grid at least a few waves
+    size_t max_tiles = 1;
     for (int p = 0; p < B; ++p)
-        max_feat = std::max<size_t>(max_feat, (size_t)(m->pt_off[p + 1] - m->pt_off[p]) + (m->ls_off[p + 1] - m->ls_off[p]));
-    int bpp = (int)std::max<size_t>(1, std::min<size_t>(max_feat / 512, 64));
-    while ((long)B * bpp < 8L * ctx->sm_count && bpp < 64) ++bpp;
+        max_tiles = std::max<size_t>(max_tiles, (size_t)((m->pt_off[p + 1] - m->pt_off[p] + 255) / 256) +
+                                                    (size_t)((m->ls_off[p + 1] - m->ls_off[p] + 255) / 256));
+    int bpp = (int)std::max<size_t>(1, std::min<size_t>(max_tiles / 8, 64));
+    while ((long)B * bpp < 6L * ctx->sm_count && bpp < (int)max_tiles && bpp < 64) ++bpp;
     CK(ctx, ctx->gn_in[0].ensure((size_t)B * 16 * 8));
     CK(ctx, ctx->gn_in[1].ensure((size_t)B * bpp * (ACC_N + 1) * 8));
     CK(ctx, ctx->gn_out[2].ensure((size_t)B * 36 * 8));
@@ -1068,12 +1075,14 @@ int plstvo_gn_eval_stream(PlContext* ctx, const PlCamera* cam, const PlConfig* c
     cudaEvent_t e0, e1;
     CK(ctx, cudaEventCreate(&e0));
     CK(ctx, cudaEventCreate(&e1));
-    CK(ctx, launch_gn_eval_stream(*cam, *cfg, md, B, ctx->gn_in[0].as<double>(), ctx->gn_in[1].as<double>(), bpp, dH, dg,
-                                  de, s));   // warm-up
+    auto sweep = [&]() {
+        return launch_gn_eval_stream(*cam, *cfg, bufs[0].as<int32_t>(), bufs[1].as<int32_t>(), rec_pt.as<float4>(),
+                                     rec_ls.as<float4>(), B, ctx->gn_in[0].as<double>(), ctx->gn_in[1].as<double>(), bpp,
+                                     dH, dg, de, s);
+    };
+    CK(ctx, sweep());   // warm-up
     CK(ctx, cudaEventRecord(e0, s));
-    for (int i = 0; i < iters; ++i)
-        CK(ctx, launch_gn_eval_stream(*cam, *cfg, md, B, ctx->gn_in[0].as<double>(), ctx->gn_in[1].as<double>(), bpp, dH,
-                                      dg, de, s));
+    for (int i = 0; i < iters; ++i) CK(ctx, sweep());
     CK(ctx, cudaEventRecord(e1, s));
     ctx->launches += 2 * (iters + 1);
     if (H) CK(ctx, cudaMemcpyAsync(H, dH, (size_t)B * 36 * 8, cudaMemcpyDeviceToHost, s));

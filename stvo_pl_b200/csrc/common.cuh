@@ -116,10 +116,11 @@ cudaError_t launch_algebra_selftest(const double* H, const double* g, int n, dou
 cudaError_t launch_popc_bench(uint32_t* out, int iters, int blocks, cudaStream_t stream);
 size_t k1_smem_bytes(int max_tsplit);
 
-// GN evaluation streamed from HBM (roofline kernel of config C5)
-cudaError_t launch_gn_eval_stream(const PlCamera& cam, const PlConfig& cfg, const MatchedDev& m, int B,
-                                  const double* DT, double* partial, int blocks_per_problem,
-                                  double* H, double* g, double* e, cudaStream_t stream);
+// GN evaluation streamed from HBM (roofline kernel of config C5): fp32-packed records, TMA-staged tiles
+cudaError_t launch_pack_records(const MatchedDev& m, int n_pt, int n_ls, float4* pt, float4* ls, cudaStream_t stream);
+cudaError_t launch_gn_eval_stream(const PlCamera& cam, const PlConfig& cfg, const int32_t* pt_off, const int32_t* ls_off,
+                                  const float4* pt, const float4* ls, int B, const double* DT, double* partial,
+                                  int blocks_per_problem, double* H, double* g, double* e, cudaStream_t stream);
 
 // ---- PTX helpers: mbarrier + 1-D bulk async copy (TMA engine, UBLKCP in SASS) ------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

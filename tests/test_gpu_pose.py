@@ -198,7 +198,9 @@ def test_batch_of_64_pairs_sharded_invariance(engine, oracle):
 
 
 def test_gn_eval_stream_vs_oracle(engine, oracle):
-    """optimizeFunctions streamed from HBM (the C5 roofline kernel) against the oracle's evaluation."""
+    """optimizeFunctions streamed from HBM (the C5 roofline kernel: fp32-packed records, fp32 per-feature math, fp64
+    reduction) against the oracle's double evaluation: agreement at the fp32 level (1e-4 relative on H, g, e), and the
+    Gauss-Newton step computed from it within the 1e-5 rad / 1e-4 m bar."""
     cfg = T.kitti_config()
     prev, curr, Tgt, cam = synth.make_batch("kitti", 3, n_pt=900, n_ls=250)
     o = oracle.track_batch(cam, cfg, prev, curr)
@@ -207,10 +209,25 @@ def test_gn_eval_stream_vs_oracle(engine, oracle):
     H, g, e, ms = engine.gn_eval_stream(cam, cfg, matched, DT, iters=2)
     for p in range(3):
         Hr, gr, er = oracle.optimize_functions(cam, cfg, matched, p, DT[p])
-        np.testing.assert_allclose(H[p], Hr, rtol=1e-10, atol=1e-6 * np.abs(Hr).max() * 1e-6)
-        np.testing.assert_allclose(g[p], gr, rtol=1e-9, atol=1e-9 * np.abs(gr).max())
-        assert abs(e[p] - er) < 1e-12
+        np.testing.assert_allclose(H[p], Hr, rtol=2e-4, atol=2e-5 * np.abs(Hr).max())
+        # g = sum J r w cancels almost completely near the optimum: bound the error by the Cauchy-Schwarz scale
+        # |g_i| <= sqrt(H_ii * sum r^2 w) instead of by |g_i| itself
+        n_feat = (matched.pt_off[p + 1] - matched.pt_off[p]) + (matched.ls_off[p + 1] - matched.ls_off[p])
+        scale = np.sqrt(np.diag(Hr) * er * n_feat)
+        assert (np.abs(g[p] - gr) < 2e-4 * scale).all(), (g[p], gr, scale)
+        assert abs(e[p] - er) < 1e-5
+        inc, inc_r = np.linalg.solve(H[p], g[p]), np.linalg.solve(Hr, gr)
+        assert np.linalg.norm(inc[:3] - inc_r[:3]) < 1e-4 and np.linalg.norm(inc[3:] - inc_r[3:]) < 1e-5
     assert ms > 0
+    # ragged / tiny problems and explicit outlier flags
+    mb, Ts, cam2 = synth.make_matched_batch("kitti", 2)
+    mb.pt_inlier = (np.arange(len(mb.pt_sigma2)) % 7 != 0).astype(np.uint8)
+    mb.ls_inlier = (np.arange(len(mb.ls_sigma2)) % 5 != 0).astype(np.uint8)
+    H, g, e, _ = engine.gn_eval_stream(cam2, cfg, mb, Ts, iters=1)
+    for p in range(2):
+        Hr, gr, er = oracle.optimize_functions(cam2, cfg, mb, p, Ts[p])
+        np.testing.assert_allclose(H[p], Hr, rtol=2e-4, atol=2e-5 * np.abs(Hr).max())
+        assert abs(e[p] - er) < 1e-5
 
 
 def test_onchip_6x6_algebra(engine, oracle):
