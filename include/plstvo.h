@@ -171,6 +171,32 @@ int plstvo_match_batch(PlContext* ctx, int B, const uint8_t* d1, const int32_t* 
                        const uint8_t* d2, const int32_t* off2, float nnr, int best_lr_matches,
                        int32_t* m12, int32_t* counts);
 
+/* ---- include/matching.h surface, the stereo (left/right) step: StVO::matchGrid (src/matching.cpp:111-258) ----------
+ * SURVEY 8(f)-1, the row next to the hot path: same 256-bit Hamming primitive, candidates restricted to a window of
+ * the 64 x 48 bucket grid (GridStructure::get, src/gridStructure.cpp:65-76), the loop-carried gate of
+ * Config::bestLRMatches() (a train is only considered by a query if it beats the train's running minimum over all
+ * EARLIER queries, :145-150), best / second best with multiplicity, ratio test in double, mutual filter.
+ * Batched over B frames: q_off / t_off are prefix offsets of queries (left image) and trains (right image). */
+typedef struct PlGridWindow {   /* GridWindow: width = (left, right), height = (up, down), include/gridStructure.h:39-41 */
+    int32_t left, right, up, down;
+} PlGridWindow;
+
+/* points (src/matching.cpp:111-177; caller src/stereoFrame.cpp:129-146): q_cell / t_cell = integer grid cell (x, y) of
+ * every query / train keypoint (kp.pt.x * inv_width, kp.pt.y * inv_height truncated).  m12: problem-local index or -1.
+ * counts (optional) = the reference's return value per frame. */
+int plstvo_match_grid_points(PlContext* ctx, int B, int grid_rows, int grid_cols, PlGridWindow w, int best_lr_matches,
+                             double min_ratio_12_p, const int32_t* q_off, const int32_t* q_cell, const uint8_t* d1,
+                             const int32_t* t_off, const int32_t* t_cell, const uint8_t* d2, int32_t* m12,
+                             int32_t* counts);
+/* lines (src/matching.cpp:179-258; caller src/stereoFrame.cpp:318-345): q_line = integer cells (sp.x, sp.y, ep.x, ep.y) of
+ * the query segments; t_line = train segment end points in GRID UNITS as doubles (x1, y1, x2, y2), rasterised into
+ * cells exactly like getLineCoords / LineIterator (src/lineIterator.cpp:34-77); t_dir = directions2 (normalised).
+ * The reference uses minRatio12P here too (:241). */
+int plstvo_match_grid_lines(PlContext* ctx, int B, int grid_rows, int grid_cols, PlGridWindow w, int best_lr_matches,
+                            double min_ratio_12_p, double line_sim_th, const int32_t* q_off, const int32_t* q_line,
+                            const uint8_t* d1, const int32_t* t_off, const double* t_line, const double* t_dir,
+                            const uint8_t* d2, int32_t* m12, int32_t* counts);
+
 /* ---- include/stereoFrameHandler.h surface ----------------------------------------------------- */
 /* StereoFrameHandler::f2fTracking (src/stereoFrameHandler.cpp:106-180) for B independent
  * (prev, curr) pairs: descriptor matching for points and lines; m12_* hold problem-local indices

@@ -63,6 +63,14 @@ class Oracle:
         L.orc_match.argtypes = [u8p, C.c_int, u8p, C.c_int, C.c_float, C.c_int, C.c_int, i32p]
         L.orc_knn2.restype = None
         L.orc_knn2.argtypes = [u8p, C.c_int, u8p, C.c_int, i32p, i32p]
+        L.orc_match_grid_points.restype = C.c_int
+        L.orc_match_grid_points.argtypes = [C.c_int, C.c_int, T.PlGridWindow, C.c_int, C.c_double, i32p, u8p, C.c_int,
+                                            i32p, u8p, C.c_int, i32p]
+        L.orc_match_grid_lines.restype = C.c_int
+        L.orc_match_grid_lines.argtypes = [C.c_int, C.c_int, T.PlGridWindow, C.c_int, C.c_double, C.c_double, i32p, u8p,
+                                           C.c_int, dp, dp, u8p, C.c_int, i32p]
+        L.orc_line_cells.restype = C.c_int
+        L.orc_line_cells.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, i32p, C.c_int]
         for name, n_in, n_out in [("orc_inverse_se3", 16, 16), ("orc_expmap_se3", 6, 16),
                                   ("orc_logmap_se3", 16, 6), ("orc_adjoint_se3", 16, 36),
                                   ("orc_inv6", 36, 36), ("orc_eig6_sym", 36, 6)]:
@@ -141,6 +149,32 @@ class Oracle:
         n = self.lib.orc_match(d1.ctypes.data_as(T.c_uint8_p), len(d1), d2.ctypes.data_as(T.c_uint8_p), len(d2),
                                C.c_float(nnr), int(best_lr), int(threads), m12.ctypes.data_as(T.c_int32_p))
         return n, m12
+
+    def match_grid_points(self, q_cell, d1, t_cell, d2, window, ratio, best_lr=True, rows=T.GRID_ROWS, cols=T.GRID_COLS):
+        q_cell, t_cell = np.ascontiguousarray(q_cell, np.int32), np.ascontiguousarray(t_cell, np.int32)
+        d1, d2 = np.ascontiguousarray(d1, np.uint8), np.ascontiguousarray(d2, np.uint8)
+        m12 = np.full(len(d1), -1, np.int32)
+        n = self.lib.orc_match_grid_points(rows, cols, window, int(best_lr), float(ratio), q_cell.ctypes.data_as(T.c_int32_p),
+                                           d1.ctypes.data_as(T.c_uint8_p), len(d1), t_cell.ctypes.data_as(T.c_int32_p),
+                                           d2.ctypes.data_as(T.c_uint8_p), len(d2), m12.ctypes.data_as(T.c_int32_p))
+        return n, m12
+
+    def match_grid_lines(self, q_line, d1, t_line, t_dir, d2, window, ratio, line_sim_th, best_lr=True,
+                         rows=T.GRID_ROWS, cols=T.GRID_COLS):
+        q_line = np.ascontiguousarray(q_line, np.int32)
+        t_line, t_dir = np.ascontiguousarray(t_line, np.float64), np.ascontiguousarray(t_dir, np.float64)
+        d1, d2 = np.ascontiguousarray(d1, np.uint8), np.ascontiguousarray(d2, np.uint8)
+        m12 = np.full(len(d1), -1, np.int32)
+        n = self.lib.orc_match_grid_lines(rows, cols, window, int(best_lr), float(ratio), float(line_sim_th),
+                                          q_line.ctypes.data_as(T.c_int32_p), d1.ctypes.data_as(T.c_uint8_p), len(d1),
+                                          self._dp(t_line), self._dp(t_dir), d2.ctypes.data_as(T.c_uint8_p), len(d2),
+                                          m12.ctypes.data_as(T.c_int32_p))
+        return n, m12
+
+    def line_cells(self, x1, y1, x2, y2, cap=512):
+        cells = np.zeros((cap, 2), np.int32)
+        n = self.lib.orc_line_cells(float(x1), float(y1), float(x2), float(y2), cells.ctypes.data_as(T.c_int32_p), cap)
+        return cells[:min(n, cap)]
 
     # ---- SE(3) / statistics ----
     def inverse_se3(self, Tm):

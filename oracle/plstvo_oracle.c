@@ -570,6 +570,169 @@ int orc_match(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr, i
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * StVO::matchGrid — the stereo (left/right) step, SURVEY 8(f)-1
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {   /* GridStructure: cols x rows lists of train indices (src/gridStructure.cpp:43-63) */
+    int rows, cols;
+    int* head;     /* [cols*rows] first entry of the cell's list or -1 */
+    int* next;     /* linked entries */
+    int* item;
+    int n, cap;
+} OrcGrid;
+
+static void grid_init(OrcGrid* g, int rows, int cols, int cap) {
+    g->rows = rows;
+    g->cols = cols;
+    g->head = (int*)malloc((size_t)rows * cols * sizeof(int));
+    for (int i = 0; i < rows * cols; i++) g->head[i] = -1;
+    g->cap = cap > 0 ? cap : 1;
+    g->next = (int*)malloc((size_t)g->cap * sizeof(int));
+    g->item = (int*)malloc((size_t)g->cap * sizeof(int));
+    g->n = 0;
+}
+static void grid_free(OrcGrid* g) { free(g->head); free(g->next); free(g->item); }
+static void grid_push(OrcGrid* g, int x, int y, int idx) {   /* grid.at(x, y).push_back(idx); out of bounds -> discarded list */
+    if (!(x >= 0 && x < g->cols && y >= 0 && y < g->rows)) return;
+    if (g->n == g->cap) {
+        g->cap *= 2;
+        g->next = (int*)realloc(g->next, (size_t)g->cap * sizeof(int));
+        g->item = (int*)realloc(g->item, (size_t)g->cap * sizeof(int));
+    }
+    g->item[g->n] = idx;
+    g->next[g->n] = g->head[x * g->rows + y];
+    g->head[x * g->rows + y] = g->n++;
+}
+/* GridStructure::get (src/gridStructure.cpp:65-76): union of the cells of the window into a set (stamp = dedupe) */
+static int grid_get(const OrcGrid* g, int x, int y, PlGridWindow w, int* stamp, int tag, int* out, int n_out) {
+    int min_x = x - w.left > 0 ? x - w.left : 0;
+    int max_x = x + w.right + 1 < g->cols ? x + w.right + 1 : g->cols;
+    int min_y = y - w.up > 0 ? y - w.up : 0;
+    int max_y = y + w.down + 1 < g->rows ? y + w.down + 1 : g->rows;
+    for (int x_ = min_x; x_ < max_x; ++x_)
+        for (int y_ = min_y; y_ < max_y; ++y_)
+            for (int e = g->head[x_ * g->rows + y_]; e >= 0; e = g->next[e]) {
+                int i2 = g->item[e];
+                if (stamp[i2] != tag) {
+                    stamp[i2] = tag;
+                    out[n_out++] = i2;
+                }
+            }
+    return n_out;
+}
+
+int orc_line_cells(double x1, double y1, double x2, double y2, int32_t* cells, int cap) { /* src/lineIterator.cpp:34-77 */
+    int steep = fabs(y2 - y1) > fabs(x2 - x1);
+    if (steep) { double t = x1; x1 = y1; y1 = t; t = x2; x2 = y2; y2 = t; }
+    if (x1 > x2) { double t = x1; x1 = x2; x2 = t; t = y1; y1 = y2; y2 = t; }
+    double dx = x2 - x1, dy = fabs(y2 - y1), error = dx / 2.0;
+    int ystep = (y1 < y2) ? 1 : -1;
+    int x = (int)x1, y = (int)y1, maxX = (int)x2, n = 0;
+    while (!(x > maxX)) {
+        if (n < cap) {
+            cells[2 * n] = steep ? y : x;
+            cells[2 * n + 1] = steep ? x : y;
+        }
+        n++;
+        error -= dy;
+        if (error < 0) { y += ystep; error += dx; }
+        x++;
+    }
+    return n;
+}
+
+/* shared tail of both overloads: candidate loop (:139-158 / :214-239), ratio test (:160 / :241), mutual filter (:166-174) */
+static int match_grid_core(int n1, int n2, const uint8_t* d1, const uint8_t* d2, int best_lr, double ratio,
+                           const OrcGrid* g, PlGridWindow w, const int32_t* q_cells, int cells_per_query,
+                           const double* dirs2, double line_sim_th, int32_t* m12) {
+    int matches = 0;
+    for (int i = 0; i < n1; i++) m12[i] = -1;
+    int* matches_21 = (int*)malloc((size_t)(n2 + 1) * sizeof(int));
+    int* distances = (int*)malloc((size_t)(n2 + 1) * sizeof(int));
+    int* stamp = (int*)malloc((size_t)(n2 + 1) * sizeof(int));
+    int* cand = (int*)malloc((size_t)(n2 + 1) * sizeof(int));
+    for (int i = 0; i < n2; i++) { matches_21[i] = -1; distances[i] = INT_MAX; stamp[i] = -1; }
+    for (int i1 = 0; i1 < n1; ++i1) {
+        int best_d = INT_MAX, best_d2 = INT_MAX, best_idx = -1;
+        const int32_t* c = q_cells + (size_t)i1 * 2 * cells_per_query;
+        double vx = 0, vy = 0;
+        if (cells_per_query == 2) {   /* v = normalize(ep - sp) in INTEGER cell coordinates (:207-211): NaN when equal */
+            vx = (double)(c[2] - c[0]);
+            vy = (double)(c[3] - c[1]);
+            double mag = sqrt(vx * vx + vy * vy);
+            vx /= mag;
+            vy /= mag;
+        }
+        int nc = 0;
+        for (int k = 0; k < cells_per_query; k++) nc = grid_get(g, c[2 * k], c[2 * k + 1], w, stamp, i1, cand, nc);
+        if (nc == 0) continue;
+        for (int k = 0; k < nc; k++) {
+            int i2 = cand[k];
+            if (i2 < 0 || i2 >= n2) continue;
+            if (cells_per_query == 2) {
+                double dt = vx * dirs2[2 * i2] + vy * dirs2[2 * i2 + 1];
+                if (fabs(dt) < line_sim_th) continue;   /* NaN passes (:221) */
+            }
+            int d = orc_distance(d1 + (size_t)i1 * 32, d2 + (size_t)i2 * 32);
+            if (best_lr) {
+                if (d < distances[i2]) {
+                    distances[i2] = d;
+                    matches_21[i2] = i1;
+                } else
+                    continue;
+            }
+            if (d < best_d) {
+                best_d2 = best_d;
+                best_d = d;
+                best_idx = i2;
+            } else if (d < best_d2)
+                best_d2 = d;
+        }
+        if ((double)best_d < (double)best_d2 * ratio) {   /* int * double (:160) */
+            m12[i1] = best_idx;
+            matches++;
+        }
+    }
+    if (best_lr)
+        for (int i1 = 0; i1 < n1; ++i1) {
+            int i2 = m12[i1];
+            if (i2 >= 0 && matches_21[i2] != i1) {
+                m12[i1] = -1;
+                matches--;
+            }
+        }
+    free(matches_21); free(distances); free(stamp); free(cand);
+    return matches;
+}
+
+int orc_match_grid_points(int rows, int cols, PlGridWindow w, int best_lr, double ratio, const int32_t* q_cell,
+                          const uint8_t* d1, int n1, const int32_t* t_cell, const uint8_t* d2, int n2, int32_t* m12) {
+    OrcGrid g;
+    grid_init(&g, rows, cols, n2);
+    for (int idx = 0; idx < n2; ++idx) grid_push(&g, t_cell[2 * idx], t_cell[2 * idx + 1], idx);   /* stereoFrame.cpp:135-139 */
+    int r = match_grid_core(n1, n2, d1, d2, best_lr, ratio, &g, w, q_cell, 1, NULL, 0.0, m12);
+    grid_free(&g);
+    return r;
+}
+
+int orc_match_grid_lines(int rows, int cols, PlGridWindow w, int best_lr, double ratio, double line_sim_th,
+                         const int32_t* q_line, const uint8_t* d1, int n1, const double* t_line, const double* t_dir,
+                         const uint8_t* d2, int n2, int32_t* m12) {
+    OrcGrid g;
+    grid_init(&g, rows, cols, 4 * n2 + 16);
+    int cap = 4 * (rows + cols) + 16;
+    int32_t* cells = (int32_t*)malloc((size_t)cap * 2 * sizeof(int32_t));
+    for (int idx = 0; idx < n2; ++idx) {   /* stereoFrame.cpp:329-339 */
+        int n = orc_line_cells(t_line[4 * idx], t_line[4 * idx + 1], t_line[4 * idx + 2], t_line[4 * idx + 3], cells, cap);
+        if (n > cap) n = cap;
+        for (int k = 0; k < n; k++) grid_push(&g, cells[2 * k], cells[2 * k + 1], idx);
+    }
+    int r = match_grid_core(n1, n2, d1, d2, best_lr, ratio, &g, w, q_line, 2, t_dir, line_sim_th, m12);
+    free(cells);
+    grid_free(&g);
+    return r;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * the handler state (StereoFrameHandler: matched_pt / matched_ls lists, include/stereoFrameHandler.h)
  * ---------------------------------------------------------------------------------------------- */
 typedef struct { /* PointFeature fields the path reads (include/stereoFeatures.h:30-58) */

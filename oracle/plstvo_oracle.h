@@ -36,6 +36,16 @@ int orc_match(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr, i
 /* raw 2-NN lists, for the comparison with cv2.BFMatcher: idx[2*i+k], dist[2*i+k]; -1 when absent */
 void orc_knn2(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int32_t* idx, int32_t* dist);
 
+/* StVO::matchGrid, points and lines (src/matching.cpp:111-177, :179-258) with GridStructure (src/gridStructure.cpp:43-76)
+ * and LineIterator (src/lineIterator.cpp:34-77) restated; one frame per call */
+int orc_match_grid_points(int rows, int cols, PlGridWindow w, int best_lr, double ratio, const int32_t* q_cell,
+                          const uint8_t* d1, int n1, const int32_t* t_cell, const uint8_t* d2, int n2, int32_t* m12);
+int orc_match_grid_lines(int rows, int cols, PlGridWindow w, int best_lr, double ratio, double line_sim_th,
+                         const int32_t* q_line, const uint8_t* d1, int n1, const double* t_line, const double* t_dir,
+                         const uint8_t* d2, int n2, int32_t* m12);
+/* getLineCoords: cells visited by LineIterator; returns the count, writes up to cap (x, y) pairs */
+int orc_line_cells(double x1, double y1, double x2, double y2, int32_t* cells, int cap);
+
 /* src/auxiliar.cpp */
 void   orc_inverse_se3(const double T[16], double Tinv[16]);            /* :113-122 */
 void   orc_expmap_se3(const double x[6], double T[16]);                 /* :124-141 */

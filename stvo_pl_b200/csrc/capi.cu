@@ -646,6 +646,108 @@ int plstvo_match_nnr(PlContext* ctx, const uint8_t* d1, int n1, const uint8_t* d
     return plstvo_match(ctx, d1, n1, d2, n2, stride_bytes, nnr, 0, m12);
 }
 
+// ---- matchGrid (stereo step) -------------------------------------------------------------------------------------
+static int match_grid_common(PlContext* ctx, bool lines, int B, int rows, int cols, PlGridWindow w, int best_lr,
+                             double ratio, double line_sim_th, const int32_t* q_off, const int32_t* q_cell,
+                             const uint8_t* d1, const int32_t* t_off, const int32_t* t_cell, const double* t_line,
+                             const double* t_dir, const uint8_t* d2, int32_t* m12, int32_t* counts) {
+    if (!ctx) return PLSTVO_E_INVALID;
+    if (B < 0 || rows <= 0 || cols <= 0 || rows * cols > 8192) return fail(ctx, PLSTVO_E_INVALID, "bad grid");
+    if (B == 0) return 0;
+    if (!q_off || !t_off || !m12 || q_off[0] || t_off[0]) return fail(ctx, PLSTVO_E_INVALID, "bad offsets");
+    CK(ctx, cudaSetDevice(ctx->device));
+    constexpr int CAP = 128;                      // candidates per query window (the reference has no limit; typical: ~10)
+    const int qw = lines ? 4 : 2;
+    const size_t N1 = q_off[B], N2 = t_off[B];
+    for (int p = 0; p < B; ++p) {
+        const int n1 = q_off[p + 1] - q_off[p], n2 = t_off[p + 1] - t_off[p];
+        if (n1 < 0 || n2 < 0) return fail(ctx, PLSTVO_E_INVALID, "offsets are not non-decreasing");
+        if (n1 > PLSTVO_MAX_FEATURES || n2 > PLSTVO_MAX_FEATURES) return fail(ctx, PLSTVO_E_TOO_LARGE, "more than 65535 features");
+    }
+    if ((N1 && (!q_cell || !d1)) || (N2 && (!d2 || (lines ? (!t_line || !t_dir) : !t_cell))))
+        return fail(ctx, PLSTVO_E_INVALID, "null input array");
+    const size_t per_train_cells = lines ? (size_t)std::max(rows, cols) + 2 : 1;
+    // one arena for inputs, outputs and scratch
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_qcell = take(N1 * qw * 4), o_d1 = take(N1 * 32), o_d2 = take(N2 * 32);
+    const size_t o_tcell = take(lines ? 0 : N2 * 8), o_tline = take(lines ? N2 * 32 : 0), o_tdir = take(lines ? N2 * 16 : 0);
+    const size_t o_m12 = take(N1 * 4), o_cnt = take((size_t)B * 4), o_items = take(N2 * per_train_cells * 4);
+    const size_t o_qpairs = take(N1 * CAP * 8), o_qcount = take(N1 * 4), o_tcount = take(N2 * 4);
+    const size_t o_tstart = take((N2 + B) * 4), o_tslots = take(N1 * CAP * 4), o_seen = take(N1 * CAP), o_m21 = take(N2 * 4);
+    const size_t o_prob = take((size_t)B * sizeof(GridProblem));
+    static DevBuf arena;
+    CK(ctx, arena.ensure(off));
+    uint8_t* base = arena.as<uint8_t>();
+    std::vector<GridProblem> probs((size_t)B);
+    for (int p = 0; p < B; ++p) {
+        GridProblem& g = probs[p];
+        const size_t a = q_off[p], b = t_off[p];
+        g.n1 = q_off[p + 1] - q_off[p];
+        g.n2 = t_off[p + 1] - t_off[p];
+        g.q_cell = reinterpret_cast<int32_t*>(base + o_qcell) + a * qw;
+        g.d1 = base + o_d1 + a * 32;
+        g.t_cell = lines ? nullptr : reinterpret_cast<int32_t*>(base + o_tcell) + b * 2;
+        g.t_line = lines ? reinterpret_cast<double*>(base + o_tline) + b * 4 : nullptr;
+        g.t_dir = lines ? reinterpret_cast<double*>(base + o_tdir) + b * 2 : nullptr;
+        g.d2 = base + o_d2 + b * 32;
+        g.m12 = reinterpret_cast<int32_t*>(base + o_m12) + a;
+        g.count = reinterpret_cast<int32_t*>(base + o_cnt) + p;
+        g.grid_items = reinterpret_cast<int32_t*>(base + o_items) + b * per_train_cells;
+        g.q_pairs = reinterpret_cast<int2*>(base + o_qpairs) + a * CAP;
+        g.q_count = reinterpret_cast<int32_t*>(base + o_qcount) + a;
+        g.t_count = reinterpret_cast<int32_t*>(base + o_tcount) + b;
+        g.t_start = reinterpret_cast<int32_t*>(base + o_tstart) + b + p;
+        g.t_slots = reinterpret_cast<int32_t*>(base + o_tslots) + a * CAP;
+        g.seen = base + o_seen + a * CAP;
+        g.m21 = reinterpret_cast<int32_t*>(base + o_m21) + b;
+    }
+    cudaStream_t s = ctx->s_main;
+    auto up = [&](size_t o, const void* src, size_t bytes) -> cudaError_t {
+        return (src && bytes) ? cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, s) : cudaSuccess;
+    };
+    CK(ctx, up(o_qcell, q_cell, N1 * qw * 4));
+    CK(ctx, up(o_d1, d1, N1 * 32));
+    CK(ctx, up(o_d2, d2, N2 * 32));
+    if (lines) {
+        CK(ctx, up(o_tline, t_line, N2 * 32));
+        CK(ctx, up(o_tdir, t_dir, N2 * 16));
+    } else {
+        CK(ctx, up(o_tcell, t_cell, N2 * 8));
+    }
+    CK(ctx, up(o_prob, probs.data(), (size_t)B * sizeof(GridProblem)));
+    GridParams prm{rows, cols, CAP, best_lr ? 1 : 0, w, ratio, line_sim_th};
+    CK(ctx, launch_match_grid(reinterpret_cast<GridProblem*>(base + o_prob), B, prm, lines, s));
+    ctx->launches++;
+    std::vector<int32_t> cnt((size_t)B);
+    if (N1) CK(ctx, cudaMemcpyAsync(m12, base + o_m12, N1 * 4, cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaMemcpyAsync(cnt.data(), base + o_cnt, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaStreamSynchronize(s));
+    long total = 0;
+    for (int p = 0; p < B; ++p) {
+        if (cnt[p] < 0) return fail(ctx, cnt[p], "matchGrid: more than 128 candidates in one query window");
+        if (counts) counts[p] = cnt[p];
+        total += cnt[p];
+    }
+    return (int)total;
+}
+
+int plstvo_match_grid_points(PlContext* ctx, int B, int grid_rows, int grid_cols, PlGridWindow w, int best_lr_matches,
+                             double min_ratio_12_p, const int32_t* q_off, const int32_t* q_cell, const uint8_t* d1,
+                             const int32_t* t_off, const int32_t* t_cell, const uint8_t* d2, int32_t* m12,
+                             int32_t* counts) {
+    return match_grid_common(ctx, false, B, grid_rows, grid_cols, w, best_lr_matches, min_ratio_12_p, 0.0, q_off, q_cell, d1,
+                             t_off, t_cell, nullptr, nullptr, d2, m12, counts);
+}
+
+int plstvo_match_grid_lines(PlContext* ctx, int B, int grid_rows, int grid_cols, PlGridWindow w, int best_lr_matches,
+                            double min_ratio_12_p, double line_sim_th, const int32_t* q_off, const int32_t* q_line,
+                            const uint8_t* d1, const int32_t* t_off, const double* t_line, const double* t_dir,
+                            const uint8_t* d2, int32_t* m12, int32_t* counts) {
+    return match_grid_common(ctx, true, B, grid_rows, grid_cols, w, best_lr_matches, min_ratio_12_p, line_sim_th, q_off,
+                             q_line, d1, t_off, nullptr, t_line, t_dir, d2, m12, counts);
+}
+
 // ---- stereoFrameHandler.h surface ------------------------------------------------------------------------
 int plstvo_f2f_tracking(PlContext* ctx, const PlConfig* cfg, const PlFrameBatch* prev, const PlFrameBatch* curr,
                         int32_t* m12_pt, int32_t* m12_ls, int32_t* n_matched) {

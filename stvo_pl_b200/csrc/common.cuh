@@ -116,6 +116,35 @@ cudaError_t launch_algebra_selftest(const double* H, const double* g, int n, dou
 cudaError_t launch_popc_bench(uint32_t* out, int iters, int blocks, cudaStream_t stream);
 size_t k1_smem_bytes(int max_tsplit);
 
+// ---- StVO::matchGrid (match_grid.cu) ---------------------------------------------------------------------------
+struct GridProblem {          // one frame: queries = left image, trains = right image
+    int32_t n1, n2;
+    const int32_t* q_cell;    // points: [n1][2]; lines: [n1][4] (sp.x, sp.y, ep.x, ep.y)
+    const uint8_t* d1;
+    const int32_t* t_cell;    // points: [n2][2]
+    const double*  t_line;    // lines: [n2][4] in grid units
+    const double*  t_dir;     // lines: [n2][2]
+    const uint8_t* d2;
+    int32_t* m12;             // [n1]
+    int32_t* count;           // matches (or a negative error code)
+    // scratch
+    int32_t* grid_items;
+    int2*    q_pairs;         // [n1][cap] (i2, d)
+    int32_t* q_count;         // [n1]
+    int32_t* t_count;         // [n2]
+    int32_t* t_start;         // [n2 + 1]
+    int32_t* t_slots;         // [n1 * cap]
+    uint8_t* seen;            // [n1 * cap]
+    int32_t* m21;             // [n2]
+};
+struct GridParams {
+    int32_t rows, cols, cap, best_lr;
+    PlGridWindow w;
+    double ratio, line_sim_th;
+};
+size_t match_grid_smem_bytes(int rows, int cols);
+cudaError_t launch_match_grid(const GridProblem* problems, int B, const GridParams& prm, bool lines, cudaStream_t stream);
+
 // GN evaluation streamed from HBM (roofline kernel of config C5): fp32-packed records, TMA-staged tiles
 cudaError_t launch_pack_records(const MatchedDev& m, int n_pt, int n_ls, float4* pt, float4* ls, cudaStream_t stream);
 cudaError_t launch_gn_eval_stream(const PlCamera& cam, const PlConfig& cfg, const int32_t* pt_off, const int32_t* ls_off,

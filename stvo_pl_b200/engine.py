@@ -42,6 +42,10 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "plstvo_match_nnr": (C.c_int, [vp, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_float, i32p]),
         "plstvo_match": (C.c_int, [vp, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_float, C.c_int, i32p]),
         "plstvo_match_batch": (C.c_int, [vp, C.c_int, u8p, i32p, u8p, i32p, C.c_float, C.c_int, i32p, i32p]),
+        "plstvo_match_grid_points": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, T.PlGridWindow, C.c_int, C.c_double, i32p, i32p,
+                                               u8p, i32p, i32p, u8p, i32p, i32p]),
+        "plstvo_match_grid_lines": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, T.PlGridWindow, C.c_int, C.c_double,
+                                              C.c_double, i32p, i32p, u8p, i32p, dp, dp, u8p, i32p, i32p]),
         "plstvo_f2f_tracking": (C.c_int, [vp, cfg, fb, fb, i32p, i32p, i32p]),
         "plstvo_optimize_pose": (C.c_int, [vp, cam, cfg, mb, vp, vp, u8p, u8p]),
         "plstvo_track_batch": (C.c_int, [vp, cam, cfg, fb, fb, vp, vp, i32p, i32p, u8p, u8p]),
@@ -69,7 +73,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
 
 EXPORTED_SYMBOLS = [
     "plstvo_version", "plstvo_create", "plstvo_destroy", "plstvo_last_error", "plstvo_default_config",
-    "plstvo_kitti_config", "plstvo_match_nnr", "plstvo_match", "plstvo_match_batch", "plstvo_f2f_tracking",
+    "plstvo_kitti_config", "plstvo_match_nnr", "plstvo_match", "plstvo_match_batch", "plstvo_match_grid_points",
+    "plstvo_match_grid_lines", "plstvo_f2f_tracking",
     "plstvo_optimize_pose", "plstvo_track_batch", "plstvo_track_batch_async", "plstvo_wait", "plstvo_batch_upload", "plstvo_batch_run",
     "plstvo_batch_run_timed", "plstvo_batch_download", "plstvo_batch_free", "plstvo_synchronize",
     "plstvo_host_alloc", "plstvo_host_free", "plstvo_launch_count", "plstvo_batch_kernel_times",
@@ -204,6 +209,36 @@ class Engine:
         n = self._ck(self.lib.plstvo_match_batch(self.ctx, B, _p(d1, T.c_uint8_p), _p(off1, T.c_int32_p),
                                                  _p(d2, T.c_uint8_p), _p(off2, T.c_int32_p), C.c_float(nnr),
                                                  int(best_lr), _p(m12, T.c_int32_p), _p(counts, T.c_int32_p)))
+        return n, m12, counts
+
+    def match_grid_points(self, q_off, q_cell, d1, t_off, t_cell, d2, window: T.PlGridWindow, ratio: float,
+                          best_lr=True, rows=T.GRID_ROWS, cols=T.GRID_COLS):
+        """StVO::matchGrid, points overload (src/matching.cpp:111-177), batched over frames."""
+        q_off, t_off = np.ascontiguousarray(q_off, np.int32), np.ascontiguousarray(t_off, np.int32)
+        q_cell, t_cell = np.ascontiguousarray(q_cell, np.int32).reshape(-1, 2), np.ascontiguousarray(t_cell, np.int32).reshape(-1, 2)
+        d1, d2 = np.ascontiguousarray(d1, np.uint8).reshape(-1, 32), np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
+        B = len(q_off) - 1
+        m12, counts = np.full(len(d1), -1, np.int32), np.zeros(B, np.int32)
+        n = self._ck(self.lib.plstvo_match_grid_points(
+            self.ctx, B, rows, cols, window, int(best_lr), float(ratio), _p(q_off, T.c_int32_p), _p(q_cell, T.c_int32_p),
+            _p(d1, T.c_uint8_p), _p(t_off, T.c_int32_p), _p(t_cell, T.c_int32_p), _p(d2, T.c_uint8_p),
+            _p(m12, T.c_int32_p), _p(counts, T.c_int32_p)))
+        return n, m12, counts
+
+    def match_grid_lines(self, q_off, q_line, d1, t_off, t_line, t_dir, d2, window: T.PlGridWindow, ratio: float,
+                         line_sim_th: float, best_lr=True, rows=T.GRID_ROWS, cols=T.GRID_COLS):
+        """StVO::matchGrid, lines overload (src/matching.cpp:179-258), batched over frames."""
+        q_off, t_off = np.ascontiguousarray(q_off, np.int32), np.ascontiguousarray(t_off, np.int32)
+        q_line = np.ascontiguousarray(q_line, np.int32).reshape(-1, 4)
+        t_line = np.ascontiguousarray(t_line, np.float64).reshape(-1, 4)
+        t_dir = np.ascontiguousarray(t_dir, np.float64).reshape(-1, 2)
+        d1, d2 = np.ascontiguousarray(d1, np.uint8).reshape(-1, 32), np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
+        B = len(q_off) - 1
+        m12, counts = np.full(len(d1), -1, np.int32), np.zeros(B, np.int32)
+        n = self._ck(self.lib.plstvo_match_grid_lines(
+            self.ctx, B, rows, cols, window, int(best_lr), float(ratio), float(line_sim_th), _p(q_off, T.c_int32_p),
+            _p(q_line, T.c_int32_p), _p(d1, T.c_uint8_p), _p(t_off, T.c_int32_p), _p(t_line, T.c_double_p),
+            _p(t_dir, T.c_double_p), _p(d2, T.c_uint8_p), _p(m12, T.c_int32_p), _p(counts, T.c_int32_p)))
         return n, m12, counts
 
     # ---- stereoFrameHandler.h surface ----

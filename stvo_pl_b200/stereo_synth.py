@@ -1,0 +1,61 @@
+"""Synthetic left/right stereo feature sets for StVO::matchGrid (the stereo step, src/stereoFrame.cpp:120-173, :309-398):
+keypoints / segments in the left image, their right-image counterparts shifted left by a disparity, descriptors that differ
+in a few bits, plus clutter.  Grid quantities are formed exactly like the caller does (inv_width = 64 / W, inv_height = 48 / H,
+integer truncation for the query cells, doubles for the Bresenham rasterisation of the train segments)."""
+from __future__ import annotations
+
+import numpy as np
+
+from .types import GRID_COLS, GRID_ROWS
+
+
+def make_stereo_points(n_l, n_r, W=1241, H=376, seed=0, overlap=0.8, bitflip=0.08, max_disp=120.0, tie_stress=False):
+    rng = np.random.default_rng(seed)
+    inv_w, inv_h = GRID_COLS / W, GRID_ROWS / H
+    pl = np.stack([rng.uniform(0, W, n_l), rng.uniform(0, H, n_l)], 1)
+    pr = np.stack([rng.uniform(0, W, n_r), rng.uniform(0, H, n_r)], 1)
+    if tie_stress:
+        d1 = (rng.integers(0, 2, (n_l, 32), dtype=np.uint8) * 255).astype(np.uint8)
+        d2 = (rng.integers(0, 2, (n_r, 32), dtype=np.uint8) * 255).astype(np.uint8)
+    else:
+        d1 = rng.integers(0, 256, (n_l, 32), dtype=np.uint8)
+        d2 = rng.integers(0, 256, (n_r, 32), dtype=np.uint8)
+    k = int(min(n_l, n_r) * overlap)
+    src, dst = rng.permutation(n_l)[:k], rng.permutation(n_r)[:k]
+    disp = rng.uniform(1.0, max_disp, k)
+    pr[dst, 0] = np.clip(pl[src, 0] - disp, 0, W - 1e-3)
+    pr[dst, 1] = np.clip(pl[src, 1] + rng.normal(0, 0.3, k), 0, H - 1e-3)
+    flips = (rng.random((k, 32, 8)) < bitflip)
+    d2[dst] = d1[src] ^ np.packbits(flips, axis=2).reshape(k, 32)
+    q_cell = np.stack([(pl[:, 0] * inv_w).astype(np.int32), (pl[:, 1] * inv_h).astype(np.int32)], 1)
+    t_cell = np.stack([(pr[:, 0] * inv_w).astype(np.int32), (pr[:, 1] * inv_h).astype(np.int32)], 1)
+    return q_cell, d1, t_cell, d2
+
+
+def make_stereo_lines(n_l, n_r, W=1241, H=376, seed=0, overlap=0.8, bitflip=0.08, max_disp=120.0):
+    rng = np.random.default_rng(seed)
+    inv_w, inv_h = GRID_COLS / W, GRID_ROWS / H
+
+    def segs(n):
+        s = np.stack([rng.uniform(0, W, n), rng.uniform(0, H, n)], 1)
+        ang, ln = rng.uniform(0, np.pi, n), rng.uniform(5, 200, n)   # includes segments shorter than one cell
+        e = s + np.stack([ln * np.cos(ang), ln * np.sin(ang)], 1)
+        return s, np.clip(e, 0, [W - 1e-3, H - 1e-3])
+    sl, el = segs(n_l)
+    sr, er = segs(n_r)
+    d1 = rng.integers(0, 256, (n_l, 32), dtype=np.uint8)
+    d2 = rng.integers(0, 256, (n_r, 32), dtype=np.uint8)
+    k = int(min(n_l, n_r) * overlap)
+    src, dst = rng.permutation(n_l)[:k], rng.permutation(n_r)[:k]
+    disp = rng.uniform(1.0, max_disp, (k, 1))
+    sr[dst] = np.clip(sl[src] - np.concatenate([disp, np.zeros((k, 1))], 1), 0, [W - 1e-3, H - 1e-3])
+    er[dst] = np.clip(el[src] - np.concatenate([disp, np.zeros((k, 1))], 1), 0, [W - 1e-3, H - 1e-3])
+    flips = (rng.random((k, 32, 8)) < bitflip)
+    d2[dst] = d1[src] ^ np.packbits(flips, axis=2).reshape(k, 32)
+    q_line = np.stack([(sl[:, 0] * inv_w).astype(np.int32), (sl[:, 1] * inv_h).astype(np.int32),
+                       (el[:, 0] * inv_w).astype(np.int32), (el[:, 1] * inv_h).astype(np.int32)], 1)
+    t_line = np.stack([sr[:, 0] * inv_w, sr[:, 1] * inv_h, er[:, 0] * inv_w, er[:, 1] * inv_h], 1)
+    v = np.stack([(er[:, 0] - sr[:, 0]) * inv_w, (er[:, 1] - sr[:, 1]) * inv_h], 1)   # stereoFrame.cpp:331-333
+    with np.errstate(all="ignore"):
+        t_dir = v / np.sqrt((v * v).sum(1, keepdims=True))
+    return q_line, d1, t_line, t_dir, d2

@@ -52,6 +52,14 @@ class PlMatchedBatch(C.Structure):
                 ("ls_inlier", c_uint8_p)]
 
 
+class PlGridWindow(C.Structure):
+    """GridWindow: width = (left, right), height = (up, down) — include/gridStructure.h:39-41."""
+    _fields_ = [("left", C.c_int32), ("right", C.c_int32), ("up", C.c_int32), ("down", C.c_int32)]
+
+
+GRID_ROWS, GRID_COLS = 48, 64     # include/stereoFrame.h:51-52
+
+
 class PlPrior(C.Structure):
     _fields_ = [("Tfw", C.c_double * 16), ("Tfw_cov", C.c_double * 36), ("DT", C.c_double * 16),
                 ("DT_cov", C.c_double * 36), ("err_norm", C.c_double)]

@@ -1,0 +1,25 @@
+"""One small invocation of every kernel, for compute-sanitizer (tools/sanitize.sh)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+
+from stvo_pl_b200 import stereo_synth as SS, synth, types as T  # noqa: E402
+from stvo_pl_b200.engine import Engine  # noqa: E402
+
+eng = Engine(0)
+cfg = T.kitti_config()
+prev, curr, Tgt, cam = synth.make_batch("kitti", 3, n_pt=700, n_ls=180)
+out = eng.track_batch(cam, cfg, prev, curr)
+m = T.matched_from_frames(prev, curr, out["m12_pt"], out["m12_ls"])
+eng.optimize_pose(cam, cfg, m)
+cfg.solver_mode = 1
+eng.track_batch(cam, cfg, prev, curr)
+eng.gn_eval_stream(cam, cfg, m, Tgt, iters=1)
+eng.match(prev.pdesc, curr.pdesc, 0.75)
+q_cell, d1, t_cell, d2 = SS.make_stereo_points(500, 480, seed=1)
+eng.match_grid_points([0, 500], q_cell, d1, [0, 480], t_cell, d2, T.PlGridWindow(10, 0, 0, 0), 0.75)
+q_line, d1, t_line, t_dir, d2 = SS.make_stereo_lines(150, 160, seed=2)
+eng.match_grid_lines([0, 150], q_line, d1, [0, 160], t_line, t_dir, d2, T.PlGridWindow(10, 0, 0, 0), 0.75, 0.75)
+print("sanitized run ok", int(out["results"]["good"].sum()))
