@@ -54,11 +54,31 @@ def cpu_model() -> str:
     return "unknown"
 
 
+# BASELINE.json configs that run through the same match + optimizePose pipeline (C4 = C2 sharded over ranks)
+WORKLOADS = {
+    "c2": ("kitti", T.kitti_config, 0, WORKLOAD),
+    "c1": ("kitti_points", T.kitti_config, 0,
+           "C1: KITTI-calibrated plumbing pairs, 2000 ORB points, no lines (synthetic: no KITTI images on the box)"),
+    "c3": ("euroc", T.euroc_config, 1,
+           "C3: synthetic EuRoC-shape 752x480, 1000 pts + 300 lines, robust weights on (MAD-scaled Cauchy, solver_mode 1)"),
+}
+ACTIVE = "c2"
+
+
+def workload_config():
+    shape, cfgf, mode, _ = WORKLOADS[ACTIVE]
+    cfg = cfgf()
+    cfg.solver_mode = mode
+    if ACTIVE == "c1":
+        cfg.has_lines = 0
+    return cfg
+
+
 def make_workload(pairs: int, first_pair: int):
     """The bench workload: every prev feature is re-observed in curr (overlap 1.0) so that the solver sees the
-    named 2000 points + 500 lines; 10 % of the observations are gross outliers; descriptors of true
-    correspondences differ in 10 % of their bits."""
-    return synth.make_batch("kitti", pairs, first_pair=first_pair, overlap=1.0)
+    named feature counts (C2: 2000 points + 500 lines); 10 % of the observations are gross outliers; descriptors of
+    true correspondences differ in 10 % of their bits."""
+    return synth.make_batch(WORKLOADS[ACTIVE][0], pairs, first_pair=first_pair, overlap=1.0)
 
 
 class ClockSampler:
@@ -145,7 +165,7 @@ def cpu_port_rate(pairs_sample: int, threads: int, first_pair: int = 0, repeats:
     from oracle.oracle import Oracle
     orc = Oracle(native=True)
     prev, curr, _, cam = make_workload(pairs_sample, first_pair)
-    cfg = T.kitti_config()
+    cfg = workload_config()
     orc.track_batch(cam, cfg, prev.select(range(min(threads, pairs_sample))),
                     curr.select(range(min(threads, pairs_sample))), threads=threads)   # warm-up
     best, stage = None, None
@@ -170,7 +190,7 @@ def run_reference(args):
     from oracle.oracle import Oracle
     orc = Oracle(native=True)
     prev, curr, _, cam = make_workload(sample, 0)
-    cfg = T.kitti_config()
+    cfg = workload_config()
     for _ in range(max(args.warmup, 1)):
         orc.track_batch(cam, cfg, prev, curr, threads=threads)
     t0 = time.perf_counter()
@@ -183,7 +203,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pairs_per_step": sample,
+        "config": {"workload": WORKLOADS[ACTIVE][3], "pairs_per_step": sample,
                    "note": "CPU oracle port of the reference path; N GPUs are not used by this arm"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample} frame pairs per step x {args.steps} steps, one pair per thread",
@@ -222,7 +242,7 @@ def run_ours(args):
         return float(t.item())
 
     eng = Engine(local)
-    cfg = T.kitti_config()
+    cfg = workload_config()
     B = args.pairs
     prev, curr, Tgt, cam = make_workload(B, first_pair=rank * B)   # weak scaling: own pairs per rank
 
@@ -282,6 +302,12 @@ def run_ours(args):
 
     # ---------------- e2e: host buffers through the C-ABI, H2D + D2H inside the timed region ----------------
     pprev, pcurr = eng.pinned.pin_frames(prev), eng.pinned.pin_frames(curr)
+    h2d_ms = None
+    for _ in range(2):          # PCIe probe: how long the step's inputs alone take to cross (pinned, second try)
+        t0 = time.perf_counter()
+        dbp = eng.upload(cam, cfg, pprev, pcurr)
+        h2d_ms = (time.perf_counter() - t0) * 1e3
+        dbp.free()
     pouts = [eng.pinned_outputs(prev), eng.pinned_outputs(prev)]
     pout = pouts[0]
     # (a) the synchronous call, one batch at a time: returns when the results are in host memory
@@ -322,7 +348,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pairs_per_gpu": B, "global_pairs_per_step": world * B,
+        "config": {"workload": WORKLOADS[ACTIVE][3], "pairs_per_gpu": B, "global_pairs_per_step": world * B,
                    "parallelism": f"independent pairs sharded over {world} GPU(s), no collective",
                    "l2": f"inputs larger than L2: {(h2d + kt['n_tiles'] * 0) / 1e6:.0f} MB of inputs + "
                          f"{B * 156000 / 1e6:.0f} MB of tile partials per pass vs 126 MB L2",
@@ -332,7 +358,9 @@ def run_ours(args):
                 "ms_per_step": e2e_s / args.steps * 1e3,
                 "mode": "plstvo_track_batch_async + plstvo_wait, 2 batches in flight (pinned host buffers)",
                 "sync_value": world * B * args.steps / sync_s, "sync_ms_per_step": sync_s / args.steps * 1e3,
-                "sync_mode": "plstvo_track_batch, one blocking call per step"},
+                "sync_mode": "plstvo_track_batch, one blocking call per step",
+                "h2d_only_ms_per_step": h2d_ms, "h2d_only_gbs": h2d / (h2d_ms * 1e-3) / 1e9,
+                "note": "the pipelined figure is bounded by the host->device copy of the step's inputs (h2d_only_ms_per_step)"},
         "gpu_launches": int(launches),
         "roofline": roofline,
     }
@@ -394,12 +422,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=512, help="frame pairs per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
-                    help="c2: the headline solves/s bench; c5: HBM-roofline run of the streamed GN evaluation "
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c5"],
+                    help="c2: the headline solves/s bench (default); c1 / c3: the same pipeline on the points-only and the "
+                         "EuRoC-shape robust configurations; c5: HBM-roofline run of the streamed GN evaluation "
                          "(1920x1080, 8000 points + 2000 lines, >= 1024 problems resident, 20 evaluations)")
     ap.add_argument("--kernels-only", action="store_true",
                     help="profiling aid: upload, launch K1 and K2 over the whole batch twice, exit (for ncu)")
     args = ap.parse_args()
+    global ACTIVE
+    if args.workload in WORKLOADS:
+        ACTIVE = args.workload
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "c5":
