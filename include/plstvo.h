@@ -197,6 +197,30 @@ int plstvo_match_grid_lines(PlContext* ctx, int B, int grid_rows, int grid_cols,
                             const uint8_t* d1, const int32_t* t_off, const double* t_line, const double* t_dir,
                             const uint8_t* d2, int32_t* m12, int32_t* counts);
 
+/* ---- 3-D lifting of the stereo matches: the step that turns matchGrid's output into the PointFeature /
+ * LineFeature records the solver consumes (src/stereoFrame.cpp:149-172 points, :348-397 lines, filterLineSegmentDisparity
+ * :405-415, lineSegmentOverlapStereo :473-508, backProjection src/pinholeStereoCamera.cpp:221-229).  Pure per-feature
+ * arithmetic + an ordered compaction (surviving features keep ascending left index, like the reference's push_back loop).
+ * Batched over B frames; outputs of frame p are written densely starting at element l_off[p]; counts[p] = survivors. */
+typedef struct PlStereoConfig {   /* Config accessors read by this step (include/config.h:72-96, src/config.cpp:58-106) */
+    double max_dist_epip, min_disp, ls_min_disp_ratio, line_horiz_th, stereo_overlap_th, orb_scale_factor, lsd_scale;
+} PlStereoConfig;
+void plstvo_default_stereo_config(PlStereoConfig* c);
+/* kp_l / kp_r: cv::KeyPoint::pt (float x, y); octave_l: cv::KeyPoint::octave; m12: matchGrid output (local right index or -1).
+ * out: PointFeature::pl, disp, P, sigma2, level; pdesc_out = the surviving rows of desc_l (pdesc_l_aux); src_idx = their i1. */
+int plstvo_stereo_lift_points(PlContext* ctx, const PlCamera* cam, const PlStereoConfig* scfg, int B, const int32_t* l_off,
+                              const float* kp_l, const int32_t* octave_l, const uint8_t* desc_l, const int32_t* r_off,
+                              const float* kp_r, const int32_t* m12, double* pt_pl, double* pt_disp, double* pt_P,
+                              double* pt_sigma2, int32_t* pt_level, uint8_t* pdesc_out, int32_t* src_idx, int32_t* counts);
+/* seg_l / seg_r: KeyLine start / end points (float sx, sy, ex, ey); angle_l: KeyLine::angle; octave_l: KeyLine::octave.
+ * out: LineFeature::spl, epl, sdisp, edisp, sP, eP, le, angle, sigma2, level; ldesc_out, src_idx as for points. */
+int plstvo_stereo_lift_lines(PlContext* ctx, const PlCamera* cam, const PlStereoConfig* scfg, int B, const int32_t* l_off,
+                             const float* seg_l, const float* angle_l, const int32_t* octave_l, const uint8_t* desc_l,
+                             const int32_t* r_off, const float* seg_r, const int32_t* m12, double* ls_spl, double* ls_epl,
+                             double* ls_sdisp, double* ls_edisp, double* ls_sP, double* ls_eP, double* ls_le,
+                             double* ls_angle, double* ls_sigma2, int32_t* ls_level, uint8_t* ldesc_out, int32_t* src_idx,
+                             int32_t* counts);
+
 /* ---- include/stereoFrameHandler.h surface ----------------------------------------------------- */
 /* StereoFrameHandler::f2fTracking (src/stereoFrameHandler.cpp:106-180) for B independent
  * (prev, curr) pairs: descriptor matching for points and lines; m12_* hold problem-local indices

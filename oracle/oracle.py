@@ -69,6 +69,15 @@ class Oracle:
         L.orc_match_grid_lines.restype = C.c_int
         L.orc_match_grid_lines.argtypes = [C.c_int, C.c_int, T.PlGridWindow, C.c_int, C.c_double, C.c_double, i32p, u8p,
                                            C.c_int, dp, dp, u8p, C.c_int, i32p]
+        fp, scp = T.c_float_p, C.POINTER(T.PlStereoConfig)
+        L.orc_stereo_lift_points.restype = C.c_int
+        L.orc_stereo_lift_points.argtypes = [C.POINTER(T.PlCamera), scp, C.c_int, fp, i32p, u8p, fp, i32p, dp, dp, dp, dp, i32p,
+                                             u8p, i32p]
+        L.orc_stereo_lift_lines.restype = C.c_int
+        L.orc_stereo_lift_lines.argtypes = [C.POINTER(T.PlCamera), scp, C.c_int, fp, fp, i32p, u8p, fp, i32p, dp, dp, dp, dp,
+                                            dp, dp, dp, dp, dp, i32p, u8p, i32p]
+        L.orc_line_segment_overlap_stereo.restype = C.c_double
+        L.orc_line_segment_overlap_stereo.argtypes = [scp, C.c_double, C.c_double, C.c_double, C.c_double]
         L.orc_line_cells.restype = C.c_int
         L.orc_line_cells.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, i32p, C.c_int]
         for name, n_in, n_out in [("orc_inverse_se3", 16, 16), ("orc_expmap_se3", 6, 16),
@@ -170,6 +179,43 @@ class Oracle:
                                           self._dp(t_line), self._dp(t_dir), d2.ctypes.data_as(T.c_uint8_p), len(d2),
                                           m12.ctypes.data_as(T.c_int32_p))
         return n, m12
+
+    # ---- 3-D lifting of the stereo matches (one frame) ----
+    def stereo_lift_points(self, cam, scfg, kp_l, octave_l, desc_l, kp_r, m12):
+        kp_l, kp_r = np.ascontiguousarray(kp_l, np.float32).reshape(-1, 2), np.ascontiguousarray(kp_r, np.float32).reshape(-1, 2)
+        octave_l, m12 = np.ascontiguousarray(octave_l, np.int32), np.ascontiguousarray(m12, np.int32)
+        desc_l = np.ascontiguousarray(desc_l, np.uint8).reshape(-1, 32)
+        n = len(kp_l)
+        out = dict(pl=np.zeros((n, 2)), disp=np.zeros(n), P=np.zeros((n, 3)), sigma2=np.zeros(n), level=np.zeros(n, np.int32),
+                   desc=np.zeros((n, 32), np.uint8), src_idx=np.full(n, -1, np.int32))
+        i32, u8, f32 = T.c_int32_p, T.c_uint8_p, T.c_float_p
+        k = self.lib.orc_stereo_lift_points(
+            C.byref(cam), C.byref(scfg), n, kp_l.ctypes.data_as(f32), octave_l.ctypes.data_as(i32), desc_l.ctypes.data_as(u8),
+            kp_r.ctypes.data_as(f32), m12.ctypes.data_as(i32), self._dp(out["pl"]), self._dp(out["disp"]), self._dp(out["P"]),
+            self._dp(out["sigma2"]), out["level"].ctypes.data_as(i32), out["desc"].ctypes.data_as(u8),
+            out["src_idx"].ctypes.data_as(i32))
+        return k, {key: v[:k] for key, v in out.items()}
+
+    def stereo_lift_lines(self, cam, scfg, seg_l, angle_l, octave_l, desc_l, seg_r, m12):
+        seg_l, seg_r = np.ascontiguousarray(seg_l, np.float32).reshape(-1, 4), np.ascontiguousarray(seg_r, np.float32).reshape(-1, 4)
+        angle_l = np.ascontiguousarray(angle_l, np.float32)
+        octave_l, m12 = np.ascontiguousarray(octave_l, np.int32), np.ascontiguousarray(m12, np.int32)
+        desc_l = np.ascontiguousarray(desc_l, np.uint8).reshape(-1, 32)
+        n = len(seg_l)
+        out = dict(spl=np.zeros((n, 2)), epl=np.zeros((n, 2)), sdisp=np.zeros(n), edisp=np.zeros(n), sP=np.zeros((n, 3)),
+                   eP=np.zeros((n, 3)), le=np.zeros((n, 3)), angle=np.zeros(n), sigma2=np.zeros(n),
+                   level=np.zeros(n, np.int32), desc=np.zeros((n, 32), np.uint8), src_idx=np.full(n, -1, np.int32))
+        i32, u8, f32 = T.c_int32_p, T.c_uint8_p, T.c_float_p
+        k = self.lib.orc_stereo_lift_lines(
+            C.byref(cam), C.byref(scfg), n, seg_l.ctypes.data_as(f32), angle_l.ctypes.data_as(f32),
+            octave_l.ctypes.data_as(i32), desc_l.ctypes.data_as(u8), seg_r.ctypes.data_as(f32), m12.ctypes.data_as(i32),
+            self._dp(out["spl"]), self._dp(out["epl"]), self._dp(out["sdisp"]), self._dp(out["edisp"]), self._dp(out["sP"]),
+            self._dp(out["eP"]), self._dp(out["le"]), self._dp(out["angle"]), self._dp(out["sigma2"]),
+            out["level"].ctypes.data_as(i32), out["desc"].ctypes.data_as(u8), out["src_idx"].ctypes.data_as(i32))
+        return k, {key: v[:k] for key, v in out.items()}
+
+    def line_segment_overlap_stereo(self, scfg, spl_obs, epl_obs, spl_proj, epl_proj):
+        return self.lib.orc_line_segment_overlap_stereo(C.byref(scfg), float(spl_obs), float(epl_obs), float(spl_proj), float(epl_proj))
 
     def line_cells(self, x1, y1, x2, y2, cap=512):
         cells = np.zeros((cap, 2), np.int32)

@@ -733,6 +733,108 @@ int orc_match_grid_lines(int rows, int cols, PlGridWindow w, int best_lr, double
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * 3-D lifting of the stereo matches — SURVEY 8(f)-2
+ * ---------------------------------------------------------------------------------------------- */
+static double sigma2_of_level(int level, double scale) {   /* PointFeature / LineFeature ctors (src/stereoFeatures.cpp:41-47, :107-115) */
+    double sigma2 = 1.0;
+    for (int i = 0; i < level; i++) sigma2 *= scale;
+    return 1.0 / (sigma2 * sigma2);
+}
+
+int orc_stereo_lift_points(const PlCamera* cam, const PlStereoConfig* sc, int n_l, const float* kp_l, const int32_t* octave_l,
+                           const uint8_t* desc_l, const float* kp_r, const int32_t* m12, double* pt_pl, double* pt_disp,
+                           double* pt_P, double* pt_sigma2, int32_t* pt_level, uint8_t* pdesc_out, int32_t* src_idx) {
+    int k = 0;
+    for (int i1 = 0; i1 < n_l; ++i1) {   /* src/stereoFrame.cpp:151-170 */
+        const int i2 = m12[i1];
+        if (i2 < 0) continue;
+        const float yl = kp_l[2 * i1 + 1], yr = kp_r[2 * i2 + 1];
+        if ((double)fabsf(yl - yr) <= sc->max_dist_epip) {          /* float subtraction (cv::Point2f) */
+            const double disp_ = (double)(kp_l[2 * i1] - kp_r[2 * i2]);   /* float - float, then widened */
+            if (disp_ >= sc->min_disp) {
+                memcpy(pdesc_out + (size_t)k * 32, desc_l + (size_t)i1 * 32, 32);
+                const double u = (double)kp_l[2 * i1], v = (double)kp_l[2 * i1 + 1];
+                pt_pl[2 * k] = u;
+                pt_pl[2 * k + 1] = v;
+                pt_disp[k] = disp_;
+                orc_back_projection(cam, u, v, disp_, pt_P + 3 * k);
+                pt_level[k] = octave_l[i1];
+                pt_sigma2[k] = sigma2_of_level(octave_l[i1], sc->orb_scale_factor);
+                src_idx[k] = i1;
+                k++;
+            }
+        }
+    }
+    return k;
+}
+
+double orc_line_segment_overlap_stereo(const PlStereoConfig* sc, double spl_obs, double epl_obs, double spl_proj, double epl_proj) {
+    double overlap = 1.0;   /* src/stereoFrame.cpp:473-508 */
+    if (fabs(epl_obs - spl_obs) > sc->line_horiz_th) {
+        double sln = spl_obs < epl_obs ? spl_obs : epl_obs, eln = spl_obs < epl_obs ? epl_obs : spl_obs;
+        double spn = spl_proj < epl_proj ? spl_proj : epl_proj, epn = spl_proj < epl_proj ? epl_proj : spl_proj;
+        if (epl_obs < spl_obs) { sln = epl_obs; eln = spl_obs; }
+        if (epl_proj < spl_proj) { spn = epl_proj; epn = spl_proj; }
+        const double length = eln - spn;
+        if ((epn < sln) || (spn > eln)) overlap = 0.0;
+        else {
+            if ((epn > eln) && (spn < sln)) overlap = eln - sln;
+            else overlap = (eln < epn ? eln : epn) - (sln < spn ? spn : sln);
+        }
+        if (length > (double)0.01f) overlap = overlap / length;
+        else overlap = 0.0;
+        if (overlap > 1.0) overlap = 1.0;
+    }
+    return overlap;
+}
+
+int orc_stereo_lift_lines(const PlCamera* cam, const PlStereoConfig* sc, int n_l, const float* seg_l, const float* angle_l,
+                          const int32_t* octave_l, const uint8_t* desc_l, const float* seg_r, const int32_t* m12,
+                          double* ls_spl, double* ls_epl, double* ls_sdisp, double* ls_edisp, double* ls_sP, double* ls_eP,
+                          double* ls_le, double* ls_angle, double* ls_sigma2, int32_t* ls_level, uint8_t* ldesc_out,
+                          int32_t* src_idx) {
+    int k = 0;
+    for (int i1 = 0; i1 < n_l; ++i1) {   /* src/stereoFrame.cpp:351-393 */
+        const int i2 = m12[i1];
+        if (i2 < 0) continue;
+        const double sp_l[2] = {seg_l[4 * i1], seg_l[4 * i1 + 1]}, ep_l[2] = {seg_l[4 * i1 + 2], seg_l[4 * i1 + 3]};
+        /* le_l = sp_l x ep_l (homogeneous), normalised by sqrt(a^2 + b^2) (:357-358) */
+        double le[3] = {sp_l[1] - ep_l[1], ep_l[0] - sp_l[0], sp_l[0] * ep_l[1] - sp_l[1] * ep_l[0]};
+        const double nrm = sqrt(le[0] * le[0] + le[1] * le[1]);
+        le[0] /= nrm; le[1] /= nrm; le[2] /= nrm;
+        double sp_r[2] = {seg_r[4 * i2], seg_r[4 * i2 + 1]}, ep_r[2] = {seg_r[4 * i2 + 2], seg_r[4 * i2 + 3]};
+        const double overlap = orc_line_segment_overlap_stereo(sc, sp_l[1], ep_l[1], sp_r[1], ep_r[1]);   /* :362 */
+        /* :366-367 — the comma initialiser writes sp_r(0), then sp_r(1); ep_r is then computed from the UPDATED sp_r */
+        sp_r[0] = (sp_r[0] * (sp_l[1] - ep_r[1]) + ep_r[0] * (sp_r[1] - sp_l[1])) / (sp_r[1] - ep_r[1]);
+        sp_r[1] = sp_l[1];
+        ep_r[0] = (sp_r[0] * (ep_l[1] - ep_r[1]) + ep_r[0] * (sp_r[1] - ep_l[1])) / (sp_r[1] - ep_r[1]);
+        ep_r[1] = ep_l[1];
+        /* filterLineSegmentDisparity (:405-415) */
+        double disp_s = sp_l[0] - sp_r[0], disp_e = ep_l[0] - ep_r[0];
+        {
+            const double mn = disp_e < disp_s ? disp_e : disp_s, mx = disp_s < disp_e ? disp_e : disp_s;
+            if (mn / mx < sc->ls_min_disp_ratio) { disp_s = -1.0; disp_e = -1.0; }
+        }
+        if (disp_s >= sc->min_disp && disp_e >= sc->min_disp && fabs(sp_l[1] - ep_l[1]) > sc->line_horiz_th &&
+            fabs(sp_r[1] - ep_r[1]) > sc->line_horiz_th && overlap > sc->stereo_overlap_th) {   /* :371-374 */
+            orc_back_projection(cam, sp_l[0], sp_l[1], disp_s, ls_sP + 3 * k);
+            orc_back_projection(cam, ep_l[0], ep_l[1], disp_e, ls_eP + 3 * k);
+            memcpy(ldesc_out + (size_t)k * 32, desc_l + (size_t)i1 * 32, 32);
+            ls_spl[2 * k] = sp_l[0]; ls_spl[2 * k + 1] = sp_l[1];
+            ls_epl[2 * k] = ep_l[0]; ls_epl[2 * k + 1] = ep_l[1];
+            ls_sdisp[k] = disp_s; ls_edisp[k] = disp_e;
+            ls_le[3 * k] = le[0]; ls_le[3 * k + 1] = le[1]; ls_le[3 * k + 2] = le[2];
+            ls_angle[k] = (double)angle_l[i1];
+            ls_level[k] = octave_l[i1];
+            ls_sigma2[k] = sigma2_of_level(octave_l[i1], sc->lsd_scale);
+            src_idx[k] = i1;
+            k++;
+        }
+    }
+    return k;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * the handler state (StereoFrameHandler: matched_pt / matched_ls lists, include/stereoFrameHandler.h)
  * ---------------------------------------------------------------------------------------------- */
 typedef struct { /* PointFeature fields the path reads (include/stereoFeatures.h:30-58) */

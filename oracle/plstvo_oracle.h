@@ -46,6 +46,18 @@ int orc_match_grid_lines(int rows, int cols, PlGridWindow w, int best_lr, double
 /* getLineCoords: cells visited by LineIterator; returns the count, writes up to cap (x, y) pairs */
 int orc_line_cells(double x1, double y1, double x2, double y2, int32_t* cells, int cap);
 
+/* 3-D lifting of the stereo matches, one frame per call (src/stereoFrame.cpp:149-172, :348-397, :405-415, :473-508);
+ * outputs dense from element 0; returns the number of surviving features */
+int orc_stereo_lift_points(const PlCamera* cam, const PlStereoConfig* sc, int n_l, const float* kp_l, const int32_t* octave_l,
+                           const uint8_t* desc_l, const float* kp_r, const int32_t* m12, double* pt_pl, double* pt_disp,
+                           double* pt_P, double* pt_sigma2, int32_t* pt_level, uint8_t* pdesc_out, int32_t* src_idx);
+int orc_stereo_lift_lines(const PlCamera* cam, const PlStereoConfig* sc, int n_l, const float* seg_l, const float* angle_l,
+                          const int32_t* octave_l, const uint8_t* desc_l, const float* seg_r, const int32_t* m12,
+                          double* ls_spl, double* ls_epl, double* ls_sdisp, double* ls_edisp, double* ls_sP, double* ls_eP,
+                          double* ls_le, double* ls_angle, double* ls_sigma2, int32_t* ls_level, uint8_t* ldesc_out,
+                          int32_t* src_idx);
+double orc_line_segment_overlap_stereo(const PlStereoConfig* sc, double spl_obs, double epl_obs, double spl_proj, double epl_proj);
+
 /* src/auxiliar.cpp */
 void   orc_inverse_se3(const double T[16], double Tinv[16]);            /* :113-122 */
 void   orc_expmap_se3(const double x[6], double T[16]);                 /* :124-141 */

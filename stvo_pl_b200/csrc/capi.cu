@@ -748,6 +748,158 @@ int plstvo_match_grid_lines(PlContext* ctx, int B, int grid_rows, int grid_cols,
                              q_line, d1, t_off, nullptr, t_line, t_dir, d2, m12, counts);
 }
 
+// ---- 3-D lifting of the stereo matches (src/stereoFrame.cpp:149-172, :348-397) ------------------------------
+void plstvo_default_stereo_config(PlStereoConfig* c) {   // src/config.cpp:58-69, :96, :106
+    if (!c) return;
+    c->max_dist_epip = 1.0; c->min_disp = 1.0; c->ls_min_disp_ratio = 0.7; c->line_horiz_th = 0.1;
+    c->stereo_overlap_th = 0.75; c->orb_scale_factor = 1.2; c->lsd_scale = 1.2;
+}
+
+namespace {
+struct LiftArena {
+    size_t off = 0;
+    size_t take(size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; }
+};
+int lift_check_offsets(PlContext* ctx, int B, const int32_t* l_off, const int32_t* r_off) {
+    if (!l_off || !r_off || l_off[0] || r_off[0]) return fail(ctx, PLSTVO_E_INVALID, "bad offsets");
+    for (int p = 0; p < B; ++p) {
+        const int n1 = l_off[p + 1] - l_off[p], n2 = r_off[p + 1] - r_off[p];
+        if (n1 < 0 || n2 < 0) return fail(ctx, PLSTVO_E_INVALID, "offsets are not non-decreasing");
+        if (n1 > PLSTVO_MAX_FEATURES || n2 > PLSTVO_MAX_FEATURES) return fail(ctx, PLSTVO_E_TOO_LARGE, "more than 65535 features");
+    }
+    return 0;
+}
+}  // namespace
+
+int plstvo_stereo_lift_points(PlContext* ctx, const PlCamera* cam, const PlStereoConfig* scfg, int B, const int32_t* l_off,
+                              const float* kp_l, const int32_t* octave_l, const uint8_t* desc_l, const int32_t* r_off,
+                              const float* kp_r, const int32_t* m12, double* pt_pl, double* pt_disp, double* pt_P,
+                              double* pt_sigma2, int32_t* pt_level, uint8_t* pdesc_out, int32_t* src_idx, int32_t* counts) {
+    if (!ctx) return PLSTVO_E_INVALID;
+    if (!cam || !scfg || B < 0) return fail(ctx, PLSTVO_E_INVALID, "null camera / config or negative batch size");
+    if (B == 0) return 0;
+    int rc = lift_check_offsets(ctx, B, l_off, r_off);
+    if (rc) return rc;
+    const size_t N1 = l_off[B], N2 = r_off[B];
+    if (N1 && (!kp_l || !octave_l || !desc_l || !m12)) return fail(ctx, PLSTVO_E_INVALID, "null input array");
+    if (N2 && !kp_r) return fail(ctx, PLSTVO_E_INVALID, "null input array");
+    CK(ctx, cudaSetDevice(ctx->device));
+    LiftArena a;
+    const size_t o_loff = a.take((size_t)(B + 1) * 4), o_roff = a.take((size_t)(B + 1) * 4), o_kpl = a.take(N1 * 8);
+    const size_t o_oct = a.take(N1 * 4), o_desc = a.take(N1 * 32), o_kpr = a.take(N2 * 8), o_m12 = a.take(N1 * 4);
+    const size_t o_pl = a.take(N1 * 16), o_disp = a.take(N1 * 8), o_P = a.take(N1 * 24), o_s2 = a.take(N1 * 8);
+    const size_t o_lvl = a.take(N1 * 4), o_dout = a.take(N1 * 32), o_src = a.take(N1 * 4), o_cnt = a.take((size_t)B * 4);
+    static DevBuf arena;
+    CK(ctx, arena.ensure(a.off));
+    uint8_t* base = arena.as<uint8_t>();
+    cudaStream_t s = ctx->s_main;
+    auto up = [&](size_t o, const void* src, size_t bytes) -> cudaError_t {
+        return (src && bytes) ? cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, s) : cudaSuccess;
+    };
+    auto down = [&](void* dst, size_t o, size_t bytes) -> cudaError_t {
+        return (dst && bytes) ? cudaMemcpyAsync(dst, base + o, bytes, cudaMemcpyDeviceToHost, s) : cudaSuccess;
+    };
+    CK(ctx, up(o_loff, l_off, (size_t)(B + 1) * 4));
+    CK(ctx, up(o_roff, r_off, (size_t)(B + 1) * 4));
+    CK(ctx, up(o_kpl, kp_l, N1 * 8));
+    CK(ctx, up(o_oct, octave_l, N1 * 4));
+    CK(ctx, up(o_desc, desc_l, N1 * 32));
+    CK(ctx, up(o_kpr, kp_r, N2 * 8));
+    CK(ctx, up(o_m12, m12, N1 * 4));
+    auto I = [&](size_t o) { return reinterpret_cast<int32_t*>(base + o); };
+    auto D = [&](size_t o) { return reinterpret_cast<double*>(base + o); };
+    auto F = [&](size_t o) { return reinterpret_cast<float*>(base + o); };
+    CK(ctx, launch_lift_points(*cam, *scfg, B, I(o_loff), F(o_kpl), I(o_oct), base + o_desc, I(o_roff), F(o_kpr), I(o_m12),
+                               D(o_pl), D(o_disp), D(o_P), D(o_s2), I(o_lvl), base + o_dout, I(o_src), I(o_cnt), s));
+    ctx->launches++;
+    std::vector<int32_t> cnt((size_t)B);
+    CK(ctx, down(pt_pl, o_pl, N1 * 16));
+    CK(ctx, down(pt_disp, o_disp, N1 * 8));
+    CK(ctx, down(pt_P, o_P, N1 * 24));
+    CK(ctx, down(pt_sigma2, o_s2, N1 * 8));
+    CK(ctx, down(pt_level, o_lvl, N1 * 4));
+    CK(ctx, down(pdesc_out, o_dout, N1 * 32));
+    CK(ctx, down(src_idx, o_src, N1 * 4));
+    CK(ctx, down(cnt.data(), o_cnt, (size_t)B * 4));
+    CK(ctx, cudaStreamSynchronize(s));
+    long total = 0;
+    for (int p = 0; p < B; ++p) {
+        if (counts) counts[p] = cnt[p];
+        total += cnt[p];
+    }
+    return (int)total;
+}
+
+int plstvo_stereo_lift_lines(PlContext* ctx, const PlCamera* cam, const PlStereoConfig* scfg, int B, const int32_t* l_off,
+                             const float* seg_l, const float* angle_l, const int32_t* octave_l, const uint8_t* desc_l,
+                             const int32_t* r_off, const float* seg_r, const int32_t* m12, double* ls_spl, double* ls_epl,
+                             double* ls_sdisp, double* ls_edisp, double* ls_sP, double* ls_eP, double* ls_le,
+                             double* ls_angle, double* ls_sigma2, int32_t* ls_level, uint8_t* ldesc_out, int32_t* src_idx,
+                             int32_t* counts) {
+    if (!ctx) return PLSTVO_E_INVALID;
+    if (!cam || !scfg || B < 0) return fail(ctx, PLSTVO_E_INVALID, "null camera / config or negative batch size");
+    if (B == 0) return 0;
+    int rc = lift_check_offsets(ctx, B, l_off, r_off);
+    if (rc) return rc;
+    const size_t N1 = l_off[B], N2 = r_off[B];
+    if (N1 && (!seg_l || !angle_l || !octave_l || !desc_l || !m12)) return fail(ctx, PLSTVO_E_INVALID, "null input array");
+    if (N2 && !seg_r) return fail(ctx, PLSTVO_E_INVALID, "null input array");
+    CK(ctx, cudaSetDevice(ctx->device));
+    LiftArena a;
+    const size_t o_loff = a.take((size_t)(B + 1) * 4), o_roff = a.take((size_t)(B + 1) * 4), o_segl = a.take(N1 * 16);
+    const size_t o_ang = a.take(N1 * 4), o_oct = a.take(N1 * 4), o_desc = a.take(N1 * 32), o_segr = a.take(N2 * 16);
+    const size_t o_m12 = a.take(N1 * 4), o_spl = a.take(N1 * 16), o_epl = a.take(N1 * 16), o_sd = a.take(N1 * 8);
+    const size_t o_ed = a.take(N1 * 8), o_sP = a.take(N1 * 24), o_eP = a.take(N1 * 24), o_le = a.take(N1 * 24);
+    const size_t o_angd = a.take(N1 * 8), o_s2 = a.take(N1 * 8), o_lvl = a.take(N1 * 4), o_dout = a.take(N1 * 32);
+    const size_t o_src = a.take(N1 * 4), o_cnt = a.take((size_t)B * 4);
+    static DevBuf arena;
+    CK(ctx, arena.ensure(a.off));
+    uint8_t* base = arena.as<uint8_t>();
+    cudaStream_t s = ctx->s_main;
+    auto up = [&](size_t o, const void* src, size_t bytes) -> cudaError_t {
+        return (src && bytes) ? cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, s) : cudaSuccess;
+    };
+    auto down = [&](void* dst, size_t o, size_t bytes) -> cudaError_t {
+        return (dst && bytes) ? cudaMemcpyAsync(dst, base + o, bytes, cudaMemcpyDeviceToHost, s) : cudaSuccess;
+    };
+    CK(ctx, up(o_loff, l_off, (size_t)(B + 1) * 4));
+    CK(ctx, up(o_roff, r_off, (size_t)(B + 1) * 4));
+    CK(ctx, up(o_segl, seg_l, N1 * 16));
+    CK(ctx, up(o_ang, angle_l, N1 * 4));
+    CK(ctx, up(o_oct, octave_l, N1 * 4));
+    CK(ctx, up(o_desc, desc_l, N1 * 32));
+    CK(ctx, up(o_segr, seg_r, N2 * 16));
+    CK(ctx, up(o_m12, m12, N1 * 4));
+    auto I = [&](size_t o) { return reinterpret_cast<int32_t*>(base + o); };
+    auto D = [&](size_t o) { return reinterpret_cast<double*>(base + o); };
+    auto F = [&](size_t o) { return reinterpret_cast<float*>(base + o); };
+    CK(ctx, launch_lift_lines(*cam, *scfg, B, I(o_loff), F(o_segl), F(o_ang), I(o_oct), base + o_desc, I(o_roff), F(o_segr),
+                              I(o_m12), D(o_spl), D(o_epl), D(o_sd), D(o_ed), D(o_sP), D(o_eP), D(o_le), D(o_angd), D(o_s2),
+                              I(o_lvl), base + o_dout, I(o_src), I(o_cnt), s));
+    ctx->launches++;
+    std::vector<int32_t> cnt((size_t)B);
+    CK(ctx, down(ls_spl, o_spl, N1 * 16));
+    CK(ctx, down(ls_epl, o_epl, N1 * 16));
+    CK(ctx, down(ls_sdisp, o_sd, N1 * 8));
+    CK(ctx, down(ls_edisp, o_ed, N1 * 8));
+    CK(ctx, down(ls_sP, o_sP, N1 * 24));
+    CK(ctx, down(ls_eP, o_eP, N1 * 24));
+    CK(ctx, down(ls_le, o_le, N1 * 24));
+    CK(ctx, down(ls_angle, o_angd, N1 * 8));
+    CK(ctx, down(ls_sigma2, o_s2, N1 * 8));
+    CK(ctx, down(ls_level, o_lvl, N1 * 4));
+    CK(ctx, down(ldesc_out, o_dout, N1 * 32));
+    CK(ctx, down(src_idx, o_src, N1 * 4));
+    CK(ctx, down(cnt.data(), o_cnt, (size_t)B * 4));
+    CK(ctx, cudaStreamSynchronize(s));
+    long total = 0;
+    for (int p = 0; p < B; ++p) {
+        if (counts) counts[p] = cnt[p];
+        total += cnt[p];
+    }
+    return (int)total;
+}
+
 // ---- stereoFrameHandler.h surface ------------------------------------------------------------------------
 int plstvo_f2f_tracking(PlContext* ctx, const PlConfig* cfg, const PlFrameBatch* prev, const PlFrameBatch* curr,
                         int32_t* m12_pt, int32_t* m12_ls, int32_t* n_matched) {

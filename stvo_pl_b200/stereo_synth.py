@@ -59,3 +59,61 @@ def make_stereo_lines(n_l, n_r, W=1241, H=376, seed=0, overlap=0.8, bitflip=0.08
     with np.errstate(all="ignore"):
         t_dir = v / np.sqrt((v * v).sum(1, keepdims=True))
     return q_line, d1, t_line, t_dir, d2
+
+
+# ---- inputs of the 3-D lifting step (src/stereoFrame.cpp:149-172, :348-397) ----
+def make_lift_points(n_l, n_r, seed, W=1241, H=376):
+    """Left keypoints, a right set and a matchGrid-style m12 with: unmatched rows, matches violating the epipolar bound,
+    disparities below / exactly at min_disp, several pyramid levels."""
+    rng = np.random.default_rng(seed)
+    kp_l = np.stack([rng.uniform(0, W, n_l), rng.uniform(0, H, n_l)], 1).astype(np.float32)
+    kp_r = np.stack([rng.uniform(0, W, n_r), rng.uniform(0, H, n_r)], 1).astype(np.float32)
+    m12 = np.full(n_l, -1, np.int32)
+    k = int(min(n_l, n_r) * 0.8)
+    src, dst = rng.permutation(n_l)[:k], rng.permutation(n_r)[:k]
+    m12[src] = dst
+    disp = rng.uniform(-2.0, 120.0, k).astype(np.float32)
+    disp[: k // 10] = 1.0                                             # exactly the default min_disp
+    kp_r[dst, 0] = kp_l[src, 0] - disp
+    dy = rng.normal(0, 0.6, k).astype(np.float32)
+    dy[k // 10: k // 5] = 0.0
+    dy[k // 5: k // 4] = 1.0                                          # exactly the default max_dist_epip (when representable)
+    kp_r[dst, 1] = kp_l[src, 1] + dy
+    octave = rng.integers(0, 8, n_l).astype(np.int32)
+    desc = rng.integers(0, 256, (n_l, 32), dtype=np.uint8)
+    return kp_l, octave, desc, kp_r, m12
+
+
+def make_lift_lines(n_l, n_r, seed, W=1241, H=376):
+    """Inputs of the line lifting step (src/stereoFrame.cpp:348-397): segments, KeyLine angle / octave, descriptors, m12."""
+    rng = np.random.default_rng(seed)
+
+    def segs(n):
+        s = np.stack([rng.uniform(0, W, n), rng.uniform(0, H, n)], 1)
+        ang, ln = rng.uniform(0, np.pi, n), rng.uniform(5, 200, n)
+        return s, s + np.stack([ln * np.cos(ang), ln * np.sin(ang)], 1)
+    sl, el = segs(n_l)
+    sr, er = segs(n_r)
+    m12 = np.full(n_l, -1, np.int32)
+    k = int(min(n_l, n_r) * 0.8)
+    src, dst = rng.permutation(n_l)[:k], rng.permutation(n_r)[:k]
+    m12[src] = dst
+    ds, de = rng.uniform(-2.0, 120.0, k), None
+    de = ds * rng.uniform(0.5, 1.5, k)                                # some pairs fail ls_min_disp_ratio
+    # the right segment covers a perturbed sub-range of the left one along the same image line
+    t0, t1 = rng.uniform(-0.3, 0.3, k), rng.uniform(0.7, 1.3, k)
+    d = el[src] - sl[src]
+    sr[dst] = sl[src] + t0[:, None] * d - np.stack([ds, np.zeros(k)], 1)
+    er[dst] = sl[src] + t1[:, None] * d - np.stack([de, np.zeros(k)], 1)
+    flip = rng.random(k) < 0.3                                        # right endpoints in the opposite order
+    sr[dst[flip]], er[dst[flip]] = er[dst[flip]].copy(), sr[dst[flip]].copy()
+    h = src[: max(k // 12, 1)]                                        # horizontal left segments
+    el[h, 1] = sl[h, 1] + rng.uniform(-0.15, 0.15, len(h))
+    hr = dst[max(k // 12, 1): max(k // 8, 2)]                         # exactly horizontal right segments (division by zero)
+    er[hr, 1] = sr[hr, 1]
+    seg_l = np.concatenate([sl, el], 1).astype(np.float32)
+    seg_r = np.concatenate([sr, er], 1).astype(np.float32)
+    angle = rng.uniform(-np.pi, np.pi, n_l).astype(np.float32)
+    octave = rng.integers(0, 3, n_l).astype(np.int32)
+    desc = rng.integers(0, 256, (n_l, 32), dtype=np.uint8)
+    return seg_l, angle, octave, desc, seg_r, m12

@@ -16,6 +16,7 @@ DESC_BYTES = 32
 MAX_FEATURES = 65535
 
 c_double_p = C.POINTER(C.c_double)
+c_float_p = C.POINTER(C.c_float)
 c_int32_p = C.POINTER(C.c_int32)
 c_uint8_p = C.POINTER(C.c_uint8)
 
@@ -55,6 +56,16 @@ class PlMatchedBatch(C.Structure):
 class PlGridWindow(C.Structure):
     """GridWindow: width = (left, right), height = (up, down) — include/gridStructure.h:39-41."""
     _fields_ = [("left", C.c_int32), ("right", C.c_int32), ("up", C.c_int32), ("down", C.c_int32)]
+
+
+class PlStereoConfig(C.Structure):
+    """Config values read by the 3-D lifting step (include/config.h:72-96, src/config.cpp:58-106)."""
+    _fields_ = [(k, C.c_double) for k in ("max_dist_epip", "min_disp", "ls_min_disp_ratio", "line_horiz_th",
+                                          "stereo_overlap_th", "orb_scale_factor", "lsd_scale")]
+
+
+def default_stereo_config() -> "PlStereoConfig":
+    return PlStereoConfig(1.0, 1.0, 0.7, 0.1, 0.75, 1.2, 1.2)   # src/config.cpp:58-69, :96, :106
 
 
 GRID_ROWS, GRID_COLS = 48, 64     # include/stereoFrame.h:51-52

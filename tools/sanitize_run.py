@@ -22,4 +22,9 @@ q_cell, d1, t_cell, d2 = SS.make_stereo_points(500, 480, seed=1)
 eng.match_grid_points([0, 500], q_cell, d1, [0, 480], t_cell, d2, T.PlGridWindow(10, 0, 0, 0), 0.75)
 q_line, d1, t_line, t_dir, d2 = SS.make_stereo_lines(150, 160, seed=2)
 eng.match_grid_lines([0, 150], q_line, d1, [0, 160], t_line, t_dir, d2, T.PlGridWindow(10, 0, 0, 0), 0.75, 0.75)
+sc = T.default_stereo_config()
+kp_l, octave, desc, kp_r, m12 = SS.make_lift_points(700, 650, seed=3)
+eng.stereo_lift_points(cam, sc, [0, 700], kp_l, octave, desc, [0, 650], kp_r, m12)
+seg_l, angle, octave, desc, seg_r, m12 = SS.make_lift_lines(300, 280, seed=4)
+eng.stereo_lift_lines(cam, sc, [0, 300], seg_l, angle, octave, desc, [0, 280], seg_r, m12)
 print("sanitized run ok", int(out["results"]["good"].sum()))
