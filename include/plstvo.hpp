@@ -2,7 +2,9 @@
 // the reference's method names (include/stereoFrameHandler.h:41-54) for frames of pre-extracted features.  It has no
 // Eigen / OpenCV dependency; the Eigen/OpenCV shim that makes it a drop-in for libstvo.so is in INTEGRATION.md.
 #pragma once
+#include <algorithm>
 #include <array>
+#include <cmath>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -73,14 +75,194 @@ inline int match(Context& c, const std::vector<uint8_t>& d1, const std::vector<u
                                 best_lr_matches ? 1 : 0, matches_12.data()));
 }
 
+// Host-side SE(3) helpers of the key-frame test (src/auxiliar.cpp:113-122, :143-173, :175-190), row-major arrays.
+namespace se3 {
+using Mat4 = std::array<double, 16>;
+using Mat6 = std::array<double, 36>;
+using Vec6 = std::array<double, 6>;
+
+inline Mat4 identity4() { return Mat4{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}; }
+inline Mat4 mul(const Mat4& A, const Mat4& B) {
+    Mat4 C{};
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double acc = 0.0;
+            for (int k = 0; k < 4; ++k) acc += A[4 * i + k] * B[4 * k + j];
+            C[4 * i + j] = acc;
+        }
+    return C;
+}
+inline Mat4 inverse(const Mat4& T) {                     // inverse_se3: [R^T, -R^T t]
+    Mat4 Ti = identity4();
+    for (int i = 0; i < 3; ++i) {
+        double acc = 0.0;
+        for (int k = 0; k < 3; ++k) {
+            Ti[4 * i + k] = T[4 * k + i];
+            acc += -T[4 * k + i] * T[4 * k + 3];
+        }
+        Ti[4 * i + 3] = acc;
+    }
+    return Ti;
+}
+inline Vec6 logmap(const Mat4& T) {                      // logmap_se3: x = [V^-1 t ; w]
+    double cosine = (T[0] + T[5] + T[10] - 1.0) / 2.0;
+    cosine = std::min(1.0, std::max(-1.0, cosine));
+    const double sine = std::min(1.0, std::sqrt(1.0 - cosine * cosine)), theta = std::acos(cosine);
+    double w[3] = {0, 0, 0}, V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (theta > 0.000001) {
+        const double k = theta / (2.0 * sine);
+        w[0] = k * (T[9] - T[6]);                        // skewcoords(theta (R - R^T) / (2 sine))
+        w[1] = k * (T[2] - T[8]);
+        w[2] = k * (T[4] - T[1]);
+        const double s[9] = {0, -w[2] / theta, w[1] / theta, w[2] / theta, 0, -w[0] / theta, -w[1] / theta, w[0] / theta, 0};
+        const double a = (1.0 - cosine) / theta, b = (theta - sine) / theta;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double ss = 0.0;
+                for (int m = 0; m < 3; ++m) ss += s[3 * i + m] * s[3 * m + j];
+                V[3 * i + j] = (i == j ? 1.0 : 0.0) + s[3 * i + j] * a + ss * b;
+            }
+    }
+    // V^-1 t by cofactors (Eigen's fixed 3x3 inverse)
+    const double c00 = V[4] * V[8] - V[5] * V[7], c01 = V[5] * V[6] - V[3] * V[8], c02 = V[3] * V[7] - V[4] * V[6];
+    const double det = V[0] * c00 + V[1] * c01 + V[2] * c02;
+    const double inv[9] = {c00 / det, (V[2] * V[7] - V[1] * V[8]) / det, (V[1] * V[5] - V[2] * V[4]) / det,
+                           c01 / det, (V[0] * V[8] - V[2] * V[6]) / det, (V[2] * V[3] - V[0] * V[5]) / det,
+                           c02 / det, (V[1] * V[6] - V[0] * V[7]) / det, (V[0] * V[4] - V[1] * V[3]) / det};
+    Vec6 x{};
+    for (int i = 0; i < 3; ++i) {
+        x[i] = inv[3 * i] * T[3] + inv[3 * i + 1] * T[7] + inv[3 * i + 2] * T[11];
+        x[3 + i] = w[i];
+    }
+    return x;
+}
+inline Mat6 adjoint(const Mat4& T) {                     // adjoint_se3: [R, skew(t) R; 0, R]
+    Mat6 A{};
+    const double t[3] = {T[3], T[7], T[11]};
+    const double sk[9] = {0, -t[2], t[1], t[2], 0, -t[0], -t[1], t[0], 0};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            A[6 * i + j] = T[4 * i + j];
+            A[6 * (i + 3) + j + 3] = T[4 * i + j];
+            double acc = 0.0;
+            for (int k = 0; k < 3; ++k) acc += sk[3 * i + k] * T[4 * k + j];
+            A[6 * i + j + 3] = acc;
+        }
+    return A;
+}
+inline Mat6 sandwich(const Mat6& A, const Mat6& C) {     // A C A^T
+    Mat6 AC{}, out{};
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
+            double acc = 0.0;
+            for (int k = 0; k < 6; ++k) acc += A[6 * i + k] * C[6 * k + j];
+            AC[6 * i + j] = acc;
+        }
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
+            double acc = 0.0;
+            for (int k = 0; k < 6; ++k) acc += AC[6 * i + k] * A[6 * j + k];
+            out[6 * i + j] = acc;
+        }
+    return out;
+}
+inline Mat6 uncTinv(const Mat4& T, const Mat6& cov) { return sandwich(adjoint(inverse(T)), cov); }   // uncTinv_se3
+inline double det6(Mat6 A) {                             // Matrix6d::determinant (partial-pivot LU)
+    double det = 1.0;
+    for (int c = 0; c < 6; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 6; ++r)
+            if (std::fabs(A[6 * r + c]) > std::fabs(A[6 * piv + c])) piv = r;
+        if (A[6 * piv + c] == 0.0) return 0.0;
+        if (piv != c) {
+            for (int j = 0; j < 6; ++j) std::swap(A[6 * c + j], A[6 * piv + j]);
+            det = -det;
+        }
+        det *= A[6 * c + c];
+        for (int r = c + 1; r < 6; ++r) {
+            const double f = A[6 * r + c] / A[6 * c + c];
+            for (int j = c + 1; j < 6; ++j) A[6 * r + j] -= f * A[6 * c + j];
+        }
+    }
+    return det;
+}
+}  // namespace se3
+
+// The Config values of the handler's host-side state machine (adaptive FAST threshold, key-frame test):
+// include/config.h:42-44, :56, :76-80, :100; defaults src/config.cpp:40-42, :52, :72-76, :102.
+struct HandlerConfig {
+    bool adaptative_fast = true;
+    int fast_min_th = 5, fast_max_th = 50, fast_inc_th = 5, fast_feat_th = 50;
+    float fast_err_th = 0.5f;
+    int orb_fast_th = 20;
+    double min_entropy_ratio = 0.85, max_kf_t_dist = 5.0, max_kf_r_dist = 15.0;
+};
+
+// StereoFrameHandler::updateFrame's adaptive FAST threshold (src/stereoFrameHandler.cpp:66-86): the threshold the caller's
+// keypoint detector should use for the NEXT frame.
+inline int updateFastThreshold(const HandlerConfig& c, int orb_fast_th, const StereoFrame& curr, int n_inliers_pt) {
+    if (!c.adaptative_fast) return orb_fast_th;
+    const int inc = c.fast_inc_th, feat = c.fast_feat_th;
+    if (curr.DT == se3::identity4() || curr.err_norm > c.fast_err_th) return std::max(c.fast_min_th, orb_fast_th - 2 * inc);
+    if (n_inliers_pt < feat) return std::max(c.fast_min_th, orb_fast_th - 2 * inc);
+    if (n_inliers_pt < feat * 2) return std::max(c.fast_min_th, orb_fast_th - inc);
+    if (n_inliers_pt > feat * 3) return std::min(c.fast_max_th, orb_fast_th + inc);
+    return orb_fast_th;   // the reference's last branch (> 4 feat: + 2 inc, :84-85) is unreachable behind "> 3 feat"
+}
+
+// Key-frame test on the accumulated pose entropy (src/stereoFrameHandler.cpp:1136-1218; state include/stereoFrameHandler.h:81-86)
+struct KeyframeTest {
+    bool prev_f_iskf = true;
+    double entropy_first_prevKF = 0.0;
+    se3::Mat4 T_prevKF = se3::identity4();
+    se3::Mat6 cov_prevKF_currF{};
+    int N_prevKF_currF = 0;
+    double entropy_curr = 0.0, entropy_ratio = 0.0, kf_t = 0.0, kf_r = 0.0;   // diagnostics of the last test
+
+    bool needNewKF(const HandlerConfig& hcfg_, const StereoFrame& curr_frame) {   // :1136-1187
+        const double k_entropy = 3.0 * (1.0 + std::log(2.0 * std::acos(-1.0)));
+        if (prev_f_iskf) {                               // :1140-1153
+            const double d = se3::det6(curr_frame.DT_cov);
+            entropy_first_prevKF = (d != 0.0) ? k_entropy + 0.5 * std::log(d) : -999999999.99;
+            prev_f_iskf = false;
+        }
+        const se3::Vec6 dX = se3::logmap(se3::mul(se3::inverse(curr_frame.Tfw), T_prevKF));   // :1156-1159
+        kf_t = std::sqrt(dX[0] * dX[0] + dX[1] * dX[1] + dX[2] * dX[2]);
+        kf_r = std::sqrt(dX[3] * dX[3] + dX[4] * dX[4] + dX[5] * dX[5]) * 180.f / 3.1415926535897932384626433832795;
+        const se3::Mat6 add = se3::sandwich(se3::adjoint(T_prevKF), se3::uncTinv(curr_frame.DT, curr_frame.DT_cov));   // :1162-1164
+        for (int i = 0; i < 36; ++i) cov_prevKF_currF[i] += add[i];
+        entropy_curr = k_entropy + 0.5 * std::log(se3::det6(cov_prevKF_currF));
+        entropy_ratio = entropy_curr / entropy_first_prevKF;
+        bool zero_cov = true;
+        for (double v : curr_frame.DT_cov) zero_cov = zero_cov && (v == 0.0);
+        if (entropy_ratio < hcfg_.min_entropy_ratio || std::isnan(entropy_ratio) || std::isinf(entropy_ratio) ||
+            (zero_cov && curr_frame.DT == se3::identity4()) || kf_t > hcfg_.max_kf_t_dist || kf_r > hcfg_.max_kf_r_dist ||
+            N_prevKF_currF > 10)                         // :1173-1175
+            return true;
+        N_prevKF_currF++;
+        return false;
+    }
+    void currFrameIsKF(StereoFrame& curr_frame) {        // :1189-1218 (feature idx renumbering is the caller's: dense order already)
+        curr_frame.Tfw = se3::identity4();
+        for (int i = 0; i < 36; ++i) curr_frame.Tfw_cov[i] = (i % 7 == 0) ? 1.0 : 0.0;
+        T_prevKF = curr_frame.Tfw;
+        cov_prevKF_currF.fill(0.0);
+        prev_f_iskf = true;
+        N_prevKF_currF = 0;
+    }
+};
+
 // StereoFrameHandler surface: initialize / insertStereoPair / optimizePose / updateFrame (app/imagesStVO.cpp:88-124)
 class StereoFrameHandler {
 public:
-    StereoFrameHandler(Context& ctx, const PlCamera& cam, const PlConfig& cfg) : ctx_(ctx), cam_(cam), cfg_(cfg) {}
+    StereoFrameHandler(Context& ctx, const PlCamera& cam, const PlConfig& cfg, const HandlerConfig& hcfg = HandlerConfig{})
+        : ctx_(ctx), cam_(cam), cfg_(cfg), hcfg_(hcfg) {}
 
     void initialize(StereoFrame frame) {                 // src/stereoFrameHandler.cpp:35-52
+        orb_fast_th = hcfg_.orb_fast_th;                 // :38 (the caller extracts features with this threshold)
         prev_frame = std::move(frame);
         for (int i = 0; i < 36; ++i) prev_frame.Tfw_cov[i] = (i % 7 == 0) ? 1.0 : 0.0;
+        kf = KeyframeTest{};                             // :48-51
         has_prev_ = true;
     }
     void insertStereoPair(StereoFrame frame) {           // :54-60 (feature extraction is the caller's)
@@ -119,20 +301,28 @@ public:
         n_inliers = result_.n_inliers;
     }
     void updateFrame() {                                 // :62-102
+        orb_fast_th = updateFastThreshold(hcfg_, orb_fast_th, curr_frame, n_inliers_pt);   // :66-86
         prev_frame = std::move(curr_frame);
         curr_frame = StereoFrame{};
     }
+
+    // key-frame test (:1136-1218), PL-SLAM hooks: state in `kf`
+    bool needNewKF() { return kf.needNewKF(hcfg_, curr_frame); }
+    void currFrameIsKF() { kf.currFrameIsKF(curr_frame); }
     const PlPoseResult& result() const { return result_; }
 
     StereoFrame prev_frame, curr_frame;
     std::vector<int32_t> matches_pt, matches_ls;         // prev index -> curr index or -1
     std::vector<uint8_t> inlier_pt, inlier_ls;           // per prev feature: matched and still an inlier
     int n_inliers = 0, n_inliers_pt = 0, n_inliers_ls = 0;
+    int orb_fast_th = 20;                                // include/stereoFrameHandler.h:62
+    KeyframeTest kf;
 
 private:
     Context& ctx_;
     PlCamera cam_;
     PlConfig cfg_;
+    HandlerConfig hcfg_;
     PlPoseResult result_{};
     bool has_prev_ = false;
 };

@@ -51,6 +51,18 @@ def lib_path(native: bool = False) -> str:
     return lib
 
 
+class OrcHandlerConfig(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("adaptative_fast", "fast_min_th", "fast_max_th", "fast_inc_th", "fast_feat_th",
+                                         "orb_fast_th")] + [("fast_err_th", C.c_float), ("min_entropy_ratio", C.c_double),
+                                                            ("max_kf_t_dist", C.c_double), ("max_kf_r_dist", C.c_double)]
+
+
+class OrcKfState(C.Structure):
+    _fields_ = [("prev_f_iskf", C.c_int32), ("N_prevKF_currF", C.c_int32), ("entropy_first_prevKF", C.c_double),
+                ("T_prevKF", C.c_double * 16), ("cov_prevKF_currF", C.c_double * 36), ("entropy_curr", C.c_double),
+                ("entropy_ratio", C.c_double), ("t", C.c_double), ("r", C.c_double)]
+
+
 class Oracle:
     def __init__(self, native: bool = False):
         self.lib = L = C.CDLL(lib_path(native))
@@ -78,6 +90,18 @@ class Oracle:
                                             dp, dp, dp, dp, dp, i32p, u8p, i32p]
         L.orc_line_segment_overlap_stereo.restype = C.c_double
         L.orc_line_segment_overlap_stereo.argtypes = [scp, C.c_double, C.c_double, C.c_double, C.c_double]
+        L.orc_handler_default_config.restype = None
+        L.orc_handler_default_config.argtypes = [C.POINTER(OrcHandlerConfig)]
+        L.orc_update_fast_threshold.restype = C.c_int
+        L.orc_update_fast_threshold.argtypes = [C.POINTER(OrcHandlerConfig), C.c_int, dp, C.c_double, C.c_int]
+        L.orc_kf_reset.restype = None
+        L.orc_kf_reset.argtypes = [C.POINTER(OrcKfState)]
+        L.orc_det6.restype = C.c_double
+        L.orc_det6.argtypes = [dp]
+        L.orc_unctinv_se3.restype = None
+        L.orc_unctinv_se3.argtypes = [dp, dp, dp]
+        L.orc_need_new_kf.restype = C.c_int
+        L.orc_need_new_kf.argtypes = [C.POINTER(OrcHandlerConfig), C.POINTER(OrcKfState), dp, dp, dp]
         L.orc_line_cells.restype = C.c_int
         L.orc_line_cells.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, i32p, C.c_int]
         for name, n_in, n_out in [("orc_inverse_se3", 16, 16), ("orc_expmap_se3", 6, 16),
@@ -179,6 +203,34 @@ class Oracle:
                                           self._dp(t_line), self._dp(t_dir), d2.ctypes.data_as(T.c_uint8_p), len(d2),
                                           m12.ctypes.data_as(T.c_int32_p))
         return n, m12
+
+    # ---- host-side state machine (adaptive FAST threshold, key-frame test) ----
+    def handler_default_config(self):
+        c = OrcHandlerConfig()
+        self.lib.orc_handler_default_config(C.byref(c))
+        return c
+
+    def update_fast_threshold(self, c, th, DT, err_norm, n_inliers_pt):
+        DT = np.ascontiguousarray(DT, np.float64)
+        return self.lib.orc_update_fast_threshold(C.byref(c), int(th), self._dp(DT), float(err_norm), int(n_inliers_pt))
+
+    def kf_state(self):
+        s = OrcKfState()
+        self.lib.orc_kf_reset(C.byref(s))
+        return s
+
+    def need_new_kf(self, c, state, Tfw, DT, DT_cov):
+        Tfw, DT, DT_cov = (np.ascontiguousarray(a, np.float64) for a in (Tfw, DT, DT_cov))
+        return bool(self.lib.orc_need_new_kf(C.byref(c), C.byref(state), self._dp(Tfw), self._dp(DT), self._dp(DT_cov)))
+
+    def det6(self, A):
+        return self.lib.orc_det6(self._dp(np.ascontiguousarray(A, np.float64)))
+
+    def unctinv_se3(self, T, cov):
+        out = np.zeros((6, 6))
+        self.lib.orc_unctinv_se3(self._dp(np.ascontiguousarray(T, np.float64)), self._dp(np.ascontiguousarray(cov, np.float64)),
+                                 self._dp(out))
+        return out
 
     # ---- 3-D lifting of the stereo matches (one frame) ----
     def stereo_lift_points(self, cam, scfg, kp_l, octave_l, desc_l, kp_r, m12):

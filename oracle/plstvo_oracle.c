@@ -1473,3 +1473,112 @@ int orc_track_batch(const PlCamera* cam, const PlConfig* cfg, const PlFrameBatch
     free(th);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * host-side state machine: adaptive FAST threshold and the key-frame test
+ * ---------------------------------------------------------------------------------------------- */
+void orc_handler_default_config(OrcHandlerConfig* c) {   /* src/config.cpp:40-42, :52, :72-76, :102 */
+    c->adaptative_fast = 1; c->fast_min_th = 5; c->fast_max_th = 50; c->fast_inc_th = 5; c->fast_feat_th = 50;
+    c->orb_fast_th = 20; c->fast_err_th = 0.5f; c->min_entropy_ratio = 0.85; c->max_kf_t_dist = 5.0; c->max_kf_r_dist = 15.0;
+}
+
+static int is_identity4(const double T[16]) {
+    for (int i = 0; i < 16; ++i)
+        if (T[i] != ((i % 5 == 0) ? 1.0 : 0.0)) return 0;
+    return 1;
+}
+
+int orc_update_fast_threshold(const OrcHandlerConfig* c, int th, const double DT[16], double err_norm, int n_inliers_pt) {
+    if (!c->adaptative_fast) return th;   /* src/stereoFrameHandler.cpp:66-86 */
+    const int mn = c->fast_min_th, mx = c->fast_max_th, inc = c->fast_inc_th, feat = c->fast_feat_th;
+    if (is_identity4(DT) || err_norm > c->fast_err_th) th = (mn > th - 2 * inc) ? mn : th - 2 * inc;
+    else if (n_inliers_pt < feat) th = (mn > th - 2 * inc) ? mn : th - 2 * inc;
+    else if (n_inliers_pt < feat * 2) th = (mn > th - inc) ? mn : th - inc;
+    else if (n_inliers_pt > feat * 3) th = (mx < th + inc) ? mx : th + inc;
+    else if (n_inliers_pt > feat * 4) th = (mx < th + 2 * inc) ? mx : th + 2 * inc;
+    return th;
+}
+
+void orc_kf_reset(OrcKfState* s) {
+    memset(s, 0, sizeof(*s));
+    for (int i = 0; i < 4; ++i) s->T_prevKF[5 * i] = 1.0;
+    s->prev_f_iskf = 1;
+}
+
+double orc_det6(const double Ain[36]) {   /* Eigen: PartialPivLU determinant for fixed sizes above 4 */
+    double A[36], det = 1.0;
+    memcpy(A, Ain, sizeof(A));
+    for (int c = 0; c < 6; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 6; ++r)
+            if (fabs(A[6 * r + c]) > fabs(A[6 * piv + c])) piv = r;
+        if (A[6 * piv + c] == 0.0) return 0.0;
+        if (piv != c) {
+            for (int j = 0; j < 6; ++j) { double t = A[6 * c + j]; A[6 * c + j] = A[6 * piv + j]; A[6 * piv + j] = t; }
+            det = -det;
+        }
+        det *= A[6 * c + c];
+        for (int r = c + 1; r < 6; ++r) {
+            const double f = A[6 * r + c] / A[6 * c + c];
+            for (int j = c + 1; j < 6; ++j) A[6 * r + j] -= f * A[6 * c + j];
+        }
+    }
+    return det;
+}
+
+static void sandwich6(const double A[36], const double C[36], double out[36]) {   /* A C A^T */
+    double AC[36];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
+            double acc = 0.0;
+            for (int k = 0; k < 6; ++k) acc += A[6 * i + k] * C[6 * k + j];
+            AC[6 * i + j] = acc;
+        }
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
+            double acc = 0.0;
+            for (int k = 0; k < 6; ++k) acc += AC[6 * i + k] * A[6 * j + k];
+            out[6 * i + j] = acc;
+        }
+}
+
+void orc_unctinv_se3(const double T[16], const double cov[36], double out[36]) {   /* src/auxiliar.cpp:184-190 */
+    double Ti[16], Ad[36];
+    orc_inverse_se3(T, Ti);
+    orc_adjoint_se3(Ti, Ad);
+    sandwich6(Ad, cov, out);
+}
+
+int orc_need_new_kf(const OrcHandlerConfig* c, OrcKfState* s, const double Tfw[16], const double DT[16], const double DT_cov[36]) {
+    const double k_entropy = 3.0 * (1.0 + log(2.0 * acos(-1)));   /* src/stereoFrameHandler.cpp:1136-1187 */
+    if (s->prev_f_iskf) {
+        const double d = orc_det6(DT_cov);
+        s->entropy_first_prevKF = (d != 0.0) ? k_entropy + 0.5 * log(d) : -999999999.99;
+        s->prev_f_iskf = 0;
+    }
+    double Ti[16], D[16], dX[6];
+    orc_inverse_se3(Tfw, Ti);
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double acc = 0.0;
+            for (int k = 0; k < 4; ++k) acc += Ti[4 * i + k] * s->T_prevKF[4 * k + j];
+            D[4 * i + j] = acc;
+        }
+    orc_logmap_se3(D, dX);
+    s->t = sqrt(dX[0] * dX[0] + dX[1] * dX[1] + dX[2] * dX[2]);
+    s->r = sqrt(dX[3] * dX[3] + dX[4] * dX[4] + dX[5] * dX[5]) * 180.f / 3.1415926535897932384626433832795;
+    double Ad[36], cinv[36], add[36];
+    orc_adjoint_se3(s->T_prevKF, Ad);
+    orc_unctinv_se3(DT, DT_cov, cinv);
+    sandwich6(Ad, cinv, add);
+    for (int i = 0; i < 36; ++i) s->cov_prevKF_currF[i] += add[i];
+    s->entropy_curr = k_entropy + 0.5 * log(orc_det6(s->cov_prevKF_currF));
+    s->entropy_ratio = s->entropy_curr / s->entropy_first_prevKF;
+    int zero_cov = 1;
+    for (int i = 0; i < 36; ++i) zero_cov = zero_cov && (DT_cov[i] == 0.0);
+    if (s->entropy_ratio < c->min_entropy_ratio || isnan(s->entropy_ratio) || isinf(s->entropy_ratio) ||
+        (zero_cov && is_identity4(DT)) || s->t > c->max_kf_t_dist || s->r > c->max_kf_r_dist || s->N_prevKF_currF > 10)
+        return 1;
+    s->N_prevKF_currF++;
+    return 0;
+}

@@ -102,6 +102,26 @@ int orc_track_batch(const PlCamera* cam, const PlConfig* cfg, const PlFrameBatch
                     int32_t* m12_pt, int32_t* m12_ls, uint8_t* inlier_pt, uint8_t* inlier_ls,
                     int threads, int faithful, double* stage_ms);
 
+/* ---- host-side state machine of the handler ---- */
+typedef struct OrcHandlerConfig {   /* src/config.cpp:40-42, :52, :72-76, :102 */
+    int32_t adaptative_fast, fast_min_th, fast_max_th, fast_inc_th, fast_feat_th, orb_fast_th;
+    float   fast_err_th;
+    double  min_entropy_ratio, max_kf_t_dist, max_kf_r_dist;
+} OrcHandlerConfig;
+typedef struct OrcKfState {         /* include/stereoFrameHandler.h:81-86 */
+    int32_t prev_f_iskf, N_prevKF_currF;
+    double  entropy_first_prevKF, T_prevKF[16], cov_prevKF_currF[36];
+    double  entropy_curr, entropy_ratio, t, r;   /* diagnostics of the last test */
+} OrcKfState;
+void   orc_handler_default_config(OrcHandlerConfig* c);
+/* updateFrame's adaptive FAST threshold, src/stereoFrameHandler.cpp:66-86 */
+int    orc_update_fast_threshold(const OrcHandlerConfig* c, int orb_fast_th, const double DT[16], double err_norm, int n_inliers_pt);
+void   orc_kf_reset(OrcKfState* s);                                                     /* :48-51, :1213-1216 */
+double orc_det6(const double A[36]);                                                    /* Matrix6d::determinant */
+void   orc_unctinv_se3(const double T[16], const double cov[36], double out[36]);       /* src/auxiliar.cpp:184-190 */
+int    orc_need_new_kf(const OrcHandlerConfig* c, OrcKfState* s, const double Tfw[16], const double DT[16],
+                       const double DT_cov[36]);                                        /* :1136-1187 */
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,111 @@ from .engine import Engine
 
 
 @dataclass
+class HandlerConfig:
+    """Config values of the host-side state machine (src/config.cpp:40-42, :52, :72-76, :102)."""
+    adaptative_fast: bool = True
+    fast_min_th: int = 5
+    fast_max_th: int = 50
+    fast_inc_th: int = 5
+    fast_feat_th: int = 50
+    fast_err_th: float = 0.5
+    orb_fast_th: int = 20
+    min_entropy_ratio: float = 0.85
+    max_kf_t_dist: float = 5.0
+    max_kf_r_dist: float = 15.0
+
+
+def update_fast_threshold(c: HandlerConfig, orb_fast_th: int, DT, err_norm: float, n_inliers_pt: int) -> int:
+    """updateFrame's adaptive FAST threshold (src/stereoFrameHandler.cpp:66-86)."""
+    if not c.adaptative_fast:
+        return orb_fast_th
+    inc, feat = c.fast_inc_th, c.fast_feat_th
+    if np.array_equal(np.asarray(DT).reshape(4, 4), np.eye(4)) or err_norm > float(np.float32(c.fast_err_th)):
+        return max(c.fast_min_th, orb_fast_th - 2 * inc)
+    if n_inliers_pt < feat:
+        return max(c.fast_min_th, orb_fast_th - 2 * inc)
+    if n_inliers_pt < 2 * feat:
+        return max(c.fast_min_th, orb_fast_th - inc)
+    if n_inliers_pt > 3 * feat:
+        return min(c.fast_max_th, orb_fast_th + inc)
+    return orb_fast_th          # the reference's "> 4 feat" branch (:84-85) sits behind "> 3 feat": unreachable
+
+
+def _inverse_se3(T):
+    Ti = np.eye(4)
+    Ti[:3, :3] = T[:3, :3].T
+    Ti[:3, 3] = -T[:3, :3].T @ T[:3, 3]
+    return Ti
+
+
+def _skew(v):
+    return np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]], float)
+
+
+def _adjoint_se3(T):
+    A = np.zeros((6, 6))
+    A[:3, :3] = A[3:, 3:] = T[:3, :3]
+    A[:3, 3:] = _skew(T[:3, 3]) @ T[:3, :3]
+    return A
+
+
+def _logmap_se3(T):
+    """src/auxiliar.cpp:143-173."""
+    R = T[:3, :3]
+    cosine = min(1.0, max(-1.0, (np.trace(R) - 1.0) / 2.0))
+    sine = min(1.0, np.sqrt(1.0 - cosine * cosine))
+    theta = np.arccos(cosine)
+    w, V = np.zeros(3), np.eye(3)
+    if theta > 1e-6:
+        w_hat = theta * (R - R.T) / (2.0 * sine)
+        w = np.array([w_hat[2, 1], w_hat[0, 2], w_hat[1, 0]])
+        s = _skew(w) / theta
+        V = np.eye(3) + s * (1.0 - cosine) / theta + s @ s * (theta - sine) / theta
+    return np.concatenate([np.linalg.solve(V, T[:3, 3]), w])
+
+
+class KeyframeTest:
+    """needNewKF / currFrameIsKF (src/stereoFrameHandler.cpp:1136-1218; state include/stereoFrameHandler.h:81-86)."""
+    K_ENTROPY = 3.0 * (1.0 + np.log(2.0 * np.arccos(-1.0)))
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.prev_f_iskf, self.N_prevKF_currF = True, 0
+        self.entropy_first_prevKF = 0.0
+        self.T_prevKF, self.cov_prevKF_currF = np.eye(4), np.zeros((6, 6))
+        self.entropy_curr = self.entropy_ratio = self.t = self.r = 0.0
+
+    def needNewKF(self, c: HandlerConfig, Tfw, DT, DT_cov) -> bool:
+        Tfw, DT, DT_cov = np.asarray(Tfw).reshape(4, 4), np.asarray(DT).reshape(4, 4), np.asarray(DT_cov).reshape(6, 6)
+        with np.errstate(all="ignore"):
+            if self.prev_f_iskf:
+                d = np.linalg.det(DT_cov)
+                self.entropy_first_prevKF = self.K_ENTROPY + 0.5 * np.log(d) if d != 0.0 else -999999999.99
+                self.prev_f_iskf = False
+            dX = _logmap_se3(_inverse_se3(Tfw) @ self.T_prevKF)
+            self.t = float(np.linalg.norm(dX[:3]))
+            self.r = float(np.linalg.norm(dX[3:]) * 180.0 / np.pi)
+            adj_inv = _adjoint_se3(_inverse_se3(DT))
+            adj_kf = _adjoint_se3(self.T_prevKF)
+            self.cov_prevKF_currF = self.cov_prevKF_currF + adj_kf @ (adj_inv @ DT_cov @ adj_inv.T) @ adj_kf.T
+            self.entropy_curr = float(self.K_ENTROPY + 0.5 * np.log(np.linalg.det(self.cov_prevKF_currF)))
+            self.entropy_ratio = float(self.entropy_curr / self.entropy_first_prevKF)
+        degenerate = not DT_cov.any() and np.array_equal(DT, np.eye(4))
+        if (self.entropy_ratio < c.min_entropy_ratio or not np.isfinite(self.entropy_ratio) or degenerate
+                or self.t > c.max_kf_t_dist or self.r > c.max_kf_r_dist or self.N_prevKF_currF > 10):
+            return True
+        self.N_prevKF_currF += 1
+        return False
+
+    def currFrameIsKF(self, frame):
+        frame.Tfw, frame.Tfw_cov = np.eye(4), np.eye(6)
+        self.T_prevKF, self.cov_prevKF_currF = np.eye(4), np.zeros((6, 6))
+        self.prev_f_iskf, self.N_prevKF_currF = True, 0
+
+
+@dataclass
 class StereoFrame:
     """What the path reads of StereoFrame (include/stereoFrame.h:59-115) + the per-frame results."""
     features: T.FrameBatch                    # a batch of exactly one frame
@@ -30,8 +135,12 @@ class StereoFrame:
 
 
 class StereoFrameHandler:
-    def __init__(self, cam: T.PlCamera, cfg: Optional[T.PlConfig] = None, engine: Optional[Engine] = None):
+    def __init__(self, cam: T.PlCamera, cfg: Optional[T.PlConfig] = None, engine: Optional[Engine] = None,
+                 hcfg: Optional[HandlerConfig] = None):
         self.cam, self.cfg = cam, cfg or T.default_config()
+        self.hcfg = hcfg or HandlerConfig()
+        self.orb_fast_th = self.hcfg.orb_fast_th         # src/stereoFrameHandler.cpp:38
+        self.kf = KeyframeTest()
         self.engine = engine or Engine()
         self.prev_frame: Optional[StereoFrame] = None
         self.curr_frame: Optional[StereoFrame] = None
@@ -45,6 +154,8 @@ class StereoFrameHandler:
         assert features.B == 1
         self.prev_frame = StereoFrame(features, idx)
         self.curr_frame = self.prev_frame
+        self.orb_fast_th = self.hcfg.orb_fast_th
+        self.kf.reset()                                  # :48-51
 
     def insertStereoPair(self, features: T.FrameBatch, idx: int = 0):
         """src/stereoFrameHandler.cpp:54-60: new frame + f2fTracking.  The fused device call already computes the
@@ -78,8 +189,19 @@ class StereoFrameHandler:
         self.n_inliers_pt, self.n_inliers_ls, self.n_inliers = int(r["n_inliers_pt"]), int(r["n_inliers_ls"]), int(r["n_inliers"])
         self.status = int(r["status"])
 
+    def needNewKF(self) -> bool:
+        """src/stereoFrameHandler.cpp:1136-1187."""
+        c = self.curr_frame
+        return self.kf.needNewKF(self.hcfg, c.Tfw, c.DT, c.DT_cov)
+
+    def currFrameIsKF(self):
+        """src/stereoFrameHandler.cpp:1189-1218."""
+        self.kf.currFrameIsKF(self.curr_frame)
+
     def updateFrame(self):
-        """src/stereoFrameHandler.cpp:62-102 (the adaptive FAST threshold belongs to feature extraction)."""
+        """src/stereoFrameHandler.cpp:62-102: orb_fast_th is the threshold the caller's detector uses for the next frame."""
+        c = self.curr_frame
+        self.orb_fast_th = update_fast_threshold(self.hcfg, self.orb_fast_th, c.DT, c.err_norm, self.n_inliers_pt)
         self.matched_pt = np.zeros(0, np.int64)
         self.matched_ls = np.zeros(0, np.int64)
         self.prev_frame, self.curr_frame = self.curr_frame, None
