@@ -1309,17 +1309,16 @@ int plstvo_gn_eval_stream(PlContext* ctx, const PlCamera* cam, const PlConfig* c
     static DevBuf rec_pt, rec_ls;
     CK(ctx, rec_pt.ensure(std::max<size_t>(n * 32, 32)));
     CK(ctx, rec_ls.ensure(std::max<size_t>(l * 64, 64)));
-    CK(ctx, launch_pack_records(md, (int)n, (int)l, rec_pt.as<float4>(), rec_ls.as<float4>(), s));
+    CK(ctx, launch_pack_records(md, B, (int)n, (int)l, rec_pt.as<float4>(), rec_ls.as<float4>(), s));
     ctx->launches++;
-    // blocks per problem: every CTA gets at least ~4 tiles of 256 records, and the grid at least a few waves
-    size_t max_tiles = 1;
+    // slices per problem: a work item is ~12 tiles of 16 KB (more slices only when the batch cannot fill the persistent grid)
+    int max_tiles = 1;
     for (int p = 0; p < B; ++p)
-        max_tiles = std::max<size_t>(max_tiles, (size_t)((m->pt_off[p + 1] - m->pt_off[p] + 255) / 256) +
-                                                    (size_t)((m->ls_off[p + 1] - m->ls_off[p] + 255) / 256));
-    int bpp = (int)std::max<size_t>(1, std::min<size_t>(max_tiles / 8, 64));
-    while ((long)B * bpp < 6L * ctx->sm_count && bpp < (int)max_tiles && bpp < 64) ++bpp;
+        max_tiles = std::max(max_tiles, gn_stream_tiles(m->pt_off[p + 1] - m->pt_off[p], m->ls_off[p + 1] - m->ls_off[p]));
+    int bpp = std::max(1, std::min(64, max_tiles / 12));
+    while ((long)B * bpp < 4L * ctx->sm_count && 2 * bpp <= max_tiles && bpp < 64) ++bpp;
     CK(ctx, ctx->gn_in[0].ensure((size_t)B * 16 * 8));
-    CK(ctx, ctx->gn_in[1].ensure((size_t)B * bpp * (ACC_N + 1) * 8));
+    CK(ctx, ctx->gn_in[1].ensure((size_t)B * bpp * gn_stream_partials_per_slice() * (ACC_N + 1) * 8));
     CK(ctx, ctx->gn_out[2].ensure((size_t)B * 36 * 8));
     CK(ctx, ctx->gn_out[3].ensure((size_t)B * 7 * 8));
     CK(ctx, cudaMemcpyAsync(ctx->gn_in[0].p, DT, (size_t)B * 16 * 8, cudaMemcpyHostToDevice, s));
@@ -1332,7 +1331,7 @@ int plstvo_gn_eval_stream(PlContext* ctx, const PlCamera* cam, const PlConfig* c
     auto sweep = [&]() {
         return launch_gn_eval_stream(*cam, *cfg, bufs[0].as<int32_t>(), bufs[1].as<int32_t>(), rec_pt.as<float4>(),
                                      rec_ls.as<float4>(), B, ctx->gn_in[0].as<double>(), ctx->gn_in[1].as<double>(), bpp,
-                                     dH, dg, de, s);
+                                     ctx->sm_count, dH, dg, de, s);
     };
     CK(ctx, sweep());   // warm-up
     CK(ctx, cudaEventRecord(e0, s));

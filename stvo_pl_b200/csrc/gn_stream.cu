@@ -2,17 +2,24 @@
 // matched lists STREAMED from HBM: the HBM-roofline kernel of config C5 (1920x1080, 8000 points + 2000 lines,
 // B >= 1024 problems resident so that one sweep is far larger than L2).
 //
-// Layout: the fp32-packed records SURVEY 8(a) A4/A5 define — the algorithmic bytes of one evaluation are exactly what
-// the kernel reads:
-//   point, 32 B : {Px, Py, Pz, sigma2} {u_obs, v_obs, inlier, -}
-//   line,  64 B : {sPx, sPy, sPz, sigma2} {ePx, ePy, ePz, inlier} {l0, l1, l2, -} {spl_u, spl_v, epl_u, epl_v}
-// (packed once on the device from the double arrays of PlMatchedBatch when the batch is made resident).
-// Tiles of 256 records are staged into shared memory by the TMA engine (cp.async.bulk + mbarrier, 4 stages in
-// flight per CTA), so HBM latency is decoupled from warp occupancy.  Per-feature arithmetic is fp32 (the survey's
-// precision probe: pose deviation 3e-8 rad / 8e-7 m); a thread keeps its <= 64 features' partial sums in fp32, the
-// reduction across threads, CTAs and the 10 000 features of a problem runs in fp64 in a fixed order (deterministic).
-// The solver proper (solve.cu) stays fp64 end to end; this kernel is the streamed evaluator of the roofline run.
+// Records: the fp32-packed layout SURVEY 8(a) A4/A5 defines — the algorithmic bytes of one evaluation are exactly what
+// the kernel reads.  Pose-independent per-feature quantities are formed once, in double, when the batch is packed:
+//   point, 32 B : {Px, Py, Pz, sqrt(sigma2)} {u_obs, v_obs, inlier, -}
+//   line,  64 B : {sPx, sPy, sPz, sqrt(sigma2)} {ePx, ePy, ePz, inlier} {l0, l1, l2, -} {oa, ob, oc, -}
+// (oa, ob, oc): StereoFrame::lineSegmentOverlap's parameter lambda of a projected endpoint is affine in the endpoint in all
+// three of its branches (src/stereoFrame.cpp:515-612); the coefficients depend on the previous-frame segment only.
+// Tiles of 16 KB (512 points or 256 lines) are stored plane by plane ([cnt] x float4 per plane), so that a bulk copy of
+// one contiguous range lands in shared memory in a bank-conflict-free order.
+//
+// Kernel: persistent CTAs, 2 per SM, each 8 consumer warps + 1 producer warp.  The producer's elected lane walks the CTA's
+// work items (problem, slice) and keeps a ring of 6 x 16 KB stages filled with the TMA engine (cp.async.bulk + full/empty
+// mbarriers): ~190 KB in flight per SM, HBM latency decoupled from warp occupancy, no CTA-wide barrier on the data path.
+// Per-feature arithmetic is fp32 with MUFU reciprocals / square roots (the survey's precision probe: pose deviation 3e-8
+// rad / 8e-7 m); a thread keeps its features' partial sums in fp32 and a warp folds them with a fixed-order shuffle tree;
+// warps, slices and the 10 000 features of a problem are summed in fp64 in a fixed order (deterministic).  The solver proper (solve.cu) stays fp64 end to
+// end; this kernel is the streamed evaluator of the roofline run.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -20,261 +27,397 @@ namespace plstvo {
 
 namespace {
 
-constexpr int GS_THREADS = 256;
-constexpr int GS_WARPS = GS_THREADS / 32;
-constexpr int GS_TILE = 256;                 // records per stage (one per thread)
-constexpr int GS_STAGES = 4;
-constexpr int GS_STAGE_BYTES = GS_TILE * 64;  // sized for line records
+constexpr int GS_CONSUMERS = 256;
+constexpr int GS_CWARPS = GS_CONSUMERS / 32;
+constexpr int GS_THREADS = GS_CONSUMERS + 32;          // + producer warp
+constexpr int GS_PT_TILE = 512;                        // points per stage (two per consumer thread)
+constexpr int GS_LS_TILE = 256;                        // lines per stage (one per consumer thread)
+constexpr int GS_STAGE_BYTES = 16384;
+constexpr int GS_STAGES = 6;
+constexpr int GS_NACC = ACC_N + 1;                     // 21 H + 6 g + e + count
 
-__device__ __forceinline__ void gs_jac(float sc, float gx, float gy, float gz, float dx, float dy, float* J) {
-    J[0] = +sc * dx * gz;                                   // :582-587 / :636-641
-    J[1] = +sc * dy * gz;
-    J[2] = -sc * (gx * dx + gy * dy);
-    J[3] = -sc * (gx * gy * dx + gy * gy * dy + gz * gz * dy);
-    J[4] = +sc * (gx * gx * dx + gz * gz * dx + gx * gy * dy);
-    J[5] = +sc * (gx * gz * dy - gy * gz * dx);
+__device__ __forceinline__ float gs_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float gs_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float gs_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ void gs_acc(float* acc, const float* J, float r, float w) {
-    int k = 0;
+// J (+)= the 1x6 Jacobian row of :582-587 / :636-641 with the scale folded into the direction (dxs, dys)
+template <bool ADD>
+__device__ __forceinline__ void gs_jac(float X, float Y, float Z, float dxs, float dys, float* J) {
+    const float t = fmaf(X, dxs, Y * dys), zz = Z * Z;
+    const float j0 = dxs * Z, j1 = dys * Z, j3 = fmaf(Y, t, zz * dys), j4 = fmaf(X, t, zz * dxs);
+    const float j5 = Z * fmaf(X, dys, -(Y * dxs));
+    if (ADD) { J[0] += j0; J[1] += j1; J[2] -= t; J[3] -= j3; J[4] += j4; J[5] += j5; }
+    else     { J[0] = j0;  J[1] = j1;  J[2] = -t; J[3] = -j3; J[4] = j4;  J[5] = j5; }
+}
+
+// Per-thread accumulators: 21 unique entries of H = sum w J J^T (row-major upper triangle), 6 of g = sum w r J, e, count.
+struct GsAccScalar {
+    float a[GS_NACC];
+    __device__ __forceinline__ void clear() {
 #pragma unroll
-    for (int i = 0; i < 6; i++) {
-        const float Jw = J[i] * w;
-#pragma unroll
-        for (int j = i; j < 6; j++) acc[k++] += Jw * J[j];
-        acc[21 + i] += Jw * r;
+        for (int i = 0; i < GS_NACC; i++) a[i] = 0.f;
     }
-    acc[27] += r * r * w;
-    acc[28] += 1.0f;
-}
+    __device__ __forceinline__ void add(const float* J, float r, float w, float one) {
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            const float Jw = J[i] * w;
+#pragma unroll
+            for (int j = i; j < 6; j++) a[k] = fmaf(Jw, J[j], a[k]), k++;
+            a[21 + i] = fmaf(Jw, r, a[21 + i]);
+        }
+        a[27] = fmaf(r * w, r, a[27]);
+        a[28] += one;
+    }
+    __device__ __forceinline__ void unpack(float* out) const {
+#pragma unroll
+        for (int i = 0; i < GS_NACC; i++) out[i] = a[i];
+    }
+};
 
-__device__ __forceinline__ float gs_overlap_l(float ls, float le) {
+// The same sums with Blackwell's packed fp32 pipe (fma.rn.f32x2 -> FFMA2, one operand broadcast): 12 FFMA2 + 3 FMUL2 + 5
+// scalar ops per feature instead of 36.  Pairs: (00,01)(02,03)(04,05) (12,13)(14,15) (22,23)(24,25) (34,35) (44,45)
+// (g0,g1)(g2,g3)(g4,g5); scalars: 11, 33, 55, e, count.
+typedef unsigned long long gs_u64;
+__device__ __forceinline__ gs_u64 gs_pk(float lo, float hi) { gs_u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void gs_upk(gs_u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ gs_u64 gs_fma2(gs_u64 a, gs_u64 b, gs_u64 c) { gs_u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ gs_u64 gs_mul2(gs_u64 a, gs_u64 b) { gs_u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+struct GsAccPacked {
+    gs_u64 p[12];
+    float s[5];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < 12; i++) p[i] = 0ull;
+#pragma unroll
+        for (int i = 0; i < 5; i++) s[i] = 0.f;
+    }
+    __device__ __forceinline__ void add(const float* J, float r, float w, float one) {
+        const gs_u64 J01 = gs_pk(J[0], J[1]), J23 = gs_pk(J[2], J[3]), J45 = gs_pk(J[4], J[5]), ww = gs_pk(w, w), rr = gs_pk(r, r);
+        const gs_u64 W01 = gs_mul2(J01, ww), W23 = gs_mul2(J23, ww), W45 = gs_mul2(J45, ww);
+        float w0, w1, w2, w3, w4, w5;
+        gs_upk(W01, w0, w1); gs_upk(W23, w2, w3); gs_upk(W45, w4, w5);
+        const gs_u64 b0 = gs_pk(w0, w0), b1 = gs_pk(w1, w1), b2 = gs_pk(w2, w2), b3 = gs_pk(w3, w3), b4 = gs_pk(w4, w4);
+        p[0] = gs_fma2(b0, J01, p[0]); p[1] = gs_fma2(b0, J23, p[1]); p[2] = gs_fma2(b0, J45, p[2]);
+        p[3] = gs_fma2(b1, J23, p[3]); p[4] = gs_fma2(b1, J45, p[4]);
+        p[5] = gs_fma2(b2, J23, p[5]); p[6] = gs_fma2(b2, J45, p[6]);
+        p[7] = gs_fma2(b3, J45, p[7]);
+        p[8] = gs_fma2(b4, J45, p[8]);
+        p[9] = gs_fma2(W01, rr, p[9]); p[10] = gs_fma2(W23, rr, p[10]); p[11] = gs_fma2(W45, rr, p[11]);
+        s[0] = fmaf(w1, J[1], s[0]); s[1] = fmaf(w3, J[3], s[1]); s[2] = fmaf(w5, J[5], s[2]);
+        s[3] = fmaf(r * w, r, s[3]);
+        s[4] += one;
+    }
+    __device__ __forceinline__ void unpack(float* o) const {
+        gs_upk(p[0], o[0], o[1]); gs_upk(p[1], o[2], o[3]); gs_upk(p[2], o[4], o[5]);
+        o[6] = s[0];
+        gs_upk(p[3], o[7], o[8]); gs_upk(p[4], o[9], o[10]);
+        gs_upk(p[5], o[11], o[12]); gs_upk(p[6], o[13], o[14]);
+        o[15] = s[1];
+        gs_upk(p[7], o[16], o[17]);
+        gs_upk(p[8], o[18], o[19]);
+        o[20] = s[2];
+        gs_upk(p[9], o[21], o[22]); gs_upk(p[10], o[23], o[24]); gs_upk(p[11], o[25], o[26]);
+        o[27] = s[3];
+        o[28] = s[4];
+    }
+};
+
+__device__ __forceinline__ float gs_overlap_l(float ls, float le) {   // :601-610 on the two parameters
     const float lo = fminf(ls, le), hi = fmaxf(ls, le);
-    if (lo < 0.f && hi > 1.f) return 1.f;
-    if (hi < 0.f || lo > 1.f) return 0.f;
-    if (lo < 0.f) return hi;
-    if (hi > 1.f) return 1.f - lo;
-    return hi - lo;
+    float ov = fminf(hi, 1.f) - fmaxf(lo, 0.f);                       // covered part of [0, 1]
+    ov = (hi < 0.f || lo > 1.f) ? 0.f : ov;
+    return ov;
 }
 
-// StereoFrame::lineSegmentOverlap (src/stereoFrame.cpp:510-616)
-__device__ __forceinline__ float gs_overlap(float su, float sv, float eu, float ev, float pu, float pv, float qu,
-                                            float qv) {
-    const float lx = eu - su, ly = ev - sv;
-    if (fabsf(su - eu) < 1.f) {
-        const float il = 1.f / ly;
-        return gs_overlap_l((pv - sv) * il, (qv - sv) * il);
+struct GsPose {
+    float r[12];
+    float fx, fy, cx, cy, h, inv_h, fx_h;
+};
+
+// point block (:563-606); `use` = a live record flagged inlier
+template <class Acc>
+__device__ __forceinline__ void gs_point(const GsPose& P, const float4 a, const float4 b, bool use, Acc& acc) {
+    const float X = fmaf(P.r[0], a.x, fmaf(P.r[1], a.y, fmaf(P.r[2], a.z, P.r[3])));
+    const float Y = fmaf(P.r[4], a.x, fmaf(P.r[5], a.y, fmaf(P.r[6], a.z, P.r[7])));
+    const float Z = fmaf(P.r[8], a.x, fmaf(P.r[9], a.y, fmaf(P.r[10], a.z, P.r[11])));
+    const float iz = use ? gs_rcp(Z) : 0.f;                // a dead record contributes exact zeros, never a NaN
+    const float dx = fmaf(P.fx * X, iz, P.cx - b.x), dy = fmaf(P.fy * Y, iz, P.cy - b.y);
+    const float ss = fmaf(dx, dx, dy * dy);
+    const float n = gs_sqrt(ss), inv = fminf(P.inv_h, gs_rsqrt(ss));          // 1 / max(homogTh, n)
+    const float fg = (Z * Z > P.h) ? P.fx * iz * iz : P.fx_h;                 // fx / max(homogTh, Z^2)  (:577)
+    const float sc = fg * inv;
+    float J[6];
+    gs_jac<false>(X, Y, Z, sc * dx, sc * dy, J);
+    const float r = n * a.w;
+    const float w = use ? gs_rcp(fmaf(r, r, 1.f)) : 0.f;
+    acc.add(J, r, w, use ? 1.f : 0.f);
+}
+
+// line block (:610-684)
+template <class Acc>
+__device__ __forceinline__ void gs_line(const GsPose& P, const float4 a, const float4 b, const float4 c, const float4 d,
+                                        bool use, Acc& acc) {
+    const float sX = fmaf(P.r[0], a.x, fmaf(P.r[1], a.y, fmaf(P.r[2], a.z, P.r[3])));
+    const float sY = fmaf(P.r[4], a.x, fmaf(P.r[5], a.y, fmaf(P.r[6], a.z, P.r[7])));
+    const float sZ = fmaf(P.r[8], a.x, fmaf(P.r[9], a.y, fmaf(P.r[10], a.z, P.r[11])));
+    const float eX = fmaf(P.r[0], b.x, fmaf(P.r[1], b.y, fmaf(P.r[2], b.z, P.r[3])));
+    const float eY = fmaf(P.r[4], b.x, fmaf(P.r[5], b.y, fmaf(P.r[6], b.z, P.r[7])));
+    const float eZ = fmaf(P.r[8], b.x, fmaf(P.r[9], b.y, fmaf(P.r[10], b.z, P.r[11])));
+    const float isz = use ? gs_rcp(sZ) : 0.f, iez = use ? gs_rcp(eZ) : 0.f;
+    const float spu = fmaf(P.fx * sX, isz, P.cx), spv = fmaf(P.fy * sY, isz, P.cy);
+    const float epu = fmaf(P.fx * eX, iez, P.cx), epv = fmaf(P.fy * eY, iez, P.cy);
+    const float ds = fmaf(c.x, spu, fmaf(c.y, spv, c.z)), de = fmaf(c.x, epu, fmaf(c.y, epv, c.z));
+    const float ss = fmaf(ds, ds, de * de);
+    const float n = gs_sqrt(ss), iden = fminf(P.inv_h, gs_rsqrt(ss));
+    const float ks = ((sZ * sZ > P.h) ? P.fx * isz * isz : P.fx_h) * (ds * iden);
+    const float ke = ((eZ * eZ > P.h) ? P.fx * iez * iez : P.fx_h) * (de * iden);
+    float J[6];
+    gs_jac<false>(sX, sY, sZ, ks * c.x, ks * c.y, J);
+    gs_jac<true>(eX, eY, eZ, ke * c.x, ke * c.y, J);
+    const float r = n * a.w;
+    float w = gs_rcp(fmaf(r, r, 1.f));
+    w *= gs_overlap_l(fmaf(d.x, spu, fmaf(d.y, spv, d.z)), fmaf(d.x, epu, fmaf(d.y, epv, d.z)));   // :664-670
+    acc.add(J, r, use ? w : 0.f, use ? 1.f : 0.f);
+}
+
+__device__ __forceinline__ int gs_find_problem(const int32_t* __restrict__ off, int B, int i) {   // off[p] <= i < off[p+1]
+    int lo = 0, hi = B - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (off[mid] <= i) lo = mid; else hi = mid - 1;
     }
-    const float il = 1.f / lx;
-    if (fabsf(sv - ev) < 1.f) return gs_overlap_l((pu - su) * il, (qu - su) * il);
-    const float a = sv - ev, b = eu - su, c = su * ev - eu * sv;
-    const float lxy = 1.f / (a * a + b * b);
-    const float sx = (b * (b * pu - a * pv) - a * c) * lxy;
-    const float ex = (b * (b * qu - a * qv) - a * c) * lxy;
-    return gs_overlap_l((sx - su) * il, (ex - su) * il);
+    return lo;
 }
 
-__device__ __forceinline__ double gs_shfl_xor(double v, int m) { return __shfl_xor_sync(0xFFFFFFFFu, v, m); }
-
-// device-side packing of the double arrays into the fp32 records
-__global__ void pack_records_kernel(MatchedDev m, int n_pt, int n_ls, float4* __restrict__ pt, float4* __restrict__ ls) {
+// device-side packing of the double arrays into the tile-planar fp32 records
+__global__ void pack_records_kernel(MatchedDev m, int B, int n_pt, int n_ls, float4* __restrict__ pt, float4* __restrict__ ls) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_pt) {
+        const int p = gs_find_problem(m.pt_off, B, i), p0 = m.pt_off[p], np = m.pt_off[p + 1] - p0;
+        const int j = i - p0, t = j / GS_PT_TILE, r = j % GS_PT_TILE, cnt = min(GS_PT_TILE, np - t * GS_PT_TILE);
+        float4* base = pt + 2 * (size_t)(p0 + t * GS_PT_TILE);
         const size_t a = (size_t)i;
-        pt[2 * a] = make_float4((float)m.pt_P[3 * a], (float)m.pt_P[3 * a + 1], (float)m.pt_P[3 * a + 2], (float)m.pt_sigma2[a]);
-        pt[2 * a + 1] = make_float4((float)m.pt_pl_obs[2 * a], (float)m.pt_pl_obs[2 * a + 1],
+        base[r] = make_float4((float)m.pt_P[3 * a], (float)m.pt_P[3 * a + 1], (float)m.pt_P[3 * a + 2], (float)sqrt(m.pt_sigma2[a]));
+        base[cnt + r] = make_float4((float)m.pt_pl_obs[2 * a], (float)m.pt_pl_obs[2 * a + 1],
                                     (m.pt_inlier && !m.pt_inlier[a]) ? 0.f : 1.f, 0.f);
     }
     if (i < n_ls) {
+        const int p = gs_find_problem(m.ls_off, B, i), l0 = m.ls_off[p], nl = m.ls_off[p + 1] - l0;
+        const int j = i - l0, t = j / GS_LS_TILE, r = j % GS_LS_TILE, cnt = min(GS_LS_TILE, nl - t * GS_LS_TILE);
+        float4* base = ls + 4 * (size_t)(l0 + t * GS_LS_TILE);
         const size_t a = (size_t)i;
-        ls[4 * a] = make_float4((float)m.ls_sP[3 * a], (float)m.ls_sP[3 * a + 1], (float)m.ls_sP[3 * a + 2], (float)m.ls_sigma2[a]);
-        ls[4 * a + 1] = make_float4((float)m.ls_eP[3 * a], (float)m.ls_eP[3 * a + 1], (float)m.ls_eP[3 * a + 2],
+        const double su = m.ls_spl[2 * a], sv = m.ls_spl[2 * a + 1], eu = m.ls_epl[2 * a], ev = m.ls_epl[2 * a + 1];
+        const double lx = eu - su, ly = ev - sv;
+        double oa, ob, oc;
+        if (fabs(su - eu) < 1.0) {          // vertical (:515-544): lambda = (v - sv) / ly
+            oa = 0.0; ob = 1.0 / ly; oc = -sv / ly;
+        } else if (fabs(sv - ev) < 1.0) {   // horizontal (:545-574): lambda = (u - su) / lx
+            oa = 1.0 / lx; ob = 0.0; oc = -su / lx;
+        } else {                            // generic (:575-612): foot of the perpendicular, then (x - su) / lx
+            const double ca = sv - ev, cb = eu - su, cc = su * ev - eu * sv, lxy = 1.0 / (ca * ca + cb * cb);
+            oa = (cb * cb * lxy) / lx; ob = (-(ca * cb) * lxy) / lx; oc = (-(ca * cc) * lxy - su) / lx;
+        }
+        base[r] = make_float4((float)m.ls_sP[3 * a], (float)m.ls_sP[3 * a + 1], (float)m.ls_sP[3 * a + 2], (float)sqrt(m.ls_sigma2[a]));
+        base[cnt + r] = make_float4((float)m.ls_eP[3 * a], (float)m.ls_eP[3 * a + 1], (float)m.ls_eP[3 * a + 2],
                                     (m.ls_inlier && !m.ls_inlier[a]) ? 0.f : 1.f);
-        ls[4 * a + 2] = make_float4((float)m.ls_le_obs[3 * a], (float)m.ls_le_obs[3 * a + 1], (float)m.ls_le_obs[3 * a + 2], 0.f);
-        ls[4 * a + 3] = make_float4((float)m.ls_spl[2 * a], (float)m.ls_spl[2 * a + 1], (float)m.ls_epl[2 * a], (float)m.ls_epl[2 * a + 1]);
+        base[2 * cnt + r] = make_float4((float)m.ls_le_obs[3 * a], (float)m.ls_le_obs[3 * a + 1], (float)m.ls_le_obs[3 * a + 2], 0.f);
+        base[3 * cnt + r] = make_float4((float)oa, (float)ob, (float)oc, 0.f);
     }
 }
 
-__global__ void __launch_bounds__(GS_THREADS, 3)
+// the tiles of work item `item` = slice `item % bpp` of problem `item / bpp`: whole tiles, points first, then lines
+struct GsItem {
+    int p0, np, l0, nl, pt_lo, n_ptile, lt_lo, n_tiles;
+};
+__device__ __forceinline__ GsItem gs_item(const int32_t* __restrict__ pt_off, const int32_t* __restrict__ ls_off, int item, int bpp) {
+    GsItem it;
+    const int prob = item / bpp, blk = item % bpp;
+    it.p0 = pt_off[prob]; it.np = pt_off[prob + 1] - it.p0;
+    it.l0 = ls_off[prob]; it.nl = ls_off[prob + 1] - it.l0;
+    const int ptiles = (it.np + GS_PT_TILE - 1) / GS_PT_TILE, ltiles = (it.nl + GS_LS_TILE - 1) / GS_LS_TILE;
+    const int pt_per = (ptiles + bpp - 1) / bpp, lt_per = (ltiles + bpp - 1) / bpp;
+    it.pt_lo = min(ptiles, blk * pt_per);
+    it.lt_lo = min(ltiles, blk * lt_per);
+    it.n_ptile = min(ptiles, it.pt_lo + pt_per) - it.pt_lo;
+    it.n_tiles = it.n_ptile + min(ltiles, it.lt_lo + lt_per) - it.lt_lo;
+    return it;
+}
+
+template <class Acc>
+__global__ void __launch_bounds__(GS_THREADS, 2)
 gn_eval_stream_kernel(PlCamera cam, float homog_th, const int32_t* __restrict__ pt_off, const int32_t* __restrict__ ls_off,
                       const float4* __restrict__ pt, const float4* __restrict__ ls, const double* __restrict__ DTs,
-                      double* __restrict__ partial, int bpp) {
+                      double* __restrict__ partial, int bpp, int n_items) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ double red[GS_WARPS][32];
-    __shared__ float sDT[12];
-    __shared__ __align__(8) uint64_t bars[GS_STAGES];
-    const int prob = blockIdx.x / bpp, blk = blockIdx.x % bpp;
+    __shared__ float sDT[GS_STAGES][12];     // pose of the item whose first tile sits in the stage (written by the producer)
+    __shared__ __align__(8) uint64_t full[GS_STAGES], empty[GS_STAGES];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 12) sDT[tid] = (float)DTs[(size_t)prob * 16 + tid];
     if (tid == 0) {
-        for (int s = 0; s < GS_STAGES; ++s) mbar_init(&bars[s], 1);
+        for (int s = 0; s < GS_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], GS_CWARPS);
+        }
         fence_mbar_init();
     }
     __syncthreads();
-    float DT[12];
+
+    if (warp == GS_CWARPS) {   // ---- producer warp: one elected lane keeps the ring full ----
+        if (lane == 0) {
+            uint32_t k = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const GsItem it = gs_item(pt_off, ls_off, item, bpp);
+                for (int t = 0; t < it.n_tiles; ++t, ++k) {
+                    const uint32_t st = k % GS_STAGES;
+                    if (k >= GS_STAGES) mbar_wait(&empty[st], ((k / GS_STAGES) - 1) & 1);
+                    if (t == 0) {   // the item's pose rides with its first tile (ordered by the barrier's release / acquire)
+                        const double* DT = DTs + (size_t)(item / bpp) * 16;
 #pragma unroll
-    for (int i = 0; i < 12; i++) DT[i] = sDT[i];
-    const float fx = (float)cam.fx, fy = (float)cam.fy, cx = (float)cam.cx, cy = (float)cam.cy;
-
-    // this CTA's slice of the problem: whole tiles, points first, then lines
-    const int p0 = pt_off[prob], np = pt_off[prob + 1] - p0;
-    const int l0 = ls_off[prob], nl = ls_off[prob + 1] - l0;
-    const int ptiles = (np + GS_TILE - 1) / GS_TILE, ltiles = (nl + GS_TILE - 1) / GS_TILE;
-    const int pt_per = (ptiles + bpp - 1) / bpp, lt_per = (ltiles + bpp - 1) / bpp;
-    const int pt_lo = min(ptiles, blk * pt_per), pt_hi = min(ptiles, pt_lo + pt_per);
-    const int lt_lo = min(ltiles, blk * lt_per), lt_hi = min(ltiles, lt_lo + lt_per);
-    const int n_ptile = pt_hi - pt_lo, n_tiles = n_ptile + (lt_hi - lt_lo);
-
-    auto issue = [&](int t) {   // thread 0: bulk copy of tile t of this CTA into stage t % GS_STAGES
-        const int st = t % GS_STAGES;
-        const void* src;
-        uint32_t bytes;
-        if (t < n_ptile) {
-            const int f0 = (pt_lo + t) * GS_TILE, cnt = min(GS_TILE, np - f0);
-            src = pt + 2 * (size_t)(p0 + f0);
-            bytes = (uint32_t)cnt * 32u;
-        } else {
-            const int f0 = (lt_lo + (t - n_ptile)) * GS_TILE, cnt = min(GS_TILE, nl - f0);
-            src = ls + 4 * (size_t)(l0 + f0);
-            bytes = (uint32_t)cnt * 64u;
-        }
-        mbar_arrive_expect_tx(&bars[st], bytes);
-        bulk_g2s(smem + (size_t)st * GS_STAGE_BYTES, src, bytes, &bars[st]);
-    };
-    if (tid == 0)
-        for (int t = 0; t < min(GS_STAGES, n_tiles); ++t) issue(t);
-
-    float acc[29];
-#pragma unroll
-    for (int k = 0; k < 29; k++) acc[k] = 0.f;
-
-    for (int t = 0; t < n_tiles; ++t) {
-        const int st = t % GS_STAGES;
-        mbar_wait(&bars[st], (uint32_t)((t / GS_STAGES) & 1));
-        const float4* s = reinterpret_cast<const float4*>(smem + (size_t)st * GS_STAGE_BYTES);
-        if (t < n_ptile) {   // ---- point block (:563-606) ----
-            const int f0 = (pt_lo + t) * GS_TILE;
-            if (f0 + tid < np) {
-                const float4 a = s[2 * tid], b = s[2 * tid + 1];
-                if (b.z != 0.f) {
-                    const float X = (DT[0] * a.x + DT[1] * a.y + DT[2] * a.z) + DT[3];
-                    const float Y = (DT[4] * a.x + DT[5] * a.y + DT[6] * a.z) + DT[7];
-                    const float Z = (DT[8] * a.x + DT[9] * a.y + DT[10] * a.z) + DT[11];
-                    const float iz = __frcp_rn(Z);
-                    const float dx = (cx + fx * X * iz) - b.x, dy = (cy + fy * Y * iz) - b.y;
-                    const float n = __fsqrt_rn(dx * dx + dy * dy);
-                    const float fgz2 = (Z * Z > homog_th) ? fx * iz * iz : fx / homog_th;
-                    float J[6];
-                    gs_jac(fgz2 * __frcp_rn(fmaxf(homog_th, n)), X, Y, Z, dx, dy, J);
-                    const float r = n * __fsqrt_rn(a.w);
-                    gs_acc(acc, J, r, __frcp_rn(1.f + r * r));
-                }
-            }
-        } else {             // ---- line block (:610-684) ----
-            const int f0 = (lt_lo + (t - n_ptile)) * GS_TILE;
-            if (f0 + tid < nl) {
-                const float4 a = s[4 * tid], b = s[4 * tid + 1], c = s[4 * tid + 2], d = s[4 * tid + 3];
-                if (b.w != 0.f) {
-                    const float sX = (DT[0] * a.x + DT[1] * a.y + DT[2] * a.z) + DT[3];
-                    const float sY = (DT[4] * a.x + DT[5] * a.y + DT[6] * a.z) + DT[7];
-                    const float sZ = (DT[8] * a.x + DT[9] * a.y + DT[10] * a.z) + DT[11];
-                    const float eX = (DT[0] * b.x + DT[1] * b.y + DT[2] * b.z) + DT[3];
-                    const float eY = (DT[4] * b.x + DT[5] * b.y + DT[6] * b.z) + DT[7];
-                    const float eZ = (DT[8] * b.x + DT[9] * b.y + DT[10] * b.z) + DT[11];
-                    const float isz = __frcp_rn(sZ), iez = __frcp_rn(eZ);
-                    const float spu = cx + fx * sX * isz, spv = cy + fy * sY * isz;
-                    const float epu = cx + fx * eX * iez, epv = cy + fy * eY * iez;
-                    const float ds = c.x * spu + c.y * spv + c.z, de = c.x * epu + c.y * epv + c.z;
-                    const float n = __fsqrt_rn(ds * ds + de * de);
-                    const float iden = __frcp_rn(fmaxf(homog_th, n));
-                    float Js[6], Je[6], J[6];
-                    gs_jac(((sZ * sZ > homog_th) ? fx * isz * isz : fx / homog_th) * ds * iden, sX, sY, sZ, c.x, c.y, Js);
-                    gs_jac(((eZ * eZ > homog_th) ? fx * iez * iez : fx / homog_th) * de * iden, eX, eY, eZ, c.x, c.y, Je);
-#pragma unroll
-                    for (int k = 0; k < 6; k++) J[k] = Js[k] + Je[k];
-                    const float r = n * __fsqrt_rn(a.w);
-                    float w = __frcp_rn(1.f + r * r);
-                    w *= gs_overlap(d.x, d.y, d.z, d.w, spu, spv, epu, epv);
-                    gs_acc(acc, J, r, w);
+                        for (int i = 0; i < 12; i++) sDT[st][i] = (float)__ldg(DT + i);
+                    }
+                    const void* src;
+                    uint32_t bytes;
+                    if (t < it.n_ptile) {
+                        const int f0 = (it.pt_lo + t) * GS_PT_TILE;
+                        src = pt + 2 * (size_t)(it.p0 + f0);
+                        bytes = (uint32_t)min(GS_PT_TILE, it.np - f0) * 32u;
+                    } else {
+                        const int f0 = (it.lt_lo + (t - it.n_ptile)) * GS_LS_TILE;
+                        src = ls + 4 * (size_t)(it.l0 + f0);
+                        bytes = (uint32_t)min(GS_LS_TILE, it.nl - f0) * 64u;
+                    }
+                    mbar_arrive_expect_tx(&full[st], bytes);
+                    bulk_g2s(smem + (size_t)st * GS_STAGE_BYTES, src, bytes, &full[st]);
                 }
             }
         }
-        __syncthreads();                                   // stage consumed by every warp
-        if (tid == 0 && t + GS_STAGES < n_tiles) issue(t + GS_STAGES);
+        return;
     }
 
-    // fp64 from here on: transposed warp reduction (31 shuffles), then the 8 warps in a fixed order
-    double v[32];
+    // ---- consumer warps ----
+    GsPose P;
+    P.fx = (float)cam.fx; P.fy = (float)cam.fy; P.cx = (float)cam.cx; P.cy = (float)cam.cy;
+    P.h = homog_th; P.inv_h = 1.f / homog_th; P.fx_h = P.fx / homog_th;
+    uint32_t k = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const GsItem it = gs_item(pt_off, ls_off, item, bpp);
+        if (it.n_tiles > 0) {
+            const uint32_t st0 = k % GS_STAGES;
+            mbar_wait(&full[st0], (k / GS_STAGES) & 1);
 #pragma unroll
-    for (int k = 0; k < 32; k++) v[k] = (k < 29) ? (double)acc[k] : 0.0;
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        const bool up = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < off; i++) {
-            const double mine = up ? v[i + off] : v[i];
-            const double send = up ? v[i] : v[i + off];
-            v[i] = mine + gs_shfl_xor(send, off);
+            for (int i = 0; i < 12; i++) P.r[i] = sDT[st0][i];
         }
-    }
-    red[warp][lane] = v[0];
-    __syncthreads();
-    if (tid < 29) {
-        double s = 0.0;
+        Acc acc;
+        acc.clear();
+
+        for (int t = 0; t < it.n_tiles; ++t, ++k) {
+            const uint32_t st = k % GS_STAGES;
+            mbar_wait(&full[st], (k / GS_STAGES) & 1);
+            const float4* s = reinterpret_cast<const float4*>(smem + (size_t)st * GS_STAGE_BYTES);
+            if (t < it.n_ptile) {
+                const int cnt = min(GS_PT_TILE, it.np - (it.pt_lo + t) * GS_PT_TILE);
 #pragma unroll
-        for (int w = 0; w < GS_WARPS; w++) s += red[w][tid];
-        partial[((size_t)prob * bpp + blk) * (ACC_N + 1) + tid] = s;
+                for (int h = 0; h < GS_PT_TILE / GS_CONSUMERS; ++h) {
+                    const int idx = tid + h * GS_CONSUMERS;
+                    const bool live = idx < cnt;
+                    const int ii = live ? idx : 0;
+                    const float4 a = s[ii], b = s[cnt + ii];
+                    gs_point(P, a, b, live && b.z != 0.f, acc);
+                }
+            } else {
+                const int cnt = min(GS_LS_TILE, it.nl - (it.lt_lo + (t - it.n_ptile)) * GS_LS_TILE);
+                const bool live = tid < cnt;
+                const int ii = live ? tid : 0;
+                const float4 a = s[ii], b = s[cnt + ii], c = s[2 * cnt + ii], d = s[3 * cnt + ii];
+                gs_line(P, a, b, c, d, live && b.w != 0.f, acc);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);        // this warp is done with the stage
+        }
+
+        // transposed warp reduction (31 shuffles, fixed order): lane L ends with the warp's total of accumulator L (<= 1024
+        // features, fp32); everything above a warp — warps, slices, the reduce kernel — is summed in fp64
+        float v[32];
+        acc.unpack(v);
+#pragma unroll
+        for (int i = GS_NACC; i < 32; i++) v[i] = 0.f;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; i++) {
+                const float mine = up ? v[i + off] : v[i];
+                const float send = up ? v[i] : v[i + off];
+                v[i] = mine + __shfl_xor_sync(0xFFFFFFFFu, send, off);
+            }
+        }
+        if (lane < GS_NACC) partial[((size_t)item * GS_CWARPS + warp) * GS_NACC + lane] = (double)v[0];
     }
 }
 
-__global__ void gn_eval_reduce_kernel(const double* __restrict__ partial, int bpp, double* __restrict__ H,
+// Folds the bpp x 8 fp64 partial records of a problem in index order (a per-item fence + counter in the streaming kernel
+// costs more than this second launch: measured 82 vs 70 us per sweep).
+__global__ void gn_eval_reduce_kernel(const double* __restrict__ partial, int n_part, double* __restrict__ H,
                                       double* __restrict__ g, double* __restrict__ e) {
-    __shared__ double s[ACC_N + 1];
-    const int prob = blockIdx.x, tid = threadIdx.x;
-    if (tid <= ACC_N) {
-        double v = 0.0;
-        for (int b = 0; b < bpp; b++) v += partial[((size_t)prob * bpp + b) * (ACC_N + 1) + tid];
-        s[tid] = v;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        int k = 0;
-        for (int i = 0; i < 6; i++)
-            for (int j = i; j < 6; j++) {
-                H[(size_t)prob * 36 + i * 6 + j] = s[k];
-                H[(size_t)prob * 36 + j * 6 + i] = s[k];
-                k++;
-            }
-        for (int i = 0; i < 6; i++) g[(size_t)prob * 6 + i] = s[21 + i];
-        e[prob] = s[27] / s[28];
+    const int prob = blockIdx.x, lane = threadIdx.x;
+    double sum = 0.0;
+    if (lane < GS_NACC)
+        for (int b = 0; b < n_part; b++) sum += partial[((size_t)prob * n_part + b) * GS_NACC + lane];
+    const double cnt = __shfl_sync(0xFFFFFFFFu, sum, 28);
+    if (lane < 21) {            // upper triangle, row-major: lane -> (i, j)
+        int i = 0, k = lane;
+        while (k >= 6 - i) { k -= 6 - i; i++; }
+        const int j = i + k;
+        H[(size_t)prob * 36 + i * 6 + j] = sum;
+        H[(size_t)prob * 36 + j * 6 + i] = sum;
+    } else if (lane < 27) {
+        g[(size_t)prob * 6 + (lane - 21)] = sum;
+    } else if (lane == 27) {
+        e[prob] = sum / cnt;    // :692
     }
 }
 
 }  // namespace
 
-cudaError_t launch_pack_records(const MatchedDev& m, int n_pt, int n_ls, float4* pt, float4* ls, cudaStream_t stream) {
+int gn_stream_partials_per_slice() { return GS_CWARPS; }
+int gn_stream_tiles(int n_pt, int n_ls) {
+    return (n_pt + GS_PT_TILE - 1) / GS_PT_TILE + (n_ls + GS_LS_TILE - 1) / GS_LS_TILE;
+}
+
+cudaError_t launch_pack_records(const MatchedDev& m, int B, int n_pt, int n_ls, float4* pt, float4* ls, cudaStream_t stream) {
     const int n = n_pt > n_ls ? n_pt : n_ls;
-    if (n <= 0) return cudaSuccess;
-    pack_records_kernel<<<(n + 255) / 256, 256, 0, stream>>>(m, n_pt, n_ls, pt, ls);
+    if (n <= 0 || B <= 0) return cudaSuccess;
+    pack_records_kernel<<<(n + 255) / 256, 256, 0, stream>>>(m, B, n_pt, n_ls, pt, ls);
     return cudaGetLastError();
 }
 
 cudaError_t launch_gn_eval_stream(const PlCamera& cam, const PlConfig& cfg, const int32_t* pt_off, const int32_t* ls_off,
                                   const float4* pt, const float4* ls, int B, const double* DT, double* partial, int bpp,
-                                  double* H, double* g, double* e, cudaStream_t stream) {
+                                  int sm_count, double* H, double* g, double* e, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
     const size_t smem = (size_t)GS_STAGES * GS_STAGE_BYTES;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t err = cudaFuncSetAttribute(gn_eval_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return err;
-        configured = true;
+    static int packed = -1;   // PLSTVO_GS_SCALAR=1 selects the scalar-FFMA accumulators (A/B knob; default: packed FFMA2)
+    if (packed < 0) {
+        packed = getenv("PLSTVO_GS_SCALAR") ? 0 : 1;
+        cudaError_t err = cudaFuncSetAttribute(gn_eval_stream_kernel<GsAccPacked>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err == cudaSuccess)
+            err = cudaFuncSetAttribute(gn_eval_stream_kernel<GsAccScalar>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) { packed = -1; return err; }
     }
-    gn_eval_stream_kernel<<<B * bpp, GS_THREADS, smem, stream>>>(cam, (float)cfg.homog_th, pt_off, ls_off, pt, ls, DT,
-                                                                 partial, bpp);
+    const int n_items = B * bpp;
+    const int grid = n_items < 2 * sm_count ? n_items : 2 * sm_count;
+    if (packed)
+        gn_eval_stream_kernel<GsAccPacked><<<grid, GS_THREADS, smem, stream>>>(cam, (float)cfg.homog_th, pt_off, ls_off, pt, ls, DT,
+                                                                               partial, bpp, n_items);
+    else
+        gn_eval_stream_kernel<GsAccScalar><<<grid, GS_THREADS, smem, stream>>>(cam, (float)cfg.homog_th, pt_off, ls_off, pt, ls, DT,
+                                                                               partial, bpp, n_items);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
-    gn_eval_reduce_kernel<<<B, 32, 0, stream>>>(partial, bpp, H, g, e);
+    gn_eval_reduce_kernel<<<B, 32, 0, stream>>>(partial, bpp * GS_CWARPS, H, g, e);
     return cudaGetLastError();
 }
 

@@ -230,6 +230,46 @@ def test_gn_eval_stream_vs_oracle(engine, oracle):
         assert abs(e[p] - er) < 1e-5
 
 
+def _ragged(mb, keep_pt, keep_ls):
+    """First keep_pt[p] points / keep_ls[p] lines of every problem of an equal-sized MatchedBatch."""
+    ip = np.concatenate([np.arange(mb.pt_off[p], mb.pt_off[p] + k) for p, k in enumerate(keep_pt)]).astype(np.int64)
+    il = np.concatenate([np.arange(mb.ls_off[p], mb.ls_off[p] + k) for p, k in enumerate(keep_ls)]).astype(np.int64)
+    return T.MatchedBatch(pt_off=np.concatenate([[0], np.cumsum(keep_pt)]), ls_off=np.concatenate([[0], np.cumsum(keep_ls)]),
+                          pt_P=mb.pt_P[ip], pt_pl_obs=mb.pt_pl_obs[ip], pt_sigma2=mb.pt_sigma2[ip], ls_sP=mb.ls_sP[il],
+                          ls_eP=mb.ls_eP[il], ls_le_obs=mb.ls_le_obs[il], ls_spl=mb.ls_spl[il], ls_epl=mb.ls_epl[il],
+                          ls_sigma2=mb.ls_sigma2[il])
+
+
+def _check_stream(engine, oracle, cam, cfg, mb, Ts, probs):
+    H, g, e, _ = engine.gn_eval_stream(cam, cfg, mb, Ts, iters=1)
+    for p in probs:
+        Hr, gr, er = oracle.optimize_functions(cam, cfg, mb, p, Ts[p])
+        n_feat = (mb.pt_off[p + 1] - mb.pt_off[p]) + (mb.ls_off[p + 1] - mb.ls_off[p])
+        # fp32 level: a residual of ~0.5 px is the difference of two ~1000 px values (ulp 6e-5 px), i.e. 1e-4 .. 1e-3 relative
+        # per feature; it averages out over a list, so short lists get the per-feature bound
+        tol = 2e-4 if n_feat >= 1000 else 5e-3
+        np.testing.assert_allclose(H[p], Hr, rtol=tol, atol=0.1 * tol * np.abs(Hr).max(), err_msg=f"problem {p}")
+        scale = np.sqrt(np.diag(Hr) * er * n_feat)
+        assert (np.abs(g[p] - gr) < tol * scale + 1e-12).all(), (p, g[p], gr)
+        assert abs(e[p] - er) < (1e-5 if n_feat >= 1000 else 1e-4) * max(1.0, er), (p, e[p], er)
+
+
+def test_gn_eval_stream_tiles_and_slices(engine, oracle):
+    """The streamed evaluator's tiling: partial 16 KB tiles (512 points / 256 lines), problems without lines, a single point,
+    large problems cut into several slices, sigma2 != 1, and more work items than persistent CTAs (the ring of stages runs
+    on across item boundaries)."""
+    cfg = T.kitti_config()
+    mb, Ts, cam = synth.make_matched_batch("hd", 8)                       # 8000 + 2000 per problem
+    rng = np.random.default_rng(3)
+    mb.pt_sigma2 = 1.0 / 1.2 ** (2 * rng.integers(0, 8, len(mb.pt_sigma2)))   # pyramid levels 0..7
+    mb.ls_sigma2 = 1.0 / 1.2 ** (2 * rng.integers(0, 2, len(mb.ls_sigma2)))
+    rg = _ragged(mb, [8000, 512, 513, 1, 7999, 1024, 300, 4097], [2000, 0, 256, 1, 257, 1999, 5, 511])
+    _check_stream(engine, oracle, cam, cfg, rg, Ts, range(8))
+    many, Tm, cam2 = synth.make_matched_batch("kitti", 700)               # 700 items on 2 x 148 CTAs
+    many.pt_inlier = (np.arange(len(many.pt_sigma2)) % 11 != 0).astype(np.uint8)
+    _check_stream(engine, oracle, cam2, cfg, many, Tm, [0, 1, 295, 296, 297, 591, 592, 698, 699])
+
+
 def test_onchip_6x6_algebra(engine, oracle):
     """The warp-level 6x6 routines of K2 (lanes-as-columns Householder QR, LU inverse, parallel-order Jacobi)
     against numpy and the oracle's restatements."""

@@ -11,7 +11,7 @@ python bench.py --workload c5 > gpurun_out/bench_c5_${TAG}.json 2>> gpurun_out/b
 tail -c 900 gpurun_out/bench_c5_${TAG}.json
 # launch list of the bench command (short run): per-launch device time, compare SHARES
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu_launches_${TAG}.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu --no-hbm-run > gpurun_out/ncu_launches_${TAG}.log 2>&1
 # full captures: --kernels-only launches K1,K2 over the WHOLE batch three times; take the second occurrence
 ncu --set full --clock-control none --import-source on -k regex:hamming_knn2 -s 1 -c 1 -o gpurun_out/prof_k1_${TAG} -f \
     python bench.py --kernels-only > gpurun_out/ncu_k1_${TAG}.log 2>&1
