@@ -219,7 +219,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from stvo_pl_b200.engine import Engine
+    from stvo_pl_b200.engine import Engine, bind_to_gpu_numa
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -241,6 +241,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    numa = bind_to_gpu_numa(local) if world > 1 else None          # one process per GPU: keep pinned buffers socket-local
     eng = Engine(local)
     cfg = workload_config()
     B = args.pairs
@@ -302,12 +303,20 @@ def run_ours(args):
 
     # ---------------- e2e: host buffers through the C-ABI, H2D + D2H inside the timed region ----------------
     pprev, pcurr = eng.pinned.pin_frames(prev), eng.pinned.pin_frames(curr)
-    h2d_ms = None
-    for _ in range(2):          # PCIe probe: how long the step's inputs alone take to cross (pinned, second try)
-        t0 = time.perf_counter()
-        dbp = eng.upload(cam, cfg, pprev, pcurr)
-        h2d_ms = (time.perf_counter() - t0) * 1e3
-        dbp.free()
+    # PCIe probe: one pinned copy of the step's input byte count (plain torch plumbing), best of 4 — the floor of any e2e step
+    nbytes_in = int(prev.input_bytes("prev") + curr.input_bytes("curr"))
+    psrc = torch.empty(nbytes_in, dtype=torch.uint8).pin_memory()
+    pdst = torch.empty(nbytes_in, dtype=torch.uint8, device=f"cuda:{local}")
+    h2d_ms = 1e9
+    for _ in range(4):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record()
+        pdst.copy_(psrc, non_blocking=True)
+        ev1.record()
+        torch.cuda.synchronize()
+        h2d_ms = min(h2d_ms, ev0.elapsed_time(ev1))
+    del psrc, pdst
     pouts = [eng.pinned_outputs(prev), eng.pinned_outputs(prev)]
     pout = pouts[0]
     # (a) the synchronous call, one batch at a time: returns when the results are in host memory
@@ -352,7 +361,8 @@ def run_ours(args):
                    "parallelism": f"independent pairs sharded over {world} GPU(s), no collective",
                    "l2": f"inputs larger than L2: {(h2d + kt['n_tiles'] * 0) / 1e6:.0f} MB of inputs + "
                          f"{B * 156000 / 1e6:.0f} MB of tile partials per pass vs 126 MB L2",
-                   "overlap": 1.0, "outlier_frac": 0.10, "solved_ok": good, "e2e_equals_resident": bool(same)},
+                   "overlap": 1.0, "outlier_frac": 0.10, "solved_ok": good, "e2e_equals_resident": bool(same),
+                   "numa_bound": numa},
         "clocks": clk.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_s / args.steps * 1e3,
@@ -360,7 +370,8 @@ def run_ours(args):
                 "sync_value": world * B * args.steps / sync_s, "sync_ms_per_step": sync_s / args.steps * 1e3,
                 "sync_mode": "plstvo_track_batch, one blocking call per step",
                 "h2d_only_ms_per_step": h2d_ms, "h2d_only_gbs": h2d / (h2d_ms * 1e-3) / 1e9,
-                "note": "the pipelined figure is bounded by the host->device copy of the step's inputs (h2d_only_ms_per_step)"},
+                "note": "h2d_only_*: one pinned cudaMemcpy of the step's input bytes alone (the PCIe floor of a step); the "
+                        "pipelined figure hides it behind the previous batch's kernels"},
         "gpu_launches": int(launches),
         "roofline": roofline,
     }

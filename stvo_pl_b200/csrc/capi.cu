@@ -435,11 +435,14 @@ int ws_download_range(PlContext* ctx, Workspace& ws, int p0, int p1, PlPoseResul
 // Pipeline chunking of the host-buffer entry point: small first chunks (the GPU starts working after a few MB have
 // crossed PCIe), then chunks of about two thirds of the SM count in pairs (K2 runs one pair per SM; the rest of the
 // chip keeps running the next chunk's distance tiles on the other compute stream).
-std::vector<int> chunk_schedule(int B, int sm_count) {
+// With batches in flight behind one another (plstvo_track_batch_async) the previous batch's kernels already hide the copy:
+// no ramp, the resident pass's chunking (two launches per pass) is used instead.
+std::vector<int> chunk_schedule(int B, int sm_count, bool pipelined) {
     static const int forced = getenv("PLSTVO_E2E_CHUNK") ? atoi(getenv("PLSTVO_E2E_CHUNK")) : 0;
     std::vector<int> bounds{0};
-    if (forced > 0) {
-        for (int p = forced; p < B; p += forced) bounds.push_back(p);
+    if (forced > 0 || pipelined) {
+        const int step = forced > 0 ? forced : std::max(1, std::max(std::min(B, sm_count), (B + 1) / 2));
+        for (int p = step; p < B; p += step) bounds.push_back(p);
         bounds.push_back(B);
         return bounds;
     }
@@ -1016,12 +1019,12 @@ int plstvo_optimize_pose(PlContext* ctx, const PlCamera* cam, const PlConfig* cf
 static int track_enqueue(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfig* cfg,
                          const PlFrameBatch* prev, const PlFrameBatch* curr, const PlPrior* priors,
                          PlPoseResult* results, int32_t* m12_pt, int32_t* m12_ls, uint8_t* inlier_pt,
-                         uint8_t* inlier_ls) {
+                         uint8_t* inlier_ls, bool pipelined) {
     const int B = prev->B;
     int rc = ws_prepare(ctx, ws, cam, cfg, prev, curr, true, priors != nullptr);
     if (rc) return rc;
     const bool have_level = prev->ls_level != nullptr;
-    const std::vector<int> bounds = chunk_schedule(B, ctx->sm_count);
+    const std::vector<int> bounds = chunk_schedule(B, ctx->sm_count, pipelined);
     for (int k = 0; k + 1 < (int)bounds.size(); ++k) {
         const int p0 = bounds[k], p1 = bounds[k + 1];
         rc = ws_upload_range(ctx, ws, prev, curr, priors, p0, p1, true, ctx->s_h2d);
@@ -1051,7 +1054,7 @@ int plstvo_track_batch(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg,
     int rc = validate_frames(ctx, prev, curr, true);
     if (rc) return rc;
     if (prev->B == 0) return 0;
-    rc = track_enqueue(ctx, ctx->ws, cam, cfg, prev, curr, priors, results, m12_pt, m12_ls, inlier_pt, inlier_ls);
+    rc = track_enqueue(ctx, ctx->ws, cam, cfg, prev, curr, priors, results, m12_pt, m12_ls, inlier_pt, inlier_ls, false);
     if (rc) return rc;
     CK(ctx, cudaStreamSynchronize(ctx->s_d2h));   // every chunk's D2H waited for its compute, which waited for its H2D
     return 0;
@@ -1073,7 +1076,7 @@ int plstvo_track_batch_async(PlContext* ctx, const PlCamera* cam, const PlConfig
     if (!ctx->slot_done[slot]) CK(ctx, cudaEventCreateWithFlags(&ctx->slot_done[slot], cudaEventDisableTiming));
     if (prev->B > 0) {
         rc = track_enqueue(ctx, ctx->ws_async[slot], cam, cfg, prev, curr, priors, results, m12_pt, m12_ls, inlier_pt,
-                           inlier_ls);
+                           inlier_ls, getenv("PLSTVO_ASYNC_RAMP") == nullptr);
         if (rc) return rc;
     }
     CK(ctx, cudaEventRecord(ctx->slot_done[slot], ctx->s_d2h));
