@@ -8,6 +8,10 @@ python bench.py --steps 30 --warmup 5 > gpurun_out/bench_${TAG}.json 2> gpurun_o
 tail -c 600 gpurun_out/bench_${TAG}.json
 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref_${TAG}.json 2>> gpurun_out/bench_${TAG}.err
 python bench.py --workload c5 > gpurun_out/bench_c5_${TAG}.json 2>> gpurun_out/bench_${TAG}.err
+for W in c1 c3; do
+  python bench.py --workload $W --steps 20 --warmup 3 --no-hbm-run > gpurun_out/bench_${W}_${TAG}.json 2>> gpurun_out/bench_${TAG}.err
+  python bench.py --workload $W --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_${W}_${TAG}.json 2>> gpurun_out/bench_${TAG}.err
+done
 tail -c 900 gpurun_out/bench_c5_${TAG}.json
 # launch list of the bench command (short run): per-launch device time, compare SHARES
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv \

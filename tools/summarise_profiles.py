@@ -89,16 +89,21 @@ def main():
             if k in m:
                 lines.append(f"| `{k}` | {m[k]} |")
         lines.append("")
-        if kname == "k1":
-            def num(key):
-                v, u = m[key].split()[0], m[key].split()[1]
-                return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+        def num(key):
+            v, u = m[key].split()[0], m[key].split()[1]
+            return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+        if kname in ("k1", "gn") and "dram__bytes_read.sum" in m:
             traffic = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
-            json.dump({"dram_bytes_per_launch": traffic, "dram_bytes_read": num("dram__bytes_read.sum"),
-                       "dram_bytes_write": num("dram__bytes_write.sum"), "capture": f"profiles/{tag}_ncu_summary.md",
-                       "launch": m.get("launch__grid_size", "")},
-                      open(os.path.join(PROF, "k1_traffic.json"), "w"), indent=1)
-    for name in (f"bench_{tag}.json", f"bench_ref_{tag}.json", f"bench_c5_{tag}.json"):
+            rec = {"dram_bytes_per_launch": traffic, "dram_bytes_read": num("dram__bytes_read.sum"),
+                   "dram_bytes_write": num("dram__bytes_write.sum"), "capture": f"profiles/{tag}_ncu_summary.md",
+                   "launch": m.get("launch__grid_size", ""), "gpu_time": m.get("gpu__time_duration.sum", "")}
+            if kname == "gn":
+                rec["problems"] = 1024          # bench.py --workload c5 default
+                rec["algorithmic_bytes_per_launch"] = 1024 * (8000 * 32 + 2000 * 64)
+            json.dump(rec, open(os.path.join(PROF, f"{kname}_traffic.json"), "w"), indent=1)
+    names = [f"bench_{tag}.json", f"bench_ref_{tag}.json", f"bench_c5_{tag}.json"] + \
+            [f"bench_{w}_{tag}.json" for w in ("c1", "c3")] + [f"bench_ref_{w}_{tag}.json" for w in ("c1", "c3")]
+    for name in names:
         p = os.path.join(OUT, name)
         if os.path.exists(p):
             txt = open(p).read().strip()
