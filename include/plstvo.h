@@ -221,6 +221,29 @@ int plstvo_stereo_lift_lines(PlContext* ctx, const PlCamera* cam, const PlStereo
                              double* ls_angle, double* ls_sigma2, int32_t* ls_level, uint8_t* ldesc_out, int32_t* src_idx,
                              int32_t* counts);
 
+/* ---- StereoFrame::matchStereoPoints / matchStereoLines (src/stereoFrame.cpp:120-173, :309-398) in one device pass:
+ * grid cells from the raw key points / key lines (:129-139, :318-337: x * inv_width truncated, inv_width = grid_cols / image
+ * width), matchGrid, and the 3-D lifting, with the match list handed from kernel to kernel in HBM.  Inputs and outputs are
+ * those of plstvo_stereo_lift_*; desc_r = right descriptors; m12 (optional) = matchGrid's list per left feature. */
+typedef struct PlStereoMatchConfig {   /* include/stereoFrame.h:51-52, src/config.cpp:51, :60, :63, :91 */
+    int32_t grid_rows, grid_cols;      /* GRID_ROWS 48, GRID_COLS 64 */
+    int32_t matching_s_ws;             /* Config::matchingSWs(): cells to the left of the query, same row */
+    int32_t best_lr_matches;
+    double  min_ratio_12_p, line_sim_th;
+} PlStereoMatchConfig;
+void plstvo_default_stereo_match_config(PlStereoMatchConfig* c);
+int plstvo_match_stereo_points(PlContext* ctx, const PlCamera* cam, const PlStereoMatchConfig* mcfg, const PlStereoConfig* scfg,
+                               int B, const int32_t* l_off, const float* kp_l, const int32_t* octave_l, const uint8_t* desc_l,
+                               const int32_t* r_off, const float* kp_r, const uint8_t* desc_r, int32_t* m12, double* pt_pl,
+                               double* pt_disp, double* pt_P, double* pt_sigma2, int32_t* pt_level, uint8_t* pdesc_out,
+                               int32_t* src_idx, int32_t* counts);
+int plstvo_match_stereo_lines(PlContext* ctx, const PlCamera* cam, const PlStereoMatchConfig* mcfg, const PlStereoConfig* scfg,
+                              int B, const int32_t* l_off, const float* seg_l, const float* angle_l, const int32_t* octave_l,
+                              const uint8_t* desc_l, const int32_t* r_off, const float* seg_r, const uint8_t* desc_r,
+                              int32_t* m12, double* ls_spl, double* ls_epl, double* ls_sdisp, double* ls_edisp, double* ls_sP,
+                              double* ls_eP, double* ls_le, double* ls_angle, double* ls_sigma2, int32_t* ls_level,
+                              uint8_t* ldesc_out, int32_t* src_idx, int32_t* counts);
+
 /* ---- include/stereoFrameHandler.h surface ----------------------------------------------------- */
 /* StereoFrameHandler::f2fTracking (src/stereoFrameHandler.cpp:106-180) for B independent
  * (prev, curr) pairs: descriptor matching for points and lines; m12_* hold problem-local indices

@@ -903,6 +903,168 @@ int plstvo_stereo_lift_lines(PlContext* ctx, const PlCamera* cam, const PlStereo
     return (int)total;
 }
 
+// ---- matchStereoPoints / matchStereoLines in one device pass (src/stereoFrame.cpp:120-173, :309-398) ----------------
+void plstvo_default_stereo_match_config(PlStereoMatchConfig* c) {   // include/stereoFrame.h:51-52, src/config.cpp:51, :60, :63, :91
+    if (!c) return;
+    c->grid_rows = 48; c->grid_cols = 64; c->matching_s_ws = 10; c->best_lr_matches = 1;
+    c->min_ratio_12_p = 0.9; c->line_sim_th = 0.75;
+}
+
+namespace {
+struct StereoOut {   // host destinations of the lifted records (points use the first seven)
+    int32_t* m12; double *a_pl, *a_disp, *a_P, *a_s2; int32_t* level; uint8_t* desc; int32_t *src, *counts;
+    double *epl, *edisp, *eP, *le, *angle;   // lines only
+};
+
+int match_stereo_common(PlContext* ctx, bool lines, const PlCamera* cam, const PlStereoMatchConfig* mc, const PlStereoConfig* sc,
+                        int B, const int32_t* l_off, const float* xy_l, const float* angle_l, const int32_t* octave_l,
+                        const uint8_t* desc_l, const int32_t* r_off, const float* xy_r, const uint8_t* desc_r,
+                        const StereoOut& out) {
+    if (!ctx) return PLSTVO_E_INVALID;
+    if (!cam || !mc || !sc || B < 0) return fail(ctx, PLSTVO_E_INVALID, "null camera / config or negative batch size");
+    const int rows = mc->grid_rows, cols = mc->grid_cols;
+    if (rows <= 0 || cols <= 0 || rows * cols > 8192 || cam->width <= 0 || cam->height <= 0)
+        return fail(ctx, PLSTVO_E_INVALID, "bad grid or image size");
+    if (B == 0) return 0;
+    int rc = lift_check_offsets(ctx, B, l_off, r_off);
+    if (rc) return rc;
+    const size_t N1 = l_off[B], N2 = r_off[B];
+    if (N1 && (!xy_l || !octave_l || !desc_l || (lines && !angle_l))) return fail(ctx, PLSTVO_E_INVALID, "null input array");
+    if (N2 && (!xy_r || !desc_r)) return fail(ctx, PLSTVO_E_INVALID, "null input array");
+    CK(ctx, cudaSetDevice(ctx->device));
+    constexpr int CAP = 128;
+    const int cw = lines ? 4 : 2;                 // floats per feature (segment / key point) and ints per query cell record
+    const size_t per_train_cells = lines ? (size_t)std::max(rows, cols) + 2 : 1;
+    LiftArena a;
+    // raw inputs
+    const size_t o_loff = a.take((size_t)(B + 1) * 4), o_roff = a.take((size_t)(B + 1) * 4), o_xyl = a.take(N1 * cw * 4);
+    const size_t o_xyr = a.take(N2 * cw * 4), o_ang = a.take(lines ? N1 * 4 : 0), o_oct = a.take(N1 * 4);
+    const size_t o_d1 = a.take(N1 * 32), o_d2 = a.take(N2 * 32);
+    // matchGrid
+    const size_t o_qcell = a.take(N1 * cw * 4), o_tcell = a.take(lines ? 0 : N2 * 8), o_tline = a.take(lines ? N2 * 32 : 0);
+    const size_t o_tdir = a.take(lines ? N2 * 16 : 0), o_m12 = a.take(N1 * 4), o_gcnt = a.take((size_t)B * 4);
+    const size_t o_items = a.take(N2 * per_train_cells * 4), o_qpairs = a.take(N1 * CAP * 8), o_qcount = a.take(N1 * 4);
+    const size_t o_tcount = a.take(N2 * 4), o_tstart = a.take((N2 + B) * 4), o_tslots = a.take(N1 * CAP * 4);
+    const size_t o_seen = a.take(N1 * CAP), o_m21 = a.take(N2 * 4), o_prob = a.take((size_t)B * sizeof(GridProblem));
+    // lifted records
+    const size_t o_pl = a.take(N1 * 16), o_disp = a.take(N1 * 8), o_P = a.take(N1 * 24), o_s2 = a.take(N1 * 8);
+    const size_t o_lvl = a.take(N1 * 4), o_dout = a.take(N1 * 32), o_src = a.take(N1 * 4), o_cnt = a.take((size_t)B * 4);
+    const size_t o_epl = a.take(lines ? N1 * 16 : 0), o_edisp = a.take(lines ? N1 * 8 : 0), o_eP = a.take(lines ? N1 * 24 : 0);
+    const size_t o_le = a.take(lines ? N1 * 24 : 0), o_angd = a.take(lines ? N1 * 8 : 0);
+    static DevBuf arena;
+    CK(ctx, arena.ensure(a.off));
+    uint8_t* base = arena.as<uint8_t>();
+    auto I = [&](size_t o) { return reinterpret_cast<int32_t*>(base + o); };
+    auto D = [&](size_t o) { return reinterpret_cast<double*>(base + o); };
+    auto F = [&](size_t o) { return reinterpret_cast<float*>(base + o); };
+    std::vector<GridProblem> probs((size_t)B);
+    for (int p = 0; p < B; ++p) {
+        GridProblem& g = probs[p];
+        const size_t qa = l_off[p], tb = r_off[p];
+        g.n1 = l_off[p + 1] - l_off[p];
+        g.n2 = r_off[p + 1] - r_off[p];
+        g.q_cell = I(o_qcell) + qa * cw;
+        g.d1 = base + o_d1 + qa * 32;
+        g.t_cell = lines ? nullptr : I(o_tcell) + tb * 2;
+        g.t_line = lines ? D(o_tline) + tb * 4 : nullptr;
+        g.t_dir = lines ? D(o_tdir) + tb * 2 : nullptr;
+        g.d2 = base + o_d2 + tb * 32;
+        g.m12 = I(o_m12) + qa;
+        g.count = I(o_gcnt) + p;
+        g.grid_items = I(o_items) + tb * per_train_cells;
+        g.q_pairs = reinterpret_cast<int2*>(base + o_qpairs) + qa * CAP;
+        g.q_count = I(o_qcount) + qa;
+        g.t_count = I(o_tcount) + tb;
+        g.t_start = I(o_tstart) + tb + p;
+        g.t_slots = I(o_tslots) + qa * CAP;
+        g.seen = base + o_seen + qa * CAP;
+        g.m21 = I(o_m21) + tb;
+    }
+    cudaStream_t s = ctx->s_main;
+    auto up = [&](size_t o, const void* src, size_t bytes) -> cudaError_t {
+        return (src && bytes) ? cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, s) : cudaSuccess;
+    };
+    auto down = [&](void* dst, size_t o, size_t bytes) -> cudaError_t {
+        return (dst && bytes) ? cudaMemcpyAsync(dst, base + o, bytes, cudaMemcpyDeviceToHost, s) : cudaSuccess;
+    };
+    CK(ctx, up(o_loff, l_off, (size_t)(B + 1) * 4));
+    CK(ctx, up(o_roff, r_off, (size_t)(B + 1) * 4));
+    CK(ctx, up(o_xyl, xy_l, N1 * cw * 4));
+    CK(ctx, up(o_xyr, xy_r, N2 * cw * 4));
+    if (lines) CK(ctx, up(o_ang, angle_l, N1 * 4));
+    CK(ctx, up(o_oct, octave_l, N1 * 4));
+    CK(ctx, up(o_d1, desc_l, N1 * 32));
+    CK(ctx, up(o_d2, desc_r, N2 * 32));
+    CK(ctx, up(o_prob, probs.data(), (size_t)B * sizeof(GridProblem)));
+    // 1. grid coordinates (:47-48: inv_width = GRID_COLS / image width, inv_height = GRID_ROWS / image height)
+    const double inv_w = cols / static_cast<double>(cam->width), inv_h = rows / static_cast<double>(cam->height);
+    if (lines)
+        CK(ctx, launch_stereo_cells_lines((int)N1, (int)N2, inv_w, inv_h, F(o_xyl), F(o_xyr), I(o_qcell), D(o_tline), D(o_tdir), s));
+    else
+        CK(ctx, launch_stereo_cells_points((int)N1, (int)N2, inv_w, inv_h, F(o_xyl), F(o_xyr), I(o_qcell), I(o_tcell), s));
+    // 2. matchGrid with the stereo window (:141-143, :340-342: matching_s_ws cells to the left, same row)
+    GridParams prm{rows, cols, CAP, mc->best_lr_matches ? 1 : 0, PlGridWindow{mc->matching_s_ws, 0, 0, 0}, mc->min_ratio_12_p,
+                   mc->line_sim_th};
+    CK(ctx, launch_match_grid(reinterpret_cast<GridProblem*>(base + o_prob), B, prm, lines, s));
+    // 3. lifting, reading the match list where matchGrid left it
+    if (lines)
+        CK(ctx, launch_lift_lines(*cam, *sc, B, I(o_loff), F(o_xyl), F(o_ang), I(o_oct), base + o_d1, I(o_roff), F(o_xyr), I(o_m12),
+                                  D(o_pl), D(o_epl), D(o_disp), D(o_edisp), D(o_P), D(o_eP), D(o_le), D(o_angd), D(o_s2), I(o_lvl),
+                                  base + o_dout, I(o_src), I(o_cnt), s));
+    else
+        CK(ctx, launch_lift_points(*cam, *sc, B, I(o_loff), F(o_xyl), I(o_oct), base + o_d1, I(o_roff), F(o_xyr), I(o_m12), D(o_pl),
+                                   D(o_disp), D(o_P), D(o_s2), I(o_lvl), base + o_dout, I(o_src), I(o_cnt), s));
+    ctx->launches += 3;
+    std::vector<int32_t> gcnt((size_t)B), cnt((size_t)B);
+    CK(ctx, down(out.m12, o_m12, N1 * 4));
+    CK(ctx, down(out.a_pl, o_pl, N1 * 16));
+    CK(ctx, down(out.a_disp, o_disp, N1 * 8));
+    CK(ctx, down(out.a_P, o_P, N1 * 24));
+    CK(ctx, down(out.a_s2, o_s2, N1 * 8));
+    CK(ctx, down(out.level, o_lvl, N1 * 4));
+    CK(ctx, down(out.desc, o_dout, N1 * 32));
+    CK(ctx, down(out.src, o_src, N1 * 4));
+    if (lines) {
+        CK(ctx, down(out.epl, o_epl, N1 * 16));
+        CK(ctx, down(out.edisp, o_edisp, N1 * 8));
+        CK(ctx, down(out.eP, o_eP, N1 * 24));
+        CK(ctx, down(out.le, o_le, N1 * 24));
+        CK(ctx, down(out.angle, o_angd, N1 * 8));
+    }
+    CK(ctx, down(gcnt.data(), o_gcnt, (size_t)B * 4));
+    CK(ctx, down(cnt.data(), o_cnt, (size_t)B * 4));
+    CK(ctx, cudaStreamSynchronize(s));
+    long total = 0;
+    for (int p = 0; p < B; ++p) {
+        if (gcnt[p] < 0) return fail(ctx, gcnt[p], "matchGrid: more than 128 candidates in one query window");
+        if (out.counts) out.counts[p] = cnt[p];
+        total += cnt[p];
+    }
+    return (int)total;
+}
+}  // namespace
+
+int plstvo_match_stereo_points(PlContext* ctx, const PlCamera* cam, const PlStereoMatchConfig* mcfg, const PlStereoConfig* scfg,
+                               int B, const int32_t* l_off, const float* kp_l, const int32_t* octave_l, const uint8_t* desc_l,
+                               const int32_t* r_off, const float* kp_r, const uint8_t* desc_r, int32_t* m12, double* pt_pl,
+                               double* pt_disp, double* pt_P, double* pt_sigma2, int32_t* pt_level, uint8_t* pdesc_out,
+                               int32_t* src_idx, int32_t* counts) {
+    const StereoOut out{m12, pt_pl, pt_disp, pt_P, pt_sigma2, pt_level, pdesc_out, src_idx, counts,
+                        nullptr, nullptr, nullptr, nullptr, nullptr};
+    return match_stereo_common(ctx, false, cam, mcfg, scfg, B, l_off, kp_l, nullptr, octave_l, desc_l, r_off, kp_r, desc_r, out);
+}
+
+int plstvo_match_stereo_lines(PlContext* ctx, const PlCamera* cam, const PlStereoMatchConfig* mcfg, const PlStereoConfig* scfg,
+                              int B, const int32_t* l_off, const float* seg_l, const float* angle_l, const int32_t* octave_l,
+                              const uint8_t* desc_l, const int32_t* r_off, const float* seg_r, const uint8_t* desc_r,
+                              int32_t* m12, double* ls_spl, double* ls_epl, double* ls_sdisp, double* ls_edisp, double* ls_sP,
+                              double* ls_eP, double* ls_le, double* ls_angle, double* ls_sigma2, int32_t* ls_level,
+                              uint8_t* ldesc_out, int32_t* src_idx, int32_t* counts) {
+    const StereoOut out{m12, ls_spl, ls_sdisp, ls_sP, ls_sigma2, ls_level, ldesc_out, src_idx, counts,
+                        ls_epl, ls_edisp, ls_eP, ls_le, ls_angle};
+    return match_stereo_common(ctx, true, cam, mcfg, scfg, B, l_off, seg_l, angle_l, octave_l, desc_l, r_off, seg_r, desc_r, out);
+}
+
 // ---- stereoFrameHandler.h surface ------------------------------------------------------------------------
 int plstvo_f2f_tracking(PlContext* ctx, const PlConfig* cfg, const PlFrameBatch* prev, const PlFrameBatch* curr,
                         int32_t* m12_pt, int32_t* m12_ls, int32_t* n_matched) {

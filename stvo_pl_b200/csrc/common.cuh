@@ -144,6 +144,11 @@ struct GridParams {
 };
 size_t match_grid_smem_bytes(int rows, int cols);
 cudaError_t launch_match_grid(const GridProblem* problems, int B, const GridParams& prm, bool lines, cudaStream_t stream);
+// lift.cu: grid coordinates of raw key points / key lines (the loops in front of matchGrid, src/stereoFrame.cpp:129-139, :318-337)
+cudaError_t launch_stereo_cells_points(int n_l, int n_r, double inv_w, double inv_h, const float* kp_l, const float* kp_r,
+                                       int32_t* q_cell, int32_t* t_cell, cudaStream_t s);
+cudaError_t launch_stereo_cells_lines(int n_l, int n_r, double inv_w, double inv_h, const float* seg_l, const float* seg_r,
+                                      int32_t* q_line, double* t_line, double* t_dir, cudaStream_t s);
 // lift.cu: stereo matches -> PointFeature / LineFeature records (src/stereoFrame.cpp:149-172, :348-397)
 cudaError_t launch_lift_points(const PlCamera& cam, const PlStereoConfig& sc, int B, const int32_t* l_off, const float* kp_l,
                                const int32_t* oct_l, const uint8_t* desc_l, const int32_t* r_off, const float* kp_r,

@@ -176,7 +176,60 @@ lift_lines_kernel(PlCamera cam, PlStereoConfig sc, const int32_t* __restrict__ l
     if (tid == 0) counts[f] = s_base;
 }
 
+// grid coordinates of the raw stereo features (src/stereoFrame.cpp:129-139 points; :318-337 lines): the caller-side loops
+// that feed matchGrid.  float coordinate x double inverse cell size, truncated toward zero for the integer cells.
+__global__ void stereo_cells_points_kernel(int n_l, int n_r, double inv_w, double inv_h, const float* __restrict__ kp_l,
+                                           const float* __restrict__ kp_r, int32_t* __restrict__ q_cell,
+                                           int32_t* __restrict__ t_cell) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_l) {
+        q_cell[2 * i] = (int)((double)kp_l[2 * i] * inv_w);
+        q_cell[2 * i + 1] = (int)((double)kp_l[2 * i + 1] * inv_h);
+    }
+    if (i < n_r) {
+        t_cell[2 * i] = (int)((double)kp_r[2 * i] * inv_w);
+        t_cell[2 * i + 1] = (int)((double)kp_r[2 * i + 1] * inv_h);
+    }
+}
+
+__global__ void stereo_cells_lines_kernel(int n_l, int n_r, double inv_w, double inv_h, const float* __restrict__ seg_l,
+                                          const float* __restrict__ seg_r, int32_t* __restrict__ q_line,
+                                          double* __restrict__ t_line, double* __restrict__ t_dir) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_l) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) q_line[4 * i + k] = (int)((double)seg_l[4 * i + k] * ((k & 1) ? inv_h : inv_w));
+    }
+    if (i < n_r) {
+        const float sx = seg_r[4 * i], sy = seg_r[4 * i + 1], ex = seg_r[4 * i + 2], ey = seg_r[4 * i + 3];
+        t_line[4 * i] = (double)sx * inv_w;
+        t_line[4 * i + 1] = (double)sy * inv_h;
+        t_line[4 * i + 2] = (double)ex * inv_w;
+        t_line[4 * i + 3] = (double)ey * inv_h;
+        const double vx = (double)__fsub_rn(ex, sx) * inv_w, vy = (double)__fsub_rn(ey, sy) * inv_h;   // float - float (:332)
+        const double mag = sqrt(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));                     // include/matching.h:43-48
+        t_dir[2 * i] = vx / mag;
+        t_dir[2 * i + 1] = vy / mag;
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_stereo_cells_points(int n_l, int n_r, double inv_w, double inv_h, const float* kp_l, const float* kp_r,
+                                       int32_t* q_cell, int32_t* t_cell, cudaStream_t s) {
+    const int n = n_l > n_r ? n_l : n_r;
+    if (n <= 0) return cudaSuccess;
+    stereo_cells_points_kernel<<<(n + 255) / 256, 256, 0, s>>>(n_l, n_r, inv_w, inv_h, kp_l, kp_r, q_cell, t_cell);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stereo_cells_lines(int n_l, int n_r, double inv_w, double inv_h, const float* seg_l, const float* seg_r,
+                                      int32_t* q_line, double* t_line, double* t_dir, cudaStream_t s) {
+    const int n = n_l > n_r ? n_l : n_r;
+    if (n <= 0) return cudaSuccess;
+    stereo_cells_lines_kernel<<<(n + 255) / 256, 256, 0, s>>>(n_l, n_r, inv_w, inv_h, seg_l, seg_r, q_line, t_line, t_dir);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_lift_points(const PlCamera& cam, const PlStereoConfig& sc, int B, const int32_t* l_off, const float* kp_l,
                                const int32_t* oct_l, const uint8_t* desc_l, const int32_t* r_off, const float* kp_r,

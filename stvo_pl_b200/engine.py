@@ -51,6 +51,12 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
                                                 i32p, dp, dp, dp, dp, i32p, u8p, i32p, i32p]),
         "plstvo_stereo_lift_lines": (C.c_int, [vp, cam, C.POINTER(T.PlStereoConfig), C.c_int, i32p, fp, fp, i32p, u8p, i32p,
                                                fp, i32p, dp, dp, dp, dp, dp, dp, dp, dp, dp, i32p, u8p, i32p, i32p]),
+        "plstvo_default_stereo_match_config": (None, [C.POINTER(T.PlStereoMatchConfig)]),
+        "plstvo_match_stereo_points": (C.c_int, [vp, cam, C.POINTER(T.PlStereoMatchConfig), C.POINTER(T.PlStereoConfig), C.c_int,
+                                                 i32p, fp, i32p, u8p, i32p, fp, u8p, i32p, dp, dp, dp, dp, i32p, u8p, i32p, i32p]),
+        "plstvo_match_stereo_lines": (C.c_int, [vp, cam, C.POINTER(T.PlStereoMatchConfig), C.POINTER(T.PlStereoConfig), C.c_int,
+                                                i32p, fp, fp, i32p, u8p, i32p, fp, u8p, i32p, dp, dp, dp, dp, dp, dp, dp, dp, dp,
+                                                i32p, u8p, i32p, i32p]),
         "plstvo_f2f_tracking": (C.c_int, [vp, cfg, fb, fb, i32p, i32p, i32p]),
         "plstvo_optimize_pose": (C.c_int, [vp, cam, cfg, mb, vp, vp, u8p, u8p]),
         "plstvo_track_batch": (C.c_int, [vp, cam, cfg, fb, fb, vp, vp, i32p, i32p, u8p, u8p]),
@@ -80,7 +86,7 @@ EXPORTED_SYMBOLS = [
     "plstvo_version", "plstvo_create", "plstvo_destroy", "plstvo_last_error", "plstvo_default_config",
     "plstvo_kitti_config", "plstvo_match_nnr", "plstvo_match", "plstvo_match_batch", "plstvo_match_grid_points",
     "plstvo_match_grid_lines", "plstvo_default_stereo_config", "plstvo_stereo_lift_points", "plstvo_stereo_lift_lines",
-    "plstvo_f2f_tracking",
+    "plstvo_default_stereo_match_config", "plstvo_match_stereo_points", "plstvo_match_stereo_lines", "plstvo_f2f_tracking",
     "plstvo_optimize_pose", "plstvo_track_batch", "plstvo_track_batch_async", "plstvo_wait", "plstvo_batch_upload", "plstvo_batch_run",
     "plstvo_batch_run_timed", "plstvo_batch_download", "plstvo_batch_free", "plstvo_synchronize",
     "plstvo_host_alloc", "plstvo_host_free", "plstvo_launch_count", "plstvo_batch_kernel_times",
@@ -312,6 +318,48 @@ class Engine:
             _p(out["le"], T.c_double_p), _p(out["angle"], T.c_double_p), _p(out["sigma2"], T.c_double_p),
             _p(out["level"], T.c_int32_p), _p(out["desc"], T.c_uint8_p), _p(out["src_idx"], T.c_int32_p),
             _p(out["counts"], T.c_int32_p)))
+        return total, out
+
+    def match_stereo_points(self, cam, mcfg: T.PlStereoMatchConfig, scfg: T.PlStereoConfig, l_off, kp_l, octave_l, desc_l,
+                            r_off, kp_r, desc_r):
+        """StereoFrame::matchStereoPoints (src/stereoFrame.cpp:120-173): grid cells, matchGrid and the lifting in one device
+        pass.  Returns (total, out) like stereo_lift_points, plus out["m12"]."""
+        l_off, r_off = np.ascontiguousarray(l_off, np.int32), np.ascontiguousarray(r_off, np.int32)
+        kp_l, kp_r = np.ascontiguousarray(kp_l, np.float32).reshape(-1, 2), np.ascontiguousarray(kp_r, np.float32).reshape(-1, 2)
+        octave_l = np.ascontiguousarray(octave_l, np.int32)
+        desc_l, desc_r = np.ascontiguousarray(desc_l, np.uint8).reshape(-1, 32), np.ascontiguousarray(desc_r, np.uint8).reshape(-1, 32)
+        B, n = len(l_off) - 1, len(kp_l)
+        out = dict(m12=np.full(n, -1, np.int32), pl=np.zeros((n, 2)), disp=np.zeros(n), P=np.zeros((n, 3)), sigma2=np.zeros(n),
+                   level=np.zeros(n, np.int32), desc=np.zeros((n, 32), np.uint8), src_idx=np.full(n, -1, np.int32),
+                   counts=np.zeros(B, np.int32))
+        total = self._ck(self.lib.plstvo_match_stereo_points(
+            self.ctx, C.byref(cam), C.byref(mcfg), C.byref(scfg), B, _p(l_off, T.c_int32_p), _p(kp_l, T.c_float_p),
+            _p(octave_l, T.c_int32_p), _p(desc_l, T.c_uint8_p), _p(r_off, T.c_int32_p), _p(kp_r, T.c_float_p),
+            _p(desc_r, T.c_uint8_p), _p(out["m12"], T.c_int32_p), _p(out["pl"], T.c_double_p), _p(out["disp"], T.c_double_p),
+            _p(out["P"], T.c_double_p), _p(out["sigma2"], T.c_double_p), _p(out["level"], T.c_int32_p),
+            _p(out["desc"], T.c_uint8_p), _p(out["src_idx"], T.c_int32_p), _p(out["counts"], T.c_int32_p)))
+        return total, out
+
+    def match_stereo_lines(self, cam, mcfg: T.PlStereoMatchConfig, scfg: T.PlStereoConfig, l_off, seg_l, angle_l, octave_l,
+                           desc_l, r_off, seg_r, desc_r):
+        """StereoFrame::matchStereoLines (src/stereoFrame.cpp:309-398) in one device pass."""
+        l_off, r_off = np.ascontiguousarray(l_off, np.int32), np.ascontiguousarray(r_off, np.int32)
+        seg_l, seg_r = np.ascontiguousarray(seg_l, np.float32).reshape(-1, 4), np.ascontiguousarray(seg_r, np.float32).reshape(-1, 4)
+        angle_l, octave_l = np.ascontiguousarray(angle_l, np.float32), np.ascontiguousarray(octave_l, np.int32)
+        desc_l, desc_r = np.ascontiguousarray(desc_l, np.uint8).reshape(-1, 32), np.ascontiguousarray(desc_r, np.uint8).reshape(-1, 32)
+        B, n = len(l_off) - 1, len(seg_l)
+        out = dict(m12=np.full(n, -1, np.int32), spl=np.zeros((n, 2)), epl=np.zeros((n, 2)), sdisp=np.zeros(n), edisp=np.zeros(n),
+                   sP=np.zeros((n, 3)), eP=np.zeros((n, 3)), le=np.zeros((n, 3)), angle=np.zeros(n), sigma2=np.zeros(n),
+                   level=np.zeros(n, np.int32), desc=np.zeros((n, 32), np.uint8), src_idx=np.full(n, -1, np.int32),
+                   counts=np.zeros(B, np.int32))
+        total = self._ck(self.lib.plstvo_match_stereo_lines(
+            self.ctx, C.byref(cam), C.byref(mcfg), C.byref(scfg), B, _p(l_off, T.c_int32_p), _p(seg_l, T.c_float_p),
+            _p(angle_l, T.c_float_p), _p(octave_l, T.c_int32_p), _p(desc_l, T.c_uint8_p), _p(r_off, T.c_int32_p),
+            _p(seg_r, T.c_float_p), _p(desc_r, T.c_uint8_p), _p(out["m12"], T.c_int32_p), _p(out["spl"], T.c_double_p),
+            _p(out["epl"], T.c_double_p), _p(out["sdisp"], T.c_double_p), _p(out["edisp"], T.c_double_p),
+            _p(out["sP"], T.c_double_p), _p(out["eP"], T.c_double_p), _p(out["le"], T.c_double_p), _p(out["angle"], T.c_double_p),
+            _p(out["sigma2"], T.c_double_p), _p(out["level"], T.c_int32_p), _p(out["desc"], T.c_uint8_p),
+            _p(out["src_idx"], T.c_int32_p), _p(out["counts"], T.c_int32_p)))
         return total, out
 
     # ---- stereoFrameHandler.h surface ----

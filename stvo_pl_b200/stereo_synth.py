@@ -117,3 +117,76 @@ def make_lift_lines(n_l, n_r, seed, W=1241, H=376):
     octave = rng.integers(0, 3, n_l).astype(np.int32)
     desc = rng.integers(0, 256, (n_l, 32), dtype=np.uint8)
     return seg_l, angle, octave, desc, seg_r, m12
+
+
+# ---- raw stereo frames for matchStereoPoints / matchStereoLines (src/stereoFrame.cpp:120-173, :309-398) ----
+def make_stereo_frame_points(n_l, n_r, W=1241, H=376, seed=0, overlap=0.8, bitflip=0.08, max_disp=120.0):
+    """Left / right key points (float32 pixels), octaves and descriptors of one rectified stereo frame: true matches sit on
+    (nearly) the same row with a positive disparity, the rest is clutter.  Returns kp_l, octave_l, d1, kp_r, d2."""
+    rng = np.random.default_rng(seed)
+    kp_l = np.stack([rng.uniform(0, W, n_l), rng.uniform(0, H, n_l)], 1)
+    kp_r = np.stack([rng.uniform(0, W, n_r), rng.uniform(0, H, n_r)], 1)
+    d1 = rng.integers(0, 256, (n_l, 32), dtype=np.uint8)
+    d2 = rng.integers(0, 256, (n_r, 32), dtype=np.uint8)
+    k = int(min(n_l, n_r) * overlap)
+    src, dst = rng.permutation(n_l)[:k], rng.permutation(n_r)[:k]
+    disp = rng.uniform(0.2, max_disp, k)
+    kp_r[dst, 0] = np.clip(kp_l[src, 0] - disp, 0, W - 1e-3)
+    dy = rng.normal(0, 0.4, k)
+    dy[: k // 3] = 0.0                               # exactly rectified rows (the only survivors with max_dist_epip = 0)
+    kp_r[dst, 1] = np.clip(kp_l[src, 1] + dy, 0, H - 1e-3)
+    flips = (rng.random((k, 32, 8)) < bitflip)
+    d2[dst] = d1[src] ^ np.packbits(flips, axis=2).reshape(k, 32)
+    kp_l, kp_r = kp_l.astype(np.float32), kp_r.astype(np.float32)
+    kp_r[dst[: k // 3], 1] = kp_l[src[: k // 3], 1]
+    return kp_l, rng.integers(0, 8, n_l).astype(np.int32), d1, kp_r, d2
+
+
+def make_stereo_frame_lines(n_l, n_r, W=1241, H=376, seed=0, overlap=0.8, bitflip=0.08, max_disp=120.0):
+    """Left / right key lines (float32 start / end pixels), KeyLine angle / octave and descriptors of one stereo frame.
+    Returns seg_l, angle_l, octave_l, d1, seg_r, d2."""
+    rng = np.random.default_rng(seed)
+
+    def segs(n):
+        s = np.stack([rng.uniform(0, W, n), rng.uniform(0, H, n)], 1)
+        ang, ln = rng.uniform(0, np.pi, n), rng.uniform(5, 200, n)
+        e = s + np.stack([ln * np.cos(ang), ln * np.sin(ang)], 1)
+        return s, np.clip(e, 0, [W - 1e-3, H - 1e-3])
+    sl, el = segs(n_l)
+    sr, er = segs(n_r)
+    d1 = rng.integers(0, 256, (n_l, 32), dtype=np.uint8)
+    d2 = rng.integers(0, 256, (n_r, 32), dtype=np.uint8)
+    k = int(min(n_l, n_r) * overlap)
+    src, dst = rng.permutation(n_l)[:k], rng.permutation(n_r)[:k]
+    ds = rng.uniform(0.2, max_disp, k)
+    de = ds * rng.uniform(0.6, 1.4, k)
+    t0, t1 = rng.uniform(-0.2, 0.2, k), rng.uniform(0.8, 1.2, k)
+    d = el[src] - sl[src]
+    sr[dst] = np.clip(sl[src] + t0[:, None] * d - np.stack([ds, np.zeros(k)], 1), 0, [W - 1e-3, H - 1e-3])
+    er[dst] = np.clip(sl[src] + t1[:, None] * d - np.stack([de, np.zeros(k)], 1), 0, [W - 1e-3, H - 1e-3])
+    flips = (rng.random((k, 32, 8)) < bitflip)
+    d2[dst] = d1[src] ^ np.packbits(flips, axis=2).reshape(k, 32)
+    seg_l = np.concatenate([sl, el], 1).astype(np.float32)
+    seg_r = np.concatenate([sr, er], 1).astype(np.float32)
+    return (seg_l, rng.uniform(-np.pi, np.pi, n_l).astype(np.float32), rng.integers(0, 3, n_l).astype(np.int32), d1, seg_r, d2)
+
+
+def stereo_cells_points(kp_l, kp_r, W, H):
+    """The grid coordinates the caller of matchGrid forms (src/stereoFrame.cpp:47-48, :129-139): float pixel x double inverse
+    cell size, truncated."""
+    inv_w, inv_h = GRID_COLS / float(W), GRID_ROWS / float(H)
+    cell = lambda kp: np.stack([(kp[:, 0].astype(np.float64) * inv_w).astype(np.int32),
+                                (kp[:, 1].astype(np.float64) * inv_h).astype(np.int32)], 1)
+    return cell(np.asarray(kp_l, np.float32).reshape(-1, 2)), cell(np.asarray(kp_r, np.float32).reshape(-1, 2))
+
+
+def stereo_cells_lines(seg_l, seg_r, W, H):
+    """q_line, t_line, t_dir as src/stereoFrame.cpp:318-337 forms them."""
+    inv = np.array([GRID_COLS / float(W), GRID_ROWS / float(H)] * 2)
+    seg_l, seg_r = np.asarray(seg_l, np.float32).reshape(-1, 4), np.asarray(seg_r, np.float32).reshape(-1, 4)
+    q_line = (seg_l.astype(np.float64) * inv).astype(np.int32)
+    t_line = seg_r.astype(np.float64) * inv
+    v = (seg_r[:, 2:] - seg_r[:, :2]).astype(np.float64) * inv[:2]          # float - float, then x double (:332)
+    with np.errstate(all="ignore"):
+        t_dir = v / np.sqrt(v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1])[:, None]
+    return q_line, t_line, t_dir

@@ -68,6 +68,16 @@ def default_stereo_config() -> "PlStereoConfig":
     return PlStereoConfig(1.0, 1.0, 0.7, 0.1, 0.75, 1.2, 1.2)   # src/config.cpp:58-69, :96, :106
 
 
+class PlStereoMatchConfig(C.Structure):
+    """Grid / matcher values of matchStereoPoints / matchStereoLines (include/stereoFrame.h:51-52, src/config.cpp:51, :60, :63, :91)."""
+    _fields_ = [("grid_rows", C.c_int32), ("grid_cols", C.c_int32), ("matching_s_ws", C.c_int32), ("best_lr_matches", C.c_int32),
+                ("min_ratio_12_p", C.c_double), ("line_sim_th", C.c_double)]
+
+
+def default_stereo_match_config() -> "PlStereoMatchConfig":
+    return PlStereoMatchConfig(48, 64, 10, 1, 0.9, 0.75)
+
+
 GRID_ROWS, GRID_COLS = 48, 64     # include/stereoFrame.h:51-52
 
 

@@ -1,0 +1,174 @@
+"""StereoFrame::matchStereoPoints / matchStereoLines in one device pass (plstvo_match_stereo_*; src/stereoFrame.cpp:120-173,
+:309-398): grid cells from raw key points / key lines -> matchGrid -> 3-D lifting.  Held bitwise against the composition of the
+oracle's matchGrid and lifting restatements on the grid coordinates the reference's caller forms (stereo_synth.stereo_cells_*)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from stvo_pl_b200 import stereo_synth as SS, types as T
+
+KEYS_PT = ("pl", "disp", "P", "sigma2", "level", "desc", "src_idx")
+KEYS_LS = ("spl", "epl", "sdisp", "edisp", "sP", "eP", "le", "angle", "sigma2", "level", "desc", "src_idx")
+
+
+def _same(a, b, key):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (key, a.shape, b.shape)
+    if a.dtype.kind == "f" and a.size:
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), key
+    else:
+        assert np.array_equal(a, b), key
+
+
+def _window(mc):
+    return T.PlGridWindow(mc.matching_s_ws, 0, 0, 0)
+
+
+def oracle_points(oracle, cam, mc, sc, frame):
+    kp_l, octave, d1, kp_r, d2 = frame
+    q_cell, t_cell = SS.stereo_cells_points(kp_l, kp_r, cam.width, cam.height)
+    _, m12 = oracle.match_grid_points(q_cell, d1, t_cell, d2, _window(mc), mc.min_ratio_12_p, bool(mc.best_lr_matches),
+                                      mc.grid_rows, mc.grid_cols)
+    k, rec = oracle.stereo_lift_points(cam, sc, kp_l, octave, d1, kp_r, m12)
+    return m12, k, rec
+
+
+def oracle_lines(oracle, cam, mc, sc, frame):
+    seg_l, angle, octave, d1, seg_r, d2 = frame
+    q_line, t_line, t_dir = SS.stereo_cells_lines(seg_l, seg_r, cam.width, cam.height)
+    _, m12 = oracle.match_grid_lines(q_line, d1, t_line, t_dir, d2, _window(mc), mc.min_ratio_12_p, mc.line_sim_th,
+                                     bool(mc.best_lr_matches), mc.grid_rows, mc.grid_cols)
+    k, rec = oracle.stereo_lift_lines(cam, sc, seg_l, angle, octave, d1, seg_r, m12)
+    return m12, k, rec
+
+
+def _cat(frames, idx_l, idx_r):
+    l_off = np.concatenate([[0], np.cumsum([len(f[idx_l]) for f in frames])]).astype(np.int32)
+    r_off = np.concatenate([[0], np.cumsum([len(f[idx_r]) for f in frames])]).astype(np.int32)
+    return l_off, r_off, [np.concatenate([f[j] for f in frames]) for j in range(len(frames[0]))]
+
+
+def test_default_stereo_match_config_matches_library():
+    from stvo_pl_b200.engine import load_library
+    lib = load_library()
+    c = T.PlStereoMatchConfig()
+    lib.plstvo_default_stereo_match_config(C.byref(c))
+    d = T.default_stereo_match_config()
+    for name, _ in T.PlStereoMatchConfig._fields_:
+        assert getattr(c, name) == getattr(d, name), name
+
+
+def test_oracle_composition_finds_the_planted_matches(oracle):
+    """Sanity of the generator + composition on the CPU: most planted stereo pairs survive matchGrid and the lifting."""
+    cam, mc, sc = T.kitti_camera(), T.default_stereo_match_config(), T.default_stereo_config()
+    m12, k, rec = oracle_points(oracle, cam, mc, sc, SS.make_stereo_frame_points(900, 850, seed=3))
+    assert (m12 >= 0).sum() > 300 and 200 < k <= (m12 >= 0).sum()
+    assert np.all(rec["disp"] >= sc.min_disp) and np.all(rec["P"][:, 2] > 0)
+    m12, k, rec = oracle_lines(oracle, cam, mc, sc, SS.make_stereo_frame_lines(300, 280, seed=4))
+    assert (m12 >= 0).sum() > 60 and 10 < k <= (m12 >= 0).sum()
+    np.testing.assert_allclose(np.hypot(rec["le"][:, 0], rec["le"][:, 1]), 1.0, rtol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sizes,kitti", [([(900, 850)], False), ([(0, 0), (40, 60), (1, 1), (0, 7), (1500, 1400), (7, 0), (600, 610)], False),
+                                          ([(2000, 2000)] * 3, True)])
+def test_gpu_match_stereo_points(engine, oracle, sizes, kitti):
+    cam, mc, sc = T.kitti_camera(), T.default_stereo_match_config(), T.default_stereo_config()
+    if kitti:
+        mc.min_ratio_12_p, sc.max_dist_epip = 0.75, 0.0              # config_kitti.yaml:17, :19
+    frames = [SS.make_stereo_frame_points(a, b, seed=50 + i) for i, (a, b) in enumerate(sizes)]
+    l_off, r_off, (kp_l, octave, d1, kp_r, d2) = _cat(frames, 0, 3)
+    total, out = engine.match_stereo_points(cam, mc, sc, l_off, kp_l, octave, d1, r_off, kp_r, d2)
+    tot_ref = 0
+    for p, f in enumerate(frames):
+        m12, k, rec = oracle_points(oracle, cam, mc, sc, f)
+        a = l_off[p]
+        np.testing.assert_array_equal(out["m12"][a:a + len(m12)], m12)
+        assert out["counts"][p] == k
+        for key in KEYS_PT:
+            _same(out[key][a:a + k], rec[key], key)
+        tot_ref += k
+    assert total == tot_ref and (not kitti or total > 0)
+    # the same through the two separate entry points
+    q_cell, t_cell = SS.stereo_cells_points(kp_l, kp_r, cam.width, cam.height)
+    _, m12b, _ = engine.match_grid_points(l_off, q_cell, d1, r_off, t_cell, d2, _window(mc), mc.min_ratio_12_p,
+                                          bool(mc.best_lr_matches))
+    np.testing.assert_array_equal(m12b, out["m12"])
+    total2, out2 = engine.stereo_lift_points(cam, sc, l_off, kp_l, octave, d1, r_off, kp_r, m12b)
+    assert total2 == total
+    np.testing.assert_array_equal(out2["counts"], out["counts"])
+    for p in range(len(frames)):                                     # slots beyond counts[p] are unspecified
+        a, k = l_off[p], int(out["counts"][p])
+        for key in KEYS_PT:
+            _same(out2[key][a:a + k], out[key][a:a + k], key)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sizes", [[(300, 280)], [(0, 0), (30, 45), (1, 1), (0, 4), (520, 500), (5, 0), (257, 256)], [(500, 500)] * 3])
+def test_gpu_match_stereo_lines(engine, oracle, sizes):
+    cam, mc, sc = T.kitti_camera(), T.default_stereo_match_config(), T.default_stereo_config()
+    frames = [SS.make_stereo_frame_lines(a, b, seed=70 + i) for i, (a, b) in enumerate(sizes)]
+    l_off, r_off, (seg_l, angle, octave, d1, seg_r, d2) = _cat(frames, 0, 4)
+    total, out = engine.match_stereo_lines(cam, mc, sc, l_off, seg_l, angle, octave, d1, r_off, seg_r, d2)
+    tot_ref = 0
+    for p, f in enumerate(frames):
+        m12, k, rec = oracle_lines(oracle, cam, mc, sc, f)
+        a = l_off[p]
+        np.testing.assert_array_equal(out["m12"][a:a + len(m12)], m12)
+        assert out["counts"][p] == k
+        for key in KEYS_LS:
+            _same(out[key][a:a + k], rec[key], key)
+        tot_ref += k
+    assert total == tot_ref
+    q_line, t_line, t_dir = SS.stereo_cells_lines(seg_l, seg_r, cam.width, cam.height)
+    _, m12b, _ = engine.match_grid_lines(l_off, q_line, d1, r_off, t_line, t_dir, d2, _window(mc), mc.min_ratio_12_p,
+                                         mc.line_sim_th, bool(mc.best_lr_matches))
+    np.testing.assert_array_equal(m12b, out["m12"])
+
+
+@pytest.mark.gpu
+def test_gpu_match_stereo_feeds_the_tracker(engine, oracle):
+    """The lifted records are the tracker's PlFrameBatch fields: two stereo frames of the same scene go through
+    matchStereoPoints and then plstvo_track_batch, and the pose agrees with the oracle run on the same records."""
+    cam, mc, sc, cfg = T.kitti_camera(), T.default_stereo_match_config(), T.default_stereo_config(), T.kitti_config()
+    cfg.has_lines = 0
+    frames = []
+    for seed in (11, 12):
+        kp_l, octave, d1, kp_r, d2 = SS.make_stereo_frame_points(1200, 1200, seed=11, overlap=0.9)   # same scene twice ...
+        if seed == 12:                                                # ... second frame: everything moved 1.5 px to the right
+            kp_l, kp_r = kp_l + np.float32([1.5, 0]), kp_r + np.float32([1.5, 0])
+        off = np.array([0, len(kp_l)], np.int32)
+        tot, out = engine.match_stereo_points(cam, mc, sc, off, kp_l, octave, d1, off, kp_r, d2)
+        k = int(out["counts"][0])
+        assert k > 300
+        z = np.zeros((0, 3))
+        frames.append(T.FrameBatch(pt_off=[0, k], ls_off=[0, 0], pdesc=out["desc"][:k], ldesc=np.zeros((0, 32), np.uint8),
+                                   pt_P=out["P"][:k], pt_pl=out["pl"][:k], pt_sigma2=out["sigma2"][:k], ls_sP=z, ls_eP=z, ls_le=z,
+                                   ls_spl=np.zeros((0, 2)), ls_epl=np.zeros((0, 2)), ls_sigma2=np.zeros(0),
+                                   ls_level=np.zeros(0, np.int32)))
+    got = engine.track_batch(cam, cfg, frames[0], frames[1])
+    ref = oracle.track_batch(cam, cfg, frames[0], frames[1])
+    np.testing.assert_array_equal(got["m12_pt"], ref["m12_pt"])
+    assert got["results"]["status"][0] == ref["results"]["status"][0]
+    np.testing.assert_allclose(got["results"]["DT"][0], ref["results"]["DT"][0], atol=1e-8)
+    assert got["results"]["n_matched_pt"][0] > 250
+
+
+@pytest.mark.gpu
+def test_gpu_match_stereo_errors(engine):
+    cam, mc, sc = T.kitti_camera(), T.default_stereo_match_config(), T.default_stereo_config()
+    kp_l, octave, d1, kp_r, d2 = SS.make_stereo_frame_points(50, 50, seed=1)
+    off = np.array([0, 50], np.int32)
+    bad = T.default_stereo_match_config()
+    bad.grid_rows = 0
+    with pytest.raises(RuntimeError):
+        engine.match_stereo_points(cam, bad, sc, off, kp_l, octave, d1, off, kp_r, d2)
+    with pytest.raises(RuntimeError):                              # offsets must start at 0
+        engine.match_stereo_points(cam, mc, sc, np.array([1, 50], np.int32), kp_l, octave, d1, off, kp_r, d2)
+    # more than 128 right key points in one query window: reported, as by plstvo_match_grid_points
+    kp_r2 = np.tile(np.float32([[100.0, 100.0]]), (200, 1))
+    kp_l2 = np.tile(np.float32([[110.0, 100.0]]), (10, 1))
+    with pytest.raises(RuntimeError):
+        engine.match_stereo_points(cam, mc, sc, np.array([0, 10], np.int32), kp_l2, np.zeros(10, np.int32), d1[:10],
+                                   np.array([0, 200], np.int32), kp_r2, np.repeat(d2[:1], 200, 0))

@@ -27,4 +27,9 @@ kp_l, octave, desc, kp_r, m12 = SS.make_lift_points(700, 650, seed=3)
 eng.stereo_lift_points(cam, sc, [0, 700], kp_l, octave, desc, [0, 650], kp_r, m12)
 seg_l, angle, octave, desc, seg_r, m12 = SS.make_lift_lines(300, 280, seed=4)
 eng.stereo_lift_lines(cam, sc, [0, 300], seg_l, angle, octave, desc, [0, 280], seg_r, m12)
+mc = T.default_stereo_match_config()
+kp_l, octave, d1, kp_r, d2 = SS.make_stereo_frame_points(600, 580, seed=5)
+eng.match_stereo_points(cam, mc, sc, [0, 600], kp_l, octave, d1, [0, 580], kp_r, d2)
+seg_l, angle, octave, d1, seg_r, d2 = SS.make_stereo_frame_lines(250, 240, seed=6)
+eng.match_stereo_lines(cam, mc, sc, [0, 250], seg_l, angle, octave, d1, [0, 240], seg_r, d2)
 print("sanitized run ok", int(out["results"]["good"].sum()))
