@@ -434,6 +434,187 @@ def run_c5(args):
     return 0
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# --workload stereo: the widened rows measured to the same bar: StereoFrame::matchStereoPoints +
+# matchStereoLines (grid cells -> matchGrid -> 3-D lifting) for a batch of KITTI-shape frames, host buffers in and out.
+def stereo_frames(B, first=0):
+    from stvo_pl_b200 import stereo_synth as SS
+    pts = [SS.make_stereo_frame_points(2000, 2000, seed=9000 + first + i) for i in range(B)]
+    lns = [SS.make_stereo_frame_lines(500, 500, seed=19000 + first + i) for i in range(B)]
+    return pts, lns
+
+
+def stereo_cpu_rate(pts, lns, threads):
+    """The oracle (orc_stereo_batch: cells as the reference's caller forms them, matchGrid, lifting), one frame per host thread."""
+    from oracle.oracle import Oracle
+    orc = Oracle(native=True)
+    cam, mc, sc = T.kitti_camera(), T.default_stereo_match_config(), T.default_stereo_config()
+    B = len(pts)
+    pl_off = np.concatenate([[0], np.cumsum([len(f[0]) for f in pts])]).astype(np.int32)
+    pr_off = np.concatenate([[0], np.cumsum([len(f[3]) for f in pts])]).astype(np.int32)
+    ll_off = np.concatenate([[0], np.cumsum([len(f[0]) for f in lns])]).astype(np.int32)
+    lr_off = np.concatenate([[0], np.cumsum([len(f[4]) for f in lns])]).astype(np.int32)
+    P = [np.concatenate([f[j] for f in pts]) for j in range(5)]
+    L = [np.concatenate([f[j] for f in lns]) for j in range(6)]
+    args = (cam, mc, sc, pl_off, P[0], P[1], P[2], pr_off, P[3], P[4], ll_off, L[0], L[1], L[2], L[3], lr_off, L[4], L[5])
+    orc.stereo_batch(*args, threads=threads)                    # warm-up
+    best, n = 1e9, 0
+    for _ in range(3):
+        t0 = time.perf_counter()
+        n = int(orc.stereo_batch(*args, threads=threads).sum())
+        best = min(best, time.perf_counter() - t0)
+    return B / best, best, n
+
+
+def run_stereo(args):
+    import torch
+    from stvo_pl_b200.engine import Engine
+    metric, unit = "stereo frames matched + lifted/sec (KITTI-shape, 2k+2k pts, 500+500 lines)", "frames/s"
+    threads = host_threads()
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0
+        pts, lns = stereo_frames(max(256, 8 * threads))
+        rate, dt, _ = stereo_cpu_rate(pts, lns, threads)
+        line = {"impl": "reference", "metric": metric, "value": rate, "unit": unit, "n_gpus": args.gpus, "steps": 1, "warmup": 1,
+                "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64",
+                "data": "synthetic", "config": {"workload": "stereo: matchStereoPoints + matchStereoLines", "frames_per_step": len(pts)},
+                "cpu_baseline": {"value": rate, "unit": unit, "cores": threads, "kind": "port", "cpu": cpu_model(),
+                                 "sample": f"{len(pts)} frames, one frame per thread (oracle composition)"},
+                "e2e": {"value": rate, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+    eng = Engine(int(os.environ.get("LOCAL_RANK", "0")))
+    B = args.pairs
+    pts, lns = stereo_frames(B)
+    cam, mc, sc = T.kitti_camera(), T.default_stereo_match_config(), T.default_stereo_config()
+    off_p = np.arange(B + 1, dtype=np.int32) * 2000
+    off_l = np.arange(B + 1, dtype=np.int32) * 500
+    P = [eng.pinned.copy(np.concatenate([f[j] for f in pts])) for j in range(5)]      # pinned host buffers in and out
+    L = [eng.pinned.copy(np.concatenate([f[j] for f in lns])) for j in range(6)]
+    out_p, out_l = eng.stereo_outputs(2000 * B, B, lines=False, pinned=True), eng.stereo_outputs(500 * B, B, lines=True, pinned=True)
+    launches0 = eng.launches
+
+    def step():
+        tp, _ = eng.match_stereo_points(cam, mc, sc, off_p, P[0], P[1], P[2], off_p, P[3], P[4], out=out_p)
+        tl, _ = eng.match_stereo_lines(cam, mc, sc, off_l, L[0], L[1], L[2], L[3], off_l, L[4], L[5], out=out_l)
+        return tp, tl
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    with ClockSampler(0) as clk:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            tp, tl = step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    launches = eng.launches - launches0
+    h2d = sum(a.nbytes for a in P) + sum(a.nbytes for a in L)
+    d2h = 2000 * B * (4 + 16 + 8 + 24 + 8 + 4 + 32 + 4) + 500 * B * (4 + 16 * 2 + 8 * 2 + 24 * 3 + 8 * 2 + 4 + 32 + 4)
+    line = {"metric": metric, "value": B * args.steps / dt, "unit": unit, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/f64", "data": "synthetic",
+            "config": {"workload": "stereo: matchStereoPoints + matchStereoLines (grid cells -> matchGrid -> lifting), host buffers in / out",
+                       "frames_per_step": B, "lifted_points_per_step": int(tp), "lifted_lines_per_step": int(tl),
+                       "note": "value IS the end-to-end figure here: every step uploads the raw key points / key lines and "
+                               "descriptors and reads the records back (pinned host arrays)"},
+            "clocks": clk.summary(), "gpu_launches": int(launches),
+            "e2e": {"value": B * args.steps / dt, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "roofline": None}
+    if not args.no_cpu:
+        sp, sl = stereo_frames(max(256, 8 * threads), first=B)
+        rate, secs, _ = stereo_cpu_rate(sp, sl, threads)
+        line["cpu_baseline"] = {"value": rate, "unit": unit, "cores": threads, "kind": "port", "cpu": cpu_model(),
+                                "sample": f"{len(sp)} frames of the same workload, one frame per thread, {secs:.2f} s wall"}
+    print(json.dumps(line), flush=True)
+    eng.close()
+    return 0
+
+
+# --workload stereo_track: raw stereo features of (prev, curr) frame pairs in, poses out (plstvo_track_stereo_batch): the whole
+# of insertStereoPair() + optimizePose() behind feature detection, the lifted records never leaving HBM.
+def run_stereo_track(args):
+    import torch
+    from stvo_pl_b200 import stereo_synth as SS
+    from stvo_pl_b200.engine import Engine
+    metric, unit = "stereo pose solves/sec from raw stereo features (KITTI-shape, 2k key points + 500 key lines per image)", "solves/s"
+    threads = host_threads()
+    mc, sc, cfg = T.default_stereo_match_config(), T.default_stereo_config(), T.kitti_config()
+
+    def cpu_rate(n_pairs):
+        """CPU arm: the oracle's stereo step for both frames (C, one frame per thread) + its f2fTracking / optimizePose on
+        records of the same sizes (C, one pair per thread); the two legs are timed one after the other and their times added."""
+        from oracle.oracle import Oracle
+        orc = Oracle(native=True)
+        prev, curr, _, cam = SS.make_stereo_pairs(n_pairs, n_pt=1740, n_ls=500, seed=777)
+        t_st = 0.0
+        for d in (prev, curr):
+            a = (cam, mc, sc, d["pl_off"], d["kp_l"], d["poct_l"], d["pdesc_l"], d["pr_off"], d["kp_r"], d["pdesc_r"], d["ll_off"],
+                 d["seg_l"], d["angle_l"], d["loct_l"], d["ldesc_l"], d["lr_off"], d["seg_r"], d["ldesc_r"])
+            orc.stereo_batch(*a, threads=threads)
+            t0 = time.perf_counter()
+            orc.stereo_batch(*a, threads=threads)
+            t_st += time.perf_counter() - t0
+        pv, cv, _, cam2 = synth.make_batch("kitti", n_pairs, n_pt=1740, n_ls=500, overlap=1.0)
+        orc.track_batch(cam2, cfg, pv, cv, threads=threads)
+        t0 = time.perf_counter()
+        orc.track_batch(cam2, cfg, pv, cv, threads=threads)
+        t_tr = time.perf_counter() - t0
+        return n_pairs / (t_st + t_tr), t_st, t_tr
+
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0
+        n = max(64, 2 * threads)
+        rate, t_st, t_tr = cpu_rate(n)
+        line = {"impl": "reference", "metric": metric, "value": rate, "unit": unit, "n_gpus": args.gpus, "steps": 1, "warmup": 1,
+                "ms_per_step": (t_st + t_tr) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8/f64", "data": "synthetic", "config": {"workload": "stereo_track", "pairs_per_step": n},
+                "cpu_baseline": {"value": rate, "unit": unit, "cores": threads, "kind": "port", "cpu": cpu_model(),
+                                 "sample": f"{n} pairs: stereo step {t_st:.3f} s + tracking {t_tr:.3f} s, all host threads"},
+                "e2e": {"value": rate, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+    eng = Engine(int(os.environ.get("LOCAL_RANK", "0")))
+    B = args.pairs
+    prev, curr, Tgt, cam = SS.make_stereo_pairs(B, n_pt=1740, n_ls=500, seed=4242)     # 1740 + 15 % clutter = 2001 key points
+    pin = lambda d: {k: eng.pinned.copy(np.ascontiguousarray(v, T.STEREO_FEATURE_DTYPES[k])) for k, v in d.items()}
+    prev, curr = pin(prev), pin(curr)
+    res = eng.pinned.empty((B,), T.POSE_RESULT_DTYPE)
+    for _ in range(max(args.warmup, 3)):
+        eng.track_stereo_batch(cam, cfg, mc, sc, prev, curr, results=res)
+    torch.cuda.synchronize()
+    launches0 = eng.launches
+    with ClockSampler(0) as clk:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            _, n_st = eng.track_stereo_batch(cam, cfg, mc, sc, prev, curr, results=res)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    launches = eng.launches - launches0
+    h2d = sum(v.nbytes for v in prev.values()) + sum(v.nbytes for v in curr.values())
+    err = [float(np.linalg.norm(res["DT_opt"][p][:3, 3] - Tgt[p][:3, 3])) for p in range(B)]
+    line = {"metric": metric, "value": B * args.steps / dt, "unit": unit, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64",
+            "data": "synthetic",
+            "config": {"workload": "stereo_track: matchStereoPoints + matchStereoLines of both frames -> f2fTracking -> optimizePose, "
+                                   "raw key points / key lines and descriptors in (pinned host buffers), poses out",
+                       "pairs_per_step": B, "mean_lifted": [float(x) for x in n_st.mean(0)], "solved_ok": int(res["good"].sum()),
+                       "median_translation_error_m": float(np.median(err)),
+                       "note": "value IS the end-to-end figure: every step uploads both frames' raw features and reads the poses back"},
+            "clocks": clk.summary(), "gpu_launches": int(launches),
+            "e2e": {"value": B * args.steps / dt, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(res.nbytes + 16 * B)},
+            "roofline": None}
+    if not args.no_cpu:
+        n = max(64, 2 * threads)
+        rate, t_st, t_tr = cpu_rate(n)
+        line["cpu_baseline"] = {"value": rate, "unit": unit, "cores": threads, "kind": "port", "cpu": cpu_model(),
+                                "sample": f"{n} pairs: stereo step {t_st:.3f} s + tracking {t_tr:.3f} s, all host threads"}
+    print(json.dumps(line), flush=True)
+    eng.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -443,7 +624,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=512, help="frame pairs per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-hbm-run", action="store_true", help="skip the C5 streamed-evaluation sweeps appended at N=1")
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c5"],
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c5", "stereo", "stereo_track"],
                     help="c2: the headline solves/s bench (default); c1 / c3: the same pipeline on the points-only and the "
                          "EuRoC-shape robust configurations; c5: HBM-roofline run of the streamed GN evaluation "
                          "(1920x1080, 8000 points + 2000 lines, >= 1024 problems resident, 20 evaluations)")
@@ -453,6 +634,10 @@ def main():
     global ACTIVE
     if args.workload in WORKLOADS:
         ACTIVE = args.workload
+    if args.workload == "stereo":
+        return run_stereo(args)
+    if args.workload == "stereo_track":
+        return run_stereo_track(args)
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "c5":

@@ -244,6 +244,27 @@ int plstvo_match_stereo_lines(PlContext* ctx, const PlCamera* cam, const PlStere
                               double* ls_eP, double* ls_le, double* ls_angle, double* ls_sigma2, int32_t* ls_level,
                               uint8_t* ldesc_out, int32_t* src_idx, int32_t* counts);
 
+/* ---- raw stereo features in, pose out: the matching half of StereoFrame::extractStereoFeatures (matchStereoPoints +
+ * matchStereoLines, src/stereoFrame.cpp:120-173, :309-398) for the previous and the current frame of B independent pairs, then
+ * f2fTracking + optimizePose (src/stereoFrameHandler.cpp:106-180, :307-392) on the lifted records, which never leave HBM.
+ * The only host hop in between is the per-frame survivor counts (the tile plan of the descriptor matcher needs them). */
+typedef struct PlStereoFeatures {      /* what detectStereoFeatures leaves for B frames (src/stereoFrame.cpp:78-118, :184-307) */
+    int32_t        B;
+    const int32_t* pl_off;  const int32_t* pr_off;    /* [B+1] left / right key points */
+    const float*   kp_l;    const float*   kp_r;      /* [n][2] cv::KeyPoint::pt */
+    const int32_t* poct_l;                            /* [n_l] cv::KeyPoint::octave */
+    const uint8_t* pdesc_l; const uint8_t* pdesc_r;   /* [n][32] */
+    const int32_t* ll_off;  const int32_t* lr_off;    /* [B+1] left / right key lines */
+    const float*   seg_l;   const float*   seg_r;     /* [m][4] start / end point */
+    const float*   angle_l;                           /* [m_l] KeyLine::angle */
+    const int32_t* loct_l;                            /* [m_l] KeyLine::octave */
+    const uint8_t* ldesc_l; const uint8_t* ldesc_r;   /* [m][32] */
+} PlStereoFeatures;
+/* n_stereo (optional): [B][4] = stereo_pt.size(), stereo_ls.size() of the previous and of the current frame. */
+int plstvo_track_stereo_batch(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlStereoMatchConfig* mcfg,
+                              const PlStereoConfig* scfg, const PlStereoFeatures* prev, const PlStereoFeatures* curr,
+                              const PlPrior* priors, PlPoseResult* results, int32_t* n_stereo);
+
 /* ---- include/stereoFrameHandler.h surface ----------------------------------------------------- */
 /* StereoFrameHandler::f2fTracking (src/stereoFrameHandler.cpp:106-180) for B independent
  * (prev, curr) pairs: descriptor matching for points and lines; m12_* hold problem-local indices

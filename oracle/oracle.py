@@ -88,6 +88,16 @@ class Oracle:
         L.orc_stereo_lift_lines.restype = C.c_int
         L.orc_stereo_lift_lines.argtypes = [C.POINTER(T.PlCamera), scp, C.c_int, fp, fp, i32p, u8p, fp, i32p, dp, dp, dp, dp,
                                             dp, dp, dp, dp, dp, i32p, u8p, i32p]
+        mcp = C.POINTER(T.PlStereoMatchConfig)
+        L.orc_match_stereo_points.restype = C.c_int
+        L.orc_match_stereo_points.argtypes = [C.POINTER(T.PlCamera), mcp, scp, C.c_int, fp, i32p, u8p, C.c_int, fp, u8p, i32p, dp, dp,
+                                              dp, dp, i32p, u8p, i32p]
+        L.orc_match_stereo_lines.restype = C.c_int
+        L.orc_match_stereo_lines.argtypes = [C.POINTER(T.PlCamera), mcp, scp, C.c_int, fp, fp, i32p, u8p, C.c_int, fp, u8p, i32p, dp,
+                                             dp, dp, dp, dp, dp, dp, dp, dp, i32p, u8p, i32p]
+        L.orc_stereo_batch.restype = C.c_int
+        L.orc_stereo_batch.argtypes = [C.POINTER(T.PlCamera), mcp, scp, C.c_int, i32p, fp, i32p, u8p, i32p, fp, u8p, i32p, fp, fp, i32p,
+                                       u8p, i32p, fp, u8p, C.c_int, i32p]
         L.orc_line_segment_overlap_stereo.restype = C.c_double
         L.orc_line_segment_overlap_stereo.argtypes = [scp, C.c_double, C.c_double, C.c_double, C.c_double]
         L.orc_handler_default_config.restype = None
@@ -265,6 +275,57 @@ class Oracle:
             self._dp(out["eP"]), self._dp(out["le"]), self._dp(out["angle"]), self._dp(out["sigma2"]),
             out["level"].ctypes.data_as(i32), out["desc"].ctypes.data_as(u8), out["src_idx"].ctypes.data_as(i32))
         return k, {key: v[:k] for key, v in out.items()}
+
+    def match_stereo_points(self, cam, mcfg, scfg, kp_l, octave_l, desc_l, kp_r, desc_r):
+        """matchStereoPoints for one frame: returns m12, k, records (first k rows)."""
+        kp_l, kp_r = np.ascontiguousarray(kp_l, np.float32).reshape(-1, 2), np.ascontiguousarray(kp_r, np.float32).reshape(-1, 2)
+        octave_l = np.ascontiguousarray(octave_l, np.int32)
+        desc_l, desc_r = np.ascontiguousarray(desc_l, np.uint8).reshape(-1, 32), np.ascontiguousarray(desc_r, np.uint8).reshape(-1, 32)
+        n = len(kp_l)
+        m12 = np.full(n, -1, np.int32)
+        out = dict(pl=np.zeros((n, 2)), disp=np.zeros(n), P=np.zeros((n, 3)), sigma2=np.zeros(n), level=np.zeros(n, np.int32),
+                   desc=np.zeros((n, 32), np.uint8), src_idx=np.full(n, -1, np.int32))
+        i32, u8, f32 = T.c_int32_p, T.c_uint8_p, T.c_float_p
+        k = self.lib.orc_match_stereo_points(
+            C.byref(cam), C.byref(mcfg), C.byref(scfg), n, kp_l.ctypes.data_as(f32), octave_l.ctypes.data_as(i32),
+            desc_l.ctypes.data_as(u8), len(kp_r), kp_r.ctypes.data_as(f32), desc_r.ctypes.data_as(u8), m12.ctypes.data_as(i32),
+            self._dp(out["pl"]), self._dp(out["disp"]), self._dp(out["P"]), self._dp(out["sigma2"]),
+            out["level"].ctypes.data_as(i32), out["desc"].ctypes.data_as(u8), out["src_idx"].ctypes.data_as(i32))
+        return m12, k, {key: v[:k] for key, v in out.items()}
+
+    def match_stereo_lines(self, cam, mcfg, scfg, seg_l, angle_l, octave_l, desc_l, seg_r, desc_r):
+        seg_l, seg_r = np.ascontiguousarray(seg_l, np.float32).reshape(-1, 4), np.ascontiguousarray(seg_r, np.float32).reshape(-1, 4)
+        angle_l, octave_l = np.ascontiguousarray(angle_l, np.float32), np.ascontiguousarray(octave_l, np.int32)
+        desc_l, desc_r = np.ascontiguousarray(desc_l, np.uint8).reshape(-1, 32), np.ascontiguousarray(desc_r, np.uint8).reshape(-1, 32)
+        n = len(seg_l)
+        m12 = np.full(n, -1, np.int32)
+        out = dict(spl=np.zeros((n, 2)), epl=np.zeros((n, 2)), sdisp=np.zeros(n), edisp=np.zeros(n), sP=np.zeros((n, 3)),
+                   eP=np.zeros((n, 3)), le=np.zeros((n, 3)), angle=np.zeros(n), sigma2=np.zeros(n),
+                   level=np.zeros(n, np.int32), desc=np.zeros((n, 32), np.uint8), src_idx=np.full(n, -1, np.int32))
+        i32, u8, f32 = T.c_int32_p, T.c_uint8_p, T.c_float_p
+        k = self.lib.orc_match_stereo_lines(
+            C.byref(cam), C.byref(mcfg), C.byref(scfg), n, seg_l.ctypes.data_as(f32), angle_l.ctypes.data_as(f32),
+            octave_l.ctypes.data_as(i32), desc_l.ctypes.data_as(u8), len(seg_r), seg_r.ctypes.data_as(f32),
+            desc_r.ctypes.data_as(u8), m12.ctypes.data_as(i32), self._dp(out["spl"]), self._dp(out["epl"]), self._dp(out["sdisp"]),
+            self._dp(out["edisp"]), self._dp(out["sP"]), self._dp(out["eP"]), self._dp(out["le"]), self._dp(out["angle"]),
+            self._dp(out["sigma2"]), out["level"].ctypes.data_as(i32), out["desc"].ctypes.data_as(u8),
+            out["src_idx"].ctypes.data_as(i32))
+        return m12, k, {key: v[:k] for key, v in out.items()}
+
+    def stereo_batch(self, cam, mcfg, scfg, pl_off, kp_l, poct, pd1, pr_off, kp_r, pd2, ll_off, seg_l, angle, loct, ld1, lr_off,
+                     seg_r, ld2, threads=1):
+        """matchStereoPoints + matchStereoLines for B frames on `threads` host threads; returns counts[B, 2]."""
+        i32, u8, f32 = T.c_int32_p, T.c_uint8_p, T.c_float_p
+        cv = lambda a, dt: np.ascontiguousarray(a, dt)
+        arrs = [cv(pl_off, np.int32), cv(kp_l, np.float32), cv(poct, np.int32), cv(pd1, np.uint8), cv(pr_off, np.int32),
+                cv(kp_r, np.float32), cv(pd2, np.uint8), cv(ll_off, np.int32), cv(seg_l, np.float32), cv(angle, np.float32),
+                cv(loct, np.int32), cv(ld1, np.uint8), cv(lr_off, np.int32), cv(seg_r, np.float32), cv(ld2, np.uint8)]
+        typ = [i32, f32, i32, u8, i32, f32, u8, i32, f32, f32, i32, u8, i32, f32, u8]
+        B = len(arrs[0]) - 1
+        counts = np.zeros((B, 2), np.int32)
+        self.lib.orc_stereo_batch(C.byref(cam), C.byref(mcfg), C.byref(scfg), B, *[a.ctypes.data_as(t) for a, t in zip(arrs, typ)],
+                                  int(threads), counts.ctypes.data_as(i32))
+        return counts
 
     def line_segment_overlap_stereo(self, scfg, spl_obs, epl_obs, spl_proj, epl_proj):
         return self.lib.orc_line_segment_overlap_stereo(C.byref(scfg), float(spl_obs), float(epl_obs), float(spl_proj), float(epl_proj))

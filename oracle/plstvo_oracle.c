@@ -834,6 +834,129 @@ int orc_stereo_lift_lines(const PlCamera* cam, const PlStereoConfig* sc, int n_l
     return k;
 }
 
+/* ---- matchStereoPoints / matchStereoLines: the caller-side loops + matchGrid + lifting (src/stereoFrame.cpp:120-173, :309-398) */
+int orc_match_stereo_points(const PlCamera* cam, const PlStereoMatchConfig* mc, const PlStereoConfig* sc, int n_l, const float* kp_l,
+                            const int32_t* octave_l, const uint8_t* desc_l, int n_r, const float* kp_r, const uint8_t* desc_r,
+                            int32_t* m12, double* pt_pl, double* pt_disp, double* pt_P, double* pt_sigma2, int32_t* pt_level,
+                            uint8_t* pdesc_out, int32_t* src_idx) {
+    const double inv_width = mc->grid_cols / (double)cam->width, inv_height = mc->grid_rows / (double)cam->height;   /* :47-48 */
+    int32_t* q = (int32_t*)malloc(sizeof(int32_t) * 2 * (size_t)(n_l > 0 ? n_l : 1));
+    int32_t* t = (int32_t*)malloc(sizeof(int32_t) * 2 * (size_t)(n_r > 0 ? n_r : 1));
+    for (int i = 0; i < n_l; ++i) {   /* :131-132: pair<int,int>(kp.pt.x * inv_width, kp.pt.y * inv_height) */
+        q[2 * i] = (int)(kp_l[2 * i] * inv_width);
+        q[2 * i + 1] = (int)(kp_l[2 * i + 1] * inv_height);
+    }
+    for (int i = 0; i < n_r; ++i) {   /* :136-139: grid.at(int x, int y) */
+        t[2 * i] = (int)(kp_r[2 * i] * inv_width);
+        t[2 * i + 1] = (int)(kp_r[2 * i + 1] * inv_height);
+    }
+    const PlGridWindow w = {mc->matching_s_ws, 0, 0, 0};   /* :141-143 */
+    for (int i = 0; i < n_l; ++i) m12[i] = -1;
+    if (n_l > 0 && n_r > 0)                                /* :126-127 */
+        orc_match_grid_points(mc->grid_rows, mc->grid_cols, w, mc->best_lr_matches, mc->min_ratio_12_p, q, desc_l, n_l, t, desc_r,
+                              n_r, m12);
+    free(q);
+    free(t);
+    return orc_stereo_lift_points(cam, sc, n_l, kp_l, octave_l, desc_l, kp_r, m12, pt_pl, pt_disp, pt_P, pt_sigma2, pt_level,
+                                  pdesc_out, src_idx);
+}
+
+int orc_match_stereo_lines(const PlCamera* cam, const PlStereoMatchConfig* mc, const PlStereoConfig* sc, int n_l, const float* seg_l,
+                           const float* angle_l, const int32_t* octave_l, const uint8_t* desc_l, int n_r, const float* seg_r,
+                           const uint8_t* desc_r, int32_t* m12, double* ls_spl, double* ls_epl, double* ls_sdisp, double* ls_edisp,
+                           double* ls_sP, double* ls_eP, double* ls_le, double* ls_angle, double* ls_sigma2, int32_t* ls_level,
+                           uint8_t* ldesc_out, int32_t* src_idx) {
+    const double inv_width = mc->grid_cols / (double)cam->width, inv_height = mc->grid_rows / (double)cam->height;
+    int32_t* q = (int32_t*)malloc(sizeof(int32_t) * 4 * (size_t)(n_l > 0 ? n_l : 1));
+    double* tl = (double*)malloc(sizeof(double) * 4 * (size_t)(n_r > 0 ? n_r : 1));
+    double* td = (double*)malloc(sizeof(double) * 2 * (size_t)(n_r > 0 ? n_r : 1));
+    for (int i = 0; i < n_l; ++i) {   /* :320-322 */
+        q[4 * i] = (int)(seg_l[4 * i] * inv_width);
+        q[4 * i + 1] = (int)(seg_l[4 * i + 1] * inv_height);
+        q[4 * i + 2] = (int)(seg_l[4 * i + 2] * inv_width);
+        q[4 * i + 3] = (int)(seg_l[4 * i + 3] * inv_height);
+    }
+    for (int i = 0; i < n_r; ++i) {   /* :328-337 */
+        const float sx = seg_r[4 * i], sy = seg_r[4 * i + 1], ex = seg_r[4 * i + 2], ey = seg_r[4 * i + 3];
+        double vx = (ex - sx) * inv_width, vy = (ey - sy) * inv_height;   /* float difference, then x double */
+        const double magnitude = sqrt(vx * vx + vy * vy);                  /* include/matching.h:43-48 */
+        td[2 * i] = vx / magnitude;
+        td[2 * i + 1] = vy / magnitude;
+        tl[4 * i] = sx * inv_width;
+        tl[4 * i + 1] = sy * inv_height;
+        tl[4 * i + 2] = ex * inv_width;
+        tl[4 * i + 3] = ey * inv_height;
+    }
+    const PlGridWindow w = {mc->matching_s_ws, 0, 0, 0};
+    for (int i = 0; i < n_l; ++i) m12[i] = -1;
+    if (n_l > 0 && n_r > 0)
+        orc_match_grid_lines(mc->grid_rows, mc->grid_cols, w, mc->best_lr_matches, mc->min_ratio_12_p, mc->line_sim_th, q, desc_l,
+                             n_l, tl, td, desc_r, n_r, m12);
+    free(q);
+    free(tl);
+    free(td);
+    return orc_stereo_lift_lines(cam, sc, n_l, seg_l, angle_l, octave_l, desc_l, seg_r, m12, ls_spl, ls_epl, ls_sdisp, ls_edisp,
+                                 ls_sP, ls_eP, ls_le, ls_angle, ls_sigma2, ls_level, ldesc_out, src_idx);
+}
+
+typedef struct {
+    const PlCamera* cam; const PlStereoMatchConfig* mc; const PlStereoConfig* sc; int B;
+    const int32_t *pl_off, *poct_l, *pr_off, *ll_off, *loct_l, *lr_off;
+    const float *kp_l, *kp_r, *seg_l, *angle_l, *seg_r;
+    const uint8_t *pdesc_l, *pdesc_r, *ldesc_l, *ldesc_r;
+    int32_t* counts; int* next; pthread_mutex_t* mu;
+} StereoJob;
+
+static void* stereo_worker(void* arg) {
+    StereoJob* j = (StereoJob*)arg;
+    for (;;) {
+        pthread_mutex_lock(j->mu);
+        const int f = (*j->next)++;
+        pthread_mutex_unlock(j->mu);
+        if (f >= j->B) break;
+        const int a = j->pl_off[f], n = j->pl_off[f + 1] - a, b = j->pr_off[f], nr = j->pr_off[f + 1] - b;
+        const int c = j->ll_off[f], m = j->ll_off[f + 1] - c, d = j->lr_off[f], mr = j->lr_off[f + 1] - d;
+        const size_t cap = (size_t)((n > m ? n : m) > 0 ? (n > m ? n : m) : 1);
+        double* buf = (double*)malloc(sizeof(double) * cap * 24);
+        int32_t* ib = (int32_t*)malloc(sizeof(int32_t) * cap * 3);
+        uint8_t* db = (uint8_t*)malloc(cap * 32);
+        j->counts[2 * f] = orc_match_stereo_points(j->cam, j->mc, j->sc, n, j->kp_l + 2 * (size_t)a, j->poct_l + a,
+                                                   j->pdesc_l + 32 * (size_t)a, nr, j->kp_r + 2 * (size_t)b,
+                                                   j->pdesc_r + 32 * (size_t)b, ib, buf, buf + 2 * cap, buf + 3 * cap, buf + 6 * cap,
+                                                   ib + cap, db, ib + 2 * cap);
+        j->counts[2 * f + 1] = orc_match_stereo_lines(j->cam, j->mc, j->sc, m, j->seg_l + 4 * (size_t)c, j->angle_l + c, j->loct_l + c,
+                                                      j->ldesc_l + 32 * (size_t)c, mr, j->seg_r + 4 * (size_t)d,
+                                                      j->ldesc_r + 32 * (size_t)d, ib, buf, buf + 2 * cap, buf + 4 * cap,
+                                                      buf + 5 * cap, buf + 6 * cap, buf + 9 * cap, buf + 12 * cap, buf + 15 * cap,
+                                                      buf + 16 * cap, ib + cap, db, ib + 2 * cap);
+        free(buf);
+        free(ib);
+        free(db);
+    }
+    return NULL;
+}
+
+int orc_stereo_batch(const PlCamera* cam, const PlStereoMatchConfig* mc, const PlStereoConfig* sc, int B, const int32_t* pl_off,
+                     const float* kp_l, const int32_t* poct_l, const uint8_t* pdesc_l, const int32_t* pr_off, const float* kp_r,
+                     const uint8_t* pdesc_r, const int32_t* ll_off, const float* seg_l, const float* angle_l, const int32_t* loct_l,
+                     const uint8_t* ldesc_l, const int32_t* lr_off, const float* seg_r, const uint8_t* ldesc_r, int threads,
+                     int32_t* counts) {
+    if (threads < 1) threads = 1;
+    if (threads > B) threads = B > 0 ? B : 1;
+    int next = 0;
+    pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+    StereoJob j = {cam, mc, sc, B, pl_off, poct_l, pr_off, ll_off, loct_l, lr_off, kp_l, kp_r, seg_l, angle_l, seg_r,
+                   pdesc_l, pdesc_r, ldesc_l, ldesc_r, counts, &next, &mu};
+    pthread_t* th = (pthread_t*)calloc((size_t)threads, sizeof(pthread_t));
+    for (int t = 1; t < threads; t++) pthread_create(&th[t], NULL, stereo_worker, &j);
+    stereo_worker(&j);
+    for (int t = 1; t < threads; t++) pthread_join(th[t], NULL);
+    free(th);
+    long total = 0;
+    for (int f = 0; f < 2 * B; f++) total += counts[f];
+    return (int)total;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * the handler state (StereoFrameHandler: matched_pt / matched_ls lists, include/stereoFrameHandler.h)
  * ---------------------------------------------------------------------------------------------- */

@@ -56,6 +56,24 @@ int orc_stereo_lift_lines(const PlCamera* cam, const PlStereoConfig* sc, int n_l
                           double* ls_spl, double* ls_epl, double* ls_sdisp, double* ls_edisp, double* ls_sP, double* ls_eP,
                           double* ls_le, double* ls_angle, double* ls_sigma2, int32_t* ls_level, uint8_t* ldesc_out,
                           int32_t* src_idx);
+/* StereoFrame::matchStereoPoints / matchStereoLines for one frame (src/stereoFrame.cpp:120-173, :309-398): grid coordinates as
+ * the caller forms them (:47-48, :129-139, :318-337), matchGrid, lifting.  Outputs as orc_stereo_lift_*; m12 has n_l entries. */
+int orc_match_stereo_points(const PlCamera* cam, const PlStereoMatchConfig* mc, const PlStereoConfig* sc, int n_l, const float* kp_l,
+                            const int32_t* octave_l, const uint8_t* desc_l, int n_r, const float* kp_r, const uint8_t* desc_r,
+                            int32_t* m12, double* pt_pl, double* pt_disp, double* pt_P, double* pt_sigma2, int32_t* pt_level,
+                            uint8_t* pdesc_out, int32_t* src_idx);
+int orc_match_stereo_lines(const PlCamera* cam, const PlStereoMatchConfig* mc, const PlStereoConfig* sc, int n_l, const float* seg_l,
+                           const float* angle_l, const int32_t* octave_l, const uint8_t* desc_l, int n_r, const float* seg_r,
+                           const uint8_t* desc_r, int32_t* m12, double* ls_spl, double* ls_epl, double* ls_sdisp, double* ls_edisp,
+                           double* ls_sP, double* ls_eP, double* ls_le, double* ls_angle, double* ls_sigma2, int32_t* ls_level,
+                           uint8_t* ldesc_out, int32_t* src_idx);
+/* both of the above for B frames on `threads` host threads, one frame per thread at a time (the all-cores CPU baseline of
+ * bench.py --workload stereo); counts[2 * f], [2 * f + 1] = lifted points, lines of frame f; records are discarded */
+int orc_stereo_batch(const PlCamera* cam, const PlStereoMatchConfig* mc, const PlStereoConfig* sc, int B, const int32_t* pl_off,
+                     const float* kp_l, const int32_t* poct_l, const uint8_t* pdesc_l, const int32_t* pr_off, const float* kp_r,
+                     const uint8_t* pdesc_r, const int32_t* ll_off, const float* seg_l, const float* angle_l, const int32_t* loct_l,
+                     const uint8_t* ldesc_l, const int32_t* lr_off, const float* seg_r, const uint8_t* ldesc_r, int threads,
+                     int32_t* counts);
 double orc_line_segment_overlap_stereo(const PlStereoConfig* sc, double spl_obs, double epl_obs, double spl_proj, double epl_proj);
 
 /* src/auxiliar.cpp */

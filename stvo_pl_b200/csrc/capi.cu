@@ -88,6 +88,17 @@ struct PlContext {
     int next_slot = 0;
     DevBuf scratch;        // misc (popc bench, L2 flush)
     DevBuf gn_in[8], gn_out[4];
+    void* h_staging = nullptr;   // pinned host scratch (small tables and counters that must not block the enqueueing thread)
+    size_t h_staging_bytes = 0;
+    cudaError_t staging(size_t bytes) {
+        if (bytes <= h_staging_bytes) return cudaSuccess;
+        if (h_staging) cudaFreeHost(h_staging);
+        h_staging = nullptr;
+        h_staging_bytes = 0;
+        cudaError_t e = cudaMallocHost(&h_staging, bytes);
+        if (e == cudaSuccess) h_staging_bytes = bytes;
+        return e;
+    }
 };
 
 struct PlDeviceBatch {
@@ -534,6 +545,7 @@ void plstvo_destroy(PlContext* ctx) {
     for (auto& b : ctx->gn_in) b.release();
     for (auto& b : ctx->gn_out) b.release();
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+    if (ctx->h_staging) cudaFreeHost(ctx->h_staging);
     cudaStreamDestroy(ctx->s_main);
     cudaStreamDestroy(ctx->s_alt);
     cudaStreamDestroy(ctx->s_h2d);
@@ -1063,6 +1075,192 @@ int plstvo_match_stereo_lines(PlContext* ctx, const PlCamera* cam, const PlStere
     const StereoOut out{m12, ls_spl, ls_sdisp, ls_sP, ls_sigma2, ls_level, ldesc_out, src_idx, counts,
                         ls_epl, ls_edisp, ls_eP, ls_le, ls_angle};
     return match_stereo_common(ctx, true, cam, mcfg, scfg, B, l_off, seg_l, angle_l, octave_l, desc_l, r_off, seg_r, desc_r, out);
+}
+
+// ---- raw stereo features -> pose, records resident in HBM ---------------------------------------------------------
+int plstvo_track_stereo_batch(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlStereoMatchConfig* mc,
+                              const PlStereoConfig* sc, const PlStereoFeatures* prev, const PlStereoFeatures* curr,
+                              const PlPrior* priors, PlPoseResult* results, int32_t* n_stereo) {
+    if (!ctx) return PLSTVO_E_INVALID;
+    if (!cam || !cfg || !mc || !sc || !prev || !curr || !results) return fail(ctx, PLSTVO_E_INVALID, "null argument");
+    const int B = prev->B;
+    if (B < 0 || curr->B != B) return fail(ctx, PLSTVO_E_SIZE, "prev and curr hold different numbers of frames");
+    const int rows = mc->grid_rows, cols = mc->grid_cols;
+    if (rows <= 0 || cols <= 0 || rows * cols > 8192 || cam->width <= 0 || cam->height <= 0)
+        return fail(ctx, PLSTVO_E_INVALID, "bad grid or image size");
+    if (B == 0) return 0;
+    CK(ctx, cudaSetDevice(ctx->device));
+    constexpr int CAP = 128;
+    // the four feature sets: {prev, curr} x {points, lines}
+    struct Set {
+        bool lines; const int32_t *l_off, *r_off; const float *xy_l, *xy_r, *ang; const int32_t* oct; const uint8_t *d1, *d2;
+        size_t N1, N2, o_loff, o_roff, o_xyl, o_xyr, o_ang, o_oct, o_d1, o_d2, o_m12, o_cnt, o_gcnt, o_ooff, o_prob;
+    };
+    Set sets[4] = {
+        {false, prev->pl_off, prev->pr_off, prev->kp_l, prev->kp_r, nullptr, prev->poct_l, prev->pdesc_l, prev->pdesc_r},
+        {true, prev->ll_off, prev->lr_off, prev->seg_l, prev->seg_r, prev->angle_l, prev->loct_l, prev->ldesc_l, prev->ldesc_r},
+        {false, curr->pl_off, curr->pr_off, curr->kp_l, curr->kp_r, nullptr, curr->poct_l, curr->pdesc_l, curr->pdesc_r},
+        {true, curr->ll_off, curr->lr_off, curr->seg_l, curr->seg_r, curr->angle_l, curr->loct_l, curr->ldesc_l, curr->ldesc_r}};
+    LiftArena a;
+    size_t maxN1 = 0, maxN2 = 0, max_items = 0;
+    for (Set& st : sets) {
+        int rc = lift_check_offsets(ctx, B, st.l_off, st.r_off);
+        if (rc) return rc;
+        st.N1 = st.l_off[B];
+        st.N2 = st.r_off[B];
+        if (st.N1 && (!st.xy_l || !st.oct || !st.d1 || (st.lines && !st.ang))) return fail(ctx, PLSTVO_E_INVALID, "null input array");
+        if (st.N2 && (!st.xy_r || !st.d2)) return fail(ctx, PLSTVO_E_INVALID, "null input array");
+        const int cw = st.lines ? 4 : 2;
+        st.o_loff = a.take((size_t)(B + 1) * 4); st.o_roff = a.take((size_t)(B + 1) * 4);
+        st.o_xyl = a.take(st.N1 * cw * 4); st.o_xyr = a.take(st.N2 * cw * 4); st.o_ang = a.take(st.lines ? st.N1 * 4 : 0);
+        st.o_oct = a.take(st.N1 * 4); st.o_d1 = a.take(st.N1 * 32); st.o_d2 = a.take(st.N2 * 32); st.o_m12 = a.take(st.N1 * 4);
+        st.o_cnt = a.take((size_t)B * 4); st.o_gcnt = a.take((size_t)B * 4); st.o_ooff = a.take((size_t)(B + 1) * 4);
+        st.o_prob = a.take((size_t)B * sizeof(GridProblem));
+        maxN1 = std::max(maxN1, st.N1);
+        maxN2 = std::max(maxN2, st.N2);
+        max_items = std::max(max_items, st.N2 * (st.lines ? (size_t)std::max(rows, cols) + 2 : 1));
+    }
+    // matchGrid scratch, shared by the four sets (they run one after the other on one stream)
+    const size_t o_qcell = a.take(maxN1 * 16), o_tcell = a.take(maxN2 * 8), o_tline = a.take(maxN2 * 32), o_tdir = a.take(maxN2 * 16);
+    const size_t o_items = a.take(max_items * 4), o_qpairs = a.take(maxN1 * CAP * 8), o_qcount = a.take(maxN1 * 4);
+    const size_t o_tcount = a.take(maxN2 * 4), o_tstart = a.take((maxN2 + B) * 4), o_tslots = a.take(maxN1 * CAP * 4);
+    const size_t o_seen = a.take(maxN1 * CAP), o_m21 = a.take(maxN2 * 4);
+    static DevBuf arena;
+    CK(ctx, arena.ensure(a.off));
+    uint8_t* base = arena.as<uint8_t>();
+    auto I = [&](size_t o) { return reinterpret_cast<int32_t*>(base + o); };
+    auto D = [&](size_t o) { return reinterpret_cast<double*>(base + o); };
+    auto F = [&](size_t o) { return reinterpret_cast<float*>(base + o); };
+    cudaStream_t s = ctx->s_main, sh = ctx->s_h2d;   // uploads of set k + 1 run under the kernels of set k
+    auto up = [&](size_t o, const void* src, size_t bytes) -> cudaError_t {
+        return (src && bytes) ? cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, sh) : cudaSuccess;
+    };
+    cudaEvent_t prior_done = next_event(ctx);           // the arena may still be read by work queued on s_main earlier
+    CK(ctx, cudaEventRecord(prior_done, s));
+    CK(ctx, cudaStreamWaitEvent(sh, prior_done, 0));
+    const double inv_w = cols / static_cast<double>(cam->width), inv_h = rows / static_cast<double>(cam->height);
+    const GridParams gprm{rows, cols, CAP, mc->best_lr_matches ? 1 : 0, PlGridWindow{mc->matching_s_ws, 0, 0, 0}, mc->min_ratio_12_p,
+                          mc->line_sim_th};
+    // pinned staging: 4 problem tables + 2 x 4 x B counters (pageable copies would block this thread on the stream)
+    const size_t prob_bytes = ((size_t)B * sizeof(GridProblem) + 255) / 256 * 256;
+    CK(ctx, ctx->staging(4 * prob_bytes + (size_t)8 * B * 4));
+    uint8_t* hst = static_cast<uint8_t*>(ctx->h_staging);
+    int32_t* cnt = reinterpret_cast<int32_t*>(hst + 4 * prob_bytes);
+    int32_t* gcnt = cnt + (size_t)4 * B;
+    // ---- pass 1: cells -> matchGrid -> lifting filters (count only) per set ----
+    for (int k = 0; k < 4; ++k) {
+        Set& st = sets[k];
+        const int cw = st.lines ? 4 : 2;
+        const size_t per_train_cells = st.lines ? (size_t)std::max(rows, cols) + 2 : 1;
+        GridProblem* probs = reinterpret_cast<GridProblem*>(hst + (size_t)k * prob_bytes);
+        for (int p = 0; p < B; ++p) {
+            GridProblem& g = probs[p];
+            const size_t qa = st.l_off[p], tb = st.r_off[p];
+            g.n1 = st.l_off[p + 1] - st.l_off[p];
+            g.n2 = st.r_off[p + 1] - st.r_off[p];
+            g.q_cell = I(o_qcell) + qa * cw;
+            g.d1 = base + st.o_d1 + qa * 32;
+            g.t_cell = st.lines ? nullptr : I(o_tcell) + tb * 2;
+            g.t_line = st.lines ? D(o_tline) + tb * 4 : nullptr;
+            g.t_dir = st.lines ? D(o_tdir) + tb * 2 : nullptr;
+            g.d2 = base + st.o_d2 + tb * 32;
+            g.m12 = I(st.o_m12) + qa;
+            g.count = I(st.o_gcnt) + p;
+            g.grid_items = I(o_items) + tb * per_train_cells;
+            g.q_pairs = reinterpret_cast<int2*>(base + o_qpairs) + qa * CAP;
+            g.q_count = I(o_qcount) + qa;
+            g.t_count = I(o_tcount) + tb;
+            g.t_start = I(o_tstart) + tb + p;
+            g.t_slots = I(o_tslots) + qa * CAP;
+            g.seen = base + o_seen + qa * CAP;
+            g.m21 = I(o_m21) + tb;
+        }
+        CK(ctx, up(st.o_loff, st.l_off, (size_t)(B + 1) * 4));
+        CK(ctx, up(st.o_roff, st.r_off, (size_t)(B + 1) * 4));
+        CK(ctx, up(st.o_xyl, st.xy_l, st.N1 * cw * 4));
+        CK(ctx, up(st.o_xyr, st.xy_r, st.N2 * cw * 4));
+        if (st.lines) CK(ctx, up(st.o_ang, st.ang, st.N1 * 4));
+        CK(ctx, up(st.o_oct, st.oct, st.N1 * 4));
+        CK(ctx, up(st.o_d1, st.d1, st.N1 * 32));
+        CK(ctx, up(st.o_d2, st.d2, st.N2 * 32));
+        CK(ctx, up(st.o_prob, probs, (size_t)B * sizeof(GridProblem)));
+        cudaEvent_t uploaded = next_event(ctx);
+        CK(ctx, cudaEventRecord(uploaded, sh));
+        CK(ctx, cudaStreamWaitEvent(s, uploaded, 0));
+        if (st.lines) {
+            CK(ctx, launch_stereo_cells_lines((int)st.N1, (int)st.N2, inv_w, inv_h, F(st.o_xyl), F(st.o_xyr), I(o_qcell), D(o_tline),
+                                              D(o_tdir), s));
+            CK(ctx, launch_match_grid(reinterpret_cast<GridProblem*>(base + st.o_prob), B, gprm, true, s));
+            CK(ctx, launch_lift_lines(*cam, *sc, B, I(st.o_loff), F(st.o_xyl), F(st.o_ang), I(st.o_oct), base + st.o_d1, I(st.o_roff),
+                                      F(st.o_xyr), I(st.o_m12), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                      nullptr, nullptr, nullptr, nullptr, I(st.o_cnt), s));
+        } else {
+            CK(ctx, launch_stereo_cells_points((int)st.N1, (int)st.N2, inv_w, inv_h, F(st.o_xyl), F(st.o_xyr), I(o_qcell), I(o_tcell), s));
+            CK(ctx, launch_match_grid(reinterpret_cast<GridProblem*>(base + st.o_prob), B, gprm, false, s));
+            CK(ctx, launch_lift_points(*cam, *sc, B, I(st.o_loff), F(st.o_xyl), I(st.o_oct), base + st.o_d1, I(st.o_roff), F(st.o_xyr),
+                                       I(st.o_m12), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, I(st.o_cnt), s));
+        }
+        ctx->launches += 3;
+        CK(ctx, cudaMemcpyAsync(cnt + (size_t)k * B, base + st.o_cnt, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+        CK(ctx, cudaMemcpyAsync(gcnt + (size_t)k * B, base + st.o_gcnt, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CK(ctx, cudaStreamSynchronize(s));     // the one host hop: survivor counts -> compact offsets and the matcher's tile plan
+    std::vector<int32_t> ooff[4];
+    for (int k = 0; k < 4; ++k) {
+        ooff[k].assign((size_t)B + 1, 0);
+        for (int p = 0; p < B; ++p) {
+            if (gcnt[(size_t)k * B + p] < 0) return fail(ctx, gcnt[(size_t)k * B + p], "matchGrid: more than 128 candidates in one query window");
+            ooff[k][p + 1] = ooff[k][p] + cnt[(size_t)k * B + p];
+            if (n_stereo) n_stereo[(size_t)p * 4 + k] = cnt[(size_t)k * B + p];
+        }
+        CK(ctx, up(sets[k].o_ooff, ooff[k].data(), (size_t)(B + 1) * 4));
+    }
+    // ---- the tracker's plan on the compact lists; the records are written straight into its buffers ----
+    PlFrameBatch fp{}, fc{};
+    fp.B = fc.B = B;
+    fp.pt_off = ooff[0].data(); fp.ls_off = ooff[1].data();
+    fc.pt_off = ooff[2].data(); fc.ls_off = ooff[3].data();
+    Workspace& ws = ctx->ws;
+    int rc = ws_prepare(ctx, ws, cam, cfg, &fp, &fc, true, priors != nullptr);
+    if (rc) return rc;
+    if (priors) CK(ctx, cudaMemcpyAsync(ws.d_priors.p, priors, (size_t)B * sizeof(PlPrior), cudaMemcpyHostToDevice, ctx->s_h2d));
+    cudaEvent_t planned = next_event(ctx);
+    CK(ctx, cudaEventRecord(planned, ctx->s_h2d));
+    CK(ctx, cudaStreamWaitEvent(s, planned, 0));
+    // pass 2: the same lifting kernels, now writing at the compact offsets (prev: P, sigma2, segments, level; curr: pl, le)
+    {
+        const Set& st = sets[0];
+        CK(ctx, launch_lift_points(*cam, *sc, B, I(st.o_loff), F(st.o_xyl), I(st.o_oct), base + st.o_d1, I(st.o_roff), F(st.o_xyr),
+                                   I(st.o_m12), nullptr, nullptr, ws.d_ptP.as<double>(), ws.d_pts2.as<double>(), nullptr,
+                                   ws.d_pdesc1.as<uint8_t>(), nullptr, I(st.o_cnt), s, I(st.o_ooff)));
+    }
+    {
+        const Set& st = sets[1];
+        CK(ctx, launch_lift_lines(*cam, *sc, B, I(st.o_loff), F(st.o_xyl), F(st.o_ang), I(st.o_oct), base + st.o_d1, I(st.o_roff),
+                                  F(st.o_xyr), I(st.o_m12), ws.d_lsspl.as<double>(), ws.d_lsepl.as<double>(), nullptr, nullptr,
+                                  ws.d_lssP.as<double>(), ws.d_lseP.as<double>(), nullptr, nullptr, ws.d_lss2.as<double>(),
+                                  ws.d_lslev.as<int32_t>(), ws.d_ldesc1.as<uint8_t>(), nullptr, I(st.o_cnt), s, I(st.o_ooff)));
+    }
+    {
+        const Set& st = sets[2];
+        CK(ctx, launch_lift_points(*cam, *sc, B, I(st.o_loff), F(st.o_xyl), I(st.o_oct), base + st.o_d1, I(st.o_roff), F(st.o_xyr),
+                                   I(st.o_m12), ws.d_ptpl.as<double>(), nullptr, nullptr, nullptr, nullptr, ws.d_pdesc2.as<uint8_t>(),
+                                   nullptr, I(st.o_cnt), s, I(st.o_ooff)));
+    }
+    {
+        const Set& st = sets[3];
+        CK(ctx, launch_lift_lines(*cam, *sc, B, I(st.o_loff), F(st.o_xyl), F(st.o_ang), I(st.o_oct), base + st.o_d1, I(st.o_roff),
+                                  F(st.o_xyr), I(st.o_m12), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ws.d_lsle.as<double>(),
+                                  nullptr, nullptr, nullptr, ws.d_ldesc2.as<uint8_t>(), nullptr, I(st.o_cnt), s, I(st.o_ooff)));
+    }
+    ctx->launches += 4;
+    rc = ws_launch_match(ctx, ws, 0, B, s);
+    if (rc) return rc;
+    rc = ws_launch_solve(ctx, ws, 0, B, true, s);
+    if (rc) return rc;
+    CK(ctx, cudaMemcpyAsync(results, ws.d_results.p, (size_t)B * sizeof(PlPoseResult), cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaStreamSynchronize(s));
+    return 0;
 }
 
 // ---- stereoFrameHandler.h surface ------------------------------------------------------------------------

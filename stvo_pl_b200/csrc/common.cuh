@@ -153,13 +153,14 @@ cudaError_t launch_stereo_cells_lines(int n_l, int n_r, double inv_w, double inv
 cudaError_t launch_lift_points(const PlCamera& cam, const PlStereoConfig& sc, int B, const int32_t* l_off, const float* kp_l,
                                const int32_t* oct_l, const uint8_t* desc_l, const int32_t* r_off, const float* kp_r,
                                const int32_t* m12, double* pt_pl, double* pt_disp, double* pt_P, double* pt_sigma2,
-                               int32_t* pt_level, uint8_t* pdesc_out, int32_t* src_idx, int32_t* counts, cudaStream_t s);
+                               int32_t* pt_level, uint8_t* pdesc_out, int32_t* src_idx, int32_t* counts, cudaStream_t s,
+                               const int32_t* out_off = nullptr);   // out_off: compact output offsets per frame (else l_off); null outputs are skipped
 cudaError_t launch_lift_lines(const PlCamera& cam, const PlStereoConfig& sc, int B, const int32_t* l_off, const float* seg_l,
                               const float* ang_l, const int32_t* oct_l, const uint8_t* desc_l, const int32_t* r_off,
                               const float* seg_r, const int32_t* m12, double* ls_spl, double* ls_epl, double* ls_sdisp,
                               double* ls_edisp, double* ls_sP, double* ls_eP, double* ls_le, double* ls_angle,
                               double* ls_sigma2, int32_t* ls_level, uint8_t* ldesc_out, int32_t* src_idx, int32_t* counts,
-                              cudaStream_t s);
+                              cudaStream_t s, const int32_t* out_off = nullptr);
 
 // GN evaluation streamed from HBM (roofline kernel of config C5): fp32-packed records, TMA-staged tiles
 int gn_stream_tiles(int n_pt, int n_ls);

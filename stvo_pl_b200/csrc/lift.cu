@@ -68,10 +68,13 @@ lift_points_kernel(PlCamera cam, PlStereoConfig sc, const int32_t* __restrict__ 
                    const int32_t* __restrict__ oct_l, const uint8_t* __restrict__ desc_l, const int32_t* __restrict__ r_off,
                    const float* __restrict__ kp_r, const int32_t* __restrict__ m12, double* pt_pl, double* pt_disp,
                    double* pt_P, double* pt_sigma2, int32_t* pt_level, uint8_t* pdesc_out, int32_t* src_idx,
-                   int32_t* counts) {
+                   int32_t* counts, const int32_t* __restrict__ out_off) {
+    // out_off == nullptr: frame f's records start at element l_off[f] of every output; else at out_off[f] (compact layout).
+    // Output pointers may be null (not wanted); with all of them null the kernel only counts.
     __shared__ int s_warp[LF_THREADS / 32], s_base;
     const int f = blockIdx.x, tid = threadIdx.x;
     const int a0 = l_off[f], n = l_off[f + 1] - a0, b0 = r_off[f];
+    const size_t o0 = out_off ? (size_t)out_off[f] : (size_t)a0;
     if (tid == 0) s_base = 0;
     __syncthreads();
     for (int base = 0; base < n; base += LF_THREADS) {
@@ -91,19 +94,23 @@ lift_points_kernel(PlCamera cam, PlStereoConfig sc, const int32_t* __restrict__ 
         int tot;
         const int k = block_scan_flag(keep, s_warp, &s_base, &tot);
         if (keep) {
-            const size_t o = (size_t)a0 + k, src = (size_t)a0 + i1;
+            const size_t o = o0 + k, src = (size_t)a0 + i1;
             const double u = (double)kp_l[2 * src], v = (double)kp_l[2 * src + 1];
-            pt_pl[2 * o] = u;
-            pt_pl[2 * o + 1] = v;
-            pt_disp[o] = disp;
-            back_projection(cam, u, v, disp, pt_P + 3 * o);
-            pt_level[o] = oct_l[src];
-            pt_sigma2[o] = sigma2_of_level(oct_l[src], sc.orb_scale_factor);
-            src_idx[o] = i1;
-            const uint4* d = reinterpret_cast<const uint4*>(desc_l + src * 32);
-            uint4* q = reinterpret_cast<uint4*>(pdesc_out + o * 32);
-            q[0] = d[0];
-            q[1] = d[1];
+            if (pt_pl) {
+                pt_pl[2 * o] = u;
+                pt_pl[2 * o + 1] = v;
+            }
+            if (pt_disp) pt_disp[o] = disp;
+            if (pt_P) back_projection(cam, u, v, disp, pt_P + 3 * o);
+            if (pt_level) pt_level[o] = oct_l[src];
+            if (pt_sigma2) pt_sigma2[o] = sigma2_of_level(oct_l[src], sc.orb_scale_factor);
+            if (src_idx) src_idx[o] = i1;
+            if (pdesc_out) {
+                const uint4* d = reinterpret_cast<const uint4*>(desc_l + src * 32);
+                uint4* q = reinterpret_cast<uint4*>(pdesc_out + o * 32);
+                q[0] = d[0];
+                q[1] = d[1];
+            }
         }
         __syncthreads();   // a later round may overwrite rows this round still reads (o <= src always, rounds ascend)
     }
@@ -116,10 +123,11 @@ lift_lines_kernel(PlCamera cam, PlStereoConfig sc, const int32_t* __restrict__ l
                   const int32_t* __restrict__ r_off, const float* __restrict__ seg_r, const int32_t* __restrict__ m12,
                   double* ls_spl, double* ls_epl, double* ls_sdisp, double* ls_edisp, double* ls_sP, double* ls_eP,
                   double* ls_le, double* ls_angle, double* ls_sigma2, int32_t* ls_level, uint8_t* ldesc_out,
-                  int32_t* src_idx, int32_t* counts) {
+                  int32_t* src_idx, int32_t* counts, const int32_t* __restrict__ out_off) {
     __shared__ int s_warp[LF_THREADS / 32], s_base;
     const int f = blockIdx.x, tid = threadIdx.x;
     const int a0 = l_off[f], n = l_off[f + 1] - a0, b0 = r_off[f];
+    const size_t o0 = out_off ? (size_t)out_off[f] : (size_t)a0;
     if (tid == 0) s_base = 0;
     __syncthreads();
     for (int base = 0; base < n; base += LF_THREADS) {
@@ -155,21 +163,24 @@ lift_lines_kernel(PlCamera cam, PlStereoConfig sc, const int32_t* __restrict__ l
         int tot;
         const int k = block_scan_flag(keep, s_warp, &s_base, &tot);
         if (keep) {
-            const size_t o = (size_t)a0 + k, src = (size_t)a0 + i1;
-            back_projection(cam, spl[0], spl[1], disp_s, ls_sP + 3 * o);
-            back_projection(cam, epl[0], epl[1], disp_e, ls_eP + 3 * o);
-            ls_spl[2 * o] = spl[0]; ls_spl[2 * o + 1] = spl[1];
-            ls_epl[2 * o] = epl[0]; ls_epl[2 * o + 1] = epl[1];
-            ls_sdisp[o] = disp_s; ls_edisp[o] = disp_e;
-            ls_le[3 * o] = le[0]; ls_le[3 * o + 1] = le[1]; ls_le[3 * o + 2] = le[2];
-            ls_angle[o] = (double)ang_l[src];
-            ls_level[o] = oct_l[src];
-            ls_sigma2[o] = sigma2_of_level(oct_l[src], sc.lsd_scale);
-            src_idx[o] = i1;
-            const uint4* d = reinterpret_cast<const uint4*>(desc_l + src * 32);
-            uint4* q = reinterpret_cast<uint4*>(ldesc_out + o * 32);
-            q[0] = d[0];
-            q[1] = d[1];
+            const size_t o = o0 + k, src = (size_t)a0 + i1;
+            if (ls_sP) back_projection(cam, spl[0], spl[1], disp_s, ls_sP + 3 * o);
+            if (ls_eP) back_projection(cam, epl[0], epl[1], disp_e, ls_eP + 3 * o);
+            if (ls_spl) { ls_spl[2 * o] = spl[0]; ls_spl[2 * o + 1] = spl[1]; }
+            if (ls_epl) { ls_epl[2 * o] = epl[0]; ls_epl[2 * o + 1] = epl[1]; }
+            if (ls_sdisp) ls_sdisp[o] = disp_s;
+            if (ls_edisp) ls_edisp[o] = disp_e;
+            if (ls_le) { ls_le[3 * o] = le[0]; ls_le[3 * o + 1] = le[1]; ls_le[3 * o + 2] = le[2]; }
+            if (ls_angle) ls_angle[o] = (double)ang_l[src];
+            if (ls_level) ls_level[o] = oct_l[src];
+            if (ls_sigma2) ls_sigma2[o] = sigma2_of_level(oct_l[src], sc.lsd_scale);
+            if (src_idx) src_idx[o] = i1;
+            if (ldesc_out) {
+                const uint4* d = reinterpret_cast<const uint4*>(desc_l + src * 32);
+                uint4* q = reinterpret_cast<uint4*>(ldesc_out + o * 32);
+                q[0] = d[0];
+                q[1] = d[1];
+            }
         }
         __syncthreads();
     }
@@ -234,10 +245,11 @@ cudaError_t launch_stereo_cells_lines(int n_l, int n_r, double inv_w, double inv
 cudaError_t launch_lift_points(const PlCamera& cam, const PlStereoConfig& sc, int B, const int32_t* l_off, const float* kp_l,
                                const int32_t* oct_l, const uint8_t* desc_l, const int32_t* r_off, const float* kp_r,
                                const int32_t* m12, double* pt_pl, double* pt_disp, double* pt_P, double* pt_sigma2,
-                               int32_t* pt_level, uint8_t* pdesc_out, int32_t* src_idx, int32_t* counts, cudaStream_t s) {
+                               int32_t* pt_level, uint8_t* pdesc_out, int32_t* src_idx, int32_t* counts, cudaStream_t s,
+                               const int32_t* out_off) {
     if (B <= 0) return cudaSuccess;
     lift_points_kernel<<<B, LF_THREADS, 0, s>>>(cam, sc, l_off, kp_l, oct_l, desc_l, r_off, kp_r, m12, pt_pl, pt_disp, pt_P,
-                                                pt_sigma2, pt_level, pdesc_out, src_idx, counts);
+                                                pt_sigma2, pt_level, pdesc_out, src_idx, counts, out_off);
     return cudaGetLastError();
 }
 
@@ -246,11 +258,11 @@ cudaError_t launch_lift_lines(const PlCamera& cam, const PlStereoConfig& sc, int
                               const float* seg_r, const int32_t* m12, double* ls_spl, double* ls_epl, double* ls_sdisp,
                               double* ls_edisp, double* ls_sP, double* ls_eP, double* ls_le, double* ls_angle,
                               double* ls_sigma2, int32_t* ls_level, uint8_t* ldesc_out, int32_t* src_idx, int32_t* counts,
-                              cudaStream_t s) {
+                              cudaStream_t s, const int32_t* out_off) {
     if (B <= 0) return cudaSuccess;
     lift_lines_kernel<<<B, LF_THREADS, 0, s>>>(cam, sc, l_off, seg_l, ang_l, oct_l, desc_l, r_off, seg_r, m12, ls_spl, ls_epl,
                                                ls_sdisp, ls_edisp, ls_sP, ls_eP, ls_le, ls_angle, ls_sigma2, ls_level,
-                                               ldesc_out, src_idx, counts);
+                                               ldesc_out, src_idx, counts, out_off);
     return cudaGetLastError();
 }
 

@@ -19,7 +19,8 @@ namespace plstvo {
 
 namespace {
 
-constexpr int MG_THREADS = 256;
+constexpr int MG_CAP = 128;        // candidates per query window; pair keys pack (query:16 | slot:7 | distance:9)
+constexpr int MG_THREADS = 512;    // one CTA per frame: the work is a few thousand short dependent chains, so width buys latency
 
 __device__ __forceinline__ int mg_distance(const uint8_t* a, const uint8_t* b) {   // StVO::distance (:93-109)
     const uint4* pa = reinterpret_cast<const uint4*>(a);
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(MG_THREADS) match_grid_kernel(const GridProble
     __shared__ int s_flag;
     const GridProblem pr = problems[blockIdx.x];
     const int tid = threadIdx.x, ncell = prm.rows * prm.cols, n1 = pr.n1, n2 = pr.n2;
-    const int CAP = prm.cap;
+    constexpr int CAP = MG_CAP;
     if (tid == 0) s_flag = 0;
     for (int q = tid; q < n1; q += MG_THREADS) pr.m12[q] = -1;
     if (n1 == 0 || n2 == 0) {
@@ -181,26 +182,27 @@ __global__ void __launch_bounds__(MG_THREADS) match_grid_kernel(const GridProble
     for (int q = tid; q < n1; q += MG_THREADS) {
         const int2* seg = pr.q_pairs + (size_t)q * CAP;
         const int k = pr.q_count[q];
-        for (int j = 0; j < k; ++j)
-            if (seg[j].y >= 0) pr.t_slots[atomicAdd(&pr.t_count[seg[j].x], 1)] = q * CAP + j;
+        for (int j = 0; j < k; ++j)   // key = (query << 16) | (slot << 9) | distance: phase C never goes back to q_pairs
+            if (seg[j].y >= 0) pr.t_slots[atomicAdd(&pr.t_count[seg[j].x], 1)] = (int)(((uint32_t)q << 16) | ((uint32_t)j << 9) | (uint32_t)seg[j].y);
     }
     __syncthreads();
 
     // ---- C. the gate (:145-150): strict prefix minimum over ascending query index, per train ----
     for (int t = tid; t < n2; t += MG_THREADS) {
         const int b = pr.t_start[t], e = pr.t_start[t + 1];
+        const uint32_t* keys = reinterpret_cast<const uint32_t*>(pr.t_slots);
         int best_key = 0x7FFFFFFF;   // (d << 16 | i1): minimum distance, lowest query index = the last record setter
         for (int a = b; a < e; ++a) {
-            const int slot = pr.t_slots[a], i1 = slot / CAP, d = pr.q_pairs[slot].y;
+            const uint32_t ka = keys[a], i1 = ka >> 16, d = ka & 0x1FFu;
             bool seen = true;
             if (prm.best_lr) {
                 for (int o = b; o < e; ++o) {
-                    const int so = pr.t_slots[o], io = so / CAP;
-                    if (io < i1 && pr.q_pairs[so].y <= d) seen = false;
+                    const uint32_t ko = keys[o];
+                    if ((ko >> 16) < i1 && (ko & 0x1FFu) <= d) seen = false;
                 }
             }
-            pr.seen[slot] = seen ? 1 : 0;
-            best_key = min(best_key, (d << 16) | i1);
+            pr.seen[ka >> 9] = seen ? 1 : 0;            // ka >> 9 = query * CAP + slot
+            best_key = min(best_key, (int)((d << 16) | i1));
         }
         pr.m21[t] = (e > b) ? (best_key & 0xFFFF) : -1;
     }
@@ -245,6 +247,7 @@ size_t match_grid_smem_bytes(int rows, int cols) { return ((size_t)2 * rows * co
 
 cudaError_t launch_match_grid(const GridProblem* problems, int B, const GridParams& prm, bool lines, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
+    if (prm.cap != MG_CAP) return cudaErrorInvalidValue;   // the scratch arrays are laid out for MG_CAP candidates per query
     const size_t smem = match_grid_smem_bytes(prm.rows, prm.cols);
     if (lines) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(match_grid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

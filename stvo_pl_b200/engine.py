@@ -57,6 +57,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "plstvo_match_stereo_lines": (C.c_int, [vp, cam, C.POINTER(T.PlStereoMatchConfig), C.POINTER(T.PlStereoConfig), C.c_int,
                                                 i32p, fp, fp, i32p, u8p, i32p, fp, u8p, i32p, dp, dp, dp, dp, dp, dp, dp, dp, dp,
                                                 i32p, u8p, i32p, i32p]),
+        "plstvo_track_stereo_batch": (C.c_int, [vp, cam, cfg, C.POINTER(T.PlStereoMatchConfig), C.POINTER(T.PlStereoConfig),
+                                                C.POINTER(T.PlStereoFeatures), C.POINTER(T.PlStereoFeatures), vp, vp, i32p]),
         "plstvo_f2f_tracking": (C.c_int, [vp, cfg, fb, fb, i32p, i32p, i32p]),
         "plstvo_optimize_pose": (C.c_int, [vp, cam, cfg, mb, vp, vp, u8p, u8p]),
         "plstvo_track_batch": (C.c_int, [vp, cam, cfg, fb, fb, vp, vp, i32p, i32p, u8p, u8p]),
@@ -86,7 +88,8 @@ EXPORTED_SYMBOLS = [
     "plstvo_version", "plstvo_create", "plstvo_destroy", "plstvo_last_error", "plstvo_default_config",
     "plstvo_kitti_config", "plstvo_match_nnr", "plstvo_match", "plstvo_match_batch", "plstvo_match_grid_points",
     "plstvo_match_grid_lines", "plstvo_default_stereo_config", "plstvo_stereo_lift_points", "plstvo_stereo_lift_lines",
-    "plstvo_default_stereo_match_config", "plstvo_match_stereo_points", "plstvo_match_stereo_lines", "plstvo_f2f_tracking",
+    "plstvo_default_stereo_match_config", "plstvo_match_stereo_points", "plstvo_match_stereo_lines", "plstvo_track_stereo_batch",
+    "plstvo_f2f_tracking",
     "plstvo_optimize_pose", "plstvo_track_batch", "plstvo_track_batch_async", "plstvo_wait", "plstvo_batch_upload", "plstvo_batch_run",
     "plstvo_batch_run_timed", "plstvo_batch_download", "plstvo_batch_free", "plstvo_synchronize",
     "plstvo_host_alloc", "plstvo_host_free", "plstvo_launch_count", "plstvo_batch_kernel_times",
@@ -321,7 +324,7 @@ class Engine:
         return total, out
 
     def match_stereo_points(self, cam, mcfg: T.PlStereoMatchConfig, scfg: T.PlStereoConfig, l_off, kp_l, octave_l, desc_l,
-                            r_off, kp_r, desc_r):
+                            r_off, kp_r, desc_r, out=None):
         """StereoFrame::matchStereoPoints (src/stereoFrame.cpp:120-173): grid cells, matchGrid and the lifting in one device
         pass.  Returns (total, out) like stereo_lift_points, plus out["m12"]."""
         l_off, r_off = np.ascontiguousarray(l_off, np.int32), np.ascontiguousarray(r_off, np.int32)
@@ -329,9 +332,8 @@ class Engine:
         octave_l = np.ascontiguousarray(octave_l, np.int32)
         desc_l, desc_r = np.ascontiguousarray(desc_l, np.uint8).reshape(-1, 32), np.ascontiguousarray(desc_r, np.uint8).reshape(-1, 32)
         B, n = len(l_off) - 1, len(kp_l)
-        out = dict(m12=np.full(n, -1, np.int32), pl=np.zeros((n, 2)), disp=np.zeros(n), P=np.zeros((n, 3)), sigma2=np.zeros(n),
-                   level=np.zeros(n, np.int32), desc=np.zeros((n, 32), np.uint8), src_idx=np.full(n, -1, np.int32),
-                   counts=np.zeros(B, np.int32))
+        if out is None:
+            out = self.stereo_outputs(n, B, lines=False)
         total = self._ck(self.lib.plstvo_match_stereo_points(
             self.ctx, C.byref(cam), C.byref(mcfg), C.byref(scfg), B, _p(l_off, T.c_int32_p), _p(kp_l, T.c_float_p),
             _p(octave_l, T.c_int32_p), _p(desc_l, T.c_uint8_p), _p(r_off, T.c_int32_p), _p(kp_r, T.c_float_p),
@@ -340,18 +342,33 @@ class Engine:
             _p(out["desc"], T.c_uint8_p), _p(out["src_idx"], T.c_int32_p), _p(out["counts"], T.c_int32_p)))
         return total, out
 
+    def stereo_outputs(self, n: int, B: int, lines: bool, pinned: bool = False) -> dict:
+        """Output arrays of match_stereo_points / _lines for n left features in B frames (pinned=True: cudaMallocHost)."""
+        mk = (lambda shape, dt: self.pinned.empty(shape, dt)) if pinned else (lambda shape, dt: np.zeros(shape, dt))
+        if lines:
+            spec = dict(m12=((n,), np.int32), spl=((n, 2), np.float64), epl=((n, 2), np.float64), sdisp=((n,), np.float64),
+                        edisp=((n,), np.float64), sP=((n, 3), np.float64), eP=((n, 3), np.float64), le=((n, 3), np.float64),
+                        angle=((n,), np.float64), sigma2=((n,), np.float64), level=((n,), np.int32), desc=((n, 32), np.uint8),
+                        src_idx=((n,), np.int32), counts=((B,), np.int32))
+        else:
+            spec = dict(m12=((n,), np.int32), pl=((n, 2), np.float64), disp=((n,), np.float64), P=((n, 3), np.float64),
+                        sigma2=((n,), np.float64), level=((n,), np.int32), desc=((n, 32), np.uint8), src_idx=((n,), np.int32),
+                        counts=((B,), np.int32))
+        out = {k: mk(shape, dt) for k, (shape, dt) in spec.items()}
+        out["m12"][...] = -1
+        out["src_idx"][...] = -1
+        return out
+
     def match_stereo_lines(self, cam, mcfg: T.PlStereoMatchConfig, scfg: T.PlStereoConfig, l_off, seg_l, angle_l, octave_l,
-                           desc_l, r_off, seg_r, desc_r):
+                           desc_l, r_off, seg_r, desc_r, out=None):
         """StereoFrame::matchStereoLines (src/stereoFrame.cpp:309-398) in one device pass."""
         l_off, r_off = np.ascontiguousarray(l_off, np.int32), np.ascontiguousarray(r_off, np.int32)
         seg_l, seg_r = np.ascontiguousarray(seg_l, np.float32).reshape(-1, 4), np.ascontiguousarray(seg_r, np.float32).reshape(-1, 4)
         angle_l, octave_l = np.ascontiguousarray(angle_l, np.float32), np.ascontiguousarray(octave_l, np.int32)
         desc_l, desc_r = np.ascontiguousarray(desc_l, np.uint8).reshape(-1, 32), np.ascontiguousarray(desc_r, np.uint8).reshape(-1, 32)
         B, n = len(l_off) - 1, len(seg_l)
-        out = dict(m12=np.full(n, -1, np.int32), spl=np.zeros((n, 2)), epl=np.zeros((n, 2)), sdisp=np.zeros(n), edisp=np.zeros(n),
-                   sP=np.zeros((n, 3)), eP=np.zeros((n, 3)), le=np.zeros((n, 3)), angle=np.zeros(n), sigma2=np.zeros(n),
-                   level=np.zeros(n, np.int32), desc=np.zeros((n, 32), np.uint8), src_idx=np.full(n, -1, np.int32),
-                   counts=np.zeros(B, np.int32))
+        if out is None:
+            out = self.stereo_outputs(n, B, lines=True)
         total = self._ck(self.lib.plstvo_match_stereo_lines(
             self.ctx, C.byref(cam), C.byref(mcfg), C.byref(scfg), B, _p(l_off, T.c_int32_p), _p(seg_l, T.c_float_p),
             _p(angle_l, T.c_float_p), _p(octave_l, T.c_int32_p), _p(desc_l, T.c_uint8_p), _p(r_off, T.c_int32_p),
@@ -361,6 +378,22 @@ class Engine:
             _p(out["sigma2"], T.c_double_p), _p(out["level"], T.c_int32_p), _p(out["desc"], T.c_uint8_p),
             _p(out["src_idx"], T.c_int32_p), _p(out["counts"], T.c_int32_p)))
         return total, out
+
+    def track_stereo_batch(self, cam, cfg, mcfg, scfg, prev: dict, curr: dict, priors=None, results=None):
+        """Raw stereo features of B (prev, curr) frame pairs -> poses: matchStereoPoints / Lines for both frames, f2fTracking and
+        optimizePose, the lifted records resident in HBM.  prev / curr: dicts with the PlStereoFeatures fields.
+        Returns (results, n_stereo[B, 4])."""
+        ps, keep_p = T.stereo_features_as_c(prev)
+        cs, keep_c = T.stereo_features_as_c(curr)
+        B = ps.B
+        if results is None:
+            results = np.zeros(B, dtype=T.POSE_RESULT_DTYPE)
+        n_stereo = np.zeros((B, 4), np.int32)
+        self._ck(self.lib.plstvo_track_stereo_batch(self.ctx, C.byref(cam), C.byref(cfg), C.byref(mcfg), C.byref(scfg), C.byref(ps),
+                                                    C.byref(cs), priors.ctypes.data if priors is not None else None,
+                                                    results.ctypes.data, _p(n_stereo, T.c_int32_p)))
+        del keep_p, keep_c
+        return results, n_stereo
 
     # ---- stereoFrameHandler.h surface ----
     def f2f_tracking(self, cfg, prev: T.FrameBatch, curr: T.FrameBatch):

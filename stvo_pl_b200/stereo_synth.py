@@ -190,3 +190,72 @@ def stereo_cells_lines(seg_l, seg_r, W, H):
     with np.errstate(all="ignore"):
         t_dir = v / np.sqrt(v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1])[:, None]
     return q_line, t_line, t_dir
+
+
+# ---- raw stereo features of (prev, curr) frame pairs of one scene, for plstvo_track_stereo_batch ----
+def make_stereo_pairs(B, n_pt=1200, n_ls=300, seed=0, clutter=0.15, bitflip=0.06, noise_px=0.3):
+    """B independent (prev, curr) stereo frame pairs: a static 3-D scene of points and segments seen from two poses of a
+    rectified KITTI-shaped stereo rig.  Returns (prev, curr, T_gt[B,4,4], cam) where prev / curr are dicts with the fields of
+    PlStereoFeatures (concatenated over frames)."""
+    from .synth import expmap_se3, kitti_camera, projection
+    cam = kitti_camera()
+    W, H = cam.width, cam.height
+    rng = np.random.default_rng(seed)
+
+    def to_right(uv, Z):
+        return np.stack([uv[:, 0] - cam.b * cam.fx / Z, uv[:, 1]], 1)
+
+    def flip(d):
+        return d ^ np.packbits(rng.random((len(d), 32, 8)) < bitflip, axis=2).reshape(len(d), 32)
+
+    def clutter_pts(n):
+        return np.stack([rng.uniform(0, W, n), rng.uniform(0, H, n)], 1), rng.integers(0, 256, (n, 32), dtype=np.uint8)
+
+    frames = {"prev": [], "curr": []}
+    Ts = []
+    for _ in range(B):
+        T = expmap_se3(np.concatenate([rng.normal([0.0, 0.0, -0.6], 0.05), rng.normal(0, 0.01, 3)]))   # prev -> curr
+        Ts.append(T)
+        # scene in the prev camera frame
+        u, v, Z = rng.uniform(30, W - 30, n_pt), rng.uniform(20, H - 20, n_pt), np.exp(rng.uniform(np.log(4), np.log(40), n_pt))
+        P = np.stack([(u - cam.cx) * Z / cam.fx, (v - cam.cy) * Z / cam.fy, Z], 1)
+        dP = rng.integers(0, 256, (n_pt, 32), dtype=np.uint8)
+        octv = rng.integers(0, 4, n_pt).astype(np.int32)
+        su, sv = rng.uniform(60, W - 60, n_ls), rng.uniform(40, H - 40, n_ls)
+        Zs = np.exp(rng.uniform(np.log(5), np.log(30), n_ls))
+        ang, ln = rng.uniform(0.35, np.pi - 0.35, n_ls), rng.uniform(40, 120, n_ls)      # never horizontal
+        eu, ev = su + ln * np.cos(ang), sv + ln * np.sin(ang) * np.sign(rng.uniform(-1, 1, n_ls))
+        Ze = Zs * rng.uniform(0.97, 1.03, n_ls)
+        sP = np.stack([(su - cam.cx) * Zs / cam.fx, (sv - cam.cy) * Zs / cam.fy, Zs], 1)
+        eP = np.stack([(eu - cam.cx) * Ze / cam.fx, (ev - cam.cy) * Ze / cam.fy, Ze], 1)
+        dL = rng.integers(0, 256, (n_ls, 32), dtype=np.uint8)
+        for name, Tf in (("prev", np.eye(4)), ("curr", T)):
+            Pc = P @ Tf[:3, :3].T + Tf[:3, 3]
+            uvl = projection(cam, Pc) + rng.normal(0, noise_px, (n_pt, 2))
+            uvr = to_right(uvl, Pc[:, 2])
+            uvr[:, 0] += rng.normal(0, noise_px, n_pt)
+            nc = int(clutter * n_pt)
+            cl, cdl = clutter_pts(nc)
+            cr, cdr = clutter_pts(nc)
+            perm_l, perm_r = rng.permutation(n_pt + nc), rng.permutation(n_pt + nc)
+            kp_l = np.concatenate([uvl, cl])[perm_l].astype(np.float32)
+            kp_r = np.concatenate([uvr, cr])[perm_r].astype(np.float32)
+            inv_l, inv_r = np.argsort(perm_l), np.argsort(perm_r)                    # rectified: identical float rows
+            kp_r[inv_r[:n_pt], 1] = kp_l[inv_l[:n_pt], 1]
+            sc, ec = sP @ Tf[:3, :3].T + Tf[:3, 3], eP @ Tf[:3, :3].T + Tf[:3, 3]
+            sl, el = projection(cam, sc) + rng.normal(0, noise_px, (n_ls, 2)), projection(cam, ec) + rng.normal(0, noise_px, (n_ls, 2))
+            sr, er = to_right(sl, sc[:, 2]), to_right(el, ec[:, 2])
+            permL, permR = rng.permutation(n_ls), rng.permutation(n_ls)
+            frames[name].append(dict(
+                kp_l=kp_l, kp_r=kp_r, poct_l=np.concatenate([octv, rng.integers(0, 4, nc).astype(np.int32)])[perm_l],
+                pdesc_l=np.concatenate([flip(dP), cdl])[perm_l], pdesc_r=np.concatenate([flip(dP), cdr])[perm_r],
+                seg_l=np.concatenate([sl, el], 1)[permL].astype(np.float32), seg_r=np.concatenate([sr, er], 1)[permR].astype(np.float32),
+                angle_l=rng.uniform(-np.pi, np.pi, n_ls).astype(np.float32), loct_l=np.zeros(n_ls, np.int32),
+                ldesc_l=flip(dL)[permL], ldesc_r=flip(dL)[permR]))
+
+    def cat(fl):
+        out = {k: np.concatenate([f[k] for f in fl]) for k in fl[0]}
+        for off, key in (("pl_off", "kp_l"), ("pr_off", "kp_r"), ("ll_off", "seg_l"), ("lr_off", "seg_r")):
+            out[off] = np.concatenate([[0], np.cumsum([len(f[key]) for f in fl])]).astype(np.int32)
+        return out
+    return cat(frames["prev"]), cat(frames["curr"]), np.stack(Ts), cam

@@ -78,6 +78,30 @@ def default_stereo_match_config() -> "PlStereoMatchConfig":
     return PlStereoMatchConfig(48, 64, 10, 1, 0.9, 0.75)
 
 
+class PlStereoFeatures(C.Structure):
+    """Raw stereo features of B frames (PlStereoFeatures, include/plstvo.h)."""
+    _fields_ = [("B", C.c_int32), ("pl_off", c_int32_p), ("pr_off", c_int32_p), ("kp_l", c_float_p), ("kp_r", c_float_p),
+                ("poct_l", c_int32_p), ("pdesc_l", c_uint8_p), ("pdesc_r", c_uint8_p), ("ll_off", c_int32_p), ("lr_off", c_int32_p),
+                ("seg_l", c_float_p), ("seg_r", c_float_p), ("angle_l", c_float_p), ("loct_l", c_int32_p), ("ldesc_l", c_uint8_p),
+                ("ldesc_r", c_uint8_p)]
+
+
+STEREO_FEATURE_DTYPES = dict(pl_off=np.int32, pr_off=np.int32, kp_l=np.float32, kp_r=np.float32, poct_l=np.int32, pdesc_l=np.uint8,
+                             pdesc_r=np.uint8, ll_off=np.int32, lr_off=np.int32, seg_l=np.float32, seg_r=np.float32,
+                             angle_l=np.float32, loct_l=np.int32, ldesc_l=np.uint8, ldesc_r=np.uint8)
+
+
+def stereo_features_as_c(d: dict):
+    """dict of arrays (keys of STEREO_FEATURE_DTYPES) -> (PlStereoFeatures, keep-alive list)."""
+    keep = {k: np.ascontiguousarray(d[k], dt) for k, dt in STEREO_FEATURE_DTYPES.items()}
+    s = PlStereoFeatures()
+    s.B = len(keep["pl_off"]) - 1
+    for k, a in keep.items():
+        typ = dict(PlStereoFeatures._fields_)[k]
+        setattr(s, k, a.ctypes.data_as(typ))
+    return s, keep
+
+
 GRID_ROWS, GRID_COLS = 48, 64     # include/stereoFrame.h:51-52
 
 

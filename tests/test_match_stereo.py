@@ -43,6 +43,34 @@ def oracle_lines(oracle, cam, mc, sc, frame):
     return m12, k, rec
 
 
+def test_oracle_fused_equals_composition(oracle):
+    """orc_match_stereo_* (cells formed in C like the reference's caller) == numpy cells + orc_match_grid_* + orc_stereo_lift_*;
+    the threaded batch returns the same counts."""
+    cam, mc, sc = T.kitti_camera(), T.default_stereo_match_config(), T.default_stereo_config()
+    pts = [SS.make_stereo_frame_points(a, b, seed=30 + i) for i, (a, b) in enumerate([(700, 650), (0, 0), (5, 0), (300, 310)])]
+    lns = [SS.make_stereo_frame_lines(a, b, seed=40 + i) for i, (a, b) in enumerate([(200, 190), (0, 3), (1, 1), (90, 95)])]
+    counts = []
+    for fp, fl in zip(pts, lns):
+        m12, k, rec = oracle.match_stereo_points(cam, mc, sc, fp[0], fp[1], fp[2], fp[3], fp[4])
+        m12b, kb, recb = oracle_points(oracle, cam, mc, sc, fp)
+        np.testing.assert_array_equal(m12, m12b)
+        assert k == kb
+        for key in KEYS_PT:
+            _same(rec[key], recb[key], key)
+        m12, k2, rec = oracle.match_stereo_lines(cam, mc, sc, fl[0], fl[1], fl[2], fl[3], fl[4], fl[5])
+        m12b, kb, recb = oracle_lines(oracle, cam, mc, sc, fl)
+        np.testing.assert_array_equal(m12, m12b)
+        assert k2 == kb
+        for key in KEYS_LS:
+            _same(rec[key], recb[key], key)
+        counts.append((k, k2))
+    pl_off, pr_off, P = _cat(pts, 0, 3)
+    ll_off, lr_off, L = _cat(lns, 0, 4)
+    got = oracle.stereo_batch(cam, mc, sc, pl_off, P[0], P[1], P[2], pr_off, P[3], P[4], ll_off, L[0], L[1], L[2], L[3], lr_off,
+                              L[4], L[5], threads=3)
+    np.testing.assert_array_equal(got, np.array(counts, np.int32))
+
+
 def _cat(frames, idx_l, idx_r):
     l_off = np.concatenate([[0], np.cumsum([len(f[idx_l]) for f in frames])]).astype(np.int32)
     r_off = np.concatenate([[0], np.cumsum([len(f[idx_r]) for f in frames])]).astype(np.int32)
@@ -172,3 +200,51 @@ def test_gpu_match_stereo_errors(engine):
     with pytest.raises(RuntimeError):
         engine.match_stereo_points(cam, mc, sc, np.array([0, 10], np.int32), kp_l2, np.zeros(10, np.int32), d1[:10],
                                    np.array([0, 200], np.int32), kp_r2, np.repeat(d2[:1], 200, 0))
+
+
+# ---------------------------------------------------------------------------- raw stereo features -> pose (records stay in HBM)
+def _oracle_frames(oracle, cam, mc, sc, d):
+    """Oracle stereo step for every frame of a PlStereoFeatures dict -> FrameBatch of the lifted records + counts."""
+    B = len(d["pl_off"]) - 1
+    recs_p, recs_l, counts = [], [], []
+    for p in range(B):
+        a, b, ar, br = d["pl_off"][p], d["pl_off"][p + 1], d["pr_off"][p], d["pr_off"][p + 1]
+        _, k, rp = oracle.match_stereo_points(cam, mc, sc, d["kp_l"][a:b], d["poct_l"][a:b], d["pdesc_l"][a:b], d["kp_r"][ar:br],
+                                              d["pdesc_r"][ar:br])
+        c, e, cr, er = d["ll_off"][p], d["ll_off"][p + 1], d["lr_off"][p], d["lr_off"][p + 1]
+        _, kl, rl = oracle.match_stereo_lines(cam, mc, sc, d["seg_l"][c:e], d["angle_l"][c:e], d["loct_l"][c:e], d["ldesc_l"][c:e],
+                                              d["seg_r"][cr:er], d["ldesc_r"][cr:er])
+        recs_p.append(rp); recs_l.append(rl); counts.append((k, kl))
+    cat = lambda recs, key: np.concatenate([r[key] for r in recs])
+    fb = T.FrameBatch(pt_off=np.concatenate([[0], np.cumsum([c[0] for c in counts])]),
+                      ls_off=np.concatenate([[0], np.cumsum([c[1] for c in counts])]),
+                      pdesc=cat(recs_p, "desc"), ldesc=cat(recs_l, "desc"), pt_P=cat(recs_p, "P"), pt_pl=cat(recs_p, "pl"),
+                      pt_sigma2=cat(recs_p, "sigma2"), ls_sP=cat(recs_l, "sP"), ls_eP=cat(recs_l, "eP"), ls_le=cat(recs_l, "le"),
+                      ls_spl=cat(recs_l, "spl"), ls_epl=cat(recs_l, "epl"), ls_sigma2=cat(recs_l, "sigma2"),
+                      ls_level=cat(recs_l, "level"))
+    return fb, np.array(counts, np.int32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,n_pt,n_ls", [(3, 900, 200), (1, 300, 0), (6, 1500, 350)])
+def test_gpu_track_stereo_batch_vs_oracle_chain(engine, oracle, B, n_pt, n_ls):
+    """plstvo_track_stereo_batch == oracle(matchStereoPoints / Lines of both frames) -> oracle(f2fTracking + optimizePose):
+    survivor counts and match counts equal, pose within 1e-9 rad / 1e-8 m, and close to the ground-truth motion."""
+    import ref_numpy as R
+    prev, curr, Tgt, cam = SS.make_stereo_pairs(B, n_pt=n_pt, n_ls=max(n_ls, 1), seed=B)
+    mc, sc, cfg = T.default_stereo_match_config(), T.default_stereo_config(), T.kitti_config()
+    if n_ls == 0:
+        cfg.has_lines = 0
+    res, n_stereo = engine.track_stereo_batch(cam, cfg, mc, sc, prev, curr)
+    fbp, cp = _oracle_frames(oracle, cam, mc, sc, prev)
+    fbc, cc = _oracle_frames(oracle, cam, mc, sc, curr)
+    np.testing.assert_array_equal(n_stereo, np.concatenate([cp, cc], 1))
+    ref = oracle.track_batch(cam, cfg, fbp, fbc)["results"]
+    for p in range(B):
+        assert res["status"][p] == ref["status"][p] and res["good"][p] == ref["good"][p] == 1
+        assert res["n_matched_pt"][p] == ref["n_matched_pt"][p] and res["n_matched_ls"][p] == ref["n_matched_ls"][p]
+        assert res["n_inliers"][p] == ref["n_inliers"][p]
+        ang, tr = R.pose_error(res["DT"][p], ref["DT"][p])
+        assert ang < 1e-9 and tr < 1e-8
+        ang, tr = R.pose_error(res["DT_opt"][p], Tgt[p])            # DT_opt: prev -> curr, like the generator's T
+        assert ang < 5e-3 and tr < 5e-2

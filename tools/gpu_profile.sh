@@ -13,6 +13,11 @@ for W in c1 c3; do
   python bench.py --workload $W --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_${W}_${TAG}.json 2>> gpurun_out/bench_${TAG}.err
 done
 tail -c 900 gpurun_out/bench_c5_${TAG}.json
+for W in stereo stereo_track; do
+  python bench.py --workload $W --steps 10 --warmup 3 > gpurun_out/bench_${W}_${TAG}.json 2>> gpurun_out/bench_${TAG}.err
+done
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_stereo_track_${TAG}.csv \
+    python bench.py --workload stereo_track --steps 1 --warmup 3 --no-cpu > /dev/null 2>&1
 # launch list of the bench command (short run): per-launch device time, compare SHARES
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu --no-hbm-run > gpurun_out/ncu_launches_${TAG}.log 2>&1

@@ -32,4 +32,6 @@ kp_l, octave, d1, kp_r, d2 = SS.make_stereo_frame_points(600, 580, seed=5)
 eng.match_stereo_points(cam, mc, sc, [0, 600], kp_l, octave, d1, [0, 580], kp_r, d2)
 seg_l, angle, octave, d1, seg_r, d2 = SS.make_stereo_frame_lines(250, 240, seed=6)
 eng.match_stereo_lines(cam, mc, sc, [0, 250], seg_l, angle, octave, d1, [0, 240], seg_r, d2)
+sp, scur, _, scam = SS.make_stereo_pairs(2, n_pt=500, n_ls=120, seed=7)
+eng.track_stereo_batch(scam, T.kitti_config(), mc, sc, sp, scur)
 print("sanitized run ok", int(out["results"]["good"].sum()))

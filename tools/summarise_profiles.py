@@ -102,7 +102,8 @@ def main():
                 rec["algorithmic_bytes_per_launch"] = 1024 * (8000 * 32 + 2000 * 64)
             json.dump(rec, open(os.path.join(PROF, f"{kname}_traffic.json"), "w"), indent=1)
     names = [f"bench_{tag}.json", f"bench_ref_{tag}.json", f"bench_c5_{tag}.json"] + \
-            [f"bench_{w}_{tag}.json" for w in ("c1", "c3")] + [f"bench_ref_{w}_{tag}.json" for w in ("c1", "c3")]
+            [f"bench_{w}_{tag}.json" for w in ("c1", "c3")] + [f"bench_ref_{w}_{tag}.json" for w in ("c1", "c3")] + \
+            [f"bench_{w}_{tag}.json" for w in ("stereo", "stereo_track")]
     for name in names:
         p = os.path.join(OUT, name)
         if os.path.exists(p):
