@@ -75,6 +75,63 @@ inline int match(Context& c, const std::vector<uint8_t>& d1, const std::vector<u
                                 best_lr_matches ? 1 : 0, matches_12.data()));
 }
 
+// StereoFrame::matchStereoPoints / matchStereoLines (src/stereoFrame.cpp:120-173, :309-398) for one frame of raw stereo
+// features: fills the frame's point / line records (and the compacted descriptor rows) exactly like the reference's loops.
+struct KeyPoints {                       // cv::KeyPoint fields the step reads
+    std::vector<float> pt;               // [n][2]
+    std::vector<int32_t> octave;         // [n]
+    std::vector<uint8_t> desc;           // [n][32]
+    int size() const { return (int)(desc.size() / 32); }
+};
+struct KeyLines {                        // KeyLine fields the step reads
+    std::vector<float> seg;              // [m][4] start / end point
+    std::vector<float> angle;            // [m]
+    std::vector<int32_t> octave;         // [m]
+    std::vector<uint8_t> desc;           // [m][32]
+    int size() const { return (int)(desc.size() / 32); }
+};
+inline int matchStereoPoints(Context& c, const PlCamera& cam, const PlStereoMatchConfig& mc, const PlStereoConfig& sc,
+                             const KeyPoints& l, const KeyPoints& r, StereoFrame& out, std::vector<double>* disp = nullptr) {
+    const int n = l.size();
+    const int32_t lo[2] = {0, n}, ro[2] = {0, r.size()};
+    std::vector<double> pl(2 * (size_t)n), d((size_t)n), P(3 * (size_t)n), s2((size_t)n);
+    std::vector<int32_t> level((size_t)n), src((size_t)n);
+    std::vector<uint8_t> desc(32 * (size_t)n);
+    int32_t k = 0;
+    c.check(plstvo_match_stereo_points(c.get(), &cam, &mc, &sc, 1, lo, l.pt.data(), l.octave.data(), l.desc.data(), ro, r.pt.data(),
+                                       r.desc.data(), nullptr, pl.data(), d.data(), P.data(), s2.data(), level.data(), desc.data(),
+                                       src.data(), &k));
+    out.pt_pl.assign(pl.begin(), pl.begin() + 2 * (size_t)k);
+    out.pt_P.assign(P.begin(), P.begin() + 3 * (size_t)k);
+    out.pt_sigma2.assign(s2.begin(), s2.begin() + k);
+    out.pdesc.assign(desc.begin(), desc.begin() + 32 * (size_t)k);
+    if (disp) disp->assign(d.begin(), d.begin() + k);
+    return k;
+}
+inline int matchStereoLines(Context& c, const PlCamera& cam, const PlStereoMatchConfig& mc, const PlStereoConfig& sc,
+                            const KeyLines& l, const KeyLines& r, StereoFrame& out) {
+    const int n = l.size();
+    const int32_t lo[2] = {0, n}, ro[2] = {0, r.size()};
+    const size_t N = (size_t)n;
+    std::vector<double> spl(2 * N), epl(2 * N), sd(N), ed(N), sP(3 * N), eP(3 * N), le(3 * N), ang(N), s2(N);
+    std::vector<int32_t> level(N), src(N);
+    std::vector<uint8_t> desc(32 * N);
+    int32_t k = 0;
+    c.check(plstvo_match_stereo_lines(c.get(), &cam, &mc, &sc, 1, lo, l.seg.data(), l.angle.data(), l.octave.data(), l.desc.data(), ro,
+                                      r.seg.data(), r.desc.data(), nullptr, spl.data(), epl.data(), sd.data(), ed.data(), sP.data(),
+                                      eP.data(), le.data(), ang.data(), s2.data(), level.data(), desc.data(), src.data(), &k));
+    const size_t K = (size_t)k;
+    out.ls_spl.assign(spl.begin(), spl.begin() + 2 * K);
+    out.ls_epl.assign(epl.begin(), epl.begin() + 2 * K);
+    out.ls_sP.assign(sP.begin(), sP.begin() + 3 * K);
+    out.ls_eP.assign(eP.begin(), eP.begin() + 3 * K);
+    out.ls_le.assign(le.begin(), le.begin() + 3 * K);
+    out.ls_sigma2.assign(s2.begin(), s2.begin() + K);
+    out.ls_level.assign(level.begin(), level.begin() + K);
+    out.ldesc.assign(desc.begin(), desc.begin() + 32 * K);
+    return k;
+}
+
 // Host-side SE(3) helpers of the key-frame test (src/auxiliar.cpp:113-122, :143-173, :175-190), row-major arrays.
 namespace se3 {
 using Mat4 = std::array<double, 16>;

@@ -457,6 +457,17 @@ std::vector<int> chunk_schedule(int B, int sm_count, bool pipelined) {
         bounds.push_back(B);
         return bounds;
     }
+    const char* list = getenv("PLSTVO_E2E_BOUNDS");         // tuning knob: explicit chunk ends, e.g. "74,293"
+    if (list && *list) {
+        for (const char* c = list; *c;) {
+            const int v = atoi(c);
+            if (v > bounds.back() && v < B) bounds.push_back(v);
+            while (*c && *c != ',') ++c;
+            if (*c == ',') ++c;
+        }
+        bounds.push_back(B);
+        return bounds;
+    }
     // ramp 1/6, 1/3, 2/3 of the SM count, then equal chunks of at most one pair per SM
     int p = 0;
     for (int c = std::max(8, sm_count / 6); c < sm_count && p + c < B; c *= 2) {

@@ -58,3 +58,33 @@ def test_cpp_handler_sequence_vs_oracle(tmp_path, oracle):
     assert got["n_matched_pt"] == ref["n_matched_pt"] and got["n_inliers"] == ref["n_inliers"]
     ang, tr = R.pose_error(np.array(got["DT"]).reshape(4, 4), ref["DT"])
     assert ang < 1e-9 and tr < 1e-8
+
+
+@pytest.mark.gpu
+def test_cpp_stereo_sequence_vs_fused_call(tmp_path):
+    """examples/stereo_cpp.cpp: raw stereo features -> matchStereoPoints / Lines per frame -> handler, in C++; must agree with
+    plstvo_track_stereo_batch on the same two frames."""
+    from stvo_pl_b200 import stereo_synth as SS
+    from stvo_pl_b200.engine import Engine
+    exe = str(tmp_path / "stereo_cpp")
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "stereo_cpp.cpp"), "-L", LIBDIR, "-lplstvo_b200", f"-Wl,-rpath,{LIBDIR}",
+                    "-o", exe], check=True)
+    prev, curr, Tgt, cam = SS.make_stereo_pairs(1, n_pt=800, n_ls=160, seed=5)
+    path = str(tmp_path / "stereo.bin")
+    with open(path, "wb") as f:
+        f.write(bytes(cam))
+        for d in (prev, curr):
+            for key, dt in (("kp_l", np.float32), ("poct_l", np.int32), ("pdesc_l", np.uint8), ("kp_r", np.float32),
+                            ("pdesc_r", np.uint8), ("seg_l", np.float32), ("angle_l", np.float32), ("loct_l", np.int32),
+                            ("ldesc_l", np.uint8), ("seg_r", np.float32), ("ldesc_r", np.uint8)):
+                _write_vec(f, d[key], dt)
+    got = json.loads(subprocess.run([exe, path], capture_output=True, text=True, check=True).stdout)
+    eng = Engine(0)
+    res, n_st = eng.track_stereo_batch(cam, T.kitti_config(), T.default_stereo_match_config(), T.default_stereo_config(), prev, curr)
+    eng.close()
+    assert got["stereo"] == [int(x) for x in n_st[0]]
+    assert got["good"] == int(res["good"][0]) == 1 and got["n_matched_pt"] == int(res["n_matched_pt"][0])
+    assert got["n_inliers"] == int(res["n_inliers"][0])
+    ang, tr = R.pose_error(np.array(got["DT"]).reshape(4, 4), res["DT"][0])
+    assert ang < 1e-12 and tr < 1e-12

@@ -248,3 +248,37 @@ def test_gpu_track_stereo_batch_vs_oracle_chain(engine, oracle, B, n_pt, n_ls):
         assert ang < 1e-9 and tr < 1e-8
         ang, tr = R.pose_error(res["DT_opt"][p], Tgt[p])            # DT_opt: prev -> curr, like the generator's T
         assert ang < 5e-3 and tr < 5e-2
+
+
+@pytest.mark.gpu
+def test_gpu_track_stereo_batch_edge_cases(engine, oracle):
+    """Frames whose stereo step leaves too few features (optimizePose's FEW_BEFORE branch), priors passed through, and the
+    error paths of the fused entry point."""
+    prev, curr, Tgt, cam = SS.make_stereo_pairs(3, n_pt=400, n_ls=60, seed=21)
+    mc, sc, cfg = T.default_stereo_match_config(), T.default_stereo_config(), T.kitti_config()
+    # pair 1: the previous frame's right-image features lie outside the image -> outside the grid (GridStructure::at's
+    # out_of_bounds list) -> no stereo match at all
+    a, b = prev["pr_off"][1], prev["pr_off"][2]
+    prev["kp_r"] = prev["kp_r"].copy()
+    prev["kp_r"][a:b, 0] -= 5000.0
+    c, e = prev["lr_off"][1], prev["lr_off"][2]
+    prev["seg_r"] = prev["seg_r"].copy()
+    prev["seg_r"][c:e, 0] -= 5000.0
+    prev["seg_r"][c:e, 2] -= 5000.0
+    pri = T.identity_priors(3)
+    pri["Tfw"][2][:3, 3] = [1.0, 2.0, 3.0]                          # chained into Tfw of pair 2 (:377)
+    res, n_st = engine.track_stereo_batch(cam, cfg, mc, sc, prev, curr, priors=pri)
+    fbp, cp = _oracle_frames(oracle, cam, mc, sc, prev)
+    fbc, cc = _oracle_frames(oracle, cam, mc, sc, curr)
+    np.testing.assert_array_equal(n_st, np.concatenate([cp, cc], 1))
+    ref = oracle.track_batch(cam, cfg, fbp, fbc, priors=pri)["results"]
+    np.testing.assert_array_equal(res["status"], ref["status"])
+    np.testing.assert_array_equal(res["n_inliers"], ref["n_inliers"])
+    assert n_st[1, 0] == 0 and n_st[1, 1] == 0 and res["status"][1] == T.ST_FEW_BEFORE and res["good"][1] == 0 and res["err_norm"][1] == -1.0
+    np.testing.assert_allclose(res["Tfw"], ref["Tfw"], atol=1e-8)
+    np.testing.assert_allclose(res["DT"], ref["DT"], atol=1e-8)
+    # errors
+    bad = dict(curr)
+    bad["pl_off"], bad["pr_off"], bad["ll_off"], bad["lr_off"] = (curr[k][:-1] for k in ("pl_off", "pr_off", "ll_off", "lr_off"))
+    with pytest.raises(RuntimeError):
+        engine.track_stereo_batch(cam, cfg, mc, sc, prev, bad)     # different numbers of frames
