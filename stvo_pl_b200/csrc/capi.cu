@@ -88,6 +88,9 @@ struct PlContext {
     int next_slot = 0;
     DevBuf scratch;        // misc (popc bench, L2 flush)
     DevBuf gn_in[8], gn_out[4];
+    // per-entry-point device arenas (context-owned: a process may hold one context per GPU)
+    DevBuf arena_grid, arena_lift_pt, arena_lift_ls, arena_stereo, arena_track_stereo;
+    DevBuf gs_in[13], gs_rec_pt, gs_rec_ls;   // resident inputs / packed records of the streamed evaluator
     void* h_staging = nullptr;   // pinned host scratch (small tables and counters that must not block the enqueueing thread)
     size_t h_staging_bytes = 0;
     cudaError_t staging(size_t bytes) {
@@ -555,6 +558,10 @@ void plstvo_destroy(PlContext* ctx) {
     ctx->scratch.release();
     for (auto& b : ctx->gn_in) b.release();
     for (auto& b : ctx->gn_out) b.release();
+    ctx->arena_grid.release(); ctx->arena_lift_pt.release(); ctx->arena_lift_ls.release();
+    ctx->arena_stereo.release(); ctx->arena_track_stereo.release();
+    for (auto& b : ctx->gs_in) b.release();
+    ctx->gs_rec_pt.release(); ctx->gs_rec_ls.release();
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->h_staging) cudaFreeHost(ctx->h_staging);
     cudaStreamDestroy(ctx->s_main);
@@ -702,7 +709,7 @@ static int match_grid_common(PlContext* ctx, bool lines, int B, int rows, int co
     const size_t o_qpairs = take(N1 * CAP * 8), o_qcount = take(N1 * 4), o_tcount = take(N2 * 4);
     const size_t o_tstart = take((N2 + B) * 4), o_tslots = take(N1 * CAP * 4), o_seen = take(N1 * CAP), o_m21 = take(N2 * 4);
     const size_t o_prob = take((size_t)B * sizeof(GridProblem));
-    static DevBuf arena;
+    DevBuf& arena = ctx->arena_grid;
     CK(ctx, arena.ensure(off));
     uint8_t* base = arena.as<uint8_t>();
     std::vector<GridProblem> probs((size_t)B);
@@ -815,7 +822,7 @@ int plstvo_stereo_lift_points(PlContext* ctx, const PlCamera* cam, const PlStere
     const size_t o_oct = a.take(N1 * 4), o_desc = a.take(N1 * 32), o_kpr = a.take(N2 * 8), o_m12 = a.take(N1 * 4);
     const size_t o_pl = a.take(N1 * 16), o_disp = a.take(N1 * 8), o_P = a.take(N1 * 24), o_s2 = a.take(N1 * 8);
     const size_t o_lvl = a.take(N1 * 4), o_dout = a.take(N1 * 32), o_src = a.take(N1 * 4), o_cnt = a.take((size_t)B * 4);
-    static DevBuf arena;
+    DevBuf& arena = ctx->arena_lift_pt;
     CK(ctx, arena.ensure(a.off));
     uint8_t* base = arena.as<uint8_t>();
     cudaStream_t s = ctx->s_main;
@@ -878,7 +885,7 @@ int plstvo_stereo_lift_lines(PlContext* ctx, const PlCamera* cam, const PlStereo
     const size_t o_ed = a.take(N1 * 8), o_sP = a.take(N1 * 24), o_eP = a.take(N1 * 24), o_le = a.take(N1 * 24);
     const size_t o_angd = a.take(N1 * 8), o_s2 = a.take(N1 * 8), o_lvl = a.take(N1 * 4), o_dout = a.take(N1 * 32);
     const size_t o_src = a.take(N1 * 4), o_cnt = a.take((size_t)B * 4);
-    static DevBuf arena;
+    DevBuf& arena = ctx->arena_lift_ls;
     CK(ctx, arena.ensure(a.off));
     uint8_t* base = arena.as<uint8_t>();
     cudaStream_t s = ctx->s_main;
@@ -974,7 +981,7 @@ int match_stereo_common(PlContext* ctx, bool lines, const PlCamera* cam, const P
     const size_t o_lvl = a.take(N1 * 4), o_dout = a.take(N1 * 32), o_src = a.take(N1 * 4), o_cnt = a.take((size_t)B * 4);
     const size_t o_epl = a.take(lines ? N1 * 16 : 0), o_edisp = a.take(lines ? N1 * 8 : 0), o_eP = a.take(lines ? N1 * 24 : 0);
     const size_t o_le = a.take(lines ? N1 * 24 : 0), o_angd = a.take(lines ? N1 * 8 : 0);
-    static DevBuf arena;
+    DevBuf& arena = ctx->arena_stereo;
     CK(ctx, arena.ensure(a.off));
     uint8_t* base = arena.as<uint8_t>();
     auto I = [&](size_t o) { return reinterpret_cast<int32_t*>(base + o); };
@@ -1136,7 +1143,7 @@ int plstvo_track_stereo_batch(PlContext* ctx, const PlCamera* cam, const PlConfi
     const size_t o_items = a.take(max_items * 4), o_qpairs = a.take(maxN1 * CAP * 8), o_qcount = a.take(maxN1 * 4);
     const size_t o_tcount = a.take(maxN2 * 4), o_tstart = a.take((maxN2 + B) * 4), o_tslots = a.take(maxN1 * CAP * 4);
     const size_t o_seen = a.take(maxN1 * CAP), o_m21 = a.take(maxN2 * 4);
-    static DevBuf arena;
+    DevBuf& arena = ctx->arena_track_stereo;
     CK(ctx, arena.ensure(a.off));
     uint8_t* base = arena.as<uint8_t>();
     auto I = [&](size_t o) { return reinterpret_cast<int32_t*>(base + o); };
@@ -1669,7 +1676,7 @@ int plstvo_gn_eval_stream(PlContext* ctx, const PlCamera* cam, const PlConfig* c
                            {m->pt_pl_obs, n * 16}, {m->pt_sigma2, n * 8}, {m->ls_sP, l * 24}, {m->ls_eP, l * 24},
                            {m->ls_le_obs, l * 24}, {m->ls_spl, l * 16}, {m->ls_epl, l * 16}, {m->ls_sigma2, l * 8},
                            {m->pt_inlier, n}, {m->ls_inlier, l}};
-    static DevBuf bufs[13];   // resident inputs of the roofline run (process lifetime)
+    DevBuf* bufs = ctx->gs_in;   // resident inputs of the roofline run (context lifetime)
     for (int i = 0; i < 13; ++i) {
         CK(ctx, bufs[i].ensure(std::max<size_t>(ups[i].bytes, 16)));
         if (ups[i].src && ups[i].bytes)
@@ -1680,7 +1687,7 @@ int plstvo_gn_eval_stream(PlContext* ctx, const PlCamera* cam, const PlConfig* c
                   bufs[6].as<double>(), bufs[7].as<double>(), bufs[8].as<double>(), bufs[9].as<double>(),
                   bufs[10].as<double>(), m->ls_inlier ? bufs[12].as<uint8_t>() : nullptr};
     // fp32-packed records (32 B per point, 64 B per line), packed once on the device
-    static DevBuf rec_pt, rec_ls;
+    DevBuf &rec_pt = ctx->gs_rec_pt, &rec_ls = ctx->gs_rec_ls;
     CK(ctx, rec_pt.ensure(std::max<size_t>(n * 32, 32)));
     CK(ctx, rec_ls.ensure(std::max<size_t>(l * 64, 64)));
     CK(ctx, launch_pack_records(md, B, (int)n, (int)l, rec_pt.as<float4>(), rec_ls.as<float4>(), s));

@@ -170,6 +170,19 @@ cudaError_t launch_gn_eval_stream(const PlCamera& cam, const PlConfig& cfg, cons
                                   const float4* pt, const float4* ls, int B, const double* DT, double* partial,
                                   int slices_per_problem, int sm_count, double* H, double* g, double* e, cudaStream_t stream);
 
+// cudaFuncSetAttribute is per device: a process may drive several GPUs (one context each), so the opted-in dynamic
+// shared-memory size is remembered per device (`done`: one slot per device ordinal, zero-initialised by the caller).
+inline cudaError_t ensure_dynamic_smem(const void* fn, size_t bytes, size_t* done /* [64] */) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    size_t& have = done[dev & 63];
+    if (bytes <= have) return cudaSuccess;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
+}
+
 // ---- PTX helpers: mbarrier + 1-D bulk async copy (TMA engine, UBLKCP in SASS) ------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

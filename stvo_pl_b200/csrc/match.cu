@@ -219,13 +219,10 @@ cudaError_t launch_hamming_knn2(const MatchProblem* problems, const MatchTile* t
                                 int max_tsplit, cudaStream_t stream) {
     if (n_tiles <= 0) return cudaSuccess;
     const size_t smem = k1_smem_bytes(max_tsplit);
-    static size_t configured = 0;
+    static size_t configured[64] = {};
     K1Fn fn = k1_variant();
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(fn), smem, configured);
+    if (e != cudaSuccess) return e;
     fn<<<n_tiles, K1_THREADS, smem, stream>>>(problems, tiles);
     return cudaGetLastError();
 }
@@ -248,11 +245,10 @@ cudaError_t launch_match_finalize(const MatchProblem* problems, int n_problems, 
                                   cudaStream_t stream) {
     if (n_problems <= 0) return cudaSuccess;
     const size_t smem = (size_t)(max_n2 > 0 ? max_n2 : 1) * sizeof(int32_t);
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(match_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static size_t configured[64] = {};
+    if (smem > 48 * 1024) {
+        cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(match_finalize_kernel), smem, configured);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     match_finalize_kernel<<<n_problems, 256, smem, stream>>>(problems, counts);
     return cudaGetLastError();

@@ -1419,12 +1419,9 @@ cudaError_t launch_algebra_selftest(const double* H, const double* g, int n, dou
 cudaError_t launch_track_solve(const SolveParams& prm, int n_pairs, cudaStream_t stream) {
     if (n_pairs <= 0) return cudaSuccess;
     const size_t smem = k2_smem_bytes(prm.cap_pt, prm.cap_ls, prm.sort_cap, prm.feat_in_smem != 0);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(track_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static size_t configured[64] = {};
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(track_solve_kernel), smem, configured);
+    if (e != cudaSuccess) return e;
     track_solve_kernel<<<n_pairs, K2_THREADS, smem, stream>>>(prm);
     return cudaGetLastError();
 }

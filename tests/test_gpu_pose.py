@@ -363,3 +363,32 @@ def test_explicit_lists_c5_size(engine, oracle):
         assert ang < 1e-3 and tr < 1e-2
     np.testing.assert_array_equal(ip, rp)
     np.testing.assert_array_equal(il, rl)
+
+
+def test_two_contexts_on_two_devices_in_one_process(oracle):
+    """One context per GPU inside a single process (device arenas and kernel attributes are per context / per device):
+    the same batch through both devices, interleaved, gives identical bytes.  Skipped on single-GPU boxes."""
+    import torch
+    from stvo_pl_b200.engine import Engine
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cfg = T.kitti_config()
+    prev, curr, _, cam = synth.make_batch("kitti", 6, n_pt=900, n_ls=220)
+    e0, e1 = Engine(0), Engine(1)
+    try:
+        a = e0.track_batch(cam, cfg, prev, curr)
+        b = e1.track_batch(cam, cfg, prev, curr)
+        a2 = e0.track_batch(cam, cfg, prev, curr)
+        assert a["results"].tobytes() == b["results"].tobytes() == a2["results"].tobytes()
+        mb, Ts, cam2 = synth.make_matched_batch("kitti", 40)
+        H0, g0, _, _ = e0.gn_eval_stream(cam2, cfg, mb, Ts, iters=1)
+        H1, g1, _, _ = e1.gn_eval_stream(cam2, cfg, mb, Ts, iters=1)
+        assert H0.tobytes() == H1.tobytes() and g0.tobytes() == g1.tobytes()
+        q_cell, d1, t_cell, d2 = __import__("stvo_pl_b200.stereo_synth", fromlist=["x"]).make_stereo_points(500, 480, seed=1)
+        w = T.PlGridWindow(10, 0, 0, 0)
+        m0 = e0.match_grid_points([0, 500], q_cell, d1, [0, 480], t_cell, d2, w, 0.75)[1]
+        m1 = e1.match_grid_points([0, 500], q_cell, d1, [0, 480], t_cell, d2, w, 0.75)[1]
+        np.testing.assert_array_equal(m0, m1)
+    finally:
+        e0.close()
+        e1.close()
