@@ -331,6 +331,15 @@ def run_ours(args):
     barrier()
     sync_s = max_over_ranks(sync_s)
     same = (pout["results"].tobytes() == out["results"].tobytes())
+    # (a') latency of one blocking call on ONE frame pair: what a per-frame caller of insertStereoPair() / optimizePose() sees
+    one_p, one_c = eng.pinned.pin_frames(prev.select([0])), eng.pinned.pin_frames(curr.select([0]))
+    one_out = eng.pinned_outputs(prev.select([0]))
+    lat = []
+    for k in range(60):
+        t1 = time.perf_counter()
+        eng.track_batch(cam, cfg, one_p, one_c, out=one_out)
+        lat.append((time.perf_counter() - t1) * 1e3)
+    single_ms = float(np.median(lat[10:]))
     # (b) the streaming call (plstvo_track_batch_async / plstvo_wait), two batches in flight: step k+1's H2D overlaps
     # step k's kernels.  Every step still uploads its inputs and reads back its results inside the timed region.
     for k in range(max(args.warmup, 3)):
@@ -369,6 +378,7 @@ def run_ours(args):
                 "mode": "plstvo_track_batch_async + plstvo_wait, 2 batches in flight (pinned host buffers)",
                 "sync_value": world * B * args.steps / sync_s, "sync_ms_per_step": sync_s / args.steps * 1e3,
                 "sync_mode": "plstvo_track_batch, one blocking call per step",
+                "single_pair_latency_ms": single_ms,
                 "h2d_only_ms_per_step": h2d_ms, "h2d_only_gbs": h2d / (h2d_ms * 1e-3) / 1e9,
                 "note": "h2d_only_*: one pinned cudaMemcpy of the step's input bytes alone (the PCIe floor of a step); the "
                         "pipelined figure hides it behind the previous batch's kernels"},
@@ -379,7 +389,15 @@ def run_ours(args):
         threads = host_threads()
         sample = max(64, 4 * threads)
         rate, secs, stage = cpu_port_rate(sample, threads)
+        from oracle.oracle import Oracle
+        _orc = Oracle(native=True)
+        _lat = []
+        for k in range(5):   # one pair, the reference's own threading inside a pair (points || lines, 1->2 || 2->1)
+            t1 = time.perf_counter()
+            _orc.track_batch(cam, cfg, prev.select([k]), curr.select([k]), faithful=True)
+            _lat.append((time.perf_counter() - t1) * 1e3)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                "single_pair_latency_ms": float(np.median(_lat)),
                                 "sample": f"{sample} frame pairs of the same workload, one pair per thread, "
                                           f"{secs:.2f} s wall ({stage.sum() / 1e3:.1f} s of CPU work)",
                                 "cpu": cpu_model(), "match_share": float(stage[0] / max(stage.sum(), 1e-9))}
