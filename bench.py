@@ -288,7 +288,11 @@ def run_ours(args):
         "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
         "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": kt["ms_match"], "ctas_per_launch": kt["n_tiles"],
         "share_of_step": kt["ms_match"] / (kt["ms_match"] + kt["ms_solve"]),
-        "note": "K1 is integer-ALU (POPC) bound, not HBM bound: see `alu`",
+        "note": "K1 is integer-ALU (POPC) bound, not HBM bound: see `alu` and `pipes`; the path's HBM-bound kernel is reported in "
+                "`roofline_hbm_kernel`",
+        "pipes": {"alu_pipe_pct_of_peak": traffic.get("alu_pipe_pct") if traffic else None,
+                  "xu_popc_pipe_pct_of_peak": traffic.get("xu_pipe_pct") if traffic else None,
+                  "source": "ncu --set full capture summarised in " + (traffic.get("capture", "profiles/") if traffic else "profiles/")},
         "alu": {"unit": "G pair-distances/s", "achieved": pair_dists / (kt["ms_match"] * 1e-3) / 1e9,
                 "peak": popc_rate / 8 / 1e9, "frac": 8 * pair_dists / (kt["ms_match"] * 1e-3) / popc_rate,
                 "peak_kind": "measured POPC issue rate (plstvo_popc_rate micro-benchmark, same process) / 8 POPC per "

@@ -97,6 +97,12 @@ def main():
             rec = {"dram_bytes_per_launch": traffic, "dram_bytes_read": num("dram__bytes_read.sum"),
                    "dram_bytes_write": num("dram__bytes_write.sum"), "capture": f"profiles/{tag}_ncu_summary.md",
                    "launch": m.get("launch__grid_size", ""), "gpu_time": m.get("gpu__time_duration.sum", "")}
+            def pct(key):
+                return float(m[key].split()[0]) if key in m else None
+            if kname == "k1":   # the pipes that actually bound the matcher (integer ALU and XU / POPC)
+                rec["alu_pipe_pct"] = pct("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed")
+                rec["xu_pipe_pct"] = pct("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_elapsed")
+                rec["issue_active_pct"] = pct("smsp__issue_active.avg.pct_of_peak_sustained_active")
             if kname == "gn":
                 rec["problems"] = 1024          # bench.py --workload c5 default
                 rec["algorithmic_bytes_per_launch"] = 1024 * (8000 * 32 + 2000 * 64)
