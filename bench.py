@@ -627,6 +627,23 @@ def run_stereo_track(args):
             "clocks": clk.summary(), "gpu_launches": int(launches),
             "e2e": {"value": B * args.steps / dt, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(res.nbytes + 16 * B)},
             "roofline": None}
+    # sequence mode: B + 1 consecutive frames -> B poses, every frame through the stereo step once (plstvo_track_stereo_sequence)
+    seq, _, scam = SS.make_stereo_sequence(B + 1, n_pt=1740, n_ls=500, seed=99)
+    seq = pin(seq)
+    sres = eng.pinned.empty((B,), T.POSE_RESULT_DTYPE)
+    for _ in range(3):
+        eng.track_stereo_sequence(scam, cfg, mc, sc, seq, results=sres)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.track_stereo_sequence(scam, cfg, mc, sc, seq, results=sres)
+    torch.cuda.synchronize()
+    dts = time.perf_counter() - t0
+    line["sequence_mode"] = {"value": B * args.steps / dts, "unit": "poses/s", "ms_per_step": dts / args.steps * 1e3,
+                             "frames_per_step": B + 1, "solved_ok": int(sres["good"].sum()),
+                             "h2d_bytes_per_step": int(sum(v.nbytes for v in seq.values())),
+                             "note": "plstvo_track_stereo_sequence: consecutive frames of one camera, each frame uploaded and "
+                                     "stereo-matched once; the Tfw chaining is a host-side scan (plstvo.hpp chainPoses)"}
     if not args.no_cpu:
         n = max(64, 2 * threads)
         rate, t_st, t_tr = cpu_rate(n)

@@ -265,6 +265,15 @@ int plstvo_track_stereo_batch(PlContext* ctx, const PlCamera* cam, const PlConfi
                               const PlStereoConfig* scfg, const PlStereoFeatures* prev, const PlStereoFeatures* curr,
                               const PlPrior* priors, PlPoseResult* results, int32_t* n_stereo);
 
+/* The same for a SEQUENCE: `frames` holds B + 1 consecutive frames, pair p = (frame p, frame p + 1), B results.  Every frame goes
+ * through the stereo step once (it is the current frame of one pair and the previous frame of the next, like curr_frame ->
+ * prev_frame in updateFrame, src/stereoFrameHandler.cpp:98-100).  Results are per pair with priors[p] as given (NULL: identity):
+ * the chaining of Tfw along the sequence (:377-378) is a host-side scan over the B results (plstvo.hpp: chainPoses).
+ * n_stereo (optional): [B + 1][2] = stereo_pt.size(), stereo_ls.size() per frame. */
+int plstvo_track_stereo_sequence(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlStereoMatchConfig* mcfg,
+                                 const PlStereoConfig* scfg, const PlStereoFeatures* frames, const PlPrior* priors,
+                                 PlPoseResult* results, int32_t* n_stereo);
+
 /* ---- include/stereoFrameHandler.h surface ----------------------------------------------------- */
 /* StereoFrameHandler::f2fTracking (src/stereoFrameHandler.cpp:106-180) for B independent
  * (prev, curr) pairs: descriptor matching for points and lines; m12_* hold problem-local indices

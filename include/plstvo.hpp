@@ -223,6 +223,31 @@ inline Mat6 sandwich(const Mat6& A, const Mat6& C) {     // A C A^T
         }
     return out;
 }
+inline Mat4 expmap(const Vec6& x) {                      // expmap_se3 (src/auxiliar.cpp:124-141): x = [t ; w]
+    const double w[3] = {x[3], x[4], x[5]};
+    const double theta = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t[3] = {x[0], x[1], x[2]};
+    if (!(theta < 0.000001)) {
+        const double s[9] = {0, -w[2] / theta, w[1] / theta, w[2] / theta, 0, -w[0] / theta, -w[1] / theta, w[0] / theta, 0};
+        double ss[9];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double acc = 0.0;
+                for (int m = 0; m < 3; ++m) acc += s[3 * i + m] * s[3 * m + j];
+                ss[3 * i + j] = acc;
+            }
+        const double sn = std::sin(theta), cs = std::cos(theta);
+        double V[9];
+        for (int k = 0; k < 9; ++k) {
+            const double id = (k % 4 == 0) ? 1.0 : 0.0;
+            R[k] = id + s[k] * sn + ss[k] * (1.0 - cs);
+            V[k] = id + s[k] * (1.0 - cs) / theta + ss[k] * (theta - sn) / theta;
+        }
+        const double t0[3] = {t[0], t[1], t[2]};
+        for (int i = 0; i < 3; ++i) t[i] = V[3 * i] * t0[0] + V[3 * i + 1] * t0[1] + V[3 * i + 2] * t0[2];
+    }
+    return Mat4{R[0], R[1], R[2], t[0], R[3], R[4], R[5], t[1], R[6], R[7], R[8], t[2], 0, 0, 0, 1};
+}
 inline Mat6 uncTinv(const Mat4& T, const Mat6& cov) { return sandwich(adjoint(inverse(T)), cov); }   // uncTinv_se3
 inline double det6(Mat6 A) {                             // Matrix6d::determinant (partial-pivot LU)
     double det = 1.0;
@@ -244,6 +269,34 @@ inline double det6(Mat6 A) {                             // Matrix6d::determinan
     return det;
 }
 }  // namespace se3
+
+// Chains the per-pair results of plstvo_track_stereo_sequence (or of any batch of consecutive pairs solved with identity
+// priors) into world poses exactly like optimizePose's tail does frame after frame (src/stereoFrameHandler.cpp:377-378, :388-389):
+//   good pair: Tfw_k = expmap(logmap(Tfw_{k-1} DT_k)),  Tfw_cov_k = Tfw_cov_{k-1} + Ad(Tfw_{k-1}) DT_cov_k Ad(Tfw_{k-1})^T
+//   failed   : Tfw_k = Tfw_{k-1},                       Tfw_cov_k = Tfw_cov_{k-1}
+// Tfw0 / cov0: pose and covariance of the first frame (initialize(): identity, identity).  Writes results[k].Tfw / Tfw_cov.
+inline void chainPoses(PlPoseResult* results, int n, se3::Mat4 Tfw0 = se3::identity4(), se3::Mat6 cov0 = [] {
+                           se3::Mat6 c{};
+                           for (int i = 0; i < 6; ++i) c[7 * i] = 1.0;
+                           return c;
+                       }()) {
+    se3::Mat4 T = Tfw0;
+    se3::Mat6 cov = cov0;
+    for (int k = 0; k < n; ++k) {
+        PlPoseResult& r = results[k];
+        if (r.good) {
+            se3::Mat4 DT;
+            se3::Mat6 dc;
+            std::copy(r.DT, r.DT + 16, DT.begin());
+            std::copy(r.DT_cov, r.DT_cov + 36, dc.begin());
+            const se3::Mat6 add = se3::sandwich(se3::adjoint(T), dc);
+            for (int i = 0; i < 36; ++i) cov[i] += add[i];
+            T = se3::expmap(se3::logmap(se3::mul(T, DT)));
+        }
+        std::copy(T.begin(), T.end(), r.Tfw);
+        std::copy(cov.begin(), cov.end(), r.Tfw_cov);
+    }
+}
 
 // The Config values of the handler's host-side state machine (adaptive FAST threshold, key-frame test):
 // include/config.h:42-44, :56, :76-80, :100; defaults src/config.cpp:40-42, :52, :72-76, :102.

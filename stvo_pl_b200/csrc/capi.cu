@@ -1096,23 +1096,30 @@ int plstvo_match_stereo_lines(PlContext* ctx, const PlCamera* cam, const PlStere
 }
 
 // ---- raw stereo features -> pose, records resident in HBM ---------------------------------------------------------
-int plstvo_track_stereo_batch(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlStereoMatchConfig* mc,
-                              const PlStereoConfig* sc, const PlStereoFeatures* prev, const PlStereoFeatures* curr,
-                              const PlPrior* priors, PlPoseResult* results, int32_t* n_stereo) {
+// sequence == false: B independent (prev, curr) pairs, four feature sets of B frames.
+// sequence == true : prev holds NF = B + 1 consecutive frames, pair p = (frame p, frame p + 1); two feature sets of NF frames,
+//                    every frame goes through the stereo step once and is lifted twice (as a previous and as a current frame).
+static int track_stereo_common(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlStereoMatchConfig* mc,
+                               const PlStereoConfig* sc, const PlStereoFeatures* prev, const PlStereoFeatures* curr,
+                               const PlPrior* priors, PlPoseResult* results, int32_t* n_stereo, bool sequence) {
     if (!ctx) return PLSTVO_E_INVALID;
-    if (!cam || !cfg || !mc || !sc || !prev || !curr || !results) return fail(ctx, PLSTVO_E_INVALID, "null argument");
-    const int B = prev->B;
-    if (B < 0 || curr->B != B) return fail(ctx, PLSTVO_E_SIZE, "prev and curr hold different numbers of frames");
+    if (!cam || !cfg || !mc || !sc || !prev || (!sequence && !curr) || !results) return fail(ctx, PLSTVO_E_INVALID, "null argument");
+    const int NF = prev->B;                         // frames per feature set
+    const int B = sequence ? NF - 1 : NF;           // pairs
+    if (NF < 0 || (!sequence && curr->B != NF)) return fail(ctx, PLSTVO_E_SIZE, "prev and curr hold different numbers of frames");
+    if (sequence && NF == 1) return 0;              // one frame: nothing to track
     const int rows = mc->grid_rows, cols = mc->grid_cols;
     if (rows <= 0 || cols <= 0 || rows * cols > 8192 || cam->width <= 0 || cam->height <= 0)
         return fail(ctx, PLSTVO_E_INVALID, "bad grid or image size");
-    if (B == 0) return 0;
+    if (NF == 0) return 0;
     CK(ctx, cudaSetDevice(ctx->device));
     constexpr int CAP = 128;
+    const int NSETS = sequence ? 2 : 4;
+    if (sequence) curr = prev;                      // sets 2, 3 below are unused
     // the four feature sets: {prev, curr} x {points, lines}
     struct Set {
         bool lines; const int32_t *l_off, *r_off; const float *xy_l, *xy_r, *ang; const int32_t* oct; const uint8_t *d1, *d2;
-        size_t N1, N2, o_loff, o_roff, o_xyl, o_xyr, o_ang, o_oct, o_d1, o_d2, o_m12, o_cnt, o_gcnt, o_ooff, o_prob;
+        size_t N1, N2, o_loff, o_roff, o_xyl, o_xyr, o_ang, o_oct, o_d1, o_d2, o_m12, o_cnt, o_gcnt, o_ooff, o_ooff2, o_prob;
     };
     Set sets[4] = {
         {false, prev->pl_off, prev->pr_off, prev->kp_l, prev->kp_r, nullptr, prev->poct_l, prev->pdesc_l, prev->pdesc_r},
@@ -1121,19 +1128,21 @@ int plstvo_track_stereo_batch(PlContext* ctx, const PlCamera* cam, const PlConfi
         {true, curr->ll_off, curr->lr_off, curr->seg_l, curr->seg_r, curr->angle_l, curr->loct_l, curr->ldesc_l, curr->ldesc_r}};
     LiftArena a;
     size_t maxN1 = 0, maxN2 = 0, max_items = 0;
-    for (Set& st : sets) {
-        int rc = lift_check_offsets(ctx, B, st.l_off, st.r_off);
+    for (int k = 0; k < NSETS; ++k) {
+        Set& st = sets[k];
+        int rc = lift_check_offsets(ctx, NF, st.l_off, st.r_off);
         if (rc) return rc;
-        st.N1 = st.l_off[B];
-        st.N2 = st.r_off[B];
+        st.N1 = st.l_off[NF];
+        st.N2 = st.r_off[NF];
         if (st.N1 && (!st.xy_l || !st.oct || !st.d1 || (st.lines && !st.ang))) return fail(ctx, PLSTVO_E_INVALID, "null input array");
         if (st.N2 && (!st.xy_r || !st.d2)) return fail(ctx, PLSTVO_E_INVALID, "null input array");
         const int cw = st.lines ? 4 : 2;
-        st.o_loff = a.take((size_t)(B + 1) * 4); st.o_roff = a.take((size_t)(B + 1) * 4);
+        st.o_loff = a.take((size_t)(NF + 1) * 4); st.o_roff = a.take((size_t)(NF + 1) * 4);
         st.o_xyl = a.take(st.N1 * cw * 4); st.o_xyr = a.take(st.N2 * cw * 4); st.o_ang = a.take(st.lines ? st.N1 * 4 : 0);
         st.o_oct = a.take(st.N1 * 4); st.o_d1 = a.take(st.N1 * 32); st.o_d2 = a.take(st.N2 * 32); st.o_m12 = a.take(st.N1 * 4);
-        st.o_cnt = a.take((size_t)B * 4); st.o_gcnt = a.take((size_t)B * 4); st.o_ooff = a.take((size_t)(B + 1) * 4);
-        st.o_prob = a.take((size_t)B * sizeof(GridProblem));
+        st.o_cnt = a.take((size_t)NF * 4); st.o_gcnt = a.take((size_t)NF * 4); st.o_ooff = a.take((size_t)(NF + 1) * 4);
+        st.o_ooff2 = a.take((size_t)(NF + 1) * 4);
+        st.o_prob = a.take((size_t)NF * sizeof(GridProblem));
         maxN1 = std::max(maxN1, st.N1);
         maxN2 = std::max(maxN2, st.N2);
         max_items = std::max(max_items, st.N2 * (st.lines ? (size_t)std::max(rows, cols) + 2 : 1));
@@ -1141,7 +1150,7 @@ int plstvo_track_stereo_batch(PlContext* ctx, const PlCamera* cam, const PlConfi
     // matchGrid scratch, shared by the four sets (they run one after the other on one stream)
     const size_t o_qcell = a.take(maxN1 * 16), o_tcell = a.take(maxN2 * 8), o_tline = a.take(maxN2 * 32), o_tdir = a.take(maxN2 * 16);
     const size_t o_items = a.take(max_items * 4), o_qpairs = a.take(maxN1 * CAP * 8), o_qcount = a.take(maxN1 * 4);
-    const size_t o_tcount = a.take(maxN2 * 4), o_tstart = a.take((maxN2 + B) * 4), o_tslots = a.take(maxN1 * CAP * 4);
+    const size_t o_tcount = a.take(maxN2 * 4), o_tstart = a.take((maxN2 + NF) * 4), o_tslots = a.take(maxN1 * CAP * 4);
     const size_t o_seen = a.take(maxN1 * CAP), o_m21 = a.take(maxN2 * 4);
     DevBuf& arena = ctx->arena_track_stereo;
     CK(ctx, arena.ensure(a.off));
@@ -1160,18 +1169,18 @@ int plstvo_track_stereo_batch(PlContext* ctx, const PlCamera* cam, const PlConfi
     const GridParams gprm{rows, cols, CAP, mc->best_lr_matches ? 1 : 0, PlGridWindow{mc->matching_s_ws, 0, 0, 0}, mc->min_ratio_12_p,
                           mc->line_sim_th};
     // pinned staging: 4 problem tables + 2 x 4 x B counters (pageable copies would block this thread on the stream)
-    const size_t prob_bytes = ((size_t)B * sizeof(GridProblem) + 255) / 256 * 256;
-    CK(ctx, ctx->staging(4 * prob_bytes + (size_t)8 * B * 4));
+    const size_t prob_bytes = ((size_t)NF * sizeof(GridProblem) + 255) / 256 * 256;
+    CK(ctx, ctx->staging(4 * prob_bytes + (size_t)8 * NF * 4));
     uint8_t* hst = static_cast<uint8_t*>(ctx->h_staging);
     int32_t* cnt = reinterpret_cast<int32_t*>(hst + 4 * prob_bytes);
-    int32_t* gcnt = cnt + (size_t)4 * B;
+    int32_t* gcnt = cnt + (size_t)4 * NF;
     // ---- pass 1: cells -> matchGrid -> lifting filters (count only) per set ----
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < NSETS; ++k) {
         Set& st = sets[k];
         const int cw = st.lines ? 4 : 2;
         const size_t per_train_cells = st.lines ? (size_t)std::max(rows, cols) + 2 : 1;
         GridProblem* probs = reinterpret_cast<GridProblem*>(hst + (size_t)k * prob_bytes);
-        for (int p = 0; p < B; ++p) {
+        for (int p = 0; p < NF; ++p) {
             GridProblem& g = probs[p];
             const size_t qa = st.l_off[p], tb = st.r_off[p];
             g.n1 = st.l_off[p + 1] - st.l_off[p];
@@ -1193,51 +1202,61 @@ int plstvo_track_stereo_batch(PlContext* ctx, const PlCamera* cam, const PlConfi
             g.seen = base + o_seen + qa * CAP;
             g.m21 = I(o_m21) + tb;
         }
-        CK(ctx, up(st.o_loff, st.l_off, (size_t)(B + 1) * 4));
-        CK(ctx, up(st.o_roff, st.r_off, (size_t)(B + 1) * 4));
+        CK(ctx, up(st.o_loff, st.l_off, (size_t)(NF + 1) * 4));
+        CK(ctx, up(st.o_roff, st.r_off, (size_t)(NF + 1) * 4));
         CK(ctx, up(st.o_xyl, st.xy_l, st.N1 * cw * 4));
         CK(ctx, up(st.o_xyr, st.xy_r, st.N2 * cw * 4));
         if (st.lines) CK(ctx, up(st.o_ang, st.ang, st.N1 * 4));
         CK(ctx, up(st.o_oct, st.oct, st.N1 * 4));
         CK(ctx, up(st.o_d1, st.d1, st.N1 * 32));
         CK(ctx, up(st.o_d2, st.d2, st.N2 * 32));
-        CK(ctx, up(st.o_prob, probs, (size_t)B * sizeof(GridProblem)));
+        CK(ctx, up(st.o_prob, probs, (size_t)NF * sizeof(GridProblem)));
         cudaEvent_t uploaded = next_event(ctx);
         CK(ctx, cudaEventRecord(uploaded, sh));
         CK(ctx, cudaStreamWaitEvent(s, uploaded, 0));
         if (st.lines) {
             CK(ctx, launch_stereo_cells_lines((int)st.N1, (int)st.N2, inv_w, inv_h, F(st.o_xyl), F(st.o_xyr), I(o_qcell), D(o_tline),
                                               D(o_tdir), s));
-            CK(ctx, launch_match_grid(reinterpret_cast<GridProblem*>(base + st.o_prob), B, gprm, true, s));
-            CK(ctx, launch_lift_lines(*cam, *sc, B, I(st.o_loff), F(st.o_xyl), F(st.o_ang), I(st.o_oct), base + st.o_d1, I(st.o_roff),
+            CK(ctx, launch_match_grid(reinterpret_cast<GridProblem*>(base + st.o_prob), NF, gprm, true, s));
+            CK(ctx, launch_lift_lines(*cam, *sc, NF, I(st.o_loff), F(st.o_xyl), F(st.o_ang), I(st.o_oct), base + st.o_d1, I(st.o_roff),
                                       F(st.o_xyr), I(st.o_m12), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                                       nullptr, nullptr, nullptr, nullptr, I(st.o_cnt), s));
         } else {
             CK(ctx, launch_stereo_cells_points((int)st.N1, (int)st.N2, inv_w, inv_h, F(st.o_xyl), F(st.o_xyr), I(o_qcell), I(o_tcell), s));
-            CK(ctx, launch_match_grid(reinterpret_cast<GridProblem*>(base + st.o_prob), B, gprm, false, s));
-            CK(ctx, launch_lift_points(*cam, *sc, B, I(st.o_loff), F(st.o_xyl), I(st.o_oct), base + st.o_d1, I(st.o_roff), F(st.o_xyr),
+            CK(ctx, launch_match_grid(reinterpret_cast<GridProblem*>(base + st.o_prob), NF, gprm, false, s));
+            CK(ctx, launch_lift_points(*cam, *sc, NF, I(st.o_loff), F(st.o_xyl), I(st.o_oct), base + st.o_d1, I(st.o_roff), F(st.o_xyr),
                                        I(st.o_m12), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, I(st.o_cnt), s));
         }
         ctx->launches += 3;
-        CK(ctx, cudaMemcpyAsync(cnt + (size_t)k * B, base + st.o_cnt, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-        CK(ctx, cudaMemcpyAsync(gcnt + (size_t)k * B, base + st.o_gcnt, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+        CK(ctx, cudaMemcpyAsync(cnt + (size_t)k * NF, base + st.o_cnt, (size_t)NF * 4, cudaMemcpyDeviceToHost, s));
+        CK(ctx, cudaMemcpyAsync(gcnt + (size_t)k * NF, base + st.o_gcnt, (size_t)NF * 4, cudaMemcpyDeviceToHost, s));
     }
     CK(ctx, cudaStreamSynchronize(s));     // the one host hop: survivor counts -> compact offsets and the matcher's tile plan
-    std::vector<int32_t> ooff[4];
-    for (int k = 0; k < 4; ++k) {
-        ooff[k].assign((size_t)B + 1, 0);
-        for (int p = 0; p < B; ++p) {
-            if (gcnt[(size_t)k * B + p] < 0) return fail(ctx, gcnt[(size_t)k * B + p], "matchGrid: more than 128 candidates in one query window");
-            ooff[k][p + 1] = ooff[k][p] + cnt[(size_t)k * B + p];
-            if (n_stereo) n_stereo[(size_t)p * 4 + k] = cnt[(size_t)k * B + p];
+    // compact offsets per set; in sequence mode the current-frame role of a set starts at its second frame
+    std::vector<int32_t> ooff[4], ooff2[2];
+    for (int k = 0; k < NSETS; ++k) {
+        ooff[k].assign((size_t)NF + 1, 0);
+        for (int p = 0; p < NF; ++p) {
+            if (gcnt[(size_t)k * NF + p] < 0) return fail(ctx, gcnt[(size_t)k * NF + p], "matchGrid: more than 128 candidates in one query window");
+            ooff[k][p + 1] = ooff[k][p] + cnt[(size_t)k * NF + p];
+            if (n_stereo) {
+                if (sequence) n_stereo[(size_t)p * 2 + k] = cnt[(size_t)k * NF + p];
+                else n_stereo[(size_t)p * 4 + k] = cnt[(size_t)k * NF + p];
+            }
         }
-        CK(ctx, up(sets[k].o_ooff, ooff[k].data(), (size_t)(B + 1) * 4));
+        CK(ctx, up(sets[k].o_ooff, ooff[k].data(), (size_t)(NF + 1) * 4));
+        if (sequence) {
+            ooff2[k].assign((size_t)NF, 0);          // frames 1 .. NF - 1 as current frames: offsets relative to frame 1
+            for (int p = 0; p < NF; ++p) ooff2[k][p] = ooff[k][p + 1] - ooff[k][1];
+            CK(ctx, up(sets[k].o_ooff2, ooff2[k].data(), (size_t)NF * 4));
+        }
     }
     // ---- the tracker's plan on the compact lists; the records are written straight into its buffers ----
     PlFrameBatch fp{}, fc{};
     fp.B = fc.B = B;
     fp.pt_off = ooff[0].data(); fp.ls_off = ooff[1].data();
-    fc.pt_off = ooff[2].data(); fc.ls_off = ooff[3].data();
+    fc.pt_off = sequence ? ooff2[0].data() : ooff[2].data();
+    fc.ls_off = sequence ? ooff2[1].data() : ooff[3].data();
     Workspace& ws = ctx->ws;
     int rc = ws_prepare(ctx, ws, cam, cfg, &fp, &fc, true, priors != nullptr);
     if (rc) return rc;
@@ -1245,31 +1264,38 @@ int plstvo_track_stereo_batch(PlContext* ctx, const PlCamera* cam, const PlConfi
     cudaEvent_t planned = next_event(ctx);
     CK(ctx, cudaEventRecord(planned, ctx->s_h2d));
     CK(ctx, cudaStreamWaitEvent(s, planned, 0));
-    // pass 2: the same lifting kernels, now writing at the compact offsets (prev: P, sigma2, segments, level; curr: pl, le)
-    {
-        const Set& st = sets[0];
-        CK(ctx, launch_lift_points(*cam, *sc, B, I(st.o_loff), F(st.o_xyl), I(st.o_oct), base + st.o_d1, I(st.o_roff), F(st.o_xyr),
-                                   I(st.o_m12), nullptr, nullptr, ws.d_ptP.as<double>(), ws.d_pts2.as<double>(), nullptr,
-                                   ws.d_pdesc1.as<uint8_t>(), nullptr, I(st.o_cnt), s, I(st.o_ooff)));
-    }
-    {
-        const Set& st = sets[1];
-        CK(ctx, launch_lift_lines(*cam, *sc, B, I(st.o_loff), F(st.o_xyl), F(st.o_ang), I(st.o_oct), base + st.o_d1, I(st.o_roff),
-                                  F(st.o_xyr), I(st.o_m12), ws.d_lsspl.as<double>(), ws.d_lsepl.as<double>(), nullptr, nullptr,
-                                  ws.d_lssP.as<double>(), ws.d_lseP.as<double>(), nullptr, nullptr, ws.d_lss2.as<double>(),
-                                  ws.d_lslev.as<int32_t>(), ws.d_ldesc1.as<uint8_t>(), nullptr, I(st.o_cnt), s, I(st.o_ooff)));
-    }
-    {
-        const Set& st = sets[2];
-        CK(ctx, launch_lift_points(*cam, *sc, B, I(st.o_loff), F(st.o_xyl), I(st.o_oct), base + st.o_d1, I(st.o_roff), F(st.o_xyr),
-                                   I(st.o_m12), ws.d_ptpl.as<double>(), nullptr, nullptr, nullptr, nullptr, ws.d_pdesc2.as<uint8_t>(),
-                                   nullptr, I(st.o_cnt), s, I(st.o_ooff)));
-    }
-    {
-        const Set& st = sets[3];
-        CK(ctx, launch_lift_lines(*cam, *sc, B, I(st.o_loff), F(st.o_xyl), F(st.o_ang), I(st.o_oct), base + st.o_d1, I(st.o_roff),
-                                  F(st.o_xyr), I(st.o_m12), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ws.d_lsle.as<double>(),
-                                  nullptr, nullptr, nullptr, ws.d_ldesc2.as<uint8_t>(), nullptr, I(st.o_cnt), s, I(st.o_ooff)));
+    // pass 2: the same lifting kernels, now writing at the compact offsets (prev role: P, sigma2, segments, level; curr role: pl, le).
+    // `first` = first frame of the role inside its set (sequence mode: the current-frame role starts at frame 1).
+    auto lift_prev_points = [&](const Set& st) -> cudaError_t {
+        return launch_lift_points(*cam, *sc, B, I(st.o_loff), F(st.o_xyl), I(st.o_oct), base + st.o_d1, I(st.o_roff), F(st.o_xyr),
+                                  I(st.o_m12), nullptr, nullptr, ws.d_ptP.as<double>(), ws.d_pts2.as<double>(), nullptr,
+                                  ws.d_pdesc1.as<uint8_t>(), nullptr, I(st.o_cnt), s, I(st.o_ooff));
+    };
+    auto lift_prev_lines = [&](const Set& st) -> cudaError_t {
+        return launch_lift_lines(*cam, *sc, B, I(st.o_loff), F(st.o_xyl), F(st.o_ang), I(st.o_oct), base + st.o_d1, I(st.o_roff),
+                                 F(st.o_xyr), I(st.o_m12), ws.d_lsspl.as<double>(), ws.d_lsepl.as<double>(), nullptr, nullptr,
+                                 ws.d_lssP.as<double>(), ws.d_lseP.as<double>(), nullptr, nullptr, ws.d_lss2.as<double>(),
+                                 ws.d_lslev.as<int32_t>(), ws.d_ldesc1.as<uint8_t>(), nullptr, I(st.o_cnt), s, I(st.o_ooff));
+    };
+    auto lift_curr_points = [&](const Set& st, int first, size_t o_out) -> cudaError_t {
+        return launch_lift_points(*cam, *sc, B, I(st.o_loff) + first, F(st.o_xyl), I(st.o_oct), base + st.o_d1, I(st.o_roff) + first,
+                                  F(st.o_xyr), I(st.o_m12), ws.d_ptpl.as<double>(), nullptr, nullptr, nullptr, nullptr,
+                                  ws.d_pdesc2.as<uint8_t>(), nullptr, I(st.o_cnt) + first, s, I(o_out));
+    };
+    auto lift_curr_lines = [&](const Set& st, int first, size_t o_out) -> cudaError_t {
+        return launch_lift_lines(*cam, *sc, B, I(st.o_loff) + first, F(st.o_xyl), F(st.o_ang), I(st.o_oct), base + st.o_d1,
+                                 I(st.o_roff) + first, F(st.o_xyr), I(st.o_m12), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                 ws.d_lsle.as<double>(), nullptr, nullptr, nullptr, ws.d_ldesc2.as<uint8_t>(), nullptr,
+                                 I(st.o_cnt) + first, s, I(o_out));
+    };
+    CK(ctx, lift_prev_points(sets[0]));
+    CK(ctx, lift_prev_lines(sets[1]));
+    if (sequence) {
+        CK(ctx, lift_curr_points(sets[0], 1, sets[0].o_ooff2));
+        CK(ctx, lift_curr_lines(sets[1], 1, sets[1].o_ooff2));
+    } else {
+        CK(ctx, lift_curr_points(sets[2], 0, sets[2].o_ooff));
+        CK(ctx, lift_curr_lines(sets[3], 0, sets[3].o_ooff));
     }
     ctx->launches += 4;
     rc = ws_launch_match(ctx, ws, 0, B, s);
@@ -1279,6 +1305,18 @@ int plstvo_track_stereo_batch(PlContext* ctx, const PlCamera* cam, const PlConfi
     CK(ctx, cudaMemcpyAsync(results, ws.d_results.p, (size_t)B * sizeof(PlPoseResult), cudaMemcpyDeviceToHost, s));
     CK(ctx, cudaStreamSynchronize(s));
     return 0;
+}
+
+int plstvo_track_stereo_batch(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlStereoMatchConfig* mc,
+                              const PlStereoConfig* sc, const PlStereoFeatures* prev, const PlStereoFeatures* curr,
+                              const PlPrior* priors, PlPoseResult* results, int32_t* n_stereo) {
+    return track_stereo_common(ctx, cam, cfg, mc, sc, prev, curr, priors, results, n_stereo, false);
+}
+
+int plstvo_track_stereo_sequence(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlStereoMatchConfig* mc,
+                                 const PlStereoConfig* sc, const PlStereoFeatures* frames, const PlPrior* priors,
+                                 PlPoseResult* results, int32_t* n_stereo) {
+    return track_stereo_common(ctx, cam, cfg, mc, sc, frames, nullptr, priors, results, n_stereo, true);
 }
 
 // ---- stereoFrameHandler.h surface ------------------------------------------------------------------------

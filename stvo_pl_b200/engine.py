@@ -59,6 +59,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
                                                 i32p, u8p, i32p, i32p]),
         "plstvo_track_stereo_batch": (C.c_int, [vp, cam, cfg, C.POINTER(T.PlStereoMatchConfig), C.POINTER(T.PlStereoConfig),
                                                 C.POINTER(T.PlStereoFeatures), C.POINTER(T.PlStereoFeatures), vp, vp, i32p]),
+        "plstvo_track_stereo_sequence": (C.c_int, [vp, cam, cfg, C.POINTER(T.PlStereoMatchConfig), C.POINTER(T.PlStereoConfig),
+                                                   C.POINTER(T.PlStereoFeatures), vp, vp, i32p]),
         "plstvo_f2f_tracking": (C.c_int, [vp, cfg, fb, fb, i32p, i32p, i32p]),
         "plstvo_optimize_pose": (C.c_int, [vp, cam, cfg, mb, vp, vp, u8p, u8p]),
         "plstvo_track_batch": (C.c_int, [vp, cam, cfg, fb, fb, vp, vp, i32p, i32p, u8p, u8p]),
@@ -89,7 +91,7 @@ EXPORTED_SYMBOLS = [
     "plstvo_kitti_config", "plstvo_match_nnr", "plstvo_match", "plstvo_match_batch", "plstvo_match_grid_points",
     "plstvo_match_grid_lines", "plstvo_default_stereo_config", "plstvo_stereo_lift_points", "plstvo_stereo_lift_lines",
     "plstvo_default_stereo_match_config", "plstvo_match_stereo_points", "plstvo_match_stereo_lines", "plstvo_track_stereo_batch",
-    "plstvo_f2f_tracking",
+    "plstvo_track_stereo_sequence", "plstvo_f2f_tracking",
     "plstvo_optimize_pose", "plstvo_track_batch", "plstvo_track_batch_async", "plstvo_wait", "plstvo_batch_upload", "plstvo_batch_run",
     "plstvo_batch_run_timed", "plstvo_batch_download", "plstvo_batch_free", "plstvo_synchronize",
     "plstvo_host_alloc", "plstvo_host_free", "plstvo_launch_count", "plstvo_batch_kernel_times",
@@ -393,6 +395,20 @@ class Engine:
                                                     C.byref(cs), priors.ctypes.data if priors is not None else None,
                                                     results.ctypes.data, _p(n_stereo, T.c_int32_p)))
         del keep_p, keep_c
+        return results, n_stereo
+
+    def track_stereo_sequence(self, cam, cfg, mcfg, scfg, frames: dict, priors=None, results=None):
+        """NF consecutive frames of raw stereo features -> NF - 1 poses (pair p = frames p, p + 1); every frame goes through the
+        stereo step once.  Returns (results, n_stereo[NF, 2])."""
+        fs, keep = T.stereo_features_as_c(frames)
+        NF = fs.B
+        if results is None:
+            results = np.zeros(max(NF - 1, 0), dtype=T.POSE_RESULT_DTYPE)
+        n_stereo = np.zeros((NF, 2), np.int32)
+        self._ck(self.lib.plstvo_track_stereo_sequence(self.ctx, C.byref(cam), C.byref(cfg), C.byref(mcfg), C.byref(scfg),
+                                                       C.byref(fs), priors.ctypes.data if priors is not None else None,
+                                                       results.ctypes.data, _p(n_stereo, T.c_int32_p)))
+        del keep
         return results, n_stereo
 
     # ---- stereoFrameHandler.h surface ----

@@ -80,6 +80,22 @@ def _logmap_se3(T):
     return np.concatenate([np.linalg.solve(V, T[:3, 3]), w])
 
 
+def chain_poses(results, Tfw0=None, cov0=None):
+    """World poses of a sequence from per-pair results solved with identity priors (plstvo_track_stereo_sequence), chained like
+    optimizePose's tail (src/stereoFrameHandler.cpp:377-378, :388-389).  Writes results["Tfw"], results["Tfw_cov"] in place."""
+    from .synth import expmap_se3
+    T_ = np.eye(4) if Tfw0 is None else np.asarray(Tfw0, float).reshape(4, 4).copy()
+    cov = np.eye(6) if cov0 is None else np.asarray(cov0, float).reshape(6, 6).copy()
+    for k in range(len(results)):
+        if results["good"][k]:
+            A = _adjoint_se3(T_)
+            cov = cov + A @ results["DT_cov"][k].reshape(6, 6) @ A.T
+            T_ = expmap_se3(_logmap_se3(T_ @ results["DT"][k].reshape(4, 4)))
+        results["Tfw"][k] = T_
+        results["Tfw_cov"][k] = cov
+    return results
+
+
 class KeyframeTest:
     """needNewKF / currFrameIsKF (src/stereoFrameHandler.cpp:1136-1218; state include/stereoFrameHandler.h:81-86)."""
     K_ENTROPY = 3.0 * (1.0 + np.log(2.0 * np.arccos(-1.0)))

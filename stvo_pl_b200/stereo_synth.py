@@ -259,3 +259,82 @@ def make_stereo_pairs(B, n_pt=1200, n_ls=300, seed=0, clutter=0.15, bitflip=0.06
             out[off] = np.concatenate([[0], np.cumsum([len(f[key]) for f in fl])]).astype(np.int32)
         return out
     return cat(frames["prev"]), cat(frames["curr"]), np.stack(Ts), cam
+
+
+def make_stereo_sequence(NF, n_pt=1200, n_ls=300, seed=0, clutter=0.15, bitflip=0.06, noise_px=0.3):
+    """NF consecutive stereo frames of one static scene seen from a camera moving forward (PlStereoFeatures fields, frames
+    concatenated).  Returns (frames, T_rel[NF - 1, 4, 4], cam): T_rel[k] maps frame k's camera coordinates to frame k + 1's."""
+    from .synth import expmap_se3, kitti_camera, projection
+    cam = kitti_camera()
+    W, H = cam.width, cam.height
+    rng = np.random.default_rng(seed)
+
+    def flip(d):
+        return d ^ np.packbits(rng.random((len(d), 32, 8)) < bitflip, axis=2).reshape(len(d), 32)
+
+    # a corridor of points and segments along the camera's path (frame 0 coordinates), long enough for NF frames of 0.5 m
+    total = 62.0 + 0.5 * NF
+    n_pool = int(n_pt * total / 28.0) + 64
+    P = np.stack([rng.uniform(-40, 40, n_pool), rng.uniform(-12, 12, n_pool), rng.uniform(3.0, total, n_pool)], 1)
+    dP, octv = rng.integers(0, 256, (n_pool, 32), dtype=np.uint8), rng.integers(0, 4, n_pool).astype(np.int32)
+    l_pool = int(n_ls * total / 14.0) + 64
+    sP = np.stack([rng.uniform(-25, 25, l_pool), rng.uniform(-8, 8, l_pool), rng.uniform(5.0, total, l_pool)], 1)
+    ang, ln = rng.uniform(0.4, np.pi - 0.4, l_pool), rng.uniform(0.5, 2.5, l_pool)                # metres, never horizontal
+    eP = sP + np.stack([ln * np.cos(ang), ln * np.sin(ang), rng.normal(0, 0.2, l_pool)], 1)
+    dL = rng.integers(0, 256, (l_pool, 32), dtype=np.uint8)
+    T_abs, rel, frames = np.eye(4), [], []
+    for k in range(NF):
+        if k:
+            # bounded absolute pose (the camera stays inside the corridor however long the sequence is): forward 0.5 m per frame,
+            # a gentle lateral weave, small independent attitude jitter
+            cam_pos = np.array([0.4 * np.sin(k / 9.0), 0.08 * np.sin(k / 5.0), 0.5 * k]) + rng.normal(0, 0.01, 3)
+            Rwc = expmap_se3(np.concatenate([np.zeros(3), rng.normal(0, 0.006, 3)]))[:3, :3]      # camera -> world
+            T_new = np.eye(4)
+            T_new[:3, :3], T_new[:3, 3] = Rwc.T, -Rwc.T @ cam_pos                               # world -> camera
+            rel.append(T_new @ np.linalg.inv(T_abs))
+            T_abs = T_new
+        Pc = P @ T_abs[:3, :3].T + T_abs[:3, 3]
+        uv = projection(cam, Pc)
+        vis = (Pc[:, 2] > 2.0) & (Pc[:, 2] < 60.0) & (uv[:, 0] > 5) & (uv[:, 0] < W - 5) & (uv[:, 1] > 5) & (uv[:, 1] < H - 5)
+        idx = np.nonzero(vis)[0][:n_pt]
+        uvl = uv[idx] + rng.normal(0, noise_px, (len(idx), 2))
+        uvr = np.stack([uvl[:, 0] - cam.b * cam.fx / Pc[idx, 2] + rng.normal(0, noise_px, len(idx)), uvl[:, 1]], 1)
+        nc = int(clutter * len(idx))
+        cl = np.stack([rng.uniform(0, W, nc), rng.uniform(0, H, nc)], 1)
+        cr = np.stack([rng.uniform(0, W, nc), rng.uniform(0, H, nc)], 1)
+        pl_, pr_ = rng.permutation(len(idx) + nc), rng.permutation(len(idx) + nc)
+        kp_l = np.concatenate([uvl, cl])[pl_].astype(np.float32)
+        kp_r = np.concatenate([uvr, cr])[pr_].astype(np.float32)
+        kp_r[np.argsort(pr_)[:len(idx)], 1] = kp_l[np.argsort(pl_)[:len(idx)], 1]
+        sc_, ec_ = sP @ T_abs[:3, :3].T + T_abs[:3, 3], eP @ T_abs[:3, :3].T + T_abs[:3, 3]
+        s2, e2 = projection(cam, sc_), projection(cam, ec_)
+        visl = (sc_[:, 2] > 2) & (ec_[:, 2] > 2) & (sc_[:, 2] < 45) & (np.minimum(s2[:, 0], e2[:, 0]) > 5) & (np.maximum(s2[:, 0], e2[:, 0]) < W - 5) & \
+               (np.minimum(s2[:, 1], e2[:, 1]) > 5) & (np.maximum(s2[:, 1], e2[:, 1]) < H - 5) & (np.abs(s2[:, 1] - e2[:, 1]) > 8)
+        li = np.nonzero(visl)[0][:n_ls]
+        sl, el = s2[li] + rng.normal(0, noise_px, (len(li), 2)), e2[li] + rng.normal(0, noise_px, (len(li), 2))
+        sr = np.stack([sl[:, 0] - cam.b * cam.fx / sc_[li, 2], sl[:, 1]], 1)
+        er = np.stack([el[:, 0] - cam.b * cam.fx / ec_[li, 2], el[:, 1]], 1)
+        qL, qR = rng.permutation(len(li)), rng.permutation(len(li))
+        frames.append(dict(
+            kp_l=kp_l, kp_r=kp_r, poct_l=np.concatenate([octv[idx], rng.integers(0, 4, nc).astype(np.int32)])[pl_],
+            pdesc_l=np.concatenate([flip(dP[idx]), rng.integers(0, 256, (nc, 32), dtype=np.uint8)])[pl_],
+            pdesc_r=np.concatenate([flip(dP[idx]), rng.integers(0, 256, (nc, 32), dtype=np.uint8)])[pr_],
+            seg_l=np.concatenate([sl, el], 1)[qL].astype(np.float32), seg_r=np.concatenate([sr, er], 1)[qR].astype(np.float32),
+            angle_l=rng.uniform(-np.pi, np.pi, len(li)).astype(np.float32), loct_l=np.zeros(len(li), np.int32),
+            ldesc_l=flip(dL[li])[qL], ldesc_r=flip(dL[li])[qR]))
+    out = {k: np.concatenate([f[k] for f in frames]) for k in frames[0]}
+    for off, key in (("pl_off", "kp_l"), ("pr_off", "kp_r"), ("ll_off", "seg_l"), ("lr_off", "seg_r")):
+        out[off] = np.concatenate([[0], np.cumsum([len(f[key]) for f in frames])]).astype(np.int32)
+    return out, np.stack(rel) if rel else np.zeros((0, 4, 4)), cam
+
+
+def stereo_frames_slice(d, lo, hi):
+    """Frames [lo, hi) of a PlStereoFeatures dict as a new dict (offsets rebased)."""
+    out = {}
+    for off, keys in (("pl_off", ("kp_l", "poct_l", "pdesc_l")), ("pr_off", ("kp_r", "pdesc_r")),
+                      ("ll_off", ("seg_l", "angle_l", "loct_l", "ldesc_l")), ("lr_off", ("seg_r", "ldesc_r"))):
+        a, b = d[off][lo], d[off][hi]
+        out[off] = (d[off][lo:hi + 1] - a).astype(np.int32)
+        for k in keys:
+            out[k] = d[k][a:b]
+    return out

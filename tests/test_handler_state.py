@@ -135,3 +135,31 @@ def test_fast_threshold_branches(oracle):
         assert H.update_fast_threshold(hc, th, dt, err, n) == want
     c.adaptative_fast, hc.adaptative_fast = 0, False
     assert oracle.update_fast_threshold(c, 20, np.eye(4), 0.9, 0) == 20 == H.update_fast_threshold(hc, 20, np.eye(4), 0.9, 0)
+
+
+def test_chain_poses_cpp_vs_python(tmp_path):
+    """plstvo::chainPoses (C++ host layer) == handler.chain_poses (Python mirror) on a synthetic sequence with failed pairs."""
+    from stvo_pl_b200 import types as T
+    rng = np.random.default_rng(4)
+    n = 40
+    res = np.zeros(n, dtype=T.POSE_RESULT_DTYPE)
+    for k in range(n):
+        x = np.concatenate([rng.normal([0, 0, 0.5], 0.05), rng.normal(0, 0.02, 3)])
+        A = rng.normal(size=(6, 6))
+        res["DT"][k], res["DT_cov"][k], res["good"][k] = expm(_hat(x)), 1e-6 * (A @ A.T + np.eye(6)), int(rng.random() > 0.15)
+    exe = str(tmp_path / "chain_cpp")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "chain_cpp.cpp"), "-o", exe], check=True)
+    path = str(tmp_path / "res.bin")
+    with open(path, "wb") as f:
+        for k in range(n):
+            f.write(np.concatenate([[float(res["good"][k])], res["DT"][k].ravel(), res["DT_cov"][k].ravel()]).astype(np.float64).tobytes())
+    lines = subprocess.run([exe, path], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    got = np.array([[float(v) for v in ln.split()] for ln in lines])
+    ref = H.chain_poses(res.copy())
+    assert 0 < (res["good"] == 0).sum() < n
+    np.testing.assert_allclose(got[:, :16].reshape(n, 4, 4), ref["Tfw"], atol=1e-12)
+    np.testing.assert_allclose(got[:, 16:].reshape(n, 6, 6), ref["Tfw_cov"], rtol=1e-10, atol=1e-15)
+    k0 = int(np.nonzero(res["good"] == 0)[0][0])
+    if k0 > 0:
+        np.testing.assert_array_equal(ref["Tfw"][k0], ref["Tfw"][k0 - 1])      # a failed pair carries the pose over (:388-389)

@@ -282,3 +282,41 @@ def test_gpu_track_stereo_batch_edge_cases(engine, oracle):
     bad["pl_off"], bad["pr_off"], bad["ll_off"], bad["lr_off"] = (curr[k][:-1] for k in ("pl_off", "pr_off", "ll_off", "lr_off"))
     with pytest.raises(RuntimeError):
         engine.track_stereo_batch(cam, cfg, mc, sc, prev, bad)     # different numbers of frames
+
+
+@pytest.mark.gpu
+def test_gpu_track_stereo_sequence(engine, oracle):
+    """Sequence mode: NF consecutive frames, every frame through the stereo step once.  The NF - 1 results equal, byte for byte,
+    those of plstvo_track_stereo_batch on (frames[:-1], frames[1:]); chained on the host they equal the handler fed frame by
+    frame (priors = the previous frame's chained pose), and follow the generator's trajectory."""
+    import ref_numpy as R
+    from stvo_pl_b200 import handler as Hd
+    NF = 7
+    frames, rel, cam = SS.make_stereo_sequence(NF, n_pt=900, n_ls=180, seed=8)
+    mc, sc, cfg = T.default_stereo_match_config(), T.default_stereo_config(), T.kitti_config()
+    res, n_st = engine.track_stereo_sequence(cam, cfg, mc, sc, frames)
+    assert len(res) == NF - 1 and n_st.shape == (NF, 2) and (res["good"] == 1).all()
+    ref, n_b = engine.track_stereo_batch(cam, cfg, mc, sc, SS.stereo_frames_slice(frames, 0, NF - 1), SS.stereo_frames_slice(frames, 1, NF))
+    assert res.tobytes() == ref.tobytes()
+    np.testing.assert_array_equal(n_st[:-1], n_b[:, :2])
+    np.testing.assert_array_equal(n_st[1:], n_b[:, 2:])
+    # chaining: host scan == pairs solved one after the other with the previous chained pose as prior
+    chained = Hd.chain_poses(res.copy())
+    Tfw, cov = np.eye(4), np.eye(6)
+    for k in range(NF - 1):
+        pri = T.identity_priors(1)
+        pri["Tfw"][0], pri["Tfw_cov"][0] = Tfw, cov
+        one, _ = engine.track_stereo_batch(cam, cfg, mc, sc, SS.stereo_frames_slice(frames, k, k + 1),
+                                           SS.stereo_frames_slice(frames, k + 1, k + 2), priors=pri)
+        Tfw, cov = one["Tfw"][0], one["Tfw_cov"][0]
+        np.testing.assert_allclose(chained["Tfw"][k], Tfw, atol=1e-9)
+        np.testing.assert_allclose(chained["Tfw_cov"][k], cov, rtol=1e-7, atol=1e-12)
+    # trajectory: DT_opt (prev -> curr) against the generator's relative motion
+    for k in range(NF - 1):
+        ang, tr = R.pose_error(res["DT_opt"][k], rel[k])
+        assert ang < 5e-3 and tr < 5e-2
+    # a single frame: nothing to do; two frames: one result
+    r1, _ = engine.track_stereo_sequence(cam, cfg, mc, sc, SS.stereo_frames_slice(frames, 0, 1))
+    assert len(r1) == 0
+    r2, _ = engine.track_stereo_sequence(cam, cfg, mc, sc, SS.stereo_frames_slice(frames, 2, 4))
+    assert r2.tobytes() == res[2:3].tobytes()

@@ -34,4 +34,6 @@ seg_l, angle, octave, d1, seg_r, d2 = SS.make_stereo_frame_lines(250, 240, seed=
 eng.match_stereo_lines(cam, mc, sc, [0, 250], seg_l, angle, octave, d1, [0, 240], seg_r, d2)
 sp, scur, _, scam = SS.make_stereo_pairs(2, n_pt=500, n_ls=120, seed=7)
 eng.track_stereo_batch(scam, T.kitti_config(), mc, sc, sp, scur)
+sq, _, qcam = SS.make_stereo_sequence(4, n_pt=400, n_ls=90, seed=9)
+eng.track_stereo_sequence(qcam, T.kitti_config(), mc, sc, sq)
 print("sanitized run ok", int(out["results"]["good"].sum()))
