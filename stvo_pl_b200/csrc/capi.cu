@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -73,6 +74,7 @@ struct Workspace {
 }  // namespace
 
 struct PlContext {
+    std::recursive_mutex mu;   // entry points serialise on it: one context may be shared by the caller's threads
     int device = 0;
     int sm_count = 0;
     size_t smem_optin = 0;
@@ -121,6 +123,8 @@ namespace {
             return PLSTVO_E_CUDA;                                                                \
         }                                                                                        \
     } while (0)
+
+#define LOCK(ctx) std::lock_guard<std::recursive_mutex> lock__((ctx)->mu)
 
 int fail(PlContext* ctx, int code, const char* msg) {
     if (ctx) ctx->err = msg;
@@ -589,6 +593,7 @@ void plstvo_kitti_config(PlConfig* c) {   // config/config/config_kitti.yaml:19,
 
 int plstvo_synchronize(PlContext* ctx) {
     if (!ctx) return PLSTVO_E_INVALID;
+    LOCK(ctx);
     CK(ctx, cudaSetDevice(ctx->device));
     CK(ctx, cudaStreamSynchronize(ctx->s_h2d));
     CK(ctx, cudaStreamSynchronize(ctx->s_main));
@@ -612,6 +617,7 @@ int64_t plstvo_launch_count(const PlContext* ctx) { return ctx ? ctx->launches :
 int plstvo_match_batch(PlContext* ctx, int B, const uint8_t* d1, const int32_t* off1, const uint8_t* d2,
                        const int32_t* off2, float nnr, int best_lr_matches, int32_t* m12, int32_t* counts) {
     if (!ctx) return PLSTVO_E_INVALID;
+    LOCK(ctx);
     if (B < 0 || (B > 0 && (!off1 || !off2 || !m12))) return fail(ctx, PLSTVO_E_INVALID, "bad arguments");
     if (B == 0) return 0;
     CK(ctx, cudaSetDevice(ctx->device));
@@ -666,6 +672,7 @@ int plstvo_match_batch(PlContext* ctx, int B, const uint8_t* d1, const int32_t* 
 int plstvo_match(PlContext* ctx, const uint8_t* d1, int n1, const uint8_t* d2, int n2, int stride_bytes,
                  float nnr, int best_lr_matches, int32_t* m12) {
     if (!ctx) return PLSTVO_E_INVALID;
+    LOCK(ctx);
     if (stride_bytes != PLSTVO_DESC_BYTES) return fail(ctx, PLSTVO_E_INVALID, "descriptor rows must be 32 contiguous bytes");
     if (n1 < 0 || n2 < 0) return fail(ctx, PLSTVO_E_INVALID, "negative row count");
     if (n1 == 0) return 0;
@@ -685,6 +692,7 @@ static int match_grid_common(PlContext* ctx, bool lines, int B, int rows, int co
                              const uint8_t* d1, const int32_t* t_off, const int32_t* t_cell, const double* t_line,
                              const double* t_dir, const uint8_t* d2, int32_t* m12, int32_t* counts) {
     if (!ctx) return PLSTVO_E_INVALID;
+    LOCK(ctx);
     if (B < 0 || rows <= 0 || cols <= 0 || rows * cols > 8192) return fail(ctx, PLSTVO_E_INVALID, "bad grid");
     if (B == 0) return 0;
     if (!q_off || !t_off || !m12 || q_off[0] || t_off[0]) return fail(ctx, PLSTVO_E_INVALID, "bad offsets");
@@ -809,6 +817,7 @@ int plstvo_stereo_lift_points(PlContext* ctx, const PlCamera* cam, const PlStere
                               const float* kp_r, const int32_t* m12, double* pt_pl, double* pt_disp, double* pt_P,
                               double* pt_sigma2, int32_t* pt_level, uint8_t* pdesc_out, int32_t* src_idx, int32_t* counts) {
     if (!ctx) return PLSTVO_E_INVALID;
+    LOCK(ctx);
     if (!cam || !scfg || B < 0) return fail(ctx, PLSTVO_E_INVALID, "null camera / config or negative batch size");
     if (B == 0) return 0;
     int rc = lift_check_offsets(ctx, B, l_off, r_off);
@@ -870,6 +879,7 @@ int plstvo_stereo_lift_lines(PlContext* ctx, const PlCamera* cam, const PlStereo
                              double* ls_angle, double* ls_sigma2, int32_t* ls_level, uint8_t* ldesc_out, int32_t* src_idx,
                              int32_t* counts) {
     if (!ctx) return PLSTVO_E_INVALID;
+    LOCK(ctx);
     if (!cam || !scfg || B < 0) return fail(ctx, PLSTVO_E_INVALID, "null camera / config or negative batch size");
     if (B == 0) return 0;
     int rc = lift_check_offsets(ctx, B, l_off, r_off);
@@ -951,6 +961,7 @@ int match_stereo_common(PlContext* ctx, bool lines, const PlCamera* cam, const P
                         const uint8_t* desc_l, const int32_t* r_off, const float* xy_r, const uint8_t* desc_r,
                         const StereoOut& out) {
     if (!ctx) return PLSTVO_E_INVALID;
+    LOCK(ctx);
     if (!cam || !mc || !sc || B < 0) return fail(ctx, PLSTVO_E_INVALID, "null camera / config or negative batch size");
     const int rows = mc->grid_rows, cols = mc->grid_cols;
     if (rows <= 0 || cols <= 0 || rows * cols > 8192 || cam->width <= 0 || cam->height <= 0)
@@ -1103,6 +1114,7 @@ static int track_stereo_common(PlContext* ctx, const PlCamera* cam, const PlConf
                                const PlStereoConfig* sc, const PlStereoFeatures* prev, const PlStereoFeatures* curr,
                                const PlPrior* priors, PlPoseResult* results, int32_t* n_stereo, bool sequence) {
     if (!ctx) return PLSTVO_E_INVALID;
+    LOCK(ctx);
     if (!cam || !cfg || !mc || !sc || !prev || (!sequence && !curr) || !results) return fail(ctx, PLSTVO_E_INVALID, "null argument");
     const int NF = prev->B;                         // frames per feature set
     const int B = sequence ? NF - 1 : NF;           // pairs
@@ -1323,6 +1335,7 @@ int plstvo_track_stereo_sequence(PlContext* ctx, const PlCamera* cam, const PlCo
 int plstvo_f2f_tracking(PlContext* ctx, const PlConfig* cfg, const PlFrameBatch* prev, const PlFrameBatch* curr,
                         int32_t* m12_pt, int32_t* m12_ls, int32_t* n_matched) {
     if (!ctx || !cfg) return PLSTVO_E_INVALID;
+    LOCK(ctx);
     CK(ctx, cudaSetDevice(ctx->device));
     int rc = validate_frames(ctx, prev, curr, false);
     if (rc) return rc;
@@ -1355,6 +1368,7 @@ int plstvo_f2f_tracking(PlContext* ctx, const PlConfig* cfg, const PlFrameBatch*
 int plstvo_optimize_pose(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlMatchedBatch* m,
                          const PlPrior* priors, PlPoseResult* results, uint8_t* inlier_pt, uint8_t* inlier_ls) {
     if (!ctx || !cam || !cfg || !m || !results) return PLSTVO_E_INVALID;
+    LOCK(ctx);
     const int B = m->B;
     if (B < 0) return fail(ctx, PLSTVO_E_INVALID, "negative batch size");
     if (B == 0) return 0;
@@ -1466,6 +1480,7 @@ int plstvo_track_batch(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg,
                        const PlFrameBatch* curr, const PlPrior* priors, PlPoseResult* results, int32_t* m12_pt,
                        int32_t* m12_ls, uint8_t* inlier_pt, uint8_t* inlier_ls) {
     if (!ctx || !cam || !cfg) return PLSTVO_E_INVALID;
+    LOCK(ctx);
     CK(ctx, cudaSetDevice(ctx->device));
     int rc = validate_frames(ctx, prev, curr, true);
     if (rc) return rc;
@@ -1480,6 +1495,7 @@ int plstvo_track_batch_async(PlContext* ctx, const PlCamera* cam, const PlConfig
                              const PlFrameBatch* curr, const PlPrior* priors, PlPoseResult* results, int32_t* m12_pt,
                              int32_t* m12_ls, uint8_t* inlier_pt, uint8_t* inlier_ls) {
     if (!ctx || !cam || !cfg) return PLSTVO_E_INVALID;
+    LOCK(ctx);
     CK(ctx, cudaSetDevice(ctx->device));
     int rc = validate_frames(ctx, prev, curr, true);
     if (rc) return rc;
@@ -1503,8 +1519,14 @@ int plstvo_track_batch_async(PlContext* ctx, const PlCamera* cam, const PlConfig
 int plstvo_wait(PlContext* ctx, int ticket) {
     if (!ctx || ticket < 0 || ticket > 1) return PLSTVO_E_INVALID;
     CK(ctx, cudaSetDevice(ctx->device));
-    if (ctx->slot_busy[ticket]) {
-        CK(ctx, cudaEventSynchronize(ctx->slot_done[ticket]));
+    cudaEvent_t ev = nullptr;
+    {
+        LOCK(ctx);
+        if (ctx->slot_busy[ticket]) ev = ctx->slot_done[ticket];
+    }
+    if (ev) {   // wait outside the lock: other threads may keep enqueueing on this context
+        CK(ctx, cudaEventSynchronize(ev));
+        LOCK(ctx);
         ctx->slot_busy[ticket] = false;
     }
     return 0;
@@ -1514,6 +1536,7 @@ int plstvo_wait(PlContext* ctx, int ticket) {
 int plstvo_batch_upload(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlFrameBatch* prev,
                         const PlFrameBatch* curr, const PlPrior* priors, PlDeviceBatch** out) {
     if (!ctx || !cam || !cfg || !out) return PLSTVO_E_INVALID;
+    LOCK(ctx);
     *out = nullptr;
     CK(ctx, cudaSetDevice(ctx->device));
     int rc = validate_frames(ctx, prev, curr, true);
@@ -1540,12 +1563,14 @@ int plstvo_batch_upload(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg
 
 int plstvo_batch_run(PlContext* ctx, PlDeviceBatch* db) {
     if (!ctx || !db) return PLSTVO_E_INVALID;
+    LOCK(ctx);
     CK(ctx, cudaSetDevice(ctx->device));
     return ws_run(ctx, db->ws, db->ws.have_level);
 }
 
 int plstvo_batch_run_timed(PlContext* ctx, PlDeviceBatch* db, int iters, int flush_l2, float* ms_total) {
     if (!ctx || !db || iters <= 0 || !ms_total) return PLSTVO_E_INVALID;
+    LOCK(ctx);
     CK(ctx, cudaSetDevice(ctx->device));
     const size_t flush_bytes = 256u << 20;
     if (flush_l2) CK(ctx, ctx->scratch.ensure(flush_bytes));
@@ -1587,6 +1612,7 @@ int plstvo_batch_run_timed(PlContext* ctx, PlDeviceBatch* db, int iters, int flu
 int plstvo_batch_kernel_times(PlContext* ctx, PlDeviceBatch* db, int iters, double* ms_match, double* ms_solve,
                               int32_t* n_tiles, int32_t* n_pairs) {
     if (!ctx || !db || iters <= 0) return PLSTVO_E_INVALID;
+    LOCK(ctx);
     CK(ctx, cudaSetDevice(ctx->device));
     Workspace& ws = db->ws;
     cudaEvent_t e0, e1, e2;
@@ -1638,6 +1664,7 @@ int plstvo_batch_kernel_times(PlContext* ctx, PlDeviceBatch* db, int iters, doub
 int plstvo_batch_download(PlContext* ctx, PlDeviceBatch* db, PlPoseResult* results, int32_t* m12_pt,
                           int32_t* m12_ls, uint8_t* inlier_pt, uint8_t* inlier_ls) {
     if (!ctx || !db) return PLSTVO_E_INVALID;
+    LOCK(ctx);
     CK(ctx, cudaSetDevice(ctx->device));
     if (db->ws.B == 0) return 0;
     int rc = ws_download_range(ctx, db->ws, 0, db->ws.B, results, m12_pt, m12_ls, inlier_pt, inlier_ls, ctx->s_main);
@@ -1659,6 +1686,7 @@ void plstvo_batch_free(PlContext* ctx, PlDeviceBatch* db) {
 int plstvo_debug_algebra(PlContext* ctx, int n, const double* H, const double* g, double* x, double* lad, double* inv,
                          double* eig) {
     if (!ctx || n < 0 || !H || !g || !x || !lad || !inv || !eig) return PLSTVO_E_INVALID;
+    LOCK(ctx);
     if (n == 0) return 0;
     CK(ctx, cudaSetDevice(ctx->device));
     const size_t in_b = (size_t)n * 42 * 8, out_b = (size_t)n * 49 * 8;
@@ -1681,6 +1709,7 @@ int plstvo_debug_algebra(PlContext* ctx, int n, const double* H, const double* g
 
 int plstvo_popc_rate(PlContext* ctx, double* popc_per_s) {
     if (!ctx || !popc_per_s) return PLSTVO_E_INVALID;
+    LOCK(ctx);
     CK(ctx, cudaSetDevice(ctx->device));
     const int blocks = ctx->sm_count * 8, iters = 20000;
     CK(ctx, ctx->scratch.ensure((size_t)blocks * 256 * 4));
@@ -1704,6 +1733,7 @@ int plstvo_popc_rate(PlContext* ctx, double* popc_per_s) {
 int plstvo_gn_eval_stream(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlMatchedBatch* m,
                           const double* DT, int iters, double* H, double* g, double* e, float* ms_total) {
     if (!ctx || !cam || !cfg || !m || !DT || iters <= 0) return PLSTVO_E_INVALID;
+    LOCK(ctx);
     const int B = m->B;
     if (B <= 0) return 0;
     CK(ctx, cudaSetDevice(ctx->device));

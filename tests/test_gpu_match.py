@@ -120,3 +120,30 @@ def test_errors(engine):
     with pytest.raises(PlstvoError) as ei:
         engine.match(big, d, 0.9)
     assert ei.value.code == -2
+
+
+def test_one_context_shared_by_threads(engine):
+    """The reference calls the matcher from up to four std::async tasks of one handler (src/stereoFrameHandler.cpp:113-119,
+    src/matching.cpp:68-74): a context shared by threads must serialise its entry points.  Four threads hammer one context with
+    different problems (ctypes releases the GIL); every result equals the single-threaded one."""
+    from concurrent.futures import ThreadPoolExecutor
+    rng = np.random.default_rng(5)
+    probs = [(rng.integers(0, 256, (n1, 32), dtype=np.uint8), rng.integers(0, 256, (n2, 32), dtype=np.uint8))
+             for n1, n2 in [(900, 800), (300, 1200), (1500, 1500), (64, 77), (2000, 500), (700, 700)]]
+    ref = [engine.match(d1, d2, 0.9, True)[1].copy() for d1, d2 in probs]
+    prev, curr, _, cam = synth.make_batch("kitti", 2, n_pt=600, n_ls=150)
+    cfg = T.kitti_config()
+    ref_pose = engine.track_batch(cam, cfg, prev, curr)["results"].tobytes()
+
+    def job(i):
+        k = i % (len(probs) + 1)
+        if k == len(probs):
+            return ("pose", engine.track_batch(cam, cfg, prev, curr)["results"].tobytes())
+        return (k, engine.match(probs[k][0], probs[k][1], 0.9, True)[1].copy())
+    with ThreadPoolExecutor(4) as ex:
+        outs = list(ex.map(job, range(56)))
+    for key, val in outs:
+        if key == "pose":
+            assert val == ref_pose
+        else:
+            np.testing.assert_array_equal(val, ref[key])
