@@ -627,6 +627,26 @@ def run_stereo_track(args):
             "clocks": clk.summary(), "gpu_launches": int(launches),
             "e2e": {"value": B * args.steps / dt, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(res.nbytes + 16 * B)},
             "roofline": None}
+    # the streaming form, two batches in flight (uploads of batch k + 1 under the kernels of batch k)
+    pc, keep_p = T.stereo_features_as_c(prev)
+    cc, keep_c = T.stereo_features_as_c(curr)
+    pres = [eng.pinned.empty((B,), T.POSE_RESULT_DTYPE) for _ in range(2)]
+    pns = [eng.pinned.empty((B, 4), np.int32) for _ in range(2)]
+    for k in range(3):
+        eng.wait(eng.track_stereo_batch_async(cam, cfg, mc, sc, pc, cc, pres[k & 1], pns[k & 1]))
+    t0 = time.perf_counter()
+    pend = None
+    for k in range(args.steps):
+        tk = eng.track_stereo_batch_async(cam, cfg, mc, sc, pc, cc, pres[k & 1], pns[k & 1])
+        if pend is not None:
+            eng.wait(pend)
+        pend = tk
+    eng.wait(pend)
+    torch.cuda.synchronize()
+    dtp = time.perf_counter() - t0
+    line["e2e"]["pipelined_value"] = B * args.steps / dtp
+    line["e2e"]["pipelined_ms_per_step"] = dtp / args.steps * 1e3
+    line["e2e"]["pipelined_equals_blocking"] = bool(pres[(args.steps - 1) & 1].tobytes() == res.tobytes())
     # sequence mode: B + 1 consecutive frames -> B poses, every frame through the stereo step once (plstvo_track_stereo_sequence)
     seq, _, scam = SS.make_stereo_sequence(B + 1, n_pt=1740, n_ls=500, seed=99)
     seq = pin(seq)

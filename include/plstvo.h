@@ -274,6 +274,16 @@ int plstvo_track_stereo_sequence(PlContext* ctx, const PlCamera* cam, const PlCo
                                  const PlStereoConfig* scfg, const PlStereoFeatures* frames, const PlPrior* priors,
                                  PlPoseResult* results, int32_t* n_stereo);
 
+/* Streaming forms: enqueue and return a ticket (0 / 1) like plstvo_track_batch_async; results / n_stereo are valid after
+ * plstvo_wait(ctx, ticket).  Two batches may be in flight, so the next batch's uploads run under this batch's kernels; inputs
+ * must stay untouched (and should be pinned, plstvo_host_alloc) until the wait returns. */
+int plstvo_track_stereo_batch_async(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlStereoMatchConfig* mcfg,
+                                    const PlStereoConfig* scfg, const PlStereoFeatures* prev, const PlStereoFeatures* curr,
+                                    const PlPrior* priors, PlPoseResult* results, int32_t* n_stereo);
+int plstvo_track_stereo_sequence_async(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlStereoMatchConfig* mcfg,
+                                       const PlStereoConfig* scfg, const PlStereoFeatures* frames, const PlPrior* priors,
+                                       PlPoseResult* results, int32_t* n_stereo);
+
 /* ---- include/stereoFrameHandler.h surface ----------------------------------------------------- */
 /* StereoFrameHandler::f2fTracking (src/stereoFrameHandler.cpp:106-180) for B independent
  * (prev, curr) pairs: descriptor matching for points and lines; m12_* hold problem-local indices

@@ -91,17 +91,19 @@ struct PlContext {
     DevBuf scratch;        // misc (popc bench, L2 flush)
     DevBuf gn_in[8], gn_out[4];
     // per-entry-point device arenas (context-owned: a process may hold one context per GPU)
-    DevBuf arena_grid, arena_lift_pt, arena_lift_ls, arena_stereo, arena_track_stereo;
+    DevBuf arena_grid, arena_lift_pt, arena_lift_ls, arena_stereo;
+    DevBuf arena_track_stereo[3];   // [0]: blocking calls, [1 + slot]: plstvo_track_stereo_*_async
     DevBuf gs_in[13], gs_rec_pt, gs_rec_ls;   // resident inputs / packed records of the streamed evaluator
-    void* h_staging = nullptr;   // pinned host scratch (small tables and counters that must not block the enqueueing thread)
-    size_t h_staging_bytes = 0;
-    cudaError_t staging(size_t bytes) {
-        if (bytes <= h_staging_bytes) return cudaSuccess;
-        if (h_staging) cudaFreeHost(h_staging);
-        h_staging = nullptr;
-        h_staging_bytes = 0;
-        cudaError_t e = cudaMallocHost(&h_staging, bytes);
-        if (e == cudaSuccess) h_staging_bytes = bytes;
+    // pinned host scratch (small tables and counters that must not block the enqueueing thread), same indexing as the arenas
+    void* h_staging[3] = {nullptr, nullptr, nullptr};
+    size_t h_staging_bytes[3] = {0, 0, 0};
+    cudaError_t staging(int k, size_t bytes) {
+        if (bytes <= h_staging_bytes[k]) return cudaSuccess;
+        if (h_staging[k]) cudaFreeHost(h_staging[k]);
+        h_staging[k] = nullptr;
+        h_staging_bytes[k] = 0;
+        cudaError_t e = cudaMallocHost(&h_staging[k], bytes);
+        if (e == cudaSuccess) h_staging_bytes[k] = bytes;
         return e;
     }
 };
@@ -563,11 +565,13 @@ void plstvo_destroy(PlContext* ctx) {
     for (auto& b : ctx->gn_in) b.release();
     for (auto& b : ctx->gn_out) b.release();
     ctx->arena_grid.release(); ctx->arena_lift_pt.release(); ctx->arena_lift_ls.release();
-    ctx->arena_stereo.release(); ctx->arena_track_stereo.release();
+    ctx->arena_stereo.release();
+    for (auto& b : ctx->arena_track_stereo) b.release();
     for (auto& b : ctx->gs_in) b.release();
     ctx->gs_rec_pt.release(); ctx->gs_rec_ls.release();
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
-    if (ctx->h_staging) cudaFreeHost(ctx->h_staging);
+    for (void* h : ctx->h_staging)
+        if (h) cudaFreeHost(h);
     cudaStreamDestroy(ctx->s_main);
     cudaStreamDestroy(ctx->s_alt);
     cudaStreamDestroy(ctx->s_h2d);
@@ -1112,7 +1116,8 @@ int plstvo_match_stereo_lines(PlContext* ctx, const PlCamera* cam, const PlStere
 //                    every frame goes through the stereo step once and is lifted twice (as a previous and as a current frame).
 static int track_stereo_common(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlStereoMatchConfig* mc,
                                const PlStereoConfig* sc, const PlStereoFeatures* prev, const PlStereoFeatures* curr,
-                               const PlPrior* priors, PlPoseResult* results, int32_t* n_stereo, bool sequence) {
+                               const PlPrior* priors, PlPoseResult* results, int32_t* n_stereo, bool sequence, int slot) {
+    // slot < 0: blocking (returns with the results in host memory); slot 0 / 1: enqueue only, results valid after plstvo_wait
     if (!ctx) return PLSTVO_E_INVALID;
     LOCK(ctx);
     if (!cam || !cfg || !mc || !sc || !prev || (!sequence && !curr) || !results) return fail(ctx, PLSTVO_E_INVALID, "null argument");
@@ -1164,7 +1169,7 @@ static int track_stereo_common(PlContext* ctx, const PlCamera* cam, const PlConf
     const size_t o_items = a.take(max_items * 4), o_qpairs = a.take(maxN1 * CAP * 8), o_qcount = a.take(maxN1 * 4);
     const size_t o_tcount = a.take(maxN2 * 4), o_tstart = a.take((maxN2 + NF) * 4), o_tslots = a.take(maxN1 * CAP * 4);
     const size_t o_seen = a.take(maxN1 * CAP), o_m21 = a.take(maxN2 * 4);
-    DevBuf& arena = ctx->arena_track_stereo;
+    DevBuf& arena = ctx->arena_track_stereo[slot + 1];
     CK(ctx, arena.ensure(a.off));
     uint8_t* base = arena.as<uint8_t>();
     auto I = [&](size_t o) { return reinterpret_cast<int32_t*>(base + o); };
@@ -1174,16 +1179,14 @@ static int track_stereo_common(PlContext* ctx, const PlCamera* cam, const PlConf
     auto up = [&](size_t o, const void* src, size_t bytes) -> cudaError_t {
         return (src && bytes) ? cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, sh) : cudaSuccess;
     };
-    cudaEvent_t prior_done = next_event(ctx);           // the arena may still be read by work queued on s_main earlier
-    CK(ctx, cudaEventRecord(prior_done, s));
-    CK(ctx, cudaStreamWaitEvent(sh, prior_done, 0));
+    // (this slot's arena is free: a blocking call ends synchronised, an async slot is reused only after its event completed)
     const double inv_w = cols / static_cast<double>(cam->width), inv_h = rows / static_cast<double>(cam->height);
     const GridParams gprm{rows, cols, CAP, mc->best_lr_matches ? 1 : 0, PlGridWindow{mc->matching_s_ws, 0, 0, 0}, mc->min_ratio_12_p,
                           mc->line_sim_th};
     // pinned staging: 4 problem tables + 2 x 4 x B counters (pageable copies would block this thread on the stream)
     const size_t prob_bytes = ((size_t)NF * sizeof(GridProblem) + 255) / 256 * 256;
-    CK(ctx, ctx->staging(4 * prob_bytes + (size_t)8 * NF * 4));
-    uint8_t* hst = static_cast<uint8_t*>(ctx->h_staging);
+    CK(ctx, ctx->staging(slot + 1, 4 * prob_bytes + (size_t)8 * NF * 4));
+    uint8_t* hst = static_cast<uint8_t*>(ctx->h_staging[slot + 1]);
     int32_t* cnt = reinterpret_cast<int32_t*>(hst + 4 * prob_bytes);
     int32_t* gcnt = cnt + (size_t)4 * NF;
     // ---- pass 1: cells -> matchGrid -> lifting filters (count only) per set ----
@@ -1269,7 +1272,7 @@ static int track_stereo_common(PlContext* ctx, const PlCamera* cam, const PlConf
     fp.pt_off = ooff[0].data(); fp.ls_off = ooff[1].data();
     fc.pt_off = sequence ? ooff2[0].data() : ooff[2].data();
     fc.ls_off = sequence ? ooff2[1].data() : ooff[3].data();
-    Workspace& ws = ctx->ws;
+    Workspace& ws = slot < 0 ? ctx->ws : ctx->ws_async[slot];
     int rc = ws_prepare(ctx, ws, cam, cfg, &fp, &fc, true, priors != nullptr);
     if (rc) return rc;
     if (priors) CK(ctx, cudaMemcpyAsync(ws.d_priors.p, priors, (size_t)B * sizeof(PlPrior), cudaMemcpyHostToDevice, ctx->s_h2d));
@@ -1315,20 +1318,53 @@ static int track_stereo_common(PlContext* ctx, const PlCamera* cam, const PlConf
     rc = ws_launch_solve(ctx, ws, 0, B, true, s);
     if (rc) return rc;
     CK(ctx, cudaMemcpyAsync(results, ws.d_results.p, (size_t)B * sizeof(PlPoseResult), cudaMemcpyDeviceToHost, s));
-    CK(ctx, cudaStreamSynchronize(s));
+    if (slot < 0) CK(ctx, cudaStreamSynchronize(s));
     return 0;
+}
+
+// ticket bookkeeping shared with plstvo_track_batch_async: two slots, plstvo_wait(ticket) blocks until the slot's results are home
+static int stereo_async(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlStereoMatchConfig* mc,
+                        const PlStereoConfig* sc, const PlStereoFeatures* a, const PlStereoFeatures* b, const PlPrior* priors,
+                        PlPoseResult* results, int32_t* n_stereo, bool sequence) {
+    if (!ctx) return PLSTVO_E_INVALID;
+    LOCK(ctx);
+    CK(ctx, cudaSetDevice(ctx->device));
+    const int slot = ctx->next_slot;
+    ctx->next_slot ^= 1;
+    if (ctx->slot_busy[slot]) {
+        CK(ctx, cudaEventSynchronize(ctx->slot_done[slot]));
+        ctx->slot_busy[slot] = false;
+    }
+    if (!ctx->slot_done[slot]) CK(ctx, cudaEventCreateWithFlags(&ctx->slot_done[slot], cudaEventDisableTiming));
+    const int rc = track_stereo_common(ctx, cam, cfg, mc, sc, a, b, priors, results, n_stereo, sequence, slot);
+    if (rc) return rc;
+    CK(ctx, cudaEventRecord(ctx->slot_done[slot], ctx->s_main));
+    ctx->slot_busy[slot] = true;
+    return slot;
+}
+
+int plstvo_track_stereo_batch_async(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlStereoMatchConfig* mc,
+                                    const PlStereoConfig* sc, const PlStereoFeatures* prev, const PlStereoFeatures* curr,
+                                    const PlPrior* priors, PlPoseResult* results, int32_t* n_stereo) {
+    return stereo_async(ctx, cam, cfg, mc, sc, prev, curr, priors, results, n_stereo, false);
+}
+
+int plstvo_track_stereo_sequence_async(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlStereoMatchConfig* mc,
+                                       const PlStereoConfig* sc, const PlStereoFeatures* frames, const PlPrior* priors,
+                                       PlPoseResult* results, int32_t* n_stereo) {
+    return stereo_async(ctx, cam, cfg, mc, sc, frames, nullptr, priors, results, n_stereo, true);
 }
 
 int plstvo_track_stereo_batch(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlStereoMatchConfig* mc,
                               const PlStereoConfig* sc, const PlStereoFeatures* prev, const PlStereoFeatures* curr,
                               const PlPrior* priors, PlPoseResult* results, int32_t* n_stereo) {
-    return track_stereo_common(ctx, cam, cfg, mc, sc, prev, curr, priors, results, n_stereo, false);
+    return track_stereo_common(ctx, cam, cfg, mc, sc, prev, curr, priors, results, n_stereo, false, -1);
 }
 
 int plstvo_track_stereo_sequence(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlStereoMatchConfig* mc,
                                  const PlStereoConfig* sc, const PlStereoFeatures* frames, const PlPrior* priors,
                                  PlPoseResult* results, int32_t* n_stereo) {
-    return track_stereo_common(ctx, cam, cfg, mc, sc, frames, nullptr, priors, results, n_stereo, true);
+    return track_stereo_common(ctx, cam, cfg, mc, sc, frames, nullptr, priors, results, n_stereo, true, -1);
 }
 
 // ---- stereoFrameHandler.h surface ------------------------------------------------------------------------

@@ -61,6 +61,10 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
                                                 C.POINTER(T.PlStereoFeatures), C.POINTER(T.PlStereoFeatures), vp, vp, i32p]),
         "plstvo_track_stereo_sequence": (C.c_int, [vp, cam, cfg, C.POINTER(T.PlStereoMatchConfig), C.POINTER(T.PlStereoConfig),
                                                    C.POINTER(T.PlStereoFeatures), vp, vp, i32p]),
+        "plstvo_track_stereo_batch_async": (C.c_int, [vp, cam, cfg, C.POINTER(T.PlStereoMatchConfig), C.POINTER(T.PlStereoConfig),
+                                                      C.POINTER(T.PlStereoFeatures), C.POINTER(T.PlStereoFeatures), vp, vp, i32p]),
+        "plstvo_track_stereo_sequence_async": (C.c_int, [vp, cam, cfg, C.POINTER(T.PlStereoMatchConfig), C.POINTER(T.PlStereoConfig),
+                                                         C.POINTER(T.PlStereoFeatures), vp, vp, i32p]),
         "plstvo_f2f_tracking": (C.c_int, [vp, cfg, fb, fb, i32p, i32p, i32p]),
         "plstvo_optimize_pose": (C.c_int, [vp, cam, cfg, mb, vp, vp, u8p, u8p]),
         "plstvo_track_batch": (C.c_int, [vp, cam, cfg, fb, fb, vp, vp, i32p, i32p, u8p, u8p]),
@@ -91,7 +95,8 @@ EXPORTED_SYMBOLS = [
     "plstvo_kitti_config", "plstvo_match_nnr", "plstvo_match", "plstvo_match_batch", "plstvo_match_grid_points",
     "plstvo_match_grid_lines", "plstvo_default_stereo_config", "plstvo_stereo_lift_points", "plstvo_stereo_lift_lines",
     "plstvo_default_stereo_match_config", "plstvo_match_stereo_points", "plstvo_match_stereo_lines", "plstvo_track_stereo_batch",
-    "plstvo_track_stereo_sequence", "plstvo_f2f_tracking",
+    "plstvo_track_stereo_sequence", "plstvo_track_stereo_batch_async", "plstvo_track_stereo_sequence_async",
+    "plstvo_f2f_tracking",
     "plstvo_optimize_pose", "plstvo_track_batch", "plstvo_track_batch_async", "plstvo_wait", "plstvo_batch_upload", "plstvo_batch_run",
     "plstvo_batch_run_timed", "plstvo_batch_download", "plstvo_batch_free", "plstvo_synchronize",
     "plstvo_host_alloc", "plstvo_host_free", "plstvo_launch_count", "plstvo_batch_kernel_times",
@@ -396,6 +401,18 @@ class Engine:
                                                     results.ctypes.data, _p(n_stereo, T.c_int32_p)))
         del keep_p, keep_c
         return results, n_stereo
+
+    def track_stereo_batch_async(self, cam, cfg, mcfg, scfg, prev_c, curr_c, results, n_stereo, priors=None) -> int:
+        """Streaming form: prev_c / curr_c are PlStereoFeatures structs built once by T.stereo_features_as_c over PINNED arrays
+        (keep the returned keep-alive dicts); results / n_stereo are caller-owned (pinned) arrays, valid after wait(ticket)."""
+        return self._ck(self.lib.plstvo_track_stereo_batch_async(
+            self.ctx, C.byref(cam), C.byref(cfg), C.byref(mcfg), C.byref(scfg), C.byref(prev_c), C.byref(curr_c),
+            priors.ctypes.data if priors is not None else None, results.ctypes.data, _p(n_stereo, T.c_int32_p)))
+
+    def track_stereo_sequence_async(self, cam, cfg, mcfg, scfg, frames_c, results, n_stereo, priors=None) -> int:
+        return self._ck(self.lib.plstvo_track_stereo_sequence_async(
+            self.ctx, C.byref(cam), C.byref(cfg), C.byref(mcfg), C.byref(scfg), C.byref(frames_c),
+            priors.ctypes.data if priors is not None else None, results.ctypes.data, _p(n_stereo, T.c_int32_p)))
 
     def track_stereo_sequence(self, cam, cfg, mcfg, scfg, frames: dict, priors=None, results=None):
         """NF consecutive frames of raw stereo features -> NF - 1 poses (pair p = frames p, p + 1); every frame goes through the

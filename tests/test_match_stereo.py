@@ -320,3 +320,32 @@ def test_gpu_track_stereo_sequence(engine, oracle):
     assert len(r1) == 0
     r2, _ = engine.track_stereo_sequence(cam, cfg, mc, sc, SS.stereo_frames_slice(frames, 2, 4))
     assert r2.tobytes() == res[2:3].tobytes()
+
+
+@pytest.mark.gpu
+def test_gpu_track_stereo_async_equals_blocking(engine):
+    """plstvo_track_stereo_batch_async / _sequence_async + plstvo_wait, two batches in flight, different inputs per slot."""
+    mc, sc, cfg = T.default_stereo_match_config(), T.default_stereo_config(), T.kitti_config()
+    batches = [SS.make_stereo_pairs(4, n_pt=500 + 100 * k, n_ls=100, seed=60 + k) for k in range(3)]
+    cam = batches[0][3]
+    ref = [engine.track_stereo_batch(cam, cfg, mc, sc, b[0], b[1]) for b in batches]
+    pin = lambda d: {k: engine.pinned.copy(np.ascontiguousarray(v, T.STEREO_FEATURE_DTYPES[k])) for k, v in d.items()}
+    cs = [(T.stereo_features_as_c(pin(b[0])), T.stereo_features_as_c(pin(b[1]))) for b in batches]
+    res = [engine.pinned.empty((4,), T.POSE_RESULT_DTYPE) for _ in batches]
+    nst = [engine.pinned.empty((4, 4), np.int32) for _ in batches]
+    tickets = []
+    for k, ((pc, _kp), (cc, _kc)) in enumerate(cs):
+        tickets.append(engine.track_stereo_batch_async(cam, cfg, mc, sc, pc, cc, res[k], nst[k]))
+        if k >= 1:
+            engine.wait(tickets[k - 1])
+    engine.wait(tickets[-1])
+    for k in range(3):
+        assert res[k].tobytes() == ref[k][0].tobytes()
+        np.testing.assert_array_equal(nst[k], ref[k][1])
+    frames, _, scam = SS.make_stereo_sequence(5, n_pt=600, n_ls=100, seed=3)
+    rs, ns = engine.track_stereo_sequence(scam, cfg, mc, sc, frames)
+    fc, _kf = T.stereo_features_as_c(pin(frames))
+    r2, n2 = engine.pinned.empty((4,), T.POSE_RESULT_DTYPE), engine.pinned.empty((5, 2), np.int32)
+    engine.wait(engine.track_stereo_sequence_async(scam, cfg, mc, sc, fc, r2, n2))
+    assert r2.tobytes() == rs.tobytes()
+    np.testing.assert_array_equal(n2, ns)
