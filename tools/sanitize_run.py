@@ -36,4 +36,11 @@ sp, scur, _, scam = SS.make_stereo_pairs(2, n_pt=500, n_ls=120, seed=7)
 eng.track_stereo_batch(scam, T.kitti_config(), mc, sc, sp, scur)
 sq, _, qcam = SS.make_stereo_sequence(4, n_pt=400, n_ls=90, seed=9)
 eng.track_stereo_sequence(qcam, T.kitti_config(), mc, sc, sq)
+pin = lambda d: {k: eng.pinned.copy(np.ascontiguousarray(v, T.STEREO_FEATURE_DTYPES[k])) for k, v in d.items()}
+(pc, _k1), (cc, _k2) = T.stereo_features_as_c(pin(sp)), T.stereo_features_as_c(pin(scur))
+ares, ans = eng.pinned.empty((2,), T.POSE_RESULT_DTYPE), eng.pinned.empty((2, 4), np.int32)
+t1 = eng.track_stereo_batch_async(scam, T.kitti_config(), mc, sc, pc, cc, ares, ans)
+t2 = eng.track_stereo_batch_async(scam, T.kitti_config(), mc, sc, pc, cc, ares, ans)
+eng.wait(t1)
+eng.wait(t2)
 print("sanitized run ok", int(out["results"]["good"].sum()))
