@@ -150,6 +150,23 @@ class StereoFrame:
     err_norm: float = -1.0
 
 
+def stereo_features(engine: Engine, cam: T.PlCamera, raw: dict, mcfg: Optional[T.PlStereoMatchConfig] = None,
+                    scfg: Optional[T.PlStereoConfig] = None) -> T.FrameBatch:
+    """The matching half of StereoFrame::extractStereoFeatures (matchStereoPoints + matchStereoLines, src/stereoFrame.cpp:120-173,
+    :309-398) for ONE frame of raw stereo features (a dict with the PlStereoFeatures fields): the frame's stereo_pt / stereo_ls
+    records as the FrameBatch the handler consumes."""
+    mcfg, scfg = mcfg or T.default_stereo_match_config(), scfg or T.default_stereo_config()
+    assert len(raw["pl_off"]) == 2, "one frame"
+    kp, op = engine.match_stereo_points(cam, mcfg, scfg, raw["pl_off"], raw["kp_l"], raw["poct_l"], raw["pdesc_l"], raw["pr_off"],
+                                        raw["kp_r"], raw["pdesc_r"])
+    kl, ol = engine.match_stereo_lines(cam, mcfg, scfg, raw["ll_off"], raw["seg_l"], raw["angle_l"], raw["loct_l"], raw["ldesc_l"],
+                                       raw["lr_off"], raw["seg_r"], raw["ldesc_r"])
+    return T.FrameBatch(pt_off=[0, kp], ls_off=[0, kl], pdesc=op["desc"][:kp], ldesc=ol["desc"][:kl], pt_P=op["P"][:kp],
+                        pt_pl=op["pl"][:kp], pt_sigma2=op["sigma2"][:kp], ls_sP=ol["sP"][:kl], ls_eP=ol["eP"][:kl],
+                        ls_le=ol["le"][:kl], ls_spl=ol["spl"][:kl], ls_epl=ol["epl"][:kl], ls_sigma2=ol["sigma2"][:kl],
+                        ls_level=ol["level"][:kl])
+
+
 class StereoFrameHandler:
     def __init__(self, cam: T.PlCamera, cfg: Optional[T.PlConfig] = None, engine: Optional[Engine] = None,
                  hcfg: Optional[HandlerConfig] = None):

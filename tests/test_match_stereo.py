@@ -349,3 +349,29 @@ def test_gpu_track_stereo_async_equals_blocking(engine):
     engine.wait(engine.track_stereo_sequence_async(scam, cfg, mc, sc, fc, r2, n2))
     assert r2.tobytes() == rs.tobytes()
     np.testing.assert_array_equal(n2, ns)
+
+
+@pytest.mark.gpu
+def test_python_handler_from_raw_features_equals_sequence_call(engine):
+    """The Python mirror of the reference's main loop (initialize / insertStereoPair / optimizePose / updateFrame, frames built by
+    handler.stereo_features from raw stereo features) walks a sequence frame by frame; its poses equal the batched sequence call
+    chained on the host."""
+    from stvo_pl_b200 import handler as Hd
+    NF = 5
+    frames, rel, cam = SS.make_stereo_sequence(NF, n_pt=700, n_ls=140, seed=12)
+    cfg = T.kitti_config()
+    h = Hd.StereoFrameHandler(cam, cfg, engine)
+    h.initialize(Hd.stereo_features(engine, cam, SS.stereo_frames_slice(frames, 0, 1)))
+    poses = []
+    for k in range(1, NF):
+        h.insertStereoPair(Hd.stereo_features(engine, cam, SS.stereo_frames_slice(frames, k, k + 1)), k)
+        h.optimizePose()
+        poses.append((h.curr_frame.DT.copy(), h.curr_frame.Tfw.copy(), h.n_inliers))
+        h.needNewKF()
+        h.updateFrame()
+    res, _ = engine.track_stereo_sequence(cam, cfg, T.default_stereo_match_config(), T.default_stereo_config(), frames)
+    chained = Hd.chain_poses(res.copy())
+    for k in range(NF - 1):
+        np.testing.assert_allclose(poses[k][0], res["DT"][k], atol=1e-12)
+        np.testing.assert_allclose(poses[k][1], chained["Tfw"][k], atol=1e-9)
+        assert poses[k][2] == res["n_inliers"][k]
