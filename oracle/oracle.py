@@ -34,6 +34,9 @@ def _stale(lib: str) -> bool:
 def lib_path(native: bool = False) -> str:
     """Portable build (x86-64-v3: AVX2 + POPCNT) travels with the repo; the native build used for the CPU
     baseline is compiled on the machine that times it (-march=native, the reference's own flag)."""
+    override = os.environ.get("PLSTVO_ORACLE_LIB")   # e.g. an -fsanitize=address,undefined build (tools/oracle_asan.sh)
+    if override:
+        return override
     if not native:
         lib = os.path.join(_HERE, "libplstvo_oracle.so")
         if _stale(lib):
