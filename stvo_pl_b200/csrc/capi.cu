@@ -242,6 +242,8 @@ int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfi
     const long want = 3L * ctx->sm_count;   // about one full wave of resident K1 CTAs
     int split = 1;
     if (base_tiles > 0 && base_tiles < want) split = (int)((want + base_tiles - 1) / base_tiles);
+    static const int forced_split = getenv("PLSTVO_K1_SPLIT") ? atoi(getenv("PLSTVO_K1_SPLIT")) : 0;   // tuning knob
+    if (forced_split > 0) split = forced_split;
 
     ws.problems.assign((size_t)2 * B, MatchProblem{});
     ws.tiles.clear();
