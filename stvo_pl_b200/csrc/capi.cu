@@ -242,8 +242,11 @@ int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfi
     const long want = 3L * ctx->sm_count;   // about one full wave of resident K1 CTAs
     int split = 1;
     if (base_tiles > 0 && base_tiles < want) split = (int)((want + base_tiles - 1) / base_tiles);
+    // Big batches too: four train blocks per problem (tiles of 512 queries x ~n2/4 trains, at least 256).  Finer tiles shrink
+    // the tail of the last wave of CTAs (2560 tiles of 0.57 ms on 444 slots = 5.77 waves); measured on C2: K1 3.32 -> 3.12 ms,
+    // 129.0 -> 132.4 K solves/s, the blocking call 99 -> 109 K; beyond 4 the extra partials cost K2 more than K1 gains.
     static const int forced_split = getenv("PLSTVO_K1_SPLIT") ? atoi(getenv("PLSTVO_K1_SPLIT")) : 0;   // tuning knob
-    if (forced_split > 0) split = forced_split;
+    split = forced_split > 0 ? forced_split : std::max(split, 4);
 
     ws.problems.assign((size_t)2 * B, MatchProblem{});
     ws.tiles.clear();
