@@ -85,3 +85,30 @@ def test_degenerate_sizes(oracle):
     assert n == 0 and (m == -1).all()
     n, m = oracle.match(d[:0], d, 0.9)
     assert n == 0 and len(m) == 0
+
+
+def test_mutual_matching_is_symmetric_property(oracle):
+    """StVO::match with bestLRMatches (src/matching.cpp:63-91): i -> j survives only if j -> i in the reverse problem, so the
+    result of match(d2, d1) is the inverse map of match(d1, d2).  Randomised over sizes, entropies and ratios."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(2, 70), st.integers(2, 70), st.integers(0, 2**31 - 1), st.sampled_from([0.6, 0.75, 0.9, 1.0]),
+           st.sampled_from(["random", "ties"]))
+    def prop(n1, n2, seed, nnr, mode):
+        rng = np.random.default_rng(seed)
+        if mode == "ties":
+            d1 = (rng.integers(0, 2, (n1, 32), dtype=np.uint8) * 255).astype(np.uint8)
+            d2 = (rng.integers(0, 2, (n2, 32), dtype=np.uint8) * 255).astype(np.uint8)
+        else:
+            d1 = rng.integers(0, 256, (n1, 32), dtype=np.uint8)
+            d2 = rng.integers(0, 256, (n2, 32), dtype=np.uint8)
+            k = min(n1, n2) // 2                      # plant near-duplicates so that matches exist
+            d2[:k] = d1[:k] ^ (rng.random((k, 32)) < 0.05).astype(np.uint8)
+        n12, m12 = oracle.match(d1, d2, nnr, True)
+        n21, m21 = oracle.match(d2, d1, nnr, True)
+        assert n12 == n21 == int((m12 >= 0).sum())
+        for i, j in enumerate(m12):
+            if j >= 0:
+                assert m21[j] == i
+    prop()
