@@ -373,7 +373,7 @@ def run_ours(args):
         "config": {"workload": WORKLOADS[ACTIVE][3], "pairs_per_gpu": B, "global_pairs_per_step": world * B,
                    "parallelism": f"independent pairs sharded over {world} GPU(s), no collective",
                    "l2": f"inputs larger than L2: {(h2d + kt['n_tiles'] * 0) / 1e6:.0f} MB of inputs + "
-                         f"{B * 156000 / 1e6:.0f} MB of tile partials per pass vs 126 MB L2",
+                         f"{B * 140000 / 1e6:.0f} MB of tile partials per pass vs 126 MB L2",
                    "overlap": 1.0, "outlier_frac": 0.10, "solved_ok": good, "e2e_equals_resident": bool(same),
                    "numa_bound": numa},
         "clocks": clk.summary(),
