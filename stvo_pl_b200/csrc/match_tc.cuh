@@ -1,0 +1,44 @@
+// match_tc.cuh — work description of the tensor-core form of K1 (match_tc.cu).  Internal, not part of the boundary.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace plstvo {
+
+constexpr int TC_ROWS = 128;                    // descriptor rows per operand tile (UMMA M and N)
+constexpr int TC_TILE_BYTES = TC_ROWS * 256;    // 128 rows x 256 e4m3 bytes, swizzled K-major layout
+constexpr int TC_XSTAGES = 4;                   // query tiles in flight (shared memory ring)
+constexpr int TC_ASTAGES = 2;                   // accumulator stages in TMEM (256 columns each)
+constexpr int TC_THREADS = 320;                 // producer warp + MMA warp + 8 epilogue warps
+
+// one descriptor matrix to expand (queries or trains of one matching problem)
+struct TcSide {
+    const uint8_t* src;   // [n][32] descriptor rows
+    int32_t n;
+    uint8_t* dst;         // ceil(n / 128) tiles of TC_TILE_BYTES
+};
+
+// one matching problem = StVO::match(desc1, desc2): queries stream through the M side, trains sit on the N side
+struct TcProblem {
+    const uint8_t* xe;    // expanded queries  (desc1): ceil(n1 / 128) tiles
+    const uint8_t* ye;    // expanded trains   (desc2): ceil(n2 / 128) tiles
+    int32_t n1, n2;
+    uint2* rowp;          // [ceil(n2 / 128)][n1]: {best | second << 16 (f16 bits of 256 - 2 d), candidate tag}
+    uint2* colp;          // [n2]:                 {best | second << 16, lane tag}
+};
+
+// one work item of the persistent kernel: all query tiles of a problem against 256 trains
+struct TcItem {
+    int32_t problem;
+    int32_t yblk;
+};
+
+size_t tc_smem_bytes();
+cudaError_t launch_tc_expand(const TcSide* sides, int n_sides, int max_tiles, cudaStream_t stream);
+cudaError_t launch_tc_hamming(const TcProblem* problems, const TcItem* items, int n_items, int grid, __half* debug_tile,
+                              cudaStream_t stream);
+// writes MatchProblem::rowpart[0][n1] / colpart[0][n2] (ntb = nqb = 1) in K1's packed-key format
+cudaError_t launch_tc_resolve(const MatchProblem* mps, const TcProblem* tps, int n_problems, int slices, cudaStream_t stream);
+
+}  // namespace plstvo
