@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "match_tc.cuh"
 
 using namespace plstvo;
 
@@ -61,12 +62,21 @@ struct Workspace {
     DevBuf d_priors, d_results, d_m12p, d_m12l, d_inlp, d_inll;
     DevBuf d_rowpart, d_colpart, d_problems, d_tiles, d_feat;
     DevBuf d_phase;   // debug phase timers (PLSTVO_PHASE_DEBUG)
+    // tensor-core form of K1 (match_tc.cu): expanded operands, per-block value partials, work items
+    bool use_tc = true;
+    std::vector<TcProblem> tc_problems;   // [2B], parallel to `problems`
+    std::vector<TcSide> tc_sides;         // [4B]: queries, trains of every problem
+    std::vector<TcItem> tc_items;
+    std::vector<int32_t> item_start;      // [B+1] first work item of each pair
+    int tc_max_tiles = 0;
+    DevBuf d_tcprob, d_tcsides, d_tcitems, d_exp, d_rowp, d_colp;
     size_t feat_stride = 0;
     void release() {
         DevBuf* all[] = {&d_poff1, &d_poff2, &d_loff1, &d_loff2, &d_pdesc1, &d_pdesc2, &d_ldesc1, &d_ldesc2,
                          &d_ptP, &d_pts2, &d_ptpl, &d_lssP, &d_lseP, &d_lsspl, &d_lsepl, &d_lss2, &d_lslev,
                          &d_lsle, &d_priors, &d_results, &d_m12p, &d_m12l, &d_inlp, &d_inll, &d_rowpart,
-                         &d_colpart, &d_problems, &d_tiles, &d_feat, &d_phase};
+                         &d_colpart, &d_problems, &d_tiles, &d_feat, &d_phase, &d_tcprob, &d_tcsides, &d_tcitems,
+                         &d_exp, &d_rowp, &d_colp};
         for (DevBuf* b : all) b->release();
     }
 };
@@ -154,7 +164,16 @@ int pow2_ceil_host(int n) {
 
 // ---- planning -------------------------------------------------------------------------------------
 // target_ctas: how many K1 tiles we would like at least, so that small batches still fill the chip
-void plan_problem(MatchProblem& pr, int n1, int n2, bool enabled, float nnr, int best_lr, int tsplit_hint) {
+// PLSTVO_K1=popc selects the integer (XOR + POPC) form of K1; the default is the tensor-core form (match_tc.cu)
+bool k1_use_tc() {
+    static const bool tc = [] {
+        const char* v = getenv("PLSTVO_K1");
+        return !(v && !strcmp(v, "popc"));
+    }();
+    return tc;
+}
+
+void plan_problem(MatchProblem& pr, int n1, int n2, bool enabled, float nnr, int best_lr, int tsplit_hint, bool use_tc) {
     pr.n1 = n1;
     pr.n2 = n2;
     pr.nnr = nnr;
@@ -162,6 +181,11 @@ void plan_problem(MatchProblem& pr, int n1, int n2, bool enabled, float nnr, int
     pr.enabled = (enabled && n1 > 0 && n2 > 0) ? 1 : 0;   // src/stereoFrameHandler.cpp:137-138, :160-161
     if (!pr.enabled) {
         pr.nqb = pr.ntb = 0;
+        pr.tsplit = 32;
+        return;
+    }
+    if (use_tc) {   // tc_resolve_kernel leaves ONE merged partial per row and per column
+        pr.nqb = pr.ntb = 1;
         pr.tsplit = 32;
         return;
     }
@@ -224,6 +248,7 @@ int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfi
     }
     ws.planned = false;
     ws.B = B;
+    ws.use_tc = k1_use_tc();
     if (cam) ws.cam = *cam;
     ws.cfg = *cfg;
     ws.has_priors = has_priors;
@@ -254,10 +279,16 @@ int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfi
     ws.max_tsplit = 32;
     ws.cap_pt = ws.cap_ls = 0;
     ws.max_n2 = 0;
-    size_t row_elems = 0, col_elems = 0;
+    size_t row_elems = 0, col_elems = 0, exp_tiles = 0, rowp_elems = 0, colp_elems = 0;
+    ws.tc_problems.assign(ws.use_tc ? (size_t)2 * B : 0, TcProblem{});
+    ws.tc_sides.assign(ws.use_tc ? (size_t)4 * B : 0, TcSide{});
+    ws.tc_items.clear();
+    ws.item_start.assign((size_t)B + 1, 0);
+    ws.tc_max_tiles = 0;
     const float nnr_p = (float)cfg->min_ratio_12_p, nnr_l = (float)cfg->min_ratio_12_l;   // double -> float at the call
     for (int p = 0; p < B; ++p) {
         ws.tile_start[p] = (int32_t)ws.tiles.size();
+        ws.item_start[p] = (int32_t)ws.tc_items.size();
         for (int type = 0; type < 2; ++type) {
             MatchProblem& pr = ws.problems[(size_t)2 * p + type];
             const int n1 = type ? ws.l_off1[p + 1] - ws.l_off1[p] : ws.p_off1[p + 1] - ws.p_off1[p];
@@ -268,7 +299,25 @@ int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfi
                 if (hint < 256) hint = 256;
             }
             plan_problem(pr, n1, n2, type ? cfg->has_lines != 0 : cfg->has_points != 0, type ? nnr_l : nnr_p,
-                         cfg->best_lr_matches != 0, hint);
+                         cfg->best_lr_matches != 0, hint, ws.use_tc);
+            if (ws.use_tc) {
+                // operands and partials as element / tile indices first, fixed up after allocation
+                const int t1 = pr.enabled ? (n1 + TC_ROWS - 1) / TC_ROWS : 0, t2 = pr.enabled ? (n2 + TC_ROWS - 1) / TC_ROWS : 0;
+                TcProblem& tp = ws.tc_problems[(size_t)2 * p + type];
+                tp.n1 = n1;
+                tp.n2 = n2;
+                tp.xe = reinterpret_cast<const uint8_t*>(exp_tiles);
+                tp.ye = reinterpret_cast<const uint8_t*>(exp_tiles + t1);
+                tp.rowp = reinterpret_cast<uint2*>(rowp_elems);
+                tp.colp = reinterpret_cast<uint2*>(colp_elems);
+                ws.tc_sides[(size_t)4 * p + 2 * type] = TcSide{nullptr, pr.enabled ? n1 : 0, nullptr};
+                ws.tc_sides[(size_t)4 * p + 2 * type + 1] = TcSide{nullptr, pr.enabled ? n2 : 0, nullptr};
+                exp_tiles += (size_t)t1 + t2;
+                rowp_elems += (size_t)t2 * n1;
+                colp_elems += (size_t)(pr.enabled ? n2 : 0);
+                ws.tc_max_tiles = std::max(ws.tc_max_tiles, std::max(t1, t2));
+                for (int yb = 0; yb < (t2 + 1) / 2; ++yb) ws.tc_items.push_back(TcItem{2 * p + type, yb});
+            }
             // offsets into the partial buffers are stored as element indices first, fixed up after allocation
             pr.rowpart = reinterpret_cast<uint2*>(row_elems);
             pr.colpart = reinterpret_cast<uint2*>(col_elems);
@@ -283,15 +332,18 @@ int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfi
         }
     }
     ws.tile_start[B] = (int32_t)ws.tiles.size();
+    ws.item_start[B] = (int32_t)ws.tc_items.size();
     ws.cap_pt = std::max(ws.cap_pt, 1);
     ws.cap_ls = std::max(ws.cap_ls, 1);
     ws.sort_cap = pow2_ceil_host(std::max(std::max(ws.cap_pt, ws.cap_ls), (ws.max_n2 + 1) / 2));
     // matched lists live in shared memory when they fit (C2: 152 KB), else in a global scratch slice (C5)
     static const bool no_smem = getenv("PLSTVO_K2_FEAT_GLOBAL") != nullptr;
     ws.feat_in_smem = !no_smem && k2_smem_bytes(ws.cap_pt, ws.cap_ls, ws.sort_cap, true) <= ctx->smem_optin;
-    if (!ws.feat_in_smem && k2_smem_bytes(ws.cap_pt, ws.cap_ls, ws.sort_cap, false) > ctx->smem_optin)
+    // the per-pair solver's limits only apply when it runs (track mode): matching-only calls take any frame up to
+    // PLSTVO_MAX_FEATURES rows
+    if (with_features && !ws.feat_in_smem && k2_smem_bytes(ws.cap_pt, ws.cap_ls, ws.sort_cap, false) > ctx->smem_optin)
         return fail(ctx, PLSTVO_E_TOO_LARGE, "frame too large for the per-pair solver's shared memory");
-    if (k1_smem_bytes(ws.max_tsplit) > ctx->smem_optin)
+    if (!ws.use_tc && k1_smem_bytes(ws.max_tsplit) > ctx->smem_optin)
         return fail(ctx, PLSTVO_E_TOO_LARGE, "train set too large for one K1 tile");
 
     // --- device storage ---
@@ -305,6 +357,14 @@ int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfi
     CK(ctx, ws.d_colpart.ensure(col_elems * sizeof(uint2)));
     CK(ctx, ws.d_problems.ensure(ws.problems.size() * sizeof(MatchProblem)));
     CK(ctx, ws.d_tiles.ensure(ws.tiles.size() * sizeof(MatchTile)));
+    if (ws.use_tc) {
+        CK(ctx, ws.d_exp.ensure(exp_tiles * TC_TILE_BYTES + 1024));
+        CK(ctx, ws.d_rowp.ensure(rowp_elems * sizeof(uint2)));
+        CK(ctx, ws.d_colp.ensure(colp_elems * sizeof(uint2)));
+        CK(ctx, ws.d_tcprob.ensure(ws.tc_problems.size() * sizeof(TcProblem)));
+        CK(ctx, ws.d_tcsides.ensure(ws.tc_sides.size() * sizeof(TcSide)));
+        CK(ctx, ws.d_tcitems.ensure(ws.tc_items.size() * sizeof(TcItem)));
+    }
     if (with_features) {
         CK(ctx, ws.d_poff1.ensure((B + 1) * 4));
         CK(ctx, ws.d_poff2.ensure((B + 1) * 4));
@@ -344,8 +404,31 @@ int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfi
                 pr.d2 = ws.d_ldesc2.as<uint8_t>() + (size_t)ws.l_off2[p] * 32;
                 pr.m12 = ws.d_m12l.as<int32_t>() + ws.l_off1[p];
             }
+            if (ws.use_tc) {
+                TcProblem& tp = ws.tc_problems[(size_t)2 * p + type];
+                uint8_t* ebase = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws.d_exp.p) + 1023) & ~(uintptr_t)1023);
+                uint8_t* xe = ebase + reinterpret_cast<size_t>(tp.xe) * TC_TILE_BYTES;
+                uint8_t* ye = ebase + reinterpret_cast<size_t>(tp.ye) * TC_TILE_BYTES;
+                tp.xe = xe;
+                tp.ye = ye;
+                tp.rowp = ws.d_rowp.as<uint2>() + reinterpret_cast<size_t>(tp.rowp);
+                tp.colp = ws.d_colp.as<uint2>() + reinterpret_cast<size_t>(tp.colp);
+                ws.tc_sides[(size_t)4 * p + 2 * type].src = pr.d1;
+                ws.tc_sides[(size_t)4 * p + 2 * type].dst = xe;
+                ws.tc_sides[(size_t)4 * p + 2 * type + 1].src = pr.d2;
+                ws.tc_sides[(size_t)4 * p + 2 * type + 1].dst = ye;
+            }
         }
     cudaStream_t s = ctx->s_h2d;
+    if (ws.use_tc && !ws.tc_problems.empty()) {
+        CK(ctx, cudaMemcpyAsync(ws.d_tcprob.p, ws.tc_problems.data(), ws.tc_problems.size() * sizeof(TcProblem),
+                                cudaMemcpyHostToDevice, s));
+        CK(ctx, cudaMemcpyAsync(ws.d_tcsides.p, ws.tc_sides.data(), ws.tc_sides.size() * sizeof(TcSide),
+                                cudaMemcpyHostToDevice, s));
+        if (!ws.tc_items.empty())
+            CK(ctx, cudaMemcpyAsync(ws.d_tcitems.p, ws.tc_items.data(), ws.tc_items.size() * sizeof(TcItem),
+                                    cudaMemcpyHostToDevice, s));
+    }
     if (!ws.problems.empty())
         CK(ctx, cudaMemcpyAsync(ws.d_problems.p, ws.problems.data(), ws.problems.size() * sizeof(MatchProblem),
                                 cudaMemcpyHostToDevice, s));
@@ -398,6 +481,18 @@ int ws_upload_range(PlContext* ctx, Workspace& ws, const PlFrameBatch* prev, con
 }
 
 int ws_launch_match(PlContext* ctx, Workspace& ws, int p0, int p1, cudaStream_t s) {
+    if (ws.use_tc) {
+        const int i0 = ws.item_start[p0], i1 = ws.item_start[p1];
+        if (i1 > i0) {
+            CK(ctx, launch_tc_expand(ws.d_tcsides.as<TcSide>() + (size_t)4 * p0, 4 * (p1 - p0), ws.tc_max_tiles, s));
+            CK(ctx, launch_tc_hamming(ws.d_tcprob.as<TcProblem>(), ws.d_tcitems.as<TcItem>() + i0, i1 - i0, ctx->sm_count,
+                                      nullptr, s));
+            CK(ctx, launch_tc_resolve(ws.d_problems.as<MatchProblem>() + (size_t)2 * p0, ws.d_tcprob.as<TcProblem>() + (size_t)2 * p0,
+                                      2 * (p1 - p0), 4, s));
+            ctx->launches += 3;
+        }
+        return 0;
+    }
     const int t0 = ws.tile_start[p0], t1 = ws.tile_start[p1];
     if (t1 > t0) {
         CK(ctx, launch_hamming_knn2(ws.d_problems.as<MatchProblem>(), ws.d_tiles.as<MatchTile>() + t0, t1 - t0,
@@ -1559,15 +1654,16 @@ int plstvo_track_batch_async(PlContext* ctx, const PlCamera* cam, const PlConfig
 
 int plstvo_wait(PlContext* ctx, int ticket) {
     if (!ctx || ticket < 0 || ticket > 1) return PLSTVO_E_INVALID;
-    CK(ctx, cudaSetDevice(ctx->device));
     cudaEvent_t ev = nullptr;
     {
         LOCK(ctx);
+        CK(ctx, cudaSetDevice(ctx->device));
         if (ctx->slot_busy[ticket]) ev = ctx->slot_done[ticket];
     }
     if (ev) {   // wait outside the lock: other threads may keep enqueueing on this context
-        CK(ctx, cudaEventSynchronize(ev));
-        LOCK(ctx);
+        const cudaError_t e = cudaEventSynchronize(ev);
+        LOCK(ctx);   // ctx->err is only ever written under the lock
+        CK(ctx, e);
         ctx->slot_busy[ticket] = false;
     }
     return 0;

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "../../include/plstvo.h"
 
 namespace plstvo {
@@ -173,6 +175,8 @@ cudaError_t launch_gn_eval_stream(const PlCamera& cam, const PlConfig& cfg, cons
 // cudaFuncSetAttribute is per device: a process may drive several GPUs (one context each), so the opted-in dynamic
 // shared-memory size is remembered per device (`done`: one slot per device ordinal, zero-initialised by the caller).
 inline cudaError_t ensure_dynamic_smem(const void* fn, size_t bytes, size_t* done /* [64] */) {
+    static std::mutex mu;   // the caches are per function, contexts (and their locks) are per device: two contexts on one
+    std::lock_guard<std::mutex> lock(mu);   // device may launch the same kernel concurrently
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;

@@ -19,7 +19,8 @@ namespace plstvo {
 
 namespace {
 
-constexpr int MG_CAP = 128;        // candidates per query window; pair keys pack (query:16 | slot:7 | distance:9)
+constexpr int MG_CAP = 128;        // candidates per query window on the fast path (pair keys pack query:16 | slot:7 | distance:9);
+                                   // a frame with a fuller window falls back to mg_sequential (no limit)
 constexpr int MG_THREADS = 512;    // one CTA per frame: the work is a few thousand short dependent chains, so width buys latency
 
 __device__ __forceinline__ int mg_distance(const uint8_t* a, const uint8_t* b) {   // StVO::distance (:93-109)
@@ -66,6 +67,100 @@ __device__ int mg_block_exclusive_scan(int* data, int n, int* s_tmp /* >= MG_THR
     for (int i = lo; i < hi; i++) { const int v = data[i]; data[i] = run; run += v; }
     __syncthreads();
     return s_tmp[MG_THREADS];
+}
+
+
+// ---- overflow path: more than MG_CAP candidates in one query window --------------------------------------------------
+// The reference has no limit (the candidates are an unordered_set, src/matching.cpp:128-139, :213-224).  A frame that
+// overflows the fixed per-query segments of the fast path is re-run here by the reference's own schedule: queries one
+// after the other (the gate's running minimum `distances[i2]` is loop-carried, :145-150), the whole CTA sharing the
+// candidates of the current query.  Exact, about 3 us per query: the price is paid only by the dense frame.
+template <bool LINES>
+__device__ void mg_sequential(const GridProblem& pr, const GridParams& prm, const int* cell_start, int* s_tmp) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n1 = pr.n1, n2 = pr.n2;
+    int* dist = pr.t_start;      // distances[i2] (:124), INT_MAX = none yet
+    int* stamp = pr.t_count;     // last query that enumerated train i2: de-duplicates like the unordered_set
+    for (int t = tid; t < n2; t += MG_THREADS) { dist[t] = 0x7FFFFFFF; stamp[t] = -1; pr.m21[t] = -1; }
+    __syncthreads();
+    int matches = 0;             // thread 0 only
+    for (int q = 0; q < n1; ++q) {
+        const int* qc = pr.q_cell + (size_t)q * (LINES ? 4 : 2);
+        double vx = 0.0, vy = 0.0;
+        if (LINES) {
+            vx = (double)(qc[2] - qc[0]);
+            vy = (double)(qc[3] - qc[1]);
+            const double mag = sqrt(vx * vx + vy * vy);
+            vx /= mag;
+            vy /= mag;
+        }
+        const uint8_t* dq = pr.d1 + (size_t)q * 32;
+        int b1 = 0x7FFFFFFF, b2 = 0x7FFFFFFF, bi = -1, any = 0;
+        for (int e = 0; e < (LINES ? 2 : 1); ++e) {
+            const int x = qc[2 * e], y = qc[2 * e + 1];
+            const int min_x = max(0, x - prm.w.left), max_x = min(prm.cols, x + prm.w.right + 1);
+            const int min_y = max(0, y - prm.w.up), max_y = min(prm.rows, y + prm.w.down + 1);
+            const int wx = max(0, max_x - min_x), wy = max(0, max_y - min_y);
+            for (int c = warp; c < wx * wy; c += MG_THREADS / 32) {   // one warp per cell, one lane per item
+                const int cell = (min_x + c / wy) * prm.rows + (min_y + c % wy);
+                for (int it = cell_start[cell] + lane; it < cell_start[cell + 1]; it += 32) {
+                    const int i2 = pr.grid_items[it];
+                    if (atomicExch(&stamp[i2], q) == q) continue;   // already in this query's candidate set
+                    any = 1;
+                    if (LINES) {
+                        const double dt = vx * pr.t_dir[2 * i2] + vy * pr.t_dir[2 * i2 + 1];
+                        if (fabs(dt) < prm.line_sim_th) continue;    // NaN passes (:221)
+                    }
+                    const int d = mg_distance(dq, pr.d2 + (size_t)i2 * 32);
+                    if (prm.best_lr) {          // each train appears once per query: no race on dist[i2]
+                        if (d < dist[i2]) { dist[i2] = d; pr.m21[i2] = q; } else continue;
+                    }
+                    if (d < b1) { b2 = b1; b1 = d; bi = i2; }
+                    else if (d < b2) b2 = d;
+                }
+            }
+        }
+        // block-wide best / second best with multiplicity; the smallest distance's train (lowest index on a tie)
+        for (int o = 16; o; o >>= 1) {
+            const int c1 = __shfl_xor_sync(0xFFFFFFFFu, b1, o), c2 = __shfl_xor_sync(0xFFFFFFFFu, b2, o),
+                      ci = __shfl_xor_sync(0xFFFFFFFFu, bi, o), ca = __shfl_xor_sync(0xFFFFFFFFu, any, o);
+            const int m2 = min(max(b1, c1), min(b2, c2));
+            if (c1 < b1 || (c1 == b1 && ci >= 0 && (bi < 0 || ci < bi))) bi = ci;
+            b1 = min(b1, c1);
+            b2 = m2;
+            any |= ca;
+        }
+        if (lane == 0) { s_tmp[4 * warp] = b1; s_tmp[4 * warp + 1] = b2; s_tmp[4 * warp + 2] = bi; s_tmp[4 * warp + 3] = any; }
+        __syncthreads();
+        if (tid == 0) {
+            b1 = b2 = 0x7FFFFFFF; bi = -1; any = 0;
+            for (int w = 0; w < MG_THREADS / 32; ++w) {
+                const int c1 = s_tmp[4 * w], c2 = s_tmp[4 * w + 1], ci = s_tmp[4 * w + 2];
+                const int m2 = min(max(b1, c1), min(b2, c2));
+                if (c1 < b1 || (c1 == b1 && ci >= 0 && (bi < 0 || ci < bi))) bi = ci;
+                b1 = min(b1, c1);
+                b2 = m2;
+                any |= s_tmp[4 * w + 3];
+            }
+            int i2 = -1;
+            if (any && (double)b1 < (double)b2 * prm.ratio) { i2 = bi; matches++; }   // :160-163
+            pr.m12[q] = i2;
+        }
+        __syncthreads();
+    }
+    // mutual filter (:166-174)
+    __shared__ int s_drop;
+    if (tid == 0) s_drop = 0;
+    __syncthreads();
+    if (prm.best_lr) {
+        int drop = 0;
+        for (int q = tid; q < n1; q += MG_THREADS) {
+            const int i2 = pr.m12[q];
+            if (i2 >= 0 && pr.m21[i2] != q) { pr.m12[q] = -1; drop++; }
+        }
+        if (drop) atomicAdd(&s_drop, drop);
+    }
+    __syncthreads();
+    if (tid == 0 && pr.count) *pr.count = matches - s_drop;
 }
 
 template <bool LINES>
@@ -167,8 +262,8 @@ __global__ void __launch_bounds__(MG_THREADS) match_grid_kernel(const GridProble
         if (overflow) s_flag = 1;
     }
     __syncthreads();
-    if (s_flag) {   // more than CAP candidates in one window: report, never guess
-        if (tid == 0 && pr.count) *pr.count = PLSTVO_E_TOO_LARGE;
+    if (s_flag) {   // more than CAP candidates in one window: this frame takes the sequential, unbounded path
+        mg_sequential<LINES>(pr, prm, cell_start, s_tmp);
         return;
     }
 
