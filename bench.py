@@ -193,6 +193,18 @@ def measured_peak():
     return 6650.0, "fallback"
 
 
+def measured_tensor_peak():
+    """fp8 (e4m3) dense peak for the tensor roofline: MEASURED_PEAKS.json holds the cuBLAS bf16 burst figure; the 8-bit kinds
+    run at twice the 16-bit rate on this part (nominal 4.5 vs 2.25 PFLOP/s), so 2 x the measured bf16 number is used."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return 2.0 * float(json.load(open(p))["bf16_tflops"]), "2 x measured cuBLAS bf16 burst (fp8 runs at twice the bf16 rate)"
+        except Exception:
+            pass
+    return 2.0 * 1590.0, "2 x fallback bf16"
+
+
 def ncu_traffic(name="k1_traffic.json"):
     """dram bytes per launch of a kernel from the committed ncu capture (profiles/), or None."""
     p = os.path.join(ROOT, "profiles", name)
@@ -335,7 +347,10 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    numa = bind_to_gpu_numa(local) if world > 1 else None          # one process per GPU: keep pinned buffers socket-local
+    # pinned buffers are allocated with the process bound to the GPU's NUMA node (at N = 1 too: the 1-GPU lease may sit on
+    # either socket); the affinity is restored afterwards so that the cpu_baseline leg still sees every usable core
+    affinity0 = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa(local)
     eng = Engine(local)
     cfg = workload_config()
     B = args.pairs
@@ -363,50 +378,76 @@ def run_ours(args):
     out = db.download()
     good = int(out["results"]["good"].sum())
 
-    # ---------------- roofline of the dominant kernel (K1, hamming_knn2), rank 0 ----------------
-    kt = db.kernel_times(iters=max(3, min(args.steps, 10)))
+    # ---------------- per-kernel times and the roofline of the dominant kernel, rank 0 ----------------
+    st = db.stage_times(iters=max(5, min(args.steps, 20)))
+    kt = {"ms_match": st["ms_expand"] + st["ms_distance"] + st["ms_resolve"], "ms_solve": st["ms_solve"], "n_tiles": st["n_items"]}
     n1p = int(prev.pt_off[-1]); n1l = int(prev.ls_off[-1]); n2p = int(curr.pt_off[-1]); n2l = int(curr.ls_off[-1])
     k1_bytes = 32 * (n1p + n2p + n1l + n2l) + 4 * (n1p + n1l)          # descriptors in + match indices out
-    step_bytes = k1_bytes + 32 * int(out["results"]["n_matched_pt"].sum()) + \
-        64 * int(out["results"]["n_matched_ls"].sum()) + 632 * B        # SURVEY 8(d) compulsory bytes per solve
+    n_mp, n_ml = int(out["results"]["n_matched_pt"].sum()), int(out["results"]["n_matched_ls"].sum())
+    k2_bytes = 32 * n_mp + 64 * n_ml + 632 * B                          # matched records in (fp32-packed size) + results out
+    step_bytes = k1_bytes + k2_bytes                                    # SURVEY 8(d) compulsory bytes per solve, summed
     peak, peak_kind = measured_peak()
+    tpeak, tpeak_kind = measured_tensor_peak()
     pair_dists = sum(int((prev.pt_off[p + 1] - prev.pt_off[p])) * int((curr.pt_off[p + 1] - curr.pt_off[p])) +
                      int((prev.ls_off[p + 1] - prev.ls_off[p])) * int((curr.ls_off[p + 1] - curr.ls_off[p]))
                      for p in range(B))
-    popc_rate = eng.popc_rate()
-    achieved = k1_bytes / (kt["ms_match"] * 1e-3) / 1e9
-    traffic = ncu_traffic()
-    roofline = {
-        "kernel": "hamming_knn2_kernel (K1)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "peak_kind": f"of {peak_kind}",
-        "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
-        "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": kt["ms_match"], "ctas_per_launch": kt["n_tiles"],
-        "share_of_step": kt["ms_match"] / (kt["ms_match"] + kt["ms_solve"]),
-        "note": "K1 is integer-ALU (POPC) bound, not HBM bound: see `alu` and `pipes`; the path's HBM-bound kernel is reported in "
-                "`roofline_hbm_kernel`",
-        "pipes": {"alu_pipe_pct_of_peak": traffic.get("alu_pipe_pct") if traffic else None,
-                  "xu_popc_pipe_pct_of_peak": traffic.get("xu_pipe_pct") if traffic else None,
-                  "source": "ncu --set full capture summarised in " + (traffic.get("capture", "profiles/") if traffic else "profiles/")},
-        "alu": {"unit": "G pair-distances/s", "achieved": pair_dists / (kt["ms_match"] * 1e-3) / 1e9,
-                "peak": popc_rate / 8 / 1e9, "frac": 8 * pair_dists / (kt["ms_match"] * 1e-3) / popc_rate,
-                "peak_kind": "measured POPC issue rate (plstvo_popc_rate micro-benchmark, same process) / 8 POPC per "
-                             "256-bit distance = the XU-pipe bound of the straightforward XOR+POPC matcher; the kernel "
-                             "folds the 8 XOR words with carry-save adders (6 LOP3) into 5 POPC, so frac > 1 is possible",
-                "popc32_per_s_measured": popc_rate},
-        "k2": {"kernel": "track_solve_kernel (K2)", "ms_per_launch": kt["ms_solve"], "ctas_per_launch": kt["n_pairs"]},
-        "step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes * args.steps / (ms * 1e-3) / 1e9,
-                 "frac": step_bytes * args.steps / (ms * 1e-3) / 1e9 / peak},
+    step_ms = sum(st[k] for k in ("ms_expand", "ms_distance", "ms_resolve", "ms_solve"))
+    tc_flops = 2.0 * 256 * pair_dists
+    kernels = {
+        "tc_expand_kernel": {"ms": st["ms_expand"], "bound": "hbm", "algorithmic_bytes": 9 * 32 * (n1p + n2p + n1l + n2l),
+                             "note": "32 B descriptor in, 256 B e4m3 operand row out"},
+        ("tc_hamming_kernel" if st["tensor_core_form"] else "hamming_knn2_kernel"):
+            {"ms": st["ms_distance"], "bound": "tensor" if st["tensor_core_form"] else "alu", "flops": tc_flops,
+             "pair_distances": pair_dists, "work_items": st["n_items"]},
+        "tc_resolve_kernel": {"ms": st["ms_resolve"], "bound": "latency"},
+        "track_solve_kernel": {"ms": st["ms_solve"], "bound": "latency (fp64 pipe in its evaluations)", "algorithmic_bytes": k2_bytes,
+                               "ctas": B},
     }
+    for k in kernels.values():
+        k["share_of_step"] = k["ms"] / step_ms if step_ms > 0 else 0.0
+    dom_name = max(kernels, key=lambda n: kernels[n]["ms"])
+    dom = kernels[dom_name]
+    traffic = ncu_traffic("k_traffic.json") or {}
+    if dom["bound"] == "tensor":
+        achieved = tc_flops / (dom["ms"] * 1e-3) / 1e12
+        roofline = {"kernel": dom_name, "bound": "tensor", "achieved": achieved, "peak": tpeak, "unit": "TFLOP/s",
+                    "frac": achieved / tpeak, "peak_kind": tpeak_kind,
+                    "traffic": (traffic.get(dom_name) or {}).get("dram_bytes_per_launch"),
+                    "algorithmic_flops_per_launch": tc_flops, "ms_per_launch": dom["ms"],
+                    "note": "2 x 256 flop per 256-bit pair distance (the +-1 contraction); the kernel is bound by its top-2 epilogue "
+                            "on the ALU pipe (3 packed min/max per two distances and direction), not by the tensor pipe: see `pipes`"}
+    else:
+        alg = dom.get("algorithmic_bytes", k2_bytes)
+        achieved = alg / (dom["ms"] * 1e-3) / 1e9
+        roofline = {"kernel": dom_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "peak_kind": f"of {peak_kind}", "traffic": (traffic.get(dom_name) or {}).get("dram_bytes_per_launch"),
+                    "algorithmic_bytes_per_launch": alg, "ms_per_launch": dom["ms"],
+                    "note": "one persistent CTA per pair: ~16 dependent evaluate -> reduce -> 6x6 solve rounds; latency-bound, far from "
+                            "the HBM roofline by construction (features are read once into shared memory)"}
+    roofline["share_of_step"] = dom["share_of_step"]
+    roofline["kernels"] = kernels
+    roofline["pipes"] = traffic.get("pipes")
+    roofline["tensor"] = {"kernel": "tc_hamming_kernel", "achieved": tc_flops / (st["ms_distance"] * 1e-3) / 1e12, "peak": tpeak,
+                          "unit": "TFLOP/s", "frac": tc_flops / (st["ms_distance"] * 1e-3) / 1e12 / tpeak, "peak_kind": tpeak_kind,
+                          "pair_distances_per_s": pair_dists / (st["ms_distance"] * 1e-3)} if st["tensor_core_form"] else None
+    roofline["rates"] = {"unit": UNIT, "match_only": B / (kt["ms_match"] * 1e-3), "gn_only": B / (kt["ms_solve"] * 1e-3),
+                         "note": "resident inputs, each stage's kernels timed alone over the whole batch"}
+    roofline["step"] = {"algorithmic_bytes": step_bytes, "achieved": step_bytes * args.steps / (ms * 1e-3) / 1e9,
+                        "frac": step_bytes * args.steps / (ms * 1e-3) / 1e9 / peak}
+    # spread of single steps (the contract's `value` is the mean over the K timed steps above)
+    singles = sorted(db.run_timed(1, flush_l2=False) for _ in range(20))
+    spread = {"single_step_ms": {"min": singles[0], "median": singles[len(singles) // 2], "max": singles[-1]}, "reps": len(singles)}
     db.free()
 
     # ---------------- e2e: host buffers through the C-ABI, H2D + D2H inside the timed region ----------------
     pprev, pcurr = eng.pinned.pin_frames(prev), eng.pinned.pin_frames(curr)
-    # PCIe probe: one pinned copy of the step's input byte count (plain torch plumbing), best of 4 — the floor of any e2e step
+    # PCIe probe: one copy of the step's input byte count out of the library's own pinned allocator (same NUMA node as the
+    # frames above), best of 6 — the floor of any e2e step
     nbytes_in = int(prev.input_bytes("prev") + curr.input_bytes("curr"))
-    psrc = torch.empty(nbytes_in, dtype=torch.uint8).pin_memory()
+    psrc = torch.from_numpy(eng.pinned.empty((nbytes_in,), np.uint8))
     pdst = torch.empty(nbytes_in, dtype=torch.uint8, device=f"cuda:{local}")
     h2d_ms = 1e9
-    for _ in range(4):
+    for _ in range(6):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         ev0.record()
@@ -414,7 +455,7 @@ def run_ours(args):
         ev1.record()
         torch.cuda.synchronize()
         h2d_ms = min(h2d_ms, ev0.elapsed_time(ev1))
-    del psrc, pdst
+    del pdst
     pouts = [eng.pinned_outputs(prev), eng.pinned_outputs(prev)]
     pout = pouts[0]
     # (a) the synchronous call, one batch at a time: returns when the results are in host memory
@@ -432,6 +473,7 @@ def run_ours(args):
     # (a') latency of one blocking call on ONE frame pair: what a per-frame caller of insertStereoPair() / optimizePose() sees
     one_p, one_c = eng.pinned.pin_frames(prev.select([0])), eng.pinned.pin_frames(curr.select([0]))
     one_out = eng.pinned_outputs(prev.select([0]))
+    os.sched_setaffinity(0, affinity0)          # every pinned buffer exists now: give the cores back
     lat = []
     for k in range(60):
         t1 = time.perf_counter()
@@ -478,11 +520,57 @@ def run_ours(args):
                 "sync_mode": "plstvo_track_batch, one blocking call per step",
                 "single_pair_latency_ms": single_ms,
                 "h2d_only_ms_per_step": h2d_ms, "h2d_only_gbs": h2d / (h2d_ms * 1e-3) / 1e9,
-                "note": "h2d_only_*: one pinned cudaMemcpy of the step's input bytes alone (the PCIe floor of a step); the "
-                        "pipelined figure hides it behind the previous batch's kernels"},
+                "h2d_gbs_inside_pipelined_loop": h2d / (e2e_s / args.steps) / 1e9,
+                "bound": "PCIe" if h2d_ms > 0.8 * (e2e_s / args.steps * 1e3) else "kernels",
+                "note": "h2d_only_*: one pinned cudaMemcpy of the step's input bytes alone (the PCIe floor of a step); "
+                        "h2d_gbs_inside_pipelined_loop: the same bytes over the pipelined step time (a lower bound of the link rate)"},
         "gpu_launches": int(launches),
         "roofline": roofline,
+        "spread": spread,
     }
+    # ---------------- C4 as BASELINE.json states it: 512 pairs IN TOTAL cut into 512 / N per GPU (strong scaling) ----------------
+    STRONG_TOTAL = 512
+    Bs = max(1, STRONG_TOTAL // world)
+    if world == 1 and B == STRONG_TOTAL:
+        line["strong"] = {"pairs_total": STRONG_TOTAL, "pairs_per_gpu": B, "value": value, "ms_per_step": ms / args.steps,
+                          "e2e_value": e2e_value, "e2e_ms_per_step": e2e_s / args.steps * 1e3, "note": "N = 1: the run above"}
+    else:
+        sp, sc = prev.select(range(min(Bs, B))), curr.select(range(min(Bs, B)))
+        sdb = eng.upload(cam, cfg, sp, sc)
+        for _ in range(5):
+            sdb.run()
+        eng.synchronize()
+        ssteps = max(args.steps, 50)
+        barrier()
+        sms = sdb.run_timed(ssteps, flush_l2=False)
+        barrier()
+        sms = max_over_ranks(sms)
+        sst = sdb.stage_times(iters=5)
+        sdb.free()
+        spp, spc = eng.pinned.pin_frames(sp), eng.pinned.pin_frames(sc)
+        spo = [eng.pinned_outputs(sp), eng.pinned_outputs(sp)]
+        for k in range(4):
+            eng.wait(eng.track_batch_async(cam, cfg, spp, spc, spo[k & 1]))
+        barrier()
+        t0 = time.perf_counter()
+        pending = None
+        for k in range(ssteps):
+            tk = eng.track_batch_async(cam, cfg, spp, spc, spo[k & 1])
+            if pending is not None:
+                eng.wait(pending)
+            pending = tk
+        eng.wait(pending)
+        torch.cuda.synchronize()
+        se2e = time.perf_counter() - t0
+        barrier()
+        se2e = max_over_ranks(se2e)
+        nb = sp.B
+        line["strong"] = {"pairs_total": nb * world, "pairs_per_gpu": nb, "steps": ssteps,
+                          "value": world * nb * ssteps / (sms * 1e-3), "ms_per_step": sms / ssteps,
+                          "e2e_value": world * nb * ssteps / se2e, "e2e_ms_per_step": se2e / ssteps * 1e3,
+                          "stage_ms": {k: sst[k] for k in ("ms_expand", "ms_distance", "ms_resolve", "ms_solve")},
+                          "note": "strong scaling of the named config: the same 512 pairs in total, 512 / N per GPU; compare with the "
+                                  "N = 1 line's value / e2e.value (efficiency = value(N) / (N x value(1)) is the driver's to compute)"}
     if world == 1 and rank == 0 and not args.no_cpu:
         threads, _, _ = cpu_threads_to_use()
         line["cpu_baseline"] = cpu_leg(max(32, 2 * threads), budget_s=20.0)

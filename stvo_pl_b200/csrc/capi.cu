@@ -66,17 +66,17 @@ struct Workspace {
     bool use_tc = true;
     std::vector<TcProblem> tc_problems;   // [2B], parallel to `problems`
     std::vector<TcSide> tc_sides;         // [4B]: queries, trains of every problem
-    std::vector<TcItem> tc_items;
-    std::vector<int32_t> item_start;      // [B+1] first work item of each pair
+    std::vector<TcItem> tc_items[2];      // work items of the point problems (long) and of the line problems (short)
+    std::vector<int32_t> item_start[2];   // [B+1] first work item of each pair in either list
     int tc_max_tiles = 0;
-    DevBuf d_tcprob, d_tcsides, d_tcitems, d_exp, d_rowp, d_colp;
+    DevBuf d_tcprob, d_tcsides, d_tcitems[2], d_exp, d_rowp, d_colp, d_sched;
     size_t feat_stride = 0;
     void release() {
         DevBuf* all[] = {&d_poff1, &d_poff2, &d_loff1, &d_loff2, &d_pdesc1, &d_pdesc2, &d_ldesc1, &d_ldesc2,
                          &d_ptP, &d_pts2, &d_ptpl, &d_lssP, &d_lseP, &d_lsspl, &d_lsepl, &d_lss2, &d_lslev,
                          &d_lsle, &d_priors, &d_results, &d_m12p, &d_m12l, &d_inlp, &d_inll, &d_rowpart,
-                         &d_colpart, &d_problems, &d_tiles, &d_feat, &d_phase, &d_tcprob, &d_tcsides, &d_tcitems,
-                         &d_exp, &d_rowp, &d_colp};
+                         &d_colpart, &d_problems, &d_tiles, &d_feat, &d_phase, &d_tcprob, &d_tcsides, &d_tcitems[0],
+                         &d_tcitems[1], &d_exp, &d_rowp, &d_colp, &d_sched};
         for (DevBuf* b : all) b->release();
     }
 };
@@ -282,13 +282,16 @@ int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfi
     size_t row_elems = 0, col_elems = 0, exp_tiles = 0, rowp_elems = 0, colp_elems = 0;
     ws.tc_problems.assign(ws.use_tc ? (size_t)2 * B : 0, TcProblem{});
     ws.tc_sides.assign(ws.use_tc ? (size_t)4 * B : 0, TcSide{});
-    ws.tc_items.clear();
-    ws.item_start.assign((size_t)B + 1, 0);
+    for (int k = 0; k < 2; ++k) {
+        ws.tc_items[k].clear();
+        ws.item_start[k].assign((size_t)B + 1, 0);
+    }
     ws.tc_max_tiles = 0;
     const float nnr_p = (float)cfg->min_ratio_12_p, nnr_l = (float)cfg->min_ratio_12_l;   // double -> float at the call
     for (int p = 0; p < B; ++p) {
         ws.tile_start[p] = (int32_t)ws.tiles.size();
-        ws.item_start[p] = (int32_t)ws.tc_items.size();
+        ws.item_start[0][p] = (int32_t)ws.tc_items[0].size();
+        ws.item_start[1][p] = (int32_t)ws.tc_items[1].size();
         for (int type = 0; type < 2; ++type) {
             MatchProblem& pr = ws.problems[(size_t)2 * p + type];
             const int n1 = type ? ws.l_off1[p + 1] - ws.l_off1[p] : ws.p_off1[p + 1] - ws.p_off1[p];
@@ -308,15 +311,15 @@ int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfi
                 tp.n2 = n2;
                 tp.xe = reinterpret_cast<const uint8_t*>(exp_tiles);
                 tp.ye = reinterpret_cast<const uint8_t*>(exp_tiles + t1);
-                tp.rowp = reinterpret_cast<uint2*>(rowp_elems);
-                tp.colp = reinterpret_cast<uint2*>(colp_elems);
+                tp.rowp = reinterpret_cast<uint32_t*>(rowp_elems);
+                tp.colp = reinterpret_cast<uint32_t*>(colp_elems);
                 ws.tc_sides[(size_t)4 * p + 2 * type] = TcSide{nullptr, pr.enabled ? n1 : 0, nullptr};
                 ws.tc_sides[(size_t)4 * p + 2 * type + 1] = TcSide{nullptr, pr.enabled ? n2 : 0, nullptr};
                 exp_tiles += (size_t)t1 + t2;
                 rowp_elems += (size_t)t2 * n1;
                 colp_elems += (size_t)(pr.enabled ? n2 : 0);
                 ws.tc_max_tiles = std::max(ws.tc_max_tiles, std::max(t1, t2));
-                for (int yb = 0; yb < (t2 + 1) / 2; ++yb) ws.tc_items.push_back(TcItem{2 * p + type, yb});
+                for (int yb = 0; yb < (t2 + 1) / 2; ++yb) ws.tc_items[type].push_back(TcItem{2 * p + type, yb});
             }
             // offsets into the partial buffers are stored as element indices first, fixed up after allocation
             pr.rowpart = reinterpret_cast<uint2*>(row_elems);
@@ -332,7 +335,8 @@ int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfi
         }
     }
     ws.tile_start[B] = (int32_t)ws.tiles.size();
-    ws.item_start[B] = (int32_t)ws.tc_items.size();
+    ws.item_start[0][B] = (int32_t)ws.tc_items[0].size();
+    ws.item_start[1][B] = (int32_t)ws.tc_items[1].size();
     ws.cap_pt = std::max(ws.cap_pt, 1);
     ws.cap_ls = std::max(ws.cap_ls, 1);
     ws.sort_cap = pow2_ceil_host(std::max(std::max(ws.cap_pt, ws.cap_ls), (ws.max_n2 + 1) / 2));
@@ -359,11 +363,15 @@ int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfi
     CK(ctx, ws.d_tiles.ensure(ws.tiles.size() * sizeof(MatchTile)));
     if (ws.use_tc) {
         CK(ctx, ws.d_exp.ensure(exp_tiles * TC_TILE_BYTES + 1024));
-        CK(ctx, ws.d_rowp.ensure(rowp_elems * sizeof(uint2)));
-        CK(ctx, ws.d_colp.ensure(colp_elems * sizeof(uint2)));
+        CK(ctx, ws.d_rowp.ensure(rowp_elems * sizeof(uint32_t)));
+        CK(ctx, ws.d_colp.ensure(colp_elems * sizeof(uint32_t)));
         CK(ctx, ws.d_tcprob.ensure(ws.tc_problems.size() * sizeof(TcProblem)));
         CK(ctx, ws.d_tcsides.ensure(ws.tc_sides.size() * sizeof(TcSide)));
-        CK(ctx, ws.d_tcitems.ensure(ws.tc_items.size() * sizeof(TcItem)));
+        for (int k = 0; k < 2; ++k) CK(ctx, ws.d_tcitems[k].ensure(ws.tc_items[k].size() * sizeof(TcItem)));
+        if (!ws.d_sched.p) {   // scheduler words of the persistent matcher: one pair per compute stream, self re-arming
+            CK(ctx, ws.d_sched.ensure(64));
+            CK(ctx, cudaMemsetAsync(ws.d_sched.p, 0, 64, ctx->s_h2d));
+        }
     }
     if (with_features) {
         CK(ctx, ws.d_poff1.ensure((B + 1) * 4));
@@ -411,8 +419,8 @@ int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfi
                 uint8_t* ye = ebase + reinterpret_cast<size_t>(tp.ye) * TC_TILE_BYTES;
                 tp.xe = xe;
                 tp.ye = ye;
-                tp.rowp = ws.d_rowp.as<uint2>() + reinterpret_cast<size_t>(tp.rowp);
-                tp.colp = ws.d_colp.as<uint2>() + reinterpret_cast<size_t>(tp.colp);
+                tp.rowp = ws.d_rowp.as<uint32_t>() + reinterpret_cast<size_t>(tp.rowp);
+                tp.colp = ws.d_colp.as<uint32_t>() + reinterpret_cast<size_t>(tp.colp);
                 ws.tc_sides[(size_t)4 * p + 2 * type].src = pr.d1;
                 ws.tc_sides[(size_t)4 * p + 2 * type].dst = xe;
                 ws.tc_sides[(size_t)4 * p + 2 * type + 1].src = pr.d2;
@@ -425,9 +433,10 @@ int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfi
                                 cudaMemcpyHostToDevice, s));
         CK(ctx, cudaMemcpyAsync(ws.d_tcsides.p, ws.tc_sides.data(), ws.tc_sides.size() * sizeof(TcSide),
                                 cudaMemcpyHostToDevice, s));
-        if (!ws.tc_items.empty())
-            CK(ctx, cudaMemcpyAsync(ws.d_tcitems.p, ws.tc_items.data(), ws.tc_items.size() * sizeof(TcItem),
-                                    cudaMemcpyHostToDevice, s));
+        for (int k = 0; k < 2; ++k)
+            if (!ws.tc_items[k].empty())
+                CK(ctx, cudaMemcpyAsync(ws.d_tcitems[k].p, ws.tc_items[k].data(), ws.tc_items[k].size() * sizeof(TcItem),
+                                        cudaMemcpyHostToDevice, s));
     }
     if (!ws.problems.empty())
         CK(ctx, cudaMemcpyAsync(ws.d_problems.p, ws.problems.data(), ws.problems.size() * sizeof(MatchProblem),
@@ -480,13 +489,17 @@ int ws_upload_range(PlContext* ctx, Workspace& ws, const PlFrameBatch* prev, con
     return 0;
 }
 
-int ws_launch_match(PlContext* ctx, Workspace& ws, int p0, int p1, cudaStream_t s) {
+int ws_launch_match(PlContext* ctx, Workspace& ws, int p0, int p1, cudaStream_t s, cudaEvent_t* marks = nullptr) {
     if (ws.use_tc) {
-        const int i0 = ws.item_start[p0], i1 = ws.item_start[p1];
-        if (i1 > i0) {
+        const int a0 = ws.item_start[0][p0], a1 = ws.item_start[0][p1], b0 = ws.item_start[1][p0], b1 = ws.item_start[1][p1];
+        if (a1 > a0 || b1 > b0) {
             CK(ctx, launch_tc_expand(ws.d_tcsides.as<TcSide>() + (size_t)4 * p0, 4 * (p1 - p0), ws.tc_max_tiles, s));
-            CK(ctx, launch_tc_hamming(ws.d_tcprob.as<TcProblem>(), ws.d_tcitems.as<TcItem>() + i0, i1 - i0, ctx->sm_count,
-                                      nullptr, s));
+            if (marks) CK(ctx, cudaEventRecord(marks[0], s));
+            // launches on the two compute streams may overlap: each has its own pair of scheduler words
+            int* sched = ws.d_sched.as<int>() + (s == ctx->s_alt ? 8 : 0);
+            CK(ctx, launch_tc_hamming(ws.d_tcprob.as<TcProblem>(), ws.d_tcitems[0].as<TcItem>() + a0, a1 - a0,
+                                      ws.d_tcitems[1].as<TcItem>() + b0, b1 - b0, sched, ctx->sm_count, nullptr, s));
+            if (marks) CK(ctx, cudaEventRecord(marks[1], s));
             CK(ctx, launch_tc_resolve(ws.d_problems.as<MatchProblem>() + (size_t)2 * p0, ws.d_tcprob.as<TcProblem>() + (size_t)2 * p0,
                                       2 * (p1 - p0), 4, s));
             ctx->launches += 3;
@@ -1795,6 +1808,44 @@ int plstvo_batch_kernel_times(PlContext* ctx, PlDeviceBatch* db, int iters, doub
     if (ms_solve) *ms_solve = tsv / iters;
     if (n_tiles) *n_tiles = (int32_t)ws.tiles.size();
     if (n_pairs) *n_pairs = ws.B;
+    return 0;
+}
+
+int plstvo_batch_stage_times(PlContext* ctx, PlDeviceBatch* db, int iters, double ms[4], int32_t counts[4]) {
+    if (!ctx || !db || iters <= 0 || !ms) return PLSTVO_E_INVALID;
+    LOCK(ctx);
+    CK(ctx, cudaSetDevice(ctx->device));
+    Workspace& ws = db->ws;
+    cudaEvent_t ev[5];
+    for (auto& e : ev) CK(ctx, cudaEventCreate(&e));
+    double acc[4] = {0, 0, 0, 0};
+    for (int i = 0; i < iters; ++i) {
+        CK(ctx, cudaEventRecord(ev[0], ctx->s_main));
+        if (!ws.use_tc) {   // the integer form is one kernel: report it in slot 1
+            CK(ctx, cudaEventRecord(ev[1], ctx->s_main));
+        }
+        int rc = ws_launch_match(ctx, ws, 0, ws.B, ctx->s_main, ws.use_tc ? &ev[1] : nullptr);
+        if (rc) return rc;
+        if (!ws.use_tc) CK(ctx, cudaEventRecord(ev[2], ctx->s_main));
+        CK(ctx, cudaEventRecord(ev[3], ctx->s_main));
+        rc = ws_launch_solve(ctx, ws, 0, ws.B, ws.have_level, ctx->s_main);
+        if (rc) return rc;
+        CK(ctx, cudaEventRecord(ev[4], ctx->s_main));
+        CK(ctx, cudaEventSynchronize(ev[4]));
+        for (int k = 0; k < 4; ++k) {
+            float t = 0.f;
+            CK(ctx, cudaEventElapsedTime(&t, ev[k], ev[k + 1]));
+            acc[k] += t;
+        }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    for (int k = 0; k < 4; ++k) ms[k] = acc[k] / iters;
+    if (counts) {
+        counts[0] = ws.use_tc ? 1 : 0;
+        counts[1] = ws.use_tc ? (int32_t)(ws.tc_items[0].size() + ws.tc_items[1].size()) : (int32_t)ws.tiles.size();
+        counts[2] = (int32_t)ws.problems.size();
+        counts[3] = ws.B;
+    }
     return 0;
 }
 

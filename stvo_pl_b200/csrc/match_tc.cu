@@ -24,6 +24,9 @@
 // Integer-exact end to end: the bit-exact parity tests of the matcher are the acceptance test.
 #include <cuda_fp16.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "match_tc.cuh"
 
@@ -99,6 +102,7 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// packed f16x2 arithmetic on raw 32-bit registers.  max(max(a, b), c) is fused by ptxas into one 3-input VHMNMX.
 __device__ __forceinline__ uint32_t hmax2u(uint32_t a, uint32_t b) {
     uint32_t d;
     asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
@@ -119,37 +123,97 @@ __device__ __forceinline__ uint32_t hgt2mask(uint32_t a, uint32_t b) {   // 0xFF
     asm("set.gt.u32.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
     return d;
 }
-__device__ __forceinline__ float h_lo(uint32_t p) { return __half2float(__ushort_as_half((unsigned short)(p & 0xFFFFu))); }
-__device__ __forceinline__ float h_hi(uint32_t p) { return __half2float(__ushort_as_half((unsigned short)(p >> 16))); }
-__device__ __forceinline__ uint32_t f2h_bits(float f) { return (uint32_t)__half_as_ushort(__float2half_rn(f)); }
+__device__ __forceinline__ uint32_t hfma2u(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t hfma2relu(uint32_t a, uint32_t b, uint32_t c) {   // max(0, a * b + c)
+    uint32_t d;
+    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t hadd2u(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t swap16(uint32_t a) { return __byte_perm(a, a, 0x1032); }
+__device__ __forceinline__ uint32_t sel32(uint32_t mask, uint32_t a, uint32_t b) { return (mask & a) | (~mask & b); }   // one LOP3
+__device__ __forceinline__ uint32_t h2u_lo(uint32_t p) {   // low half (an integer-valued f16 >= 0) -> uint32
+    uint32_t d;
+    asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; cvt.rni.u32.f16 %0, lo; }" : "=r"(d) : "r"(p));
+    return d;
+}
+__device__ __forceinline__ uint32_t h2u_hi(uint32_t p) {
+    uint32_t d;
+    asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; cvt.rni.u32.f16 %0, hi; }" : "=r"(d) : "r"(p));
+    return d;
+}
 
-constexpr uint32_t NEG2 = 0xFC00FC00u;   // (-inf, -inf)
+// "no value" sentinel: -1024 (finite, so that the FMA-pipe form of the update stays exact: |x - y| <= 1280 < 2048)
+constexpr uint32_t NEG2 = 0xE400E400u;
+constexpr uint32_t H2_ONE = 0x3C003C00u, H2_NEG1 = 0xBC00BC00u, H2_NEGHALF = 0xB800B800u, H2_128 = 0x58005800u,
+                   H2_511 = 0x5FFC5FFCu;
+// (best, second) dot values packed (lo, hi) -> distances d = (256 - v) / 2 (exact), "none" (sentinel) -> 511
+__device__ __forceinline__ uint32_t dots_to_dist(uint32_t pv) { return hmin2u(hfma2u(pv, H2_NEGHALF, H2_128), H2_511); }
+
+// running top-2 update with one new packed value; ALU-pipe form (3 min/max) and FMA-pipe form (5 HFMA2 / HADD2):
+//   t = relu(v - k1); k1 += t; m = v - t (= min(k1, v)); k2 += relu(m - k2)        (all values integers, exact in f16)
+__device__ __forceinline__ void top2_alu(uint32_t& k1, uint32_t& k2, uint32_t v) {
+    const uint32_t t = hmin2u(k1, v);
+    k1 = hmax2u(k1, v);
+    k2 = hmax2u(k2, t);
+}
+__device__ __forceinline__ void top2_fma(uint32_t& k1, uint32_t& k2, uint32_t v) {
+    const uint32_t t = hfma2relu(k1, H2_NEG1, v);
+    const uint32_t m = hfma2u(t, H2_NEG1, v);
+    k1 = hadd2u(k1, t);
+    k2 = hadd2u(k2, hfma2relu(k2, H2_NEG1, m));
+}
+// two new values at once: 5 ops (3 HMNMX2 + 2 VHMNMX)
+__device__ __forceinline__ void top2_pair(uint32_t& k1, uint32_t& k2, uint32_t a, uint32_t b) {
+    const uint32_t hi = hmax2u(a, b), lo = hmin2u(a, b);
+    const uint32_t t = hmin2u(k1, hi);
+    k2 = hmax2u(hmax2u(k2, lo), t);
+    k1 = hmax2u(hmax2u(k1, a), b);
+}
 
 // shared-memory operand descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart (SBO), version 1
 __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)0x40004040u << 32);
 }
-// instruction descriptor: D = f16, A = B = e4m3, both K-major, N = 128, M = 128
-constexpr uint32_t TC_IDESC = (uint32_t)((TC_ROWS >> 3) << 17) | (uint32_t)((TC_ROWS >> 4) << 24);
+// instruction descriptor: D = f16, A = B = e4m3, both K-major, M = 128, N = 256
+constexpr uint32_t TC_IDESC = (uint32_t)((256 >> 3) << 17) | (uint32_t)((TC_ROWS >> 4) << 24);
 
 // ---------------------------------------------------------------------------------------------------------------
 // the matcher
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int TC_OFF_X = 0;
-constexpr int TC_OFF_Y = TC_XSTAGES * TC_TILE_BYTES;
+constexpr int TC_OFF_Y = TC_XSTAGES * TC_TILE_BYTES;                      // [slab 0..1][256 rows]: 64 KB
 constexpr int TC_OFF_SCR = TC_OFF_Y + 2 * TC_TILE_BYTES;                  // per epilogue warp: 16 x 33 words
 constexpr int TC_SCR_WARP = 16 * 33 * 4;
 constexpr int TC_OFF_MRG = TC_OFF_SCR + 8 * TC_SCR_WARP;                  // [2 groups][4 quarters][128 columns] uint2
 constexpr int TC_OFF_BAR = TC_OFF_MRG + 2 * 4 * 128 * 8;
-constexpr int TC_NBARS = 2 * TC_XSTAGES + 2 + 2 * TC_ASTAGES;
-constexpr int TC_OFF_SLOT = TC_OFF_BAR + TC_NBARS * 8;
+constexpr int TC_IRING = 4;                                               // work items announced ahead
+constexpr int TC_NBARS = 2 * TC_XSTAGES + 2 + 2 * TC_ASTAGES + 2 * TC_IRING;
+constexpr int TC_OFF_RING = TC_OFF_BAR + TC_NBARS * 8;
+constexpr int TC_OFF_SLOT = TC_OFF_RING + TC_IRING * 4;
 constexpr int TC_SMEM_USED = TC_OFF_SLOT + 16;
 
 size_t tc_smem_bytes() { return (size_t)TC_SMEM_USED + 1024; }
 
+template <int NF>   // NF: column-state registers per 16-register chunk updated on the FMA pipe (0 .. 16)
+#ifndef TC_MAXNREG
+#define TC_MAXNREG 0
+#endif
+#if TC_MAXNREG > 0
+__global__ void __maxnreg__(TC_MAXNREG)
+#else
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_hamming_kernel(const TcProblem* __restrict__ problems, const TcItem* __restrict__ items, int n_items,
-                  __half* __restrict__ debug_tile) {
+#endif
+tc_hamming_kernel(const TcProblem* __restrict__ problems, const TcItem* __restrict__ items_a, int n_a,
+                  const TcItem* __restrict__ items_b, int n_b, int* __restrict__ sched, __half* __restrict__ debug_tile) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;
@@ -161,9 +225,13 @@ tc_hamming_kernel(const TcProblem* __restrict__ problems, const TcItem* __restri
     uint64_t* y_empty = y_full + 1;
     uint64_t* t_full = y_empty + 1;
     uint64_t* t_empty = t_full + TC_ASTAGES;
+    uint64_t* i_full = t_empty + TC_ASTAGES;
+    uint64_t* i_empty = i_full + TC_IRING;
+    volatile int* iring = reinterpret_cast<volatile int*>(sm + TC_OFF_RING);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + TC_OFF_SLOT);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_items = n_a + n_b;
 
     if (tid == 0) {
         for (int i = 0; i < TC_XSTAGES; ++i) {
@@ -175,6 +243,10 @@ tc_hamming_kernel(const TcProblem* __restrict__ problems, const TcItem* __restri
         for (int i = 0; i < TC_ASTAGES; ++i) {
             mbar_init(&t_full[i], 1);
             mbar_init(&t_empty[i], 8);
+        }
+        for (int i = 0; i < TC_IRING; ++i) {
+            mbar_init(&i_full[i], 1);
+            mbar_init(&i_empty[i], 9);   // the MMA thread + 8 epilogue warps
         }
         fence_mbar_init();
     }
@@ -189,20 +261,32 @@ tc_hamming_kernel(const TcProblem* __restrict__ problems, const TcItem* __restri
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // work items are handed out by an atomic counter (long ones first: list a, then list b) and announced to the other
+    // roles through a small ring in shared memory; -1 ends the kernel
+    auto item_at = [&](int it) -> TcItem { return it < n_a ? items_a[it] : items_b[it - n_a]; };
+
     if (warp == 0) {
-        // ===== producer: bulk copies of operand tiles =====
+        // ===== producer: work distribution + bulk copies of operand tiles =====
         if (lane == 0) {
-            uint32_t xs = 0, xph = 0, yit = 0;
-            for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++yit) {
-                const TcItem item = items[it];
+            uint32_t xs = 0, xph = 0;
+            for (uint32_t k = 0;; ++k) {
+                const uint32_t slot = k % TC_IRING;
+                mbar_wait(&i_empty[slot], ((k / TC_IRING) & 1) ^ 1);
+                int it = atomicAdd(sched, 1);
+                if (it >= n_items) it = -1;
+                iring[slot] = it;
+                mbar_arrive(&i_full[slot]);
+                if (it < 0) break;
+                const TcItem item = item_at(it);
                 const TcProblem pr = problems[item.problem];
                 const int nyt = (pr.n2 + TC_ROWS - 1) / TC_ROWS, nxt = (pr.n1 + TC_ROWS - 1) / TC_ROWS;
                 const int ytiles = min(2, nyt - 2 * item.yblk);
-                mbar_wait(y_empty, (yit & 1) ^ 1);
+                mbar_wait(y_empty, (k & 1) ^ 1);
                 mbar_arrive_expect_tx(y_full, (uint32_t)ytiles * TC_TILE_BYTES);
                 for (int h = 0; h < ytiles; ++h)
-                    bulk_g2s(sm + TC_OFF_Y + h * TC_TILE_BYTES, pr.ye + (size_t)(2 * item.yblk + h) * TC_TILE_BYTES,
-                             TC_TILE_BYTES, y_full);
+                    for (int sl = 0; sl < 2; ++sl)
+                        bulk_g2s(sm + TC_OFF_Y + sl * 32768 + h * 16384,
+                                 pr.ye + (size_t)(2 * item.yblk + h) * TC_TILE_BYTES + sl * 16384, 16384, y_full);
                 for (int t = 0; t < nxt; ++t) {
                     mbar_wait(&x_empty[xs], xph ^ 1);
                     mbar_arrive_expect_tx(&x_full[xs], TC_TILE_BYTES);
@@ -215,27 +299,27 @@ tc_hamming_kernel(const TcProblem* __restrict__ problems, const TcItem* __restri
     } else if (warp == 1) {
         // ===== MMA issuer: one thread =====
         if (lane == 0) {
-            uint32_t xs = 0, xph = 0, as = 0, aph = 0, yit = 0;
-            for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++yit) {
-                const TcItem item = items[it];
+            uint32_t xs = 0, xph = 0, as = 0, aph = 0;
+            for (uint32_t k = 0;; ++k) {
+                const uint32_t slot = k % TC_IRING;
+                mbar_wait(&i_full[slot], (k / TC_IRING) & 1);
+                const int it = iring[slot];
+                mbar_arrive(&i_empty[slot]);
+                if (it < 0) break;
+                const TcItem item = item_at(it);
                 const TcProblem pr = problems[item.problem];
                 const int nxt = (pr.n1 + TC_ROWS - 1) / TC_ROWS;
-                mbar_wait(y_full, yit & 1);
+                mbar_wait(y_full, k & 1);
                 for (int t = 0; t < nxt; ++t) {
                     mbar_wait(&t_empty[as], aph ^ 1);
                     mbar_wait(&x_full[xs], xph);
                     tc_fence_after();
-                    const uint32_t xa = sbase + TC_OFF_X + xs * TC_TILE_BYTES;
+                    const uint32_t xa = sbase + TC_OFF_X + xs * TC_TILE_BYTES, ya = sbase + TC_OFF_Y;
+                    const uint32_t d = tmem_base + as * 256;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const uint32_t ya = sbase + TC_OFF_Y + h * TC_TILE_BYTES;
-                        const uint32_t d = tmem_base + as * 256 + h * 128;
-#pragma unroll
-                        for (int kk = 0; kk < 8; ++kk) {
-                            const uint32_t ko = (kk >> 2) * 16384 + (kk & 3) * 32;
-                            tc_mma_f8(d, tc_desc(xa + ko), tc_desc(ya + ko), TC_IDESC, kk > 0);
-                        }
-                    }
+                    for (int kk = 0; kk < 8; ++kk)
+                        tc_mma_f8(d, tc_desc(xa + (kk >> 2) * 16384 + (kk & 3) * 32),
+                                  tc_desc(ya + (kk >> 2) * 32768 + (kk & 3) * 32), TC_IDESC, kk > 0);
                     tc_commit(&x_empty[xs]);
                     tc_commit(&t_full[as]);
                     if (++xs == TC_XSTAGES) { xs = 0; xph ^= 1; }
@@ -250,8 +334,14 @@ tc_hamming_kernel(const TcProblem* __restrict__ problems, const TcItem* __restri
         uint32_t* scr = reinterpret_cast<uint32_t*>(sm + TC_OFF_SCR + ew * TC_SCR_WARP);
         uint2* mrg = reinterpret_cast<uint2*>(sm + TC_OFF_MRG) + gq * 4 * 128;
         uint32_t as = 0, aph = 0;
-        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-            const TcItem item = items[it];
+        for (uint32_t k = 0;; ++k) {
+            const uint32_t slot = k % TC_IRING;
+            mbar_wait(&i_full[slot], (k / TC_IRING) & 1);
+            const int it = iring[slot];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&i_empty[slot]);
+            if (it < 0) break;
+            const TcItem item = item_at(it);
             const TcProblem pr = problems[item.problem];
             const int nxt = (pr.n1 + TC_ROWS - 1) / TC_ROWS;
             const int half = item.yblk * 2 + gq;              // 128-column block index of this group
@@ -266,41 +356,61 @@ tc_hamming_kernel(const TcProblem* __restrict__ problems, const TcItem* __restri
                 tc_fence_after();
                 const int x = t * TC_ROWS + q * 32 + lane;
                 const bool xvalid = x < pr.n1;
-                const bool clean = (nvalid == TC_ROWS) && ((t + 1) * TC_ROWS <= pr.n1);   // warp-uniform
-                uint32_t r1 = NEG2, r2 = NEG2, rc = 0;
+                // two independent row chains: A = registers 0..7 (16-column group 2c), B = registers 8..15 (group 2c + 1)
+                uint32_t ra1 = NEG2, ra2 = NEG2, rb1 = NEG2, rb2 = NEG2, ta = 0, tb = 0;
                 const uint32_t tad = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + gq * 128;
+                auto fold = [&](const uint32_t (&v)[16], const int c) {
+                    const uint32_t olda = ra1, oldb = rb1;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t v[16];
-                    tc_ld32(tad + c * 32, v);
+                    for (int i = 0; i < 4; ++i) {
+                        top2_pair(ra1, ra2, v[2 * i], v[2 * i + 1]);
+                        top2_pair(rb1, rb2, v[8 + 2 * i], v[8 + 2 * i + 1]);
+                    }
+                    ta = sel32(hne2mask(ra1, olda), (uint32_t)((2 * c) * 0x00010001u), ta);
+                    tb = sel32(hne2mask(rb1, oldb), (uint32_t)((2 * c + 1) * 0x00010001u), tb);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        if (i < NF) top2_fma(c1[c * 16 + i], c2[c * 16 + i], v[i]);
+                        else top2_alu(c1[c * 16 + i], c2[c * 16 + i], v[i]);
+                    }
+                };
+                if (nvalid == TC_ROWS && (t + 1) * TC_ROWS <= pr.n1 && debug_tile == nullptr) {
+                    // full tile of a full block (the common case): no per-chunk branches, the next chunk's TMEM load is in
+                    // flight while this one is folded
+                    uint32_t va[16], vb[16];
+                    tc_ld32(tad, va);
                     tc_wait_ld();
-                    if (debug_tile && it == 0 && t == 0) {
+                    tc_ld32(tad + 32, vb);
+                    fold(va, 0);
+                    tc_wait_ld();
+                    tc_ld32(tad + 64, va);
+                    fold(vb, 1);
+                    tc_wait_ld();
+                    tc_ld32(tad + 96, vb);
+                    fold(va, 2);
+                    tc_wait_ld();
+                    fold(vb, 3);
+                } else {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            *reinterpret_cast<uint32_t*>(debug_tile + (size_t)(q * 32 + lane) * 256 + gq * 128 + c * 32 + 2 * i) = v[i];
-                    }
-                    if (!clean) {
+                    for (int c = 0; c < 4; ++c) {
+                        if (c * 32 >= nvalid) continue;           // warp-uniform: no valid column in this chunk
+                        uint32_t v[16];
+                        tc_ld32(tad + c * 32, v);
+                        tc_wait_ld();
+                        if (debug_tile && it == 0 && t == 0) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int col = c * 32 + 2 * i;
-                            if (!xvalid || col >= nvalid) v[i] = NEG2;
-                            else if (col + 1 >= nvalid) v[i] = (v[i] & 0xFFFFu) | 0xFC000000u;
+                            for (int i = 0; i < 16; ++i)
+                                *reinterpret_cast<uint32_t*>(debug_tile + (size_t)(q * 32 + lane) * 256 + gq * 128 + c * 32 + 2 * i) = v[i];
                         }
-                    }
-                    const uint32_t old = r1;
+                        if (c * 32 + 32 > nvalid) {               // the one boundary chunk of a partial block
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const uint32_t tmin = hmin2u(r1, v[i]);
-                        r1 = hmax2u(r1, v[i]);
-                        r2 = hmax2u(r2, tmin);
-                    }
-                    const uint32_t chg = hne2mask(r1, old);
-                    rc = (chg & (uint32_t)(c * 0x00010001u)) | (~chg & rc);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const uint32_t tmin = hmin2u(c1[c * 16 + i], v[i]);
-                        c1[c * 16 + i] = hmax2u(c1[c * 16 + i], v[i]);
-                        c2[c * 16 + i] = hmax2u(c2[c * 16 + i], tmin);
+                            for (int i = 0; i < 16; ++i) {
+                                const int col = c * 32 + 2 * i;
+                                if (col >= nvalid) v[i] = NEG2;
+                                else if (col + 1 >= nvalid) v[i] = (v[i] & 0xFFFFu) | (NEG2 & 0xFFFF0000u);
+                            }
+                        }
+                        if (xvalid) fold(v, c);                   // rows past the end (zero operand rows) contribute nothing
                     }
                 }
                 tc_fence_before();
@@ -308,12 +418,14 @@ tc_hamming_kernel(const TcProblem* __restrict__ problems, const TcItem* __restri
                 if (lane == 0) mbar_arrive(&t_empty[as]);
                 if (++as == TC_ASTAGES) { as = 0; aph ^= 1; }
                 if (xvalid && nvalid > 0) {
-                    // combine the even-column and odd-column streams of this 128-column block
-                    const float a1 = h_lo(r1), b1 = h_hi(r1), a2 = h_lo(r2), b2 = h_hi(r2);
-                    const float v1 = fmaxf(a1, b1), v2 = fmaxf(fminf(a1, b1), fmaxf(a2, b2));
-                    const uint32_t par = b1 > a1 ? 1u : 0u;
-                    const uint32_t chunk = par ? (rc >> 16) : (rc & 0xFFFFu);
-                    pr.rowp[(size_t)half * pr.n1 + x] = make_uint2(f2h_bits(v1) | (f2h_bits(v2) << 16), chunk | (par << 2));
+                    // chains, then the even- and odd-column streams; everything packed, the result sits in the low halves
+                    const uint32_t m1 = hmax2u(ra1, rb1), m2 = hmax2u(hmax2u(hmin2u(ra1, rb1), ra2), rb2);
+                    const uint32_t tg = sel32(hgt2mask(rb1, ra1), tb, ta);
+                    const uint32_t s1 = swap16(m1), s2 = swap16(m2), st = swap16(tg);
+                    const uint32_t f1 = hmax2u(m1, s1), f2 = hmax2u(hmax2u(hmin2u(m1, s1), m2), s2);
+                    const uint32_t tag = sel32(hgt2mask(s1, m1), (st << 1) | 1u, tg << 1) & 0xFu;   // group << 1 | parity
+                    const uint32_t dd = dots_to_dist(__byte_perm(f1, f2, 0x5410));
+                    pr.rowp[(size_t)half * pr.n1 + x] = h2u_lo(dd) | (h2u_hi(dd) << 9) | (tag << 18);
                 }
             }
 
@@ -328,13 +440,12 @@ tc_hamming_kernel(const TcProblem* __restrict__ problems, const TcItem* __restri
                 __syncwarp();
                 uint32_t m1 = NEG2, m2 = NEG2, id = 0;
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const uint32_t v = scr[j * 33 + hl * 16 + k];
+                for (int kk = 0; kk < 16; ++kk) {
+                    const uint32_t v = scr[j * 33 + hl * 16 + kk];
                     const uint32_t tmin = hmin2u(m1, v);
                     const uint32_t nm = hmax2u(m1, v);
                     m2 = hmax2u(m2, tmin);
-                    const uint32_t chg = hne2mask(nm, m1);
-                    id = (chg & (uint32_t)((hl * 16 + k) * 0x00010001u)) | (~chg & id);
+                    id = sel32(hne2mask(nm, m1), (uint32_t)((hl * 16 + kk) * 0x00010001u), id);
                     m1 = nm;
                 }
                 __syncwarp();
@@ -342,15 +453,14 @@ tc_hamming_kernel(const TcProblem* __restrict__ problems, const TcItem* __restri
                 for (int i = 0; i < 16; ++i) scr[i * 33 + lane] = c2[p * 16 + i];
                 __syncwarp();
 #pragma unroll
-                for (int k = 0; k < 16; ++k) m2 = hmax2u(m2, scr[j * 33 + hl * 16 + k]);
+                for (int kk = 0; kk < 16; ++kk) m2 = hmax2u(m2, scr[j * 33 + hl * 16 + kk]);
                 __syncwarp();
                 // halves: lanes L and L ^ 16 hold the same register over the other 16 source lanes
                 const uint32_t o1 = __shfl_xor_sync(0xFFFFFFFFu, m1, 16), o2 = __shfl_xor_sync(0xFFFFFFFFu, m2, 16),
                                oid = __shfl_xor_sync(0xFFFFFFFFu, id, 16);
-                const uint32_t gt = hgt2mask(o1, m1);
-                const uint32_t n2v = hmax2u(hmin2u(m1, o1), hmax2u(m2, o2));
+                const uint32_t n2v = hmax2u(hmax2u(hmin2u(m1, o1), m2), o2);
                 const uint32_t n1v = hmax2u(m1, o1);
-                const uint32_t nid = (gt & oid) | (~gt & id);
+                const uint32_t nid = sel32(hgt2mask(o1, m1), oid, id);
                 if (hl == 0) {
                     const int col = (p * 16 + j) * 2;
                     mrg[q * 128 + col] = make_uint2((n1v & 0xFFFFu) | (n2v << 16), nid & 0xFFFFu);
@@ -360,16 +470,19 @@ tc_hamming_kernel(const TcProblem* __restrict__ problems, const TcItem* __restri
             asm volatile("bar.sync %0, 128;" ::"r"(1 + gq) : "memory");
             {
                 const int col = (ew & 3) * 32 + lane;
-                float b1 = -1e30f, b2 = -1e30f;
-                uint32_t bt = 0;
+                uint32_t b1 = NEG2, b2 = NEG2, bt = 0;   // only the low halves are meaningful
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq) {
                     const uint2 e = mrg[qq * 128 + col];
-                    const float a1 = h_lo(e.x), a2 = h_hi(e.x);
-                    b2 = fmaxf(fminf(b1, a1), fmaxf(b2, a2));
-                    if (a1 > b1) { b1 = a1; bt = (uint32_t)qq * 32u + e.y; }
+                    const uint32_t a1 = e.x & 0xFFFFu, a2 = e.x >> 16;
+                    b2 = hmax2u(hmax2u(hmin2u(b1, a1), b2), a2);
+                    bt = sel32(hgt2mask(a1, b1), (uint32_t)qq * 32u + e.y, bt);
+                    b1 = hmax2u(b1, a1);
                 }
-                if (col < nvalid) pr.colp[ycol0 + col] = make_uint2(f2h_bits(b1) | (f2h_bits(b2) << 16), bt);
+                if (col < nvalid) {
+                    const uint32_t dd = dots_to_dist(__byte_perm(b1, b2, 0x5410));
+                    pr.colp[ycol0 + col] = h2u_lo(dd) | (h2u_hi(dd) << 9) | ((bt & 0x7Fu) << 18);
+                }
             }
             asm volatile("bar.sync %0, 128;" ::"r"(1 + gq) : "memory");
         }
@@ -381,17 +494,53 @@ tc_hamming_kernel(const TcProblem* __restrict__ problems, const TcItem* __restri
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_ASTAGES * 256)
                      : "memory");
     }
+    // the last CTA out re-arms the scheduler words for the next launch on this stream
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) {
+            sched[0] = 0;
+            sched[1] = 0;
+            __threadfence();
+        }
+    }
 }
 
-cudaError_t launch_tc_hamming(const TcProblem* problems, const TcItem* items, int n_items, int grid, __half* debug_tile,
-                              cudaStream_t stream) {
+static int tc_nf() {   // tuning knob: how many of the 16 column registers per chunk use the FMA-pipe update
+    static const int nf = [] {
+        const char* v = getenv("PLSTVO_TC_NF");
+        return v ? atoi(v) : 0;
+    }();
+    return nf;
+}
+
+cudaError_t launch_tc_hamming(const TcProblem* problems, const TcItem* items_a, int n_a, const TcItem* items_b, int n_b,
+                              int* sched, int grid, __half* debug_tile, cudaStream_t stream) {
+    const int n_items = n_a + n_b;
     if (n_items <= 0) return cudaSuccess;
-    static size_t configured[64] = {};
+    typedef void (*Fn)(const TcProblem*, const TcItem*, int, const TcItem*, int, int*, __half*);
+    Fn fn;
+    switch (tc_nf()) {
+        case 4: fn = tc_hamming_kernel<4>; break;
+        case 6: fn = tc_hamming_kernel<6>; break;
+        case 8: fn = tc_hamming_kernel<8>; break;
+        case 10: fn = tc_hamming_kernel<10>; break;
+        case 12: fn = tc_hamming_kernel<12>; break;
+        default: fn = tc_hamming_kernel<0>; break;
+    }
+    static size_t configured[8][64] = {};
     const size_t smem = tc_smem_bytes();
-    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(tc_hamming_kernel), smem, configured);
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(fn), smem, configured[(tc_nf() / 2) & 7]);
     if (e != cudaSuccess) return e;
     if (grid > n_items) grid = n_items;
-    tc_hamming_kernel<<<grid, TC_THREADS, smem, stream>>>(problems, items, n_items, debug_tile);
+    if (getenv("PLSTVO_TC_DIAG")) {
+        cudaFuncAttributes fa;
+        int occ = -1;
+        cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(fn));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, TC_THREADS, smem);
+        fprintf(stderr, "[tc diag] regs %d, maxThreadsPerBlock %d, static smem %zu, local %zu, dynamic smem %zu, occupancy %d\n",
+                fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, fa.localSizeBytes, smem, occ);
+    }
+    fn<<<grid, TC_THREADS, smem, stream>>>(problems, items_a, n_a, items_b, n_b, sched, debug_tile);
     return cudaGetLastError();
 }
 
@@ -410,30 +559,30 @@ __global__ void __launch_bounds__(256) tc_resolve_kernel(const MatchProblem* __r
     const TcProblem tp = tps[blockIdx.x];
     const int nyh = (mp.n2 + TC_ROWS - 1) / TC_ROWS, nxt = (mp.n1 + TC_ROWS - 1) / TC_ROWS;
     const int slice = blockIdx.y, nslices = gridDim.y;
-    // queries: top-2 trains
+    // partial word: best distance (9 bits) | second distance << 9 (511 = none) | candidate tag << 18
+    // queries: top-2 trains over the 128-train blocks (lowest block wins a tie: its indices are lower)
     for (int x = slice * blockDim.x + threadIdx.x; x < mp.n1; x += nslices * blockDim.x) {
-        float b1 = -1e30f, b2 = -1e30f;
+        uint32_t b1 = 511, b2 = 511, btag = 0;
         int bh = 0;
-        uint32_t bid = 0;
         for (int h = 0; h < nyh; ++h) {
-            const uint2 e = tp.rowp[(size_t)h * mp.n1 + x];
-            const float a1 = h_lo(e.x), a2 = h_hi(e.x);
-            b2 = fmaxf(fminf(b1, a1), fmaxf(b2, a2));
-            if (a1 > b1) { b1 = a1; bh = h; bid = e.y; }
+            const uint32_t e = __ldg(&tp.rowp[(size_t)h * mp.n1 + x]);
+            const uint32_t a1 = e & 511u, a2 = (e >> 9) & 511u;
+            b2 = min(max(b1, a1), min(b2, a2));
+            if (a1 < b1) { b1 = a1; bh = h; btag = e >> 18; }
         }
-        const int d1 = (256 - (int)b1) >> 1;
+        const int d1 = (int)b1;
         uint32_t k2 = KEY_NONE;
         int idx = 0;
         if (mp.n2 >= 2) {
-            const int d2 = (256 - (int)b2) >> 1;
+            const int d2 = (int)b2;
             k2 = ((uint32_t)d2 << 16) | 0xFFFEu;
             if ((float)d1 < __fmul_rn((float)d2, mp.nnr)) {
                 const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(mp.d1 + (size_t)x * 32)),
                             a1 = __ldg(reinterpret_cast<const uint4*>(mp.d1 + (size_t)x * 32) + 1);
                 idx = -1;
-                if (d1 != d2) {
-                    const int base = bh * TC_ROWS + (int)(bid & 3u) * 32 + (int)((bid >> 2) & 1u);
-                    for (int i = 0; i < 16 && idx < 0; ++i) {
+                if (d1 != d2) {   // unique best: it is one of the 8 tagged trains (16-column group, one parity)
+                    const int base = bh * TC_ROWS + (int)((btag >> 1) & 7u) * 16 + (int)(btag & 1u);
+                    for (int i = 0; i < 8 && idx < 0; ++i) {
                         const int j = base + 2 * i;
                         if (j < mp.n2 && hamming256(a0, a1, mp.d2 + (size_t)j * 32) == d1) idx = j;
                     }
@@ -449,20 +598,21 @@ __global__ void __launch_bounds__(256) tc_resolve_kernel(const MatchProblem* __r
     }
     // trains: top-2 queries
     for (int y = slice * blockDim.x + threadIdx.x; y < mp.n2; y += nslices * blockDim.x) {
-        const uint2 e = tp.colp[y];
-        const int d1 = (256 - (int)h_lo(e.x)) >> 1;
+        const uint32_t e = __ldg(&tp.colp[y]);
+        const int d1 = (int)(e & 511u);
         uint32_t k2 = KEY_NONE;
         int idx = 0;
         if (mp.n1 >= 2) {
-            const int d2 = (256 - (int)h_hi(e.x)) >> 1;
+            const int d2 = (int)((e >> 9) & 511u);
             k2 = ((uint32_t)d2 << 16) | 0xFFFEu;
             if ((float)d1 < __fmul_rn((float)d2, mp.nnr)) {
                 const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(mp.d2 + (size_t)y * 32)),
                             a1 = __ldg(reinterpret_cast<const uint4*>(mp.d2 + (size_t)y * 32) + 1);
                 idx = -1;
-                if (d1 != d2) {
+                if (d1 != d2) {   // unique best: one of the queries the tagged epilogue thread saw (row = tag mod 128)
+                    const int t = (int)((e >> 18) & 127u);
                     for (int i = 0; i < nxt && idx < 0; ++i) {
-                        const int j = (int)e.y + i * TC_ROWS;
+                        const int j = t + i * TC_ROWS;
                         if (j < mp.n1 && hamming256(a0, a1, mp.d1 + (size_t)j * 32) == d1) idx = j;
                     }
                 }

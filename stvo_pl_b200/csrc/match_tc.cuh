@@ -24,8 +24,8 @@ struct TcProblem {
     const uint8_t* xe;    // expanded queries  (desc1): ceil(n1 / 128) tiles
     const uint8_t* ye;    // expanded trains   (desc2): ceil(n2 / 128) tiles
     int32_t n1, n2;
-    uint2* rowp;          // [ceil(n2 / 128)][n1]: {best | second << 16 (f16 bits of 256 - 2 d), candidate tag}
-    uint2* colp;          // [n2]:                 {best | second << 16, lane tag}
+    uint32_t* rowp;       // [ceil(n2 / 128)][n1]: best distance | second << 9 (511 = none) | tag << 18 (16-column group, parity)
+    uint32_t* colp;       // [n2]:                 best | second << 9 | tag << 18 (query row mod 128)
 };
 
 // one work item of the persistent kernel: all query tiles of a problem against 256 trains
@@ -36,8 +36,9 @@ struct TcItem {
 
 size_t tc_smem_bytes();
 cudaError_t launch_tc_expand(const TcSide* sides, int n_sides, int max_tiles, cudaStream_t stream);
-cudaError_t launch_tc_hamming(const TcProblem* problems, const TcItem* items, int n_items, int grid, __half* debug_tile,
-                              cudaStream_t stream);
+// items_a then items_b form the work list (long items first); sched: two zeroed ints per concurrently running launch
+cudaError_t launch_tc_hamming(const TcProblem* problems, const TcItem* items_a, int n_a, const TcItem* items_b, int n_b,
+                              int* sched, int grid, __half* debug_tile, cudaStream_t stream);
 // writes MatchProblem::rowpart[0][n1] / colpart[0][n2] (ntb = nqb = 1) in K1's packed-key format
 cudaError_t launch_tc_resolve(const MatchProblem* mps, const TcProblem* tps, int n_problems, int slices, cudaStream_t stream);
 

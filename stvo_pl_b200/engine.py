@@ -80,6 +80,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "plstvo_host_free": (None, [vp]),
         "plstvo_launch_count": (C.c_int64, [vp]),
         "plstvo_batch_kernel_times": (C.c_int, [vp, vp, C.c_int, dp, dp, i32p, i32p]),
+        "plstvo_batch_stage_times": (C.c_int, [vp, vp, C.c_int, dp, i32p]),
         "plstvo_gn_eval_stream": (C.c_int, [vp, cam, cfg, mb, dp, C.c_int, dp, dp, dp, C.POINTER(C.c_float)]),
         "plstvo_popc_rate": (C.c_int, [vp, dp]),
         "plstvo_debug_algebra": (C.c_int, [vp, C.c_int, dp, dp, dp, dp, dp, dp]),
@@ -99,7 +100,7 @@ EXPORTED_SYMBOLS = [
     "plstvo_f2f_tracking",
     "plstvo_optimize_pose", "plstvo_track_batch", "plstvo_track_batch_async", "plstvo_wait", "plstvo_batch_upload", "plstvo_batch_run",
     "plstvo_batch_run_timed", "plstvo_batch_download", "plstvo_batch_free", "plstvo_synchronize",
-    "plstvo_host_alloc", "plstvo_host_free", "plstvo_launch_count", "plstvo_batch_kernel_times",
+    "plstvo_host_alloc", "plstvo_host_free", "plstvo_launch_count", "plstvo_batch_kernel_times", "plstvo_batch_stage_times",
     "plstvo_gn_eval_stream", "plstvo_popc_rate", "plstvo_debug_algebra"]
 
 
@@ -191,6 +192,13 @@ class DeviceBatch:
             self.eng.ctx, self.handle, iters, a.ctypes.data_as(T.c_double_p), b.ctypes.data_as(T.c_double_p),
             nt.ctypes.data_as(T.c_int32_p), npairs.ctypes.data_as(T.c_int32_p)))
         return dict(ms_match=float(a[0]), ms_solve=float(b[0]), n_tiles=int(nt[0]), n_pairs=int(npairs[0]))
+
+    def stage_times(self, iters: int = 3):
+        ms, cnt = np.zeros(4), np.zeros(4, np.int32)
+        self.eng._ck(self.eng.lib.plstvo_batch_stage_times(self.eng.ctx, self.handle, iters, ms.ctypes.data_as(T.c_double_p),
+                                                           cnt.ctypes.data_as(T.c_int32_p)))
+        return dict(ms_expand=float(ms[0]), ms_distance=float(ms[1]), ms_resolve=float(ms[2]), ms_solve=float(ms[3]),
+                    tensor_core_form=bool(cnt[0]), n_items=int(cnt[1]), n_problems=int(cnt[2]), n_pairs=int(cnt[3]))
 
     def download(self):
         res = np.zeros(self.B, dtype=T.POSE_RESULT_DTYPE)

@@ -194,12 +194,18 @@ def test_gpu_match_stereo_errors(engine):
         engine.match_stereo_points(cam, bad, sc, off, kp_l, octave, d1, off, kp_r, d2)
     with pytest.raises(RuntimeError):                              # offsets must start at 0
         engine.match_stereo_points(cam, mc, sc, np.array([1, 50], np.int32), kp_l, octave, d1, off, kp_r, d2)
-    # more than 128 right key points in one query window: reported, as by plstvo_match_grid_points
+    # more than 128 right key points in one query window: no limit, as in the reference (the frame takes matchGrid's
+    # sequential path); exact against the oracle
     kp_r2 = np.tile(np.float32([[100.0, 100.0]]), (200, 1))
     kp_l2 = np.tile(np.float32([[110.0, 100.0]]), (10, 1))
-    with pytest.raises(RuntimeError):
-        engine.match_stereo_points(cam, mc, sc, np.array([0, 10], np.int32), kp_l2, np.zeros(10, np.int32), d1[:10],
-                                   np.array([0, 200], np.int32), kp_r2, np.repeat(d2[:1], 200, 0))
+    rng = np.random.default_rng(5)
+    d2_200 = rng.integers(0, 256, (200, 32), dtype=np.uint8)
+    tot, out = engine.match_stereo_points(cam, mc, sc, np.array([0, 10], np.int32), kp_l2, np.zeros(10, np.int32), d1[:10],
+                                          np.array([0, 200], np.int32), kp_r2, d2_200)
+    from oracle.oracle import Oracle
+    m12_o, k_o, _ = Oracle().match_stereo_points(cam, mc, sc, kp_l2, np.zeros(10, np.int32), d1[:10], kp_r2, d2_200)
+    np.testing.assert_array_equal(out["m12"], m12_o)
+    assert tot == k_o
 
 
 # ---------------------------------------------------------------------------- raw stereo features -> pose (records stay in HBM)

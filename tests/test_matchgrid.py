@@ -92,9 +92,9 @@ def _clustered_points(n_l, n_r, seed, tie=False):
     t_cell = t_cell.copy()
     q_cell = q_cell.copy()
     hot_t = rng.random(n_r) < 0.6
-    t_cell[hot_t] = np.stack([rng.integers(20, 24, hot_t.sum()), rng.integers(10, 12, hot_t.sum())], 1)
+    t_cell[hot_t] = np.stack([rng.integers(20, 22, hot_t.sum()), rng.integers(10, 11, hot_t.sum())], 1)
     hot_q = rng.random(n_l) < 0.5
-    q_cell[hot_q] = np.stack([rng.integers(22, 30, hot_q.sum()), rng.integers(10, 12, hot_q.sum())], 1)
+    q_cell[hot_q] = np.stack([rng.integers(21, 30, hot_q.sum()), rng.integers(10, 11, hot_q.sum())], 1)
     return q_cell, d1, t_cell, d2
 
 

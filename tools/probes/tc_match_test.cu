@@ -90,18 +90,19 @@ int main(int argc, char** argv) {
         }
     }
     uint8_t *d1, *d2, *ex;
-    uint2 *rowp, *colp, *rowpart, *colpart;
+    uint32_t *rowp, *colp;
+    uint2 *rowpart, *colpart;
     CK(cudaMalloc(&d1, h1.size() + 32));
     CK(cudaMalloc(&d2, h2.size() + 32));
     CK(cudaMalloc(&ex, tiles * TC_TILE_BYTES));
-    CK(cudaMalloc(&rowp, nrowp * 8 + 8));
-    CK(cudaMalloc(&colp, ncolp * 8 + 8));
+    CK(cudaMalloc(&rowp, nrowp * 4 + 8));
+    CK(cudaMalloc(&colp, ncolp * 4 + 8));
     CK(cudaMalloc(&rowpart, nrp * 8 + 8));
     CK(cudaMalloc(&colpart, ncp * 8 + 8));
     CK(cudaMemcpy(d1, h1.data(), h1.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d2, h2.data(), h2.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemset(rowp, 0xAB, nrowp * 8));
-    CK(cudaMemset(colp, 0xAB, ncolp * 8));
+    CK(cudaMemset(rowp, 0xAB, nrowp * 4));
+    CK(cudaMemset(colp, 0xAB, ncolp * 4));
     CK(cudaMemset(rowpart, 0xCD, nrp * 8));
     CK(cudaMemset(colpart, 0xCD, ncp * 8));
 
@@ -129,7 +130,9 @@ int main(int argc, char** argv) {
         const int nyb = (pr[p].n2 + 255) / 256;
         for (int b = 0; b < nyb; ++b) items.push_back({p, b});
     }
-    TcSide* dsides; TcProblem* dtps; MatchProblem* dmps; TcItem* ditems; __half* dbg;
+    TcSide* dsides; TcProblem* dtps; MatchProblem* dmps; TcItem* ditems; __half* dbg; int* sched;
+    CK(cudaMalloc(&sched, 64));
+    CK(cudaMemset(sched, 0, 64));
     CK(cudaMalloc(&dsides, sides.size() * sizeof(TcSide)));
     CK(cudaMalloc(&dtps, P * sizeof(TcProblem)));
     CK(cudaMalloc(&dmps, P * sizeof(MatchProblem)));
@@ -152,7 +155,7 @@ int main(int argc, char** argv) {
     CK(launch_tc_expand(dsides, (int)sides.size(), max_tiles, s));
     CK(cudaStreamSynchronize(s));
     printf("expand ok\n"); fflush(stdout);
-    CK(launch_tc_hamming(dtps, ditems, (int)items.size(), sms, dbg, s));
+    CK(launch_tc_hamming(dtps, ditems, (int)items.size(), nullptr, 0, sched, sms, dbg, s));
     CK(cudaStreamSynchronize(s));
     printf("tc ok\n"); fflush(stdout);
     CK(launch_tc_resolve(dmps, dtps, P, 4, s));
@@ -224,7 +227,7 @@ int main(int argc, char** argv) {
         CK(cudaEventRecord(e0, s));
         CK(launch_tc_expand(dsides, (int)sides.size(), max_tiles, s));
         CK(cudaEventRecord(e1, s));
-        CK(launch_tc_hamming(dtps, ditems, (int)items.size(), sms, nullptr, s));
+        CK(launch_tc_hamming(dtps, ditems, (int)items.size(), nullptr, 0, sched, sms, nullptr, s));
         CK(cudaEventRecord(e2, s));
         CK(launch_tc_resolve(dmps, dtps, P, 4, s));
         CK(cudaEventRecord(e3, s));
