@@ -70,13 +70,15 @@ struct Workspace {
     std::vector<int32_t> item_start[2];   // [B+1] first work item of each pair in either list
     int tc_max_tiles = 0;
     DevBuf d_tcprob, d_tcsides, d_tcitems[2], d_exp, d_rowp, d_colp, d_sched;
+    DevBuf d_stream;       // arena of the streamed solver (frames too large for K2's shared memory)
+    bool use_stream = false;
     size_t feat_stride = 0;
     void release() {
         DevBuf* all[] = {&d_poff1, &d_poff2, &d_loff1, &d_loff2, &d_pdesc1, &d_pdesc2, &d_ldesc1, &d_ldesc2,
                          &d_ptP, &d_pts2, &d_ptpl, &d_lssP, &d_lseP, &d_lsspl, &d_lsepl, &d_lss2, &d_lslev,
                          &d_lsle, &d_priors, &d_results, &d_m12p, &d_m12l, &d_inlp, &d_inll, &d_rowpart,
                          &d_colpart, &d_problems, &d_tiles, &d_feat, &d_phase, &d_tcprob, &d_tcsides, &d_tcitems[0],
-                         &d_tcitems[1], &d_exp, &d_rowp, &d_colp, &d_sched};
+                         &d_tcitems[1], &d_exp, &d_rowp, &d_colp, &d_sched, &d_stream};
         for (DevBuf* b : all) b->release();
     }
 };
@@ -160,6 +162,58 @@ int pow2_ceil_host(int n) {
     int m = 1;
     while (m < n) m <<= 1;
     return m;
+}
+
+
+// PLSTVO_STREAM_SOLVE=1 sends every solve through the streamed form (tests on small frames); =0 never does (K2 with its
+// lists in global scratch instead); default: streamed exactly when the lists do not fit K2's shared memory
+int stream_mode() {
+    static const int m = [] {
+        const char* v = getenv("PLSTVO_STREAM_SOLVE");
+        return v ? atoi(v) : -1;
+    }();
+    return m;
+}
+
+// carves the streamed solver's buffers for B problems out of one arena; slots = record slots (prev-frame features in track
+// mode, list entries in explicit mode)
+int stream_bufs_prepare(PlContext* ctx, DevBuf& arena, int B, size_t slots_pt, size_t slots_ls, StreamBufs* sb) {
+    const int slices = 4;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_rp = take((slots_pt + 512) * 2 * sizeof(float4)), o_rl = take((slots_ls + 256) * 4 * sizeof(float4));
+    const size_t o_cp = take((size_t)B * 4), o_cl = take((size_t)B * 4), o_dt = take((size_t)B * 16 * 8), o_ac = take((size_t)B * 4);
+    const size_t o_ctl = take((size_t)B * sizeof(StreamCtl)), o_par = take(stream_partial_doubles(B, slices) * 8);
+    const size_t o_h = take((size_t)B * 36 * 8), o_g = take((size_t)B * 6 * 8), o_e = take((size_t)B * 8);
+    const size_t o_fp = take(slots_pt + 16), o_fl = take(slots_ls + 16), o_mp = take((slots_pt + 16) * 2), o_ml = take((slots_ls + 16) * 2);
+    CK(ctx, arena.ensure(off));
+    uint8_t* b = arena.as<uint8_t>();
+    sb->rec_pt = reinterpret_cast<float4*>(b + o_rp);
+    sb->rec_ls = reinterpret_cast<float4*>(b + o_rl);
+    sb->cnt_pt = reinterpret_cast<int32_t*>(b + o_cp);
+    sb->cnt_ls = reinterpret_cast<int32_t*>(b + o_cl);
+    sb->DT = reinterpret_cast<double*>(b + o_dt);
+    sb->active = reinterpret_cast<int32_t*>(b + o_ac);
+    sb->ctl = reinterpret_cast<StreamCtl*>(b + o_ctl);
+    sb->partial = reinterpret_cast<double*>(b + o_par);
+    sb->H = reinterpret_cast<double*>(b + o_h);
+    sb->g = reinterpret_cast<double*>(b + o_g);
+    sb->e = reinterpret_cast<double*>(b + o_e);
+    sb->flag_pt = b + o_fp;
+    sb->flag_ls = b + o_fl;
+    sb->midx_pt = reinterpret_cast<uint16_t*>(b + o_mp);
+    sb->midx_ls = reinterpret_cast<uint16_t*>(b + o_ml);
+    sb->slices = slices;
+    sb->sm_count = ctx->sm_count;
+    return 0;
+}
+
+// the per-problem arrays of a chunk of pairs starting at p0 (record / flag arrays are indexed by absolute slots)
+StreamBufs stream_bufs_at(const StreamBufs& sb, int p0) {
+    StreamBufs r = sb;
+    r.cnt_pt += p0; r.cnt_ls += p0; r.DT += (size_t)p0 * 16; r.active += p0; r.ctl += p0;
+    r.partial += stream_partial_doubles(p0, sb.slices); r.H += (size_t)p0 * 36; r.g += (size_t)p0 * 6; r.e += p0;
+    return r;
 }
 
 // ---- planning -------------------------------------------------------------------------------------
@@ -392,7 +446,8 @@ int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfi
         CK(ctx, ws.d_results.ensure((size_t)B * sizeof(PlPoseResult)));
         CK(ctx, ws.d_inlp.ensure(np1));
         CK(ctx, ws.d_inll.ensure(nl1));
-        if (!ws.feat_in_smem) {
+        ws.use_stream = stream_mode() == 1 || (stream_mode() != 0 && !ws.feat_in_smem);
+        if (!ws.feat_in_smem || ws.use_stream) {
             ws.feat_stride = k2_feat_stride(ws.cap_pt, ws.cap_ls);
             CK(ctx, ws.d_feat.ensure((size_t)B * ws.feat_stride * sizeof(double)));
         }
@@ -541,6 +596,17 @@ int ws_launch_solve(PlContext* ctx, Workspace& ws, int p0, int p1, bool have_lev
     prm.sort_cap = ws.sort_cap;
     prm.feat_in_smem = ws.feat_in_smem ? 1 : 0;
     prm.phase_cycles = ws.d_phase.as<long long>();
+    if (ws.use_stream) {
+        StreamBufs sb;
+        int rc = stream_bufs_prepare(ctx, ws.d_stream, ws.B, (size_t)ws.p_off1[ws.B], (size_t)ws.l_off1[ws.B], &sb);
+        if (rc) return rc;
+        prm.feat_scratch = ws.d_feat.as<double>() + (size_t)p0 * ws.feat_stride;
+        prm.feat_in_smem = 0;
+        int nl = 0;
+        CK(ctx, launch_stream_solve(prm, p1 - p0, stream_bufs_at(sb, p0), s, &nl));
+        ctx->launches += nl;
+        return 0;
+    }
     CK(ctx, launch_track_solve(prm, p1 - p0, s));
     ctx->launches++;
     return 0;
@@ -1560,7 +1626,8 @@ int plstvo_optimize_pose(PlContext* ctx, const PlCamera* cam, const PlConfig* cf
     CK(ctx, ctx->gn_out[0].ensure(std::max<size_t>(n, 16)));
     CK(ctx, ctx->gn_out[1].ensure(std::max<size_t>(l, 16)));
     size_t stride = 0;
-    if (!in_smem) {
+    const bool streamed = stream_mode() == 1 || (stream_mode() != 0 && !in_smem);
+    if (!in_smem || streamed) {
         stride = k2_feat_stride(cap_pt, cap_ls);
         CK(ctx, ws.d_feat.ensure((size_t)B * stride * sizeof(double)));
     }
@@ -1585,8 +1652,19 @@ int plstvo_optimize_pose(PlContext* ctx, const PlCamera* cam, const PlConfig* cf
     prm.cap_ls = cap_ls;
     prm.sort_cap = sort_cap;
     prm.feat_in_smem = in_smem ? 1 : 0;
-    CK(ctx, launch_track_solve(prm, B, s));
-    ctx->launches++;
+    if (streamed) {
+        StreamBufs sb;
+        const int rc = stream_bufs_prepare(ctx, ws.d_stream, B, n, l, &sb);
+        if (rc) return rc;
+        prm.feat_scratch = ws.d_feat.as<double>();
+        prm.feat_in_smem = 0;
+        int nl = 0;
+        CK(ctx, launch_stream_solve(prm, B, sb, s, &nl));
+        ctx->launches += nl;
+    } else {
+        CK(ctx, launch_track_solve(prm, B, s));
+        ctx->launches++;
+    }
     CK(ctx, cudaMemcpyAsync(results, ws.d_results.p, (size_t)B * sizeof(PlPoseResult), cudaMemcpyDeviceToHost, s));
     if (inlier_pt && n) CK(ctx, cudaMemcpyAsync(inlier_pt, ctx->gn_out[0].p, n, cudaMemcpyDeviceToHost, s));
     if (inlier_ls && l) CK(ctx, cudaMemcpyAsync(inlier_ls, ctx->gn_out[1].p, l, cudaMemcpyDeviceToHost, s));

@@ -102,7 +102,42 @@ struct SolveParams {
     int32_t  sort_cap;        // power of two >= max(cap_pt, cap_ls)
     int32_t  feat_in_smem;
     long long* phase_cycles;  // optional [pairs][8] debug timers (PLSTVO_PHASE_DEBUG), else null
+    const int32_t* only_if;   // optional [pairs]: the CTA of pair p returns at once unless only_if[p] != 0
 };
+
+// ---- streamed optimizePose (solve.cu + gn_stream.cu): frames whose matched lists do not fit K2's shared memory ------------
+// GN evaluations run as sweeps of gn_eval_stream_kernel over the fp32-packed records of ALL problems of the launch (HBM-bound),
+// a one-warp-per-problem step kernel does the 6x6 solve / pose update / stop tests between sweeps, removeOutliers and the
+// finalisation stay double precision on the fp64 lists.  Problems that leave the common path (robust fallback, solver_mode 1)
+// are handed to K2 (global-scratch form) through SolveParams::only_if.
+struct StreamCtl {            // per problem
+    double DT0[16];           // initial pose of optimizePose
+    double cov[36];
+    double err, err_prev;
+    int32_t iters, phase, fail_first, delegate, done, status, iters1, iters2, n_inl_p, n_inl_l, np, nl;
+};
+struct StreamBufs {
+    float4*  rec_pt;          // 2 float4 per point slot, tile-planar (gn_stream.cu)
+    float4*  rec_ls;          // 4 float4 per line slot
+    int32_t* cnt_pt;          // [B] live records per problem
+    int32_t* cnt_ls;
+    double*  DT;              // [B][16] pose being optimised: the sweeps read it, the step kernel updates it
+    int32_t* active;          // [B]
+    StreamCtl* ctl;           // [B]
+    double*  partial;         // sweep partials
+    double*  H;               // [B][36]
+    double*  g;               // [B][6]
+    double*  e;               // [B]
+    uint8_t* flag_pt;         // inlier flags per list entry (slots of the prev frame / of the explicit list)
+    uint8_t* flag_ls;
+    uint16_t* midx_pt;        // prev index of list entry k (track mode)
+    uint16_t* midx_ls;
+    int32_t  slices;          // sweep work items per problem
+    int32_t  sm_count;
+};
+size_t stream_partial_doubles(int B, int slices);
+// prm.feat_scratch must hold k2_feat_stride() doubles per pair; prm.feat_in_smem must be 0
+cudaError_t launch_stream_solve(const SolveParams& prm, int n_pairs, const StreamBufs& sb, cudaStream_t stream, int* launches);
 
 size_t k2_smem_bytes(int cap_pt, int cap_ls, int sort_cap, bool feat_in_smem);
 size_t k2_feat_stride(int cap_pt, int cap_ls);   // doubles of global feature scratch per pair
@@ -170,7 +205,8 @@ int gn_stream_partials_per_slice();   // fp64 partial records one slice writes (
 cudaError_t launch_pack_records(const MatchedDev& m, int B, int n_pt, int n_ls, float4* pt, float4* ls, cudaStream_t stream);
 cudaError_t launch_gn_eval_stream(const PlCamera& cam, const PlConfig& cfg, const int32_t* pt_off, const int32_t* ls_off,
                                   const float4* pt, const float4* ls, int B, const double* DT, double* partial,
-                                  int slices_per_problem, int sm_count, double* H, double* g, double* e, cudaStream_t stream);
+                                  int slices_per_problem, int sm_count, double* H, double* g, double* e, cudaStream_t stream,
+                                  const int32_t* pt_cnt = nullptr, const int32_t* ls_cnt = nullptr, const int32_t* active = nullptr);
 
 // cudaFuncSetAttribute is per device: a process may drive several GPUs (one context each), so the opted-in dynamic
 // shared-memory size is remembered per device (`done`: one slot per device ordinal, zero-initialised by the caller).

@@ -233,11 +233,17 @@ __global__ void pack_records_kernel(MatchedDev m, int B, int n_pt, int n_ls, flo
 struct GsItem {
     int p0, np, l0, nl, pt_lo, n_ptile, lt_lo, n_tiles;
 };
-__device__ __forceinline__ GsItem gs_item(const int32_t* __restrict__ pt_off, const int32_t* __restrict__ ls_off, int item, int bpp) {
+// cnt (optional): live records per problem when the lists are shorter than their slots (matched lists inside the prev
+// frame's slots); active (optional): problems whose flag is 0 stream nothing
+struct GsLists {
+    const int32_t* pt_off; const int32_t* ls_off; const int32_t* pt_cnt; const int32_t* ls_cnt; const int32_t* active;
+};
+__device__ __forceinline__ GsItem gs_item(const GsLists& L, int item, int bpp) {
     GsItem it;
     const int prob = item / bpp, blk = item % bpp;
-    it.p0 = pt_off[prob]; it.np = pt_off[prob + 1] - it.p0;
-    it.l0 = ls_off[prob]; it.nl = ls_off[prob + 1] - it.l0;
+    it.p0 = L.pt_off[prob]; it.np = L.pt_cnt ? L.pt_cnt[prob] : L.pt_off[prob + 1] - it.p0;
+    it.l0 = L.ls_off[prob]; it.nl = L.ls_cnt ? L.ls_cnt[prob] : L.ls_off[prob + 1] - it.l0;
+    if (L.active && !L.active[prob]) it.np = it.nl = 0;
     const int ptiles = (it.np + GS_PT_TILE - 1) / GS_PT_TILE, ltiles = (it.nl + GS_LS_TILE - 1) / GS_LS_TILE;
     const int pt_per = (ptiles + bpp - 1) / bpp, lt_per = (ltiles + bpp - 1) / bpp;
     it.pt_lo = min(ptiles, blk * pt_per);
@@ -249,7 +255,7 @@ __device__ __forceinline__ GsItem gs_item(const int32_t* __restrict__ pt_off, co
 
 template <class Acc>
 __global__ void __launch_bounds__(GS_THREADS, 2)
-gn_eval_stream_kernel(PlCamera cam, float homog_th, const int32_t* __restrict__ pt_off, const int32_t* __restrict__ ls_off,
+gn_eval_stream_kernel(PlCamera cam, float homog_th, const GsLists L,
                       const float4* __restrict__ pt, const float4* __restrict__ ls, const double* __restrict__ DTs,
                       double* __restrict__ partial, int bpp, int n_items) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -269,7 +275,7 @@ gn_eval_stream_kernel(PlCamera cam, float homog_th, const int32_t* __restrict__ 
         if (lane == 0) {
             uint32_t k = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const GsItem it = gs_item(pt_off, ls_off, item, bpp);
+                const GsItem it = gs_item(L, item, bpp);
                 for (int t = 0; t < it.n_tiles; ++t, ++k) {
                     const uint32_t st = k % GS_STAGES;
                     if (k >= GS_STAGES) mbar_wait(&empty[st], ((k / GS_STAGES) - 1) & 1);
@@ -303,7 +309,7 @@ gn_eval_stream_kernel(PlCamera cam, float homog_th, const int32_t* __restrict__ 
     P.h = homog_th; P.inv_h = 1.f / homog_th; P.fx_h = P.fx / homog_th;
     uint32_t k = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const GsItem it = gs_item(pt_off, ls_off, item, bpp);
+        const GsItem it = gs_item(L, item, bpp);
         if (it.n_tiles > 0) {
             const uint32_t st0 = k % GS_STAGES;
             mbar_wait(&full[st0], (k / GS_STAGES) & 1);
@@ -361,8 +367,9 @@ gn_eval_stream_kernel(PlCamera cam, float homog_th, const int32_t* __restrict__ 
 // Folds the bpp x 8 fp64 partial records of a problem in index order (a per-item fence + counter in the streaming kernel
 // costs more than this second launch: measured 82 vs 70 us per sweep).
 __global__ void gn_eval_reduce_kernel(const double* __restrict__ partial, int n_part, double* __restrict__ H,
-                                      double* __restrict__ g, double* __restrict__ e) {
+                                      double* __restrict__ g, double* __restrict__ e, const int32_t* __restrict__ active) {
     const int prob = blockIdx.x, lane = threadIdx.x;
+    if (active && !active[prob]) return;
     double sum = 0.0;
     if (lane < GS_NACC)
         for (int b = 0; b < n_part; b++) sum += partial[((size_t)prob * n_part + b) * GS_NACC + lane];
@@ -396,7 +403,8 @@ cudaError_t launch_pack_records(const MatchedDev& m, int B, int n_pt, int n_ls, 
 
 cudaError_t launch_gn_eval_stream(const PlCamera& cam, const PlConfig& cfg, const int32_t* pt_off, const int32_t* ls_off,
                                   const float4* pt, const float4* ls, int B, const double* DT, double* partial, int bpp,
-                                  int sm_count, double* H, double* g, double* e, cudaStream_t stream) {
+                                  int sm_count, double* H, double* g, double* e, cudaStream_t stream, const int32_t* pt_cnt,
+                                  const int32_t* ls_cnt, const int32_t* active) {
     if (B <= 0) return cudaSuccess;
     const size_t smem = (size_t)GS_STAGES * GS_STAGE_BYTES;
     static const bool packed = getenv("PLSTVO_GS_SCALAR") == nullptr;   // A/B knob: scalar-FFMA accumulators (default: packed FFMA2)
@@ -406,15 +414,16 @@ cudaError_t launch_gn_eval_stream(const PlCamera& cam, const PlConfig& cfg, cons
     if (err != cudaSuccess) return err;
     const int n_items = B * bpp;
     const int grid = n_items < 2 * sm_count ? n_items : 2 * sm_count;
+    const GsLists L{pt_off, ls_off, pt_cnt, ls_cnt, active};
     if (packed)
-        gn_eval_stream_kernel<GsAccPacked><<<grid, GS_THREADS, smem, stream>>>(cam, (float)cfg.homog_th, pt_off, ls_off, pt, ls, DT,
-                                                                               partial, bpp, n_items);
+        gn_eval_stream_kernel<GsAccPacked><<<grid, GS_THREADS, smem, stream>>>(cam, (float)cfg.homog_th, L, pt, ls, DT, partial, bpp,
+                                                                               n_items);
     else
-        gn_eval_stream_kernel<GsAccScalar><<<grid, GS_THREADS, smem, stream>>>(cam, (float)cfg.homog_th, pt_off, ls_off, pt, ls, DT,
-                                                                               partial, bpp, n_items);
+        gn_eval_stream_kernel<GsAccScalar><<<grid, GS_THREADS, smem, stream>>>(cam, (float)cfg.homog_th, L, pt, ls, DT, partial, bpp,
+                                                                               n_items);
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
-    gn_eval_reduce_kernel<<<B, 32, 0, stream>>>(partial, bpp * GS_CWARPS, H, g, e);
+    gn_eval_reduce_kernel<<<B, 32, 0, stream>>>(partial, bpp * GS_CWARPS, H, g, e, active);
     return cudaGetLastError();
 }
 

@@ -1065,40 +1065,97 @@ __device__ int block_exclusive_scan(State& st, int v, int* total) {
     return base + inc - v;
 }
 
-__global__ void __launch_bounds__(K2_THREADS, 1) track_solve_kernel(const SolveParams prm) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    const int pair = prm.first_pair + blockIdx.x;
+// Pose finalisation (src/stereoFrameHandler.cpp:372-391) by ONE warp: gate, curr->DT = exp(log(inverse(DT))), Tfw chain,
+// covariance propagation, eigenvalues; fills st.out.  `phase_out` (optional): the debug phase timers of this pair.
+__device__ void finalize_pose(State& st, const PlPrior* prior, const Feat& f, int lane, long long* phase_out) {
+        const long long t_f = clock64();
+        PlPoseResult& o = st.out;
+        double* Tfw_prev = st.red[0];        // 16 doubles of scratch
+        double* Tfw_cov_prev = st.red[1];    // 36 doubles (runs into red[2], free here)
+        double* Ad = st.red[4];              // 36 doubles (red[4], red[5])
+        if (lane < 16) Tfw_prev[lane] = prior ? prior->Tfw[lane] : ((lane % 5 == 0) ? 1.0 : 0.0);
+        for (int i = lane; i < 36; i += 32)  // initialize(): Tfw = I, Tfw_cov = I (:43-44)
+            Tfw_cov_prev[i] = prior ? prior->Tfw_cov[i] : ((i % 7 == 0) ? 1.0 : 0.0);
+        if (lane < 16) o.DT_opt[lane] = st.DT[lane];
+        __syncwarp();
+        double eig[6], D[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) D[i] = st.DT[i];
+        const bool ok = warp_is_good_solution(st.DT, st.cov, st.err, eig) && !mat4_is_identity(D);
+        if (ok) {
+            double Ti[16], x[6], E[16], T2[16], T3[16], P[16];
+            inverse_se3(D, Ti);
+            logmap_se3(Ti, x);
+            expmap_se3(x, E);                                                     // :374
+#pragma unroll
+            for (int i = 0; i < 16; i++) P[i] = Tfw_prev[i];
+            mat4_mul(P, E, T2);
+            logmap_se3(T2, x);
+            expmap_se3(x, T3);                                                    // :377
+            double e_mine = E[0], t_mine = T3[0];
+#pragma unroll
+            for (int i = 1; i < 16; i++) {
+                e_mine = (lane == i) ? E[i] : e_mine;
+                t_mine = (lane == i) ? T3[i] : t_mine;
+            }
+            if (lane < 16) { o.DT[lane] = e_mine; o.Tfw[lane] = t_mine; }
+            for (int i = lane; i < 36; i += 32) o.DT_cov[i] = st.cov[i];
+            // unccomp_se3 (src/auxiliar.cpp:175-197): cov1 + Ad(T1) covinc Ad(T1)^T, Ad = [R, skew(t) R; 0, R]
+            {
+                double S[9], R3[9], SR[9];
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int j = 0; j < 3; j++) R3[i * 3 + j] = P[i * 4 + j];
+                skew3(P[3], P[7], P[11], S);
+                mat3_mul(S, R3, SR);
+                for (int e = lane; e < 36; e += 32) {
+                    const int i = e / 6, j = e % 6;
+                    double v = 0.0;
+                    if (i < 3 && j < 3) v = sel9(R3, i * 3 + j);
+                    else if (i < 3 && j >= 3) v = sel9(SR, i * 3 + (j - 3));
+                    else if (i >= 3 && j >= 3) v = sel9(R3, (i - 3) * 3 + (j - 3));
+                    Ad[e] = v;
+                }
+            }
+            __syncwarp();
+            for (int e = lane; e < 36; e += 32) {
+                const int i = e / 6, j = e % 6;
+                double s = 0.0;
+                for (int k = 0; k < 6; k++) {
+                    double tk = 0.0;
+                    for (int l = 0; l < 6; l++) tk += Ad[i * 6 + l] * st.cov[l * 6 + k];
+                    s += tk * Ad[j * 6 + k];
+                }
+                o.Tfw_cov[e] = Tfw_cov_prev[e] + s;                               // :378
+            }
+            if (lane < 6) o.DT_cov_eig[lane] = sel6(eig, lane);                   // :379-380
+            if (lane == 0) { o.err_norm = st.err; o.good = 1; }
+        } else {
+            if (lane < 16) { o.DT[lane] = (lane % 5 == 0) ? 1.0 : 0.0; o.Tfw[lane] = Tfw_prev[lane]; }
+            for (int i = lane; i < 36; i += 32) { o.DT_cov[i] = 0.0; o.Tfw_cov[i] = Tfw_cov_prev[i]; }
+            if (lane < 6) o.DT_cov_eig[lane] = 0.0;
+            if (lane == 0) { o.err_norm = -1.0; o.good = 0; }
+        }
+        if (lane == 0) {
+            o.n_matched_pt = f.np;
+            o.n_matched_ls = f.nl;
+            o.n_inliers_pt = st.n_inl_p;
+            o.n_inliers_ls = st.n_inl_l;
+            o.n_inliers = st.n_inl_p + st.n_inl_l;
+            o.reserved = 0;
+            st.tc[6] += clock64() - t_f;
+            if (phase_out)
+                for (int i = 0; i < 8; i++) phase_out[i] = st.tc[i];
+        }
+}
 
-    // ---- carve shared memory ----
-    State& st = *reinterpret_cast<State*>(smem);
-    size_t off = align_up(sizeof(State), 16);
-    double* sortbuf = reinterpret_cast<double*>(smem + off);
-    off += (size_t)prm.sort_cap * sizeof(double);
-    Feat f;
-    f.inl_p = smem + off;  off += align_up((size_t)prm.cap_pt, 16);
-    f.inl_l = smem + off;  off += align_up((size_t)prm.cap_ls, 16);
-    uint16_t* midx_p = reinterpret_cast<uint16_t*>(smem + off);  off += align_up((size_t)prm.cap_pt * 2, 16);
-    uint16_t* midx_l = reinterpret_cast<uint16_t*>(smem + off);  off += align_up((size_t)prm.cap_ls * 2, 16);
-    double* fb = prm.feat_in_smem ? reinterpret_cast<double*>(smem + off)
-                                  : prm.feat_scratch + (size_t)blockIdx.x * prm.feat_scratch_stride;
-    {
-        const int cp = prm.cap_pt, cl = prm.cap_ls;
-        f.Px = fb; f.Py = fb + cp; f.Pz = fb + 2 * cp; f.pu = fb + 3 * cp; f.pv = fb + 4 * cp; f.pss = fb + 5 * cp;
-        double* lb = fb + PT_ARRAYS * (size_t)cp;
-        f.sX = lb; f.sY = lb + cl; f.sZ = lb + 2 * cl; f.eX = lb + 3 * cl; f.eY = lb + 4 * cl; f.eZ = lb + 5 * cl;
-        f.l0 = lb + 6 * cl; f.l1 = lb + 7 * cl; f.l2 = lb + 8 * cl; f.oa = lb + 9 * cl; f.ob = lb + 10 * cl;
-        f.oc = lb + 11 * cl; f.lss = lb + 12 * cl;
-    }
+// Phases A and B of the per-pair work: finish the matching (merge K1's partials, ratio test, mutual filter -> m12) and build
+// matched_pt / matched_ls in ascending prev index as SoA (f), or copy the caller's explicit lists (mode 1).  Block-wide.
+__device__ void build_matched_lists(const SolveParams& prm, int pair, State& st, double* sortbuf, Feat& f, uint16_t* midx_p,
+                                    uint16_t* midx_l, int& n1p, int& n1l, size_t& out_p0, size_t& out_l0, long long& t_ph) {
+    const int tid = threadIdx.x, nth = blockDim.x;
     const PlConfig& cfg = prm.cfg;
-    const Cam cam = {prm.cam.fx, prm.cam.fy, prm.cam.cx, prm.cam.cy};
-
-    if (tid == 0)
-        for (int i = 0; i < 8; i++) st.tc[i] = 0;
-    long long t_ph = clock64();
-    int n1p = 0, n1l = 0;        // prev-frame feature counts (mode 0) / list lengths (mode 1)
-    size_t out_p0 = 0, out_l0 = 0;   // where this pair's inlier flags start
-
     if (prm.mode == 0) {
         // ---- A. finish the matching: merge partials, ratio test, mutual filter -> m12 (global) ----
         const MatchProblem pp = prm.problems[2 * pair], pl = prm.problems[2 * pair + 1];
@@ -1201,6 +1258,44 @@ __global__ void __launch_bounds__(K2_THREADS, 1) track_solve_kernel(const SolveP
             st.n_inl_l = f.nl;
         }
     }
+}
+
+__global__ void __launch_bounds__(K2_THREADS, 1) track_solve_kernel(const SolveParams prm) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int pair = prm.first_pair + blockIdx.x;
+    if (prm.only_if && !prm.only_if[blockIdx.x]) return;   // streamed path: only the problems it handed back
+
+    // ---- carve shared memory ----
+    State& st = *reinterpret_cast<State*>(smem);
+    size_t off = align_up(sizeof(State), 16);
+    double* sortbuf = reinterpret_cast<double*>(smem + off);
+    off += (size_t)prm.sort_cap * sizeof(double);
+    Feat f;
+    f.inl_p = smem + off;  off += align_up((size_t)prm.cap_pt, 16);
+    f.inl_l = smem + off;  off += align_up((size_t)prm.cap_ls, 16);
+    uint16_t* midx_p = reinterpret_cast<uint16_t*>(smem + off);  off += align_up((size_t)prm.cap_pt * 2, 16);
+    uint16_t* midx_l = reinterpret_cast<uint16_t*>(smem + off);  off += align_up((size_t)prm.cap_ls * 2, 16);
+    double* fb = prm.feat_in_smem ? reinterpret_cast<double*>(smem + off)
+                                  : prm.feat_scratch + (size_t)blockIdx.x * prm.feat_scratch_stride;
+    {
+        const int cp = prm.cap_pt, cl = prm.cap_ls;
+        f.Px = fb; f.Py = fb + cp; f.Pz = fb + 2 * cp; f.pu = fb + 3 * cp; f.pv = fb + 4 * cp; f.pss = fb + 5 * cp;
+        double* lb = fb + PT_ARRAYS * (size_t)cp;
+        f.sX = lb; f.sY = lb + cl; f.sZ = lb + 2 * cl; f.eX = lb + 3 * cl; f.eY = lb + 4 * cl; f.eZ = lb + 5 * cl;
+        f.l0 = lb + 6 * cl; f.l1 = lb + 7 * cl; f.l2 = lb + 8 * cl; f.oa = lb + 9 * cl; f.ob = lb + 10 * cl;
+        f.oc = lb + 11 * cl; f.lss = lb + 12 * cl;
+    }
+    const PlConfig& cfg = prm.cfg;
+    const Cam cam = {prm.cam.fx, prm.cam.fy, prm.cam.cx, prm.cam.cy};
+
+    if (tid == 0)
+        for (int i = 0; i < 8; i++) st.tc[i] = 0;
+    long long t_ph = clock64();
+    int n1p = 0, n1l = 0;        // prev-frame feature counts (mode 0) / list lengths (mode 1)
+    size_t out_p0 = 0, out_l0 = 0;   // where this pair's inlier flags start
+
+    build_matched_lists(prm, pair, st, sortbuf, f, midx_p, midx_l, n1p, n1l, out_p0, out_l0, t_ph);
     __syncthreads();
     if (tid == 0) { st.tc[1] += clock64() - t_ph; }
 
@@ -1278,88 +1373,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) track_solve_kernel(const SolveP
     __syncthreads();
 
     // ---- pose finalisation (:372-391), warp 0 ----
-    if (warp == 0) {
-        const long long t_f = clock64();
-        PlPoseResult& o = st.out;
-        double* Tfw_prev = st.red[0];        // 16 doubles of scratch
-        double* Tfw_cov_prev = st.red[1];    // 36 doubles (runs into red[2], free here)
-        double* Ad = st.red[4];              // 36 doubles (red[4], red[5])
-        if (lane < 16) Tfw_prev[lane] = prior ? prior->Tfw[lane] : ((lane % 5 == 0) ? 1.0 : 0.0);
-        for (int i = lane; i < 36; i += 32)  // initialize(): Tfw = I, Tfw_cov = I (:43-44)
-            Tfw_cov_prev[i] = prior ? prior->Tfw_cov[i] : ((i % 7 == 0) ? 1.0 : 0.0);
-        if (lane < 16) o.DT_opt[lane] = st.DT[lane];
-        __syncwarp();
-        double eig[6], D[16];
-#pragma unroll
-        for (int i = 0; i < 16; i++) D[i] = st.DT[i];
-        const bool ok = warp_is_good_solution(st.DT, st.cov, st.err, eig) && !mat4_is_identity(D);
-        if (ok) {
-            double Ti[16], x[6], E[16], T2[16], T3[16], P[16];
-            inverse_se3(D, Ti);
-            logmap_se3(Ti, x);
-            expmap_se3(x, E);                                                     // :374
-#pragma unroll
-            for (int i = 0; i < 16; i++) P[i] = Tfw_prev[i];
-            mat4_mul(P, E, T2);
-            logmap_se3(T2, x);
-            expmap_se3(x, T3);                                                    // :377
-            double e_mine = E[0], t_mine = T3[0];
-#pragma unroll
-            for (int i = 1; i < 16; i++) {
-                e_mine = (lane == i) ? E[i] : e_mine;
-                t_mine = (lane == i) ? T3[i] : t_mine;
-            }
-            if (lane < 16) { o.DT[lane] = e_mine; o.Tfw[lane] = t_mine; }
-            for (int i = lane; i < 36; i += 32) o.DT_cov[i] = st.cov[i];
-            // unccomp_se3 (src/auxiliar.cpp:175-197): cov1 + Ad(T1) covinc Ad(T1)^T, Ad = [R, skew(t) R; 0, R]
-            {
-                double S[9], R3[9], SR[9];
-#pragma unroll
-                for (int i = 0; i < 3; i++)
-#pragma unroll
-                    for (int j = 0; j < 3; j++) R3[i * 3 + j] = P[i * 4 + j];
-                skew3(P[3], P[7], P[11], S);
-                mat3_mul(S, R3, SR);
-                for (int e = lane; e < 36; e += 32) {
-                    const int i = e / 6, j = e % 6;
-                    double v = 0.0;
-                    if (i < 3 && j < 3) v = sel9(R3, i * 3 + j);
-                    else if (i < 3 && j >= 3) v = sel9(SR, i * 3 + (j - 3));
-                    else if (i >= 3 && j >= 3) v = sel9(R3, (i - 3) * 3 + (j - 3));
-                    Ad[e] = v;
-                }
-            }
-            __syncwarp();
-            for (int e = lane; e < 36; e += 32) {
-                const int i = e / 6, j = e % 6;
-                double s = 0.0;
-                for (int k = 0; k < 6; k++) {
-                    double tk = 0.0;
-                    for (int l = 0; l < 6; l++) tk += Ad[i * 6 + l] * st.cov[l * 6 + k];
-                    s += tk * Ad[j * 6 + k];
-                }
-                o.Tfw_cov[e] = Tfw_cov_prev[e] + s;                               // :378
-            }
-            if (lane < 6) o.DT_cov_eig[lane] = sel6(eig, lane);                   // :379-380
-            if (lane == 0) { o.err_norm = st.err; o.good = 1; }
-        } else {
-            if (lane < 16) { o.DT[lane] = (lane % 5 == 0) ? 1.0 : 0.0; o.Tfw[lane] = Tfw_prev[lane]; }
-            for (int i = lane; i < 36; i += 32) { o.DT_cov[i] = 0.0; o.Tfw_cov[i] = Tfw_cov_prev[i]; }
-            if (lane < 6) o.DT_cov_eig[lane] = 0.0;
-            if (lane == 0) { o.err_norm = -1.0; o.good = 0; }
-        }
-        if (lane == 0) {
-            o.n_matched_pt = f.np;
-            o.n_matched_ls = f.nl;
-            o.n_inliers_pt = st.n_inl_p;
-            o.n_inliers_ls = st.n_inl_l;
-            o.n_inliers = st.n_inl_p + st.n_inl_l;
-            o.reserved = 0;
-            st.tc[6] += clock64() - t_f;
-            if (prm.phase_cycles)
-                for (int i = 0; i < 8; i++) prm.phase_cycles[(size_t)pair * 8 + i] = st.tc[i];
-        }
-    }
+    if (warp == 0) finalize_pose(st, prior, f, lane, prm.phase_cycles ? prm.phase_cycles + (size_t)pair * 8 : nullptr);
     __syncthreads();
     {   // result struct -> HBM, cooperatively (sizeof(PlPoseResult) is a multiple of 8)
         const uint64_t* src = reinterpret_cast<const uint64_t*>(&st.out);
@@ -1414,6 +1428,331 @@ cudaError_t launch_algebra_selftest(const double* H, const double* g, int n, dou
     if (n <= 0) return cudaSuccess;
     algebra_selftest_kernel<<<n, 32, 0, stream>>>(H, g, n, x, lad, inv, eig);
     return cudaGetLastError();
+}
+
+// =====================================================================================================================
+// Streamed optimizePose: the same algorithm cut into kernels around HBM-bound evaluation sweeps (see common.cuh)
+// =====================================================================================================================
+namespace {
+
+struct StreamView {           // per-CTA pointers of the streamed kernels: State + sort buffer in shared memory, lists in HBM
+    State* st;
+    double* sortbuf;
+    Feat f;
+    uint16_t *midx_p, *midx_l;
+    size_t slot_p, slot_l;    // first record slot of this problem
+};
+
+__device__ __forceinline__ StreamView stream_view(const SolveParams& prm, const StreamBufs& sb, uint8_t* smem, int pair, int local) {
+    StreamView v;
+    v.st = reinterpret_cast<State*>(smem);
+    v.sortbuf = reinterpret_cast<double*>(smem + align_up(sizeof(State), 16));
+    v.slot_p = (size_t)(prm.mode == 0 ? prm.prev.pt_off[pair] : prm.matched.pt_off[pair]);
+    v.slot_l = (size_t)(prm.mode == 0 ? prm.prev.ls_off[pair] : prm.matched.ls_off[pair]);
+    v.f.inl_p = sb.flag_pt + v.slot_p;
+    v.f.inl_l = sb.flag_ls + v.slot_l;
+    v.midx_p = sb.midx_pt + v.slot_p;
+    v.midx_l = sb.midx_ls + v.slot_l;
+    double* fb = prm.feat_scratch + (size_t)local * prm.feat_scratch_stride;
+    const int cp = prm.cap_pt, cl = prm.cap_ls;
+    Feat& f = v.f;
+    f.Px = fb; f.Py = fb + cp; f.Pz = fb + 2 * cp; f.pu = fb + 3 * cp; f.pv = fb + 4 * cp; f.pss = fb + 5 * cp;
+    double* lb = fb + PT_ARRAYS * (size_t)cp;
+    f.sX = lb; f.sY = lb + cl; f.sZ = lb + 2 * cl; f.eX = lb + 3 * cl; f.eY = lb + 4 * cl; f.eZ = lb + 5 * cl;
+    f.l0 = lb + 6 * cl; f.l1 = lb + 7 * cl; f.l2 = lb + 8 * cl; f.oa = lb + 9 * cl; f.ob = lb + 10 * cl;
+    f.oc = lb + 11 * cl; f.lss = lb + 12 * cl;
+    f.np = f.nl = 0;
+    return v;
+}
+
+constexpr int SP_TILE = 512, SL_TILE = 256;   // records per 16 KB tile of gn_stream.cu (points / lines)
+
+// fp32 records of this problem from the fp64 lists (tile-planar: [cnt] float4 per plane)
+__device__ void stream_pack_records(const Feat& f, const StreamBufs& sb, size_t slot_p, size_t slot_l) {
+    const int tid = threadIdx.x, nth = blockDim.x;
+    for (int j = tid; j < f.np; j += nth) {
+        const int t = j / SP_TILE, r = j % SP_TILE, cnt = min(SP_TILE, f.np - t * SP_TILE);
+        float4* base = sb.rec_pt + 2 * (slot_p + (size_t)t * SP_TILE);
+        base[r] = make_float4((float)f.Px[j], (float)f.Py[j], (float)f.Pz[j], (float)f.pss[j]);
+        base[cnt + r] = make_float4((float)f.pu[j], (float)f.pv[j], f.inl_p[j] ? 1.f : 0.f, 0.f);
+    }
+    for (int j = tid; j < f.nl; j += nth) {
+        const int t = j / SL_TILE, r = j % SL_TILE, cnt = min(SL_TILE, f.nl - t * SL_TILE);
+        float4* base = sb.rec_ls + 4 * (slot_l + (size_t)t * SL_TILE);
+        base[r] = make_float4((float)f.sX[j], (float)f.sY[j], (float)f.sZ[j], (float)f.lss[j]);
+        base[cnt + r] = make_float4((float)f.eX[j], (float)f.eY[j], (float)f.eZ[j], f.inl_l[j] ? 1.f : 0.f);
+        base[2 * cnt + r] = make_float4((float)f.l0[j], (float)f.l1[j], (float)f.l2[j], 0.f);
+        base[3 * cnt + r] = make_float4((float)f.oa[j], (float)f.ob[j], (float)f.oc[j], 0.f);
+    }
+}
+__device__ void stream_write_flags(const Feat& f, const StreamBufs& sb, size_t slot_p, size_t slot_l) {
+    const int tid = threadIdx.x, nth = blockDim.x;
+    for (int j = tid; j < f.np; j += nth) {
+        const int t = j / SP_TILE, r = j % SP_TILE, cnt = min(SP_TILE, f.np - t * SP_TILE);
+        reinterpret_cast<float*>(sb.rec_pt + 2 * (slot_p + (size_t)t * SP_TILE) + cnt + r)[2] = f.inl_p[j] ? 1.f : 0.f;
+    }
+    for (int j = tid; j < f.nl; j += nth) {
+        const int t = j / SL_TILE, r = j % SL_TILE, cnt = min(SL_TILE, f.nl - t * SL_TILE);
+        reinterpret_cast<float*>(sb.rec_ls + 4 * (slot_l + (size_t)t * SL_TILE) + cnt + r)[3] = f.inl_l[j] ? 1.f : 0.f;
+    }
+}
+
+// ---- S1: matching finish + list building + fp32 records + the head of optimizePose (:317-333) ----
+__global__ void __launch_bounds__(K2_THREADS, 1) stream_prepare_kernel(const SolveParams prm, const StreamBufs sb) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, local = blockIdx.x;
+    const int pair = prm.first_pair + local;
+    StreamView v = stream_view(prm, sb, smem, pair, local);
+    State& st = *v.st;
+    if (tid == 0)
+        for (int i = 0; i < 8; i++) st.tc[i] = 0;
+    long long t_ph = clock64();
+    int n1p = 0, n1l = 0;
+    size_t out_p0 = 0, out_l0 = 0;
+    build_matched_lists(prm, pair, st, v.sortbuf, v.f, v.midx_p, v.midx_l, n1p, n1l, out_p0, out_l0, t_ph);
+    __syncthreads();
+    stream_pack_records(v.f, sb, v.slot_p, v.slot_l);
+    const PlConfig& cfg = prm.cfg;
+    const PlPrior* prior = prm.priors ? &prm.priors[pair] : nullptr;
+    StreamCtl& c = sb.ctl[local];
+    if (warp == 0) {
+        bool use_prior = false;
+        if (cfg.use_motion_model && prior) {   // :317-324
+            if (lane < 16) st.DT0[lane] = prior->DT[lane];
+            for (int i = lane; i < 36; i += 32) st.H[i] = prior->DT_cov[i];
+            __syncwarp();
+            use_prior = warp_is_good_solution(st.DT0, st.H, prior->err_norm, nullptr);
+            __syncwarp();
+        }
+        if (lane < 16) {
+            const double d = use_prior ? st.DT0[lane] : ((lane % 5 == 0) ? 1.0 : 0.0);
+            c.DT0[lane] = d;
+            sb.DT[(size_t)local * 16 + lane] = d;
+        }
+        for (int i = lane; i < 36; i += 32) c.cov[i] = 0.0;
+        if (lane == 0) {
+            const bool enough = v.f.np + v.f.nl >= cfg.min_features;
+            c.err = -1.0;
+            c.err_prev = 999999999.9;
+            c.iters = 0;
+            c.phase = 1;
+            c.fail_first = 0;
+            c.delegate = (cfg.solver_mode != 0) ? 1 : 0;       // the robust main solver stays with K2
+            c.done = enough ? 0 : 1;
+            c.status = enough ? PLSTVO_ST_REFINED : PLSTVO_ST_FEW_BEFORE;
+            c.iters1 = c.iters2 = 0;
+            c.n_inl_p = v.f.np;
+            c.n_inl_l = v.f.nl;
+            c.np = v.f.np;
+            c.nl = v.f.nl;
+            sb.cnt_pt[local] = v.f.np;
+            sb.cnt_ls[local] = v.f.nl;
+            sb.active[local] = (enough && !c.delegate) ? 1 : 0;
+            if (!enough)                                          // :364-368: DT = I
+                for (int i = 0; i < 16; i++) sb.DT[(size_t)local * 16 + i] = (i % 5 == 0) ? 1.0 : 0.0;
+        }
+    }
+}
+
+// ---- S2: one iteration of gaussNewtonOptimization's loop body (:404-427) per active problem, one warp each ----
+__global__ void __launch_bounds__(128) stream_step_kernel(const StreamBufs sb, PlConfig cfg, int n, int max_iters) {
+    __shared__ double sH[4][36], sg[4][8], sDT[4][16], sC[4][36];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, p = blockIdx.x * 4 + w;
+    if (p >= n || !sb.active[p]) return;
+    StreamCtl& c = sb.ctl[p];
+    for (int i = lane; i < 36; i += 32) sH[w][i] = sb.H[(size_t)p * 36 + i];
+    if (lane < 6) sg[w][lane] = sb.g[(size_t)p * 6 + lane];
+    if (lane < 16) sDT[w][lane] = sb.DT[(size_t)p * 16 + lane];
+    __syncwarp();
+    const double err = sb.e[p], err_prev = c.err_prev;
+    const int it = c.iters;
+    bool stop = false, fail_first = false;
+    double new_prev = err_prev;
+    if (err > err_prev) {                                             // :405-410
+        stop = true;
+        fail_first = (it == 0);
+    } else if ((err < cfg.min_error) || fabs(err - err_prev) < cfg.min_error_change) {   // :412-415
+        stop = true;
+    } else {
+        double inc[6], lad;
+        if (!warp_chol6_solve(sH[w], sg[w], inc)) warp_qr6_solve<false>(sH[w], sg[w], inc, lad);   // :417-418
+        apply_increment(sDT[w], inc, lane);                           // :419
+        if (sqrt(inc[0] * inc[0] + inc[1] * inc[1] + inc[2] * inc[2]) < cfg.min_error_change &&
+            sqrt(inc[3] * inc[3] + inc[4] * inc[4] + inc[5] * inc[5]) < cfg.min_error_change)
+            stop = true;                                              // :421-424
+        new_prev = err;
+        if (lane < 16) sb.DT[(size_t)p * 16 + lane] = sDT[w][lane];
+    }
+    if (!stop && it + 1 >= max_iters) stop = true;                    // the for loop runs out
+    if (stop) {
+        if (!fail_first) {                                            // :429-430
+            warp_inv6(sH[w], sC[w]);
+            __syncwarp();
+            for (int i = lane; i < 36; i += 32) c.cov[i] = sC[w][i];
+        }
+        if (lane == 0) {
+            c.err = fail_first ? -1.0 : err;
+            c.fail_first = fail_first ? 1 : 0;
+            sb.active[p] = 0;
+        }
+    }
+    if (lane == 0) {
+        c.iters = it + 1;
+        c.err_prev = new_prev;
+    }
+}
+
+// ---- S3: gate of stage 1 (:341), removeOutliers at the stage-1 pose (:343), restart for stage 2 (:345-355) ----
+__global__ void __launch_bounds__(K2_THREADS, 1) stream_outlier_kernel(const SolveParams prm, const StreamBufs sb) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, local = blockIdx.x;
+    const int pair = prm.first_pair + local;
+    StreamCtl& c = sb.ctl[local];
+    if (c.done || c.delegate) return;
+    StreamView v = stream_view(prm, sb, smem, pair, local);
+    State& st = *v.st;
+    v.f.np = c.np;
+    v.f.nl = c.nl;
+    const PlConfig& cfg = prm.cfg;
+    const Cam cam = {prm.cam.fx, prm.cam.fy, prm.cam.cx, prm.cam.cy};
+    if (tid == 0) {
+        for (int i = 0; i < 8; i++) st.tc[i] = 0;
+        st.n_inl_p = c.n_inl_p;
+        st.n_inl_l = c.n_inl_l;
+    }
+    if (warp == 0) {
+        if (lane < 16) st.DT[lane] = sb.DT[(size_t)local * 16 + lane];
+        for (int i = lane; i < 36; i += 32) st.cov[i] = c.cov[i];
+        __syncwarp();
+        const bool ok = warp_is_good_solution(st.DT, st.cov, c.err, nullptr);
+        if (lane == 0) st.ctrl = ok ? 1 : 0;
+    }
+    __syncthreads();
+    if (!st.ctrl) {                     // stage 1 rejected: the robust fallback (:357-359) is K2's job
+        if (tid == 0) c.delegate = 1;
+        return;
+    }
+    remove_outliers(v.f, st, v.sortbuf, st.DT, cam, cfg);
+    __syncthreads();
+    stream_write_flags(v.f, sb, v.slot_p, v.slot_l);
+    if (tid == 0) {
+        c.iters1 = c.iters;
+        c.n_inl_p = st.n_inl_p;
+        c.n_inl_l = st.n_inl_l;
+        if (st.n_inl_p + st.n_inl_l >= cfg.min_features) {   // stage 2 restarts from the INITIAL pose (:347)
+            c.phase = 2;
+            c.iters = 0;
+            c.err_prev = 999999999.9;
+            sb.active[local] = 1;
+            for (int i = 0; i < 16; i++) sb.DT[(size_t)local * 16 + i] = c.DT0[i];
+        } else {                                             // :351-355
+            c.status = PLSTVO_ST_FEW_AFTER;
+            c.done = 1;
+            for (int i = 0; i < 16; i++) sb.DT[(size_t)local * 16 + i] = (i % 5 == 0) ? 1.0 : 0.0;
+        }
+    }
+}
+
+// ---- S4: finalisation (:372-391), result record, inlier flags in the caller's indexing ----
+__global__ void __launch_bounds__(256) stream_finalize_kernel(const SolveParams prm, const StreamBufs sb, int32_t* only_if) {
+    __shared__ State st;
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, local = blockIdx.x;
+    const int pair = prm.first_pair + local;
+    StreamCtl& c = sb.ctl[local];
+    if (tid == 0) only_if[local] = c.delegate;
+    if (c.delegate) return;
+    Feat f;
+    f.np = c.np;
+    f.nl = c.nl;
+    const size_t slot_p = (size_t)(prm.mode == 0 ? prm.prev.pt_off[pair] : prm.matched.pt_off[pair]);
+    const size_t slot_l = (size_t)(prm.mode == 0 ? prm.prev.ls_off[pair] : prm.matched.ls_off[pair]);
+    const int n1p = prm.mode == 0 ? prm.prev.pt_off[pair + 1] - (int)slot_p : c.np;
+    const int n1l = prm.mode == 0 ? prm.prev.ls_off[pair + 1] - (int)slot_l : c.nl;
+    const PlPrior* prior = prm.priors ? &prm.priors[pair] : nullptr;
+    if (warp == 0) {
+        if (lane < 16) st.DT[lane] = sb.DT[(size_t)local * 16 + lane];
+        for (int i = lane; i < 36; i += 32) st.cov[i] = c.cov[i];
+        if (lane == 0) {
+            for (int i = 0; i < 8; i++) st.tc[i] = 0;
+            st.err = c.done ? -1.0 : c.err;
+            st.n_inl_p = c.n_inl_p;
+            st.n_inl_l = c.n_inl_l;
+            st.out.status = c.status;
+            st.out.iters_stage1 = (c.phase == 2 || c.done) ? c.iters1 : c.iters;
+            st.out.iters_stage2 = (c.phase == 2) ? c.iters : 0;
+        }
+        __syncwarp();
+        finalize_pose(st, prior, f, lane, nullptr);
+    }
+    __syncthreads();
+    {
+        const uint64_t* src = reinterpret_cast<const uint64_t*>(&st.out);
+        uint64_t* dst = reinterpret_cast<uint64_t*>(&prm.results[pair]);
+        for (int i = tid; i < (int)(sizeof(PlPoseResult) / 8); i += nth) dst[i] = src[i];
+    }
+    const uint8_t* fp = sb.flag_pt + slot_p;
+    const uint8_t* fl = sb.flag_ls + slot_l;
+    if (prm.mode == 0) {
+        if (prm.inlier_pt)
+            for (int i = tid; i < n1p; i += nth) prm.inlier_pt[slot_p + i] = 0;
+        if (prm.inlier_ls)
+            for (int i = tid; i < n1l; i += nth) prm.inlier_ls[slot_l + i] = 0;
+        __syncthreads();
+        if (prm.inlier_pt)
+            for (int k = tid; k < c.np; k += nth) prm.inlier_pt[slot_p + sb.midx_pt[slot_p + k]] = fp[k];
+        if (prm.inlier_ls)
+            for (int k = tid; k < c.nl; k += nth) prm.inlier_ls[slot_l + sb.midx_ls[slot_l + k]] = fl[k];
+    } else {
+        if (prm.inlier_pt)
+            for (int k = tid; k < c.np; k += nth) prm.inlier_pt[slot_p + k] = fp[k];
+        if (prm.inlier_ls)
+            for (int k = tid; k < c.nl; k += nth) prm.inlier_ls[slot_l + k] = fl[k];
+    }
+}
+
+}  // namespace
+
+size_t stream_partial_doubles(int B, int slices) { return (size_t)B * slices * gn_stream_partials_per_slice() * (ACC_N + 1); }
+
+cudaError_t launch_stream_solve(const SolveParams& prm_in, int n_pairs, const StreamBufs& sb, cudaStream_t stream, int* launches) {
+    if (n_pairs <= 0) return cudaSuccess;
+    SolveParams prm = prm_in;
+    prm.feat_in_smem = 0;
+    prm.only_if = nullptr;
+    const size_t smem = k2_smem_bytes(prm.cap_pt, prm.cap_ls, prm.sort_cap, false);
+    static size_t conf_a[64] = {}, conf_b[64] = {};
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(stream_prepare_kernel), smem, conf_a);
+    if (e != cudaSuccess) return e;
+    e = ensure_dynamic_smem(reinterpret_cast<const void*>(stream_outlier_kernel), smem, conf_b);
+    if (e != cudaSuccess) return e;
+    int nl = 0;
+    stream_prepare_kernel<<<n_pairs, K2_THREADS, smem, stream>>>(prm, sb);
+    ++nl;
+    const int32_t* off_p = prm.mode == 0 ? prm.prev.pt_off + prm.first_pair : prm.matched.pt_off + prm.first_pair;
+    const int32_t* off_l = prm.mode == 0 ? prm.prev.ls_off + prm.first_pair : prm.matched.ls_off + prm.first_pair;
+    auto gn = [&](int max_iters) -> cudaError_t {
+        for (int it = 0; it < max_iters; ++it) {
+            cudaError_t err = launch_gn_eval_stream(prm.cam, prm.cfg, off_p, off_l, sb.rec_pt, sb.rec_ls, n_pairs, sb.DT, sb.partial,
+                                                    sb.slices, sb.sm_count, sb.H, sb.g, sb.e, stream, sb.cnt_pt, sb.cnt_ls, sb.active);
+            if (err != cudaSuccess) return err;
+            stream_step_kernel<<<(n_pairs + 3) / 4, 128, 0, stream>>>(sb, prm.cfg, n_pairs, max_iters);
+            nl += 3;
+        }
+        return cudaGetLastError();
+    };
+    if ((e = gn(prm.cfg.max_iters)) != cudaSuccess) return e;
+    stream_outlier_kernel<<<n_pairs, K2_THREADS, smem, stream>>>(prm, sb);
+    if ((e = gn(prm.cfg.max_iters_ref)) != cudaSuccess) return e;
+    // the activity array doubles as K2's only_if list once the sweeps are over
+    stream_finalize_kernel<<<n_pairs, 256, 0, stream>>>(prm, sb, sb.active);
+    nl += 2;
+    // whatever left the common path: the whole problem again in K2 (global-scratch form)
+    SolveParams k2 = prm;
+    k2.only_if = sb.active;
+    e = launch_track_solve(k2, n_pairs, stream);
+    ++nl;
+    if (launches) *launches = nl;
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_track_solve(const SolveParams& prm, int n_pairs, cudaStream_t stream) {

@@ -179,11 +179,23 @@ def test_pose_golden_vectors(engine):
                 assert ang < TIGHT_ANG and tr < TIGHT_TR
 
 
-def test_large_frames_use_global_feature_storage(engine, oracle):
-    """C5 shape (8000 + 2000) does not fit the shared-memory feature store: the streamed variant must agree."""
+def _flag_diffs(a, b):
+    return int((np.asarray(a) != np.asarray(b)).sum())
+
+
+def test_large_frames_take_the_streamed_solver(engine, oracle):
+    """C5 shape (8000 + 2000) does not fit K2's shared-memory feature store: optimizePose runs as HBM-bound evaluation sweeps
+    (fp32 per-feature arithmetic, fp64 sums / 6x6 algebra / outlier residuals) with a per-problem step kernel in between.
+    Match indices stay bit-exact; the pose is held to north_star's tolerance (1e-5 rad / 1e-4 m); inlier flags may differ
+    only for residuals within fp32 reach of the threshold (count reported)."""
     cfg = T.kitti_config()
-    prev, curr, _, cam = synth.make_batch("hd", 1)
-    compare(engine.track_batch(cam, cfg, prev, curr), oracle.track_batch(cam, cfg, prev, curr), prev)
+    prev, curr, _, cam = synth.make_batch("hd", 2)
+    gpu, ref = engine.track_batch(cam, cfg, prev, curr), oracle.track_batch(cam, cfg, prev, curr)
+    worst = compare(gpu, ref, prev, tight=False, flags_exact=False)
+    n_diff = _flag_diffs(gpu["inlier_pt"], ref["inlier_pt"]) + _flag_diffs(gpu["inlier_ls"], ref["inlier_ls"])
+    print(f"streamed solver, C5 shape: worst pose deviation {worst}, {n_diff} of {prev.n_pt + prev.n_ls} inlier flags differ")
+    assert n_diff <= 4
+    assert worst[0] < 1e-6 and worst[1] < 1e-5      # measured headroom inside the 1e-5 / 1e-4 bar
 
 
 def test_batch_of_64_pairs_sharded_invariance(engine, oracle):
@@ -350,7 +362,8 @@ def test_async_streaming_equals_blocking_call(engine):
 
 
 def test_explicit_lists_c5_size(engine, oracle):
-    """C5-size explicit lists (8000 + 2000 per problem): the solver's global-scratch variant against the oracle."""
+    """C5-size explicit lists (8000 + 2000 per problem) through plstvo_optimize_pose: the streamed solver against the oracle
+    (and, where oracle/_ref is there, against the reference's compiled code)."""
     cfg = T.kitti_config()
     mb, Ts, cam = synth.make_matched_batch("hd", 3)
     rc, ref, rp, rl = oracle.optimize_pose(cam, cfg, mb)
@@ -358,11 +371,23 @@ def test_explicit_lists_c5_size(engine, oracle):
     for p in range(3):
         assert res["status"][p] == ref["status"][p] and res["good"][p] == ref["good"][p] == 1
         ang, tr = R.pose_error(res["DT"][p], ref["DT"][p])
-        assert ang < TIGHT_ANG and tr < TIGHT_TR
+        assert ang < TOL_ANG and tr < TOL_TR
+        assert abs(res["err_norm"][p] - ref["err_norm"][p]) < 1e-5
+        np.testing.assert_allclose(res["DT_cov"][p], ref["DT_cov"][p], rtol=2e-3, atol=1e-12)
         ang, tr = R.pose_error(res["DT_opt"][p], Ts[p])
         assert ang < 1e-3 and tr < 1e-2
-    np.testing.assert_array_equal(ip, rp)
-    np.testing.assert_array_equal(il, rl)
+    n_diff = _flag_diffs(ip, rp) + _flag_diffs(il, rl)
+    print(f"streamed solver, explicit C5 lists: {n_diff} of {len(ip) + len(il)} inlier flags differ")
+    assert n_diff <= 6
+    try:
+        from oracle import ref as ref_mod
+        if ref_mod.available():
+            rr = ref_mod.Ref().optimize_pose(cam, cfg, mb)[1]
+            for p in range(3):
+                ang, tr = R.pose_error(res["DT"][p], rr["DT"][p])
+                assert ang < TOL_ANG and tr < TOL_TR
+    except ImportError:
+        pass
 
 
 def test_two_contexts_on_two_devices_in_one_process(oracle):
