@@ -617,7 +617,7 @@ def tile_batch(fb, reps):
     return fb.select([i % B for i in range(B * reps)])
 
 
-def c5_pipeline(eng, B, steps=3, distinct=32):
+def c5_pipeline(eng, B, steps=3, distinct=128):
     """BASELINE config C5 through the PRODUCT path (plstvo_batch_upload / plstvo_batch_run): 1920x1080, 8000 points + 2000 lines per
     frame, f2fTracking (8000 x 8000 and 2000 x 2000 Hamming problems, both directions) + optimizePose with the KITTI solver
     parameters.  Lists of this size do not fit K2's shared memory: the solve runs as evaluation sweeps streamed from HBM
@@ -644,11 +644,12 @@ def c5_pipeline(eng, B, steps=3, distinct=32):
     sweep_bytes = int(per_eval.sum())                         # one sweep over every problem
     peak, kind = measured_peak()
     tr = ncu_traffic("c5_traffic.json") or {}
-    solve_s = st["ms_solve"] * 1e-3
+    solve_s = st["ms_optimize_pose"] * 1e-3
     return {"workload": "C5: 1920x1080, 8000 pts + 2000 lines per frame, match + optimizePose (KITTI solver parameters), "
                         f"{B} pairs resident ({min(B, distinct)} distinct, repeated)",
             "pairs": B, "ms_per_step": ms, "value": B / (ms * 1e-3), "unit": UNIT, "solved_ok": int(res["good"].sum()),
-            "stage_ms": {k: st[k] for k in ("ms_expand", "ms_distance", "ms_resolve", "ms_solve")},
+            "stage_ms": {k: st[k] for k in ("ms_expand", "ms_distance", "ms_resolve", "ms_lists", "ms_optimize_pose")},
+            "streamed_solver": st["streamed_solver"],
             "evaluations_per_solve": {"mean": float(evals.mean()), "min": int(evals.min()), "max": int(evals.max())},
             "clocks": clk.summary(),
             "roofline": {"kernel": "streamed optimizePose: gn_eval_stream_kernel sweeps + step / outlier / finalize kernels",
@@ -656,9 +657,11 @@ def c5_pipeline(eng, B, steps=3, distinct=32):
                          "frac": alg / solve_s / 1e9 / peak, "peak_kind": f"of {kind}",
                          "algorithmic_bytes_per_step": alg, "bytes_per_sweep": sweep_bytes,
                          "l2": f"{sweep_bytes / 1e6:.0f} MB per sweep vs 126 MB L2",
-                         "traffic": tr.get("dram_bytes_per_sweep"), "ms_solve": st["ms_solve"],
-                         "note": "whole solve stage (list building, 15 sweeps, reduces, step kernels, removeOutliers, finalisation) "
-                                 "timed by CUDA events; bytes = evaluations that actually ran x record bytes"}}
+                         "traffic": tr.get("dram_bytes_per_sweep"), "ms_optimize_pose": st["ms_optimize_pose"],
+                         "frac_including_list_building": alg / ((st["ms_lists"] + st["ms_optimize_pose"]) * 1e-3) / 1e9 / peak,
+                         "note": "optimizePose = everything after matched_pt / matched_ls exist: up to 15 sweeps with their step kernels, "
+                                 "the gate, removeOutliers, finalisation (CUDA events); bytes = evaluations that actually ran x record "
+                                 "bytes.  ms_lists (f2fTracking's list building + record packing) is reported separately"}}
 
 
 def run_c5_pipeline(args):

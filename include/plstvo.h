@@ -348,10 +348,12 @@ int64_t plstvo_launch_count(const PlContext* ctx);
  * launch.  n_tiles / n_pairs (optional) = CTAs per launch. */
 int     plstvo_batch_kernel_times(PlContext* ctx, PlDeviceBatch* db, int iters, double* ms_match,
                                   double* ms_solve, int32_t* n_tiles, int32_t* n_pairs);
-/* The same per stage of the matcher: ms[0] = operand expansion, ms[1] = distance + top-2 kernel (tcgen05 form) or the
- * integer K1 (PLSTVO_K1=popc: ms[0] = ms[2] = 0), ms[2] = index resolution, ms[3] = K2.  counts (optional) =
- * {1 if the tensor-core form ran, work items (or tiles) of the distance kernel, matching problems, pairs}. */
-int     plstvo_batch_stage_times(PlContext* ctx, PlDeviceBatch* db, int iters, double ms[4], int32_t counts[4]);
+/* The same per stage: ms[0] = operand expansion, ms[1] = distance + top-2 kernel (tcgen05 form) or the integer K1
+ * (PLSTVO_K1=popc: ms[0] = ms[2] = 0), ms[2] = index resolution, ms[3] = building matched_pt / matched_ls when that is a
+ * kernel of its own (the streamed solver; 0 when K2 does it internally), ms[4] = optimizePose (K2, or the streamed solver's
+ * sweeps + step / outlier / finalize kernels).  counts (optional) = {bit 0: tensor-core matcher, bit 1: streamed solver;
+ * work items (or tiles) of the distance kernel; matching problems; pairs}. */
+int     plstvo_batch_stage_times(PlContext* ctx, PlDeviceBatch* db, int iters, double ms[5], int32_t counts[4]);
 /* GN evaluation (optimizeFunctions, src/stereoFrameHandler.cpp:549-694) of the resident matched
  * lists at given poses, streamed from HBM: the roofline kernel of config C5.
  * DT: [B][16]; H: [B][36]; g: [B][6]; e: [B]. */

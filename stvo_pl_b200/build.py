@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libplstvo_b200.so")
 SOURCES = ["match.cu", "match_tc.cu", "match_grid.cu", "lift.cu", "solve.cu", "gn_stream.cu", "capi.cu"]
-HEADERS = ["common.cuh", "match_finalize.cuh", "match_tc.cuh", os.path.join("..", "..", "include", "plstvo.h")]
+HEADERS = ["common.cuh", "match_finalize.cuh", "match_tc.cuh", "gn_stream.cuh", os.path.join("..", "..", "include", "plstvo.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--use_fast_math=false"]
 

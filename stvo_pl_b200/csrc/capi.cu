@@ -186,6 +186,7 @@ int stream_bufs_prepare(PlContext* ctx, DevBuf& arena, int B, size_t slots_pt, s
     const size_t o_ctl = take((size_t)B * sizeof(StreamCtl)), o_par = take(stream_partial_doubles(B, slices) * 8);
     const size_t o_h = take((size_t)B * 36 * 8), o_g = take((size_t)B * 6 * 8), o_e = take((size_t)B * 8);
     const size_t o_fp = take(slots_pt + 16), o_fl = take(slots_ls + 16), o_mp = take((slots_pt + 16) * 2), o_ml = take((slots_ls + 16) * 2);
+    const size_t o_resp = take((slots_pt + 16) * 8), o_resl = take((slots_ls + 16) * 8), o_q = take((size_t)B * 2 * 4 + 16);
     CK(ctx, arena.ensure(off));
     uint8_t* b = arena.as<uint8_t>();
     sb->rec_pt = reinterpret_cast<float4*>(b + o_rp);
@@ -199,6 +200,9 @@ int stream_bufs_prepare(PlContext* ctx, DevBuf& arena, int B, size_t slots_pt, s
     sb->H = reinterpret_cast<double*>(b + o_h);
     sb->g = reinterpret_cast<double*>(b + o_g);
     sb->e = reinterpret_cast<double*>(b + o_e);
+    sb->res_pt = reinterpret_cast<double*>(b + o_resp);
+    sb->res_ls = reinterpret_cast<double*>(b + o_resl);
+    sb->queue = reinterpret_cast<int32_t*>(b + o_q);
     sb->flag_pt = b + o_fp;
     sb->flag_ls = b + o_fl;
     sb->midx_pt = reinterpret_cast<uint16_t*>(b + o_mp);
@@ -213,6 +217,7 @@ StreamBufs stream_bufs_at(const StreamBufs& sb, int p0) {
     StreamBufs r = sb;
     r.cnt_pt += p0; r.cnt_ls += p0; r.DT += (size_t)p0 * 16; r.active += p0; r.ctl += p0;
     r.partial += stream_partial_doubles(p0, sb.slices); r.H += (size_t)p0 * 36; r.g += (size_t)p0 * 6; r.e += p0;
+    r.queue += 2 * (size_t)p0;   // a chunk starts at a distinct pair: its two queue words are its own
     return r;
 }
 
@@ -393,7 +398,8 @@ int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfi
     ws.item_start[1][B] = (int32_t)ws.tc_items[1].size();
     ws.cap_pt = std::max(ws.cap_pt, 1);
     ws.cap_ls = std::max(ws.cap_ls, 1);
-    ws.sort_cap = pow2_ceil_host(std::max(std::max(ws.cap_pt, ws.cap_ls), (ws.max_n2 + 1) / 2));
+    // at least 32: the outlier statistics sort max(n, 32) padded entries (solve.cu: remove_outliers)
+    ws.sort_cap = pow2_ceil_host(std::max(32, std::max(std::max(ws.cap_pt, ws.cap_ls), (ws.max_n2 + 1) / 2)));
     // matched lists live in shared memory when they fit (C2: 152 KB), else in a global scratch slice (C5)
     static const bool no_smem = getenv("PLSTVO_K2_FEAT_GLOBAL") != nullptr;
     ws.feat_in_smem = !no_smem && k2_smem_bytes(ws.cap_pt, ws.cap_ls, ws.sort_cap, true) <= ctx->smem_optin;
@@ -570,7 +576,7 @@ int ws_launch_match(PlContext* ctx, Workspace& ws, int p0, int p1, cudaStream_t 
     return 0;
 }
 
-int ws_launch_solve(PlContext* ctx, Workspace& ws, int p0, int p1, bool have_level, cudaStream_t s) {
+int ws_launch_solve(PlContext* ctx, Workspace& ws, int p0, int p1, bool have_level, cudaStream_t s, cudaEvent_t lists_done = nullptr) {
     if (p1 <= p0) return 0;
     SolveParams prm{};
     prm.cam = ws.cam;
@@ -603,10 +609,11 @@ int ws_launch_solve(PlContext* ctx, Workspace& ws, int p0, int p1, bool have_lev
         prm.feat_scratch = ws.d_feat.as<double>() + (size_t)p0 * ws.feat_stride;
         prm.feat_in_smem = 0;
         int nl = 0;
-        CK(ctx, launch_stream_solve(prm, p1 - p0, stream_bufs_at(sb, p0), s, &nl));
+        CK(ctx, launch_stream_solve(prm, p1 - p0, stream_bufs_at(sb, p0), s, &nl, lists_done));
         ctx->launches += nl;
         return 0;
     }
+    if (lists_done) CK(ctx, cudaEventRecord(lists_done, s));   // fused kernel: the list building is inside K2
     CK(ctx, launch_track_solve(prm, p1 - p0, s));
     ctx->launches++;
     return 0;
@@ -1601,7 +1608,7 @@ int plstvo_optimize_pose(PlContext* ctx, const PlCamera* cam, const PlConfig* cf
     if (n && (!m->pt_P || !m->pt_pl_obs || !m->pt_sigma2)) return fail(ctx, PLSTVO_E_INVALID, "point arrays missing");
     if (l && (!m->ls_sP || !m->ls_eP || !m->ls_le_obs || !m->ls_spl || !m->ls_epl || !m->ls_sigma2))
         return fail(ctx, PLSTVO_E_INVALID, "line arrays missing");
-    const int sort_cap = pow2_ceil_host(std::max(cap_pt, cap_ls));
+    const int sort_cap = pow2_ceil_host(std::max(32, std::max(cap_pt, cap_ls)));
     bool in_smem = getenv("PLSTVO_K2_FEAT_GLOBAL") == nullptr && k2_smem_bytes(cap_pt, cap_ls, sort_cap, true) <= ctx->smem_optin;
     if (!in_smem && k2_smem_bytes(cap_pt, cap_ls, sort_cap, false) > ctx->smem_optin)
         return fail(ctx, PLSTVO_E_TOO_LARGE, "lists too long for the per-pair solver's shared memory");
@@ -1889,37 +1896,35 @@ int plstvo_batch_kernel_times(PlContext* ctx, PlDeviceBatch* db, int iters, doub
     return 0;
 }
 
-int plstvo_batch_stage_times(PlContext* ctx, PlDeviceBatch* db, int iters, double ms[4], int32_t counts[4]) {
+int plstvo_batch_stage_times(PlContext* ctx, PlDeviceBatch* db, int iters, double ms[5], int32_t counts[4]) {
     if (!ctx || !db || iters <= 0 || !ms) return PLSTVO_E_INVALID;
     LOCK(ctx);
     CK(ctx, cudaSetDevice(ctx->device));
     Workspace& ws = db->ws;
-    cudaEvent_t ev[5];
+    cudaEvent_t ev[6];
     for (auto& e : ev) CK(ctx, cudaEventCreate(&e));
-    double acc[4] = {0, 0, 0, 0};
+    double acc[5] = {0, 0, 0, 0, 0};
     for (int i = 0; i < iters; ++i) {
         CK(ctx, cudaEventRecord(ev[0], ctx->s_main));
-        if (!ws.use_tc) {   // the integer form is one kernel: report it in slot 1
-            CK(ctx, cudaEventRecord(ev[1], ctx->s_main));
-        }
+        if (!ws.use_tc) CK(ctx, cudaEventRecord(ev[1], ctx->s_main));   // the integer form is one kernel: reported in slot 1
         int rc = ws_launch_match(ctx, ws, 0, ws.B, ctx->s_main, ws.use_tc ? &ev[1] : nullptr);
         if (rc) return rc;
         if (!ws.use_tc) CK(ctx, cudaEventRecord(ev[2], ctx->s_main));
         CK(ctx, cudaEventRecord(ev[3], ctx->s_main));
-        rc = ws_launch_solve(ctx, ws, 0, ws.B, ws.have_level, ctx->s_main);
+        rc = ws_launch_solve(ctx, ws, 0, ws.B, ws.have_level, ctx->s_main, ev[4]);
         if (rc) return rc;
-        CK(ctx, cudaEventRecord(ev[4], ctx->s_main));
-        CK(ctx, cudaEventSynchronize(ev[4]));
-        for (int k = 0; k < 4; ++k) {
+        CK(ctx, cudaEventRecord(ev[5], ctx->s_main));
+        CK(ctx, cudaEventSynchronize(ev[5]));
+        for (int k = 0; k < 5; ++k) {
             float t = 0.f;
             CK(ctx, cudaEventElapsedTime(&t, ev[k], ev[k + 1]));
             acc[k] += t;
         }
     }
     for (auto& e : ev) cudaEventDestroy(e);
-    for (int k = 0; k < 4; ++k) ms[k] = acc[k] / iters;
+    for (int k = 0; k < 5; ++k) ms[k] = acc[k] / iters;
     if (counts) {
-        counts[0] = ws.use_tc ? 1 : 0;
+        counts[0] = (ws.use_tc ? 1 : 0) | (ws.use_stream ? 2 : 0);
         counts[1] = ws.use_tc ? (int32_t)(ws.tc_items[0].size() + ws.tc_items[1].size()) : (int32_t)ws.tiles.size();
         counts[2] = (int32_t)ws.problems.size();
         counts[3] = ws.B;

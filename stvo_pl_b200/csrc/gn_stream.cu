@@ -22,167 +22,11 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "gn_stream.cuh"
 
 namespace plstvo {
 
 namespace {
-
-constexpr int GS_CONSUMERS = 256;
-constexpr int GS_CWARPS = GS_CONSUMERS / 32;
-constexpr int GS_THREADS = GS_CONSUMERS + 32;          // + producer warp
-constexpr int GS_PT_TILE = 512;                        // points per stage (two per consumer thread)
-constexpr int GS_LS_TILE = 256;                        // lines per stage (one per consumer thread)
-constexpr int GS_STAGE_BYTES = 16384;
-constexpr int GS_STAGES = 6;
-constexpr int GS_NACC = ACC_N + 1;                     // 21 H + 6 g + e + count
-
-__device__ __forceinline__ float gs_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float gs_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float gs_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// J (+)= the 1x6 Jacobian row of :582-587 / :636-641 with the scale folded into the direction (dxs, dys)
-template <bool ADD>
-__device__ __forceinline__ void gs_jac(float X, float Y, float Z, float dxs, float dys, float* J) {
-    const float t = fmaf(X, dxs, Y * dys), zz = Z * Z;
-    const float j0 = dxs * Z, j1 = dys * Z, j3 = fmaf(Y, t, zz * dys), j4 = fmaf(X, t, zz * dxs);
-    const float j5 = Z * fmaf(X, dys, -(Y * dxs));
-    if (ADD) { J[0] += j0; J[1] += j1; J[2] -= t; J[3] -= j3; J[4] += j4; J[5] += j5; }
-    else     { J[0] = j0;  J[1] = j1;  J[2] = -t; J[3] = -j3; J[4] = j4;  J[5] = j5; }
-}
-
-// Per-thread accumulators: 21 unique entries of H = sum w J J^T (row-major upper triangle), 6 of g = sum w r J, e, count.
-struct GsAccScalar {
-    float a[GS_NACC];
-    __device__ __forceinline__ void clear() {
-#pragma unroll
-        for (int i = 0; i < GS_NACC; i++) a[i] = 0.f;
-    }
-    __device__ __forceinline__ void add(const float* J, float r, float w, float one) {
-        int k = 0;
-#pragma unroll
-        for (int i = 0; i < 6; i++) {
-            const float Jw = J[i] * w;
-#pragma unroll
-            for (int j = i; j < 6; j++) a[k] = fmaf(Jw, J[j], a[k]), k++;
-            a[21 + i] = fmaf(Jw, r, a[21 + i]);
-        }
-        a[27] = fmaf(r * w, r, a[27]);
-        a[28] += one;
-    }
-    __device__ __forceinline__ void unpack(float* out) const {
-#pragma unroll
-        for (int i = 0; i < GS_NACC; i++) out[i] = a[i];
-    }
-};
-
-// The same sums with Blackwell's packed fp32 pipe (fma.rn.f32x2 -> FFMA2, one operand broadcast): 12 FFMA2 + 3 FMUL2 + 5
-// scalar ops per feature instead of 36.  Pairs: (00,01)(02,03)(04,05) (12,13)(14,15) (22,23)(24,25) (34,35) (44,45)
-// (g0,g1)(g2,g3)(g4,g5); scalars: 11, 33, 55, e, count.
-typedef unsigned long long gs_u64;
-__device__ __forceinline__ gs_u64 gs_pk(float lo, float hi) { gs_u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void gs_upk(gs_u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ gs_u64 gs_fma2(gs_u64 a, gs_u64 b, gs_u64 c) { gs_u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-__device__ __forceinline__ gs_u64 gs_mul2(gs_u64 a, gs_u64 b) { gs_u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-struct GsAccPacked {
-    gs_u64 p[12];
-    float s[5];
-    __device__ __forceinline__ void clear() {
-#pragma unroll
-        for (int i = 0; i < 12; i++) p[i] = 0ull;
-#pragma unroll
-        for (int i = 0; i < 5; i++) s[i] = 0.f;
-    }
-    __device__ __forceinline__ void add(const float* J, float r, float w, float one) {
-        const gs_u64 J01 = gs_pk(J[0], J[1]), J23 = gs_pk(J[2], J[3]), J45 = gs_pk(J[4], J[5]), ww = gs_pk(w, w), rr = gs_pk(r, r);
-        const gs_u64 W01 = gs_mul2(J01, ww), W23 = gs_mul2(J23, ww), W45 = gs_mul2(J45, ww);
-        float w0, w1, w2, w3, w4, w5;
-        gs_upk(W01, w0, w1); gs_upk(W23, w2, w3); gs_upk(W45, w4, w5);
-        const gs_u64 b0 = gs_pk(w0, w0), b1 = gs_pk(w1, w1), b2 = gs_pk(w2, w2), b3 = gs_pk(w3, w3), b4 = gs_pk(w4, w4);
-        p[0] = gs_fma2(b0, J01, p[0]); p[1] = gs_fma2(b0, J23, p[1]); p[2] = gs_fma2(b0, J45, p[2]);
-        p[3] = gs_fma2(b1, J23, p[3]); p[4] = gs_fma2(b1, J45, p[4]);
-        p[5] = gs_fma2(b2, J23, p[5]); p[6] = gs_fma2(b2, J45, p[6]);
-        p[7] = gs_fma2(b3, J45, p[7]);
-        p[8] = gs_fma2(b4, J45, p[8]);
-        p[9] = gs_fma2(W01, rr, p[9]); p[10] = gs_fma2(W23, rr, p[10]); p[11] = gs_fma2(W45, rr, p[11]);
-        s[0] = fmaf(w1, J[1], s[0]); s[1] = fmaf(w3, J[3], s[1]); s[2] = fmaf(w5, J[5], s[2]);
-        s[3] = fmaf(r * w, r, s[3]);
-        s[4] += one;
-    }
-    __device__ __forceinline__ void unpack(float* o) const {
-        gs_upk(p[0], o[0], o[1]); gs_upk(p[1], o[2], o[3]); gs_upk(p[2], o[4], o[5]);
-        o[6] = s[0];
-        gs_upk(p[3], o[7], o[8]); gs_upk(p[4], o[9], o[10]);
-        gs_upk(p[5], o[11], o[12]); gs_upk(p[6], o[13], o[14]);
-        o[15] = s[1];
-        gs_upk(p[7], o[16], o[17]);
-        gs_upk(p[8], o[18], o[19]);
-        o[20] = s[2];
-        gs_upk(p[9], o[21], o[22]); gs_upk(p[10], o[23], o[24]); gs_upk(p[11], o[25], o[26]);
-        o[27] = s[3];
-        o[28] = s[4];
-    }
-};
-
-__device__ __forceinline__ float gs_overlap_l(float ls, float le) {   // :601-610 on the two parameters
-    const float lo = fminf(ls, le), hi = fmaxf(ls, le);
-    float ov = fminf(hi, 1.f) - fmaxf(lo, 0.f);                       // covered part of [0, 1]
-    ov = (hi < 0.f || lo > 1.f) ? 0.f : ov;
-    return ov;
-}
-
-struct GsPose {
-    float r[12];
-    float fx, fy, cx, cy, h, inv_h, fx_h;
-};
-
-// point block (:563-606); `use` = a live record flagged inlier
-template <class Acc>
-__device__ __forceinline__ void gs_point(const GsPose& P, const float4 a, const float4 b, bool use, Acc& acc) {
-    const float X = fmaf(P.r[0], a.x, fmaf(P.r[1], a.y, fmaf(P.r[2], a.z, P.r[3])));
-    const float Y = fmaf(P.r[4], a.x, fmaf(P.r[5], a.y, fmaf(P.r[6], a.z, P.r[7])));
-    const float Z = fmaf(P.r[8], a.x, fmaf(P.r[9], a.y, fmaf(P.r[10], a.z, P.r[11])));
-    const float iz = use ? gs_rcp(Z) : 0.f;                // a dead record contributes exact zeros, never a NaN
-    const float dx = fmaf(P.fx * X, iz, P.cx - b.x), dy = fmaf(P.fy * Y, iz, P.cy - b.y);
-    const float ss = fmaf(dx, dx, dy * dy);
-    const float n = gs_sqrt(ss), inv = fminf(P.inv_h, gs_rsqrt(ss));          // 1 / max(homogTh, n)
-    const float fg = (Z * Z > P.h) ? P.fx * iz * iz : P.fx_h;                 // fx / max(homogTh, Z^2)  (:577)
-    const float sc = fg * inv;
-    float J[6];
-    gs_jac<false>(X, Y, Z, sc * dx, sc * dy, J);
-    const float r = n * a.w;
-    const float w = use ? gs_rcp(fmaf(r, r, 1.f)) : 0.f;
-    acc.add(J, r, w, use ? 1.f : 0.f);
-}
-
-// line block (:610-684)
-template <class Acc>
-__device__ __forceinline__ void gs_line(const GsPose& P, const float4 a, const float4 b, const float4 c, const float4 d,
-                                        bool use, Acc& acc) {
-    const float sX = fmaf(P.r[0], a.x, fmaf(P.r[1], a.y, fmaf(P.r[2], a.z, P.r[3])));
-    const float sY = fmaf(P.r[4], a.x, fmaf(P.r[5], a.y, fmaf(P.r[6], a.z, P.r[7])));
-    const float sZ = fmaf(P.r[8], a.x, fmaf(P.r[9], a.y, fmaf(P.r[10], a.z, P.r[11])));
-    const float eX = fmaf(P.r[0], b.x, fmaf(P.r[1], b.y, fmaf(P.r[2], b.z, P.r[3])));
-    const float eY = fmaf(P.r[4], b.x, fmaf(P.r[5], b.y, fmaf(P.r[6], b.z, P.r[7])));
-    const float eZ = fmaf(P.r[8], b.x, fmaf(P.r[9], b.y, fmaf(P.r[10], b.z, P.r[11])));
-    const float isz = use ? gs_rcp(sZ) : 0.f, iez = use ? gs_rcp(eZ) : 0.f;
-    const float spu = fmaf(P.fx * sX, isz, P.cx), spv = fmaf(P.fy * sY, isz, P.cy);
-    const float epu = fmaf(P.fx * eX, iez, P.cx), epv = fmaf(P.fy * eY, iez, P.cy);
-    const float ds = fmaf(c.x, spu, fmaf(c.y, spv, c.z)), de = fmaf(c.x, epu, fmaf(c.y, epv, c.z));
-    const float ss = fmaf(ds, ds, de * de);
-    const float n = gs_sqrt(ss), iden = fminf(P.inv_h, gs_rsqrt(ss));
-    const float ks = ((sZ * sZ > P.h) ? P.fx * isz * isz : P.fx_h) * (ds * iden);
-    const float ke = ((eZ * eZ > P.h) ? P.fx * iez * iez : P.fx_h) * (de * iden);
-    float J[6];
-    gs_jac<false>(sX, sY, sZ, ks * c.x, ks * c.y, J);
-    gs_jac<true>(eX, eY, eZ, ke * c.x, ke * c.y, J);
-    const float r = n * a.w;
-    float w = gs_rcp(fmaf(r, r, 1.f));
-    w *= gs_overlap_l(fmaf(d.x, spu, fmaf(d.y, spv, d.z)), fmaf(d.x, epu, fmaf(d.y, epv, d.z)));   // :664-670
-    acc.add(J, r, use ? w : 0.f, use ? 1.f : 0.f);
-}
 
 __device__ __forceinline__ int gs_find_problem(const int32_t* __restrict__ off, int B, int i) {   // off[p] <= i < off[p+1]
     int lo = 0, hi = B - 1;
@@ -422,7 +266,7 @@ cudaError_t launch_gn_eval_stream(const PlCamera& cam, const PlConfig& cfg, cons
         gn_eval_stream_kernel<GsAccScalar><<<grid, GS_THREADS, smem, stream>>>(cam, (float)cfg.homog_th, L, pt, ls, DT, partial, bpp,
                                                                                n_items);
     err = cudaGetLastError();
-    if (err != cudaSuccess) return err;
+    if (err != cudaSuccess || !H) return err;   // H == nullptr: the caller folds the partials itself
     gn_eval_reduce_kernel<<<B, 32, 0, stream>>>(partial, bpp * GS_CWARPS, H, g, e, active);
     return cudaGetLastError();
 }

@@ -18,6 +18,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "gn_stream.cuh"
 #include "match_finalize.cuh"
 
 namespace plstvo {
@@ -757,6 +758,83 @@ __device__ __forceinline__ int pow2_ceil(int n) {
     return m;
 }
 
+// ---- k-th smallest of val(0 .. m) by an 8 x 8-bit radix select (block-wide, exact, order-independent) -----------------------
+// Replaces full sorts where only one order statistic is wanted (the median and the MAD of src/auxiliar.cpp:387-460).
+// `hist`: 260 ints of shared scratch.  Stops refining as soon as a single value remains under the decided prefix.  Doubles are mapped to keys whose unsigned order is the numeric order.
+__device__ __forceinline__ unsigned long long select_key(double x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double select_unkey(unsigned long long k) {
+    return __longlong_as_double((long long)((k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k));
+}
+template <class Val>
+__device__ double block_select_kth(int* hist, int m, int k, Val val) {
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31;
+    unsigned long long prefix = 0;
+    int kk = k;
+    for (int pass = 7; pass >= 0; --pass) {
+        for (int b = tid; b < 256; b += nth) hist[b] = 0;
+        __syncthreads();
+        const int sh = 8 * pass;
+        for (int i0 = 0; i0 < m; i0 += nth) {   // uniform trip count: the aggregation below is warp-collective
+            const int i = i0 + tid;
+            bool take = false;
+            unsigned bin = 0;
+            if (i < m) {
+                const unsigned long long key = select_key(val(i));
+                take = (pass == 7) || ((key >> (sh + 8)) == (prefix >> (sh + 8)));
+                bin = (unsigned)(key >> sh) & 255u;
+            }
+            const unsigned act = __ballot_sync(FULL_MASK, take);
+            if (take) {   // one shared-memory atomic per distinct bin and warp (the top bytes of residuals are all alike)
+                const unsigned peers = __match_any_sync(act, bin);
+                if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&hist[bin], __popc(peers));
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {   // the bin that holds rank kk: 8 bins per lane, warp scan, then a short walk
+            int c[8], s = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) { c[j] = hist[8 * lane + j]; s += c[j]; }
+            int inc = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULL_MASK, inc, o);
+                if (lane >= o) inc += t;
+            }
+            const unsigned over = __ballot_sync(FULL_MASK, inc > kk);
+            const int fl = over ? (__ffs(over) - 1) : 31;
+            if (lane == fl) {
+                int before = inc - s, b = 0;
+                while (b < 7 && before + c[b] <= kk) { before += c[b]; b++; }
+                hist[256] = 8 * lane + b;
+                hist[257] = kk - before;
+                hist[258] = c[b];
+            }
+        }
+        __syncthreads();
+        prefix |= (unsigned long long)(unsigned)hist[256] << sh;
+        kk = hist[257];
+        const int in_bin = hist[258];
+        __syncthreads();
+        if (in_bin == 1 && pass > 0) {   // one value left under this prefix: fetch it instead of refining byte by byte
+            for (int i = tid; i < m; i += nth) {
+                const unsigned long long key = select_key(val(i));
+                if ((key >> sh) == (prefix >> sh)) {
+                    hist[256] = (int)(unsigned)(key & 0xFFFFFFFFull);
+                    hist[257] = (int)(unsigned)(key >> 32);
+                }
+            }
+            __syncthreads();
+            prefix = ((unsigned long long)(unsigned)hist[257] << 32) | (unsigned long long)(unsigned)hist[256];
+            __syncthreads();
+            break;
+        }
+    }
+    return select_unkey(prefix);
+}
+
 // median / MAD of the n finite values in `buf` SORTED ascending (+inf padding behind them):
 // median = sorted[n/2]; stdv = 1.4826 * sorted(|x - median| rounded to float)[n/2]  (src/auxiliar.cpp:396-403).
 // The deviations of a sorted array form a V (non-increasing up to the median, non-decreasing after it): their n/2-th
@@ -990,6 +1068,58 @@ __device__ void gauss_newton(const Feat& f, State& st, double* sortbuf, const Ca
     __syncthreads();
 }
 
+// removeOutliers (:988-1067) for LONG lists (the streamed solver: 8000 + 2000 entries): res_pt(i) / res_ls(i) = |e| sqrt(sigma2)
+// of matched feature i at the stage-1 pose, each read once into shared memory; median and MAD by radix selection (a full
+// bitonic sort of 8192 doubles through shared memory costs 10x more).  Same order statistics, same flags as remove_outliers.
+template <class ResP, class ResL>
+__device__ void remove_outliers_select(const Feat& f, State& st, double* sortbuf, const PlConfig& cfg, ResP res_pt, ResL res_ls) {
+    const int tid = threadIdx.x, nth = blockDim.x;
+    for (int type = 0; type < 2; type++) {
+        const int n = type ? f.nl : f.np;
+        if (type == 0 ? !cfg.has_points : !cfg.has_lines) continue;
+        if (n == 0) continue;   // vector_mean_stdv_mad of an empty vector: nothing to flag
+        // residuals of ALL matched features (inliers or not), each formed once and kept in shared memory
+        for (int i = tid; i < n; i += nth) sortbuf[i] = (type == 0) ? res_pt(i) : res_ls(i);
+        __syncthreads();
+        auto residual = [&](int i) -> double { return sortbuf[i]; };
+        const long long t_s = clock64();
+        // median = sorted[n / 2]; stdv = 1.4826 * sorted(|x - median| rounded to float)[n / 2]  (src/auxiliar.cpp:396-403):
+        // two order statistics, no sort
+        int* hist = reinterpret_cast<int*>(&st.red[0][0]);
+        const double median = block_select_kth(hist, n, n / 2, residual);
+        const double mad = block_select_kth(hist, n, n / 2, [&](int i) -> double { return (double)fabsf((float)(sortbuf[i] - median)); });
+        const double stdv = 1.4826 * mad;
+        if (tid == 0) st.tc[7] += clock64() - t_s;
+        // mean of the residuals below 2 stdv if there are enough of them, else plain mean (auxiliar.cpp:406-427)
+        double s[3] = {0.0, 0.0, 0.0};
+        for (int i = tid; i < n; i += nth) {
+            const double r = residual(i);
+            s[2] += r;
+            if (r < 2.0 * stdv) {
+                s[0] += r;
+                s[1] += 1.0;
+            }
+        }
+        block_sum<3>(st, s);
+        const int k = (int)s[1];
+        const double mean = (k >= (int)(0.2 * (double)n)) ? s[0] / (double)k : s[2] / (double)n;
+        const double th = cfg.inlier_k * stdv;
+        double removed[1] = {0.0};
+        uint8_t* inl = type ? f.inl_l : f.inl_p;
+        for (int i = tid; i < n; i += nth)
+            if (inl[i] && fabs(residual(i) - mean) > th) {
+                inl[i] = 0;
+                removed[0] += 1.0;
+            }
+        block_sum<1>(st, removed);
+        if (tid == 0) {
+            if (type == 0) st.n_inl_p -= (int)removed[0];
+            else st.n_inl_l -= (int)removed[0];
+        }
+        __syncthreads();
+    }
+}
+
 // removeOutliers (:988-1067) at pose DT (shared)
 __device__ void remove_outliers(const Feat& f, State& st, double* sortbuf, const double* DT, const Cam& cam,
                                 const PlConfig& cfg) {
@@ -1063,6 +1193,24 @@ __device__ int block_exclusive_scan(State& st, int v, int* total) {
     *total = tot;
     __syncthreads();
     return base + inc - v;
+}
+
+// rank of this thread's flag among the block's set flags (ascending thread index), and their number
+__device__ __forceinline__ int block_rank(State& st, bool flag, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned bal = __ballot_sync(FULL_MASK, flag);
+    __syncthreads();                       // scan[] may still be read from the previous round
+    if (lane == 0) st.scan[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < K2_WARPS; w++) {
+        const int c = st.scan[w];
+        before += (w < warp) ? c : 0;
+        tot += c;
+    }
+    *total = tot;
+    return before + __popc(bal & ((1u << lane) - 1u));
 }
 
 // Pose finalisation (src/stereoFrameHandler.cpp:372-391) by ONE warp: gate, curr->DT = exp(log(inverse(DT))), Tfw chain,
@@ -1172,56 +1320,56 @@ __device__ void build_matched_lists(const SolveParams& prm, int pair, State& st,
         const int a0 = P.pt_off[pair], b0 = C.pt_off[pair];
         n1p = P.pt_off[pair + 1] - a0;
         out_p0 = (size_t)a0;
-        {
-            const int per = (n1p + nth - 1) / nth, lo = min(n1p, tid * per), hi = min(n1p, lo + per);
-            int cnt = 0;
-            for (int i = lo; i < hi; i++) cnt += (pp.m12[i] >= 0);
-            int total;
-            int k = block_exclusive_scan(st, cnt, &total);
-            for (int i = lo; i < hi; i++) {
-                const int i2 = pp.m12[i];
-                if (i2 < 0) continue;
-                const double* p3 = P.pt_P + 3 * (size_t)(a0 + i);
-                f.Px[k] = p3[0]; f.Py[k] = p3[1]; f.Pz[k] = p3[2];
-                const double* o2 = C.pt_pl + 2 * (size_t)(b0 + i2);    // pl_obs = curr pl (:148)
-                f.pu[k] = o2[0]; f.pv[k] = o2[1];
-                f.pss[k] = sqrt(P.pt_sigma2[a0 + i]);                  // PointFeature::safeCopy keeps sigma2
-                f.inl_p[k] = 1;
-                midx_p[k] = (uint16_t)i;
-                k++;
+        {   // chunks of blockDim consecutive prev features: coalesced reads, output position = matches before it
+            int base = 0;
+            for (int i0 = 0; i0 < n1p; i0 += nth) {
+                const int i = i0 + tid;
+                const int i2 = (i < n1p) ? pp.m12[i] : -1;
+                int tot;
+                const int k = base + block_rank(st, i2 >= 0, &tot);
+                if (i2 >= 0) {
+                    const double* p3 = P.pt_P + 3 * (size_t)(a0 + i);
+                    f.Px[k] = p3[0]; f.Py[k] = p3[1]; f.Pz[k] = p3[2];
+                    const double* o2 = C.pt_pl + 2 * (size_t)(b0 + i2);    // pl_obs = curr pl (:148)
+                    f.pu[k] = o2[0]; f.pv[k] = o2[1];
+                    f.pss[k] = sqrt(P.pt_sigma2[a0 + i]);                  // PointFeature::safeCopy keeps sigma2
+                    f.inl_p[k] = 1;
+                    midx_p[k] = (uint16_t)i;
+                }
+                base += tot;
             }
-            f.np = total;
+            f.np = base;
         }
         const int c0 = P.ls_off[pair], d0 = C.ls_off[pair];
         n1l = P.ls_off[pair + 1] - c0;
         out_l0 = (size_t)c0;
         {
-            const int per = (n1l + nth - 1) / nth, lo = min(n1l, tid * per), hi = min(n1l, lo + per);
-            int cnt = 0;
-            for (int i = lo; i < hi; i++) cnt += (pl.m12[i] >= 0);
-            int total;
-            int k = block_exclusive_scan(st, cnt, &total);
-            for (int i = lo; i < hi; i++) {
-                const int i2 = pl.m12[i];
-                if (i2 < 0) continue;
-                const size_t a = (size_t)(c0 + i);
-                f.sX[k] = P.ls_sP[3 * a]; f.sY[k] = P.ls_sP[3 * a + 1]; f.sZ[k] = P.ls_sP[3 * a + 2];
-                f.eX[k] = P.ls_eP[3 * a]; f.eY[k] = P.ls_eP[3 * a + 1]; f.eZ[k] = P.ls_eP[3 * a + 2];
-                const double* le = C.ls_le + 3 * (size_t)(d0 + i2);    // le_obs = curr le (:175)
-                f.l0[k] = le[0]; f.l1[k] = le[1]; f.l2[k] = le[2];
-                overlap_coeffs(P.ls_spl[2 * a], P.ls_spl[2 * a + 1], P.ls_epl[2 * a], P.ls_epl[2 * a + 1], f.oa[k],
-                               f.ob[k], f.oc[k]);
-                // LineFeature::safeCopy -> ctor re-applies the level rule (src/stereoFeatures.cpp:117-135):
-                // sigma2' = 1 / (sigma2 * lsdScale^level)^2
-                double s2 = P.ls_sigma2[a];
-                const int level = P.ls_level ? P.ls_level[a] : 0;
-                for (int l = 0; l < level; l++) s2 *= cfg.lsd_scale;
-                f.lss[k] = sqrt(1.0 / (s2 * s2));
-                f.inl_l[k] = 1;
-                midx_l[k] = (uint16_t)i;
-                k++;
+            int base = 0;
+            for (int i0 = 0; i0 < n1l; i0 += nth) {
+                const int i = i0 + tid;
+                const int i2 = (i < n1l) ? pl.m12[i] : -1;
+                int tot;
+                const int k = base + block_rank(st, i2 >= 0, &tot);
+                if (i2 >= 0) {
+                    const size_t a = (size_t)(c0 + i);
+                    f.sX[k] = P.ls_sP[3 * a]; f.sY[k] = P.ls_sP[3 * a + 1]; f.sZ[k] = P.ls_sP[3 * a + 2];
+                    f.eX[k] = P.ls_eP[3 * a]; f.eY[k] = P.ls_eP[3 * a + 1]; f.eZ[k] = P.ls_eP[3 * a + 2];
+                    const double* le = C.ls_le + 3 * (size_t)(d0 + i2);    // le_obs = curr le (:175)
+                    f.l0[k] = le[0]; f.l1[k] = le[1]; f.l2[k] = le[2];
+                    overlap_coeffs(P.ls_spl[2 * a], P.ls_spl[2 * a + 1], P.ls_epl[2 * a], P.ls_epl[2 * a + 1], f.oa[k],
+                                   f.ob[k], f.oc[k]);
+                    // LineFeature::safeCopy -> ctor re-applies the level rule (src/stereoFeatures.cpp:117-135):
+                    // sigma2' = 1 / (sigma2 * lsdScale^level)^2
+                    double s2 = P.ls_sigma2[a];
+                    const int level = P.ls_level ? P.ls_level[a] : 0;
+                    for (int l = 0; l < level; l++) s2 *= cfg.lsd_scale;
+                    f.lss[k] = sqrt(1.0 / (s2 * s2));
+                    f.inl_l[k] = 1;
+                    midx_l[k] = (uint16_t)i;
+                }
+                base += tot;
             }
-            f.nl = total;
+            f.nl = base;
         }
         if (tid == 0) {
             st.n_inl_p = f.np;   // f2fTracking: n_inliers_* = list sizes (:126-128)
@@ -1554,17 +1702,32 @@ __global__ void __launch_bounds__(K2_THREADS, 1) stream_prepare_kernel(const Sol
     }
 }
 
-// ---- S2: one iteration of gaussNewtonOptimization's loop body (:404-427) per active problem, one warp each ----
-__global__ void __launch_bounds__(128) stream_step_kernel(const StreamBufs sb, PlConfig cfg, int n, int max_iters) {
+// ---- S2: fold the sweep's fp64 partials (fixed order) and run one iteration of gaussNewtonOptimization's loop body
+//          (:404-427) per active problem, one warp each ----
+__global__ void __launch_bounds__(128) stream_step_kernel(const StreamBufs sb, PlConfig cfg, int n, int max_iters, int n_part) {
     __shared__ double sH[4][36], sg[4][8], sDT[4][16], sC[4][36];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, p = blockIdx.x * 4 + w;
     if (p >= n || !sb.active[p]) return;
     StreamCtl& c = sb.ctl[p];
-    for (int i = lane; i < 36; i += 32) sH[w][i] = sb.H[(size_t)p * 36 + i];
-    if (lane < 6) sg[w][lane] = sb.g[(size_t)p * 6 + lane];
+    // lane L sums accumulator L over the problem's partial records in index order: 21 H (upper triangle), 6 g, e, count
+    double sum = 0.0;
+    if (lane <= ACC_N) {
+        const double* part = sb.partial + (size_t)p * n_part * (ACC_N + 1) + lane;
+        for (int b = 0; b < n_part; b++) sum += part[(size_t)b * (ACC_N + 1)];
+    }
+    const double cnt = __shfl_sync(FULL_MASK, sum, 28), esum = __shfl_sync(FULL_MASK, sum, 27);
+    if (lane < 21) {
+        int i = 0, k = lane;
+        while (k >= 6 - i) { k -= 6 - i; i++; }
+        const int j = i + k;
+        sH[w][i * 6 + j] = sum;
+        sH[w][j * 6 + i] = sum;
+    } else if (lane < 27) {
+        sg[w][lane - 21] = sum;
+    }
     if (lane < 16) sDT[w][lane] = sb.DT[(size_t)p * 16 + lane];
     __syncwarp();
-    const double err = sb.e[p], err_prev = c.err_prev;
+    const double err = esum / cnt, err_prev = c.err_prev;             // e /= (N_l + N_p)  (:692)
     const int it = c.iters;
     bool stop = false, fail_first = false;
     double new_prev = err_prev;
@@ -1602,6 +1765,183 @@ __global__ void __launch_bounds__(128) stream_step_kernel(const StreamBufs sb, P
     }
 }
 
+// ---- S2': the whole Gauss-Newton call of one problem inside one persistent CTA, its records streamed from HBM every iteration ----
+// gaussNewtonOptimization (:394-431) for the streamed solver.  CTAs (2 per SM) take problems from an atomic queue; per
+// iteration the producer lane streams the problem's 16 KB record tiles through a TMA ring (cp.async.bulk + mbarriers), eight
+// consumer warps evaluate optimizeFunctions on them (fp32 per feature, folded to fp64 every few tiles, fixed order), warp 0 sums
+// the warps, runs the stop tests / 6x6 solve / SE(3) update in double and publishes the new pose.  No grid-wide step between
+// iterations: while one CTA of an SM solves its 6x6 system the other keeps the memory pipe busy, so the launch as a whole
+// streams at HBM speed.  One launch replaces max_iters x (sweep + reduce + step).
+constexpr int GL_FOLD = 4;   // tiles between fp32 -> fp64 folds of a thread's accumulators
+__global__ void __launch_bounds__(GS_THREADS, 2)
+gn_loop_stream_kernel(const PlCamera cam, const PlConfig cfg, const int32_t* __restrict__ pt_off, const int32_t* __restrict__ ls_off,
+                      const StreamBufs sb, int n, int max_iters, int* __restrict__ queue) {
+    extern __shared__ __align__(128) uint8_t ring[];
+    __shared__ __align__(8) uint64_t full[GS_STAGES], empty[GS_STAGES];
+    __shared__ double red[GS_CWARPS][32], sH[36], sg[8], sDT[16], sC[36];
+    __shared__ float sPose[12];
+    __shared__ int s_prob, s_stop;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int st = 0; st < GS_STAGES; ++st) {
+            mbar_init(&full[st], 1);
+            mbar_init(&empty[st], GS_CWARPS);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    GsPose P;
+    P.fx = (float)cam.fx; P.fy = (float)cam.fy; P.cx = (float)cam.cx; P.cy = (float)cam.cy;
+    P.h = (float)cfg.homog_th; P.inv_h = 1.f / P.h; P.fx_h = P.fx / P.h;
+    uint32_t k = 0;   // tiles through the ring so far: producer and consumers count the same sequence
+    for (;;) {
+        if (tid == 0) s_prob = atomicAdd(queue, 1);
+        __syncthreads();
+        const int p = s_prob;
+        if (p >= n) break;
+        const bool live = sb.active[p] != 0;
+        __syncthreads();                       // s_prob may be rewritten only after everyone has read it
+        if (!live) continue;
+        StreamCtl& c = sb.ctl[p];
+        const int np = sb.cnt_pt[p], nl = sb.cnt_ls[p], p0 = pt_off[p], l0 = ls_off[p];
+        const int ptiles = (np + GS_PT_TILE - 1) / GS_PT_TILE, n_tiles = ptiles + (nl + GS_LS_TILE - 1) / GS_LS_TILE;
+        if (tid < 16) sDT[tid] = sb.DT[(size_t)p * 16 + tid];
+        if (tid < 12) sPose[tid] = (float)sb.DT[(size_t)p * 16 + tid];
+        double err_prev = c.err_prev, err = 0.0;   // warp 0's copies are the authoritative ones
+        int it = 0;
+        bool fail_first = false;
+        __syncthreads();
+        for (;; ++it) {
+            if (warp == GS_CWARPS) {           // ---- producer ----
+                if (lane == 0) {
+                    for (int t = 0; t < n_tiles; ++t, ++k) {
+                        const uint32_t st = k % GS_STAGES;
+                        if (k >= GS_STAGES) mbar_wait(&empty[st], ((k / GS_STAGES) - 1) & 1);
+                        const void* src;
+                        uint32_t bytes;
+                        if (t < ptiles) {
+                            src = sb.rec_pt + 2 * (size_t)(p0 + t * GS_PT_TILE);
+                            bytes = (uint32_t)min(GS_PT_TILE, np - t * GS_PT_TILE) * 32u;
+                        } else {
+                            const int f0 = (t - ptiles) * GS_LS_TILE;
+                            src = sb.rec_ls + 4 * (size_t)(l0 + f0);
+                            bytes = (uint32_t)min(GS_LS_TILE, nl - f0) * 64u;
+                        }
+                        mbar_arrive_expect_tx(&full[st], bytes);
+                        bulk_g2s(ring + (size_t)st * GS_STAGE_BYTES, src, bytes, &full[st]);
+                    }
+                }
+                k = __shfl_sync(FULL_MASK, k, 0);
+            } else {                           // ---- consumers ----
+#pragma unroll
+                for (int i = 0; i < 12; i++) P.r[i] = sPose[i];
+                GsAccPacked acc;
+                acc.clear();
+                double run = 0.0;              // lane L: this warp's fp64 total of accumulator L so far
+                for (int t = 0; t < n_tiles; ++t, ++k) {
+                    const uint32_t st = k % GS_STAGES;
+                    mbar_wait(&full[st], (k / GS_STAGES) & 1);
+                    const float4* sr = reinterpret_cast<const float4*>(ring + (size_t)st * GS_STAGE_BYTES);
+                    if (t < ptiles) {
+                        const int cnt = min(GS_PT_TILE, np - t * GS_PT_TILE);
+#pragma unroll
+                        for (int h = 0; h < GS_PT_TILE / GS_CONSUMERS; ++h) {
+                            const int idx = tid + h * GS_CONSUMERS;
+                            const bool lv = idx < cnt;
+                            const int ii = lv ? idx : 0;
+                            const float4 a = sr[ii], b = sr[cnt + ii];
+                            gs_point(P, a, b, lv && b.z != 0.f, acc);
+                        }
+                    } else {
+                        const int cnt = min(GS_LS_TILE, nl - (t - ptiles) * GS_LS_TILE);
+                        const bool lv = tid < cnt;
+                        const int ii = lv ? tid : 0;
+                        const float4 a = sr[ii], b = sr[cnt + ii], cc = sr[2 * cnt + ii], d = sr[3 * cnt + ii];
+                        gs_line(P, a, b, cc, d, lv && b.w != 0.f, acc);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[st]);
+                    if ((t % GL_FOLD) == GL_FOLD - 1 || t == n_tiles - 1) {   // fp32 partials -> fp64, fixed order
+                        float v[32];
+                        acc.unpack(v);
+#pragma unroll
+                        for (int i = GS_NACC; i < 32; i++) v[i] = 0.f;
+#pragma unroll
+                        for (int off = 16; off >= 1; off >>= 1) {
+                            const bool up = (lane & off) != 0;
+#pragma unroll
+                            for (int i = 0; i < off; i++) {
+                                const float mine = up ? v[i + off] : v[i];
+                                const float send = up ? v[i] : v[i + off];
+                                v[i] = mine + __shfl_xor_sync(FULL_MASK, send, off);
+                            }
+                        }
+                        run += (double)v[0];
+                        acc.clear();
+                    }
+                }
+                red[warp][lane] = run;
+            }
+            __syncthreads();
+            if (warp == 0) {                   // ---- the loop body of :404-427 on the summed normal equations ----
+                double sum = 0.0;
+#pragma unroll
+                for (int w = 0; w < GS_CWARPS; w++) sum += red[w][lane];
+                const double cnt = __shfl_sync(FULL_MASK, sum, 28), esum = __shfl_sync(FULL_MASK, sum, 27);
+                if (lane < 21) {
+                    int i = 0, q = lane;
+                    while (q >= 6 - i) { q -= 6 - i; i++; }
+                    const int j = i + q;
+                    sH[i * 6 + j] = sum;
+                    sH[j * 6 + i] = sum;
+                } else if (lane < 27) {
+                    sg[lane - 21] = sum;
+                }
+                __syncwarp();
+                err = esum / cnt;              // e /= (N_l + N_p)  (:692)
+                bool stop = false;
+                if (err > err_prev) {                                             // :405-410
+                    stop = true;
+                    fail_first = (it == 0);
+                } else if ((err < cfg.min_error) || fabs(err - err_prev) < cfg.min_error_change) {   // :412-415
+                    stop = true;
+                } else {
+                    double inc[6], lad;
+                    if (!warp_chol6_solve(sH, sg, inc)) warp_qr6_solve<false>(sH, sg, inc, lad);   // :417-418
+                    apply_increment(sDT, inc, lane);                              // :419
+                    if (lane < 12) sPose[lane] = (float)sDT[lane];
+                    if (sqrt(inc[0] * inc[0] + inc[1] * inc[1] + inc[2] * inc[2]) < cfg.min_error_change &&
+                        sqrt(inc[3] * inc[3] + inc[4] * inc[4] + inc[5] * inc[5]) < cfg.min_error_change)
+                        stop = true;                                              // :421-424
+                    err_prev = err;
+                }
+                if (!stop && it + 1 >= max_iters) stop = true;                    // the for loop runs out
+                if (lane == 0) s_stop = stop ? 1 : 0;
+            }
+            __syncthreads();
+            const int stop = s_stop;
+            __syncthreads();
+            if (stop) break;
+        }
+        if (warp == 0) {                       // :429-430 and the state the next kernels read
+            if (!fail_first) {
+                warp_inv6(sH, sC);
+                __syncwarp();
+                for (int i = lane; i < 36; i += 32) c.cov[i] = sC[i];
+            }
+            if (lane < 16) sb.DT[(size_t)p * 16 + lane] = sDT[lane];
+            if (lane == 0) {
+                c.err = fail_first ? -1.0 : err;
+                c.fail_first = fail_first ? 1 : 0;
+                c.iters = it + 1;
+                c.err_prev = err_prev;
+                sb.active[p] = 0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- S3: gate of stage 1 (:341), removeOutliers at the stage-1 pose (:343), restart for stage 2 (:345-355) ----
 __global__ void __launch_bounds__(K2_THREADS, 1) stream_outlier_kernel(const SolveParams prm, const StreamBufs sb) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -1632,7 +1972,22 @@ __global__ void __launch_bounds__(K2_THREADS, 1) stream_outlier_kernel(const Sol
         if (tid == 0) c.delegate = 1;
         return;
     }
-    remove_outliers(v.f, st, v.sortbuf, st.DT, cam, cfg);
+    // the lists live in HBM here: every residual is formed ONCE (same fp64 arithmetic as K2's), then read back by the statistics
+    double* rp = sb.res_pt + v.slot_p;
+    double* rl = sb.res_ls + v.slot_l;
+    {
+        const Feat& f = v.f;
+        for (int i = tid; i < f.np; i += K2_THREADS) {
+            double X, Y, Z, iz, dx, dy;
+            rp[i] = point_residual(f, i, st.DT, cam, X, Y, Z, iz, dx, dy) * f.pss[i];
+        }
+        for (int i = tid; i < f.nl; i += K2_THREADS) {
+            LineRes r;
+            rl[i] = line_residual(f, i, st.DT, cam, r) * f.lss[i];
+        }
+    }
+    __syncthreads();
+    remove_outliers_select(v.f, st, v.sortbuf, cfg, [&](int i) -> double { return rp[i]; }, [&](int i) -> double { return rl[i]; });
     __syncthreads();
     stream_write_flags(v.f, sb, v.slot_p, v.slot_l);
     if (tid == 0) {
@@ -1714,7 +2069,8 @@ __global__ void __launch_bounds__(256) stream_finalize_kernel(const SolveParams 
 
 size_t stream_partial_doubles(int B, int slices) { return (size_t)B * slices * gn_stream_partials_per_slice() * (ACC_N + 1); }
 
-cudaError_t launch_stream_solve(const SolveParams& prm_in, int n_pairs, const StreamBufs& sb, cudaStream_t stream, int* launches) {
+cudaError_t launch_stream_solve(const SolveParams& prm_in, int n_pairs, const StreamBufs& sb, cudaStream_t stream, int* launches,
+                                cudaEvent_t lists_done) {
     if (n_pairs <= 0) return cudaSuccess;
     SolveParams prm = prm_in;
     prm.feat_in_smem = 0;
@@ -1728,15 +2084,34 @@ cudaError_t launch_stream_solve(const SolveParams& prm_in, int n_pairs, const St
     int nl = 0;
     stream_prepare_kernel<<<n_pairs, K2_THREADS, smem, stream>>>(prm, sb);
     ++nl;
+    if (lists_done) cudaEventRecord(lists_done, stream);   // instrumentation: list building | optimizePose
     const int32_t* off_p = prm.mode == 0 ? prm.prev.pt_off + prm.first_pair : prm.matched.pt_off + prm.first_pair;
     const int32_t* off_l = prm.mode == 0 ? prm.prev.ls_off + prm.first_pair : prm.matched.ls_off + prm.first_pair;
+    static size_t conf_c[64] = {};
+    const size_t ring = (size_t)GS_STAGES * GS_STAGE_BYTES;
+    e = ensure_dynamic_smem(reinterpret_cast<const void*>(gn_loop_stream_kernel), ring, conf_c);
+    if (e != cudaSuccess) return e;
+    static const bool sweeps = getenv("PLSTVO_STREAM_SWEEPS") != nullptr;   // A/B knob: one sweep + step launch pair per iteration
+    int gn_calls = 0;
     auto gn = [&](int max_iters) -> cudaError_t {
-        for (int it = 0; it < max_iters; ++it) {
-            cudaError_t err = launch_gn_eval_stream(prm.cam, prm.cfg, off_p, off_l, sb.rec_pt, sb.rec_ls, n_pairs, sb.DT, sb.partial,
-                                                    sb.slices, sb.sm_count, sb.H, sb.g, sb.e, stream, sb.cnt_pt, sb.cnt_ls, sb.active);
+        if (!sweeps) {   // the whole GN call in one launch: persistent CTAs, one problem each at a time
+            int* q = sb.queue + (gn_calls++);
+            cudaError_t err = cudaMemsetAsync(q, 0, sizeof(int), stream);
             if (err != cudaSuccess) return err;
-            stream_step_kernel<<<(n_pairs + 3) / 4, 128, 0, stream>>>(sb, prm.cfg, n_pairs, max_iters);
-            nl += 3;
+            const int grid = n_pairs < 2 * sb.sm_count ? n_pairs : 2 * sb.sm_count;
+            gn_loop_stream_kernel<<<grid, GS_THREADS, ring, stream>>>(prm.cam, prm.cfg, off_p, off_l, sb, n_pairs, max_iters, q);
+            nl += 1;
+            return cudaGetLastError();
+        }
+        for (int it = 0; it < max_iters; ++it) {
+            // H = nullptr: the sweep leaves its partials; the step kernel folds them itself (one launch less per iteration)
+            cudaError_t err = launch_gn_eval_stream(prm.cam, prm.cfg, off_p, off_l, sb.rec_pt, sb.rec_ls, n_pairs, sb.DT, sb.partial,
+                                                    sb.slices, sb.sm_count, nullptr, nullptr, nullptr, stream, sb.cnt_pt, sb.cnt_ls,
+                                                    sb.active);
+            if (err != cudaSuccess) return err;
+            stream_step_kernel<<<(n_pairs + 3) / 4, 128, 0, stream>>>(sb, prm.cfg, n_pairs, max_iters,
+                                                                      sb.slices * gn_stream_partials_per_slice());
+            nl += 2;
         }
         return cudaGetLastError();
     };
