@@ -786,10 +786,14 @@ __device__ double block_select_kth(int* hist, int m, int k, Val val) {
                 take = (pass == 7) || ((key >> (sh + 8)) == (prefix >> (sh + 8)));
                 bin = (unsigned)(key >> sh) & 255u;
             }
-            const unsigned act = __ballot_sync(FULL_MASK, take);
-            if (take) {   // one shared-memory atomic per distinct bin and warp (the top bytes of residuals are all alike)
-                const unsigned peers = __match_any_sync(act, bin);
-                if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&hist[bin], __popc(peers));
+            if (pass >= 6) {   // sign / exponent bytes: nearly all keys alike -> one shared-memory atomic per distinct bin and warp
+                const unsigned act = __ballot_sync(FULL_MASK, take);
+                if (take) {
+                    const unsigned peers = __match_any_sync(act, bin);
+                    if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&hist[bin], __popc(peers));
+                }
+            } else if (take) {   // mantissa bytes: keys spread over the bins, plain atomics are cheaper
+                atomicAdd(&hist[bin], 1);
             }
         }
         __syncthreads();
@@ -1977,13 +1981,18 @@ __global__ void __launch_bounds__(K2_THREADS, 1) stream_outlier_kernel(const Sol
     double* rl = sb.res_ls + v.slot_l;
     {
         const Feat& f = v.f;
+        double DTr[12];                       // pose in registers: the loops below are pure streaming arithmetic
+#pragma unroll
+        for (int i = 0; i < 12; i++) DTr[i] = st.DT[i];
+#pragma unroll 4
         for (int i = tid; i < f.np; i += K2_THREADS) {
             double X, Y, Z, iz, dx, dy;
-            rp[i] = point_residual(f, i, st.DT, cam, X, Y, Z, iz, dx, dy) * f.pss[i];
+            rp[i] = point_residual(f, i, DTr, cam, X, Y, Z, iz, dx, dy) * f.pss[i];
         }
+#pragma unroll 2
         for (int i = tid; i < f.nl; i += K2_THREADS) {
             LineRes r;
-            rl[i] = line_residual(f, i, st.DT, cam, r) * f.lss[i];
+            rl[i] = line_residual(f, i, DTr, cam, r) * f.lss[i];
         }
     }
     __syncthreads();
