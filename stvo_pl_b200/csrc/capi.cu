@@ -1924,7 +1924,16 @@ int plstvo_batch_stage_times(PlContext* ctx, PlDeviceBatch* db, int iters, doubl
     for (auto& e : ev) cudaEventDestroy(e);
     for (int k = 0; k < 5; ++k) ms[k] = acc[k] / iters;
     if (counts) {
-        counts[0] = (ws.use_tc ? 1 : 0) | (ws.use_stream ? 2 : 0);
+        int delegated = 0;   // streamed solver: problems it handed to the fp64 kernel in the last pass (its only_if list)
+        if (ws.use_stream && ws.B > 0) {
+            StreamBufs sb;
+            int rc = stream_bufs_prepare(ctx, ws.d_stream, ws.B, (size_t)ws.p_off1[ws.B], (size_t)ws.l_off1[ws.B], &sb);
+            if (rc) return rc;
+            std::vector<int32_t> act((size_t)ws.B);
+            CK(ctx, cudaMemcpy(act.data(), sb.active, (size_t)ws.B * sizeof(int32_t), cudaMemcpyDeviceToHost));
+            for (int32_t a : act) delegated += a != 0;
+        }
+        counts[0] = (ws.use_tc ? 1 : 0) | (ws.use_stream ? 2 : 0) | (delegated << 8);
         counts[1] = ws.use_tc ? (int32_t)(ws.tc_items[0].size() + ws.tc_items[1].size()) : (int32_t)ws.tiles.size();
         counts[2] = (int32_t)ws.problems.size();
         counts[3] = ws.B;
@@ -2029,7 +2038,7 @@ int plstvo_gn_eval_stream(PlContext* ctx, const PlCamera* cam, const PlConfig* c
     DevBuf &rec_pt = ctx->gs_rec_pt, &rec_ls = ctx->gs_rec_ls;
     CK(ctx, rec_pt.ensure(std::max<size_t>(n * 32, 32)));
     CK(ctx, rec_ls.ensure(std::max<size_t>(l * 64, 64)));
-    CK(ctx, launch_pack_records(md, B, (int)n, (int)l, rec_pt.as<float4>(), rec_ls.as<float4>(), s));
+    CK(ctx, launch_pack_records(md, *cam, B, (int)n, (int)l, rec_pt.as<float4>(), rec_ls.as<float4>(), s));
     ctx->launches++;
     // slices per problem: a work item is ~12 tiles of 16 KB (more slices only when the batch cannot fill the persistent grid)
     int max_tiles = 1;

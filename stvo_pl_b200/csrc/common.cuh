@@ -206,7 +206,8 @@ cudaError_t launch_lift_lines(const PlCamera& cam, const PlStereoConfig& sc, int
 // GN evaluation streamed from HBM (roofline kernel of config C5): fp32-packed records, TMA-staged tiles
 int gn_stream_tiles(int n_pt, int n_ls);
 int gn_stream_partials_per_slice();   // fp64 partial records one slice writes (one per consumer warp)   // 16 KB tiles of one problem (512 points or 256 lines each)
-cudaError_t launch_pack_records(const MatchedDev& m, int B, int n_pt, int n_ls, float4* pt, float4* ls, cudaStream_t stream);
+cudaError_t launch_pack_records(const MatchedDev& m, const PlCamera& cam, int B, int n_pt, int n_ls, float4* pt, float4* ls,
+                                cudaStream_t stream);
 cudaError_t launch_gn_eval_stream(const PlCamera& cam, const PlConfig& cfg, const int32_t* pt_off, const int32_t* ls_off,
                                   const float4* pt, const float4* ls, int B, const double* DT, double* partial,
                                   int slices_per_problem, int sm_count, double* H, double* g, double* e, cudaStream_t stream,

@@ -3,11 +3,11 @@
 // B >= 1024 problems resident so that one sweep is far larger than L2).
 //
 // Records: the fp32-packed layout SURVEY 8(a) A4/A5 defines — the algorithmic bytes of one evaluation are exactly what
-// the kernel reads.  Pose-independent per-feature quantities are formed once, in double, when the batch is packed:
-//   point, 32 B : {Px, Py, Pz, sqrt(sigma2)} {u_obs, v_obs, inlier, -}
-//   line,  64 B : {sPx, sPy, sPz, sqrt(sigma2)} {ePx, ePy, ePz, inlier} {l0, l1, l2, -} {oa, ob, oc, -}
-// (oa, ob, oc): StereoFrame::lineSegmentOverlap's parameter lambda of a projected endpoint is affine in the endpoint in all
-// three of its branches (src/stereoFrame.cpp:515-612); the coefficients depend on the previous-frame segment only.
+// the kernel reads: 32 B per point, 64 B per line.  Pose-independent per-feature quantities are formed once, in double,
+// when the batch is packed (gn_stream.cuh, "records": normalised coordinates, the residual at the identity pose, the overlap
+// parameters at the identity pose); (oa, ob, oc): StereoFrame::lineSegmentOverlap's parameter lambda of a projected endpoint is
+// affine in the endpoint in all three of its branches (src/stereoFrame.cpp:515-612); the coefficients depend on the
+// previous-frame segment only.
 // Tiles of 16 KB (512 points or 256 lines) are stored plane by plane ([cnt] x float4 per plane), so that a bulk copy of
 // one contiguous range lands in shared memory in a bank-conflict-free order.
 //
@@ -38,16 +38,17 @@ __device__ __forceinline__ int gs_find_problem(const int32_t* __restrict__ off, 
 }
 
 // device-side packing of the double arrays into the tile-planar fp32 records
-__global__ void pack_records_kernel(MatchedDev m, int B, int n_pt, int n_ls, float4* __restrict__ pt, float4* __restrict__ ls) {
+__global__ void pack_records_kernel(MatchedDev m, PlCamera cam, int B, int n_pt, int n_ls, float4* __restrict__ pt,
+                                    float4* __restrict__ ls) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const GsCamD c = {cam.fx, cam.fy, cam.cx, cam.cy};
     if (i < n_pt) {
         const int p = gs_find_problem(m.pt_off, B, i), p0 = m.pt_off[p], np = m.pt_off[p + 1] - p0;
         const int j = i - p0, t = j / GS_PT_TILE, r = j % GS_PT_TILE, cnt = min(GS_PT_TILE, np - t * GS_PT_TILE);
         float4* base = pt + 2 * (size_t)(p0 + t * GS_PT_TILE);
         const size_t a = (size_t)i;
-        base[r] = make_float4((float)m.pt_P[3 * a], (float)m.pt_P[3 * a + 1], (float)m.pt_P[3 * a + 2], (float)sqrt(m.pt_sigma2[a]));
-        base[cnt + r] = make_float4((float)m.pt_pl_obs[2 * a], (float)m.pt_pl_obs[2 * a + 1],
-                                    (m.pt_inlier && !m.pt_inlier[a]) ? 0.f : 1.f, 0.f);
+        gs_pack_point(c, m.pt_P[3 * a], m.pt_P[3 * a + 1], m.pt_P[3 * a + 2], m.pt_pl_obs[2 * a], m.pt_pl_obs[2 * a + 1],
+                      sqrt(m.pt_sigma2[a]), !(m.pt_inlier && !m.pt_inlier[a]), base[r], base[cnt + r]);
     }
     if (i < n_ls) {
         const int p = gs_find_problem(m.ls_off, B, i), l0 = m.ls_off[p], nl = m.ls_off[p + 1] - l0;
@@ -65,11 +66,9 @@ __global__ void pack_records_kernel(MatchedDev m, int B, int n_pt, int n_ls, flo
             const double ca = sv - ev, cb = eu - su, cc = su * ev - eu * sv, lxy = 1.0 / (ca * ca + cb * cb);
             oa = (cb * cb * lxy) / lx; ob = (-(ca * cb) * lxy) / lx; oc = (-(ca * cc) * lxy - su) / lx;
         }
-        base[r] = make_float4((float)m.ls_sP[3 * a], (float)m.ls_sP[3 * a + 1], (float)m.ls_sP[3 * a + 2], (float)sqrt(m.ls_sigma2[a]));
-        base[cnt + r] = make_float4((float)m.ls_eP[3 * a], (float)m.ls_eP[3 * a + 1], (float)m.ls_eP[3 * a + 2],
-                                    (m.ls_inlier && !m.ls_inlier[a]) ? 0.f : 1.f);
-        base[2 * cnt + r] = make_float4((float)m.ls_le_obs[3 * a], (float)m.ls_le_obs[3 * a + 1], (float)m.ls_le_obs[3 * a + 2], 0.f);
-        base[3 * cnt + r] = make_float4((float)oa, (float)ob, (float)oc, 0.f);
+        gs_pack_line(c, m.ls_sP[3 * a], m.ls_sP[3 * a + 1], m.ls_sP[3 * a + 2], m.ls_eP[3 * a], m.ls_eP[3 * a + 1], m.ls_eP[3 * a + 2],
+                     m.ls_le_obs[3 * a], m.ls_le_obs[3 * a + 1], m.ls_le_obs[3 * a + 2], oa, ob, oc, sqrt(m.ls_sigma2[a]),
+                     !(m.ls_inlier && !m.ls_inlier[a]), base[r], base[cnt + r], base[2 * cnt + r], base[3 * cnt + r]);
     }
 }
 
@@ -126,7 +125,7 @@ gn_eval_stream_kernel(PlCamera cam, float homog_th, const GsLists L,
                     if (t == 0) {   // the item's pose rides with its first tile (ordered by the barrier's release / acquire)
                         const double* DT = DTs + (size_t)(item / bpp) * 16;
 #pragma unroll
-                        for (int i = 0; i < 12; i++) sDT[st][i] = (float)__ldg(DT + i);
+                        for (int i = 0; i < 12; i++) sDT[st][i] = gs_pose_entry(__ldg(DT + i), i);
                     }
                     const void* src;
                     uint32_t bytes;
@@ -238,10 +237,11 @@ int gn_stream_tiles(int n_pt, int n_ls) {
     return (n_pt + GS_PT_TILE - 1) / GS_PT_TILE + (n_ls + GS_LS_TILE - 1) / GS_LS_TILE;
 }
 
-cudaError_t launch_pack_records(const MatchedDev& m, int B, int n_pt, int n_ls, float4* pt, float4* ls, cudaStream_t stream) {
+cudaError_t launch_pack_records(const MatchedDev& m, const PlCamera& cam, int B, int n_pt, int n_ls, float4* pt, float4* ls,
+                                cudaStream_t stream) {
     const int n = n_pt > n_ls ? n_pt : n_ls;
     if (n <= 0 || B <= 0) return cudaSuccess;
-    pack_records_kernel<<<(n + 255) / 256, 256, 0, stream>>>(m, B, n_pt, n_ls, pt, ls);
+    pack_records_kernel<<<(n + 255) / 256, 256, 0, stream>>>(m, cam, B, n_pt, n_ls, pt, ls);
     return cudaGetLastError();
 }
 

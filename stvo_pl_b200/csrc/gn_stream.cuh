@@ -19,9 +19,15 @@ constexpr int GS_STAGE_BYTES = 16384;
 constexpr int GS_STAGES = 6;
 constexpr int GS_NACC = ACC_N + 1;                     // 21 H + 6 g + e + count
 
+#ifdef GS_EXACT_MATH   // A/B build: IEEE division / square root instead of the approximate SFU forms
+__device__ __forceinline__ float gs_rcp(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ float gs_sqrt(float x) { return __fsqrt_rn(x); }
+__device__ __forceinline__ float gs_rsqrt(float x) { return __frcp_rn(__fsqrt_rn(x)); }
+#else
 __device__ __forceinline__ float gs_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float gs_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float gs_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#endif
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -116,25 +122,72 @@ __device__ __forceinline__ float gs_overlap_l(float ls, float le) {   // :601-61
     return ov;
 }
 
+// The pose as the evaluator holds it: r[] = the top three rows of DT with the identity taken off the rotation, (R - I | t),
+// rounded to fp32 AFTER the subtraction (a frame-to-frame rotation is close to I: its difference from I keeps ~1e-9 of absolute
+// accuracy in fp32, R itself only 6e-8).
 struct GsPose {
     float r[12];
     float fx, fy, cx, cy, h, inv_h, fx_h;
 };
+__device__ __forceinline__ float gs_pose_entry(double v, int i) { return (float)((i == 0 || i == 5 || i == 10) ? v - 1.0 : v); }
+
+// ---- records (formed once per list, in double) ------------------------------------------------------------------------------
+// Every pose-independent part of a residual is evaluated in fp64 when the record is packed, at the identity pose; the kernel
+// adds the pose-dependent CHANGE of the projection, which is a small quantity without cancellation:
+//     u(DT) - u_obs = [fx x/z + cx - u_obs]  +  fx (dx - (x/z) dz) / (z + dz),      (dx, dy, dz) = (R - I) P + t
+// (the naive fp32 form subtracts two ~1000 px numbers and carries ~2e-4 px of rounding noise into every residual; this form
+// carries ~1e-5 px, which matters for the stop tests of the Gauss-Newton loop: they compare errors that differ in the 6th digit).
+//   point, 32 B : {x/z, y/z, z, sqrt(sigma2)} {du0, dv0, inlier, -}                du0 = fx x/z + cx - u_obs
+//   line,  64 B : {sx/sz, sy/sz, sz, sqrt(sigma2)} {ex/ez, ey/ez, ez, inlier} {l0, l1, ds0, de0} {oa, ob, lam_s0, lam_e0}
+//                 ds0 = l . (projection of sP at identity, 1), lam_s0 = (oa, ob, oc) . (that projection, 1)
+struct GsCamD {
+    double fx, fy, cx, cy;
+};
+__device__ __forceinline__ void gs_pack_point(const GsCamD& c, double x, double y, double z, double u, double v, double pss,
+                                              bool inl, float4& A, float4& B) {
+    const double xn = x / z, yn = y / z;
+    A = make_float4((float)xn, (float)yn, (float)z, (float)pss);
+    B = make_float4((float)(c.fx * xn + c.cx - u), (float)(c.fy * yn + c.cy - v), inl ? 1.f : 0.f, 0.f);
+}
+__device__ __forceinline__ void gs_pack_line(const GsCamD& c, double sx, double sy, double sz, double ex, double ey, double ez,
+                                             double l0, double l1, double l2, double oa, double ob, double oc, double lss,
+                                             bool inl, float4& A, float4& B, float4& C, float4& D) {
+    const double sxn = sx / sz, syn = sy / sz, exn = ex / ez, eyn = ey / ez;
+    const double spu = c.fx * sxn + c.cx, spv = c.fy * syn + c.cy, epu = c.fx * exn + c.cx, epv = c.fy * eyn + c.cy;
+    A = make_float4((float)sxn, (float)syn, (float)sz, (float)lss);
+    B = make_float4((float)exn, (float)eyn, (float)ez, inl ? 1.f : 0.f);
+    C = make_float4((float)l0, (float)l1, (float)(l0 * spu + l1 * spv + l2), (float)(l0 * epu + l1 * epv + l2));
+    D = make_float4((float)oa, (float)ob, (float)(oa * spu + ob * spv + oc), (float)(oa * epu + ob * epv + oc));
+}
+
+// one 3D point through the pose: camera-frame coordinates and the change of its projection against the identity pose
+struct GsProj {
+    float X, Y, Z, iz, du, dv;
+};
+__device__ __forceinline__ GsProj gs_project(const GsPose& P, float xn, float yn, float z, bool use) {
+    const float x = xn * z, y = yn * z;
+    const float ddx = fmaf(P.r[0], x, fmaf(P.r[1], y, fmaf(P.r[2], z, P.r[3])));
+    const float ddy = fmaf(P.r[4], x, fmaf(P.r[5], y, fmaf(P.r[6], z, P.r[7])));
+    const float ddz = fmaf(P.r[8], x, fmaf(P.r[9], y, fmaf(P.r[10], z, P.r[11])));
+    GsProj q;
+    q.X = x + ddx; q.Y = y + ddy; q.Z = z + ddz;
+    q.iz = use ? gs_rcp(q.Z) : 0.f;                      // a dead record contributes exact zeros, never a NaN
+    q.du = P.fx * fmaf(-xn, ddz, ddx) * q.iz;
+    q.dv = P.fy * fmaf(-yn, ddz, ddy) * q.iz;
+    return q;
+}
 
 // point block (:563-606); `use` = a live record flagged inlier
 template <class Acc>
 __device__ __forceinline__ void gs_point(const GsPose& P, const float4 a, const float4 b, bool use, Acc& acc) {
-    const float X = fmaf(P.r[0], a.x, fmaf(P.r[1], a.y, fmaf(P.r[2], a.z, P.r[3])));
-    const float Y = fmaf(P.r[4], a.x, fmaf(P.r[5], a.y, fmaf(P.r[6], a.z, P.r[7])));
-    const float Z = fmaf(P.r[8], a.x, fmaf(P.r[9], a.y, fmaf(P.r[10], a.z, P.r[11])));
-    const float iz = use ? gs_rcp(Z) : 0.f;                // a dead record contributes exact zeros, never a NaN
-    const float dx = fmaf(P.fx * X, iz, P.cx - b.x), dy = fmaf(P.fy * Y, iz, P.cy - b.y);
+    const GsProj q = gs_project(P, a.x, a.y, a.z, use);
+    const float dx = b.x + q.du, dy = b.y + q.dv;
     const float ss = fmaf(dx, dx, dy * dy);
     const float n = gs_sqrt(ss), inv = fminf(P.inv_h, gs_rsqrt(ss));          // 1 / max(homogTh, n)
-    const float fg = (Z * Z > P.h) ? P.fx * iz * iz : P.fx_h;                 // fx / max(homogTh, Z^2)  (:577)
+    const float fg = (q.Z * q.Z > P.h) ? P.fx * q.iz * q.iz : P.fx_h;          // fx / max(homogTh, Z^2)  (:577)
     const float sc = fg * inv;
     float J[6];
-    gs_jac<false>(X, Y, Z, sc * dx, sc * dy, J);
+    gs_jac<false>(q.X, q.Y, q.Z, sc * dx, sc * dy, J);
     const float r = n * a.w;
     const float w = use ? gs_rcp(fmaf(r, r, 1.f)) : 0.f;
     acc.add(J, r, w, use ? 1.f : 0.f);
@@ -144,26 +197,18 @@ __device__ __forceinline__ void gs_point(const GsPose& P, const float4 a, const 
 template <class Acc>
 __device__ __forceinline__ void gs_line(const GsPose& P, const float4 a, const float4 b, const float4 c, const float4 d,
                                         bool use, Acc& acc) {
-    const float sX = fmaf(P.r[0], a.x, fmaf(P.r[1], a.y, fmaf(P.r[2], a.z, P.r[3])));
-    const float sY = fmaf(P.r[4], a.x, fmaf(P.r[5], a.y, fmaf(P.r[6], a.z, P.r[7])));
-    const float sZ = fmaf(P.r[8], a.x, fmaf(P.r[9], a.y, fmaf(P.r[10], a.z, P.r[11])));
-    const float eX = fmaf(P.r[0], b.x, fmaf(P.r[1], b.y, fmaf(P.r[2], b.z, P.r[3])));
-    const float eY = fmaf(P.r[4], b.x, fmaf(P.r[5], b.y, fmaf(P.r[6], b.z, P.r[7])));
-    const float eZ = fmaf(P.r[8], b.x, fmaf(P.r[9], b.y, fmaf(P.r[10], b.z, P.r[11])));
-    const float isz = use ? gs_rcp(sZ) : 0.f, iez = use ? gs_rcp(eZ) : 0.f;
-    const float spu = fmaf(P.fx * sX, isz, P.cx), spv = fmaf(P.fy * sY, isz, P.cy);
-    const float epu = fmaf(P.fx * eX, iez, P.cx), epv = fmaf(P.fy * eY, iez, P.cy);
-    const float ds = fmaf(c.x, spu, fmaf(c.y, spv, c.z)), de = fmaf(c.x, epu, fmaf(c.y, epv, c.z));
+    const GsProj s = gs_project(P, a.x, a.y, a.z, use), e = gs_project(P, b.x, b.y, b.z, use);
+    const float ds = fmaf(c.x, s.du, fmaf(c.y, s.dv, c.z)), de = fmaf(c.x, e.du, fmaf(c.y, e.dv, c.w));
     const float ss = fmaf(ds, ds, de * de);
     const float n = gs_sqrt(ss), iden = fminf(P.inv_h, gs_rsqrt(ss));
-    const float ks = ((sZ * sZ > P.h) ? P.fx * isz * isz : P.fx_h) * (ds * iden);
-    const float ke = ((eZ * eZ > P.h) ? P.fx * iez * iez : P.fx_h) * (de * iden);
+    const float ks = ((s.Z * s.Z > P.h) ? P.fx * s.iz * s.iz : P.fx_h) * (ds * iden);
+    const float ke = ((e.Z * e.Z > P.h) ? P.fx * e.iz * e.iz : P.fx_h) * (de * iden);
     float J[6];
-    gs_jac<false>(sX, sY, sZ, ks * c.x, ks * c.y, J);
-    gs_jac<true>(eX, eY, eZ, ke * c.x, ke * c.y, J);
+    gs_jac<false>(s.X, s.Y, s.Z, ks * c.x, ks * c.y, J);
+    gs_jac<true>(e.X, e.Y, e.Z, ke * c.x, ke * c.y, J);
     const float r = n * a.w;
     float w = gs_rcp(fmaf(r, r, 1.f));
-    w *= gs_overlap_l(fmaf(d.x, spu, fmaf(d.y, spv, d.z)), fmaf(d.x, epu, fmaf(d.y, epv, d.z)));   // :664-670
+    w *= gs_overlap_l(fmaf(d.x, s.du, fmaf(d.y, s.dv, d.z)), fmaf(d.x, e.du, fmaf(d.y, e.dv, d.w)));   // :664-670
     acc.add(J, r, use ? w : 0.f, use ? 1.f : 0.f);
 }
 

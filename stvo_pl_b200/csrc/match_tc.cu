@@ -153,8 +153,7 @@ __device__ __forceinline__ uint32_t h2u_hi(uint32_t p) {
 
 // "no value" sentinel: -1024 (finite, so that the FMA-pipe form of the update stays exact: |x - y| <= 1280 < 2048)
 constexpr uint32_t NEG2 = 0xE400E400u;
-constexpr uint32_t H2_ONE = 0x3C003C00u, H2_NEG1 = 0xBC00BC00u, H2_NEGHALF = 0xB800B800u, H2_128 = 0x58005800u,
-                   H2_511 = 0x5FFC5FFCu;
+constexpr uint32_t H2_NEG1 = 0xBC00BC00u, H2_NEGHALF = 0xB800B800u, H2_128 = 0x58005800u, H2_511 = 0x5FFC5FFCu;
 // (best, second) dot values packed (lo, hi) -> distances d = (256 - v) / 2 (exact), "none" (sentinel) -> 511
 __device__ __forceinline__ uint32_t dots_to_dist(uint32_t pv) { return hmin2u(hfma2u(pv, H2_NEGHALF, H2_128), H2_511); }
 

@@ -12,7 +12,7 @@ import numpy as np
 from . import types as T
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libplstvo_b200.so")
+LIB_PATH = os.environ.get("PLSTVO_LIB") or os.path.join(_HERE, "lib", "libplstvo_b200.so")   # PLSTVO_LIB: A/B builds
 
 ERRORS = {-1: "PLSTVO_E_INVALID", -2: "PLSTVO_E_TOO_LARGE", -3: "PLSTVO_E_CUDA", -4: "PLSTVO_E_NO_DEVICE",
           -5: "PLSTVO_E_SIZE"}
@@ -199,7 +199,7 @@ class DeviceBatch:
                                                            cnt.ctypes.data_as(T.c_int32_p)))
         return dict(ms_expand=float(ms[0]), ms_distance=float(ms[1]), ms_resolve=float(ms[2]), ms_lists=float(ms[3]),
                     ms_solve=float(ms[3] + ms[4]), ms_optimize_pose=float(ms[4]),
-                    tensor_core_form=bool(cnt[0] & 1), streamed_solver=bool(cnt[0] & 2), n_items=int(cnt[1]),
+                    tensor_core_form=bool(cnt[0] & 1), streamed_solver=bool(cnt[0] & 2), delegated_to_fp64=int(cnt[0] >> 8), n_items=int(cnt[1]),
                     n_problems=int(cnt[2]), n_pairs=int(cnt[3]))
 
     def download(self):

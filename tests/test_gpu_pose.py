@@ -195,7 +195,7 @@ def test_large_frames_take_the_streamed_solver(engine, oracle):
     n_diff = _flag_diffs(gpu["inlier_pt"], ref["inlier_pt"]) + _flag_diffs(gpu["inlier_ls"], ref["inlier_ls"])
     print(f"streamed solver, C5 shape: worst pose deviation {worst}, {n_diff} of {prev.n_pt + prev.n_ls} inlier flags differ")
     assert n_diff <= 4
-    assert worst[0] < 5e-6 and worst[1] < 5e-5      # measured 1.2e-6 / 6e-6: headroom inside the 1e-5 / 1e-4 bar
+    assert worst[0] < 1e-7 and worst[1] < 1e-6      # measured 2.3e-10 / 6e-9 (delta-form residuals): far inside the 1e-5 / 1e-4 bar
 
 
 def test_batch_of_64_pairs_sharded_invariance(engine, oracle):
@@ -372,7 +372,11 @@ def test_explicit_lists_c5_size(engine, oracle):
         assert res["status"][p] == ref["status"][p] and res["good"][p] == ref["good"][p] == 1
         ang, tr = R.pose_error(res["DT"][p], ref["DT"][p])
         assert ang < TOL_ANG and tr < TOL_TR
-        assert abs(res["err_norm"][p] - ref["err_norm"][p]) < 1e-5
+        a, b, c, d = mb.pt_off[p], mb.pt_off[p + 1], mb.ls_off[p], mb.ls_off[p + 1]
+        flips = _flag_diffs(ip[a:b], rp[a:b]) + _flag_diffs(il[c:d], rl[c:d])
+        # same inlier set: the error agrees to the fp32 evaluation's noise; a flag that flipped (a residual within fp32 reach of the
+        # removeOutliers threshold) moves it by about one feature's share
+        assert abs(res["err_norm"][p] - ref["err_norm"][p]) < (1e-6 if flips == 0 else 2e-4 * flips)
         np.testing.assert_allclose(res["DT_cov"][p], ref["DT_cov"][p], rtol=2e-3, atol=1e-12)
         ang, tr = R.pose_error(res["DT_opt"][p], Ts[p])
         assert ang < 1e-3 and tr < 1e-2
