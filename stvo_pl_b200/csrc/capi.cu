@@ -165,8 +165,12 @@ int pow2_ceil_host(int n) {
 }
 
 
-// PLSTVO_STREAM_SOLVE=1 sends every solve through the streamed form (tests on small frames); =0 never does (K2 with its
-// lists in global scratch instead); default: streamed exactly when the lists do not fit K2's shared memory
+// Which solver a batch takes.  K2 (one fp64 CTA per pair, lists in shared memory) has the lower latency and follows the
+// reference to rounding; the streamed solver (fp32 per-feature arithmetic, fp64 sums / algebra / outlier statistics, close stop
+// tests re-decided in fp64) has the higher throughput once a batch is more than one wave of K2 CTAs, and is the only form for
+// lists that do not fit K2's shared memory.  Default: streamed when the lists do not fit, or when the batch has more pairs than
+// the device has SMs.  PLSTVO_STREAM_SOLVE=1: always streamed (tests on small frames); =0: never (K2, lists in global scratch
+// if need be).
 int stream_mode() {
     static const int m = [] {
         const char* v = getenv("PLSTVO_STREAM_SOLVE");
@@ -295,6 +299,7 @@ int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfi
     if (ws.planned && ws.B == B && ws.planned_features == with_features && ws.sm_planned == ctx->sm_count &&
         ws.cfg.has_points == cfg->has_points && ws.cfg.has_lines == cfg->has_lines &&
         ws.cfg.best_lr_matches == cfg->best_lr_matches && ws.cfg.min_ratio_12_p == cfg->min_ratio_12_p &&
+        (ws.cfg.solver_mode != 0) == (cfg->solver_mode != 0) &&
         ws.cfg.min_ratio_12_l == cfg->min_ratio_12_l && (int)ws.p_off1.size() == B + 1 &&
         !memcmp(ws.p_off1.data(), prev->pt_off, (size_t)(B + 1) * 4) &&
         !memcmp(ws.p_off2.data(), curr->pt_off, (size_t)(B + 1) * 4) &&
@@ -452,7 +457,9 @@ int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfi
         CK(ctx, ws.d_results.ensure((size_t)B * sizeof(PlPoseResult)));
         CK(ctx, ws.d_inlp.ensure(np1));
         CK(ctx, ws.d_inll.ensure(nl1));
-        ws.use_stream = stream_mode() == 1 || (stream_mode() != 0 && !ws.feat_in_smem);
+        // (the robust main solver, solver_mode != 0, is K2-only: the streamed form would hand every problem back)
+        ws.use_stream = stream_mode() == 1 ||
+                        (stream_mode() != 0 && (!ws.feat_in_smem || (B > ctx->sm_count && cfg->solver_mode == 0)));
         if (!ws.feat_in_smem || ws.use_stream) {
             ws.feat_stride = k2_feat_stride(ws.cap_pt, ws.cap_ls);
             CK(ctx, ws.d_feat.ensure((size_t)B * ws.feat_stride * sizeof(double)));
@@ -1633,7 +1640,7 @@ int plstvo_optimize_pose(PlContext* ctx, const PlCamera* cam, const PlConfig* cf
     CK(ctx, ctx->gn_out[0].ensure(std::max<size_t>(n, 16)));
     CK(ctx, ctx->gn_out[1].ensure(std::max<size_t>(l, 16)));
     size_t stride = 0;
-    const bool streamed = stream_mode() == 1 || (stream_mode() != 0 && !in_smem);
+    const bool streamed = stream_mode() == 1 || (stream_mode() != 0 && (!in_smem || (B > ctx->sm_count && cfg->solver_mode == 0)));
     if (!in_smem || streamed) {
         stride = k2_feat_stride(cap_pt, cap_ls);
         CK(ctx, ws.d_feat.ensure((size_t)B * stride * sizeof(double)));
