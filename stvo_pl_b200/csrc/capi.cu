@@ -182,15 +182,13 @@ int stream_mode() {
 // carves the streamed solver's buffers for B problems out of one arena; slots = record slots (prev-frame features in track
 // mode, list entries in explicit mode)
 int stream_bufs_prepare(PlContext* ctx, DevBuf& arena, int B, size_t slots_pt, size_t slots_ls, StreamBufs* sb) {
-    const int slices = 4;
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     const size_t o_rp = take((slots_pt + 512) * 2 * sizeof(float4)), o_rl = take((slots_ls + 256) * 4 * sizeof(float4));
     const size_t o_cp = take((size_t)B * 4), o_cl = take((size_t)B * 4), o_dt = take((size_t)B * 16 * 8), o_ac = take((size_t)B * 4);
-    const size_t o_ctl = take((size_t)B * sizeof(StreamCtl)), o_par = take(stream_partial_doubles(B, slices) * 8);
-    const size_t o_h = take((size_t)B * 36 * 8), o_g = take((size_t)B * 6 * 8), o_e = take((size_t)B * 8);
+    const size_t o_ctl = take((size_t)B * sizeof(StreamCtl));
     const size_t o_fp = take(slots_pt + 16), o_fl = take(slots_ls + 16), o_mp = take((slots_pt + 16) * 2), o_ml = take((slots_ls + 16) * 2);
-    const size_t o_resp = take((slots_pt + 16) * 8), o_resl = take((slots_ls + 16) * 8), o_q = take((size_t)B * 2 * 4 + 16);
+    const size_t o_q = take((size_t)B * 2 * 4 + 16);
     CK(ctx, arena.ensure(off));
     uint8_t* b = arena.as<uint8_t>();
     sb->rec_pt = reinterpret_cast<float4*>(b + o_rp);
@@ -200,18 +198,11 @@ int stream_bufs_prepare(PlContext* ctx, DevBuf& arena, int B, size_t slots_pt, s
     sb->DT = reinterpret_cast<double*>(b + o_dt);
     sb->active = reinterpret_cast<int32_t*>(b + o_ac);
     sb->ctl = reinterpret_cast<StreamCtl*>(b + o_ctl);
-    sb->partial = reinterpret_cast<double*>(b + o_par);
-    sb->H = reinterpret_cast<double*>(b + o_h);
-    sb->g = reinterpret_cast<double*>(b + o_g);
-    sb->e = reinterpret_cast<double*>(b + o_e);
-    sb->res_pt = reinterpret_cast<double*>(b + o_resp);
-    sb->res_ls = reinterpret_cast<double*>(b + o_resl);
     sb->queue = reinterpret_cast<int32_t*>(b + o_q);
     sb->flag_pt = b + o_fp;
     sb->flag_ls = b + o_fl;
     sb->midx_pt = reinterpret_cast<uint16_t*>(b + o_mp);
     sb->midx_ls = reinterpret_cast<uint16_t*>(b + o_ml);
-    sb->slices = slices;
     sb->sm_count = ctx->sm_count;
     return 0;
 }
@@ -220,7 +211,6 @@ int stream_bufs_prepare(PlContext* ctx, DevBuf& arena, int B, size_t slots_pt, s
 StreamBufs stream_bufs_at(const StreamBufs& sb, int p0) {
     StreamBufs r = sb;
     r.cnt_pt += p0; r.cnt_ls += p0; r.DT += (size_t)p0 * 16; r.active += p0; r.ctl += p0;
-    r.partial += stream_partial_doubles(p0, sb.slices); r.H += (size_t)p0 * 36; r.g += (size_t)p0 * 6; r.e += p0;
     r.queue += 2 * (size_t)p0;   // a chunk starts at a distinct pair: its two queue words are its own
     return r;
 }

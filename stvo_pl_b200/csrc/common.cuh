@@ -121,24 +121,16 @@ struct StreamBufs {
     float4*  rec_ls;          // 4 float4 per line slot
     int32_t* cnt_pt;          // [B] live records per problem
     int32_t* cnt_ls;
-    double*  DT;              // [B][16] pose being optimised: the sweeps read it, the step kernel updates it
+    double*  DT;              // [B][16] pose being optimised: read and updated by the GN loop kernel
     int32_t* active;          // [B]
     StreamCtl* ctl;           // [B]
-    double*  partial;         // sweep partials
-    double*  H;               // [B][36]
-    double*  g;               // [B][6]
-    double*  e;               // [B]
-    double*  res_pt;          // residual of list entry k at the stage-1 pose (removeOutliers), fp64
-    double*  res_ls;
     uint8_t* flag_pt;         // inlier flags per list entry (slots of the prev frame / of the explicit list)
     uint8_t* flag_ls;
     uint16_t* midx_pt;        // prev index of list entry k (track mode)
     uint16_t* midx_ls;
     int32_t* queue;           // problem queues of the persistent GN kernel (one int per launch of a solve: [2] per chunk)
-    int32_t  slices;          // sweep work items per problem
     int32_t  sm_count;
 };
-size_t stream_partial_doubles(int B, int slices);
 // prm.feat_scratch must hold k2_feat_stride() doubles per pair; prm.feat_in_smem must be 0
 cudaError_t launch_stream_solve(const SolveParams& prm, int n_pairs, const StreamBufs& sb, cudaStream_t stream, int* launches,
                                 cudaEvent_t lists_done = nullptr);

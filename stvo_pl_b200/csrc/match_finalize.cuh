@@ -26,6 +26,24 @@ __device__ __forceinline__ int match_finalize_block(const MatchProblem& pr, int3
         for (int q = tid; q < pr.n1; q += nth) pr.m12[q] = -1;
         return 0;
     }
+    if (pr.nqb == 1 && pr.ntb == 1) {   // one partial per row / column (the tensor-core matcher): plain streaming loops, unrolled
+                                        // so that several of their independent loads are in flight per thread
+#pragma unroll 4
+        for (int t = tid; t < pr.n2; t += nth) {
+            const uint2 c = pr.colpart[t];
+            m21[t] = ratio_accept(c.x, c.y, pr.nnr) ? (int32_t)(c.x & 0xFFFFu) : -1;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int q = tid; q < pr.n1; q += nth) {
+            const uint2 c = pr.rowpart[q];
+            int32_t i2 = ratio_accept(c.x, c.y, pr.nnr) ? (int32_t)(c.x & 0xFFFFu) : -1;
+            if (pr.best_lr && i2 >= 0 && m21[i2] != q) i2 = -1;
+            pr.m12[q] = i2;
+            count += (i2 >= 0);
+        }
+        return count;
+    }
     for (int t = tid; t < pr.n2; t += nth) {
         uint32_t a = KEY_NONE, b = KEY_NONE;
         for (int qb = 0; qb < pr.nqb; ++qb) merge_top2(a, b, pr.colpart[(size_t)qb * pr.n2 + t]);

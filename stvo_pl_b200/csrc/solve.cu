@@ -1236,18 +1236,26 @@ __device__ void gauss_newton(const Feat& f, State& st, double* sortbuf, const Ca
 }
 
 // removeOutliers (:988-1067) for LONG lists (the streamed solver: 8000 + 2000 entries): res_pt(i) / res_ls(i) = |e| sqrt(sigma2)
-// of matched feature i at the stage-1 pose, each read once into shared memory; median and MAD by radix selection (a full
-// bitonic sort of 8192 doubles through shared memory costs 10x more).  Same order statistics, same flags as remove_outliers.
-template <class ResP, class ResL>
+// of matched feature i at the stage-1 pose, each formed ONCE, straight into shared memory; median and MAD by radix selection
+// (a full bitonic sort of 8192 doubles through shared memory costs 10x more).  Same order statistics, same flags as
+// remove_outliers.  `points_filled`: the caller has already put the point residuals into sortbuf.  drop_pt(i) / drop_ls(i): told
+// of every flag that goes from 1 to 0 (the streamed solver clears the flag inside its fp32 record there).
+template <class ResP, class ResL, class DropP, class DropL>
 __device__ void remove_outliers_select(const Feat& f, State& st, double* sortbuf, const SelScratch& sel, const PlConfig& cfg,
-                                       ResP res_pt, ResL res_ls) {
+                                       bool points_filled, ResP res_pt, ResL res_ls, DropP drop_pt, DropL drop_ls) {
     const int tid = threadIdx.x, nth = blockDim.x;
     for (int type = 0; type < 2; type++) {
         const int n = type ? f.nl : f.np;
         if (type == 0 ? !cfg.has_points : !cfg.has_lines) continue;
         if (n == 0) continue;   // vector_mean_stdv_mad of an empty vector: nothing to flag
-        // residuals of ALL matched features (inliers or not), each formed once and kept in shared memory
-        for (int i = tid; i < n; i += nth) sortbuf[i] = (type == 0) ? res_pt(i) : res_ls(i);
+        // residuals of ALL matched features (inliers or not)
+        if (type == 1) {
+#pragma unroll 2
+            for (int i = tid; i < n; i += nth) sortbuf[i] = res_ls(i);
+        } else if (!points_filled) {
+#pragma unroll 4
+            for (int i = tid; i < n; i += nth) sortbuf[i] = res_pt(i);
+        }
         __syncthreads();
         auto residual = [&](int i) -> double { return sortbuf[i]; };
         const long long t_s = clock64();
@@ -1273,10 +1281,12 @@ __device__ void remove_outliers_select(const Feat& f, State& st, double* sortbuf
         const double th = cfg.inlier_k * stdv;
         double removed[1] = {0.0};
         uint8_t* inl = type ? f.inl_l : f.inl_p;
+#pragma unroll 4
         for (int i = tid; i < n; i += nth)
-            if (inl[i] && fabs(residual(i) - mean) > th) {
+            if (fabs(residual(i) - mean) > th && inl[i]) {
                 inl[i] = 0;
                 removed[0] += 1.0;
+                if (type == 0) drop_pt(i); else drop_ls(i);
             }
         block_sum<1>(st, removed);
         if (tid == 0) {
@@ -1361,25 +1371,6 @@ __device__ int block_exclusive_scan(State& st, int v, int* total) {
     *total = tot;
     __syncthreads();
     return base + inc - v;
-}
-
-// rank of this thread's flag among the block's set flags (ascending thread index), and their number
-__device__ __forceinline__ int block_rank(State& st, bool flag, int* total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned bal = __ballot_sync(FULL_MASK, flag);
-    __syncthreads();                       // scan[] may still be read from the previous round
-    if (lane == 0) st.scan[warp] = __popc(bal);
-    __syncthreads();
-    int before = 0, tot = 0;
-    const int nw = blockDim.x >> 5;
-#pragma unroll
-    for (int w = 0; w < K2_WARPS; w++) {
-        const int c = (w < nw) ? st.scan[w] : 0;
-        before += (w < warp) ? c : 0;
-        tot += c;
-    }
-    *total = tot;
-    return before + __popc(bal & ((1u << lane) - 1u));
 }
 
 // Pose finalisation (src/stereoFrameHandler.cpp:372-391) by ONE warp: gate, curr->DT = exp(log(inverse(DT))), Tfw chain,
@@ -1469,9 +1460,59 @@ __device__ void finalize_pose(State& st, const PlPrior* prior, const Feat& f, in
 
 // Phases A and B of the per-pair work: finish the matching (merge K1's partials, ratio test, mutual filter -> m12) and build
 // matched_pt / matched_ls in ascending prev index as SoA (f), or copy the caller's explicit lists (mode 1).  Block-wide.
+// where the streamed solver wants the fp32 records of the lists (gn_stream.cuh "records"); on = false: fp64 lists only (K2)
+struct RecordSink {
+    bool on;
+    float4* pt;      // first record slot of this problem (tile-planar: [cnt] float4 per plane, GS_PT_TILE / GS_LS_TILE per tile)
+    float4* ls;
+    GsCamD cam;
+};
+__device__ __forceinline__ void sink_point(const RecordSink& rs, int k, int np, double x, double y, double z, double u, double v,
+                                           double pss, bool inl) {
+    const int t = k / GS_PT_TILE, r = k % GS_PT_TILE, cnt = min(GS_PT_TILE, np - t * GS_PT_TILE);
+    float4* base = rs.pt + 2 * (size_t)t * GS_PT_TILE;
+    gs_pack_point(rs.cam, x, y, z, u, v, pss, inl, base[r], base[cnt + r]);
+}
+__device__ __forceinline__ void sink_line(const RecordSink& rs, int k, int nl, double sx, double sy, double sz, double ex, double ey,
+                                          double ez, double l0, double l1, double l2, double oa, double ob, double oc, double lss,
+                                          bool inl) {
+    const int t = k / GS_LS_TILE, r = k % GS_LS_TILE, cnt = min(GS_LS_TILE, nl - t * GS_LS_TILE);
+    float4* base = rs.ls + 4 * (size_t)t * GS_LS_TILE;
+    gs_pack_line(rs.cam, sx, sy, sz, ex, ey, ez, l0, l1, l2, oa, ob, oc, lss, inl, base[r], base[cnt + r], base[2 * cnt + r],
+                 base[3 * cnt + r]);
+}
+
+// Ordered compaction plan of m12[0 .. n1): cc[ch] = number of matches before 32-feature chunk ch (exclusive prefix), returns the
+// total.  One ballot per chunk, ONE block scan in all: the gather loops that follow have no block barrier in them, so their
+// dependent global loads (m12 -> the matched curr feature) of different chunks overlap freely.
+__device__ int compaction_plan(State& st, const int32_t* __restrict__ m12, int n1, int* cc) {
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nth >> 5;
+    const int nch = (n1 + 31) >> 5;
+    for (int ch = warp; ch < nch; ch += nw) {
+        const int i = ch * 32 + lane;
+        const unsigned bal = __ballot_sync(FULL_MASK, i < n1 && m12[i] >= 0);
+        if (lane == 0) cc[ch] = __popc(bal);
+    }
+    __syncthreads();
+    const int per = (nch + nth - 1) / nth, c0 = tid * per;
+    int sum = 0;
+    for (int j = 0; j < per; j++) sum += (c0 + j < nch) ? cc[c0 + j] : 0;
+    int total;
+    int run = block_exclusive_scan(st, sum, &total);      // (barriers inside: every read of cc above is done before the writes below)
+    for (int j = 0; j < per; j++)
+        if (c0 + j < nch) {
+            const int c = cc[c0 + j];
+            cc[c0 + j] = run;
+            run += c;
+        }
+    __syncthreads();
+    return total;
+}
+
 __device__ void build_matched_lists(const SolveParams& prm, int pair, State& st, double* sortbuf, Feat& f, uint16_t* midx_p,
-                                    uint16_t* midx_l, int& n1p, int& n1l, size_t& out_p0, size_t& out_l0, long long& t_ph) {
-    const int tid = threadIdx.x, nth = blockDim.x;
+                                    uint16_t* midx_l, int& n1p, int& n1l, size_t& out_p0, size_t& out_l0, long long& t_ph,
+                                    const RecordSink& rs) {
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nth >> 5;
     const PlConfig& cfg = prm.cfg;
     if (prm.mode == 0) {
         // ---- A. finish the matching: merge partials, ratio test, mutual filter -> m12 (global) ----
@@ -1483,62 +1524,73 @@ __device__ void build_matched_lists(const SolveParams& prm, int pair, State& st,
         if (tid == 0) { st.tc[0] += clock64() - t_ph; }
         t_ph = clock64();
 
-        // ---- B. f2fTracking glue: ordered compaction of the matched features into SoA ----
+        // ---- B. f2fTracking glue: ordered compaction of the matched features into SoA (and, streamed solver, fp32 records) ----
         const FrameDev& P = prm.prev;
         const FrameDev& C = prm.curr;
+        int* cc = reinterpret_cast<int*>(sortbuf);
         const int a0 = P.pt_off[pair], b0 = C.pt_off[pair];
         n1p = P.pt_off[pair + 1] - a0;
         out_p0 = (size_t)a0;
-        {   // chunks of blockDim consecutive prev features: coalesced reads, output position = matches before it
-            int base = 0;
-            for (int i0 = 0; i0 < n1p; i0 += nth) {
-                const int i = i0 + tid;
+        {
+            const int np = compaction_plan(st, pp.m12, n1p, cc);
+            const int nch = (n1p + 31) >> 5;
+            for (int ch = warp; ch < nch; ch += nw) {
+                const int i = ch * 32 + lane;
                 const int i2 = (i < n1p) ? pp.m12[i] : -1;
-                int tot;
-                const int k = base + block_rank(st, i2 >= 0, &tot);
+                const unsigned bal = __ballot_sync(FULL_MASK, i2 >= 0);
                 if (i2 >= 0) {
+                    const int k = cc[ch] + __popc(bal & ((1u << lane) - 1u));
                     const double* p3 = P.pt_P + 3 * (size_t)(a0 + i);
-                    f.Px[k] = p3[0]; f.Py[k] = p3[1]; f.Pz[k] = p3[2];
                     const double* o2 = C.pt_pl + 2 * (size_t)(b0 + i2);    // pl_obs = curr pl (:148)
-                    f.pu[k] = o2[0]; f.pv[k] = o2[1];
-                    f.pss[k] = sqrt(P.pt_sigma2[a0 + i]);                  // PointFeature::safeCopy keeps sigma2
+                    const double x = p3[0], y = p3[1], z = p3[2], u = o2[0], v = o2[1];
+                    const double pss = sqrt(P.pt_sigma2[a0 + i]);          // PointFeature::safeCopy keeps sigma2
+                    f.Px[k] = x; f.Py[k] = y; f.Pz[k] = z;
+                    f.pu[k] = u; f.pv[k] = v;
+                    f.pss[k] = pss;
                     f.inl_p[k] = 1;
                     midx_p[k] = (uint16_t)i;
+                    if (rs.on) sink_point(rs, k, np, x, y, z, u, v, pss, true);
                 }
-                base += tot;
             }
-            f.np = base;
+            f.np = np;
+            __syncthreads();                 // cc is reused by the lines
         }
         const int c0 = P.ls_off[pair], d0 = C.ls_off[pair];
         n1l = P.ls_off[pair + 1] - c0;
         out_l0 = (size_t)c0;
         {
-            int base = 0;
-            for (int i0 = 0; i0 < n1l; i0 += nth) {
-                const int i = i0 + tid;
+            const int nl = compaction_plan(st, pl.m12, n1l, cc);
+            const int nch = (n1l + 31) >> 5;
+            for (int ch = warp; ch < nch; ch += nw) {
+                const int i = ch * 32 + lane;
                 const int i2 = (i < n1l) ? pl.m12[i] : -1;
-                int tot;
-                const int k = base + block_rank(st, i2 >= 0, &tot);
+                const unsigned bal = __ballot_sync(FULL_MASK, i2 >= 0);
                 if (i2 >= 0) {
+                    const int k = cc[ch] + __popc(bal & ((1u << lane) - 1u));
                     const size_t a = (size_t)(c0 + i);
-                    f.sX[k] = P.ls_sP[3 * a]; f.sY[k] = P.ls_sP[3 * a + 1]; f.sZ[k] = P.ls_sP[3 * a + 2];
-                    f.eX[k] = P.ls_eP[3 * a]; f.eY[k] = P.ls_eP[3 * a + 1]; f.eZ[k] = P.ls_eP[3 * a + 2];
+                    const double sx = P.ls_sP[3 * a], sy = P.ls_sP[3 * a + 1], sz = P.ls_sP[3 * a + 2];
+                    const double ex = P.ls_eP[3 * a], ey = P.ls_eP[3 * a + 1], ez = P.ls_eP[3 * a + 2];
                     const double* le = C.ls_le + 3 * (size_t)(d0 + i2);    // le_obs = curr le (:175)
-                    f.l0[k] = le[0]; f.l1[k] = le[1]; f.l2[k] = le[2];
-                    overlap_coeffs(P.ls_spl[2 * a], P.ls_spl[2 * a + 1], P.ls_epl[2 * a], P.ls_epl[2 * a + 1], f.oa[k],
-                                   f.ob[k], f.oc[k]);
+                    const double l0 = le[0], l1 = le[1], l2 = le[2];
+                    double oa, ob, oc;
+                    overlap_coeffs(P.ls_spl[2 * a], P.ls_spl[2 * a + 1], P.ls_epl[2 * a], P.ls_epl[2 * a + 1], oa, ob, oc);
                     // LineFeature::safeCopy -> ctor re-applies the level rule (src/stereoFeatures.cpp:117-135):
                     // sigma2' = 1 / (sigma2 * lsdScale^level)^2
                     double s2 = P.ls_sigma2[a];
                     const int level = P.ls_level ? P.ls_level[a] : 0;
                     for (int l = 0; l < level; l++) s2 *= cfg.lsd_scale;
-                    f.lss[k] = sqrt(1.0 / (s2 * s2));
+                    const double lss = sqrt(1.0 / (s2 * s2));
+                    f.sX[k] = sx; f.sY[k] = sy; f.sZ[k] = sz;
+                    f.eX[k] = ex; f.eY[k] = ey; f.eZ[k] = ez;
+                    f.l0[k] = l0; f.l1[k] = l1; f.l2[k] = l2;
+                    f.oa[k] = oa; f.ob[k] = ob; f.oc[k] = oc;
+                    f.lss[k] = lss;
                     f.inl_l[k] = 1;
                     midx_l[k] = (uint16_t)i;
+                    if (rs.on) sink_line(rs, k, nl, sx, sy, sz, ex, ey, ez, l0, l1, l2, oa, ob, oc, lss, true);
                 }
-                base += tot;
             }
-            f.nl = base;
+            f.nl = nl;
         }
         if (tid == 0) {
             st.n_inl_p = f.np;   // f2fTracking: n_inliers_* = list sizes (:126-128)
@@ -1554,20 +1606,31 @@ __device__ void build_matched_lists(const SolveParams& prm, int pair, State& st,
         out_l0 = (size_t)c0;
         for (int i = tid; i < f.np; i += nth) {
             const size_t a = (size_t)(a0 + i);
-            f.Px[i] = M.pt_P[3 * a]; f.Py[i] = M.pt_P[3 * a + 1]; f.Pz[i] = M.pt_P[3 * a + 2];
-            f.pu[i] = M.pt_pl_obs[2 * a]; f.pv[i] = M.pt_pl_obs[2 * a + 1];
-            f.pss[i] = sqrt(M.pt_sigma2[a]);
-            f.inl_p[i] = M.pt_inlier ? (M.pt_inlier[a] != 0) : 1;
+            const double x = M.pt_P[3 * a], y = M.pt_P[3 * a + 1], z = M.pt_P[3 * a + 2];
+            const double u = M.pt_pl_obs[2 * a], v = M.pt_pl_obs[2 * a + 1], pss = sqrt(M.pt_sigma2[a]);
+            const bool inl = M.pt_inlier ? (M.pt_inlier[a] != 0) : true;
+            f.Px[i] = x; f.Py[i] = y; f.Pz[i] = z;
+            f.pu[i] = u; f.pv[i] = v;
+            f.pss[i] = pss;
+            f.inl_p[i] = inl ? 1 : 0;
+            if (rs.on) sink_point(rs, i, f.np, x, y, z, u, v, pss, inl);
         }
         for (int i = tid; i < f.nl; i += nth) {
             const size_t a = (size_t)(c0 + i);
-            f.sX[i] = M.ls_sP[3 * a]; f.sY[i] = M.ls_sP[3 * a + 1]; f.sZ[i] = M.ls_sP[3 * a + 2];
-            f.eX[i] = M.ls_eP[3 * a]; f.eY[i] = M.ls_eP[3 * a + 1]; f.eZ[i] = M.ls_eP[3 * a + 2];
-            f.l0[i] = M.ls_le_obs[3 * a]; f.l1[i] = M.ls_le_obs[3 * a + 1]; f.l2[i] = M.ls_le_obs[3 * a + 2];
-            overlap_coeffs(M.ls_spl[2 * a], M.ls_spl[2 * a + 1], M.ls_epl[2 * a], M.ls_epl[2 * a + 1], f.oa[i], f.ob[i],
-                           f.oc[i]);
-            f.lss[i] = sqrt(M.ls_sigma2[a]);
-            f.inl_l[i] = M.ls_inlier ? (M.ls_inlier[a] != 0) : 1;
+            const double sx = M.ls_sP[3 * a], sy = M.ls_sP[3 * a + 1], sz = M.ls_sP[3 * a + 2];
+            const double ex = M.ls_eP[3 * a], ey = M.ls_eP[3 * a + 1], ez = M.ls_eP[3 * a + 2];
+            const double l0 = M.ls_le_obs[3 * a], l1 = M.ls_le_obs[3 * a + 1], l2 = M.ls_le_obs[3 * a + 2];
+            double oa, ob, oc;
+            overlap_coeffs(M.ls_spl[2 * a], M.ls_spl[2 * a + 1], M.ls_epl[2 * a], M.ls_epl[2 * a + 1], oa, ob, oc);
+            const double lss = sqrt(M.ls_sigma2[a]);
+            const bool inl = M.ls_inlier ? (M.ls_inlier[a] != 0) : true;
+            f.sX[i] = sx; f.sY[i] = sy; f.sZ[i] = sz;
+            f.eX[i] = ex; f.eY[i] = ey; f.eZ[i] = ez;
+            f.l0[i] = l0; f.l1[i] = l1; f.l2[i] = l2;
+            f.oa[i] = oa; f.ob[i] = ob; f.oc[i] = oc;
+            f.lss[i] = lss;
+            f.inl_l[i] = inl ? 1 : 0;
+            if (rs.on) sink_line(rs, i, f.nl, sx, sy, sz, ex, ey, ez, l0, l1, l2, oa, ob, oc, lss, inl);
         }
         // the reference sets n_inliers from the list sizes; explicit flags only matter to the evaluator
         if (tid == 0) {
@@ -1612,7 +1675,11 @@ __global__ void __launch_bounds__(K2_THREADS, 1) track_solve_kernel(const SolveP
     int n1p = 0, n1l = 0;        // prev-frame feature counts (mode 0) / list lengths (mode 1)
     size_t out_p0 = 0, out_l0 = 0;   // where this pair's inlier flags start
 
-    build_matched_lists(prm, pair, st, sortbuf, f, midx_p, midx_l, n1p, n1l, out_p0, out_l0, t_ph);
+    {
+        RecordSink none;
+        none.on = false;
+        build_matched_lists(prm, pair, st, sortbuf, f, midx_p, midx_l, n1p, n1l, out_p0, out_l0, t_ph, none);
+    }
     __syncthreads();
     if (tid == 0) { st.tc[1] += clock64() - t_ph; }
 
@@ -1782,35 +1849,6 @@ __device__ __forceinline__ StreamView stream_view(const SolveParams& prm, const 
     return v;
 }
 
-constexpr int SP_TILE = 512, SL_TILE = 256;   // records per 16 KB tile of gn_stream.cu (points / lines)
-
-// fp32 records of this problem from the fp64 lists (tile-planar: [cnt] float4 per plane; contents: gn_stream.cuh "records")
-__device__ void stream_pack_records(const Feat& f, const PlCamera& cam, const StreamBufs& sb, size_t slot_p, size_t slot_l) {
-    const int tid = threadIdx.x, nth = blockDim.x;
-    const GsCamD c = {cam.fx, cam.fy, cam.cx, cam.cy};
-    for (int j = tid; j < f.np; j += nth) {
-        const int t = j / SP_TILE, r = j % SP_TILE, cnt = min(SP_TILE, f.np - t * SP_TILE);
-        float4* base = sb.rec_pt + 2 * (slot_p + (size_t)t * SP_TILE);
-        gs_pack_point(c, f.Px[j], f.Py[j], f.Pz[j], f.pu[j], f.pv[j], f.pss[j], f.inl_p[j] != 0, base[r], base[cnt + r]);
-    }
-    for (int j = tid; j < f.nl; j += nth) {
-        const int t = j / SL_TILE, r = j % SL_TILE, cnt = min(SL_TILE, f.nl - t * SL_TILE);
-        float4* base = sb.rec_ls + 4 * (slot_l + (size_t)t * SL_TILE);
-        gs_pack_line(c, f.sX[j], f.sY[j], f.sZ[j], f.eX[j], f.eY[j], f.eZ[j], f.l0[j], f.l1[j], f.l2[j], f.oa[j], f.ob[j], f.oc[j],
-                     f.lss[j], f.inl_l[j] != 0, base[r], base[cnt + r], base[2 * cnt + r], base[3 * cnt + r]);
-    }
-}
-__device__ void stream_write_flags(const Feat& f, const StreamBufs& sb, size_t slot_p, size_t slot_l) {
-    const int tid = threadIdx.x, nth = blockDim.x;
-    for (int j = tid; j < f.np; j += nth) {
-        const int t = j / SP_TILE, r = j % SP_TILE, cnt = min(SP_TILE, f.np - t * SP_TILE);
-        reinterpret_cast<float*>(sb.rec_pt + 2 * (slot_p + (size_t)t * SP_TILE) + cnt + r)[2] = f.inl_p[j] ? 1.f : 0.f;
-    }
-    for (int j = tid; j < f.nl; j += nth) {
-        const int t = j / SL_TILE, r = j % SL_TILE, cnt = min(SL_TILE, f.nl - t * SL_TILE);
-        reinterpret_cast<float*>(sb.rec_ls + 4 * (slot_l + (size_t)t * SL_TILE) + cnt + r)[3] = f.inl_l[j] ? 1.f : 0.f;
-    }
-}
 
 // ---- S1: matching finish + list building + fp32 records + the head of optimizePose (:317-333) ----
 // 256-thread CTAs, up to three per SM: list building is a chain of short block-wide steps (see stream_outlier_kernel)
@@ -1827,9 +1865,15 @@ __global__ void __launch_bounds__(SPREP_THREADS, 3) stream_prepare_kernel(const 
     long long t_ph = clock64();
     int n1p = 0, n1l = 0;
     size_t out_p0 = 0, out_l0 = 0;
-    build_matched_lists(prm, pair, st, v.sortbuf, v.f, v.midx_p, v.midx_l, n1p, n1l, out_p0, out_l0, t_ph);
+    {
+        RecordSink rs;
+        rs.on = true;
+        rs.pt = sb.rec_pt + 2 * v.slot_p;
+        rs.ls = sb.rec_ls + 4 * v.slot_l;
+        rs.cam = GsCamD{prm.cam.fx, prm.cam.fy, prm.cam.cx, prm.cam.cy};
+        build_matched_lists(prm, pair, st, v.sortbuf, v.f, v.midx_p, v.midx_l, n1p, n1l, out_p0, out_l0, t_ph, rs);
+    }
     __syncthreads();
-    stream_pack_records(v.f, prm.cam, sb, v.slot_p, v.slot_l);
     const PlConfig& cfg = prm.cfg;
     const PlPrior* prior = prm.priors ? &prm.priors[pair] : nullptr;
     StreamCtl& c = sb.ctl[local];
@@ -2167,9 +2211,7 @@ __global__ void __launch_bounds__(SO_THREADS, 3) stream_outlier_kernel(const Sol
     v.f.nl = c.nl;
     const PlConfig& cfg = prm.cfg;
     const Cam cam = {prm.cam.fx, prm.cam.fy, prm.cam.cx, prm.cam.cy};
-    // the lists live in HBM here: every residual is formed ONCE (same fp64 arithmetic as K2's), then read back by the statistics
-    double* rp = sb.res_pt + v.slot_p;
-    double* rl = sb.res_ls + v.slot_l;
+    // the lists live in HBM here: every residual is formed ONCE (same fp64 arithmetic as K2's), straight into shared memory
     if (warp == 0) {
         if (lane == 0) {
             for (int i = 0; i < 8; i++) st.tc[i] = 0;
@@ -2181,31 +2223,44 @@ __global__ void __launch_bounds__(SO_THREADS, 3) stream_outlier_kernel(const Sol
         __syncwarp();
         const bool ok = warp_is_good_solution(st.DT, st.cov, c.err, nullptr);
         if (lane == 0) st.ctrl = ok ? 1 : 0;
-    } else {
-        const Feat& f = v.f;
-        double DTr[12];                       // pose in registers: the loops below are pure streaming arithmetic
+    }
+    double DTr[12];                           // pose in registers: the residual loops are pure streaming arithmetic
 #pragma unroll
-        for (int i = 0; i < 12; i++) DTr[i] = sb.DT[(size_t)local * 16 + i];
+    for (int i = 0; i < 12; i++) DTr[i] = sb.DT[(size_t)local * 16 + i];
+    const Feat& f = v.f;
+    auto res_pt = [&](int i) -> double {
+        double X, Y, Z, iz, dx, dy;
+        return point_residual(f, i, DTr, cam, X, Y, Z, iz, dx, dy) * f.pss[i];
+    };
+    auto res_ls = [&](int i) -> double {
+        LineRes r;
+        return line_residual(f, i, DTr, cam, r) * f.lss[i];
+    };
+    const bool pts = cfg.has_points && f.np > 0;
+    if (warp != 0 && pts) {                   // the other warps already form the point residuals the gate will (almost always) let through
         const int wt = tid - 32, nwt = SO_THREADS - 32;
-#pragma unroll 2
-        for (int i = wt; i < f.np; i += nwt) {
-            double X, Y, Z, iz, dx, dy;
-            rp[i] = point_residual(f, i, DTr, cam, X, Y, Z, iz, dx, dy) * f.pss[i];
-        }
-#pragma unroll 2
-        for (int i = wt; i < f.nl; i += nwt) {
-            LineRes r;
-            rl[i] = line_residual(f, i, DTr, cam, r) * f.lss[i];
-        }
+#pragma unroll 4
+        for (int i = wt; i < f.np; i += nwt) v.sortbuf[i] = res_pt(i);
     }
     __syncthreads();
     if (!st.ctrl) {                     // stage 1 rejected: the robust fallback (:357-359) is K2's job
         if (tid == 0) c.delegate = 1;
         return;
     }
-    remove_outliers_select(v.f, st, v.sortbuf, sel, cfg, [&](int i) -> double { return rp[i]; }, [&](int i) -> double { return rl[i]; });
+    float4* rec_p = sb.rec_pt + 2 * v.slot_p;
+    float4* rec_l = sb.rec_ls + 4 * v.slot_l;
+    const int np = f.np, nl = f.nl;
+    remove_outliers_select(
+        f, st, v.sortbuf, sel, cfg, pts, res_pt, res_ls,
+        [&](int j) {   // the inlier flag inside the fp32 record (gn_stream.cuh "records")
+            const int t = j / GS_PT_TILE, r = j % GS_PT_TILE, cnt = min(GS_PT_TILE, np - t * GS_PT_TILE);
+            reinterpret_cast<float*>(rec_p + 2 * (size_t)t * GS_PT_TILE + cnt + r)[2] = 0.f;
+        },
+        [&](int j) {
+            const int t = j / GS_LS_TILE, r = j % GS_LS_TILE, cnt = min(GS_LS_TILE, nl - t * GS_LS_TILE);
+            reinterpret_cast<float*>(rec_l + 4 * (size_t)t * GS_LS_TILE + cnt + r)[3] = 0.f;
+        });
     __syncthreads();
-    stream_write_flags(v.f, sb, v.slot_p, v.slot_l);
     if (tid == 0) {
         c.iters1 = c.iters;
         c.n_inl_p = st.n_inl_p;
@@ -2282,8 +2337,6 @@ __global__ void __launch_bounds__(256) stream_finalize_kernel(const SolveParams 
 }
 
 }  // namespace
-
-size_t stream_partial_doubles(int B, int slices) { return (size_t)B * slices * gn_stream_partials_per_slice() * (ACC_N + 1); }
 
 cudaError_t launch_stream_solve(const SolveParams& prm_in, int n_pairs, const StreamBufs& sb, cudaStream_t stream, int* launches,
                                 cudaEvent_t lists_done) {
