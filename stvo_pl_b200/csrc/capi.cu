@@ -573,7 +573,7 @@ int ws_launch_match(PlContext* ctx, Workspace& ws, int p0, int p1, cudaStream_t 
     return 0;
 }
 
-int ws_launch_solve(PlContext* ctx, Workspace& ws, int p0, int p1, bool have_level, cudaStream_t s, cudaEvent_t lists_done = nullptr) {
+int ws_launch_solve(PlContext* ctx, Workspace& ws, int p0, int p1, bool have_level, cudaStream_t s, cudaEvent_t* marks = nullptr) {
     if (p1 <= p0) return 0;
     SolveParams prm{};
     prm.cam = ws.cam;
@@ -606,11 +606,12 @@ int ws_launch_solve(PlContext* ctx, Workspace& ws, int p0, int p1, bool have_lev
         prm.feat_scratch = ws.d_feat.as<double>() + (size_t)p0 * ws.feat_stride;
         prm.feat_in_smem = 0;
         int nl = 0;
-        CK(ctx, launch_stream_solve(prm, p1 - p0, stream_bufs_at(sb, p0), s, &nl, lists_done));
+        CK(ctx, launch_stream_solve(prm, p1 - p0, stream_bufs_at(sb, p0), s, &nl, marks));
         ctx->launches += nl;
         return 0;
     }
-    if (lists_done) CK(ctx, cudaEventRecord(lists_done, s));   // fused kernel: the list building is inside K2
+    if (marks)   // fused kernel: list building, both GN stages and the outlier pass are inside K2
+        for (int k = 0; k < 4; ++k) CK(ctx, cudaEventRecord(marks[k], s));
     CK(ctx, launch_track_solve(prm, p1 - p0, s));
     ctx->launches++;
     return 0;
@@ -1893,14 +1894,16 @@ int plstvo_batch_kernel_times(PlContext* ctx, PlDeviceBatch* db, int iters, doub
     return 0;
 }
 
-int plstvo_batch_stage_times(PlContext* ctx, PlDeviceBatch* db, int iters, double ms[5], int32_t counts[4]) {
+int plstvo_batch_stage_times(PlContext* ctx, PlDeviceBatch* db, int iters, double ms[8], int32_t counts[4]) {
     if (!ctx || !db || iters <= 0 || !ms) return PLSTVO_E_INVALID;
     LOCK(ctx);
     CK(ctx, cudaSetDevice(ctx->device));
     Workspace& ws = db->ws;
-    cudaEvent_t ev[6];
+    // events: 0 start, 1 expand done, 2 distance done, 3 match done, 4 lists done, 5 GN stage 1 done, 6 outlier pass done,
+    // 7 GN stage 2 done, 8 end
+    cudaEvent_t ev[9];
     for (auto& e : ev) CK(ctx, cudaEventCreate(&e));
-    double acc[5] = {0, 0, 0, 0, 0};
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < iters; ++i) {
         CK(ctx, cudaEventRecord(ev[0], ctx->s_main));
         if (!ws.use_tc) CK(ctx, cudaEventRecord(ev[1], ctx->s_main));   // the integer form is one kernel: reported in slot 1
@@ -1908,18 +1911,22 @@ int plstvo_batch_stage_times(PlContext* ctx, PlDeviceBatch* db, int iters, doubl
         if (rc) return rc;
         if (!ws.use_tc) CK(ctx, cudaEventRecord(ev[2], ctx->s_main));
         CK(ctx, cudaEventRecord(ev[3], ctx->s_main));
-        rc = ws_launch_solve(ctx, ws, 0, ws.B, ws.have_level, ctx->s_main, ev[4]);
+        rc = ws_launch_solve(ctx, ws, 0, ws.B, ws.have_level, ctx->s_main, &ev[4]);
         if (rc) return rc;
-        CK(ctx, cudaEventRecord(ev[5], ctx->s_main));
-        CK(ctx, cudaEventSynchronize(ev[5]));
-        for (int k = 0; k < 5; ++k) {
+        CK(ctx, cudaEventRecord(ev[8], ctx->s_main));
+        CK(ctx, cudaEventSynchronize(ev[8]));
+        auto span = [&](int a, int b, double& out) -> int {
             float t = 0.f;
-            CK(ctx, cudaEventElapsedTime(&t, ev[k], ev[k + 1]));
-            acc[k] += t;
-        }
+            CK(ctx, cudaEventElapsedTime(&t, ev[a], ev[b]));
+            out += t;
+            return 0;
+        };
+        for (int k = 0; k < 4; ++k)
+            if ((rc = span(k, k + 1, acc[k]))) return rc;
+        if ((rc = span(4, 8, acc[4])) || (rc = span(4, 5, acc[5])) || (rc = span(5, 6, acc[6])) || (rc = span(6, 7, acc[7]))) return rc;
     }
     for (auto& e : ev) cudaEventDestroy(e);
-    for (int k = 0; k < 5; ++k) ms[k] = acc[k] / iters;
+    for (int k = 0; k < 8; ++k) ms[k] = acc[k] / iters;
     if (counts) {
         int delegated = 0;   // streamed solver: problems it handed to the fp64 kernel in the last pass (its only_if list)
         if (ws.use_stream && ws.B > 0) {

@@ -133,7 +133,7 @@ struct StreamBufs {
 };
 // prm.feat_scratch must hold k2_feat_stride() doubles per pair; prm.feat_in_smem must be 0
 cudaError_t launch_stream_solve(const SolveParams& prm, int n_pairs, const StreamBufs& sb, cudaStream_t stream, int* launches,
-                                cudaEvent_t lists_done = nullptr);
+                                cudaEvent_t* marks = nullptr);   // marks: 4 events (see solve.cu), instrumentation only
 
 size_t k2_smem_bytes(int cap_pt, int cap_ls, int sort_cap, bool feat_in_smem);
 size_t k2_feat_stride(int cap_pt, int cap_ls);   // doubles of global feature scratch per pair

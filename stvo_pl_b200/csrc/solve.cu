@@ -2339,7 +2339,7 @@ __global__ void __launch_bounds__(256) stream_finalize_kernel(const SolveParams 
 }  // namespace
 
 cudaError_t launch_stream_solve(const SolveParams& prm_in, int n_pairs, const StreamBufs& sb, cudaStream_t stream, int* launches,
-                                cudaEvent_t lists_done) {
+                                cudaEvent_t* marks) {
     if (n_pairs <= 0) return cudaSuccess;
     SolveParams prm = prm_in;
     prm.feat_in_smem = 0;
@@ -2354,7 +2354,8 @@ cudaError_t launch_stream_solve(const SolveParams& prm_in, int n_pairs, const St
     int nl = 0;
     stream_prepare_kernel<<<n_pairs, SPREP_THREADS, smem_prep, stream>>>(prm, sb);
     ++nl;
-    if (lists_done) cudaEventRecord(lists_done, stream);   // instrumentation: list building | optimizePose
+    // instrumentation (optional): lists built | GN stage 1 done | outlier pass done | GN stage 2 done
+    if (marks) cudaEventRecord(marks[0], stream);
     const int32_t* off_p = prm.mode == 0 ? prm.prev.pt_off + prm.first_pair : prm.matched.pt_off + prm.first_pair;
     const int32_t* off_l = prm.mode == 0 ? prm.prev.ls_off + prm.first_pair : prm.matched.ls_off + prm.first_pair;
     static size_t conf_c[64] = {};
@@ -2373,8 +2374,11 @@ cudaError_t launch_stream_solve(const SolveParams& prm_in, int n_pairs, const St
         return cudaGetLastError();
     };
     if ((e = gn(prm.cfg.max_iters)) != cudaSuccess) return e;
+    if (marks) cudaEventRecord(marks[1], stream);
     stream_outlier_kernel<<<n_pairs, SO_THREADS, smem_out, stream>>>(prm, sb);
+    if (marks) cudaEventRecord(marks[2], stream);
     if ((e = gn(prm.cfg.max_iters_ref)) != cudaSuccess) return e;
+    if (marks) cudaEventRecord(marks[3], stream);
     // the activity array doubles as K2's only_if list once the sweeps are over
     stream_finalize_kernel<<<n_pairs, 256, 0, stream>>>(prm, sb, sb.active);
     nl += 2;

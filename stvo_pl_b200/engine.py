@@ -194,11 +194,12 @@ class DeviceBatch:
         return dict(ms_match=float(a[0]), ms_solve=float(b[0]), n_tiles=int(nt[0]), n_pairs=int(npairs[0]))
 
     def stage_times(self, iters: int = 3):
-        ms, cnt = np.zeros(5), np.zeros(4, np.int32)
+        ms, cnt = np.zeros(8), np.zeros(4, np.int32)
         self.eng._ck(self.eng.lib.plstvo_batch_stage_times(self.eng.ctx, self.handle, iters, ms.ctypes.data_as(T.c_double_p),
                                                            cnt.ctypes.data_as(T.c_int32_p)))
         return dict(ms_expand=float(ms[0]), ms_distance=float(ms[1]), ms_resolve=float(ms[2]), ms_lists=float(ms[3]),
-                    ms_solve=float(ms[3] + ms[4]), ms_optimize_pose=float(ms[4]),
+                    ms_solve=float(ms[3] + ms[4]), ms_optimize_pose=float(ms[4]), ms_gn_stage1=float(ms[5]),
+                    ms_outliers=float(ms[6]), ms_gn_stage2=float(ms[7]),
                     tensor_core_form=bool(cnt[0] & 1), streamed_solver=bool(cnt[0] & 2), delegated_to_fp64=int(cnt[0] >> 8), n_items=int(cnt[1]),
                     n_problems=int(cnt[2]), n_pairs=int(cnt[3]))
 
