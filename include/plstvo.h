@@ -276,7 +276,10 @@ int plstvo_track_stereo_sequence(PlContext* ctx, const PlCamera* cam, const PlCo
 
 /* Streaming forms: enqueue and return a ticket (0 / 1) like plstvo_track_batch_async; results / n_stereo are valid after
  * plstvo_wait(ctx, ticket).  Two batches may be in flight, so the next batch's uploads run under this batch's kernels; inputs
- * must stay untouched (and should be pinned, plstvo_host_alloc) until the wait returns. */
+ * must stay untouched (and should be pinned, plstvo_host_alloc) until the wait returns.
+ * NOT fully asynchronous: the call itself blocks (holding the context's lock) until the stereo step of this batch has run on
+ * the device, because the number of lifted stereo features per frame — a result of that step — sizes the tracking plan that
+ * is built on the host; what overlaps with the caller (and with the other ticket) is the tracking half and the downloads. */
 int plstvo_track_stereo_batch_async(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg, const PlStereoMatchConfig* mcfg,
                                     const PlStereoConfig* scfg, const PlStereoFeatures* prev, const PlStereoFeatures* curr,
                                     const PlPrior* priors, PlPoseResult* results, int32_t* n_stereo);

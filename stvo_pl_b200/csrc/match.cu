@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(256) match_finalize_kernel(const MatchProblem*
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
     const MatchProblem pr = problems[blockIdx.x];
-    int c = match_finalize_block(pr, reinterpret_cast<int32_t*>(smem));
+    int c = match_finalize_block(pr, reinterpret_cast<uint16_t*>(smem));
     for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_count, c);
     __syncthreads();
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(256) match_finalize_kernel(const MatchProblem*
 cudaError_t launch_match_finalize(const MatchProblem* problems, int n_problems, int max_n2, int32_t* counts,
                                   cudaStream_t stream) {
     if (n_problems <= 0) return cudaSuccess;
-    const size_t smem = (size_t)(max_n2 > 0 ? max_n2 : 1) * sizeof(int32_t);
+    const size_t smem = ((size_t)(max_n2 > 0 ? max_n2 : 1) * sizeof(uint16_t) + 15) / 16 * 16;
     static size_t configured[64] = {};
     if (smem > 48 * 1024) {
         cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(match_finalize_kernel), smem, configured);

@@ -28,6 +28,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "match_finalize.cuh"
 #include "match_tc.cuh"
 
 namespace plstvo {
@@ -608,7 +609,11 @@ __global__ void __launch_bounds__(256) tc_resolve_kernel(const MatchProblem* __r
                 const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(mp.d2 + (size_t)y * 32)),
                             a1 = __ldg(reinterpret_cast<const uint4*>(mp.d2 + (size_t)y * 32) + 1);
                 idx = -1;
-                if (d1 != d2) {   // unique best: one of the queries the tagged epilogue thread saw (row = tag mod 128)
+                if (d1 != d2 && mp.n1 <= (int)M21_DIST) {
+                    // unique best: WHICH query it is does not matter to the mutual filter (match_finalize.cuh: a query whose
+                    // nearest train is y at distance d1 is that query) — no candidate is re-evaluated
+                    idx = (int)KEY_IDX_UNRESOLVED;
+                } else if (d1 != d2) {   // (frames beyond 65024 rows) one of the queries the tagged epilogue thread saw (row = tag mod 128)
                     const int t = (int)((e >> 18) & 127u);
                     for (int i = 0; i < nxt && idx < 0; ++i) {
                         const int j = t + i * TC_ROWS;

@@ -1517,9 +1517,9 @@ __device__ void build_matched_lists(const SolveParams& prm, int pair, State& st,
     if (prm.mode == 0) {
         // ---- A. finish the matching: merge partials, ratio test, mutual filter -> m12 (global) ----
         const MatchProblem pp = prm.problems[2 * pair], pl = prm.problems[2 * pair + 1];
-        match_finalize_block(pp, reinterpret_cast<int32_t*>(sortbuf));
+        match_finalize_block(pp, reinterpret_cast<uint16_t*>(sortbuf));
         __syncthreads();
-        match_finalize_block(pl, reinterpret_cast<int32_t*>(sortbuf));
+        match_finalize_block(pl, reinterpret_cast<uint16_t*>(sortbuf));
         __syncthreads();
         if (tid == 0) { st.tc[0] += clock64() - t_ph; }
         t_ph = clock64();

@@ -51,6 +51,22 @@ def test_match_vs_oracle(engine, oracle, n1, n2, mode):
             assert n == n_ref
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("n1,n2", [(300, 65535), (65535, 300), (20000, 20000)])
+def test_match_at_the_feature_limit(engine, oracle, n1, n2):
+    """Matching-only calls take any frame up to PLSTVO_MAX_FEATURES = 65535 rows per side (the per-pair solver's shared-memory
+    limits do not apply to them; the mutual filter's scratch holds 16-bit indices so that 65535 rows fit one CTA)."""
+    rng = np.random.default_rng(n1 + 3 * n2)
+    d1, d2 = rng.integers(0, 256, (n1, 32), dtype=np.uint8), rng.integers(0, 256, (n2, 32), dtype=np.uint8)
+    k = min(n1, n2, 5000)
+    pick1, pick2 = rng.permutation(n1)[:k], rng.permutation(n2)[:k]
+    d2[pick2] = d1[pick1] ^ (rng.random((k, 32)) < 0.03).astype(np.uint8)     # true correspondences somewhere in the frames
+    n_ref, ref = oracle.match(d1, d2, 0.75, True, threads=True) if n1 * n2 > 10**8 else oracle.match(d1, d2, 0.75, True)
+    n, m = engine.match(d1, d2, 0.75, True)
+    np.testing.assert_array_equal(m, ref)
+    assert n == n_ref and n > k // 2
+
+
 def test_match_batch_ragged(engine, oracle):
     """Several problems of different sizes in one launch, including empty sides."""
     rng = np.random.default_rng(5)

@@ -4,6 +4,8 @@ launch lists (per-kernel totals and shares, and the kernel sequence of one step)
 top source lines of each capture by stall samples, the traffic / pipe JSONs bench.py reads, and the bench JSON lines.
 
 usage: python tools/summarise_profiles.py r2a
+(tools/gpu_profile.sh runs it on the GPU box with PROF_OUT=gpurun_out/profiles: the .ncu-rep files of a full pass exceed what
+gpurun copies back, so only the summaries and two of the reports travel; copy gpurun_out/profiles/* to profiles/ afterwards)
 """
 import collections
 import csv
@@ -15,7 +17,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
-PROF = os.path.join(ROOT, "profiles")
+PROF = os.environ.get("PROF_OUT") or os.path.join(ROOT, "profiles")   # PROF_OUT: summarise on the GPU box into gpurun_out/
 
 KEEP = [
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
