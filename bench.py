@@ -536,8 +536,10 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8/f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[ACTIVE][3], "pairs_per_gpu": B, "global_pairs_per_step": world * B,
+        "dtype": ("u8 matching (as e4m3 +-1 on the tensor cores, f16 accumulators: exact); solve: f32 per feature, f64 sums / 6x6 algebra / "
+                  "SE(3) / outlier statistics (streamed solver)") if st["streamed_solver"] else "u8 matching (e4m3 +-1, f16 accumulators: exact); solve: f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOADS[ACTIVE][3], "pairs_per_gpu": B, "solver": "streamed" if st["streamed_solver"] else "K2 (fp64)", "global_pairs_per_step": world * B,
                    "parallelism": f"independent pairs sharded over {world} GPU(s), no collective",
                    "l2": f"inputs larger than L2: {(h2d + kt['n_tiles'] * 0) / 1e6:.0f} MB of inputs + "
                          f"{B * 140000 / 1e6:.0f} MB of tile partials per pass vs 126 MB L2",
@@ -697,6 +699,8 @@ def c5_pipeline(eng, B, steps=3, distinct=128):
                          "ms_optimize_pose": st["ms_optimize_pose"], "ms_outliers": st["ms_outliers"],
                          "frac_of_optimize_pose": alg / solve_s / 1e9 / peak,
                          "frac_including_list_building": alg / ((st["ms_lists"] + st["ms_optimize_pose"]) * 1e-3) / 1e9 / peak,
+                         "traffic_note": "DRAM traffic below the algorithmic bytes = L2 reuse: the records of one 256-pair chunk (98 MB) stay "
+                                         "in the 126 MB L2 from one iteration to the next",
                          "note": "bytes = evaluations that actually ran x record bytes (32 B / point, 64 B / line); time = the two "
                                  "gn_loop_stream_kernel launches (CUDA events around each).  frac_of_optimize_pose divides the same bytes "
                                  "by everything after matched_pt / matched_ls exist (GN loops, gate + removeOutliers, finalisation); "
