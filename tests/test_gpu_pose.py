@@ -394,6 +394,21 @@ def test_explicit_lists_c5_size(engine, oracle):
         pass
 
 
+def test_streamed_solver_is_bit_reproducible(engine):
+    """The streamed solver on lists longer than its TMA ring (24 record tiles per problem through 6 stages: every stage is reused
+    four times per iteration) gives identical bytes run after run: fixed summation order, and no stage is overwritten before its
+    readers are done (a race there would show up as run-to-run differences)."""
+    cfg = T.kitti_config()
+    mb, Ts, cam = synth.make_matched_batch("hd", 6)
+    first = None
+    for _ in range(4):
+        res, ip, il = engine.optimize_pose(cam, cfg, mb)
+        blob = res.tobytes() + ip.tobytes() + il.tobytes()
+        if first is None:
+            first = blob
+        assert blob == first
+
+
 def test_two_contexts_on_two_devices_in_one_process(oracle):
     """One context per GPU inside a single process (device arenas and kernel attributes are per context / per device):
     the same batch through both devices, interleaved, gives identical bytes.  Skipped on single-GPU boxes."""

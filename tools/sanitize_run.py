@@ -18,6 +18,9 @@ cfg.solver_mode = 1
 eng.track_batch(cam, cfg, prev, curr)
 eng.gn_eval_stream(cam, cfg, m, Tgt, iters=1)
 eng.match(prev.pdesc, curr.pdesc, 0.75)
+# the streamed solver's long-list paths (several tiles per problem: records streamed, not resident) and an explicit list with flags
+mb_hd, T_hd, cam_hd = synth.make_matched_batch("hd", 2)
+eng.optimize_pose(cam_hd, T.kitti_config(), mb_hd)
 q_cell, d1, t_cell, d2 = SS.make_stereo_points(500, 480, seed=1)
 eng.match_grid_points([0, 500], q_cell, d1, [0, 480], t_cell, d2, T.PlGridWindow(10, 0, 0, 0), 0.75)
 q_line, d1, t_line, t_dir, d2 = SS.make_stereo_lines(150, 160, seed=2)
