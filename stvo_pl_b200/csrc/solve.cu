@@ -800,9 +800,7 @@ __device__ __forceinline__ int pow2_ceil(int n) {
     return m;
 }
 
-// ---- k-th smallest of val(0 .. m) by an 8 x 8-bit radix select (block-wide, exact, order-independent) -----------------------
-// Replaces full sorts where only one order statistic is wanted (the median and the MAD of src/auxiliar.cpp:387-460).
-// `hist`: 260 ints of shared scratch.  Stops refining as soon as a single value remains under the decided prefix.  Doubles are mapped to keys whose unsigned order is the numeric order.
+// ---- keys whose unsigned order is the numeric order of the doubles they come from ----
 __device__ __forceinline__ unsigned long long select_key(double x) {
     const unsigned long long b = (unsigned long long)__double_as_longlong(x);
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
@@ -810,82 +808,13 @@ __device__ __forceinline__ unsigned long long select_key(double x) {
 __device__ __forceinline__ double select_unkey(unsigned long long k) {
     return __longlong_as_double((long long)((k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k));
 }
-template <class Val>
-__device__ double block_select_kth(int* hist, int m, int k, Val val) {
-    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31;
-    unsigned long long prefix = 0;
-    int kk = k;
-    for (int pass = 7; pass >= 0; --pass) {
-        for (int b = tid; b < 256; b += nth) hist[b] = 0;
-        __syncthreads();
-        const int sh = 8 * pass;
-        for (int i0 = 0; i0 < m; i0 += nth) {   // uniform trip count: the aggregation below is warp-collective
-            const int i = i0 + tid;
-            bool take = false;
-            unsigned bin = 0;
-            if (i < m) {
-                const unsigned long long key = select_key(val(i));
-                take = (pass == 7) || ((key >> (sh + 8)) == (prefix >> (sh + 8)));
-                bin = (unsigned)(key >> sh) & 255u;
-            }
-            if (pass >= 6) {   // sign / exponent bytes: nearly all keys alike -> one shared-memory atomic per distinct bin and warp
-                const unsigned act = __ballot_sync(FULL_MASK, take);
-                if (take) {
-                    const unsigned peers = __match_any_sync(act, bin);
-                    if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&hist[bin], __popc(peers));
-                }
-            } else if (take) {   // mantissa bytes: keys spread over the bins, plain atomics are cheaper
-                atomicAdd(&hist[bin], 1);
-            }
-        }
-        __syncthreads();
-        if (tid < 32) {   // the bin that holds rank kk: 8 bins per lane, warp scan, then a short walk
-            int c[8], s = 0;
-#pragma unroll
-            for (int j = 0; j < 8; j++) { c[j] = hist[8 * lane + j]; s += c[j]; }
-            int inc = s;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(FULL_MASK, inc, o);
-                if (lane >= o) inc += t;
-            }
-            const unsigned over = __ballot_sync(FULL_MASK, inc > kk);
-            const int fl = over ? (__ffs(over) - 1) : 31;
-            if (lane == fl) {
-                int before = inc - s, b = 0;
-                while (b < 7 && before + c[b] <= kk) { before += c[b]; b++; }
-                hist[256] = 8 * lane + b;
-                hist[257] = kk - before;
-                hist[258] = c[b];
-            }
-        }
-        __syncthreads();
-        prefix |= (unsigned long long)(unsigned)hist[256] << sh;
-        kk = hist[257];
-        const int in_bin = hist[258];
-        __syncthreads();
-        if (in_bin == 1 && pass > 0) {   // one value left under this prefix: fetch it instead of refining byte by byte
-            for (int i = tid; i < m; i += nth) {
-                const unsigned long long key = select_key(val(i));
-                if ((key >> sh) == (prefix >> sh)) {
-                    hist[256] = (int)(unsigned)(key & 0xFFFFFFFFull);
-                    hist[257] = (int)(unsigned)(key >> 32);
-                }
-            }
-            __syncthreads();
-            prefix = ((unsigned long long)(unsigned)hist[257] << 32) | (unsigned long long)(unsigned)hist[256];
-            __syncthreads();
-            break;
-        }
-    }
-    return select_unkey(prefix);
-}
-
-// ---- the same order statistic with 11-bit digits, for the streamed solver's long lists ------------------------------------
+// ---- k-th smallest of val(0 .. m) by radix selection with 11-bit digits, for the streamed solver's lists ------------------------------------
 // Keys of one list share their sign / exponent bits, so the digits start below the common prefix of the smallest and the
 // largest key; one 2048-bin histogram then usually leaves a handful of candidates around rank k, which are ranked against
-// each other directly.  Typical cost: one min / max reduction + one histogram pass + one gather (the byte-wise form above
-// needs three to four passes and a fetch).  Scratch: SEL_BINS ints + SEL_CAND keys + 8 ints of shared memory.
+// each other directly.  Typical cost: one min / max reduction + one histogram pass + one gather (a byte-wise radix selection
+// needs three to four passes and a fetch).  K2 keeps its bitonic sort: at 2000 entries and 512 threads the sort (register /
+// shuffle strides) is as fast as four selections, and for the robust solver's per-iteration MAD at 1000 entries it is faster
+// (measured: C3 K2 1.87 ms with the sort, 2.04 ms with selections).  Scratch: SEL_BINS ints + SEL_CAND keys + 8 ints of shared memory.
 constexpr int SEL_BITS = 11, SEL_BINS = 1 << SEL_BITS, SEL_CAND = 256;
 struct SelScratch {
     int* hist;                     // [SEL_BINS]
