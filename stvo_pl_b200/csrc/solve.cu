@@ -306,7 +306,8 @@ __device__ void warp_qr6_solve(const double* Hs /* shared, row-major symmetric *
 // Cholesky (6 rsqrt on the critical path instead of the QR's pivot searches, square roots and divisions) gives the
 // same x to rounding.  Returns false — and the caller runs the column-pivoted QR, which also handles rank deficiency
 // like Eigen — when a pivot is not safely positive.
-__device__ bool warp_chol6_solve(const double* Hs, const double* gs, double* x) {
+// `lad` (optional): log|det H| = sum of the logs of the Cholesky pivots, what the robust loop tests the sign of (:455-459).
+__device__ bool warp_chol6_solve(const double* Hs, const double* gs, double* x, double* lad = nullptr) {
     const int lane = threadIdx.x & 31;
     const int lj = (lane < 6) ? lane : 0;
     double a[6];
@@ -319,11 +320,15 @@ __device__ bool warp_chol6_solve(const double* Hs, const double* gs, double* x) 
     dmax = shfl(dmax, 0);
     const double thr = dmax * 1e-12;
     bool ok = (dmax > 0.0) && (dmax == dmax) && (dmax < 1e300);
-    double rinv[6];
+    double rinv[6], dprod = 1.0, dlog = 0.0;   // product of the pivots, rescaled through dlog when it leaves [1e-100, 1e100]
 #pragma unroll
     for (int k = 0; k < 6; k++) {
         const double d = shfl(a[k], k);
         ok = ok && (d > thr);
+        if (lad) {
+            dprod *= fmax(d, 1e-300);
+            if (dprod > 1e100 || dprod < 1e-100) { dlog += log(dprod); dprod = 1.0; }
+        }
         const double r = rsqrt(fmax(d, 1e-300));
         rinv[k] = r;
         double lk[6];
@@ -354,6 +359,7 @@ __device__ bool warp_chol6_solve(const double* Hs, const double* gs, double* x) 
         for (int j = k + 1; j < 6; j++) s -= shfl(a[j], k) * x[j];
         x[k] = s * rinv[k];
     }
+    if (lad) *lad = dlog + log(dprod);
     return ok;
 }
 
@@ -1121,7 +1127,9 @@ __device__ void gauss_newton(const Feat& f, State& st, double* sortbuf, const Ca
                 if ((fabs(err - err_prev) < cfg.min_error_change) || (err < cfg.min_error)) {
                     ctrl = 1;
                 } else {
-                    warp_qr6_solve<true>(st.H, &st.acc[21], inc, lad);
+                    // SPD normal equations (the regular case): Cholesky gives the increment and log|det| for a tenth of the
+                    // pivoted QR's cycles; anything else goes through the QR like the reference
+                    if (!warp_chol6_solve(st.H, &st.acc[21], inc, &lad)) warp_qr6_solve<true>(st.H, &st.acc[21], inc, lad);
                     if (lad < 0.0) {
                         good = false;
                         ctrl = 1;

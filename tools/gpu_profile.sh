@@ -47,9 +47,10 @@ cap gn_loop_c5 gn_loop_stream 5 python bench.py --workload c5 --steps 3 --warmup
 cap stream_outlier_c5 stream_outlier 2 python bench.py --workload c5 --steps 3 --warmup 2
 cap stream_prepare_c5 stream_prepare 2 python bench.py --workload c5 --steps 3 --warmup 2
 cap tc_hamming_c5 tc_hamming 2 python bench.py --workload c5 --steps 3 --warmup 2
+cap gn_eval gn_eval_stream 2 python bench.py --workload c5_sweep
 # summarise here (ncu is on the box), keep two reports for reading at home, drop the rest (gpurun copies back <= 64 MiB)
 PROF_OUT=gpurun_out/profiles python tools/summarise_profiles.py ${TAG} > gpurun_out/summarise_${TAG}.log 2>&1
 mkdir -p gpurun_out/keep
-mv gpurun_out/prof_tc_hamming_${TAG}.ncu-rep gpurun_out/prof_gn_loop_c5_${TAG}.ncu-rep gpurun_out/prof_gn_loop_${TAG}.ncu-rep gpurun_out/keep/ 2>/dev/null
+mv gpurun_out/prof_tc_hamming_${TAG}.ncu-rep gpurun_out/prof_gn_loop_c5_${TAG}.ncu-rep gpurun_out/keep/ 2>/dev/null
 rm -f gpurun_out/prof_*_${TAG}.ncu-rep
 du -sh gpurun_out; ls gpurun_out/profiles | head -40

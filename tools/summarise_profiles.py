@@ -44,6 +44,7 @@ CAPTURES = [
     ("gn_loop_c5", "S2 gn_loop_stream_kernel, a stage-2 launch (C5: records streamed from HBM)"),
     ("stream_outlier_c5", "S3 stream_outlier_kernel (C5)"), ("stream_prepare_c5", "S1 stream_prepare_kernel (C5)"),
     ("tc_hamming_c5", "K1b tc_hamming_kernel (C5)"),
+    ("gn_eval", "stand-alone sweep kernel gn_eval_stream_kernel (--workload c5_sweep: 1024 C5 problems per sweep)"),
 ]
 
 
@@ -183,6 +184,10 @@ def main():
             k["pipes"] = {"kernel": "tc_hamming_kernel", "alu_pipe_pct": t.get("alu_pipe_pct"), "fma_pipe_pct": t.get("fma_pipe_pct"),
                           "tensor_pipe_pct": t.get("tensor_pipe_pct"), "issue_active_pct": t.get("issue_active_pct")}
         json.dump(k, open(os.path.join(PROF, "k_traffic.json"), "w"), indent=1)
+        if "gn_eval" in traffic:   # bench.py c5_sweeps: roofline_hbm_kernel.traffic
+            g = dict(traffic["gn_eval"])
+            g.update(problems=1024, algorithmic_bytes_per_launch=1024 * (8000 * 32 + 2000 * 64))
+            json.dump(g, open(os.path.join(PROF, "gn_traffic.json"), "w"), indent=1)
         if "gn_loop_c5" in traffic:
             c5 = dict(traffic["gn_loop_c5"])
             c5["note"] = "one stage-2 gn_loop_stream_kernel launch over a 256-pair chunk of the C5 batch (8000 + 2000 records per problem)"
