@@ -5,7 +5,7 @@
 #   usage: tools/gpu_profile.sh <tag> [quick]      quick: launch lists + full captures only (no bench lines)
 set -x
 mkdir -p gpurun_out
-TAG=${1:-r2a}
+TAG=${1:-r2b}
 QUICK=${2:-}
 if [ -z "$QUICK" ]; then
   python bench.py --steps 50 --warmup 5 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err

@@ -3,7 +3,7 @@
 launch lists (per-kernel totals and shares, and the kernel sequence of one step), key raw metrics of every full capture, the
 top source lines of each capture by stall samples, the traffic / pipe JSONs bench.py reads, and the bench JSON lines.
 
-usage: python tools/summarise_profiles.py r2a
+usage: python tools/summarise_profiles.py r2b
 (tools/gpu_profile.sh runs it on the GPU box with PROF_OUT=gpurun_out/profiles: the .ncu-rep files of a full pass exceed what
 gpurun copies back, so only the summaries and two of the reports travel; copy gpurun_out/profiles/* to profiles/ afterwards)
 """
@@ -122,7 +122,7 @@ def launch_section(lines, path, title, step_marker):
 
 
 def main():
-    tag = sys.argv[1] if len(sys.argv) > 1 else "r2a"
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r2b"
     os.makedirs(PROF, exist_ok=True)
     lines = [f"# ncu summary {tag}", ""]
     for suffix, title, marker in (("", "`python bench.py --steps 2 --warmup 1 --no-cpu --no-hbm-run` (C2, 512 pairs)", "tc_expand"),
