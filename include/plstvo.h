@@ -365,6 +365,11 @@ int     plstvo_batch_stage_times(PlContext* ctx, PlDeviceBatch* db, int iters, d
 int  plstvo_gn_eval_stream(PlContext* ctx, const PlCamera* cam, const PlConfig* cfg,
                            const PlMatchedBatch* matched, const double* DT, int iters,
                            double* H, double* g, double* e, float* ms_total);
+/* test hook: the block-wide radix selection of the streamed solver's outlier pass (solve.cu: block_select_wide) on n_lists
+ * caller-supplied lists (values[off[p] .. off[p+1])): out[p] = the k[p]-th smallest value (mode 0), or the k[p]-th smallest of
+ * |x - pivot[p]| rounded to float (mode 1: the MAD form of src/auxiliar.cpp:399-402). */
+int  plstvo_debug_select(PlContext* ctx, int n_lists, const int32_t* off, const double* values, const int32_t* k,
+                         const double* pivot, int mode, double* out);
 /* test hook for the on-chip 6x6 routines of the solver (ColPivHouseholderQR solve + log|det|, inverse, symmetric
  * eigenvalues) on n caller-supplied matrices: H [n][36] row-major, g [n][6] -> x [n][6], lad [n], inv [n][36], eig [n][6] */
 int  plstvo_debug_algebra(PlContext* ctx, int n, const double* H, const double* g, double* x, double* lad,

@@ -1967,6 +1967,39 @@ void plstvo_batch_free(PlContext* ctx, PlDeviceBatch* db) {
     delete db;
 }
 
+int plstvo_debug_select(PlContext* ctx, int n_lists, const int32_t* off, const double* values, const int32_t* k,
+                        const double* pivot, int mode, double* out) {
+    if (!ctx || n_lists < 0 || !off || !k || !out || (mode != 0 && mode != 1) || (mode == 1 && !pivot)) return PLSTVO_E_INVALID;
+    LOCK(ctx);
+    if (n_lists == 0) return 0;
+    const size_t n = (size_t)off[n_lists];
+    if (n > 0 && !values) return PLSTVO_E_INVALID;
+    for (int p = 0; p < n_lists; ++p) {
+        const int len = off[p + 1] - off[p];
+        if (len < 0 || (len > 0 && (k[p] < 0 || k[p] >= len))) return PLSTVO_E_INVALID;
+    }
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t b_v = (n + 2) * 8, b_o = ((size_t)n_lists + 2) * 4, b_k = (size_t)n_lists * 4 + 8, b_p = (size_t)n_lists * 8;
+    CK(ctx, ctx->scratch.ensure(b_v + b_o + b_k + 2 * b_p + 64));
+    uint8_t* d = ctx->scratch.as<uint8_t>();
+    double* dv = reinterpret_cast<double*>(d);
+    double* dp = reinterpret_cast<double*>(d + b_v);
+    double* dout = reinterpret_cast<double*>(d + b_v + b_p);
+    int32_t* doff = reinterpret_cast<int32_t*>(d + b_v + 2 * b_p);
+    int32_t* dk = reinterpret_cast<int32_t*>(d + b_v + 2 * b_p + (b_o + 7) / 8 * 8);
+    cudaStream_t s = ctx->s_main;
+    if (n) CK(ctx, cudaMemcpyAsync(dv, values, n * 8, cudaMemcpyHostToDevice, s));
+    CK(ctx, cudaMemcpyAsync(doff, off, ((size_t)n_lists + 1) * 4, cudaMemcpyHostToDevice, s));
+    CK(ctx, cudaMemcpyAsync(dk, k, (size_t)n_lists * 4, cudaMemcpyHostToDevice, s));
+    if (pivot) CK(ctx, cudaMemcpyAsync(dp, pivot, b_p, cudaMemcpyHostToDevice, s));
+    CK(ctx, cudaMemsetAsync(dout, 0, b_p, s));
+    CK(ctx, launch_select_selftest(dv, doff, dk, pivot ? dp : nullptr, mode, n_lists, dout, s));
+    ctx->launches++;
+    CK(ctx, cudaMemcpyAsync(out, dout, b_p, cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaStreamSynchronize(s));
+    return 0;
+}
+
 int plstvo_debug_algebra(PlContext* ctx, int n, const double* H, const double* g, double* x, double* lad, double* inv,
                          double* eig) {
     if (!ctx || n < 0 || !H || !g || !x || !lad || !inv || !eig) return PLSTVO_E_INVALID;

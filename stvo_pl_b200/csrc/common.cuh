@@ -144,6 +144,8 @@ cudaError_t launch_hamming_knn2(const MatchProblem* problems, const MatchTile* t
 cudaError_t launch_match_finalize(const MatchProblem* problems, int n_problems, int max_n2, int32_t* counts,
                                   cudaStream_t stream);
 cudaError_t launch_track_solve(const SolveParams& prm, int n_pairs, cudaStream_t stream);
+cudaError_t launch_select_selftest(const double* v, const int32_t* off, const int32_t* ks, const double* pivot, int mode, int n_lists,
+                                   double* out, cudaStream_t stream);
 cudaError_t launch_algebra_selftest(const double* H, const double* g, int n, double* x, double* lad, double* inv,
                                     double* eig, cudaStream_t stream);
 cudaError_t launch_popc_bench(uint32_t* out, int iters, int blocks, cudaStream_t stream);

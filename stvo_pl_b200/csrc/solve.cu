@@ -1744,6 +1744,32 @@ __global__ void algebra_selftest_kernel(const double* __restrict__ H, const doub
     for (int i = lane; i < 36; i += 32) inv[(size_t)p * 36 + i] = sInv[i];
 }
 
+// test hook: the block-wide radix selection on caller-supplied lists (one 256-thread CTA per list, like the outlier pass); mode 0:
+// the k-th smallest value, mode 1: the k-th smallest of |x - pivot| rounded to float (the MAD form of src/auxiliar.cpp:399-402)
+__global__ void __launch_bounds__(256) select_selftest_kernel(const double* __restrict__ v, const int32_t* __restrict__ off,
+                                                              const int32_t* __restrict__ ks, const double* __restrict__ pivot,
+                                                              int mode, double* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    State& st = *reinterpret_cast<State*>(smem);
+    const SelScratch sel = sel_scratch_at(smem + align_up(sizeof(State), 16));
+    const int p = blockIdx.x, a = off[p], n = off[p + 1] - a;
+    if (n <= 0) return;
+    const double* x = v + a;
+    const double piv = pivot ? pivot[p] : 0.0;
+    double r;
+    if (mode == 0) r = block_select_wide(sel, st, n, ks[p], [&](int i) -> double { return x[i]; });
+    else r = block_select_wide(sel, st, n, ks[p], [&](int i) -> double { return (double)fabsf((float)(x[i] - piv)); });
+    if (threadIdx.x == 0) out[p] = r;
+}
+
+cudaError_t launch_select_selftest(const double* v, const int32_t* off, const int32_t* ks, const double* pivot, int mode, int n_lists,
+                                   double* out, cudaStream_t stream) {
+    if (n_lists <= 0) return cudaSuccess;
+    const size_t smem = align_up(sizeof(State), 16) + sel_scratch_bytes();
+    select_selftest_kernel<<<n_lists, 256, smem, stream>>>(v, off, ks, pivot, mode, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_algebra_selftest(const double* H, const double* g, int n, double* x, double* lad, double* inv,
                                     double* eig, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;

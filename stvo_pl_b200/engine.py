@@ -84,6 +84,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "plstvo_gn_eval_stream": (C.c_int, [vp, cam, cfg, mb, dp, C.c_int, dp, dp, dp, C.POINTER(C.c_float)]),
         "plstvo_popc_rate": (C.c_int, [vp, dp]),
         "plstvo_debug_algebra": (C.c_int, [vp, C.c_int, dp, dp, dp, dp, dp, dp]),
+        "plstvo_debug_select": (C.c_int, [vp, C.c_int, i32p, dp, i32p, dp, C.c_int, dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)   # AttributeError if the library does not export a declared symbol
@@ -101,7 +102,7 @@ EXPORTED_SYMBOLS = [
     "plstvo_optimize_pose", "plstvo_track_batch", "plstvo_track_batch_async", "plstvo_wait", "plstvo_batch_upload", "plstvo_batch_run",
     "plstvo_batch_run_timed", "plstvo_batch_download", "plstvo_batch_free", "plstvo_synchronize",
     "plstvo_host_alloc", "plstvo_host_free", "plstvo_launch_count", "plstvo_batch_kernel_times", "plstvo_batch_stage_times",
-    "plstvo_gn_eval_stream", "plstvo_popc_rate", "plstvo_debug_algebra"]
+    "plstvo_gn_eval_stream", "plstvo_popc_rate", "plstvo_debug_algebra", "plstvo_debug_select"]
 
 
 def _p(a: Optional[np.ndarray], typ):
@@ -513,6 +514,18 @@ class Engine:
                                                 iters, _p(H, T.c_double_p), _p(g, T.c_double_p), _p(e, T.c_double_p),
                                                 C.byref(ms)))
         return H, g, e, float(ms.value)
+
+    def debug_select(self, lists, ks, pivots=None):
+        """Block-wide radix selection (test hook): the ks[p]-th smallest of lists[p]; with pivots, of |x - pivot| rounded to float."""
+        off = np.concatenate([[0], np.cumsum([len(x) for x in lists])]).astype(np.int32)
+        v = np.ascontiguousarray(np.concatenate([np.asarray(x, np.float64) for x in lists]) if len(lists) else np.zeros(0))
+        ks = np.ascontiguousarray(ks, np.int32)
+        out = np.zeros(len(lists))
+        pv = None if pivots is None else np.ascontiguousarray(pivots, np.float64)
+        self._ck(self.lib.plstvo_debug_select(self.ctx, len(lists), _p(off, T.c_int32_p), _p(v, T.c_double_p), _p(ks, T.c_int32_p),
+                                              _p(pv, T.c_double_p) if pv is not None else None, 0 if pv is None else 1,
+                                              _p(out, T.c_double_p)))
+        return out
 
     def debug_algebra(self, H, g):
         """On-chip 6x6 routines (test hook): returns x = H^-1 g (col-pivot QR), log|det H|, inv(H), eigvals(H)."""

@@ -308,6 +308,50 @@ def test_onchip_6x6_algebra(engine, oracle):
     np.testing.assert_allclose(eig[65], np.ones(6), atol=1e-14)
 
 
+def test_block_radix_selection(engine):
+    """The radix selection behind the streamed solver's median / MAD (solve.cu: block_select_wide) against numpy's sort, bit for
+    bit, on lists that stress it: every length from 1 up, heavy ties, all-equal lists, values straddling zero, sub-normals,
+    infinities, huge dynamic range (many digits under the common prefix), clustered values (many candidates in one bin), and
+    residual-like positive data at KITTI and C5 list lengths; every rank k for the short lists, median-type ranks for the long."""
+    rng = np.random.default_rng(7)
+    lists, ks = [], []
+
+    def add(x, k):
+        lists.append(np.asarray(x, np.float64))
+        ks.append(int(k))
+
+    for n in list(range(1, 40)) + [63, 64, 65, 255, 256, 257, 511, 513]:
+        x = rng.normal(0, 3, n)
+        for k in sorted({0, n // 2, n - 1, int(rng.integers(0, n))}):
+            add(x, k)
+    for n in (300, 2000, 8000, 9000):
+        res = np.abs(rng.standard_cauchy(n)) * rng.choice([0.3, 1.0, 40.0], n)           # residual-like, heavy tail
+        add(res, n // 2)
+        add(res, n // 2 - 1)
+        add(np.round(res, 1), n // 2)                                                    # heavy ties
+        add(np.full(n, 3.25), n // 2)                                                    # all equal
+        add(np.concatenate([np.full(n // 2, 1.0), np.full(n - n // 2, 1.0 + 2.0 ** -52)]), n // 2)   # two values one ulp apart
+        add(1.0 + rng.integers(0, 300, n) * 2.0 ** -50, n // 3)                          # > 256 candidates under one 11-bit digit
+        add(rng.normal(0, 1, n) * 10.0 ** rng.integers(-300, 300, n), n // 2)            # full exponent range, both signs
+        add(np.concatenate([rng.normal(0, 1, n - 7), [np.inf] * 4, [-np.inf] * 3]), n // 2)
+        add(np.concatenate([rng.normal(0, 1e-310, n // 2), rng.normal(0, 1, n - n // 2)]), n // 4)   # sub-normals
+    got = engine.debug_select(lists, ks)
+    for x, k, g in zip(lists, ks, got):
+        want = np.sort(x)[k]
+        assert g == want or (np.isnan(g) and np.isnan(want)), (len(x), k, g, want)
+    # the MAD form: k-th smallest of |x - median| rounded to float (src/auxiliar.cpp:399-402)
+    ml, mk, mp = [], [], []
+    for n in (5, 33, 500, 2000, 8000):
+        for scale in (1.0, 1e-3, 250.0):
+            x = np.abs(rng.standard_cauchy(n)) * scale
+            med = np.sort(x)[n // 2]
+            ml.append(x); mk.append(n // 2); mp.append(med)
+    got = engine.debug_select(ml, mk, pivots=mp)
+    for x, k, piv, g in zip(ml, mk, mp, got):
+        dev = np.abs((x - piv).astype(np.float32)).astype(np.float64)
+        assert g == np.sort(dev)[k], (len(x), k, g)
+
+
 def test_handler_mirror_sequence(engine, oracle):
     """app/imagesStVO.cpp:88-124 call sequence through the Python mirror of StereoFrameHandler: a 4-frame sequence,
     poses chained through Tfw, against the oracle run pair by pair with the same priors."""
