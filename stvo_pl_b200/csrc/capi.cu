@@ -370,7 +370,7 @@ int ws_prepare(PlContext* ctx, Workspace& ws, const PlCamera* cam, const PlConfi
                 ws.tc_sides[(size_t)4 * p + 2 * type] = TcSide{nullptr, pr.enabled ? n1 : 0, nullptr};
                 ws.tc_sides[(size_t)4 * p + 2 * type + 1] = TcSide{nullptr, pr.enabled ? n2 : 0, nullptr};
                 exp_tiles += (size_t)t1 + t2;
-                rowp_elems += (size_t)t2 * n1;
+                rowp_elems += (size_t)(pr.enabled ? (n2 + TC_CW - 1) / TC_CW : 0) * n1;
                 colp_elems += (size_t)(pr.enabled ? n2 : 0);
                 ws.tc_max_tiles = std::max(ws.tc_max_tiles, std::max(t1, t2));
                 for (int yb = 0; yb < (t2 + 1) / 2; ++yb) ws.tc_items[type].push_back(TcItem{2 * p + type, yb});

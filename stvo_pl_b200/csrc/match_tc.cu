@@ -193,13 +193,14 @@ constexpr int TC_OFF_X = 0;
 constexpr int TC_OFF_Y = TC_XSTAGES * TC_TILE_BYTES;                      // [slab 0..1][256 rows]: 64 KB
 constexpr int TC_OFF_SCR = TC_OFF_Y + 2 * TC_TILE_BYTES;                  // per epilogue warp: 16 x 33 words
 constexpr int TC_SCR_WARP = 16 * 33 * 4;
-constexpr int TC_OFF_MRG = TC_OFF_SCR + 8 * TC_SCR_WARP;                  // [2 groups][4 quarters][128 columns] uint2
-constexpr int TC_OFF_BAR = TC_OFF_MRG + 2 * 4 * 128 * 8;
+constexpr int TC_OFF_MRG = TC_OFF_SCR + TC_EW * TC_SCR_WARP;              // [groups][4 quarters][columns per group] uint2: 8 KB
+constexpr int TC_OFF_BAR = TC_OFF_MRG + 4 * 256 * 8;
 constexpr int TC_IRING = 4;                                               // work items announced ahead
 constexpr int TC_NBARS = 2 * TC_XSTAGES + 2 + 2 * TC_ASTAGES + 2 * TC_IRING;
 constexpr int TC_OFF_RING = TC_OFF_BAR + TC_NBARS * 8;
 constexpr int TC_OFF_SLOT = TC_OFF_RING + TC_IRING * 4;
 constexpr int TC_SMEM_USED = TC_OFF_SLOT + 16;
+static_assert(TC_SMEM_USED + 1024 <= 227 * 1024, "tc_hamming_kernel: shared memory");
 
 size_t tc_smem_bytes() { return (size_t)TC_SMEM_USED + 1024; }
 
@@ -242,11 +243,11 @@ tc_hamming_kernel(const TcProblem* __restrict__ problems, const TcItem* __restri
         mbar_init(y_empty, 1);
         for (int i = 0; i < TC_ASTAGES; ++i) {
             mbar_init(&t_full[i], 1);
-            mbar_init(&t_empty[i], 8);
+            mbar_init(&t_empty[i], TC_EW);
         }
         for (int i = 0; i < TC_IRING; ++i) {
             mbar_init(&i_full[i], 1);
-            mbar_init(&i_empty[i], 9);   // the MMA thread + 8 epilogue warps
+            mbar_init(&i_empty[i], TC_EW + 1);   // the MMA thread + the epilogue warps
         }
         fence_mbar_init();
     }
@@ -329,10 +330,13 @@ tc_hamming_kernel(const TcProblem* __restrict__ problems, const TcItem* __restri
             }
         }
     } else {
-        // ===== epilogue: 8 warps.  quarter q = TMEM lanes 32q..32q+31 (hardware: warp id % 4), group gq = which 128 columns
+        // ===== epilogue: TC_EW warps.  quarter q = TMEM lanes 32q..32q+31 (hardware: warp id % 4), group gq = which TC_CW columns
+        // of the 256-column accumulator (TC_EW = 8: two groups of 128, two warps per scheduler; TC_EW = 16: four groups of 64, four
+        // warps per scheduler: the min / max chains of one warp issue into the dependency stalls of the others)
+        constexpr int CW = TC_CW, NCH = CW / 32, NREG = CW / 2;
         const int ew = warp - 2, q = warp & 3, gq = ew >> 2;
         uint32_t* scr = reinterpret_cast<uint32_t*>(sm + TC_OFF_SCR + ew * TC_SCR_WARP);
-        uint2* mrg = reinterpret_cast<uint2*>(sm + TC_OFF_MRG) + gq * 4 * 128;
+        uint2* mrg = reinterpret_cast<uint2*>(sm + TC_OFF_MRG) + gq * 4 * CW;
         uint32_t as = 0, aph = 0;
         for (uint32_t k = 0;; ++k) {
             const uint32_t slot = k % TC_IRING;
@@ -344,12 +348,12 @@ tc_hamming_kernel(const TcProblem* __restrict__ problems, const TcItem* __restri
             const TcItem item = item_at(it);
             const TcProblem pr = problems[item.problem];
             const int nxt = (pr.n1 + TC_ROWS - 1) / TC_ROWS;
-            const int half = item.yblk * 2 + gq;              // 128-column block index of this group
-            const int ycol0 = half * TC_ROWS;
-            const int nvalid = min(TC_ROWS, pr.n2 - ycol0);   // <= 0: nothing for this group
-            uint32_t c1[64], c2[64];
+            const int blk = item.yblk * (256 / CW) + gq;      // CW-column block index of this group
+            const int ycol0 = blk * CW;
+            const int nvalid = min(CW, pr.n2 - ycol0);        // <= 0: nothing for this group
+            uint32_t c1[NREG], c2[NREG];
 #pragma unroll
-            for (int i = 0; i < 64; ++i) c1[i] = c2[i] = NEG2;
+            for (int i = 0; i < NREG; ++i) c1[i] = c2[i] = NEG2;
 
             for (int t = 0; t < nxt; ++t) {
                 mbar_wait(&t_full[as], aph);
@@ -358,7 +362,7 @@ tc_hamming_kernel(const TcProblem* __restrict__ problems, const TcItem* __restri
                 const bool xvalid = x < pr.n1;
                 // two independent row chains: A = registers 0..7 (16-column group 2c), B = registers 8..15 (group 2c + 1)
                 uint32_t ra1 = NEG2, ra2 = NEG2, rb1 = NEG2, rb2 = NEG2, ta = 0, tb = 0;
-                const uint32_t tad = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + gq * 128;
+                const uint32_t tad = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + gq * CW;
                 auto fold = [&](const uint32_t (&v)[16], const int c) {
                     const uint32_t olda = ra1, oldb = rb1;
 #pragma unroll
@@ -374,25 +378,23 @@ tc_hamming_kernel(const TcProblem* __restrict__ problems, const TcItem* __restri
                         else top2_alu(c1[c * 16 + i], c2[c * 16 + i], v[i]);
                     }
                 };
-                if (nvalid == TC_ROWS && (t + 1) * TC_ROWS <= pr.n1 && debug_tile == nullptr) {
+                if (nvalid == CW && (t + 1) * TC_ROWS <= pr.n1 && debug_tile == nullptr) {
                     // full tile of a full block (the common case): no per-chunk branches, the next chunk's TMEM load is in
                     // flight while this one is folded
                     uint32_t va[16], vb[16];
                     tc_ld32(tad, va);
-                    tc_wait_ld();
-                    tc_ld32(tad + 32, vb);
-                    fold(va, 0);
-                    tc_wait_ld();
-                    tc_ld32(tad + 64, va);
-                    fold(vb, 1);
-                    tc_wait_ld();
-                    tc_ld32(tad + 96, vb);
-                    fold(va, 2);
-                    tc_wait_ld();
-                    fold(vb, 3);
+#pragma unroll
+                    for (int c = 0; c < NCH; c += 2) {
+                        tc_wait_ld();
+                        tc_ld32(tad + (c + 1) * 32, vb);
+                        fold(va, c);
+                        tc_wait_ld();
+                        if (c + 2 < NCH) tc_ld32(tad + (c + 2) * 32, va);
+                        fold(vb, c + 1);
+                    }
                 } else {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
+                    for (int c = 0; c < NCH; ++c) {
                         if (c * 32 >= nvalid) continue;           // warp-uniform: no valid column in this chunk
                         uint32_t v[16];
                         tc_ld32(tad + c * 32, v);
@@ -400,7 +402,7 @@ tc_hamming_kernel(const TcProblem* __restrict__ problems, const TcItem* __restri
                         if (debug_tile && it == 0 && t == 0) {
 #pragma unroll
                             for (int i = 0; i < 16; ++i)
-                                *reinterpret_cast<uint32_t*>(debug_tile + (size_t)(q * 32 + lane) * 256 + gq * 128 + c * 32 + 2 * i) = v[i];
+                                *reinterpret_cast<uint32_t*>(debug_tile + (size_t)(q * 32 + lane) * 256 + gq * CW + c * 32 + 2 * i) = v[i];
                         }
                         if (c * 32 + 32 > nvalid) {               // the one boundary chunk of a partial block
 #pragma unroll
@@ -425,7 +427,7 @@ tc_hamming_kernel(const TcProblem* __restrict__ problems, const TcItem* __restri
                     const uint32_t f1 = hmax2u(m1, s1), f2 = hmax2u(hmax2u(hmin2u(m1, s1), m2), s2);
                     const uint32_t tag = sel32(hgt2mask(s1, m1), (st << 1) | 1u, tg << 1) & 0xFu;   // group << 1 | parity
                     const uint32_t dd = dots_to_dist(__byte_perm(f1, f2, 0x5410));
-                    pr.rowp[(size_t)half * pr.n1 + x] = h2u_lo(dd) | (h2u_hi(dd) << 9) | (tag << 18);
+                    pr.rowp[(size_t)blk * pr.n1 + x] = h2u_lo(dd) | (h2u_hi(dd) << 9) | (tag << 18);
                 }
             }
 
@@ -433,7 +435,7 @@ tc_hamming_kernel(const TcProblem* __restrict__ problems, const TcItem* __restri
             // per warp: transpose 16 registers at a time through shared memory; lane L folds register (L & 15) over
             // source lanes 16 (L >> 4) .. +15, the two halves meet by shuffle; then the four quarters merge per column.
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
+            for (int p = 0; p < NCH; ++p) {
                 const int j = lane & 15, hl = lane >> 4;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) scr[i * 33 + lane] = c1[p * 16 + i];
@@ -463,17 +465,17 @@ tc_hamming_kernel(const TcProblem* __restrict__ problems, const TcItem* __restri
                 const uint32_t nid = sel32(hgt2mask(o1, m1), oid, id);
                 if (hl == 0) {
                     const int col = (p * 16 + j) * 2;
-                    mrg[q * 128 + col] = make_uint2((n1v & 0xFFFFu) | (n2v << 16), nid & 0xFFFFu);
-                    mrg[q * 128 + col + 1] = make_uint2((n1v >> 16) | (n2v & 0xFFFF0000u), nid >> 16);
+                    mrg[q * CW + col] = make_uint2((n1v & 0xFFFFu) | (n2v << 16), nid & 0xFFFFu);
+                    mrg[q * CW + col + 1] = make_uint2((n1v >> 16) | (n2v & 0xFFFF0000u), nid >> 16);
                 }
             }
             asm volatile("bar.sync %0, 128;" ::"r"(1 + gq) : "memory");
-            {
-                const int col = (ew & 3) * 32 + lane;
+            if (lane < CW / 4) {   // the group's four warps share its CW columns
+                const int col = (ew & 3) * (CW / 4) + lane;
                 uint32_t b1 = NEG2, b2 = NEG2, bt = 0;   // only the low halves are meaningful
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq) {
-                    const uint2 e = mrg[qq * 128 + col];
+                    const uint2 e = mrg[qq * CW + col];
                     const uint32_t a1 = e.x & 0xFFFFu, a2 = e.x >> 16;
                     b2 = hmax2u(hmax2u(hmin2u(b1, a1), b2), a2);
                     bt = sel32(hgt2mask(a1, b1), (uint32_t)qq * 32u + e.y, bt);
@@ -557,7 +559,7 @@ __global__ void __launch_bounds__(256) tc_resolve_kernel(const MatchProblem* __r
     const MatchProblem mp = mps[blockIdx.x];
     if (!mp.enabled) return;
     const TcProblem tp = tps[blockIdx.x];
-    const int nyh = (mp.n2 + TC_ROWS - 1) / TC_ROWS, nxt = (mp.n1 + TC_ROWS - 1) / TC_ROWS;
+    const int nyh = (mp.n2 + TC_CW - 1) / TC_CW, nxt = (mp.n1 + TC_ROWS - 1) / TC_ROWS;   // row partials: one per TC_CW-train block
     const int slice = blockIdx.y, nslices = gridDim.y;
     // partial word: best distance (9 bits) | second distance << 9 (511 = none) | candidate tag << 18
     // queries: top-2 trains over the 128-train blocks (lowest block wins a tie: its indices are lower)
@@ -581,7 +583,7 @@ __global__ void __launch_bounds__(256) tc_resolve_kernel(const MatchProblem* __r
                             a1 = __ldg(reinterpret_cast<const uint4*>(mp.d1 + (size_t)x * 32) + 1);
                 idx = -1;
                 if (d1 != d2) {   // unique best: it is one of the 8 tagged trains (16-column group, one parity)
-                    const int base = bh * TC_ROWS + (int)((btag >> 1) & 7u) * 16 + (int)(btag & 1u);
+                    const int base = bh * TC_CW + (int)((btag >> 1) & 7u) * 16 + (int)(btag & 1u);
                     for (int i = 0; i < 8 && idx < 0; ++i) {
                         const int j = base + 2 * i;
                         if (j < mp.n2 && hamming256(a0, a1, mp.d2 + (size_t)j * 32) == d1) idx = j;

@@ -65,7 +65,7 @@ int main(int argc, char** argv) {
         const int t1 = (q.n1 + 127) / 128, t2 = (q.n2 + 127) / 128;
         q.e1 = tiles; tiles += t1;
         q.e2 = tiles; tiles += t2;
-        q.rowp = nrowp; nrowp += (size_t)t2 * q.n1;
+        q.rowp = nrowp; nrowp += (size_t)((q.n2 + TC_CW - 1) / TC_CW) * q.n1;
         q.colp = ncolp; ncolp += q.n2;
         q.rowpart = nrp; nrp += q.n1;
         q.colpart = ncp; ncp += q.n2;
