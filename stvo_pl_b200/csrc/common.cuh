@@ -204,8 +204,7 @@ cudaError_t launch_pack_records(const MatchedDev& m, const PlCamera& cam, int B,
                                 cudaStream_t stream);
 cudaError_t launch_gn_eval_stream(const PlCamera& cam, const PlConfig& cfg, const int32_t* pt_off, const int32_t* ls_off,
                                   const float4* pt, const float4* ls, int B, const double* DT, double* partial,
-                                  int slices_per_problem, int sm_count, double* H, double* g, double* e, cudaStream_t stream,
-                                  const int32_t* pt_cnt = nullptr, const int32_t* ls_cnt = nullptr, const int32_t* active = nullptr);
+                                  int slices_per_problem, int sm_count, double* H, double* g, double* e, cudaStream_t stream);
 
 // cudaFuncSetAttribute is per device: a process may drive several GPUs (one context each), so the opted-in dynamic
 // shared-memory size is remembered per device (`done`: one slot per device ordinal, zero-initialised by the caller).

@@ -76,17 +76,14 @@ __global__ void pack_records_kernel(MatchedDev m, PlCamera cam, int B, int n_pt,
 struct GsItem {
     int p0, np, l0, nl, pt_lo, n_ptile, lt_lo, n_tiles;
 };
-// cnt (optional): live records per problem when the lists are shorter than their slots (matched lists inside the prev
-// frame's slots); active (optional): problems whose flag is 0 stream nothing
 struct GsLists {
-    const int32_t* pt_off; const int32_t* ls_off; const int32_t* pt_cnt; const int32_t* ls_cnt; const int32_t* active;
+    const int32_t* pt_off; const int32_t* ls_off;
 };
 __device__ __forceinline__ GsItem gs_item(const GsLists& L, int item, int bpp) {
     GsItem it;
     const int prob = item / bpp, blk = item % bpp;
-    it.p0 = L.pt_off[prob]; it.np = L.pt_cnt ? L.pt_cnt[prob] : L.pt_off[prob + 1] - it.p0;
-    it.l0 = L.ls_off[prob]; it.nl = L.ls_cnt ? L.ls_cnt[prob] : L.ls_off[prob + 1] - it.l0;
-    if (L.active && !L.active[prob]) it.np = it.nl = 0;
+    it.p0 = L.pt_off[prob]; it.np = L.pt_off[prob + 1] - it.p0;
+    it.l0 = L.ls_off[prob]; it.nl = L.ls_off[prob + 1] - it.l0;
     const int ptiles = (it.np + GS_PT_TILE - 1) / GS_PT_TILE, ltiles = (it.nl + GS_LS_TILE - 1) / GS_LS_TILE;
     const int pt_per = (ptiles + bpp - 1) / bpp, lt_per = (ltiles + bpp - 1) / bpp;
     it.pt_lo = min(ptiles, blk * pt_per);
@@ -210,9 +207,8 @@ gn_eval_stream_kernel(PlCamera cam, float homog_th, const GsLists L,
 // Folds the bpp x 8 fp64 partial records of a problem in index order (a per-item fence + counter in the streaming kernel
 // costs more than this second launch: measured 82 vs 70 us per sweep).
 __global__ void gn_eval_reduce_kernel(const double* __restrict__ partial, int n_part, double* __restrict__ H,
-                                      double* __restrict__ g, double* __restrict__ e, const int32_t* __restrict__ active) {
+                                      double* __restrict__ g, double* __restrict__ e) {
     const int prob = blockIdx.x, lane = threadIdx.x;
-    if (active && !active[prob]) return;
     double sum = 0.0;
     if (lane < GS_NACC)
         for (int b = 0; b < n_part; b++) sum += partial[((size_t)prob * n_part + b) * GS_NACC + lane];
@@ -247,8 +243,7 @@ cudaError_t launch_pack_records(const MatchedDev& m, const PlCamera& cam, int B,
 
 cudaError_t launch_gn_eval_stream(const PlCamera& cam, const PlConfig& cfg, const int32_t* pt_off, const int32_t* ls_off,
                                   const float4* pt, const float4* ls, int B, const double* DT, double* partial, int bpp,
-                                  int sm_count, double* H, double* g, double* e, cudaStream_t stream, const int32_t* pt_cnt,
-                                  const int32_t* ls_cnt, const int32_t* active) {
+                                  int sm_count, double* H, double* g, double* e, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
     const size_t smem = (size_t)GS_STAGES * GS_STAGE_BYTES;
     static const bool packed = getenv("PLSTVO_GS_SCALAR") == nullptr;   // A/B knob: scalar-FFMA accumulators (default: packed FFMA2)
@@ -258,7 +253,7 @@ cudaError_t launch_gn_eval_stream(const PlCamera& cam, const PlConfig& cfg, cons
     if (err != cudaSuccess) return err;
     const int n_items = B * bpp;
     const int grid = n_items < 2 * sm_count ? n_items : 2 * sm_count;
-    const GsLists L{pt_off, ls_off, pt_cnt, ls_cnt, active};
+    const GsLists L{pt_off, ls_off};
     if (packed)
         gn_eval_stream_kernel<GsAccPacked><<<grid, GS_THREADS, smem, stream>>>(cam, (float)cfg.homog_th, L, pt, ls, DT, partial, bpp,
                                                                                n_items);
@@ -266,8 +261,8 @@ cudaError_t launch_gn_eval_stream(const PlCamera& cam, const PlConfig& cfg, cons
         gn_eval_stream_kernel<GsAccScalar><<<grid, GS_THREADS, smem, stream>>>(cam, (float)cfg.homog_th, L, pt, ls, DT, partial, bpp,
                                                                                n_items);
     err = cudaGetLastError();
-    if (err != cudaSuccess || !H) return err;   // H == nullptr: the caller folds the partials itself
-    gn_eval_reduce_kernel<<<B, 32, 0, stream>>>(partial, bpp * GS_CWARPS, H, g, e, active);
+    if (err != cudaSuccess) return err;
+    gn_eval_reduce_kernel<<<B, 32, 0, stream>>>(partial, bpp * GS_CWARPS, H, g, e);
     return cudaGetLastError();
 }
 
