@@ -1916,22 +1916,31 @@ __device__ void exact_error_partial(const Feat& f, const double* DT, const Cam& 
 #define GL_FOLD_TILES 4
 #endif
 constexpr int GL_FOLD = GL_FOLD_TILES;
+// CTA shape of the GN loop kernel: consumer warps, ring stages, CTAs per SM (three digits).  862 keeps a KITTI-size problem's
+// records resident in the ring.  434 (twice the problems in flight per SM, records re-streamed from L2 every iteration) was
+// measured: the kernel alone gets faster at C2 (0.262 -> 0.227 ms per 512 problems) but the pass as a whole does not (two solver
+// chains already run side by side), and C5's stage 2 gets slower (0.45 -> 0.51 ms).
+#ifndef GL_SHAPE
+#define GL_SHAPE 862
+#endif
+constexpr int GL_CWARPS = GL_SHAPE / 100, GL_STAGES = (GL_SHAPE / 10) % 10, GL_MINBLOCKS = GL_SHAPE % 10;
+constexpr int GL_CONSUMERS = GL_CWARPS * 32, GL_THREADS = GL_CONSUMERS + 32;
 constexpr double GL_ERR_BAND = 2.5e-7;   // relative half-width of the "could go either way" band of the error tests (~10x the noise)
 constexpr double GL_INC_BAND = 1e-3;     // the same for the increment-norm test   // tiles between fp32 -> fp64 folds of a thread's accumulators
-__global__ void __launch_bounds__(GS_THREADS, 2)
+__global__ void __launch_bounds__(GL_THREADS, GL_MINBLOCKS)
 gn_loop_stream_kernel(const PlCamera cam, const PlConfig cfg, const int32_t* __restrict__ pt_off, const int32_t* __restrict__ ls_off,
                       const StreamBufs sb, int n, int max_iters, int* __restrict__ queue, double* __restrict__ feat_scratch,
                       size_t feat_stride, int cap_pt, int cap_ls) {
     extern __shared__ __align__(128) uint8_t ring[];
-    __shared__ __align__(8) uint64_t full[GS_STAGES], empty[GS_STAGES];
-    __shared__ double red[GS_CWARPS + 1][32], sH[36], sg[8], sDT[16], sDTprev[16], sC[36], s_exact[4];
+    __shared__ __align__(8) uint64_t full[GL_STAGES], empty[GL_STAGES];
+    __shared__ double red[GL_CWARPS + 1][32], sH[36], sg[8], sDT[16], sDTprev[16], sC[36], s_exact[4];
     __shared__ float sPose[12];
     __shared__ int s_prob, s_stop, s_amb;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        for (int st = 0; st < GS_STAGES; ++st) {
+        for (int st = 0; st < GL_STAGES; ++st) {
             mbar_init(&full[st], 1);
-            mbar_init(&empty[st], GS_CWARPS);
+            mbar_init(&empty[st], GL_CWARPS);
         }
         fence_mbar_init();
     }
@@ -1953,7 +1962,7 @@ gn_loop_stream_kernel(const PlCamera cam, const PlConfig cfg, const int32_t* __r
         const int ptiles = (np + GS_PT_TILE - 1) / GS_PT_TILE, n_tiles = ptiles + (nl + GS_LS_TILE - 1) / GS_LS_TILE;
         // a problem whose records fit the ring (KITTI-size: 4 point tiles + 2 line tiles) is loaded ONCE per GN call and
         // re-evaluated from shared memory; longer lists stream through the ring every iteration
-        const bool resident = n_tiles <= GS_STAGES;
+        const bool resident = n_tiles <= GL_STAGES;
         if (tid < 16) sDT[tid] = sb.DT[(size_t)p * 16 + tid];
         if (tid < 12) sPose[tid] = gs_pose_entry(sb.DT[(size_t)p * 16 + tid], tid);
         double err_prev = c.err_prev, err = 0.0;   // warp 0's copies are the authoritative ones
@@ -1961,11 +1970,11 @@ gn_loop_stream_kernel(const PlCamera cam, const PlConfig cfg, const int32_t* __r
         bool fail_first = false, delegated = false;
         __syncthreads();
         for (;; ++it) {
-            if (warp == GS_CWARPS) {           // ---- producer ----
+            if (warp == GL_CWARPS) {           // ---- producer ----
                 if (lane == 0 && (!resident || it == 0)) {
                     for (int t = 0; t < n_tiles; ++t) {
-                        const uint32_t kk = k + t, st = kk % GS_STAGES;
-                        if (kk >= GS_STAGES) mbar_wait(&empty[st], ((kk / GS_STAGES) - 1) & 1);
+                        const uint32_t kk = k + t, st = kk % GL_STAGES;
+                        if (kk >= GL_STAGES) mbar_wait(&empty[st], ((kk / GL_STAGES) - 1) & 1);
                         const void* src;
                         uint32_t bytes;
                         if (t < ptiles) {
@@ -1987,14 +1996,14 @@ gn_loop_stream_kernel(const PlCamera cam, const PlConfig cfg, const int32_t* __r
                 acc.clear();
                 double run = 0.0;              // lane L: this warp's fp64 total of accumulator L so far
                 for (int t = 0; t < n_tiles; ++t) {
-                    const uint32_t kk = k + t, st = kk % GS_STAGES;
-                    if (!resident || it == 0) mbar_wait(&full[st], (kk / GS_STAGES) & 1);
+                    const uint32_t kk = k + t, st = kk % GL_STAGES;
+                    if (!resident || it == 0) mbar_wait(&full[st], (kk / GL_STAGES) & 1);
                     const float4* sr = reinterpret_cast<const float4*>(ring + (size_t)st * GS_STAGE_BYTES);
                     if (t < ptiles) {
                         const int cnt = min(GS_PT_TILE, np - t * GS_PT_TILE);
 #pragma unroll
-                        for (int h = 0; h < GS_PT_TILE / GS_CONSUMERS; ++h) {
-                            const int idx = tid + h * GS_CONSUMERS;
+                        for (int h = 0; h < GS_PT_TILE / GL_CONSUMERS; ++h) {
+                            const int idx = tid + h * GL_CONSUMERS;
                             const bool lv = idx < cnt;
                             const int ii = lv ? idx : 0;
                             const float4 a = sr[ii], b = sr[cnt + ii];
@@ -2002,10 +2011,14 @@ gn_loop_stream_kernel(const PlCamera cam, const PlConfig cfg, const int32_t* __r
                         }
                     } else {
                         const int cnt = min(GS_LS_TILE, nl - (t - ptiles) * GS_LS_TILE);
-                        const bool lv = tid < cnt;
-                        const int ii = lv ? tid : 0;
-                        const float4 a = sr[ii], b = sr[cnt + ii], cc = sr[2 * cnt + ii], d = sr[3 * cnt + ii];
-                        gs_line(P, a, b, cc, d, lv && b.w != 0.f, acc);
+#pragma unroll
+                        for (int h = 0; h < GS_LS_TILE / GL_CONSUMERS; ++h) {
+                            const int idx = tid + h * GL_CONSUMERS;
+                            const bool lv = idx < cnt;
+                            const int ii = lv ? idx : 0;
+                            const float4 a = sr[ii], b = sr[cnt + ii], cc = sr[2 * cnt + ii], d = sr[3 * cnt + ii];
+                            gs_line(P, a, b, cc, d, lv && b.w != 0.f, acc);
+                        }
                     }
                     __syncwarp();
                     if (lane == 0 && !resident) mbar_arrive(&empty[st]);
@@ -2034,7 +2047,7 @@ gn_loop_stream_kernel(const PlCamera cam, const PlConfig cfg, const int32_t* __r
             if (warp == 0) {                   // ---- the loop body of :404-427 on the summed normal equations ----
                 double sum = 0.0;
 #pragma unroll
-                for (int w = 0; w < GS_CWARPS; w++) sum += red[w][lane];
+                for (int w = 0; w < GL_CWARPS; w++) sum += red[w][lane];
                 const double cnt = __shfl_sync(FULL_MASK, sum, 28), esum = __shfl_sync(FULL_MASK, sum, 27);
                 if (lane < 21) {
                     int i = 0, q = lane;
@@ -2084,7 +2097,7 @@ gn_loop_stream_kernel(const PlCamera cam, const PlConfig cfg, const int32_t* __r
                 __syncthreads();
                 if (tid < 4) {
                     double t = 0.0;
-                    for (int w = 0; w <= GS_CWARPS; w++) t += red[w][tid];
+                    for (int w = 0; w <= GL_CWARPS; w++) t += red[w][tid];
                     s_exact[tid] = t;
                 }
                 __syncthreads();
@@ -2130,8 +2143,8 @@ gn_loop_stream_kernel(const PlCamera cam, const PlConfig cfg, const int32_t* __r
             if (stop) break;
         }
         if (resident) {                        // the records sat in the ring for the whole call: hand the stages back now
-            if (warp < GS_CWARPS && lane == 0)
-                for (int t = 0; t < n_tiles; ++t) mbar_arrive(&empty[(k + t) % GS_STAGES]);
+            if (warp < GL_CWARPS && lane == 0)
+                for (int t = 0; t < n_tiles; ++t) mbar_arrive(&empty[(k + t) % GL_STAGES]);
             k += n_tiles;
         }
         if (warp == 0) {                       // :429-430 and the state the next kernels read
@@ -2322,7 +2335,7 @@ cudaError_t launch_stream_solve(const SolveParams& prm_in, int n_pairs, const St
     const int32_t* off_p = prm.mode == 0 ? prm.prev.pt_off + prm.first_pair : prm.matched.pt_off + prm.first_pair;
     const int32_t* off_l = prm.mode == 0 ? prm.prev.ls_off + prm.first_pair : prm.matched.ls_off + prm.first_pair;
     static size_t conf_c[64] = {};
-    const size_t ring = (size_t)GS_STAGES * GS_STAGE_BYTES;
+    const size_t ring = (size_t)GL_STAGES * GS_STAGE_BYTES;
     e = ensure_dynamic_smem(reinterpret_cast<const void*>(gn_loop_stream_kernel), ring, conf_c);
     if (e != cudaSuccess) return e;
     int gn_calls = 0;
@@ -2330,8 +2343,8 @@ cudaError_t launch_stream_solve(const SolveParams& prm_in, int n_pairs, const St
         int* q = sb.queue + (gn_calls++);
         cudaError_t err = cudaMemsetAsync(q, 0, sizeof(int), stream);
         if (err != cudaSuccess) return err;
-        const int grid = n_pairs < 2 * sb.sm_count ? n_pairs : 2 * sb.sm_count;
-        gn_loop_stream_kernel<<<grid, GS_THREADS, ring, stream>>>(prm.cam, prm.cfg, off_p, off_l, sb, n_pairs, max_iters, q,
+        const int grid = n_pairs < GL_MINBLOCKS * sb.sm_count ? n_pairs : GL_MINBLOCKS * sb.sm_count;
+        gn_loop_stream_kernel<<<grid, GL_THREADS, ring, stream>>>(prm.cam, prm.cfg, off_p, off_l, sb, n_pairs, max_iters, q,
                                                                   prm.feat_scratch, (size_t)prm.feat_scratch_stride, prm.cap_pt, prm.cap_ls);
         nl += 1;
         return cudaGetLastError();
