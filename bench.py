@@ -127,7 +127,8 @@ def make_workload(pairs: int, first_pair: int):
 
 
 class ClockSampler:
-    """Samples SM clock and throttle reasons DURING the timed region (pynvml, ~20 ms period)."""
+    """Samples SM clock and throttle reasons DURING the timed region (pynvml, ~4 ms period: a default run's timed region is
+    only ~65 ms long)."""
 
     def __init__(self, index: int):
         self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
@@ -164,7 +165,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.004)
 
     def __enter__(self):
         if self.ok:
